@@ -1,0 +1,300 @@
+// cal_core.cuh — per-thread building blocks of the CALITAS B200 engine (device code; also compiled for the host by the
+// test-only hostsim build, tests/hostsim/, so the logic can be checked without a GPU).
+//
+// Reference behaviour implemented here (files under calitas/src/main/scala/com/editasmedicine/aligner/):
+//   scorer              SequentialGuideAligner.scala:139-153, 192-208
+//   glocal DP+traceback fgbio 2.0.0 alignment.Aligner (Mode.Glocal) as called at SequentialGuideAligner.scala:261,278,295,299
+//   PAM extension       SequentialGuideAligner.scala:433-492
+//   record coordinates  SequentialGuideAligner.scala:263-310, 505-524; GuideAlignment.scala:21-31
+//   per-window filter   SequentialGuideAligner.scala:315-322; GuideAlignment.scala:119-129
+//   genome-wide sweep   SearchReference.scala:653-675; ReferenceHit.scala:135-144
+#pragma once
+#include <stdint.h>
+#include "../../include/calitas_b200.h"
+
+#if defined(__CUDACC__) && !defined(CAL_HOSTSIM)
+#define CAL_HD __host__ __device__ __forceinline__
+#define CAL_D __device__ __forceinline__
+#else
+#define CAL_HD inline
+#define CAL_D inline
+#endif
+
+namespace cal {
+
+// ---- target codes ------------------------------------------------------------------------------------------------
+// One 4-bit code per reference base: the IUPAC base set (A=1, C=2, G=4, T/U=8, ambiguity codes = unions), with two
+// specials: 15 = upper-case 'N' (never matches, SequentialGuideAligner.scala:144; trimmed from window ends,
+// SearchReference.scala:58-59) and 0 = 'n' or any non-IUPAC byte (never matches, not trimmed).
+enum { CODE_N = 15 };
+
+CAL_HD uint32_t iupac_set(uint8_t b) {
+  switch (b & 0xDF) {  // case-insensitive for letters
+    case 'A': return 1;  case 'C': return 2;  case 'G': return 4;  case 'T': return 8;  case 'U': return 8;
+    case 'M': return 3;  case 'R': return 5;  case 'W': return 9;  case 'S': return 6;  case 'Y': return 10; case 'K': return 12;
+    case 'V': return 7;  case 'H': return 11; case 'D': return 13; case 'B': return 14; case 'N': return 15;
+    default:  return 0;
+  }
+}
+CAL_HD uint32_t target_code(uint8_t b) {
+  if (b == 'N') return CODE_N;
+  uint32_t s = iupac_set(b);          // 0 for any non-IUPAC byte
+  return s == 15 ? 0u : s;            // 'n'
+}
+// complement of a base set: A<->T, C<->G = reverse the 4 bits; 0 and 15 map to themselves
+CAL_HD uint32_t comp_code(uint32_t c) { return ((c & 1) << 3) | ((c & 2) << 1) | ((c & 4) >> 1) | ((c & 8) >> 3); }
+// does a query base set pair with a target code?  (scorePairing: N never matches)
+CAL_HD bool pairs(uint32_t qset, uint32_t tcode) { return tcode != CODE_N && (qset & tcode) != 0; }
+
+// ---- scores (SequentialGuideAligner.scala:192-208, 213) ---------------------------------------------------------
+struct Scores {
+  int32_t match, mismatch, pam_match, pam_mismatch, query_gap /* cigar D */, target_gap /* cigar I */, worst_guide_diff;
+  int32_t abs_mm, abs_genome_gap, abs_guide_gap;
+};
+CAL_HD int32_t iabs(int32_t v) { return v < 0 ? -v : v; }
+CAL_HD Scores make_scores(const calitas_costs& c) {
+  Scores s;
+  s.abs_mm = iabs(c.mismatch_net_cost); s.abs_genome_gap = iabs(c.genome_gap_net_cost); s.abs_guide_gap = iabs(c.guide_gap_net_cost);
+  s.match = s.abs_mm / 2;
+  s.mismatch = -(s.abs_mm - s.match);
+  s.query_gap = -s.abs_guide_gap;
+  s.target_gap = -s.abs_genome_gap + s.match;
+  s.pam_match = iabs(c.pam_mismatch_net_cost) / 2;
+  s.pam_mismatch = -(iabs(c.pam_mismatch_net_cost) - s.pam_match);
+  int32_t w = -s.abs_mm; if (-s.abs_genome_gap < w) w = -s.abs_genome_gap; if (-s.abs_guide_gap < w) w = -s.abs_guide_gap;
+  s.worst_guide_diff = w;
+  return s;
+}
+
+// ---- per-guide device descriptor ------------------------------------------------------------------------------------
+// The DP always runs with the PAM on the right (SequentialGuideAligner.scala:255-259): `q` is the protospacer for a
+// 3' PAM and its reverse complement for a 5' PAM; `pam` likewise.  dir 0 scans the target as given, dir 1 scans its
+// reverse complement; strand = (dir ^ five_prime) ? '-' : '+'.
+struct GuideSpec {
+  uint32_t peq[2][16];                       // Myers match masks per scan direction and target code, top-aligned (row i = bit 32-lp+i), low bits all 1
+  uint8_t  q[CALITAS_MAX_PROTOSPACER];       // base set per DP-query row
+  uint8_t  pam[CALITAS_MAX_PAMS][CALITAS_MAX_PAM_LEN];
+  uint8_t  pam_len[CALITAS_MAX_PAMS];
+  int32_t  lp, n_pams, five_prime;
+  int32_t  d, p, g;                          // maxGuideDiffs, maxPamDiffs, maxGapsBetweenGuideAndPam
+  int32_t  max_tot_filter;                   // d + g + p (SequentialGuideAligner.scala:249)
+  int32_t  max_total_diffs, max_overlap;     // post filter (:317)
+  int32_t  min_score;                        // :239-243
+  int32_t  k_edits;                          // candidate threshold of the bit-parallel scan: unit edits <= k_edits is necessary for score >= min_score
+  int32_t  span;                             // max target columns any co-optimal alignment of an accepted end column can cover
+  int32_t  slots;                            // alignment slots per candidate end column = max(1, n_pams)
+};
+
+// ---- bit-parallel candidate scan (Myers/Hyyro, semi-global: free target start) ----------------------------------------
+// State of one (window, direction, guide) scan.  Column update for target code `eq` = peq[dir][code].
+struct MyersState { uint32_t pv, mv; int32_t score; };
+CAL_HD void myers_init(MyersState& s, int lp) {
+  s.pv = lp >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> lp);   // D[i][0] = i : leading insertions at the window's left edge
+  s.mv = 0; s.score = lp;
+}
+CAL_HD void myers_step(MyersState& s, uint32_t eq) {
+  uint32_t xv = eq | s.mv;
+  uint32_t xh = (((eq & s.pv) + s.pv) ^ s.pv) | eq;
+  uint32_t ph = s.mv | ~(xh | s.pv);
+  uint32_t mh = s.pv & xh;
+  s.score += (int32_t)(ph >> 31) - (int32_t)(mh >> 31);
+  ph <<= 1; mh <<= 1;
+  s.pv = mh | ~(xv | ph);
+  s.mv = ph & xv;
+}
+
+// ---- banded glocal DP with traceback for one candidate end column ------------------------------------------------------
+enum { OP_EQ = 0, OP_X = 1, OP_I = 2, OP_D = 3 };
+enum { TR_LEFT = 0, TR_UP = 1, TR_DIAG = 2, TR_DONE = 3 };
+const int32_t NEG_SCORE = -(1 << 28);
+const int MAX_SPAN = 2 * CALITAS_MAX_PROTOSPACER + 2;     // columns of the DP rectangle
+const int MAX_GUIDE_OPS = CALITAS_MAX_PROTOSPACER + MAX_SPAN;
+
+struct GuideAln {          // one fgbio `Alignment` of the protospacer, in DP orientation
+  int32_t score;
+  int32_t t_start;         // 1-based first target column (targetStart)
+  int32_t t_end;           // 1-based last target column (targetEnd) == the candidate end column
+  int32_t n_ops;
+  int32_t diffs;           // non-'=' columns (SequentialGuideAligner.scala:442)
+  int32_t terminal_gap;    // length of a trailing I or D run (:452)
+  int32_t terminal_d;      // length of a trailing D run (columns after the last guide base)
+  uint8_t ops[MAX_GUIDE_OPS];   // in DP orientation, first column first
+};
+
+// Target accessor: code of DP column p (1-based) of the scanned target, already complemented for dir 1.
+// `Fetch` is a functor: uint32_t operator()(int p).
+template <class Fetch>
+CAL_HD bool band_align(const GuideSpec& g, const Scores& sc, Fetch fetch, int32_t j, GuideAln& out, uint8_t* trace /* (lp+1)*(MAX_SPAN+1) */) {
+  const int n = g.lp;
+  const int jlo = j - g.span > 0 ? j - g.span : 0;
+  const int width = j - jlo;                         // local columns 0..width
+  const int W = MAX_SPAN + 1;
+  int32_t pd[MAX_SPAN + 1], pl[MAX_SPAN + 1], pu[MAX_SPAN + 1];   // previous row
+  int32_t cd[MAX_SPAN + 1], cl[MAX_SPAN + 1], cu[MAX_SPAN + 1];   // current row
+  uint8_t tc[MAX_SPAN + 1];
+  for (int c = 1; c <= width; ++c) { uint32_t t = fetch(jlo + c); tc[c] = (uint8_t)t; }
+  for (int c = 0; c <= width; ++c) { pd[c] = 0; pl[c] = 0; pu[c] = 0; }      // row 0: free leading target
+  const int32_t gI = sc.target_gap, gD = sc.query_gap;
+  for (int i = 1; i <= n; ++i) {
+    const uint32_t qs = g.q[i - 1];
+    cd[0] = NEG_SCORE; cl[0] = NEG_SCORE; cu[0] = pu[0] + gI;                // column 0: leading insertions only
+    trace[i * W] = (uint8_t)((i == 1 ? TR_DIAG : TR_UP) << 2);
+    for (int c = 1; c <= width; ++c) {
+      uint32_t tr;
+      {   // Diagonal cell: predecessor Diagonal > Left > Up on ties
+        int32_t add = pairs(qs, tc[c]) ? sc.match : sc.mismatch;
+        int32_t d = pd[c - 1], l = pl[c - 1], u = pu[c - 1];
+        if (d >= l && d >= u) { cd[c] = d + add; tr = TR_DIAG; } else if (l >= u) { cd[c] = l + add; tr = TR_LEFT; } else { cd[c] = u + add; tr = TR_UP; }
+      }
+      {   // Up cell (cigar I): from Diagonal or Up
+        int32_t d = pd[c] + gI, u = pu[c] + gI;
+        if (d >= u) { cu[c] = d; tr |= TR_DIAG << 2; } else { cu[c] = u; tr |= TR_UP << 2; }
+      }
+      {   // Left cell (cigar D): from Diagonal, Left or Up
+        int32_t d = cd[c - 1] + gD, l = cl[c - 1] + gD, u = cu[c - 1] + gD;
+        if (d >= l && d >= u) { cl[c] = d; tr |= TR_DIAG << 4; } else if (l >= u) { cl[c] = l; tr |= TR_LEFT << 4; } else { cl[c] = u; tr |= TR_UP << 4; }
+      }
+      trace[i * W + c] = (uint8_t)tr;
+    }
+    for (int c = 0; c <= width; ++c) { pd[c] = cd[c]; pl[c] = cl[c]; pu[c] = cu[c]; }
+  }
+  int32_t best = pd[width]; int dir = TR_DIAG;
+  if (pl[width] > best) { best = pl[width]; dir = TR_LEFT; }
+  if (pu[width] > best) { best = pu[width]; dir = TR_UP; }
+  if (best < g.min_score) return false;
+  // traceback
+  int ci = n, cc = width, cdir = dir, nrev = 0;
+  uint8_t rev[MAX_GUIDE_OPS];
+  for (;;) {
+    int next;
+    if (ci == 0) next = TR_DONE;
+    else { uint32_t t = trace[ci * W + cc]; next = cdir == TR_DIAG ? (t & 3) : (cdir == TR_UP ? ((t >> 2) & 3) : ((t >> 4) & 3)); }
+    if (next == TR_DONE) break;
+    if (cdir == TR_DIAG) { rev[nrev++] = pairs(g.q[ci - 1], tc[cc]) ? OP_EQ : OP_X; --ci; --cc; }
+    else if (cdir == TR_LEFT) { rev[nrev++] = OP_D; --cc; }
+    else { rev[nrev++] = OP_I; --ci; }
+    cdir = next;
+  }
+  out.score = best; out.t_start = jlo + cc + 1; out.t_end = j; out.n_ops = nrev; out.diffs = 0;
+  for (int k = 0; k < nrev; ++k) { uint8_t o = rev[nrev - 1 - k]; out.ops[k] = o; if (o != OP_EQ) ++out.diffs; }
+  out.terminal_gap = 0; out.terminal_d = 0;
+  if (nrev > 0 && out.ops[nrev - 1] >= OP_I) {
+    uint8_t o = out.ops[nrev - 1]; int k = nrev; while (k > 0 && out.ops[k - 1] == o) { --k; ++out.terminal_gap; }
+    if (o == OP_D) out.terminal_d = out.terminal_gap;
+  }
+  return true;
+}
+
+// ---- 2-bit op packing ------------------------------------------------------------------------------------------------------
+CAL_HD void ops_set(uint32_t* words, int idx, uint32_t op) { words[idx >> 4] |= op << ((idx & 15) * 2); }
+CAL_HD uint32_t ops_get(const uint32_t* words, int idx) { return (words[idx >> 4] >> ((idx & 15) * 2)) & 3u; }
+
+// ---- PAM extension + record (SequentialGuideAligner.scala:433-492, 505-524, 263-310) ---------------------------------------
+// Window geometry in contig (or task) coordinates: the scanned target is bases [w_begin, w_end) (dir 1: reverse complemented).
+struct WindowGeom { int32_t w_begin, w_end; };
+
+template <class Fetch>
+CAL_HD bool extend_pam(const GuideSpec& g, const Scores& sc, Fetch fetch, int32_t m /* scanned target length */, const GuideAln& a, int pam_idx,
+                       int32_t& best_score, int32_t& best_offset, uint32_t& best_xmask) {
+  const int pam_len = g.pam_len[pam_idx];
+  int max_extra = g.g - a.terminal_gap; int alt = g.max_tot_filter - a.diffs; if (alt < max_extra) max_extra = alt;
+  bool have = false;
+  for (int offset = 0; offset <= max_extra; ++offset) {
+    int t_off = a.t_end + offset;                                  // 0-based offset of the first PAM base in the scanned target
+    int limit = g.p; int l2 = g.max_tot_filter - a.diffs - offset; if (l2 < limit) limit = l2;
+    if (t_off + pam_len > m || limit < 0) continue;
+    int32_t score = 0; int nx = 0; uint32_t xmask = 0;
+    for (int i = 0; i < pam_len; ++i) {
+      int32_t add = pairs(g.pam[pam_idx][i], fetch(t_off + i + 1)) ? sc.pam_match : sc.pam_mismatch;
+      score += add;
+      if (!(add > 0)) { ++nx; xmask |= 1u << i; }                  // op '=' iff addend > 0 (:468)
+    }
+    if (nx > limit) continue;
+    int32_t total = a.score + score + offset * sc.query_gap;
+    if (!have || total > best_score) { have = true; best_score = total; best_offset = offset; best_xmask = xmask; }   // maxBy keeps the first maximum
+  }
+  return have;
+}
+
+// Builds the hit for guide alignment `a` extended with PAM `pam_idx` (or PAM-less when pam_idx < 0).
+CAL_HD void make_hit(const GuideSpec& g, const GuideAln& a, int pam_idx, int32_t score, int32_t offset, uint32_t xmask, int dir,
+                     const WindowGeom& w, int32_t guide_idx, int32_t contig_idx, int32_t task_idx, calitas_hit& h) {
+  const int pam_len = pam_idx >= 0 ? g.pam_len[pam_idx] : 0;
+  const int n_ops = a.n_ops + (pam_idx >= 0 ? offset + pam_len : 0);
+  h.guide_idx = guide_idx; h.pam_idx = pam_idx; h.contig_idx = contig_idx; h.task_idx = task_idx; h.score = score;
+  for (int k = 0; k < CALITAS_MAX_OPS / 16; ++k) h.ops[k] = 0;
+  int gaps = 0, edits = 0;
+  // ops in guide orientation: DP orientation for a 3' PAM, reversed for a 5' PAM (Cigar.reverse, :267,284)
+  for (int k = 0; k < n_ops; ++k) {
+    uint32_t op;
+    if (k < a.n_ops) op = a.ops[k];
+    else if (k < a.n_ops + offset) op = OP_D;
+    else op = ((xmask >> (k - a.n_ops - offset)) & 1u) ? OP_X : OP_EQ;
+    if (op >= OP_I) ++gaps;
+    if (op != OP_EQ) ++edits;
+    ops_set(h.ops, g.five_prime ? n_ops - 1 - k : k, op);
+  }
+  h.n_ops = (uint8_t)n_ops; h.gap_bases = (uint8_t)gaps; h.edits = (uint8_t)edits;
+  // coordinates in the scanned target (toGuideAlignment with strand '+', GuideAlignment.scala:21-31): leftDelta is always 0 because
+  // a glocal alignment starts on a guide base; rightDelta = trailing D run + guide-PAM gap + PAM.
+  const int32_t s0 = a.t_start - 1;
+  const int32_t e0 = a.t_end + (pam_idx >= 0 ? offset + pam_len : 0);
+  const int32_t gs0 = s0;
+  const int32_t ge0 = e0 - (a.terminal_d + (pam_idx >= 0 ? offset + pam_len : 0));
+  if (dir == 0) {
+    h.start_offset = w.w_begin + s0; h.end_offset = w.w_begin + e0; h.guide_start_offset = w.w_begin + gs0; h.guide_end_offset = w.w_begin + ge0;
+  } else {   // flip about the window (:271-274, 305-308)
+    h.start_offset = w.w_end - e0; h.end_offset = w.w_end - s0; h.guide_start_offset = w.w_end - ge0; h.guide_end_offset = w.w_end - gs0;
+  }
+  h.strand = (uint8_t)((dir ^ g.five_prime) ? '-' : '+');
+}
+
+// ---- per-window canonicalisation (SequentialGuideAligner.scala:315-322) ---------------------------------------------------
+// `hits[0..n)` are the alignments of one (guide, window, strand) in emission order (end column, then PAM index); `valid[i]` marks
+// filled slots.  On return rank[i] >= 0 is the position of a kept alignment in the reference's retval for this strand, -1 = dropped.
+CAL_HD int canon_group(const calitas_hit* hits, const uint8_t* valid, int32_t* rank, int n, int32_t max_total_diffs, int32_t max_overlap) {
+  // rank doubles as state: -2 = not yet visited, -1 = dropped, >= 0 kept
+  for (int i = 0; i < n; ++i) rank[i] = valid[i] ? -2 : -1;
+  int kept = 0;
+  for (;;) {
+    int b = -1;    // next in stable (score desc, gapBases asc) order
+    for (int i = 0; i < n; ++i) {
+      if (rank[i] != -2) continue;
+      if (b < 0 || hits[i].score > hits[b].score || (hits[i].score == hits[b].score && hits[i].gap_bases < hits[b].gap_bases)) b = i;
+    }
+    if (b < 0) break;
+    bool keep = hits[b].edits <= max_total_diffs;
+    if (keep) {
+      for (int i = 0; i < n && keep; ++i) {
+        if (rank[i] < 0) continue;
+        int32_t lo = hits[i].start_offset > hits[b].start_offset ? hits[i].start_offset : hits[b].start_offset;
+        int32_t hi = hits[i].end_offset < hits[b].end_offset ? hits[i].end_offset : hits[b].end_offset;
+        int32_t ov = hi - lo; if (ov < 0) ov = 0;
+        if (ov > max_overlap) keep = false;
+      }
+    }
+    rank[b] = keep ? kept++ : -1;
+  }
+  return kept;
+}
+
+// ---- genome-wide sweep (SearchReference.scala:653-675) --------------------------------------------------------------------------
+// ReferenceHit.end (ReferenceHit.scala:135-138): coordinate_start + cigar.lengthOnTarget - 1, with coordinate_start the guide-only start.
+CAL_HD int32_t hit_sweep_end(const calitas_hit& h) { return h.guide_start_offset + (h.end_offset - h.start_offset) - 1; }
+CAL_HD int32_t hit_sweep_overlap(const calitas_hit& a, const calitas_hit& b) {
+  int32_t ea = hit_sweep_end(a), eb = hit_sweep_end(b);
+  int32_t hi = ea < eb ? ea : eb, lo = a.guide_start_offset > b.guide_start_offset ? a.guide_start_offset : b.guide_start_offset;
+  int32_t o = hi - lo; return o > 0 ? o : 0;
+}
+// hits[idx[0..n)] is one (guide, contig, strand) group sorted by (coordinate_start, -score, arrival); keep[i] set for keepers.
+CAL_HD void sweep_group(const calitas_hit* hits, const uint32_t* idx, uint8_t* keep, int64_t n, int32_t max_overlap) {
+  int64_t i = 0;
+  while (i < n) {
+    const calitas_hit& hit = hits[idx[i]];
+    int64_t cur = i++;
+    while (i < n && hit_sweep_overlap(hits[idx[i]], hit) >= max_overlap && hits[idx[i]].score <= hit.score) { keep[i] = 0; ++i; }
+    keep[cur] = (i >= n || hit_sweep_overlap(hits[idx[i]], hit) < max_overlap) ? 1 : 0;
+  }
+}
+
+}  // namespace cal

@@ -1,0 +1,844 @@
+// cal_engine.cu — kernels, engine orchestration and the C ABI of include/calitas_b200.h.
+//
+// Data path of one SearchReference batch (SearchReference.scala:527-564, 641-648) on one GPU:
+//   k_scan_tiled   every owned reference window x both strands x every guide of the chunk: bit-parallel semi-global edit
+//                  distance of the protospacer (one 32-bit word per scan, tile of 64 windows staged in shared memory);
+//                  emits the candidate end columns (a lossless superset of fgbio's `score >= minScore` columns)
+//   sort           candidate keys (guide, window, strand, end column) -> fgbio's emission order
+//   k_align        per candidate: exact 3-matrix glocal DP on the band that can hold a co-optimal alignment, traceback with
+//                  the oracle's tie-breaks, PAM extension, hit record
+//   k_canon        per (guide, window, strand): the reference's sort + greedy overlap filter
+//   dedup          removeOverlaps + ReferenceHit.sort: radix sorts + per-(guide, contig, strand) sweep
+// AlignToReference / variant windows use k_scan_explicit (one thread per window and strand) and the same tail.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cal_dev.h"
+#include "cal_core.cuh"
+#include "cal_host.h"
+
+namespace cal {
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// device-side descriptors
+// ------------------------------------------------------------------------------------------------------------------------------------
+struct ContigDev { int64_t len; int64_t nib_base; /* nibble index of contig base 0 */ int64_t win_base; /* global index of window 0 */ };
+struct Tile { int32_t contig; int32_t nwin; int64_t first_k; };
+struct ExplicitWindow { int64_t nib_start; int32_t len; int32_t target_offset; int32_t guide_idx; int32_t contig_idx; };
+
+const int TILE_WINDOWS = 64;
+const int SCAN_THREADS = 2 * TILE_WINDOWS;
+const int KEY_COL_BITS = 17, KEY_WIN_SHIFT = 18, KEY_GUIDE_SHIFT = 50;
+const uint32_t MAX_WINDOW_LEN = (1u << KEY_COL_BITS) - 1;
+const int MAX_GUIDES_PER_CALL = 1 << 14;
+
+CAL_HD uint64_t make_key(uint32_t guide, uint32_t window, uint32_t strandbit, uint32_t col) {
+  return ((uint64_t)guide << KEY_GUIDE_SHIFT) | ((uint64_t)window << KEY_WIN_SHIFT) | ((uint64_t)strandbit << KEY_COL_BITS) | col;
+}
+CAL_HD uint32_t nibble_at(const uint32_t* words, int64_t idx) { return (words[idx >> 3] >> ((uint32_t)(idx & 7) * 4)) & 15u; }
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// k_pack: raw bytes -> 4-bit target codes.  Streaming, HBM-bound: 1 B read + 0.5 B written per base.
+// ------------------------------------------------------------------------------------------------------------------------------------
+CAL_KERNEL __launch_bounds__(256) k_pack(const uint8_t* __restrict__ raw, uint32_t* __restrict__ nib, int64_t n_words) {
+  CAL_SHARED_DYN(uint8_t, lut);
+  CAL_PHASE(0) { for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (uint8_t)target_code((uint8_t)i); }
+  __syncthreads();
+  CAL_PHASE(1) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+      const uint64_t v = reinterpret_cast<const uint64_t*>(raw)[w];
+      uint32_t out = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out |= (uint32_t)lut[(v >> (8 * k)) & 0xFF] << (4 * k);
+      nib[w] = out;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// k_scan_tiled: the hot kernel
+// ------------------------------------------------------------------------------------------------------------------------------------
+struct ScanArgs {
+  const uint32_t* nib; const ContigDev* contigs; const Tile* tiles; const GuideSpec* specs;
+  int32_t g_begin, g_end, window_size, step, min_len;
+  uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap;
+};
+
+struct Emitter {
+  uint64_t* cand; unsigned long long* count; unsigned long long cap; uint64_t key_base;
+  CAL_D void operator()(int32_t col) const {
+    unsigned long long i = atomicAdd(count, 1ull);
+    if (i < cap) cand[i] = key_base | (uint32_t)col;
+  }
+};
+
+// Scans relative nibble range [rs, re) of a word array, forwards (dir 0) or backwards (dir 1; `peq` then holds the
+// complemented masks); column p = 1.. in scan order.
+template <class Emit>
+CAL_D void scan_range(const uint32_t* words, int32_t rs, int32_t re, int dir, const uint32_t* peq, int lp, int k_edits, const Emit& emit) {
+  MyersState st; myers_init(st, lp);
+  if (dir == 0) {
+    int32_t r = rs;
+    for (; r < re && (r & 7); ++r) { myers_step(st, peq[nibble_at(words, r)]); if (st.score <= k_edits) emit(r - rs + 1); }
+    for (; r + 8 <= re; r += 8) {
+      const uint32_t w = words[r >> 3];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { myers_step(st, peq[(w >> (4 * k)) & 15u]); if (st.score <= k_edits) emit(r + k - rs + 1); }
+    }
+    for (; r < re; ++r) { myers_step(st, peq[nibble_at(words, r)]); if (st.score <= k_edits) emit(r - rs + 1); }
+  } else {
+    int32_t r = re - 1;
+    for (; r >= rs && (r & 7) != 7; --r) { myers_step(st, peq[nibble_at(words, r)]); if (st.score <= k_edits) emit(re - r); }
+    for (; r - 7 >= rs; r -= 8) {
+      const uint32_t w = words[r >> 3];
+#pragma unroll
+      for (int k = 7; k >= 0; --k) { myers_step(st, peq[(w >> (4 * k)) & 15u]); if (st.score <= k_edits) emit(re - (r - 7 + k)); }
+    }
+    for (; r >= rs; --r) { myers_step(st, peq[nibble_at(words, r)]); if (st.score <= k_edits) emit(re - r); }
+  }
+}
+
+CAL_KERNEL __launch_bounds__(SCAN_THREADS) k_scan_tiled(ScanArgs a) {
+  CAL_SHARED_DYN(uint32_t, smem);
+  const int ng = a.g_end - a.g_begin;
+  uint32_t* s_peq = smem;                       // ng * 32 words
+  int32_t* s_meta = (int32_t*)(smem + ng * 32); // ng * 4: lp, k_edits, five_prime, pad
+  uint32_t* s_tile = smem + ng * 36;
+  const Tile tile = a.tiles[blockIdx.x];
+  const ContigDev ctg = a.contigs[tile.contig];
+  const int64_t tile_start = tile.first_k * (int64_t)a.step;
+  int64_t tile_end = (tile.first_k + tile.nwin - 1) * (int64_t)a.step + a.window_size; if (tile_end > ctg.len) tile_end = ctg.len;
+  const int64_t nib0 = ctg.nib_base + tile_start;
+  const int64_t word0 = nib0 >> 3;
+  const int32_t n_words = (int32_t)(((ctg.nib_base + tile_end + 7) >> 3) - word0);
+  CAL_PHASE(0) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) s_tile[i] = __ldg(a.nib + word0 + i);
+    for (int i = threadIdx.x; i < ng * 32; i += blockDim.x) s_peq[i] = a.specs[a.g_begin + (i >> 5)].peq[(i >> 4) & 1][i & 15];
+    for (int i = threadIdx.x; i < ng; i += blockDim.x) {
+      const GuideSpec& s = a.specs[a.g_begin + i];
+      s_meta[4 * i] = s.lp; s_meta[4 * i + 1] = s.k_edits; s_meta[4 * i + 2] = s.five_prime; s_meta[4 * i + 3] = 0;
+    }
+  }
+  __syncthreads();
+  CAL_PHASE(1) {
+    const int kk = threadIdx.x % TILE_WINDOWS, dir = threadIdx.x / TILE_WINDOWS;
+    if (kk >= tile.nwin) return;
+    const int64_t ws = (tile.first_k + kk) * (int64_t)a.step;
+    int64_t we = ws + a.window_size; if (we > ctg.len) we = ctg.len;
+    const int32_t r_off = (int32_t)(nib0 & 7);
+    int32_t rs = r_off + (int32_t)(ws - tile_start), re = r_off + (int32_t)(we - tile_start);
+    while (rs < re && nibble_at(s_tile, rs) == CODE_N) ++rs;         // SearchReference.scala:58-59
+    while (rs < re && nibble_at(s_tile, re - 1) == CODE_N) --re;
+    const int32_t m = re - rs;
+    if (m <= 0 || m < a.min_len) return;                              // SearchReference.scala:536
+    const uint32_t wid = (uint32_t)(ctg.win_base + tile.first_k + kk);
+    for (int g = 0; g < ng; ++g) {
+      const int lp = s_meta[4 * g], k_edits = s_meta[4 * g + 1], five = s_meta[4 * g + 2];
+      Emitter emit{ a.cand, a.cand_count, a.cand_cap, make_key((uint32_t)(a.g_begin + g), wid, (uint32_t)(dir ^ five), 0) };
+      scan_range(s_tile, rs, re, dir, s_peq + g * 32 + dir * 16, lp, k_edits, emit);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// k_scan_explicit: one thread per (window, direction); windows are short (AlignToReference regions, variant windows)
+// ------------------------------------------------------------------------------------------------------------------------------------
+struct ScanExplicitArgs {
+  const uint32_t* nib; const ExplicitWindow* windows; int64_t n_windows; const GuideSpec* specs;
+  uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap;
+};
+struct GlobalWords {   // word accessor over global memory with nibble base offset
+  const uint32_t* nib; int64_t base;
+  CAL_D uint32_t operator[](int32_t w) const { return __ldg(nib + base + w); }
+};
+template <class Words, class Emit>
+CAL_D void scan_range_generic(const Words& words, int32_t rs, int32_t re, int dir, const uint32_t* peq, int lp, int k_edits, const Emit& emit) {
+  MyersState st; myers_init(st, lp);
+  if (dir == 0) { for (int32_t r = rs; r < re; ++r) { uint32_t c = (words[r >> 3] >> ((r & 7) * 4)) & 15u; myers_step(st, peq[c]); if (st.score <= k_edits) emit(r - rs + 1); } }
+  else { for (int32_t r = re - 1; r >= rs; --r) { uint32_t c = (words[r >> 3] >> ((r & 7) * 4)) & 15u; myers_step(st, peq[c]); if (st.score <= k_edits) emit(re - r); } }
+}
+CAL_KERNEL __launch_bounds__(128) k_scan_explicit(ScanExplicitArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * a.n_windows) return;
+  const int dir = t >= a.n_windows ? 1 : 0;
+  const int64_t w = dir ? t - a.n_windows : t;
+  const ExplicitWindow ew = a.windows[w];
+  if (ew.len <= 0) return;
+  const GuideSpec& s = a.specs[ew.guide_idx];
+  GlobalWords words{ a.nib, ew.nib_start >> 3 };
+  const int32_t rs = (int32_t)(ew.nib_start & 7), re = rs + ew.len;
+  Emitter emit{ a.cand, a.cand_count, a.cand_cap, make_key(0, (uint32_t)w, (uint32_t)(dir ^ s.five_prime), 0) };
+  scan_range_generic(words, rs, re, dir, s.peq[dir], s.lp, s.k_edits, emit);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// k_align: candidate -> exact DP + traceback + PAM extension -> hit slots
+// ------------------------------------------------------------------------------------------------------------------------------------
+struct AlignArgs {
+  const uint64_t* cand; int64_t n_cand; const GuideSpec* specs; Scores sc; int32_t slots;
+  int32_t explicit_mode;
+  const uint32_t* nib;
+  const ContigDev* contigs; int32_t n_contigs; int32_t window_size, step;     // tiled
+  const ExplicitWindow* windows; int32_t task_base;                          // explicit (window ids are relative to task_base)
+  calitas_hit* hits; uint8_t* valid;
+};
+struct NibFetch {
+  const uint32_t* nib; int64_t first; int32_t m; int dir;
+  CAL_D uint32_t operator()(int32_t p) const {       // DP column p (1-based) of the scanned target
+    const int64_t idx = first + (dir == 0 ? p - 1 : m - p);
+    const uint32_t c = (__ldg(nib + (idx >> 3)) >> ((uint32_t)(idx & 7) * 4)) & 15u;
+    return dir == 0 ? c : comp_code(c);
+  }
+};
+// window id -> contig, trimmed [begin, end) in contig coordinates (tiled mode)
+CAL_D void locate_window(const uint32_t* nib, const ContigDev* contigs, int32_t n_contigs, int32_t window_size, int32_t step, uint32_t wid,
+                         int32_t& contig, int64_t& wb, int64_t& we) {
+  int lo = 0, hi = n_contigs - 1;
+  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (contigs[mid].win_base <= (int64_t)wid) lo = mid; else hi = mid - 1; }
+  contig = lo;
+  const ContigDev c = contigs[lo];
+  wb = ((int64_t)wid - c.win_base) * step; we = wb + window_size; if (we > c.len) we = c.len;
+  while (wb < we && nibble_at(nib, c.nib_base + wb) == CODE_N) ++wb;
+  while (wb < we && nibble_at(nib, c.nib_base + we - 1) == CODE_N) --we;
+}
+CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_cand) return;
+  const uint64_t key = a.cand[i];
+  const int32_t col = (int32_t)(key & MAX_WINDOW_LEN);
+  const uint32_t strandbit = (uint32_t)(key >> KEY_COL_BITS) & 1u, wid = (uint32_t)(key >> KEY_WIN_SHIFT);
+  int32_t gidx = (int32_t)(key >> KEY_GUIDE_SHIFT), contig_idx; WindowGeom geom; int64_t first;
+  if (a.explicit_mode) {
+    const ExplicitWindow ew = a.windows[wid];
+    gidx = ew.guide_idx; contig_idx = ew.contig_idx; geom.w_begin = ew.target_offset; geom.w_end = ew.target_offset + ew.len; first = ew.nib_start;
+  } else {
+    int64_t wb, we; locate_window(a.nib, a.contigs, a.n_contigs, a.window_size, a.step, wid, contig_idx, wb, we);
+    geom.w_begin = (int32_t)wb; geom.w_end = (int32_t)we; first = a.contigs[contig_idx].nib_base + wb;
+  }
+  const GuideSpec& g = a.specs[gidx];
+  const int dir = (int)(strandbit ^ (uint32_t)g.five_prime);
+  const int32_t m = geom.w_end - geom.w_begin;
+  const NibFetch fetch{ a.nib, first, m, dir };
+  const int64_t base = i * a.slots;
+  for (int s = 0; s < a.slots; ++s) a.valid[base + s] = 0;
+  GuideAln aln;
+  uint8_t trace[(CALITAS_MAX_PROTOSPACER + 1) * (MAX_SPAN + 1)];
+  if (!band_align(g, a.sc, fetch, col, aln, trace)) return;
+  if (aln.diffs > g.d) return;                                   // SequentialGuideAligner.scala:447,450
+  if (g.n_pams == 0) {
+    make_hit(g, aln, -1, aln.score, 0, 0u, dir, geom, gidx, contig_idx, (int32_t)wid + a.task_base, a.hits[base]); a.valid[base] = 1;
+  } else {
+    for (int pi = 0; pi < g.n_pams; ++pi) {
+      int32_t score = 0, offset = 0; uint32_t xmask = 0;
+      if (extend_pam(g, a.sc, fetch, m, aln, pi, score, offset, xmask)) {
+        make_hit(g, aln, pi, score, offset, xmask, dir, geom, gidx, contig_idx, (int32_t)wid + a.task_base, a.hits[base + pi]); a.valid[base + pi] = 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// k_canon: per (guide, window, strand) group — SequentialGuideAligner.scala:315-322
+// ------------------------------------------------------------------------------------------------------------------------------------
+struct CanonArgs {
+  const uint64_t* cand; int64_t n_cand; const GuideSpec* specs; int32_t slots; int32_t explicit_mode; const ExplicitWindow* windows;
+  const calitas_hit* hits; const uint8_t* valid; int32_t* rank; uint32_t* perm; uint32_t* flag;
+};
+CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_cand) return;
+  const uint64_t grp = a.cand[i] >> KEY_COL_BITS;
+  if (i > 0 && (a.cand[i - 1] >> KEY_COL_BITS) == grp) return;
+  int64_t j = i + 1; while (j < a.n_cand && (a.cand[j] >> KEY_COL_BITS) == grp) ++j;
+  const int64_t base = i * a.slots; const int n = (int)((j - i) * a.slots);
+  const int32_t gidx = a.explicit_mode ? a.windows[(uint32_t)(a.cand[i] >> KEY_WIN_SHIFT)].guide_idx : (int32_t)(a.cand[i] >> KEY_GUIDE_SHIFT);
+  const GuideSpec& g = a.specs[gidx];
+  const int kept = canon_group(a.hits + base, a.valid + base, a.rank + base, n, g.max_total_diffs, g.max_overlap);
+  for (int k = 0; k < n; ++k) a.flag[base + k] = k < kept ? 1u : 0u;
+  for (int k = 0; k < n; ++k) { const int32_t r = a.rank[base + k]; if (r >= 0) a.perm[base + r] = (uint32_t)(base + k); }
+}
+// out[pos[s]] = hits[perm[s]] for flagged slots
+CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const calitas_hit* hits, const uint32_t* perm, const uint32_t* flag, const uint32_t* pos, int64_t n, calitas_hit* out) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n || !flag[s]) return;
+  out[pos[s]] = hits[perm[s]];
+}
+CAL_KERNEL __launch_bounds__(256) k_gather(const calitas_hit* hits, const uint32_t* idx, int64_t n, calitas_hit* out) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) out[s] = hits[idx[s]];
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// dedup: removeOverlaps (SearchReference.scala:653-675) + ReferenceHit.sort (ReferenceHit.scala:276-287)
+// ------------------------------------------------------------------------------------------------------------------------------------
+// key1 = guide | contig | strand | coordinate_start ; keyA = -score (biased).  Arrival order is the array index.
+CAL_KERNEL __launch_bounds__(256) k_dedup_keys(const calitas_hit* hits, int64_t n, uint64_t* key1, uint64_t* keyA, uint32_t* idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const calitas_hit& h = hits[i];
+  key1[i] = ((uint64_t)(uint32_t)h.guide_idx << KEY_GUIDE_SHIFT) | ((uint64_t)((uint32_t)h.contig_idx & 0x3FFFFu) << 32) | ((uint64_t)(h.strand == '-' ? 1u : 0u) << 31) |
+            ((uint32_t)h.guide_start_offset & 0x7FFFFFFFu);
+  keyA[i] = (uint64_t)(uint32_t)(0x7FFFFFFF - h.score);
+  idx[i] = (uint32_t)i;
+}
+CAL_KERNEL __launch_bounds__(256) k_gather_u64(const uint64_t* in, const uint32_t* idx, int64_t n, uint64_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+CAL_KERNEL __launch_bounds__(256) k_sweep_prepare(const calitas_hit* hits, const uint32_t* idx, int64_t n, int32_t* s_start, int32_t* s_end, int32_t* s_score) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const calitas_hit& h = hits[idx[i]];
+  s_start[i] = h.guide_start_offset; s_end[i] = hit_sweep_end(h); s_score[i] = h.score;
+}
+CAL_HD int32_t soa_overlap(const int32_t* s_start, const int32_t* s_end, int64_t a, int64_t b) {
+  const int32_t hi = s_end[a] < s_end[b] ? s_end[a] : s_end[b], lo = s_start[a] > s_start[b] ? s_start[a] : s_start[b];
+  const int32_t o = hi - lo; return o > 0 ? o : 0;
+}
+CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key1, const int32_t* s_start, const int32_t* s_end, const int32_t* s_score, int64_t n, int32_t max_overlap, uint32_t* keep) {
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= n) return;
+  const uint64_t grp = key1[i0] >> 31;
+  if (i0 > 0 && (key1[i0 - 1] >> 31) == grp) return;
+  int64_t i = i0;
+  while (i < n && (key1[i] >> 31) == grp) {
+    const int64_t cur = i++;
+    while (i < n && (key1[i] >> 31) == grp && soa_overlap(s_start, s_end, i, cur) >= max_overlap && s_score[i] <= s_score[cur]) { keep[i] = 0; ++i; }
+    keep[cur] = (i >= n || (key1[i] >> 31) != grp || soa_overlap(s_start, s_end, i, cur) < max_overlap) ? 1u : 0u;
+  }
+}
+// compaction of (idx, key) by keep; key is rewritten to the final sort key guide | contig | coordinate_start | strand
+CAL_KERNEL __launch_bounds__(256) k_compact_keepers(const uint64_t* key1, const uint32_t* idx, const uint32_t* keep, const uint32_t* pos, int64_t n, uint64_t* key3, uint32_t* idx_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  const uint64_t k = key1[i];
+  key3[pos[i]] = (k & 0xFFFFFFFF00000000ull) | ((k & 0x7FFFFFFFull) << 1) | ((k >> 31) & 1ull);
+  idx_out[pos[i]] = idx[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// host-side engine
+// ------------------------------------------------------------------------------------------------------------------------------------
+struct DBuf {
+  void* p = nullptr; size_t cap = 0;
+  void ensure(size_t bytes) { if (bytes > cap) { dev::free_(p); p = nullptr; cap = 0; size_t want = bytes + bytes / 4 + 256; p = dev::alloc(want); cap = want; } }
+  void ensure_keep(size_t bytes, size_t used, dev::Stream s) {
+    if (bytes <= cap) return;
+    size_t want = bytes + bytes / 2 + 256; void* q = dev::alloc(want);
+    if (used) { dev::d2d(q, p, used, s); dev::stream_sync(s); }
+    dev::free_(p); p = q; cap = want;
+  }
+  void release() { dev::free_(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf { void* p = nullptr; size_t cap = 0; };
+
+}  // namespace cal
+
+using namespace cal;
+
+struct calitas_reference {
+  calitas_engine* owner = nullptr;
+  std::vector<std::string> names; std::vector<int64_t> len, have_b, have_e, own_b, own_e, nib_off;
+  uint32_t* d_nib = nullptr; uint8_t* d_raw = nullptr; int64_t total_padded = 0;
+  struct TileSet { std::vector<Tile> tiles; std::vector<ContigDev> contigs; Tile* d_tiles = nullptr; ContigDev* d_contigs = nullptr; int64_t n_windows = 0; };
+  std::map<std::pair<int, int>, TileSet> tilesets;   // (window_size, step)
+};
+
+struct calitas_hitset {
+  calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; double ms[4] = { 0, 0, 0, 0 }; int64_t counts[4] = { 0, 0, 0, 0 };
+};
+
+struct calitas_engine {
+  int device = 0; dev::Stream stream; Scores sc; calitas_costs costs;
+  dev::Event ev[8];
+  DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, kept, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp;
+  unsigned long long* h_count = nullptr;       // pinned
+  unsigned long long* d_count = nullptr;
+  std::vector<PinnedBuf> pinned_pool;
+  size_t cand_cap_hint = 1u << 20;
+  int64_t launches = 0;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+int set_error(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+template <class F> int guarded(F f) {
+  try { g_last_error.clear(); return f(); }
+  catch (const InvalidArgument& e) { return set_error(CALITAS_EINVAL, e.what()); }
+  catch (const LimitExceeded& e) { return set_error(CALITAS_ELIMIT, e.what()); }
+  catch (const dev::Error& e) { return set_error(CALITAS_ECUDA, e.msg); }
+  catch (const std::exception& e) { return set_error(CALITAS_ESTATE, e.what()); }
+}
+
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+PinnedBuf take_pinned(calitas_engine* e, size_t bytes) {
+  for (size_t i = 0; i < e->pinned_pool.size(); ++i) if (e->pinned_pool[i].cap >= bytes) { PinnedBuf b = e->pinned_pool[i]; e->pinned_pool.erase(e->pinned_pool.begin() + (long)i); return b; }
+  PinnedBuf b; b.cap = bytes + bytes / 4 + 4096; b.p = dev::alloc_host(b.cap); return b;
+}
+
+// Builds (or returns the cached) tiling of the owned reference windows for (window_size, step): SearchReference.scala:52-53.
+calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r, int window_size, int step, const char* chrom) {
+  auto key = std::make_pair(window_size, step);
+  auto it = r->tilesets.find(key);
+  if (it == r->tilesets.end()) {
+    calitas_reference::TileSet ts;
+    int64_t win_base = 0;
+    for (size_t c = 0; c < r->len.size(); ++c) {
+      const int64_t len = r->len[c];
+      const int64_t n_win = len - 1 > 0 ? (len - 1 + step - 1) / step : 0;       // Range(0, len-1, step).size
+      ts.contigs.push_back(ContigDev{ len, r->nib_off[c] - r->have_b[c], win_base });
+      int64_t k_lo = (r->own_b[c] + step - 1) / step;
+      int64_t k_hi = n_win;                                                      // exclusive
+      if (r->own_e[c] < len) { int64_t lim = (r->own_e[c] + step - 1) / step; if (lim < k_hi) k_hi = lim; }
+      if (k_lo < k_hi) {
+        int64_t last_end = std::min(len, (k_hi - 1) * step + window_size);
+        if (k_lo * step < r->have_b[c] || last_end > r->have_e[c])
+          throw InvalidArgument("reference shard of contig " + r->names[c] + " does not hold the bases of its owned windows (halo smaller than the window size)");
+      }
+      for (int64_t k = k_lo; k < k_hi; k += TILE_WINDOWS) ts.tiles.push_back(Tile{ (int32_t)c, (int32_t)std::min<int64_t>(TILE_WINDOWS, k_hi - k), k });
+      ts.n_windows += std::max<int64_t>(0, k_hi - k_lo);
+      win_base += n_win;
+    }
+    if (win_base >= (1ll << 32)) throw LimitExceeded("more than 2^32 reference windows");
+    ts.d_tiles = (Tile*)dev::alloc(ts.tiles.size() * sizeof(Tile));
+    ts.d_contigs = (ContigDev*)dev::alloc(ts.contigs.size() * sizeof(ContigDev));
+    dev::h2d(ts.d_tiles, ts.tiles.data(), ts.tiles.size() * sizeof(Tile), e->stream);
+    dev::h2d(ts.d_contigs, ts.contigs.data(), ts.contigs.size() * sizeof(ContigDev), e->stream);
+    dev::stream_sync(e->stream);
+    it = r->tilesets.emplace(key, std::move(ts)).first;
+  }
+  (void)chrom;
+  return it->second;
+}
+
+struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> align -> canon -> compaction
+  calitas_engine* e; const GuideSpec* d_specs; int slots; bool explicit_mode;
+  const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base;
+};
+
+// Runs sort/align/canon on e->cand[0..n_cand) and leaves the kept hits, in arrival order, in e->kept; returns their number.
+int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
+  calitas_engine* e = P.e; dev::Stream s = e->stream;
+  n_alignments = 0;
+  if (n_cand == 0) return 0;
+  if (n_cand * (int64_t)P.slots >= (1ll << 32)) throw LimitExceeded("too many candidate alignments in one batch");
+  // 1. sort candidate keys -> (guide, window, strand, end column)
+  e->cand_sorted.ensure((size_t)n_cand * 8);
+  size_t tb = dev::sort_keys_u64_tmp((size_t)n_cand, 0, 64); e->tmp.ensure(tb);
+  dev::sort_keys_u64(e->tmp.p, tb, e->cand.as<uint64_t>(), e->cand_sorted.as<uint64_t>(), (size_t)n_cand, 0, 64, s); ++e->launches;
+  // 2. align
+  const int64_t n_slots = n_cand * P.slots;
+  e->hits.ensure((size_t)n_slots * sizeof(calitas_hit)); e->valid.ensure((size_t)n_slots);
+  AlignArgs aa; std::memset(&aa, 0, sizeof aa);
+  aa.cand = e->cand_sorted.as<uint64_t>(); aa.n_cand = n_cand; aa.specs = P.d_specs; aa.sc = e->sc; aa.slots = P.slots; aa.explicit_mode = P.explicit_mode ? 1 : 0;
+  aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows; aa.task_base = P.task_base;
+  aa.hits = e->hits.as<calitas_hit>(); aa.valid = e->valid.as<uint8_t>();
+  dev::event_record(e->ev[2], s);
+  CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); ++e->launches;
+  dev::event_record(e->ev[3], s);
+  // 3. canonicalise per (guide, window, strand)
+  e->rank.ensure((size_t)n_slots * 4); e->perm.ensure((size_t)n_slots * 4); e->flag.ensure((size_t)n_slots * 4); e->pos.ensure((size_t)n_slots * 4);
+  CanonArgs ca; std::memset(&ca, 0, sizeof ca);
+  ca.cand = aa.cand; ca.n_cand = n_cand; ca.specs = P.d_specs; ca.slots = P.slots; ca.explicit_mode = aa.explicit_mode; ca.windows = P.d_windows;
+  ca.hits = aa.hits; ca.valid = aa.valid; ca.rank = e->rank.as<int32_t>(); ca.perm = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>();
+  CAL_LAUNCH(k_canon, blocks_for(n_cand, 128), 128, 0, s, 1, ca); dev::launch_check("k_canon"); ++e->launches;
+  tb = dev::exclusive_sum_u32_tmp((size_t)n_slots); e->tmp.ensure(tb);
+  dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n_slots, s); ++e->launches;
+  uint32_t last_pos = 0, last_flag = 0;
+  dev::d2h(&last_pos, e->pos.as<uint32_t>() + (n_slots - 1), 4, s); dev::d2h(&last_flag, e->flag.as<uint32_t>() + (n_slots - 1), 4, s);
+  dev::stream_sync(s);
+  const int64_t n_kept = (int64_t)last_pos + last_flag;
+  n_alignments = n_slots;
+  e->kept.ensure((size_t)n_kept * sizeof(calitas_hit));
+  if (n_kept) { CAL_LAUNCH(k_gather_flagged, blocks_for(n_slots, 256), 256, 0, s, 1, aa.hits, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, e->kept.as<calitas_hit>()); dev::launch_check("k_gather_flagged"); ++e->launches; }
+  return n_kept;
+}
+
+// removeOverlaps + final sort over e->kept[0..n) -> appended to e->out at out_n; returns number of keepers.
+int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out_n) {
+  dev::Stream s = e->stream;
+  if (n == 0) return 0;
+  if (n >= (1ll << 32)) throw LimitExceeded("too many hits in one batch");
+  const calitas_hit* hits = e->kept.as<calitas_hit>();
+  e->key1.ensure((size_t)n * 8); e->keyA.ensure((size_t)n * 8); e->key_b.ensure((size_t)n * 8); e->idx.ensure((size_t)n * 4); e->idx2.ensure((size_t)n * 4);
+  CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>()); dev::launch_check("k_dedup_keys"); ++e->launches;
+  size_t tb = dev::sort_pairs_u64_tmp((size_t)n, 0, 64); e->tmp.ensure(tb);
+  // stable by -score (arrival order = index order), then stable by (guide, contig, strand, start)
+  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, 32, s); ++e->launches;
+  CAL_LAUNCH(k_gather_u64, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), n, e->keyA.as<uint64_t>()); dev::launch_check("k_gather_u64"); ++e->launches;
+  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)n, 0, 64, s); ++e->launches;
+  // now key1[i], idx[i] sorted by (guide, contig, strand, start, -score, arrival)
+  e->sstart.ensure((size_t)n * 4); e->send.ensure((size_t)n * 4); e->sscore.ensure((size_t)n * 4); e->flag.ensure((size_t)n * 4); e->pos.ensure((size_t)n * 4);
+  CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, hits, e->idx.as<uint32_t>(), n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
+  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, e->key1.as<uint64_t>(), e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), n, max_overlap, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
+  tb = dev::exclusive_sum_u32_tmp((size_t)n); e->tmp.ensure(tb);
+  dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n, s); ++e->launches;
+  uint32_t last_pos = 0, last_flag = 0;
+  dev::d2h(&last_pos, e->pos.as<uint32_t>() + (n - 1), 4, s); dev::d2h(&last_flag, e->flag.as<uint32_t>() + (n - 1), 4, s);
+  dev::stream_sync(s);
+  const int64_t nk = (int64_t)last_pos + last_flag;
+  if (nk == 0) return 0;
+  CAL_LAUNCH(k_compact_keepers, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n, e->keyA.as<uint64_t>(), e->idx2.as<uint32_t>()); dev::launch_check("k_compact_keepers"); ++e->launches;
+  tb = dev::sort_pairs_u64_tmp((size_t)nk, 0, 64); e->tmp.ensure(tb);
+  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)nk, 0, 64, s); ++e->launches;
+  e->out.ensure_keep((size_t)(out_n + nk) * sizeof(calitas_hit), (size_t)out_n * sizeof(calitas_hit), s);
+  CAL_LAUNCH(k_gather, blocks_for(nk, 256), 256, 0, s, 1, hits, e->idx.as<uint32_t>(), nk, e->out.as<calitas_hit>() + out_n); dev::launch_check("k_gather"); ++e->launches;
+  return nk;
+}
+
+calitas_hitset* finish_hitset(calitas_engine* e, int64_t n_out, const double ms[4], const int64_t counts[4]) {
+  std::unique_ptr<calitas_hitset> hs(new calitas_hitset());
+  hs->owner = e; hs->n = n_out;
+  hs->buf = take_pinned(e, (size_t)std::max<int64_t>(1, n_out) * sizeof(calitas_hit));
+  dev::d2h(hs->buf.p, e->out.p, (size_t)n_out * sizeof(calitas_hit), e->stream);
+  dev::event_record(e->ev[1], e->stream);
+  dev::stream_sync(e->stream);
+  for (int i = 0; i < 4; ++i) { hs->ms[i] = ms[i]; hs->counts[i] = counts[i]; }
+  hs->ms[0] = dev::event_ms(e->ev[0], e->ev[1]);
+  hs->ms[3] = hs->ms[0] - hs->ms[1] - hs->ms[2];
+  return hs.release();
+}
+
+std::vector<GuideSpec> build_specs(calitas_engine* e, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits, bool best, std::vector<GuideDef>* defs_out) {
+  if (n_guides <= 0 || !guides) throw InvalidArgument("no guides given");
+  if (n_guides > MAX_GUIDES_PER_CALL) throw LimitExceeded("more than 16384 guides in one call");
+  if (!limits) throw InvalidArgument("limits is NULL");
+  std::vector<GuideSpec> specs;
+  for (int i = 0; i < n_guides; ++i) { GuideDef d = parse_guide(guides[i]); specs.push_back(make_guide_spec(d, e->sc, *limits, best)); if (defs_out) defs_out->push_back(d); }
+  return specs;
+}
+
+// explicit-window path shared by align_regions / align_targets
+calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std::vector<ExplicitWindow>& windows, const std::vector<GuideSpec>& specs) {
+  dev::Stream s = e->stream; dev::set_device(e->device);
+  e->launches = 0;
+  dev::event_record(e->ev[0], s);
+  int slots = 1; for (auto& sp : specs) slots = std::max(slots, sp.slots);
+  e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
+  e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
+  double ms[4] = { 0, 0, 0, 0 }; int64_t counts[4] = { (int64_t)windows.size(), 0, 0, 0 };
+  int64_t n_out = 0;
+  const int64_t n_windows = (int64_t)windows.size();
+  // batches bound the candidate buffer: in best mode every column of every window is a candidate
+  int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_windows, 1 << 18));
+  for (int64_t w0 = 0; w0 < n_windows; w0 += batch) {
+    const int64_t nw = std::min(batch, n_windows - w0);
+    unsigned long long n_cand = 0;
+    for (;;) {
+      e->cand.ensure(e->cand_cap_hint * 8);
+      dev::zero(e->d_count, 8, s);
+      ScanExplicitArgs sa{ d_nib, e->windows.as<ExplicitWindow>() + w0, nw, e->specs.as<GuideSpec>(), e->cand.as<uint64_t>(), e->d_count, (unsigned long long)e->cand_cap_hint };
+      dev::event_record(e->ev[4], s);
+      CAL_LAUNCH(k_scan_explicit, blocks_for(2 * nw, 128), 128, 0, s, 1, sa); dev::launch_check("k_scan_explicit"); ++e->launches;
+      dev::event_record(e->ev[5], s);
+      dev::d2h(e->h_count, e->d_count, 8, s); dev::stream_sync(s);
+      n_cand = *e->h_count;
+      if (n_cand <= e->cand_cap_hint) break;
+      e->cand_cap_hint = (size_t)(n_cand + n_cand / 4);
+    }
+    ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
+    counts[1] += (int64_t)n_cand;
+    // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
+    Pipeline P{ e, e->specs.as<GuideSpec>(), slots, true, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0 };
+    int64_t n_aln = 0;
+    const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
+    if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
+    counts[2] += n_aln;
+    if (n_kept) {
+      e->out.ensure_keep((size_t)(n_out + n_kept) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
+      dev::d2d(e->out.as<calitas_hit>() + n_out, e->kept.p, (size_t)n_kept * sizeof(calitas_hit), s);
+    }
+    n_out += n_kept;
+  }
+  counts[3] = e->launches;
+  return finish_hitset(e, n_out, ms, counts);
+}
+
+}  // namespace
+
+// ====================================================================================================================================
+// C ABI
+// ====================================================================================================================================
+extern "C" {
+
+const char* calitas_last_error(void) { return g_last_error.c_str(); }
+int calitas_tools_set_error(int code, const char* msg) { return set_error(code, msg ? msg : ""); }   // used by cal_tools.cpp
+int calitas_engine_get_costs(const calitas_engine* e, calitas_costs* out) {
+  if (!e || !out) return set_error(CALITAS_EINVAL, "bad arguments");
+  *out = e->costs; return CALITAS_OK;
+}
+
+int calitas_engine_create(int32_t device_id, const calitas_costs* costs, calitas_engine** out) {
+  return guarded([&]() -> int {
+    if (!out) throw InvalidArgument("out is NULL");
+    *out = nullptr;
+    calitas_costs c = costs ? *costs : calitas_costs{ -120, -122, -121, -260 };
+    dev::init(device_id);
+    std::unique_ptr<calitas_engine> e(new calitas_engine());
+    e->device = device_id; e->costs = c; e->sc = make_scores(c);
+    e->stream = dev::stream_create();
+    for (auto& ev : e->ev) ev = dev::event_create();
+    e->h_count = (unsigned long long*)dev::alloc_host(64);
+    e->d_count = (unsigned long long*)dev::alloc(64);
+    *out = e.release();
+    return CALITAS_OK;
+  });
+}
+
+void calitas_engine_destroy(calitas_engine* e) {
+  if (!e) return;
+  try {
+    dev::set_device(e->device);
+    dev::stream_sync(e->stream);
+    for (DBuf* b : { &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->kept, &e->out, &e->tmp, &e->key1, &e->keyA,
+                     &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp }) b->release();
+    for (auto& p : e->pinned_pool) dev::free_host(p.p);
+    dev::free_host(e->h_count); dev::free_(e->d_count);
+    for (auto& ev : e->ev) dev::event_destroy(ev);
+    dev::stream_destroy(e->stream);
+  } catch (...) {}
+  delete e;
+}
+
+int calitas_shard_plan(int32_t n_contigs, const int64_t* lengths, int32_t shard, int32_t n_shards, int64_t halo,
+                       int64_t* own_begin, int64_t* own_end, int64_t* have_begin, int64_t* have_end) {
+  return guarded([&]() -> int {
+    if (n_contigs <= 0 || !lengths || n_shards <= 0 || shard < 0 || shard >= n_shards || halo < 0) throw InvalidArgument("bad shard plan arguments");
+    int64_t tot = 0; for (int c = 0; c < n_contigs; ++c) tot += lengths[c];
+    const int64_t lo = (int64_t)((__int128)tot * shard / n_shards), hi = (int64_t)((__int128)tot * (shard + 1) / n_shards);
+    int64_t off = 0;
+    for (int c = 0; c < n_contigs; ++c) {
+      const int64_t len = lengths[c];
+      int64_t b = std::min(std::max<int64_t>(lo - off, 0), len), en = std::min(std::max<int64_t>(hi - off, 0), len);
+      own_begin[c] = b; own_end[c] = en; have_begin[c] = b; have_end[c] = en > b ? std::min(len, en + halo) : b;
+      off += len;
+    }
+    return CALITAS_OK;
+  });
+}
+
+int calitas_reference_load(calitas_engine* e, int32_t n_contigs, const char* const* names, const int64_t* lengths, const uint8_t* const* bases,
+                           const int64_t* have_begin, const int64_t* have_end, const int64_t* own_begin, const int64_t* own_end, int32_t keep_raw,
+                           calitas_reference** out) {
+  return guarded([&]() -> int {
+    if (!e || !out || n_contigs <= 0 || !names || !lengths || !bases) throw InvalidArgument("bad reference arguments");
+    if (n_contigs >= (1 << 18)) throw LimitExceeded("more than 262143 contigs");
+    *out = nullptr; dev::set_device(e->device);
+    std::unique_ptr<calitas_reference> r(new calitas_reference());
+    r->owner = e; int64_t off = 64;
+    for (int c = 0; c < n_contigs; ++c) {
+      const int64_t len = lengths[c];
+      if (len < 0 || len >= (1ll << 31)) throw LimitExceeded("contig longer than 2^31-1 bases");
+      const int64_t hb = have_begin ? have_begin[c] : 0, he = have_end ? have_end[c] : len, ob = own_begin ? own_begin[c] : 0, oe = own_end ? own_end[c] : len;
+      if (hb < 0 || he < hb || he > len || ob < 0 || oe < ob || oe > len) throw InvalidArgument("bad base range for contig");
+      r->names.push_back(names[c] ? names[c] : ""); r->len.push_back(len); r->have_b.push_back(hb); r->have_e.push_back(he); r->own_b.push_back(ob); r->own_e.push_back(oe);
+      r->nib_off.push_back(off);
+      off += ((he - hb) + 63) / 64 * 64 + 64;
+    }
+    r->total_padded = off;
+    r->d_raw = (uint8_t*)dev::alloc((size_t)off);
+    r->d_nib = (uint32_t*)dev::alloc((size_t)off / 2);
+    dev::zero(r->d_raw, (size_t)off, e->stream);
+    for (int c = 0; c < n_contigs; ++c) {
+      const int64_t n = r->have_e[(size_t)c] - r->have_b[(size_t)c];
+      if (n > 0) { if (!bases[c]) throw InvalidArgument("bases pointer is NULL"); dev::h2d(r->d_raw + r->nib_off[(size_t)c], bases[c], (size_t)n, e->stream); }
+    }
+    const int64_t n_words = off / 8;
+    const unsigned grid = (unsigned)std::min<int64_t>((n_words + 255) / 256, (int64_t)dev::sm_count(e->device) * 16);
+    CAL_LAUNCH(k_pack, grid, 256, 256, e->stream, 2, r->d_raw, r->d_nib, n_words); dev::launch_check("k_pack");
+    dev::stream_sync(e->stream);
+    if (!keep_raw) { dev::free_(r->d_raw); r->d_raw = nullptr; }
+    *out = r.release();
+    return CALITAS_OK;
+  });
+}
+
+void calitas_reference_free(calitas_engine* e, calitas_reference* r) {
+  if (!r) return;
+  try {
+    if (e) dev::set_device(e->device);
+    dev::free_(r->d_nib); dev::free_(r->d_raw);
+    for (auto& kv : r->tilesets) { dev::free_(kv.second.d_tiles); dev::free_(kv.second.d_contigs); }
+  } catch (...) {}
+  delete r;
+}
+
+int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
+                   int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out) {
+  return guarded([&]() -> int {
+    if (!e || !ref_c || !out) throw InvalidArgument("bad search arguments");
+    *out = nullptr;
+    calitas_reference* ref = const_cast<calitas_reference*>(ref_c);
+    dev::set_device(e->device); dev::Stream s = e->stream;
+    std::vector<GuideDef> defs; std::vector<GuideSpec> specs = build_specs(e, n_guides, guides, limits, false, &defs);
+    if (window_size <= 0 || (uint32_t)window_size > MAX_WINDOW_LEN) throw InvalidArgument("window size out of range");
+    int chrom_idx = -1;
+    if (chrom && chrom[0]) { for (size_t c = 0; c < ref->names.size(); ++c) if (ref->names[c] == chrom) chrom_idx = (int)c; if (chrom_idx < 0) throw InvalidArgument(std::string("Unknown chromosome: ") + chrom); }
+    e->launches = 0;
+    dev::event_record(e->ev[0], s);
+    e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
+    double ms[4] = { 0, 0, 0, 0 }; int64_t counts[4] = { 0, 0, 0, 0 };
+    int64_t n_out = 0;
+    const int G_CHUNK = 16;
+    int g0 = 0;
+    while (g0 < n_guides) {
+      // a chunk = consecutive guides sharing the raw guide length, hence the window tiling (SearchReference.scala:528-530)
+      const int raw_len = (int)defs[(size_t)g0].raw.size();
+      int g1 = g0 + 1; while (g1 < n_guides && g1 - g0 < G_CHUNK && (int)defs[(size_t)g1].raw.size() == raw_len) ++g1;
+      const int overlap = raw_len + limits->max_guide_diffs + limits->max_gaps_between_guide_and_pam - 1;
+      const int step = window_size - overlap;
+      if (step <= 0) throw InvalidArgument("window size must exceed guide length + max-guide-diffs + max-gaps-between-guide-and-pam - 1");
+      calitas_reference::TileSet& ts = tileset_for(e, ref, window_size, step, chrom);
+      // tiles of one contig are contiguous: restrict the launch for -c
+      size_t t_begin = 0, t_end = ts.tiles.size();
+      if (chrom_idx >= 0) { t_begin = t_end = 0; bool in = false; for (size_t t = 0; t < ts.tiles.size(); ++t) { if (ts.tiles[t].contig == chrom_idx) { if (!in) { t_begin = t; in = true; } t_end = t + 1; } } }
+      const size_t n_tiles = t_end - t_begin;
+      int slots = 1; for (int g = g0; g < g1; ++g) slots = std::max(slots, specs[(size_t)g].slots);
+      const int ng = g1 - g0;
+      const int64_t tile_bases = (int64_t)(TILE_WINDOWS - 1) * step + window_size;
+      const size_t smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2) * 4;
+      if (smem > 200 * 1024) throw LimitExceeded("window size too large for the shared-memory tile");
+#ifndef CAL_HOSTSIM
+      dev::check(cudaFuncSetAttribute(k_scan_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
+#endif
+      unsigned long long n_cand = 0;
+      if (n_tiles) for (;;) {
+        e->cand.ensure(e->cand_cap_hint * 8);
+        dev::zero(e->d_count, 8, s);
+        ScanArgs sa{ ref->d_nib, ts.d_contigs, ts.d_tiles + t_begin, e->specs.as<GuideSpec>(), g0, g1, window_size, step, raw_len, e->cand.as<uint64_t>(), e->d_count, (unsigned long long)e->cand_cap_hint };
+        dev::event_record(e->ev[4], s);
+        CAL_LAUNCH(k_scan_tiled, (unsigned)n_tiles, SCAN_THREADS, smem, s, 2, sa); dev::launch_check("k_scan_tiled"); ++e->launches;
+        dev::event_record(e->ev[5], s);
+        dev::d2h(e->h_count, e->d_count, 8, s); dev::stream_sync(s);
+        n_cand = *e->h_count;
+        if (n_cand <= e->cand_cap_hint) break;
+        e->cand_cap_hint = (size_t)(n_cand + n_cand / 4);          // pool too small: grow and re-run, never truncate
+      }
+      if (n_tiles) ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
+      if (g0 == 0) { for (size_t t = t_begin; t < t_end; ++t) counts[0] += ts.tiles[t].nwin; }
+      counts[1] += (int64_t)n_cand;
+      Pipeline P{ e, e->specs.as<GuideSpec>(), slots, false, ref->d_nib, ts.d_contigs, (int)ts.contigs.size(), window_size, step, nullptr, 0 };
+      int64_t n_aln = 0;
+      const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
+      if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
+      counts[2] += n_aln;
+      if (dedup) n_out += run_dedup(e, n_kept, limits->max_overlap, n_out);
+      else if (n_kept) {
+        e->out.ensure_keep((size_t)(n_out + n_kept) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
+        dev::d2d(e->out.as<calitas_hit>() + n_out, e->kept.p, (size_t)n_kept * sizeof(calitas_hit), s);
+        n_out += n_kept;
+      }
+      g0 = g1;
+    }
+    counts[3] = e->launches;
+    *out = finish_hitset(e, n_out, ms, counts);
+    return CALITAS_OK;
+  });
+}
+
+int calitas_align_regions(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides, int64_t n_tasks,
+                          const calitas_region_task* tasks, const calitas_limits* limits, int32_t best, calitas_hitset** out) {
+  return guarded([&]() -> int {
+    if (!e || !ref || !out || n_tasks < 0 || (n_tasks && !tasks)) throw InvalidArgument("bad align_regions arguments");
+    *out = nullptr;
+    if (n_tasks >= (1ll << 31)) throw LimitExceeded("too many tasks");
+    std::vector<GuideSpec> specs = build_specs(e, n_guides, guides, limits, best != 0, nullptr);
+    std::vector<ExplicitWindow> windows((size_t)n_tasks);
+    for (int64_t i = 0; i < n_tasks; ++i) {
+      const calitas_region_task& t = tasks[i];
+      if (t.guide_idx < 0 || t.guide_idx >= n_guides) throw InvalidArgument("task guide_idx out of range");
+      if (t.contig_idx < 0 || t.contig_idx >= (int)ref->len.size()) throw InvalidArgument("Unknown chromosome index");
+      const size_t c = (size_t)t.contig_idx;
+      if (t.length < 0 || (uint32_t)t.length > MAX_WINDOW_LEN) throw InvalidArgument("region length out of range");
+      if (t.start < ref->have_b[c] || t.start + t.length > ref->have_e[c]) throw InvalidArgument("region outside the loaded bases of contig " + ref->names[c]);
+      windows[(size_t)i] = ExplicitWindow{ ref->nib_off[c] - ref->have_b[c] + t.start, t.length, (int32_t)t.start, t.guide_idx, t.contig_idx };
+    }
+    *out = run_explicit(e, ref->d_nib, windows, specs);
+    return CALITAS_OK;
+  });
+}
+
+int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_guide* guides, int64_t n_tasks, const calitas_target_task* tasks,
+                          const calitas_limits* limits, int32_t best, calitas_hitset** out) {
+  return guarded([&]() -> int {
+    if (!e || !out || n_tasks < 0 || (n_tasks && !tasks)) throw InvalidArgument("bad align_targets arguments");
+    *out = nullptr;
+    if (n_tasks >= (1ll << 31)) throw LimitExceeded("too many tasks");
+    dev::set_device(e->device);
+    std::vector<GuideSpec> specs = build_specs(e, n_guides, guides, limits, best != 0, nullptr);
+    std::vector<ExplicitWindow> windows((size_t)n_tasks);
+    int64_t total = 8;
+    for (int64_t i = 0; i < n_tasks; ++i) {
+      const calitas_target_task& t = tasks[i];
+      if (t.guide_idx < 0 || t.guide_idx >= n_guides) throw InvalidArgument("task guide_idx out of range");
+      if (t.length < 0 || (uint32_t)t.length > MAX_WINDOW_LEN || (t.length && !t.bases)) throw InvalidArgument("target length out of range");
+      windows[(size_t)i] = ExplicitWindow{ total, t.length, t.target_offset, t.guide_idx, -1 };
+      total += (t.length + 7) / 8 * 8 + 8;
+    }
+    // targets are small: pack on the host into the same 4-bit code words the device packer produces
+    std::vector<uint32_t> words((size_t)total / 8 + 1, 0u);
+    for (int64_t i = 0; i < n_tasks; ++i) {
+      const calitas_target_task& t = tasks[i]; const int64_t b = windows[(size_t)i].nib_start;
+      for (int32_t k = 0; k < t.length; ++k) words[(size_t)((b + k) >> 3)] |= target_code(t.bases[k]) << (((b + k) & 7) * 4);
+    }
+    e->nib_tmp.ensure(words.size() * 4); dev::h2d(e->nib_tmp.p, words.data(), words.size() * 4, e->stream); dev::stream_sync(e->stream);
+    *out = run_explicit(e, e->nib_tmp.as<uint32_t>(), windows, specs);
+    return CALITAS_OK;
+  });
+}
+
+int64_t calitas_hitset_count(const calitas_hitset* h) { return h ? h->n : 0; }
+const calitas_hit* calitas_hitset_data(const calitas_hitset* h) { return h ? (const calitas_hit*)h->buf.p : nullptr; }
+void calitas_hitset_free(calitas_hitset* h) { if (!h) return; if (h->owner) h->owner->pinned_pool.push_back(h->buf); delete h; }
+int calitas_hitset_stats(const calitas_hitset* h, double ms[4], int64_t counts[4]) {
+  if (!h) return set_error(CALITAS_EINVAL, "hitset is NULL");
+  for (int i = 0; i < 4; ++i) { if (ms) ms[i] = h->ms[i]; if (counts) counts[i] = h->counts[i]; }
+  return CALITAS_OK;
+}
+
+int calitas_render_alignments(const calitas_hit* hits, int64_t n_hits, int32_t n_guides, const calitas_guide* guides, int32_t n_contigs, const char* const* names,
+                              const uint8_t* const* contig_bases, const calitas_target_task* targets, int32_t upper_case, char** out_text) {
+  return guarded([&]() -> int {
+    if (!out_text || (n_hits && !hits) || !guides) throw InvalidArgument("bad render arguments");
+    *out_text = nullptr;
+    std::vector<GuideDef> defs; for (int i = 0; i < n_guides; ++i) defs.push_back(parse_guide(guides[i]));
+    std::string text = alignment_header();
+    for (int64_t i = 0; i < n_hits; ++i) {
+      const calitas_hit& h = hits[i];
+      if (h.guide_idx < 0 || h.guide_idx >= n_guides) throw InvalidArgument("hit guide_idx out of range");
+      std::string fwd, chrom = "n/a";
+      const int32_t len = h.end_offset - h.start_offset;
+      if (h.contig_idx >= 0) {
+        if (h.contig_idx >= n_contigs || !contig_bases || !contig_bases[h.contig_idx]) throw InvalidArgument("contig bases missing for a hit");
+        fwd.assign((const char*)contig_bases[h.contig_idx] + h.start_offset, (size_t)len);
+        if (names && names[h.contig_idx]) chrom = names[h.contig_idx];
+      } else {
+        if (!targets) throw InvalidArgument("targets missing for align_targets hits");
+        const calitas_target_task& t = targets[h.task_idx];
+        fwd.assign((const char*)t.bases + (h.start_offset - t.target_offset), (size_t)len);
+      }
+      Rendered r = render_hit(h, defs[(size_t)h.guide_idx], fwd, upper_case != 0);
+      text += alignment_row(h, r, chrom);
+    }
+    char* p = (char*)std::malloc(text.size() + 1); std::memcpy(p, text.data(), text.size() + 1); *out_text = p;
+    return CALITAS_OK;
+  });
+}
+void calitas_free_text(char* text) { std::free(text); }
+
+}  // extern "C"
+
+#ifdef CAL_HOSTSIM
+namespace cal { namespace sim { Dim3 threadIdx_, blockIdx_, blockDim_, gridDim_; int phase_ = 0; unsigned char smem_[256 * 1024]; } }
+#endif

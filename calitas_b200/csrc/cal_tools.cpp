@@ -1,0 +1,476 @@
+// cal_tools.cpp — host-side mirror of the reference's operators (see include/calitas_b200_tools.h).
+// Alignments are computed only by the device engine (calitas_search / calitas_align_regions / calitas_align_targets).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/calitas_b200_tools.h"
+#include "cal_host.h"
+
+using namespace cal;
+
+namespace {
+
+typedef std::string Str;
+struct ToolError { int code; Str msg; };
+[[noreturn]] void bad(const Str& m) { throw ToolError{ CALITAS_EINVAL, m }; }
+void ck(int rc) { if (rc != CALITAS_OK) throw ToolError{ rc, calitas_last_error() }; }
+
+extern "C" int calitas_tools_set_error(int code, const char* msg);   // defined in cal_engine.cu
+
+template <class F> int guarded(F f) {
+  try { return f(); }
+  catch (const ToolError& e) { return calitas_tools_set_error(e.code, e.msg.c_str()); }
+  catch (const InvalidArgument& e) { return calitas_tools_set_error(CALITAS_EINVAL, e.what()); }
+  catch (const LimitExceeded& e) { return calitas_tools_set_error(CALITAS_ELIMIT, e.what()); }
+  catch (const std::exception& e) { return calitas_tools_set_error(CALITAS_ESTATE, e.what()); }
+}
+char* dup_text(const Str& s) { char* p = (char*)std::malloc(s.size() + 1); std::memcpy(p, s.data(), s.size() + 1); return p; }
+Str to_upper(Str s) { for (auto& c : s) c = (char)std::toupper((unsigned char)c); return s; }
+
+struct HitSet {   // RAII over calitas_hitset
+  calitas_hitset* h = nullptr; ~HitSet() { calitas_hitset_free(h); }
+  int64_t n() const { return calitas_hitset_count(h); } const calitas_hit* data() const { return calitas_hitset_data(h); }
+};
+
+int contig_index(const calitas_genome_view& g, const Str& name) { for (int i = 0; i < g.n_contigs; ++i) if (name == g.names[i]) return i; return -1; }
+
+// ---- GuideAlignment ordering (GuideAlignment.scala:125-129): stable sort by score desc, gap bases asc ----
+void sort_alignments(std::vector<calitas_hit>& v) {
+  std::stable_sort(v.begin(), v.end(), [](const calitas_hit& a, const calitas_hit& b) { return a.score != b.score ? a.score > b.score : a.gap_bases < b.gap_bases; });
+}
+
+// ---- ReferenceHit rows (ReferenceHit.scala:99-132, 210-254) ----------------------------------------------------------------------
+struct VariantAllele { Str id; int pos; Str ref, alt; float af; };
+Str variant_display(const VariantAllele& v) {   // SearchReference.scala:106-109
+  char buf[64]; std::snprintf(buf, sizeof buf, "%.3f", (double)v.af);
+  return (v.id.empty() ? Str(".") : v.id) + ":" + std::to_string(v.pos - 1) + ":" + v.ref + ">" + v.alt + ":" + buf;
+}
+Str format_af(double d) {   // fgbio Metric: DecimalFormat("0.0####")
+  char buf[64]; std::snprintf(buf, sizeof buf, "%.5f", d); Str s(buf);
+  while (s.size() > 3 && s.back() == '0' && s[s.size() - 2] != '.') s.pop_back();
+  return s;
+}
+
+struct Row {   // what removeOverlaps / sort need, plus the rendered line
+  int contig; int start; char strand; int score; int sweep_end; Str key /* chromosome:strand:variant_description */; Str line;
+};
+
+struct RowContext {
+  const calitas_genome_view* genome; Str guide_id, aligner_id, arguments, time_stamp, version, vcf_id; bool has_vcf = false;
+};
+
+Str fetch_bases(const calitas_genome_view& g, int contig, int start1, int end1, bool rc) {   // ReferenceHit.scala:261-266 (1-based inclusive)
+  const int64_t len = g.lengths[contig];
+  const int as = std::max(1, start1), ae = (int)std::min<int64_t>(len, end1);
+  Str s((size_t)(as - start1), 'N');
+  if (ae >= as) s.append((const char*)g.bases[contig] + as - 1, (size_t)(ae - as + 1));
+  s.append((size_t)std::max(0, end1 - std::max(ae, as - 1)), 'N');
+  return to_upper(rc ? revcomp(s) : s);
+}
+
+struct Flanks { bool has[4] = { false, false, false, false }; Str v[4]; };   // left10, right10, left8, right8 in guide orientation
+
+Row make_row(const RowContext& cx, const calitas_hit& h, const Rendered& r, const GuideDef& gd, int contig, int so, int eo, int gso, int geo,
+             const std::vector<VariantAllele>& variants, const Flanks& fl) {
+  const calitas_genome_view& g = *cx.genome;
+  std::vector<const VariantAllele*> vs;
+  for (auto& v : variants) if (v.pos - 1 >= so && v.pos - 1 <= eo) vs.push_back(&v);       // ReferenceHit.scala:211
+  const bool neg = h.strand == '-';
+  auto ten_left = [&] { return fetch_bases(g, contig, gso + 1 - 10, gso, neg); };
+  auto ten_right = [&] { return fetch_bases(g, contig, geo + 1, geo + 10, neg); };
+  auto eight_left = [&] { return fetch_bases(g, contig, so + 1 - 8, so, neg); };
+  auto eight_right = [&] { return fetch_bases(g, contig, eo + 1, eo + 8, neg); };
+  Str build = (g.assembly && g.assembly[0]) ? g.assembly : "unknown";
+  if (!vs.empty()) build += "+variants";
+  Str pam_used; for (char c : r.guide) if (c >= 'a' && c <= 'z') pam_used += c;
+  Str vid, vdesc; float min_af = 0;
+  for (size_t i = 0; i < vs.size(); ++i) { if (i) { vid += ';'; vdesc += ';'; } vid += vs[i]->id; vdesc += variant_display(*vs[i]); if (i == 0 || vs[i]->af < min_af) min_af = vs[i]->af; }
+  auto I = [](int v) { return std::to_string(v); };
+  std::vector<Str> f = {
+    cx.guide_id, gd.protospacer, build, g.names[contig], I(gso), I(geo), Str(1, (char)h.strand), r.unpadded_target_without_pam,
+    fl.has[0] ? fl.v[0] : (neg ? ten_right() : ten_left()), fl.has[1] ? fl.v[1] : (neg ? ten_left() : ten_right()),
+    pam_used, vid, vdesc, (!vs.empty() && cx.has_vcf) ? cx.vcf_id : Str(), vs.empty() ? Str() : format_af((double)min_af),
+    I(h.score), I(r.guide_mm), I(r.guide_gaps), I(r.guide_mm_plus_gaps), I(r.pam_mm), I(r.edits), r.padded_guide, r.padded_alignment, r.padded_target,
+    fl.has[2] ? fl.v[2] : (neg ? eight_right() : eight_left()), fl.has[3] ? fl.v[3] : (neg ? eight_left() : eight_right()),
+    r.cigar, I((int)gd.protospacer.size()), I((int)r.unpadded_target_without_pam.size()), cx.aligner_id, cx.version, Str(), cx.arguments, cx.time_stamp };
+  { Str pams; for (size_t i = 0; i < gd.pams.size(); ++i) { if (i) pams += ','; pams += gd.pams[i]; } f[31] = pams; }   // ReferenceHit.scala:207
+  Row row; row.contig = contig; row.start = gso; row.strand = (char)h.strand; row.score = h.score;
+  row.sweep_end = gso + (h.end_offset - h.start_offset) - 1;           // ReferenceHit.scala:135-138 (cigar.lengthOnTarget is window-relative span)
+  row.key = Str("{") + g.names[contig] + ":" + (char)h.strand + ":" + vdesc;
+  for (size_t i = 0; i < f.size(); ++i) { if (i) row.line += '\t'; row.line += f[i]; }
+  row.line += '\n';
+  return row;
+}
+
+Str hit_header() {
+  return "guide_id\tunpadded_guide_sequence\tgenome_build\tchromosome\tcoordinate_start\tcoordinate_end\tstrand\tunpadded_target_sequence\tten_bases_5_prime\t"
+         "ten_bases_3_prime\tpam_used\tvariant_id\tvariant_description\tvariant_vcf\tallele_frequency\tscore\tguide_mm\tguide_gaps\tguide_mm_plus_gaps\tpam_mm\t"
+         "total_mm_plus_gaps\tpadded_guide\tpadded_alignment\tpadded_target\tpadded_extra_8_bases_5_prime\tpadded_extra_8_bases_3_prime\tcigar\t"
+         "unpadded_guide_sequence_length\tunpadded_target_sequence_length\taligner\taligner_version\taligner_search_pam\taligner_other_parameters\ttime_stamp\n";
+}
+
+void sort_rows(std::vector<Row>& rows) {   // ReferenceHit.sort, ReferenceHit.scala:284
+  std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) {
+    if (a.contig != b.contig) return a.contig < b.contig;
+    if (a.start != b.start) return a.start < b.start;
+    if (a.strand != b.strand) return a.strand < b.strand;
+    return a.score > b.score;
+  });
+}
+int row_overlap(const Row& a, const Row& b) { return std::max(0, std::min(a.sweep_end, b.sweep_end) - std::max(a.start, b.start)); }
+
+// removeOverlaps on the host — used only when variant-window hits must be merged with reference hits (SearchReference.scala:653-675);
+// the plain reference search does this on the device.
+std::vector<Row> remove_overlaps_host(std::vector<Row>& hits, int max_overlap) {
+  std::map<Str, std::vector<Row>> groups;
+  for (auto& h : hits) groups[h.key].push_back(std::move(h));
+  std::vector<Row> keep;
+  for (auto& kv : groups) {
+    std::vector<Row>& v = kv.second; sort_rows(v);
+    for (size_t i = 0; i < v.size();) {
+      const size_t cur = i++;
+      while (i < v.size() && row_overlap(v[i], v[cur]) >= max_overlap && v[i].score <= v[cur].score) ++i;
+      if (i >= v.size() || row_overlap(v[i], v[cur]) < max_overlap) keep.push_back(v[cur]);
+    }
+  }
+  return keep;
+}
+
+Str contig_slice(const calitas_genome_view& g, int contig, int start, int end) { return Str((const char*)g.bases[contig] + start, (size_t)(end - start)); }
+
+// ---- variant windows (SearchReference.scala:101-400) -----------------------------------------------------------------------------------
+struct VcfRecord { Str chrom; int pos; Str id, ref; std::vector<Str> alts; std::vector<float> afs; bool has_af = false; int end() const { return pos + (int)ref.size() - 1; } };
+
+std::vector<Str> split(const Str& s, char sep) { std::vector<Str> out; size_t a = 0; for (;;) { size_t b = s.find(sep, a); if (b == Str::npos) { out.push_back(s.substr(a)); return out; } out.push_back(s.substr(a, b - a)); a = b + 1; } }
+
+std::vector<VcfRecord> parse_vcf(const char* text) {
+  std::vector<VcfRecord> out;
+  for (const Str& raw : split(text, '\n')) {
+    Str line = raw; if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty() || line[0] == '#') continue;
+    std::vector<Str> f = split(line, '\t');
+    if (f.size() < 5) bad("malformed VCF record: " + line);
+    VcfRecord v; v.chrom = f[0]; v.pos = std::atoi(f[1].c_str()); v.id = f[2] == "." ? Str() : f[2]; v.ref = f[3];
+    for (const Str& a : split(f[4], ',')) if (a != ".") v.alts.push_back(a);
+    if (f.size() >= 8) for (const Str& kv : split(f[7], ';')) if (kv.compare(0, 3, "AF=") == 0) { v.has_af = true; for (const Str& x : split(kv.substr(3), ',')) v.afs.push_back(x == "." ? 0.0f : std::strtof(x.c_str(), nullptr)); }
+    out.push_back(std::move(v));
+  }
+  return out;
+}
+
+struct VariantWindow {
+  int contig; int start /* 1-based */; std::vector<VariantAllele> alleles; Str cigar_ops /* M I D per unit */; Str bases;
+  Str cigar_text() const { Str o; for (size_t i = 0; i < cigar_ops.size();) { size_t j = i; while (j < cigar_ops.size() && cigar_ops[j] == cigar_ops[i]) ++j; o += std::to_string(j - i); o += cigar_ops[i]; i = j; } return o; }
+  // SearchReference.scala:133-156
+  int ref_offset_at(int offset, bool preceding) const {
+    if (offset == (int)bases.size()) { int lot = 0; for (char c : cigar_ops) lot += (c != 'I'); return start - 1 + lot; }
+    int ref_off = start - 1, base_off = 0;
+    for (size_t i = 0; i < cigar_ops.size();) {
+      size_t j = i; while (j < cigar_ops.size() && cigar_ops[j] == cigar_ops[i]) ++j;
+      const char op = cigar_ops[i]; const int len = (int)(j - i), on_query = op == 'D' ? 0 : len, on_ref = op == 'I' ? 0 : len;
+      if (offset < base_off + on_query) {
+        if (op == 'I') return preceding ? ref_off - 1 : ref_off;
+        return ref_off + (offset - base_off);
+      }
+      ref_off += on_ref; base_off += on_query; i = j;
+    }
+    bad("window offset outside the variant window");
+  }
+};
+
+// all allele index vectors in the order of SearchReference.scala:377-399: first variant varies slowest
+void allele_vectors(const std::vector<int>& counts, std::vector<std::vector<int>>& out) {
+  size_t total = 1; for (int c : counts) total *= (size_t)c;
+  out.assign(total, std::vector<int>(counts.size(), 0));
+  for (size_t r = 0; r < total; ++r) { size_t rem = r; for (size_t i = counts.size(); i-- > 0;) { out[r][i] = (int)(rem % (size_t)counts[i]); rem /= (size_t)counts[i]; } }
+}
+
+VariantWindow build_variant_window(const std::vector<const VcfRecord*>& vars, const std::vector<int>& alleles, int contig, const Str& upper_bases, int padding) {
+  const int ws = std::max(1, vars.front()->pos - padding), we = (int)std::min<int64_t>((int64_t)upper_bases.size(), (int64_t)vars.back()->end() + padding);
+  VariantWindow w; w.contig = contig; w.start = ws; w.bases = upper_bases.substr((size_t)ws - 1, (size_t)(we - ws + 1));
+  for (size_t i = 0; i < vars.size(); ++i) {
+    const VcfRecord* v = vars[i]; const int a = alleles[i];
+    const float af = (v->has_af && a - 1 < (int)v->afs.size()) ? v->afs[(size_t)a - 1] : 0.0f;     // SearchReference.scala:199
+    w.alleles.push_back(VariantAllele{ v->id, v->pos, v->ref, v->alts[(size_t)a - 1], af });
+  }
+  for (size_t k = w.alleles.size(); k-- > 0;) {   // right to left (:270-279)
+    const VariantAllele& a = w.alleles[k]; const size_t at = (size_t)(a.pos - ws);
+    if (a.ref.size() == a.alt.size()) w.bases.replace(at, a.alt.size(), a.alt);
+    else w.bases = w.bases.substr(0, at) + a.alt + (at + a.ref.size() < w.bases.size() ? w.bases.substr(at + a.ref.size()) : Str());
+  }
+  int ref_pos = ws, base_off = 0;
+  for (auto& a : w.alleles) {   // :282-319
+    const int pre = a.pos - ref_pos;
+    if (pre > 0) { w.cigar_ops.append((size_t)pre, 'M'); ref_pos += pre; base_off += pre; }
+    if (a.ref.size() == a.alt.size()) w.cigar_ops.append(a.ref.size(), 'M');
+    else if (a.ref.size() == 1) { w.cigar_ops += 'M'; w.cigar_ops.append(a.alt.size() - 1, 'I'); }
+    else if (a.alt.size() == 1) { w.cigar_ops += 'M'; w.cigar_ops.append(a.ref.size() - 1, 'D'); }
+    else { w.cigar_ops.append(a.ref.size(), 'D'); w.cigar_ops.append(a.alt.size(), 'I'); }
+    ref_pos += (int)a.ref.size(); base_off += (int)a.alt.size();
+  }
+  const int tail = (int)w.bases.size() - base_off;
+  if (tail < 0) bad("variant window: alleles extend past the window");
+  w.cigar_ops.append((size_t)tail, 'M');
+  return w;
+}
+
+std::vector<VariantWindow> variant_windows(const calitas_genome_view& g, const std::vector<VcfRecord>& all, int chrom_idx, int padding, int max_variants) {
+  std::vector<VariantWindow> out;
+  std::vector<const VcfRecord*> vs;
+  for (auto& v : all) if (chrom_idx < 0 || v.chrom == g.names[chrom_idx]) vs.push_back(&v);
+  std::map<int, Str> upper_cache;
+  int ref_idx = chrom_idx >= 0 ? chrom_idx : 0;
+  for (size_t i = 0; i < vs.size();) {
+    std::vector<const VcfRecord*> cluster; const VcfRecord* last = vs[i++]; cluster.push_back(last);          // nextChunk :326-337
+    while (i < vs.size() && vs[i]->chrom == last->chrom && vs[i]->pos <= last->end() + padding) { last = vs[i++]; cluster.push_back(last); }
+    while (cluster.front()->chrom != g.names[ref_idx]) { if (++ref_idx >= g.n_contigs) bad("VCF contig " + cluster.front()->chrom + " not found in FASTA order"); upper_cache.clear(); }   // :251
+    if (!upper_cache.count(ref_idx)) upper_cache[ref_idx] = to_upper(Str((const char*)g.bases[ref_idx], (size_t)g.lengths[ref_idx]));   // :225
+    const Str& ub = upper_cache[ref_idx];
+    for (size_t t = 0; t < cluster.size(); ++t) {                                                            // reChunk :343-347
+      std::vector<const VcfRecord*> sub;
+      for (size_t u = t; u < cluster.size() && cluster[u]->pos - cluster[t]->end() <= padding; ++u) sub.push_back(cluster[u]);
+      if ((int)sub.size() > max_variants) {                                                                  // :352-356
+        for (size_t a = 0; a < sub[0]->alts.size(); ++a) out.push_back(build_variant_window({ sub[0] }, { (int)a + 1 }, ref_idx, ub, padding));
+        continue;
+      }
+      std::vector<int> counts; for (auto* v : sub) counts.push_back(1 + (int)v->alts.size());
+      std::vector<std::vector<int>> combos; allele_vectors(counts, combos);
+      for (auto& combo : combos) {
+        std::vector<const VcfRecord*> sv; std::vector<int> sa;
+        for (size_t k = 0; k < sub.size(); ++k) if (combo[k] != 0) { sv.push_back(sub[k]); sa.push_back(combo[k]); }
+        if (sv.empty()) continue;
+        bool valid = true;                                                                                   // VariantSet.isValid :182-193
+        for (size_t k = 0; k + 1 < sv.size() && valid; ++k) if (sv[k]->pos <= sv[k + 1]->end() && sv[k + 1]->pos <= sv[k]->end()) valid = false;
+        if (valid) out.push_back(build_variant_window(sv, sa, ref_idx, ub, padding));
+      }
+    }
+  }
+  return out;
+}
+
+Str core_parameters_search(const calitas_search_options& o, const calitas_costs& c) {   // SearchReference.scala:496-508
+  const calitas_limits& l = o.limits;
+  const int maxtot = l.max_total_diffs >= 0 ? l.max_total_diffs : l.max_guide_diffs + l.max_gaps_between_guide_and_pam + l.max_pam_mismatches;
+  std::vector<Str> kv = { "max-variants=" + std::to_string(o.max_variants), "window-size=" + std::to_string(o.window_size), "max-guide-diffs=" + std::to_string(l.max_guide_diffs),
+    "max-pam-mismatches=" + std::to_string(l.max_pam_mismatches), "max-gaps-between-guide-and-pam=" + std::to_string(l.max_gaps_between_guide_and_pam),
+    "max-total-diffs=" + std::to_string(maxtot), "max-overlap=" + std::to_string(l.max_overlap), "guide-mismatch-net-cost=" + std::to_string(c.mismatch_net_cost),
+    "pam-mismatch-net-cost=" + std::to_string(c.pam_mismatch_net_cost), "genome-gap-net-cost=" + std::to_string(c.genome_gap_net_cost), "guide-gap-net-cost=" + std::to_string(c.guide_gap_net_cost) };
+  std::sort(kv.begin(), kv.end()); Str s; for (size_t i = 0; i < kv.size(); ++i) { if (i) s += ';'; s += kv[i]; } return s;
+}
+Str core_parameters_a2r(const calitas_a2r_options& o, const calitas_costs& c) {         // AlignToReference.scala:77-86
+  auto opt = [](int v) { return v >= 0 ? "Some(" + std::to_string(v) + ")" : Str("None"); };
+  std::vector<Str> kv = { "max-guide-diffs=" + opt(o.max_guide_diffs), "max-pam-mismatches=" + opt(o.max_pam_mismatches), "max-gaps-between-guide-and-pam=" + std::to_string(o.max_gaps_between_guide_and_pam),
+    "max-overlap=" + opt(o.max_overlap), "guide-mismatch-net-cost=" + std::to_string(c.mismatch_net_cost), "pam-mismatch-net-cost=" + std::to_string(c.pam_mismatch_net_cost),
+    "genome-gap-net-cost=" + std::to_string(c.genome_gap_net_cost), "guide-gap-net-cost=" + std::to_string(c.guide_gap_net_cost) };
+  std::sort(kv.begin(), kv.end()); Str s; for (size_t i = 0; i < kv.size(); ++i) { if (i) s += ';'; s += kv[i]; } return s;
+}
+
+Str render_rows(const std::vector<calitas_hit>& hits, const GuideDef& gd, const Str& chrom, const Str& target_fwd_base, int target_offset, const calitas_genome_view* genome) {
+  Str text = alignment_header();
+  for (auto& h : hits) {
+    Str fwd;
+    if (h.contig_idx >= 0) fwd = contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset);
+    else fwd = target_fwd_base.substr((size_t)(h.start_offset - target_offset), (size_t)(h.end_offset - h.start_offset));
+    Rendered r = render_hit(h, gd, fwd, false);
+    text += alignment_row(h, r, chrom);
+  }
+  return text;
+}
+
+}  // namespace
+
+extern "C" {
+
+int calitas_tool_align(calitas_engine* e, const calitas_guide* guide, const uint8_t* target, int32_t target_len, const char* target_name,
+                       int32_t target_offset, const calitas_limits* limits, char** out_text) {
+  return guarded([&]() -> int {
+    if (!e || !guide || !limits || !out_text || (target_len && !target)) bad("bad arguments");
+    *out_text = nullptr;
+    GuideDef gd = parse_guide(*guide);
+    calitas_target_task task{ 0, target, target_len, target_offset };
+    HitSet hs; ck(calitas_align_targets(e, 1, guide, 1, &task, limits, 0, &hs.h));
+    std::vector<calitas_hit> hits(hs.data(), hs.data() + hs.n());
+    *out_text = dup_text(render_rows(hits, gd, target_name ? target_name : "n/a", Str((const char*)target, (size_t)target_len), target_offset, nullptr));
+    return CALITAS_OK;
+  });
+}
+
+int calitas_tool_align_best(calitas_engine* e, const calitas_guide* guide, const uint8_t* target, int32_t target_len, int32_t max_gaps, char** out_text) {
+  return guarded([&]() -> int {
+    if (!e || !guide || !out_text || (target_len && !target)) bad("bad arguments");
+    *out_text = nullptr;
+    GuideDef gd = parse_guide(*guide);
+    calitas_limits lim{ 0, 0, max_gaps, -1, 0 };
+    calitas_target_task task{ 0, target, target_len, 0 };
+    HitSet hs; ck(calitas_align_targets(e, 1, guide, 1, &task, &lim, 1, &hs.h));
+    if (hs.n() == 0) throw ToolError{ CALITAS_ESTATE, "empty.maxBy" };                               // SequentialGuideAligner.scala:344
+    const calitas_hit* best = hs.data(); for (int64_t i = 1; i < hs.n(); ++i) if (hs.data()[i].score > best->score) best = hs.data() + i;   // maxBy keeps the first maximum
+    *out_text = dup_text(render_rows({ *best }, gd, "n/a", Str((const char*)target, (size_t)target_len), 0, nullptr));
+    return CALITAS_OK;
+  });
+}
+
+int calitas_tool_align_to_ref(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, const calitas_guide* guide, const char* chrom,
+                              int32_t pos, int32_t window_size, int32_t best, const calitas_limits* limits, char** out_text) {
+  return guarded([&]() -> int {
+    if (!e || !ref || !genome || !guide || !chrom || !limits || !out_text) bad("bad arguments");
+    *out_text = nullptr;
+    GuideDef gd = parse_guide(*guide);
+    const int ci = contig_index(*genome, chrom);
+    if (ci < 0) bad(Str("requirement failed: Unknown chromosome: ") + chrom);                        // SequentialGuideAligner.scala:370
+    const int padding = window_size >= 0 ? window_size / 2 : gd.length() * 2;                        // :372
+    const int64_t rs = std::max<int64_t>((int64_t)pos - padding, 1), re = std::min<int64_t>((int64_t)pos + padding, genome->lengths[ci]);   // :373
+    calitas_region_task task{ 0, ci, rs - 1, (int32_t)std::max<int64_t>(0, re - rs + 1) };
+    HitSet hs; ck(calitas_align_regions(e, ref, 1, guide, 1, &task, limits, best, &hs.h));
+    std::vector<calitas_hit> hits(hs.data(), hs.data() + hs.n());
+    sort_alignments(hits);                                                                           // :386
+    if (best) { if (hits.empty()) throw ToolError{ CALITAS_ESTATE, "head of empty list" }; hits.resize(1); }   // :417
+    *out_text = dup_text(render_rows(hits, gd, chrom, Str(), 0, genome));
+    return CALITAS_OK;
+  });
+}
+
+int calitas_tool_search_reference(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, const calitas_guide* guide,
+                                  const calitas_search_options* opt, char** out_tsv, int64_t* n_hits) {
+  return guarded([&]() -> int {
+    if (!e || !ref || !genome || !guide || !opt || !out_tsv) bad("bad arguments");
+    *out_tsv = nullptr;
+    GuideDef gd = parse_guide(*guide);
+    calitas_costs costs; ck(calitas_engine_get_costs(e, &costs));
+    RowContext cx; cx.genome = genome; cx.guide_id = opt->guide_id ? opt->guide_id : ""; cx.aligner_id = "CALITAS:SearchReference";
+    cx.arguments = core_parameters_search(*opt, costs); cx.time_stamp = opt->time_stamp ? opt->time_stamp : ""; cx.version = opt->aligner_version ? opt->aligner_version : "calitas-b200";
+    cx.has_vcf = opt->vcf_text != nullptr; cx.vcf_id = opt->vcf_id ? opt->vcf_id : "";
+    int chrom_idx = -1;
+    if (opt->chrom && opt->chrom[0]) { chrom_idx = contig_index(*genome, opt->chrom); if (chrom_idx < 0) bad(Str("Unknown chromosome: ") + opt->chrom); }
+    const bool with_vcf = opt->vcf_text != nullptr;
+    std::vector<Row> rows;
+    {  // reference windows: SearchReference.scala:527-564 (+ removeOverlaps/sort on the device when there is no VCF)
+      HitSet hs; ck(calitas_search(e, ref, 1, guide, &opt->limits, opt->window_size, opt->chrom, with_vcf ? 0 : 1, &hs.h));
+      const Flanks none;
+      for (int64_t i = 0; i < hs.n(); ++i) {
+        const calitas_hit& h = hs.data()[i];
+        Rendered r = render_hit(h, gd, contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), true);     // windows are upper-cased, SearchReference.scala:67
+        rows.push_back(make_row(cx, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none));
+      }
+    }
+    if (with_vcf) {  // SearchReference.scala:570-630
+      std::vector<VcfRecord> recs = parse_vcf(opt->vcf_text);
+      const int padding = gd.length() - 1 + opt->limits.max_guide_diffs + opt->limits.max_gaps_between_guide_and_pam;     // :575
+      std::vector<VariantWindow> windows = variant_windows(*genome, recs, chrom_idx, padding, opt->max_variants);
+      std::vector<calitas_target_task> tasks;
+      for (auto& w : windows) tasks.push_back(calitas_target_task{ 0, (const uint8_t*)w.bases.data(), (int32_t)w.bases.size(), 0 });
+      HitSet hs; if (!tasks.empty()) ck(calitas_align_targets(e, 1, guide, (int64_t)tasks.size(), tasks.data(), &opt->limits, 0, &hs.h));
+      for (int64_t i = 0; i < hs.n(); ++i) {
+        const calitas_hit& h = hs.data()[i]; const VariantWindow& w = windows[(size_t)h.task_idx];
+        Rendered r = render_hit(h, gd, w.bases.substr((size_t)h.start_offset, (size_t)(h.end_offset - h.start_offset)), false);
+        const int wl = (int)w.bases.size();
+        Flanks raw;   // window-orientation flanks (:599-602)
+        if (h.guide_start_offset >= 10) { raw.has[0] = true; raw.v[0] = w.bases.substr((size_t)h.guide_start_offset - 10, 10); }
+        if (wl - h.guide_end_offset >= 10) { raw.has[1] = true; raw.v[1] = w.bases.substr((size_t)h.guide_end_offset, 10); }
+        if (h.start_offset >= 8) { raw.has[2] = true; raw.v[2] = w.bases.substr((size_t)h.start_offset - 8, 8); }
+        if (wl - h.end_offset >= 8) { raw.has[3] = true; raw.v[3] = w.bases.substr((size_t)h.end_offset, 8); }
+        Flanks fl = raw;
+        if (h.strand == '-') {   // :604-612
+          fl.has[0] = raw.has[1]; fl.v[0] = revcomp(raw.v[1]); fl.has[1] = raw.has[0]; fl.v[1] = revcomp(raw.v[0]);
+          fl.has[2] = raw.has[3]; fl.v[2] = revcomp(raw.v[3]); fl.has[3] = raw.has[2]; fl.v[3] = revcomp(raw.v[2]);
+        }
+        const int so = w.ref_offset_at(h.start_offset, true), eo = w.ref_offset_at(h.end_offset, false);             // :615-620
+        const int gso = w.ref_offset_at(h.guide_start_offset, true), geo = w.ref_offset_at(h.guide_end_offset, false);
+        rows.push_back(make_row(cx, h, r, gd, w.contig, so, eo, gso, geo, w.alleles, fl));
+      }
+      rows = remove_overlaps_host(rows, opt->limits.max_overlap);                                                     // :641
+      sort_rows(rows);                                                                                                // :647
+    }
+    Str text = hit_header(); for (auto& r : rows) text += r.line;
+    if (n_hits) *n_hits = (int64_t)rows.size();
+    *out_tsv = dup_text(text);
+    return CALITAS_OK;
+  });
+}
+
+int calitas_tool_align_to_reference(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, int64_t n_tasks,
+                                    const calitas_a2r_task* tasks, const calitas_a2r_options* opt, char** out_tsv, int64_t* n_hits) {
+  return guarded([&]() -> int {
+    if (!e || !ref || !genome || !opt || !out_tsv || (n_tasks && !tasks)) bad("bad arguments");
+    *out_tsv = nullptr;
+    const int given = (opt->max_guide_diffs >= 0) + (opt->max_pam_mismatches >= 0) + (opt->max_overlap >= 0);
+    if (given != 0 && given != 3) bad("Must specify all or none of: --max-guide-diffs, --max-pam-mismatches, --max-overlap");   // AlignToReference.scala:88-92
+    const bool best = given == 0;
+    calitas_costs costs; ck(calitas_engine_get_costs(e, &costs));
+    RowContext cx; cx.genome = genome; cx.aligner_id = "CALITAS:AlignToReference"; cx.arguments = core_parameters_a2r(*opt, costs);
+    cx.time_stamp = opt->time_stamp ? opt->time_stamp : ""; cx.version = opt->aligner_version ? opt->aligner_version : "calitas-b200";
+    calitas_limits lim{ best ? 0 : opt->max_guide_diffs, best ? 0 : opt->max_pam_mismatches, opt->max_gaps_between_guide_and_pam,
+                        best ? -1 : (opt->max_total_diffs >= 0 ? opt->max_total_diffs : opt->max_guide_diffs + opt->max_gaps_between_guide_and_pam + opt->max_pam_mismatches),
+                        best ? 0 : opt->max_overlap };
+    Str text = hit_header(); int64_t total = 0;
+    const Flanks none;
+    for (int64_t b0 = 0; b0 < n_tasks; b0 += 10000) {                                                 // AlignToReference.scala:110
+      const int64_t b1 = std::min<int64_t>(n_tasks, b0 + 10000);
+      // distinct query strings of the batch share one device guide descriptor
+      std::map<Str, int> guide_of; std::vector<Str> queries; std::vector<GuideDef> defs;
+      std::vector<calitas_region_task> rt; std::vector<int64_t> task_of;
+      for (int64_t i = b0; i < b1; ++i) {
+        const calitas_a2r_task& t = tasks[i];
+        if (!t.query || !t.chrom) bad("task query/chrom is NULL");
+        auto it = guide_of.find(t.query);
+        if (it == guide_of.end()) { it = guide_of.emplace(t.query, (int)queries.size()).first; queries.push_back(t.query); defs.push_back(parse_guide(t.query, {})); }   // :112
+        const GuideDef& gd = defs[(size_t)it->second];
+        const int ci = contig_index(*genome, t.chrom);
+        if (ci < 0) bad(Str("requirement failed: Unknown chromosome: ") + t.chrom);
+        const int padding = opt->window_size >= 0 ? opt->window_size / 2 : gd.length() * 2;
+        const int64_t rs = std::max<int64_t>((int64_t)t.position - padding, 1), re = std::min<int64_t>((int64_t)t.position + padding, genome->lengths[ci]);
+        rt.push_back(calitas_region_task{ it->second, ci, rs - 1, (int32_t)std::max<int64_t>(0, re - rs + 1) }); task_of.push_back(i);
+      }
+      std::vector<calitas_guide> cg; for (auto& q : queries) cg.push_back(calitas_guide{ q.c_str(), nullptr, 0 });
+      HitSet hs; ck(calitas_align_regions(e, ref, (int32_t)cg.size(), cg.data(), (int64_t)rt.size(), rt.data(), &lim, best ? 1 : 0, &hs.h));
+      // hits arrive grouped by task in retval order; apply `.sorted` (+ `.head` in best mode) per task, then ReferenceHit.sort per batch (:141)
+      std::vector<Row> rows;
+      for (int64_t i = 0; i < hs.n();) {
+        int64_t j = i; while (j < hs.n() && hs.data()[j].task_idx == hs.data()[i].task_idx) ++j;
+        std::vector<calitas_hit> alns(hs.data() + i, hs.data() + j); sort_alignments(alns);
+        if (best) alns.resize(1);
+        const int64_t ti = task_of[(size_t)hs.data()[i].task_idx]; const GuideDef& gd = defs[(size_t)rt[(size_t)hs.data()[i].task_idx].guide_idx];
+        RowContext c2 = cx; c2.guide_id = tasks[ti].id ? tasks[ti].id : tasks[ti].query;                // :100
+        for (auto& h : alns) {
+          Rendered r = render_hit(h, gd, contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), false);   // region is not upper-cased (SequentialGuideAligner.scala:374)
+          rows.push_back(make_row(c2, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none));
+        }
+        i = j;
+      }
+      if (best) {   // alignToRefBest(...).head on an empty result throws in the reference
+        std::vector<char> seen(rt.size(), 0); for (int64_t i = 0; i < hs.n(); ++i) seen[(size_t)hs.data()[i].task_idx] = 1;
+        for (size_t k = 0; k < seen.size(); ++k) if (!seen[k]) throw ToolError{ CALITAS_ESTATE, Str("head of empty list: no alignment for query ") + tasks[task_of[k]].query };
+      }
+      sort_rows(rows);
+      for (auto& r : rows) text += r.line;
+      total += (int64_t)rows.size();
+    }
+    if (n_hits) *n_hits = total;
+    *out_tsv = dup_text(text);
+    return CALITAS_OK;
+  });
+}
+
+int calitas_tool_variant_windows(const calitas_genome_view* genome, const char* vcf_text, const char* chrom, int32_t padding, int32_t max_variants, char** out_text) {
+  return guarded([&]() -> int {
+    if (!genome || !vcf_text || !out_text) bad("bad arguments");
+    *out_text = nullptr;
+    int chrom_idx = -1; if (chrom && chrom[0]) { chrom_idx = contig_index(*genome, chrom); if (chrom_idx < 0) bad(Str("Unknown chromosome: ") + chrom); }
+    std::vector<VcfRecord> recs = parse_vcf(vcf_text);
+    Str text;
+    for (auto& w : variant_windows(*genome, recs, chrom_idx, padding, max_variants)) {
+      text += Str(genome->names[w.contig]) + "\t" + std::to_string(w.start) + "\t" + w.cigar_text() + "\t" + w.bases + "\t";
+      for (size_t i = 0; i < w.alleles.size(); ++i) { if (i) text += ';'; text += variant_display(w.alleles[i]); }
+      text += '\n';
+    }
+    *out_text = dup_text(text);
+    return CALITAS_OK;
+  });
+}
+
+}  // extern "C"

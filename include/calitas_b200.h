@@ -1,0 +1,151 @@
+/*
+ * calitas_b200.h — C ABI of the B200-native CALITAS off-target search engine.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference (Scala/JVM) has no FFI of its
+ * own; the functions below are what a JNI/Panama shim would bind in place of the calls cited beside each one
+ * (reference files under calitas/src/main/scala/com/editasmedicine/aligner/; see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success and a non-zero CALITAS_E* code on failure; the message is
+ *     available from calitas_last_error() (thread-local) — the JVM side rethrows it as
+ *     IllegalArgumentException (CALITAS_EINVAL, mirrors the reference's `require`) or IllegalStateException;
+ *   - plain pointers and sizes only; the caller owns every input for the duration of the call, the engine
+ *     copies what it keeps; result sets are owned by the engine until *_free;
+ *   - coordinates are 0-based half-open, as in GuideAlignment.scala:60-63;
+ *   - one engine may be used from one host thread at a time; engines are independent (one per GPU);
+ *   - there is no CPU fallback: every entry point that computes fails with CALITAS_ECUDA without a device.
+ */
+#ifndef CALITAS_B200_H
+#define CALITAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CALITAS_OK      0
+#define CALITAS_EINVAL  1   /* bad argument: mirrors the reference's require()/validate() failures */
+#define CALITAS_ECUDA   2   /* CUDA runtime / device failure, or no device */
+#define CALITAS_ELIMIT  3   /* input exceeds a documented engine limit (protospacer > 32 nt, PAM > 16 nt, > 8 PAMs, ...) */
+#define CALITAS_ESTATE  4   /* wrong call order / unknown handle */
+
+#define CALITAS_MAX_PROTOSPACER 32
+#define CALITAS_MAX_PAM_LEN     16
+#define CALITAS_MAX_PAMS        8
+#define CALITAS_MAX_OPS         128   /* alignment columns per hit */
+
+typedef struct calitas_engine calitas_engine;
+typedef struct calitas_reference calitas_reference;
+typedef struct calitas_hitset calitas_hitset;
+
+/* Net costs, SequentialGuideAligner.scala:17-21,170-175 (either sign accepted, :193-198). */
+typedef struct calitas_costs {
+  int32_t mismatch_net_cost;      /* -m, default -120 */
+  int32_t genome_gap_net_cost;    /* -b, default -122 */
+  int32_t guide_gap_net_cost;     /* -B, default -121 */
+  int32_t pam_mismatch_net_cost;  /* -M, default -260 */
+} calitas_costs;
+
+/* Limits of one SequentialGuideAligner.align call (SequentialGuideAligner.scala:228-236). */
+typedef struct calitas_limits {
+  int32_t max_guide_diffs;                 /* -d */
+  int32_t max_pam_mismatches;              /* -p */
+  int32_t max_gaps_between_guide_and_pam;  /* -g */
+  int32_t max_total_diffs;                 /* -D; < 0 means d + g + p (SearchReference.scala:493) */
+  int32_t max_overlap;                     /* -O */
+} calitas_limits;
+
+/* One guide: "PROTOSPACERpam" / "pamPROTOSPACER" / "PROTOSPACER" plus auxiliary PAMs (Guide.apply, SequentialGuideAligner.scala:81-107). */
+typedef struct calitas_guide {
+  const char* sequence;
+  const char* const* aux_pams;
+  int32_t n_aux_pams;
+} calitas_guide;
+
+/* One alignment: the POD image of GuideAlignment (GuideAlignment.scala:72-88).  Strings (padded guide / alignment /
+ * target, cigar text, the derived counters of GuideAlignment.scala:99-163) are rendered on the host from `ops`
+ * and the reference bases by calitas_render_*; ops are in guide orientation, 2 bits per alignment column:
+ * 0 '=', 1 'X', 2 'I' (guide base opposite a genome gap), 3 'D' (genome base opposite a guide gap). */
+typedef struct calitas_hit {
+  int32_t guide_idx;          /* index into the guides array of the call */
+  int32_t pam_idx;            /* index into that guide's PAM list (primary = 0); -1 for a PAM-less guide */
+  int32_t contig_idx;         /* contig of the loaded reference; -1 for calitas_align_targets */
+  int32_t task_idx;           /* window index (search) or task index (align_regions / align_targets) */
+  int32_t start_offset;       /* guide+PAM span */
+  int32_t end_offset;
+  int32_t guide_start_offset; /* protospacer-only span: coordinate_start / coordinate_end of ReferenceHit.scala:223-224 */
+  int32_t guide_end_offset;
+  int32_t score;
+  uint8_t strand;             /* '+' or '-' */
+  uint8_t n_ops;
+  uint8_t gap_bases;          /* GuideAlignment.gapBases */
+  uint8_t edits;              /* GuideAlignment.edits */
+  uint32_t ops[CALITAS_MAX_OPS / 16];
+} calitas_hit;
+
+/* ---- engine ------------------------------------------------------------------------------------------- */
+/* Replaces `new SequentialGuideAligner(costs)` (SearchReference.scala:486-491, AlignToReference.scala:64-70). */
+int calitas_engine_create(int32_t device_id, const calitas_costs* costs, calitas_engine** out);
+void calitas_engine_destroy(calitas_engine* e);
+int calitas_engine_get_costs(const calitas_engine* e, calitas_costs* out);
+const char* calitas_last_error(void);
+
+/* ---- reference loading and packing ------------------------------------------------------------------------
+ * Replaces SearchReference.windowIterator's per-contig byte arrays (SearchReference.scala:39-49) and the indexed
+ * FASTA behind alignToRef (SequentialGuideAligner.scala:369-374).  Contig c has total length lengths[c]; this engine
+ * is given bases[c][0 .. have_end[c]-have_begin[c]) = contig bases [have_begin[c], have_end[c]) and owns the reference
+ * windows whose nominal start lies in [own_begin[c], own_end[c]).  Pass NULL for the four range arrays to load and own
+ * everything (single GPU).  The bytes are uploaded, then packed on the device to 4-bit IUPAC-set codes. */
+int calitas_reference_load(calitas_engine* e, int32_t n_contigs, const char* const* names, const int64_t* lengths,
+                           const uint8_t* const* bases, const int64_t* have_begin, const int64_t* have_end,
+                           const int64_t* own_begin, const int64_t* own_end, int32_t keep_raw, calitas_reference** out);
+void calitas_reference_free(calitas_engine* e, calitas_reference* r);
+/* Contiguous split of the genome into n_shards base ranges for contig-range sharding: fills, for `shard`,
+ * own_begin/own_end per contig (window starts owned) and have_begin/have_end (bases needed, incl. a halo of `halo` bases). */
+int calitas_shard_plan(int32_t n_contigs, const int64_t* lengths, int32_t shard, int32_t n_shards, int64_t halo,
+                       int64_t* own_begin, int64_t* own_end, int64_t* have_begin, int64_t* have_end);
+
+/* ---- SearchReference hot path ---------------------------------------------------------------------------------
+ * Replaces the window loop of SearchReference.execute (SearchReference.scala:527-564): windowIterator + one
+ * SequentialGuideAligner.align per window, for every guide of the batch, then (dedup != 0) removeOverlaps + ReferenceHit.sort
+ * (SearchReference.scala:641-648, 653-675; ReferenceHit.scala:276-287).  chrom may be NULL (all contigs, -c absent). */
+int calitas_search(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
+                   const calitas_limits* limits, int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out);
+
+/* ---- AlignToReference / variant windows -----------------------------------------------------------------------
+ * One SequentialGuideAligner.align per task (SequentialGuideAligner.scala:228), batched.  best != 0 applies the
+ * alignBest/alignToRefBest limits per guide (SequentialGuideAligner.scala:336-343, 407-417: d = protospacer length,
+ * p = PAM length, maxTotal = d + g + p, maxOverlap = 0) and `limits` supplies only max_gaps_between_guide_and_pam. */
+typedef struct calitas_region_task { int32_t guide_idx; int32_t contig_idx; int64_t start; int32_t length; } calitas_region_task;        /* alignToRef: bases [start, start+length) */
+typedef struct calitas_target_task { int32_t guide_idx; const uint8_t* bases; int32_t length; int32_t target_offset; } calitas_target_task; /* align(guide, target, targetOffset) */
+int calitas_align_regions(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
+                          int64_t n_tasks, const calitas_region_task* tasks, const calitas_limits* limits, int32_t best, calitas_hitset** out);
+int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_guide* guides,
+                          int64_t n_tasks, const calitas_target_task* tasks, const calitas_limits* limits, int32_t best, calitas_hitset** out);
+
+/* ---- result sets ---------------------------------------------------------------------------------------------
+ * Hits are ordered as the reference would emit them: search with dedup: ReferenceHit.sort order per guide;
+ * otherwise by (guide, window/task, '+' before '-', rank in the per-window retval of SequentialGuideAligner.scala:315-322). */
+int64_t calitas_hitset_count(const calitas_hitset* h);
+const calitas_hit* calitas_hitset_data(const calitas_hitset* h);   /* pinned host memory, valid until free */
+void calitas_hitset_free(calitas_hitset* h);
+/* Timings of the call that produced the set, in milliseconds of device time (CUDA events): [0] total, [1] scan kernel,
+ * [2] align kernel, [3] sort+canonicalise+dedup; counts: [0] windows, [1] candidate end columns, [2] alignments before
+ * canonicalisation, [3] launches. */
+int calitas_hitset_stats(const calitas_hitset* h, double ms[4], int64_t counts[4]);
+
+/* ---- host-side rendering (ReferenceHit.Builder.build, ReferenceHit.scala:210-254; GuideAlignment.scala:10-50,99-163) ---- */
+/* Renders hits as tab-separated GuideAlignment rows (same columns as oracle_alignment_header()).  `contig_bases[c]` must
+ * point at base 0 of contig c (NULL allowed for contigs without hits); for align_targets pass the task bases through
+ * `target_bases[task]` instead.  upper_case != 0 upper-cases target bases (SearchReference windows, SearchReference.scala:67).
+ * *out_text is malloc'd; release with calitas_free_text. */
+int calitas_render_alignments(const calitas_hit* hits, int64_t n_hits, int32_t n_guides, const calitas_guide* guides,
+                              int32_t n_contigs, const char* const* names, const uint8_t* const* contig_bases,
+                              const calitas_target_task* targets, int32_t upper_case, char** out_text);
+void calitas_free_text(char* text);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,66 @@
+/*
+ * calitas_b200_tools.h — host-side mirror of the reference's operator interface, on top of the C ABI in calitas_b200.h.
+ *
+ * These entry points keep the names, argument meaning and error behaviour of the reference operators so that a JVM shim, the
+ * `calitas` CLI in this repo and the parity tests all drive the GPU engine the way the reference drives its CPU aligner:
+ *   calitas_tool_align              SequentialGuideAligner.align          (SequentialGuideAligner.scala:228-323)
+ *   calitas_tool_align_best         SequentialGuideAligner.alignBest      (:333-345)
+ *   calitas_tool_align_to_ref       alignToRef / alignToRefBest           (:359-418)
+ *   calitas_tool_search_reference   SearchReference.execute               (SearchReference.scala:513-649)
+ *   calitas_tool_align_to_reference AlignToReference.execute              (AlignToReference.scala:95-147)
+ * All computation of alignments happens on the device through calitas_search / calitas_align_regions / calitas_align_targets;
+ * this layer parses, builds windows for variants, renders text and (for VCF runs) merges reference and variant hits.
+ * Text results are malloc'd; release with calitas_free_text.  Alignment rows use the columns of calitas_render_alignments;
+ * hit tables are the reference's 34-column TSV (ReferenceHit.scala:99-132) with a header line.
+ */
+#ifndef CALITAS_B200_TOOLS_H
+#define CALITAS_B200_TOOLS_H
+#include "calitas_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Host view of the genome the engine's reference was loaded from (caller-owned, full contigs): needed to render target
+ * strings and flanks (ReferenceHit.scala:213-216, 261-266).  assembly = first AS of the .dict or NULL ("unknown"). */
+typedef struct calitas_genome_view {
+  int32_t n_contigs; const char* const* names; const int64_t* lengths; const uint8_t* const* bases; const char* assembly;
+} calitas_genome_view;
+
+int calitas_tool_align(calitas_engine* e, const calitas_guide* guide, const uint8_t* target, int32_t target_len, const char* target_name,
+                       int32_t target_offset, const calitas_limits* limits, char** out_text);
+int calitas_tool_align_best(calitas_engine* e, const calitas_guide* guide, const uint8_t* target, int32_t target_len,
+                            int32_t max_gaps_between_guide_and_pam, char** out_text);
+/* window_size < 0: None (2 x guide length each side).  best != 0: alignToRefBest (one row). */
+int calitas_tool_align_to_ref(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, const calitas_guide* guide,
+                              const char* chrom, int32_t pos, int32_t window_size, int32_t best, const calitas_limits* limits, char** out_text);
+
+typedef struct calitas_search_options {      /* SearchReference.scala:452-470 */
+  const char* guide_id;                      /* -I */
+  int32_t max_variants;                      /* -V, default 16 */
+  int32_t window_size;                       /* -w, default 1000 */
+  calitas_limits limits;                     /* -d -p -g -D -O */
+  const char* chrom;                         /* -c or NULL */
+  const char* vcf_text;                      /* -v: contents of the (plain-text) VCF, or NULL */
+  const char* vcf_id;                        /* "<file name>:<md5>" (ReferenceHit.scala:175-183) */
+  const char* time_stamp;                    /* run-dependent column; NULL -> empty */
+  const char* aligner_version;               /* run-dependent column; NULL -> "calitas-b200" */
+} calitas_search_options;
+int calitas_tool_search_reference(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, const calitas_guide* guide,
+                                  const calitas_search_options* opt, char** out_tsv, int64_t* n_hits);
+
+typedef struct calitas_a2r_task { const char* id; const char* query; const char* chrom; int32_t position; } calitas_a2r_task;   /* AlignToReference.scala:97-102 */
+typedef struct calitas_a2r_options {         /* AlignToReference.scala:35-50; -1 = not given */
+  int32_t window_size, max_guide_diffs, max_pam_mismatches, max_gaps_between_guide_and_pam, max_total_diffs, max_overlap;
+  const char* time_stamp; const char* aligner_version;
+} calitas_a2r_options;
+int calitas_tool_align_to_reference(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, int64_t n_tasks,
+                                    const calitas_a2r_task* tasks, const calitas_a2r_options* opt, char** out_tsv, int64_t* n_hits);
+
+/* Inspection hook for the variant path (SearchReference.scala:217-399): one line per variant window
+ * "chrom \t start \t cigar \t bases \t id:pos:ref>alt;..." in iterator order. */
+int calitas_tool_variant_windows(const calitas_genome_view* genome, const char* vcf_text, const char* chrom, int32_t padding, int32_t max_variants, char** out_text);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

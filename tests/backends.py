@@ -36,11 +36,20 @@ class OracleBackend:
 
 
 class GpuBackend:
-    name = "gpu"
+    """name == "gpu": the product library on a CUDA device.  name == "hostsim": the same engine sources compiled for the host
+    by tests/hostsim (test-only; checks the engine's logic where no GPU exists)."""
 
-    def __init__(self):
+    def __init__(self, name="gpu"):
         import calitas_b200.testing as t
-        self.t = t
+        from calitas_b200._capi import Library
+        self.name = name
+        if name == "hostsim":
+            import subprocess
+            d = os.path.join(ROOT, "tests", "hostsim")
+            subprocess.check_call(["make", "-C", d, "-s"])
+            self.t = t.Facade(Library(os.path.join(d, "_build", "libcalitas_hostsim.so")))
+        else:
+            self.t = t.Facade()
 
     def align(self, guide, target, **kw):
         return self.t.align(guide, target, **kw)
@@ -66,5 +75,5 @@ _cache = {}
 
 def get(name):
     if name not in _cache:
-        _cache[name] = OracleBackend() if name == "oracle" else GpuBackend()
+        _cache[name] = OracleBackend() if name == "oracle" else GpuBackend(name)
     return _cache[name]

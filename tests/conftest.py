@@ -34,7 +34,7 @@ def sga_ref():
     return read_fasta(os.path.join(ROOT, "tests", "golden", "sga_test_ref.fa"))
 
 
-@pytest.fixture(scope="session", params=["oracle", pytest.param("gpu", marks=pytest.mark.gpu)])
+@pytest.fixture(scope="session", params=["oracle", "hostsim", pytest.param("gpu", marks=pytest.mark.gpu)])
 def backend(request):
     """The same reference-test bodies run against the CPU oracle (here) and against the CUDA engine through its C ABI (-m gpu)."""
     import backends
