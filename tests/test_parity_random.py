@@ -1,0 +1,163 @@
+"""Engine-vs-oracle parity on seeded synthetic inputs (SURVEY.md 8d shapes, reduced sizes): every column of every row must be identical.
+Runs against the host simulation here (-m "not gpu") and against the CUDA library on the B200 (-m gpu)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import pyoracle
+from calitas_b200 import synth
+
+ENGINES = ["hostsim", pytest.param("gpu", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(scope="module", params=ENGINES)
+def eng(request):
+    import backends
+    return backends.get(request.param)
+
+
+def rc(s):
+    return synth.revcomp_bytes(s.encode()).decode()
+
+
+IUPAC = "ACGTRYSWKMBDHVN"
+
+
+def random_case(rng):
+    lp = int(rng.integers(6, 25))
+    alphabet = IUPAC if rng.random() < 0.25 else "ACGT"
+    proto = "".join(rng.choice(list(alphabet), size=lp))
+    kind = rng.integers(0, 4)
+    pams = ["".join(rng.choice(list("acgtnryv"), size=int(rng.integers(1, 6)))) for _ in range(int(rng.integers(1, 4)))]
+    if kind == 0:
+        guide, aux = proto, []
+    elif kind == 1:
+        guide, aux = proto + pams[0], pams[1:]
+    elif kind == 2:
+        guide, aux = pams[0] + proto, pams[1:]
+    else:
+        guide, aux = proto + pams[0], []
+    # target: random background with 1-3 mutated copies of the site, sometimes N runs / lower case / IUPAC
+    tlen = int(rng.integers(lp, 160))
+    t = list(rng.choice(list("ACGT"), size=tlen))
+    concrete = "".join(c if c in "ACGT" else "ACGT"[int(rng.integers(0, 4))] for c in proto)
+    for _ in range(int(rng.integers(0, 4))):
+        site = synth.mutate_protospacer(rng, concrete.encode(), int(rng.integers(0, 4))).decode()
+        site = site + "".join(rng.choice(list("ACGT"), size=int(rng.integers(0, 3)))) + "".join(rng.choice(list("ACGT"), size=3))
+        if kind == 2:
+            site = site[::-1]
+        if rng.random() < 0.5:
+            site = rc(site)
+        if len(site) <= tlen:
+            p = int(rng.integers(0, tlen - len(site) + 1))
+            t[p:p + len(site)] = list(site)
+    t = t[:tlen]
+    if rng.random() < 0.3:
+        p = int(rng.integers(0, tlen)); n = int(rng.integers(1, 8))
+        for q in range(p, min(tlen, p + n)):
+            t[q] = "N"
+    if rng.random() < 0.2:
+        t[int(rng.integers(0, tlen))] = str(rng.choice(list("RYMKnacgt")))
+    target = "".join(t)
+    d = int(rng.integers(0, 5)); p_ = int(rng.integers(0, 3)); g = int(rng.integers(0, 4))
+    D = None if rng.random() < 0.5 else int(rng.integers(0, d + p_ + g + 1))
+    return guide, aux, target, dict(max_guide_diffs=d, max_pam_diffs=p_, max_gaps=g, max_total_diffs=(d + g + p_ if D is None else D),
+                                    max_overlap=int(rng.choice([0, 5, 10, 100])), target_offset=int(rng.integers(0, 1000)))
+
+
+def test_align_random_cases(eng):
+    rng = np.random.default_rng(7)
+    n = 400 if eng.name == "hostsim" else 150
+    for k in range(n):
+        guide, aux, target, kw = random_case(rng)
+        exp = pyoracle.align(guide, target, aux_pams=aux, **kw)
+        got = eng.align(guide, target, aux_pams=aux, **kw)
+        assert got == exp, (k, guide, aux, target, kw)
+
+
+def test_align_best_random_cases(eng):
+    rng = np.random.default_rng(8)
+    n = 150 if eng.name == "hostsim" else 60
+    for k in range(n):
+        guide, aux, target, kw = random_case(rng)
+        if len(target) < 4:
+            continue
+        try:
+            exp = pyoracle.align_best(guide, target, aux_pams=aux, max_gaps=kw["max_gaps"])
+        except pyoracle.OracleError:
+            with pytest.raises(Exception):
+                eng.align_best(guide, target, aux_pams=aux, max_gaps=kw["max_gaps"])
+            continue
+        got = eng.align_best(guide, target, aux_pams=aux, max_gaps=kw["max_gaps"])
+        assert got == exp, (k, guide, aux, target)
+
+
+def test_non_default_costs(eng):
+    rng = np.random.default_rng(9)
+    for costs in [(-100, -130, -110, -200), (-120, -121, -122, -260), (90, 95, 100, 300)]:
+        for k in range(40):
+            guide, aux, target, kw = random_case(rng)
+            exp = pyoracle.align(guide, target, aux_pams=aux, costs=costs, **kw)
+            got = eng.align(guide, target, aux_pams=aux, costs=costs, **kw)
+            assert got == exp, (costs, k, guide, aux, target, kw)
+
+
+@pytest.fixture(scope="module")
+def small_genome():
+    g = synth.config1_genome(scale=0.03, n_sites=60)
+    return g, [(n, bytes(b)) for n, b in g.contigs()]
+
+
+def _lines(text):
+    return [l for l in text.split("\n") if l]
+
+
+def test_search_reference_defaults(eng, small_genome):
+    g, contigs = small_genome
+    exp = _lines(pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, guide_id="g1", raw=True, assembly="SYN10M"))
+    got = _lines(eng.search_reference(contigs, synth.BASELINE_GUIDE, guide_id="g1", raw=True, assembly="SYN10M"))
+    assert len(exp) > 40
+    assert got == exp
+
+
+@pytest.mark.parametrize("guide,aux,kw", [
+    ("CTTGCCCCACAGGGCAGTAAngg", ["nag"], dict(d=6, g=2, p=1)),
+    ("CTTGCCCCACAGGGCAGTAA", [], dict(d=6, g=2, p=1)),
+    ("tttvCTTGCCCCACAGGGCAGTAA", [], dict(d=4, g=1, p=1, O=0)),
+    ("CTTGCCCCACAGGGCAGTAAnrg", [], dict(d=3, g=3, p=2, D=4, window_size=300, O=100)),
+])
+def test_search_reference_variants_of_the_call(eng, small_genome, guide, aux, kw):
+    g, contigs = small_genome
+    exp = _lines(pyoracle.search_reference(contigs, guide, aux_pams=aux, raw=True, **kw))
+    got = _lines(eng.search_reference(contigs, guide, aux_pams=aux, raw=True, **kw))
+    assert got == exp
+
+
+def test_search_single_chrom(eng, small_genome):
+    g, contigs = small_genome
+    exp = _lines(pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, chrom="chr2", raw=True))
+    got = _lines(eng.search_reference(contigs, synth.BASELINE_GUIDE, chrom="chr2", raw=True))
+    assert got == exp and len(exp) > 5
+
+
+def test_search_reference_with_vcf(eng, small_genome):
+    g, contigs = small_genome
+    arrays = [np.frombuffer(b, dtype=np.uint8) for _, b in contigs]
+    vcf = synth.synthetic_vcf(g, arrays, 600)
+    exp = _lines(pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, vcf_text=vcf, raw=True))
+    got = _lines(eng.search_reference(contigs, synth.BASELINE_GUIDE, vcf_text=vcf, raw=True))
+    assert got == exp
+    assert any("+variants" in l for l in exp)
+
+
+def test_align_to_reference(eng, small_genome):
+    g, contigs = small_genome
+    guides = [synth.BASELINE_GUIDE] + synth.random_guides(3)
+    tasks = synth.a2r_tasks(g, guides, 120)
+    for kw in (dict(window_size=60), dict(window_size=60, d=5, p=1, O=10), dict()):
+        exp = _lines(pyoracle.align_to_reference(contigs, tasks, raw=True, **kw))
+        got = _lines(eng.align_to_reference(contigs, tasks, raw=True, **kw))
+        assert got == exp, kw
