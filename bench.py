@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: SearchReference throughput in Gbp*guides/s on a synthetic hg38-sized genome.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (CPU arm: the oracle restatement of the reference on the host cores)
+
+One step = one calitas_search call (include/calitas_b200.h) of G guides against this rank's contig-range shard of the 3.1-Gbp genome:
+guides go host->device, every kernel of the path runs (scan, sort, align, canonicalise, removeOverlaps + sort), final hit records
+come device->host.  Shards are independent: no collective on the data path.
+  value  = genome bp x guides / device time of the step (CUDA events on the engine's stream, max over ranks)
+  e2e    = same, wall clock around the C-ABI call with host buffers (guide strings in, hit records out), max over ranks
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS_PER_COLUMN = 17          # integer instructions of one Myers column update incl. threshold test (kernel k_scan_tiled)
+REF_OPS_PER_BP_GUIDE = 240   # 2 strands x 20 rows x 6 int32 ops of the reference's recurrence
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--guides", type=int, default=100, help="guides per step (north_star: 100 guides, defaults d=5 p=1 g=3)")
+    ap.add_argument("--scale", type=float, default=1.0, help="genome scale; 1.0 = 3.1 Gbp with hg38 contig lengths")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def guide_list(n):
+    from calitas_b200 import synth
+    return [synth.BASELINE_GUIDE] + synth.random_guides(max(0, n - 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)})
+        return out
+
+
+def cpu_sample(genome, guides, threads, target_seconds, sample_bp=8_000_000):
+    """Times the oracle (C++ restatement of the reference algorithm, oracle/) on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    pyoracle.build()
+    # sample: the first contig's bases after the telomere N block
+    length = min(genome.lengths[0], sample_bp + 20000)
+    bases = bytes(genome.range(0, 0, length))
+    contigs = [(genome.names[0], bases)]
+    done, t_total, n_hits = 0, 0.0, 0
+    t0 = time.perf_counter()
+    while done < len(guides) and (done == 0 or t_total < target_seconds):
+        n, _ = pyoracle.search_reference_count(contigs, guides[done], threads=threads)
+        n_hits += n
+        done += 1
+        t_total = time.perf_counter() - t0
+    value = len(bases) * done / t_total / 1e9
+    return {"value": value, "unit": "Gbp*guides/s", "cores": threads, "kind": "port",
+            "sample": "%d guide(s) x first %.1f Mbp of %s, same windows/limits, %d threads, %.1f s; C++ restatement of the reference algorithm (the JVM reference cannot run here)"
+                      % (done, len(bases) / 1e6, genome.names[0], threads, t_total), "hits": n_hits}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from calitas_b200 import synth
+    guides = guide_list(args.guides)
+    genome = synth.hg38_like_genome(args.scale, guides=guides, sites_per_guide=200)
+    threads = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    pyoracle.build()
+    sample_bp = 4_000_000
+    length = min(genome.lengths[0], sample_bp + 20000)
+    contigs = [(genome.names[0], bytes(genome.range(0, 0, length)))]
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pyoracle.search_reference_count(contigs, guides[it % len(guides)], threads=threads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = length / (ms * 1e-3) / 1e9
+    sample = "each step: 1 guide x first %.1f Mbp of %s (bounded sample of the workload), oracle C++ restatement, %d host threads" % (length / 1e6, genome.names[0], threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "Gbp*guides/s SearchReference (hg38-size synthetic)", "value": value, "unit": "Gbp*guides/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": workload_config(args, genome),
+        "cpu_baseline": {"value": value, "unit": "Gbp*guides/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gbp*guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, genome):
+    return {"workload": "SearchReference, %d guides (CTTGCCCCACAGGGCAGTAAnrg + random 20-mers, nrg) vs %.2f Gbp synthetic hg38-sized genome (24 contigs), "
+                        "defaults d=5 p=1 g=3 O=10 w=1000, contig-range sharded" % (args.guides, genome.total() / 1e9),
+            "guides_per_step": args.guides, "genome_bp": genome.total(), "window_size": 1000, "max_guide_diffs": 5, "max_pam_mismatches": 1,
+            "max_gaps_between_guide_and_pam": 3, "max_overlap": 10, "dedup": "removeOverlaps+sort on device",
+            "l2": "inputs larger than L2 (packed reference shard per scan launch >> 126 MB)", "parallelism": "contig-range shards, 1 rank per GPU, no collective"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from calitas_b200 import synth
+    from calitas_b200._capi import Engine, Limits
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    guides = guide_list(args.guides)
+    genome = synth.hg38_like_genome(args.scale, guides=guides, sites_per_guide=200)
+    n = len(genome.lengths)
+    engine = Engine(local_rank)
+
+    # ---- this rank's contig-range shard: generate only the bases it holds ------------------------------------------------------
+    import ctypes as C
+    L = (C.c_int64 * n)(*genome.lengths)
+    ob, oe, hb, he = [(C.c_int64 * n)() for _ in range(4)]
+    halo = 4 * 1000
+    engine.lib.check(engine.lib.L.calitas_shard_plan(n, L, rank, world, C.c_int64(halo), ob, oe, hb, he))
+    t0 = time.perf_counter()
+    arrays = [genome.range(c, hb[c], he[c]) if he[c] > hb[c] else None for c in range(n)]
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = engine.load_reference_ranges(genome.names, genome.lengths, [(hb[c], he[c]) for c in range(n)], [(ob[c], oe[c]) for c in range(n)], arrays)
+    t_load = time.perf_counter() - t0
+    own_bp = sum(oe[c] - ob[c] for c in range(n))
+    del arrays
+    lim = Limits(5, 1, 3, -1, 10)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        t0 = time.perf_counter()
+        hs = engine.search(ref, guides, lim, window_size=1000, dedup=True)
+        wall = time.perf_counter() - t0
+        st = hs.stats()
+        st["hits"] = len(hs)
+        st["wall_ms"] = wall * 1e3
+        hs.free()
+        return st
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_begin = time.perf_counter()
+    stats = [step() for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_local = time.perf_counter() - t_begin
+    barrier()
+    clocks = sampler.stop()
+
+    dev_ms = sum(s["ms_total"] for s in stats) / args.steps        # CUDA events, whole step on the device incl. D2H of hits
+    wall_ms = 1e3 * t_local / args.steps
+    scan_ms = sum(s["ms_scan"] for s in stats) / args.steps
+    red = torch.tensor([dev_ms, wall_ms, scan_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(stats[-1]["hits"]), float(own_bp), float(stats[-1]["candidates"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max, scan_ms_max = [float(x) for x in red.tolist()]
+    total_hits, total_bp, total_cand = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        G = len(guides)
+        bpg = genome.total() * G
+        value = bpg / (dev_ms_max * 1e-3) / 1e9
+        e2e = bpg / (wall_ms_max * 1e-3) / 1e9
+        st = stats[-1]
+        # dominant kernel: k_scan_tiled (rank 0's launches)
+        launches = max(1, st["scan_launches"])
+        scan_launch_ms = st["ms_scan"] / launches
+        alg_bytes = st["bases_scanned"] / launches * 0.5                     # 4-bit packed reference, read once per launch
+        hbm_achieved = alg_bytes / (scan_launch_ms * 1e-3) / 1e9
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        int_peaks = {k: engine.microbench_int(i) for i, k in enumerate(("alu_lop_add", "fma_imad", "mixed_lop_imad"))}
+        own0 = sum(oe[c] - ob[c] for c in range(n))
+        scan_ops = own0 * G * 2 * OPS_PER_COLUMN                                # rank 0's shard
+        int_achieved = scan_ops / (st["ms_scan"] * 1e-3) / 1e12
+        out = {
+            "metric": "Gbp*guides/s SearchReference (hg38-size synthetic)", "value": value, "unit": "Gbp*guides/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args, genome),
+            "e2e": {"value": e2e, "unit": "Gbp*guides/s", "ms_per_step": wall_ms_max, "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
+                    "api": "calitas_search (C ABI): guide strings + limits in host memory -> deduplicated, sorted hit records in pinned host memory"},
+            "gpu_launches": int(sum(s["launches"] for s in stats)),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_scan_tiled", "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                         "note": "streaming read of the 4-bit packed shard once per launch; the kernel is integer-ALU-bound (see roofline_int), so the HBM fraction is small by design",
+                         "avg_launch_ms": scan_launch_ms, "launches_per_step": launches, "share_of_step": st["ms_scan"] / st["ms_total"]},
+            "roofline_int": {"kernel": "k_scan_tiled", "bound": "int_alu", "achieved": int_achieved, "peak": int_peaks["alu_lop_add"], "unit": "Tiop/s",
+                             "frac": int_achieved / int_peaks["alu_lop_add"] if int_peaks["alu_lop_add"] else None,
+                             "ops_per_column": OPS_PER_COLUMN, "measured_peaks_tiops": int_peaks,
+                             "reference_equivalent_tiops": bpg * REF_OPS_PER_BP_GUIDE / (dev_ms_max * 1e-3) / 1e12,
+                             "gcups_equivalent": value * 40},
+            "breakdown_ms": {"scan": st["ms_scan"], "align": st["ms_align"], "sort_canon_dedup": st["ms_other"], "d2h": st["ms_d2h"], "wall": st["wall_ms"]},
+            "counts": {"hits": total_hits, "candidates": total_cand, "windows_rank0": st["windows"], "genome_bp": genome.total(), "shard_bp_sum": total_bp},
+            "setup_s": {"generate": t_gen, "load_and_pack": t_load},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_sample(genome, guides, os.cpu_count() or 1, args.cpu_seconds)
+        print(json.dumps(out))
+    ref.free()
+    engine.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,7 +64,7 @@ EXPORTS = [
     # include/calitas_b200.h
     "calitas_engine_create", "calitas_engine_destroy", "calitas_engine_get_costs", "calitas_last_error", "calitas_reference_load", "calitas_reference_free",
     "calitas_shard_plan", "calitas_search", "calitas_align_regions", "calitas_align_targets", "calitas_hitset_count", "calitas_hitset_data",
-    "calitas_hitset_free", "calitas_hitset_stats", "calitas_render_alignments", "calitas_free_text",
+    "calitas_hitset_free", "calitas_hitset_stats", "calitas_render_alignments", "calitas_free_text", "calitas_microbench_int",
     # include/calitas_b200_tools.h
     "calitas_tool_align", "calitas_tool_align_best", "calitas_tool_align_to_ref", "calitas_tool_search_reference", "calitas_tool_align_to_reference",
     "calitas_tool_variant_windows",
@@ -159,11 +159,11 @@ class HitSet:
         return np.frombuffer(buf, dtype=np.uint8).reshape(n, C.sizeof(Hit)).copy()
 
     def stats(self):
-        ms = (C.c_double * 4)()
-        cnt = (C.c_int64 * 4)()
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
         self.lib.check(self.lib.L.calitas_hitset_stats(self.ptr, ms, cnt))
-        return {"ms_total": ms[0], "ms_scan": ms[1], "ms_align": ms[2], "ms_other": ms[3], "windows": cnt[0], "candidates": cnt[1],
-                "alignments": cnt[2], "launches": cnt[3]}
+        return {"ms_total": ms[0], "ms_scan": ms[1], "ms_align": ms[2], "ms_other": ms[3], "ms_d2h": ms[4], "windows": cnt[0], "candidates": cnt[1],
+                "alignments": cnt[2], "launches": cnt[3], "h2d_bytes": cnt[4], "d2h_bytes": cnt[5], "scan_launches": cnt[6], "bases_scanned": cnt[7]}
 
     def free(self):
         if self.ptr:
@@ -203,26 +203,33 @@ class Engine:
             self.lib.L.calitas_engine_destroy(self.ptr)
             self.ptr = None
 
+    def microbench_int(self, kind=0):
+        v = C.c_double(0)
+        self.lib.check(self.lib.L.calitas_microbench_int(self.ptr, kind, C.byref(v)))
+        return v.value
+
     # ---- reference -------------------------------------------------------------------------------------------------------------
     @staticmethod
     def genome_view(contigs, assembly=None):
         """contigs: [(name, bases as bytes/str/numpy uint8 array)] -> (GenomeView, keepalive)."""
         n = len(contigs)
         names = (C.c_char_p * n)(*[_b(c[0]) for c in contigs])
-        bufs, ptrs, lens = [], (C.c_char_p * n)(), (C.c_int64 * n)()
+        bufs, addrs, ptrs, lens = [], [], (C.c_char_p * n)(), (C.c_int64 * n)()
         for i, (_, b) in enumerate(contigs):
             if hasattr(b, "ctypes"):  # numpy array
                 bufs.append(b)
-                ptrs[i] = C.cast(b.ctypes.data, C.c_char_p)
+                addrs.append(b.ctypes.data)
                 lens[i] = b.size
             else:
                 bb = _b(b)
                 bufs.append(bb)
-                ptrs[i] = bb
+                addrs.append(C.cast(C.c_char_p(bb), C.c_void_p).value)
                 lens[i] = len(bb)
+        C.memmove(ptrs, (C.c_void_p * n)(*addrs), n * C.sizeof(C.c_void_p))
         asm = _b(assembly)
         view = GenomeView(n, names, lens, ptrs, asm)
-        return view, (names, bufs, ptrs, lens, asm)
+        view._addrs = addrs
+        return view, (names, bufs, ptrs, lens, asm, addrs)
 
     def load_reference(self, contigs, keep_raw=False, shard=None):
         """contigs: [(name, bases)] full contigs; shard=(index, count, halo) loads only that contig-range shard."""
@@ -238,8 +245,7 @@ class Engine:
             self.lib.check(self.lib.L.calitas_shard_plan(n, view.lengths, idx, cnt, C.c_int64(halo), ob, oe, hb, he))
             ptrs = (C.c_void_p * n)()
             for i in range(n):
-                base = C.cast(view.bases[i], C.c_void_p).value or 0
-                ptrs[i] = base + hb[i]
+                ptrs[i] = view._addrs[i] + hb[i]
             self.lib.check(self.lib.L.calitas_reference_load(self.ptr, n, view.names, view.lengths, ptrs, hb, he, ob, oe, 1 if keep_raw else 0, C.byref(p)))
         return Reference(self, p, contigs, (view, keep))
 

@@ -27,11 +27,13 @@ namespace cal {
 // ------------------------------------------------------------------------------------------------------------------------------------
 // device-side descriptors
 // ------------------------------------------------------------------------------------------------------------------------------------
-struct ContigDev { int64_t len; int64_t nib_base; /* nibble index of contig base 0 */ int64_t win_base; /* global index of window 0 */ };
+struct ContigDev { int64_t len; int64_t nib_base; /* nibble index of contig base 0 */ int64_t win_base; /* global index of window 0 */
+                   int64_t own_lo, own_hi; /* global ids of the windows this engine owns; windows outside are halo (processed, never reported) */ };
 struct Tile { int32_t contig; int32_t nwin; int64_t first_k; };
 struct ExplicitWindow { int64_t nib_start; int32_t len; int32_t target_offset; int32_t guide_idx; int32_t contig_idx; };
 
 const int TILE_WINDOWS = 64;
+const int HALO_WINDOWS = 2;      // windows processed beyond each interior shard cut so that removeOverlaps sees both sides of the cut
 const int SCAN_THREADS = 2 * TILE_WINDOWS;
 const int KEY_COL_BITS = 17, KEY_WIN_SHIFT = 18, KEY_GUIDE_SHIFT = 50;
 const uint32_t MAX_WINDOW_LEN = (1u << KEY_COL_BITS) - 1;
@@ -213,13 +215,14 @@ CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) {
   const uint64_t key = a.cand[i];
   const int32_t col = (int32_t)(key & MAX_WINDOW_LEN);
   const uint32_t strandbit = (uint32_t)(key >> KEY_COL_BITS) & 1u, wid = (uint32_t)(key >> KEY_WIN_SHIFT);
-  int32_t gidx = (int32_t)(key >> KEY_GUIDE_SHIFT), contig_idx; WindowGeom geom; int64_t first;
+  int32_t gidx = (int32_t)(key >> KEY_GUIDE_SHIFT), contig_idx; WindowGeom geom; int64_t first; uint8_t owned = 1;
   if (a.explicit_mode) {
     const ExplicitWindow ew = a.windows[wid];
     gidx = ew.guide_idx; contig_idx = ew.contig_idx; geom.w_begin = ew.target_offset; geom.w_end = ew.target_offset + ew.len; first = ew.nib_start;
   } else {
     int64_t wb, we; locate_window(a.nib, a.contigs, a.n_contigs, a.window_size, a.step, wid, contig_idx, wb, we);
     geom.w_begin = (int32_t)wb; geom.w_end = (int32_t)we; first = a.contigs[contig_idx].nib_base + wb;
+    owned = ((int64_t)wid >= a.contigs[contig_idx].own_lo && (int64_t)wid < a.contigs[contig_idx].own_hi) ? 1 : 2;
   }
   const GuideSpec& g = a.specs[gidx];
   const int dir = (int)(strandbit ^ (uint32_t)g.five_prime);
@@ -232,12 +235,12 @@ CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) {
   if (!band_align(g, a.sc, fetch, col, aln, trace)) return;
   if (aln.diffs > g.d) return;                                   // SequentialGuideAligner.scala:447,450
   if (g.n_pams == 0) {
-    make_hit(g, aln, -1, aln.score, 0, 0u, dir, geom, gidx, contig_idx, (int32_t)wid + a.task_base, a.hits[base]); a.valid[base] = 1;
+    make_hit(g, aln, -1, aln.score, 0, 0u, dir, geom, gidx, contig_idx, (int32_t)wid + a.task_base, a.hits[base]); a.valid[base] = owned;
   } else {
     for (int pi = 0; pi < g.n_pams; ++pi) {
       int32_t score = 0, offset = 0; uint32_t xmask = 0;
       if (extend_pam(g, a.sc, fetch, m, aln, pi, score, offset, xmask)) {
-        make_hit(g, aln, pi, score, offset, xmask, dir, geom, gidx, contig_idx, (int32_t)wid + a.task_base, a.hits[base + pi]); a.valid[base + pi] = 1;
+        make_hit(g, aln, pi, score, offset, xmask, dir, geom, gidx, contig_idx, (int32_t)wid + a.task_base, a.hits[base + pi]); a.valid[base + pi] = owned;
       }
     }
   }
@@ -248,7 +251,7 @@ CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) {
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct CanonArgs {
   const uint64_t* cand; int64_t n_cand; const GuideSpec* specs; int32_t slots; int32_t explicit_mode; const ExplicitWindow* windows;
-  const calitas_hit* hits; const uint8_t* valid; int32_t* rank; uint32_t* perm; uint32_t* flag;
+  const calitas_hit* hits; const uint8_t* valid; int32_t* rank; uint32_t* perm; uint32_t* flag; uint8_t* slot_owned; int32_t drop_halo;
 };
 CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,15 +262,19 @@ CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
   const int64_t base = i * a.slots; const int n = (int)((j - i) * a.slots);
   const int32_t gidx = a.explicit_mode ? a.windows[(uint32_t)(a.cand[i] >> KEY_WIN_SHIFT)].guide_idx : (int32_t)(a.cand[i] >> KEY_GUIDE_SHIFT);
   const GuideSpec& g = a.specs[gidx];
-  const int kept = canon_group(a.hits + base, a.valid + base, a.rank + base, n, g.max_total_diffs, g.max_overlap);
-  for (int k = 0; k < n; ++k) a.flag[base + k] = k < kept ? 1u : 0u;
+  int kept = canon_group(a.hits + base, a.valid + base, a.rank + base, n, g.max_total_diffs, g.max_overlap);
+  bool owned = true; for (int k = 0; k < n; ++k) if (a.valid[base + k] == 2) owned = false;     // a group is one window: all halo or all owned
+  if (!owned && a.drop_halo) kept = 0;
+  for (int k = 0; k < n; ++k) { a.flag[base + k] = k < kept ? 1u : 0u; a.slot_owned[base + k] = owned ? 1 : 0; }
+  if (kept == 0) return;
   for (int k = 0; k < n; ++k) { const int32_t r = a.rank[base + k]; if (r >= 0) a.perm[base + r] = (uint32_t)(base + k); }
 }
 // out[pos[s]] = hits[perm[s]] for flagged slots
-CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const calitas_hit* hits, const uint32_t* perm, const uint32_t* flag, const uint32_t* pos, int64_t n, calitas_hit* out) {
+CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const calitas_hit* hits, const uint32_t* perm, const uint32_t* flag, const uint32_t* pos, const uint8_t* slot_owned, int64_t n,
+                                                   calitas_hit* out, uint8_t* out_owned) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n || !flag[s]) return;
-  out[pos[s]] = hits[perm[s]];
+  out[pos[s]] = hits[perm[s]]; out_owned[pos[s]] = slot_owned[s];
 }
 CAL_KERNEL __launch_bounds__(256) k_gather(const calitas_hit* hits, const uint32_t* idx, int64_t n, calitas_hit* out) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -291,17 +298,17 @@ CAL_KERNEL __launch_bounds__(256) k_gather_u64(const uint64_t* in, const uint32_
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[idx[i]];
 }
-CAL_KERNEL __launch_bounds__(256) k_sweep_prepare(const calitas_hit* hits, const uint32_t* idx, int64_t n, int32_t* s_start, int32_t* s_end, int32_t* s_score) {
+CAL_KERNEL __launch_bounds__(256) k_sweep_prepare(const calitas_hit* hits, const uint8_t* owned, const uint32_t* idx, int64_t n, int32_t* s_start, int32_t* s_end, int32_t* s_score, uint8_t* s_owned) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const calitas_hit& h = hits[idx[i]];
-  s_start[i] = h.guide_start_offset; s_end[i] = hit_sweep_end(h); s_score[i] = h.score;
+  s_start[i] = h.guide_start_offset; s_end[i] = hit_sweep_end(h); s_score[i] = h.score; s_owned[i] = owned[idx[i]];
 }
 CAL_HD int32_t soa_overlap(const int32_t* s_start, const int32_t* s_end, int64_t a, int64_t b) {
   const int32_t hi = s_end[a] < s_end[b] ? s_end[a] : s_end[b], lo = s_start[a] > s_start[b] ? s_start[a] : s_start[b];
   const int32_t o = hi - lo; return o > 0 ? o : 0;
 }
-CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key1, const int32_t* s_start, const int32_t* s_end, const int32_t* s_score, int64_t n, int32_t max_overlap, uint32_t* keep) {
+CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key1, const int32_t* s_start, const int32_t* s_end, const int32_t* s_score, const uint8_t* s_owned, int64_t n, int32_t max_overlap, uint32_t* keep) {
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i0 >= n) return;
   const uint64_t grp = key1[i0] >> 31;
@@ -310,7 +317,7 @@ CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key1, const int32_t* s
   while (i < n && (key1[i] >> 31) == grp) {
     const int64_t cur = i++;
     while (i < n && (key1[i] >> 31) == grp && soa_overlap(s_start, s_end, i, cur) >= max_overlap && s_score[i] <= s_score[cur]) { keep[i] = 0; ++i; }
-    keep[cur] = (i >= n || (key1[i] >> 31) != grp || soa_overlap(s_start, s_end, i, cur) < max_overlap) ? 1u : 0u;
+    keep[cur] = ((i >= n || (key1[i] >> 31) != grp || soa_overlap(s_start, s_end, i, cur) < max_overlap) && s_owned[cur]) ? 1u : 0u;   // halo hits take part, are never reported
   }
 }
 // compaction of (idx, key) by keep; key is rewritten to the final sort key guide | contig | coordinate_start | strand
@@ -320,6 +327,36 @@ CAL_KERNEL __launch_bounds__(256) k_compact_keepers(const uint64_t* key1, const 
   const uint64_t k = key1[i];
   key3[pos[i]] = (k & 0xFFFFFFFF00000000ull) | ((k & 0x7FFFFFFFull) << 1) | ((k >> 31) & 1ull);
   idx_out[pos[i]] = idx[i];
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// k_int_peak: integer-issue microbenchmark for the roofline denominator (no integer peak in MEASURED_PEAKS.json).
+// kind 0: dependent-free LOP3 + IADD chains (the ALU pipe the scan kernel lives on); kind 1: IMAD chains (FMA pipe); kind 2: both interleaved.
+// ------------------------------------------------------------------------------------------------------------------------------------
+CAL_KERNEL __launch_bounds__(256) k_int_peak(uint32_t* out, int iters, int kind, uint32_t seed) {
+  uint32_t a[8], b = seed | 1u, c = seed * 2654435761u + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = c + k * 0x9E3779B9u;
+  if (kind == 0) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] = (a[k] & b) ^ c; a[k] = a[k] + b; }      // 1 LOP3 + 1 IADD per statement pair
+    }
+  } else if (kind == 1) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] = a[k] * b + c; a[k] = a[k] * c + b; }     // 2 IMAD
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] = (a[k] & b) ^ c; a[k] = a[k] * b + c; }   // 1 LOP3 + 1 IMAD
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r ^= a[k];
+  if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;               // keeps the chains alive
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------------
@@ -353,13 +390,13 @@ struct calitas_reference {
 };
 
 struct calitas_hitset {
-  calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; double ms[4] = { 0, 0, 0, 0 }; int64_t counts[4] = { 0, 0, 0, 0 };
+  calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 
 struct calitas_engine {
   int device = 0; dev::Stream stream; Scores sc; calitas_costs costs;
   dev::Event ev[8];
-  DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, kept, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp;
+  DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, kept, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, kept_owned, sowned;
   unsigned long long* h_count = nullptr;       // pinned
   unsigned long long* d_count = nullptr;
   std::vector<PinnedBuf> pinned_pool;
@@ -397,16 +434,20 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
     for (size_t c = 0; c < r->len.size(); ++c) {
       const int64_t len = r->len[c];
       const int64_t n_win = len - 1 > 0 ? (len - 1 + step - 1) / step : 0;       // Range(0, len-1, step).size
-      ts.contigs.push_back(ContigDev{ len, r->nib_off[c] - r->have_b[c], win_base });
       int64_t k_lo = (r->own_b[c] + step - 1) / step;
       int64_t k_hi = n_win;                                                      // exclusive
       if (r->own_e[c] < len) { int64_t lim = (r->own_e[c] + step - 1) / step; if (lim < k_hi) k_hi = lim; }
-      if (k_lo < k_hi) {
-        int64_t last_end = std::min(len, (k_hi - 1) * step + window_size);
-        if (k_lo * step < r->have_b[c] || last_end > r->have_e[c])
-          throw InvalidArgument("reference shard of contig " + r->names[c] + " does not hold the bases of its owned windows (halo smaller than the window size)");
+      if (k_lo > k_hi) k_lo = k_hi;
+      ts.contigs.push_back(ContigDev{ len, r->nib_off[c] - r->have_b[c], win_base, win_base + k_lo, win_base + k_hi });
+      // halo windows on each interior cut (removeOverlaps needs both sides of a cut; their hits are never reported)
+      int64_t p_lo = k_lo, p_hi = k_hi;
+      if (k_lo < k_hi) { if (k_lo > 0) p_lo = std::max<int64_t>(0, k_lo - HALO_WINDOWS); if (k_hi < n_win) p_hi = std::min<int64_t>(n_win, k_hi + HALO_WINDOWS); }
+      if (p_lo < p_hi) {
+        int64_t last_end = std::min(len, (p_hi - 1) * step + window_size);
+        if (p_lo * step < r->have_b[c] || last_end > r->have_e[c])
+          throw InvalidArgument("reference shard of contig " + r->names[c] + " does not hold the bases of its owned windows plus " + std::to_string(HALO_WINDOWS) + " halo windows per cut");
       }
-      for (int64_t k = k_lo; k < k_hi; k += TILE_WINDOWS) ts.tiles.push_back(Tile{ (int32_t)c, (int32_t)std::min<int64_t>(TILE_WINDOWS, k_hi - k), k });
+      for (int64_t k = p_lo; k < p_hi; k += TILE_WINDOWS) ts.tiles.push_back(Tile{ (int32_t)c, (int32_t)std::min<int64_t>(TILE_WINDOWS, p_hi - k), k });
       ts.n_windows += std::max<int64_t>(0, k_hi - k_lo);
       win_base += n_win;
     }
@@ -424,7 +465,7 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
 
 struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> align -> canon -> compaction
   calitas_engine* e; const GuideSpec* d_specs; int slots; bool explicit_mode;
-  const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base;
+  const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base; bool drop_halo;
 };
 
 // Runs sort/align/canon on e->cand[0..n_cand) and leaves the kept hits, in arrival order, in e->kept; returns their number.
@@ -448,10 +489,10 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); ++e->launches;
   dev::event_record(e->ev[3], s);
   // 3. canonicalise per (guide, window, strand)
-  e->rank.ensure((size_t)n_slots * 4); e->perm.ensure((size_t)n_slots * 4); e->flag.ensure((size_t)n_slots * 4); e->pos.ensure((size_t)n_slots * 4);
+  e->rank.ensure((size_t)n_slots * 4); e->perm.ensure((size_t)n_slots * 4); e->flag.ensure((size_t)n_slots * 4); e->pos.ensure((size_t)n_slots * 4); e->slot_owned.ensure((size_t)n_slots);
   CanonArgs ca; std::memset(&ca, 0, sizeof ca);
   ca.cand = aa.cand; ca.n_cand = n_cand; ca.specs = P.d_specs; ca.slots = P.slots; ca.explicit_mode = aa.explicit_mode; ca.windows = P.d_windows;
-  ca.hits = aa.hits; ca.valid = aa.valid; ca.rank = e->rank.as<int32_t>(); ca.perm = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>();
+  ca.hits = aa.hits; ca.valid = aa.valid; ca.rank = e->rank.as<int32_t>(); ca.perm = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>(); ca.slot_owned = e->slot_owned.as<uint8_t>(); ca.drop_halo = P.drop_halo ? 1 : 0;
   CAL_LAUNCH(k_canon, blocks_for(n_cand, 128), 128, 0, s, 1, ca); dev::launch_check("k_canon"); ++e->launches;
   tb = dev::exclusive_sum_u32_tmp((size_t)n_slots); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n_slots, s); ++e->launches;
@@ -460,8 +501,8 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   dev::stream_sync(s);
   const int64_t n_kept = (int64_t)last_pos + last_flag;
   n_alignments = n_slots;
-  e->kept.ensure((size_t)n_kept * sizeof(calitas_hit));
-  if (n_kept) { CAL_LAUNCH(k_gather_flagged, blocks_for(n_slots, 256), 256, 0, s, 1, aa.hits, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, e->kept.as<calitas_hit>()); dev::launch_check("k_gather_flagged"); ++e->launches; }
+  e->kept.ensure((size_t)n_kept * sizeof(calitas_hit)); e->kept_owned.ensure((size_t)n_kept);
+  if (n_kept) { CAL_LAUNCH(k_gather_flagged, blocks_for(n_slots, 256), 256, 0, s, 1, aa.hits, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), e->slot_owned.as<uint8_t>(), n_slots, e->kept.as<calitas_hit>(), e->kept_owned.as<uint8_t>()); dev::launch_check("k_gather_flagged"); ++e->launches; }
   return n_kept;
 }
 
@@ -479,9 +520,9 @@ int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out
   CAL_LAUNCH(k_gather_u64, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), n, e->keyA.as<uint64_t>()); dev::launch_check("k_gather_u64"); ++e->launches;
   dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)n, 0, 64, s); ++e->launches;
   // now key1[i], idx[i] sorted by (guide, contig, strand, start, -score, arrival)
-  e->sstart.ensure((size_t)n * 4); e->send.ensure((size_t)n * 4); e->sscore.ensure((size_t)n * 4); e->flag.ensure((size_t)n * 4); e->pos.ensure((size_t)n * 4);
-  CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, hits, e->idx.as<uint32_t>(), n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
-  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, e->key1.as<uint64_t>(), e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), n, max_overlap, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
+  e->sstart.ensure((size_t)n * 4); e->send.ensure((size_t)n * 4); e->sscore.ensure((size_t)n * 4); e->sowned.ensure((size_t)n); e->flag.ensure((size_t)n * 4); e->pos.ensure((size_t)n * 4);
+  CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, hits, e->kept_owned.as<uint8_t>(), e->idx.as<uint32_t>(), n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
+  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, e->key1.as<uint64_t>(), e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, max_overlap, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
   tb = dev::exclusive_sum_u32_tmp((size_t)n); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n, s); ++e->launches;
   uint32_t last_pos = 0, last_flag = 0;
@@ -497,16 +538,19 @@ int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out
   return nk;
 }
 
-calitas_hitset* finish_hitset(calitas_engine* e, int64_t n_out, const double ms[4], const int64_t counts[4]) {
+calitas_hitset* finish_hitset(calitas_engine* e, int64_t n_out, const double ms[8], const int64_t counts[8]) {
   std::unique_ptr<calitas_hitset> hs(new calitas_hitset());
   hs->owner = e; hs->n = n_out;
   hs->buf = take_pinned(e, (size_t)std::max<int64_t>(1, n_out) * sizeof(calitas_hit));
+  dev::event_record(e->ev[6], e->stream);
   dev::d2h(hs->buf.p, e->out.p, (size_t)n_out * sizeof(calitas_hit), e->stream);
   dev::event_record(e->ev[1], e->stream);
   dev::stream_sync(e->stream);
-  for (int i = 0; i < 4; ++i) { hs->ms[i] = ms[i]; hs->counts[i] = counts[i]; }
+  for (int i = 0; i < 8; ++i) { hs->ms[i] = ms[i]; hs->counts[i] = counts[i]; }
   hs->ms[0] = dev::event_ms(e->ev[0], e->ev[1]);
-  hs->ms[3] = hs->ms[0] - hs->ms[1] - hs->ms[2];
+  hs->ms[4] = dev::event_ms(e->ev[6], e->ev[1]);
+  hs->ms[3] = hs->ms[0] - hs->ms[1] - hs->ms[2] - hs->ms[4];
+  hs->counts[5] += (int64_t)((size_t)n_out * sizeof(calitas_hit));
   return hs.release();
 }
 
@@ -527,7 +571,8 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
   int slots = 1; for (auto& sp : specs) slots = std::max(slots, sp.slots);
   e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
   e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
-  double ms[4] = { 0, 0, 0, 0 }; int64_t counts[4] = { (int64_t)windows.size(), 0, 0, 0 };
+  double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { (int64_t)windows.size(), 0, 0, 0, 0, 0, 0, 0 };
+  counts[4] = (int64_t)(specs.size() * sizeof(GuideSpec) + windows.size() * sizeof(ExplicitWindow));
   int64_t n_out = 0;
   const int64_t n_windows = (int64_t)windows.size();
   // batches bound the candidate buffer: in best mode every column of every window is a candidate
@@ -550,7 +595,7 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
     ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
     counts[1] += (int64_t)n_cand;
     // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
-    Pipeline P{ e, e->specs.as<GuideSpec>(), slots, true, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0 };
+    Pipeline P{ e, e->specs.as<GuideSpec>(), slots, true, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true };
     int64_t n_aln = 0;
     const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
     if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
@@ -602,7 +647,7 @@ void calitas_engine_destroy(calitas_engine* e) {
     dev::set_device(e->device);
     dev::stream_sync(e->stream);
     for (DBuf* b : { &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->kept, &e->out, &e->tmp, &e->key1, &e->keyA,
-                     &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp }) b->release();
+                     &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp, &e->slot_owned, &e->kept_owned, &e->sowned }) b->release();
     for (auto& p : e->pinned_pool) dev::free_host(p.p);
     dev::free_host(e->h_count); dev::free_(e->d_count);
     for (auto& ev : e->ev) dev::event_destroy(ev);
@@ -621,7 +666,7 @@ int calitas_shard_plan(int32_t n_contigs, const int64_t* lengths, int32_t shard,
     for (int c = 0; c < n_contigs; ++c) {
       const int64_t len = lengths[c];
       int64_t b = std::min(std::max<int64_t>(lo - off, 0), len), en = std::min(std::max<int64_t>(hi - off, 0), len);
-      own_begin[c] = b; own_end[c] = en; have_begin[c] = b; have_end[c] = en > b ? std::min(len, en + halo) : b;
+      own_begin[c] = b; own_end[c] = en; have_begin[c] = en > b ? std::max<int64_t>(0, b - halo) : b; have_end[c] = en > b ? std::min(len, en + halo) : b;
       off += len;
     }
     return CALITAS_OK;
@@ -688,7 +733,8 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     e->launches = 0;
     dev::event_record(e->ev[0], s);
     e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
-    double ms[4] = { 0, 0, 0, 0 }; int64_t counts[4] = { 0, 0, 0, 0 };
+    double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    counts[4] = (int64_t)(specs.size() * sizeof(GuideSpec));
     int64_t n_out = 0;
     const int G_CHUNK = 16;
     int g0 = 0;
@@ -725,10 +771,10 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         if (n_cand <= e->cand_cap_hint) break;
         e->cand_cap_hint = (size_t)(n_cand + n_cand / 4);          // pool too small: grow and re-run, never truncate
       }
-      if (n_tiles) ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
-      if (g0 == 0) { for (size_t t = t_begin; t < t_end; ++t) counts[0] += ts.tiles[t].nwin; }
+      if (n_tiles) { ms[1] += dev::event_ms(e->ev[4], e->ev[5]); counts[6] += 1; int64_t nb = 0; for (size_t t = t_begin; t < t_end; ++t) nb += (int64_t)(ts.tiles[t].nwin - 1) * step + window_size; counts[7] += nb; }
+      if (g0 == 0) { for (size_t c = 0; c < ts.contigs.size(); ++c) if (chrom_idx < 0 || (int)c == chrom_idx) counts[0] += ts.contigs[c].own_hi - ts.contigs[c].own_lo; }
       counts[1] += (int64_t)n_cand;
-      Pipeline P{ e, e->specs.as<GuideSpec>(), slots, false, ref->d_nib, ts.d_contigs, (int)ts.contigs.size(), window_size, step, nullptr, 0 };
+      Pipeline P{ e, e->specs.as<GuideSpec>(), slots, false, ref->d_nib, ts.d_contigs, (int)ts.contigs.size(), window_size, step, nullptr, 0, dedup == 0 };
       int64_t n_aln = 0;
       const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
       if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
@@ -798,12 +844,32 @@ int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_gui
   });
 }
 
+int calitas_microbench_int(calitas_engine* e, int32_t kind, double* tera_ops_per_s) {
+  return guarded([&]() -> int {
+    if (!e || !tera_ops_per_s || kind < 0 || kind > 2) throw InvalidArgument("bad microbench arguments");
+    dev::set_device(e->device); dev::Stream s = e->stream;
+    const int iters = 4096; const unsigned grid = (unsigned)dev::sm_count(e->device) * 16, block = 256;
+    e->tmp.ensure((size_t)grid * block * 4);
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      dev::event_record(e->ev[4], s);
+      CAL_LAUNCH(k_int_peak, grid, block, 0, s, 1, e->tmp.as<uint32_t>(), iters, (int)kind, 12345u + (uint32_t)rep); dev::launch_check("k_int_peak");
+      dev::event_record(e->ev[5], s); dev::stream_sync(s);
+      const double ms = dev::event_ms(e->ev[4], e->ev[5]);
+      const double ops = (double)grid * block * (double)iters * 16.0;     // 8 chains x 2 integer instructions per iteration, per thread
+      if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+    }
+    *tera_ops_per_s = best;
+    return CALITAS_OK;
+  });
+}
+
 int64_t calitas_hitset_count(const calitas_hitset* h) { return h ? h->n : 0; }
 const calitas_hit* calitas_hitset_data(const calitas_hitset* h) { return h ? (const calitas_hit*)h->buf.p : nullptr; }
 void calitas_hitset_free(calitas_hitset* h) { if (!h) return; if (h->owner) h->owner->pinned_pool.push_back(h->buf); delete h; }
-int calitas_hitset_stats(const calitas_hitset* h, double ms[4], int64_t counts[4]) {
+int calitas_hitset_stats(const calitas_hitset* h, double ms[8], int64_t counts[8]) {
   if (!h) return set_error(CALITAS_EINVAL, "hitset is NULL");
-  for (int i = 0; i < 4; ++i) { if (ms) ms[i] = h->ms[i]; if (counts) counts[i] = h->counts[i]; }
+  for (int i = 0; i < 8; ++i) { if (ms) ms[i] = h->ms[i]; if (counts) counts[i] = h->counts[i]; }
   return CALITAS_OK;
 }
 

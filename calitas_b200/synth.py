@@ -40,10 +40,16 @@ class Genome:
             b0 = blk * BLOCK
             lo, hi = max(begin, b0), min(end, b0 + BLOCK)
             out[lo - begin:hi - begin] = ACGT[codes[lo - b0:hi - b0]]
-        for (pos, seq) in self.planted[contig]:
-            lo, hi = max(begin, pos), min(end, pos + len(seq))
-            if lo < hi:
-                out[lo - begin:hi - begin] = np.frombuffer(seq, dtype=np.uint8)[lo - pos:hi - pos]
+        pl = self.planted[contig]
+        if pl:
+            import bisect
+            i = max(0, bisect.bisect_left(pl, (begin - 256, b"")))
+            while i < len(pl) and pl[i][0] < end:
+                pos, seq = pl[i]
+                lo, hi = max(begin, pos), min(end, pos + len(seq))
+                if lo < hi:
+                    out[lo - begin:hi - begin] = np.frombuffer(seq, dtype=np.uint8)[lo - pos:hi - pos]
+                i += 1
         for (nb, ne) in self.n_blocks[contig]:
             lo, hi = max(begin, nb), min(end, ne)
             if lo < hi:
@@ -81,27 +87,38 @@ def mutate_protospacer(rng, proto, n_edits):
 def plant_sites(rng, lengths, guides, n_sites, n_blocks, max_edits=5, pams=(b"AGG", b"TGG", b"CAG", b"GGG", b"TGA"), margin=200):
     """planted[contig] = [(pos, bytes)], non-overlapping, outside N blocks.  guides: list of 'PROTOSPACERpam' strings (3' PAM)."""
     planted = [[] for _ in lengths]
-    taken = [[] for _ in lengths]
-    total = float(sum(lengths))
+    taken = [set() for _ in lengths]                      # occupied 128-base bins
+    blocked = []
+    for c, blocks in enumerate(n_blocks):
+        b = set()
+        for (nb, ne) in blocks:
+            if ne - nb <= (1 << 22):                      # big blocks are handled by interval test below
+                b.update(range(max(0, nb - 64) >> 7, ((ne + 64) >> 7) + 1))
+        blocked.append(b)
+    big = [[(nb, ne) for (nb, ne) in blocks if ne - nb > (1 << 22)] for blocks in n_blocks]
+    p_contig = np.array(lengths, dtype=np.float64) / float(sum(lengths))
+    protos = ["".join(c for c in g if c.isupper()).encode() for g in guides]
     for k in range(n_sites):
-        proto = "".join(c for c in guides[k % len(guides)] if c.isupper()).encode()
-        site = mutate_protospacer(rng, proto, int(rng.integers(0, max_edits + 1)))
-        site += bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, 4))).astype(np.uint8).tolist())
+        site = mutate_protospacer(rng, protos[k % len(protos)], int(rng.integers(0, max_edits + 1)))
+        site += bytes(rng.integers(0, 4, size=int(rng.integers(0, 4))).astype(np.uint8).tolist()).translate(bytes.maketrans(bytes(range(4)), b"ACGT"))
         site += pams[int(rng.integers(0, len(pams)))]
         if rng.random() < 0.5:
             site = revcomp_bytes(site)
         for _try in range(100):
-            c = int(rng.choice(len(lengths), p=[l / total for l in lengths]))
+            c = int(rng.choice(len(lengths), p=p_contig))
             if lengths[c] < 2 * margin + 64:
                 continue
             pos = int(rng.integers(margin, lengths[c] - margin - len(site)))
-            if any(pos < e + 64 and s - 64 < pos + len(site) for (s, e) in taken[c]):
+            bins = range((pos - 64) >> 7, ((pos + len(site) + 64) >> 7) + 1)
+            if any(b in taken[c] or b in blocked[c] for b in bins):
                 continue
-            if any(pos < ne + 64 and nb - 64 < pos + len(site) for (nb, ne) in n_blocks[c]):
+            if any(pos < ne + 64 and nb - 64 < pos + len(site) for (nb, ne) in big[c]):
                 continue
-            taken[c].append((pos, pos + len(site)))
+            taken[c].update(bins)
             planted[c].append((pos, site))
             break
+    for lst in planted:
+        lst.sort()
     return planted
 
 

@@ -130,10 +130,16 @@ int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_gui
 int64_t calitas_hitset_count(const calitas_hitset* h);
 const calitas_hit* calitas_hitset_data(const calitas_hitset* h);   /* pinned host memory, valid until free */
 void calitas_hitset_free(calitas_hitset* h);
-/* Timings of the call that produced the set, in milliseconds of device time (CUDA events): [0] total, [1] scan kernel,
- * [2] align kernel, [3] sort+canonicalise+dedup; counts: [0] windows, [1] candidate end columns, [2] alignments before
- * canonicalisation, [3] launches. */
-int calitas_hitset_stats(const calitas_hitset* h, double ms[4], int64_t counts[4]);
+/* Timings of the call that produced the set, milliseconds between CUDA events on the engine's stream:
+ *   ms[0] whole call on the device incl. the final D2H, ms[1] scan kernels, ms[2] align kernels, ms[3] sorts + canonicalise + dedup
+ *   (+ host gaps between launches), ms[4] final D2H of the hit records.
+ * counts[0] owned windows, [1] candidate end columns, [2] alignment slots before canonicalisation, [3] kernel launches,
+ * [4] bytes copied host->device, [5] bytes copied device->host, [6] scan-kernel launches, [7] reference bases scanned (summed over scan launches). */
+int calitas_hitset_stats(const calitas_hitset* h, double ms[8], int64_t counts[8]);
+
+/* Integer-issue microbenchmark used as the roofline denominator of the scan kernel (no integer peak is published or in
+ * MEASURED_PEAKS.json).  kind 0: LOP3+IADD chains (ALU pipe), 1: IMAD chains (FMA pipe), 2: LOP3+IMAD interleaved. */
+int calitas_microbench_int(calitas_engine* e, int32_t kind, double* tera_ops_per_s);
 
 /* ---- host-side rendering (ReferenceHit.Builder.build, ReferenceHit.scala:210-254; GuideAlignment.scala:10-50,99-163) ---- */
 /* Renders hits as tab-separated GuideAlignment rows (same columns as oracle_alignment_header()).  `contig_bases[c]` must
