@@ -80,33 +80,67 @@ struct Emitter {
   }
 };
 
-// Scans relative nibble range [rs, re) of a word array, forwards (dir 0) or backwards (dir 1; `peq` then holds the
-// complemented masks); column p = 1.. in scan order.
-template <class Emit>
-CAL_D void scan_range(const uint32_t* words, int32_t rs, int32_t re, int dir, const uint32_t* peq, int lp, int k_edits, const Emit& emit) {
-  MyersState st; myers_init(st, lp);
-  if (dir == 0) {
+// One guide of a thread's scan: its match-mask table for the thread's direction (shared memory), threshold, candidate key base.
+struct ScanGuide { const uint32_t* peq; int32_t lp, k_edits; uint64_t key_base; };
+
+// Scans relative nibble range [rs, re) of the shared-memory tile for NG guides at once (independent Myers chains that share the
+// base-code extraction and give the scheduler instruction-level parallelism).  DIR 0: left to right; DIR 1: right to left, the
+// tables then hold the complemented masks.  Column p = 1.. in scan order.  Whole 8-base words run branch-free: the running
+// minimum of the distance decides, once per word, whether the (rare) per-column emission replay is needed.
+template <int DIR, int NG>
+CAL_D void scan_window(const uint32_t* words, int32_t rs, int32_t re, const ScanGuide* sg, uint64_t* cand, unsigned long long* count, unsigned long long cap) {
+  MyersState st[NG];
+#pragma unroll
+  for (int j = 0; j < NG; ++j) myers_init(st[j], sg[j].lp);
+  // single column with emission test (partial words at both ends, and replays)
+#define CAL_STEP1(J, STATE, CODE, COL) { myers_step(STATE, sg[J].peq[CODE]); if (STATE.score <= sg[J].k_edits) { Emitter em{ cand, count, cap, sg[J].key_base }; em(COL); } }
+  if (DIR == 0) {
     int32_t r = rs;
-    for (; r < re && (r & 7); ++r) { myers_step(st, peq[nibble_at(words, r)]); if (st.score <= k_edits) emit(r - rs + 1); }
+    for (; r < re && (r & 7); ++r) { const uint32_t c = nibble_at(words, r);
+#pragma unroll
+      for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, r - rs + 1) }
     for (; r + 8 <= re; r += 8) {
       const uint32_t w = words[r >> 3];
+      MyersState save[NG]; int32_t mn[NG];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { myers_step(st, peq[(w >> (4 * k)) & 15u]); if (st.score <= k_edits) emit(r + k - rs + 1); }
+      for (int j = 0; j < NG; ++j) { save[j] = st[j]; mn[j] = 0x7FFFFFFF; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const uint32_t c = (w >> (4 * k)) & 15u;
+#pragma unroll
+        for (int j = 0; j < NG; ++j) { myers_step(st[j], sg[j].peq[c]); mn[j] = st[j].score < mn[j] ? st[j].score : mn[j]; } }
+#pragma unroll
+      for (int j = 0; j < NG; ++j) if (mn[j] <= sg[j].k_edits) { MyersState t = save[j]; for (int k = 0; k < 8; ++k) CAL_STEP1(j, t, (w >> (4 * k)) & 15u, r + k - rs + 1) }
     }
-    for (; r < re; ++r) { myers_step(st, peq[nibble_at(words, r)]); if (st.score <= k_edits) emit(r - rs + 1); }
+    for (; r < re; ++r) { const uint32_t c = nibble_at(words, r);
+#pragma unroll
+      for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, r - rs + 1) }
   } else {
     int32_t r = re - 1;
-    for (; r >= rs && (r & 7) != 7; --r) { myers_step(st, peq[nibble_at(words, r)]); if (st.score <= k_edits) emit(re - r); }
+    for (; r >= rs && (r & 7) != 7; --r) { const uint32_t c = nibble_at(words, r);
+#pragma unroll
+      for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, re - r) }
     for (; r - 7 >= rs; r -= 8) {
       const uint32_t w = words[r >> 3];
+      MyersState save[NG]; int32_t mn[NG];
 #pragma unroll
-      for (int k = 7; k >= 0; --k) { myers_step(st, peq[(w >> (4 * k)) & 15u]); if (st.score <= k_edits) emit(re - (r - 7 + k)); }
+      for (int j = 0; j < NG; ++j) { save[j] = st[j]; mn[j] = 0x7FFFFFFF; }
+#pragma unroll
+      for (int k = 7; k >= 0; --k) { const uint32_t c = (w >> (4 * k)) & 15u;
+#pragma unroll
+        for (int j = 0; j < NG; ++j) { myers_step(st[j], sg[j].peq[c]); mn[j] = st[j].score < mn[j] ? st[j].score : mn[j]; } }
+#pragma unroll
+      for (int j = 0; j < NG; ++j) if (mn[j] <= sg[j].k_edits) { MyersState t = save[j]; for (int k = 7; k >= 0; --k) CAL_STEP1(j, t, (w >> (4 * k)) & 15u, re - (r - 7 + k)) }
     }
-    for (; r >= rs; --r) { myers_step(st, peq[nibble_at(words, r)]); if (st.score <= k_edits) emit(re - r); }
+    for (; r >= rs; --r) { const uint32_t c = nibble_at(words, r);
+#pragma unroll
+      for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, re - r) }
   }
+#undef CAL_STEP1
 }
 
-CAL_KERNEL __launch_bounds__(SCAN_THREADS) k_scan_tiled(ScanArgs a) {
+// Block = TILE_WINDOWS windows x 2 directions x `slots` guide slots (blockDim.x = 128 * slots); a thread owns one window, one
+// direction and every slots-th pair of guides of the chunk.
+CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
   CAL_SHARED_DYN(uint32_t, smem);
   const int ng = a.g_end - a.g_begin;
   uint32_t* s_peq = smem;                       // ng * 32 words
@@ -129,7 +163,7 @@ CAL_KERNEL __launch_bounds__(SCAN_THREADS) k_scan_tiled(ScanArgs a) {
   }
   __syncthreads();
   CAL_PHASE(1) {
-    const int kk = threadIdx.x % TILE_WINDOWS, dir = threadIdx.x / TILE_WINDOWS;
+    const int kk = threadIdx.x % TILE_WINDOWS, dir = (threadIdx.x / TILE_WINDOWS) & 1, slot = threadIdx.x / SCAN_THREADS, n_slots = blockDim.x / SCAN_THREADS;
     if (kk >= tile.nwin) return;
     const int64_t ws = (tile.first_k + kk) * (int64_t)a.step;
     int64_t we = ws + a.window_size; if (we > ctg.len) we = ctg.len;
@@ -140,10 +174,15 @@ CAL_KERNEL __launch_bounds__(SCAN_THREADS) k_scan_tiled(ScanArgs a) {
     const int32_t m = re - rs;
     if (m <= 0 || m < a.min_len) return;                              // SearchReference.scala:536
     const uint32_t wid = (uint32_t)(ctg.win_base + tile.first_k + kk);
-    for (int g = 0; g < ng; ++g) {
-      const int lp = s_meta[4 * g], k_edits = s_meta[4 * g + 1], five = s_meta[4 * g + 2];
-      Emitter emit{ a.cand, a.cand_count, a.cand_cap, make_key((uint32_t)(a.g_begin + g), wid, (uint32_t)(dir ^ five), 0) };
-      scan_range(s_tile, rs, re, dir, s_peq + g * 32 + dir * 16, lp, k_edits, emit);
+    for (int g = 2 * slot; g < ng; g += 2 * n_slots) {
+      ScanGuide sg[2];
+      const int cnt = g + 1 < ng ? 2 : 1;
+      for (int j = 0; j < cnt; ++j) {
+        sg[j].peq = s_peq + (g + j) * 32 + dir * 16; sg[j].lp = s_meta[4 * (g + j)]; sg[j].k_edits = s_meta[4 * (g + j) + 1];
+        sg[j].key_base = make_key((uint32_t)(a.g_begin + g + j), wid, (uint32_t)(dir ^ s_meta[4 * (g + j) + 2]), 0);
+      }
+      if (cnt == 2) { if (dir == 0) scan_window<0, 2>(s_tile, rs, re, sg, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 2>(s_tile, rs, re, sg, a.cand, a.cand_count, a.cand_cap); }
+      else          { if (dir == 0) scan_window<0, 1>(s_tile, rs, re, sg, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 1>(s_tile, rs, re, sg, a.cand, a.cand_count, a.cand_cap); }
     }
   }
 }
@@ -764,7 +803,8 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         dev::zero(e->d_count, 8, s);
         ScanArgs sa{ ref->d_nib, ts.d_contigs, ts.d_tiles + t_begin, e->specs.as<GuideSpec>(), g0, g1, window_size, step, raw_len, e->cand.as<uint64_t>(), e->d_count, (unsigned long long)e->cand_cap_hint };
         dev::event_record(e->ev[4], s);
-        CAL_LAUNCH(k_scan_tiled, (unsigned)n_tiles, SCAN_THREADS, smem, s, 2, sa); dev::launch_check("k_scan_tiled"); ++e->launches;
+        const int scan_slots = ng >= 8 ? 4 : (ng >= 3 ? 2 : 1);     // guide slots per window: more resident warps when the chunk has enough guides
+        CAL_LAUNCH(k_scan_tiled, (unsigned)n_tiles, SCAN_THREADS * scan_slots, smem, s, 2, sa); dev::launch_check("k_scan_tiled"); ++e->launches;
         dev::event_record(e->ev[5], s);
         dev::d2h(e->h_count, e->d_count, 8, s); dev::stream_sync(s);
         n_cand = *e->h_count;
