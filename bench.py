@@ -209,11 +209,11 @@ def main():
         hs.free()
         return st
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs ~1 s to start: launched before the warm-up so that it is sampling during the timed steps
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     t_begin = time.perf_counter()
     stats = [step() for _ in range(args.steps)]
     torch.cuda.synchronize()
