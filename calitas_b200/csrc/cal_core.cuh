@@ -73,6 +73,7 @@ CAL_HD Scores make_scores(const calitas_costs& c) {
 struct GuideSpec {
   uint32_t peq[2][16];                       // Myers match masks per scan direction and target code, top-aligned (row i = bit 32-lp+i), low bits all 1
   uint8_t  q[CALITAS_MAX_PROTOSPACER];       // base set per DP-query row
+  uint16_t qmask[CALITAS_MAX_PROTOSPACER];   // per row: bit c set iff the row's base pairs with target code c
   uint8_t  pam[CALITAS_MAX_PAMS][CALITAS_MAX_PAM_LEN];
   uint8_t  pam_len[CALITAS_MAX_PAMS];
   int32_t  lp, n_pams, five_prime;
@@ -92,6 +93,8 @@ CAL_HD void myers_init(MyersState& s, int lp) {
   s.pv = lp >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> lp);   // D[i][0] = i : leading insertions at the window's left edge
   s.mv = 0; s.score = lp;
 }
+// 7 LOP3 + 2 LEA.HI on the ALU pipe, 3 IMAD.IADD on the FMA pipe (the compiler turns the add and both x+x shifts into IMADs).
+// Measured alternatives that were slower on B200: IMAD.WIDE (x*2 gives shift and top bit at once) runs well below IMAD rate.
 CAL_HD void myers_step(MyersState& s, uint32_t eq) {
   uint32_t xv = eq | s.mv;
   uint32_t xh = (((eq & s.pv) + s.pv) ^ s.pv) | eq;
@@ -176,6 +179,79 @@ CAL_HD bool band_align(const GuideSpec& g, const Scores& sc, Fetch fetch, int32_
     cdir = next;
   }
   out.score = best; out.t_start = jlo + cc + 1; out.t_end = j; out.n_ops = nrev; out.diffs = 0;
+  for (int k = 0; k < nrev; ++k) { uint8_t o = rev[nrev - 1 - k]; out.ops[k] = o; if (o != OP_EQ) ++out.diffs; }
+  out.terminal_gap = 0; out.terminal_d = 0;
+  if (nrev > 0 && out.ops[nrev - 1] >= OP_I) {
+    uint8_t o = out.ops[nrev - 1]; int k = nrev; while (k > 0 && out.ops[k - 1] == o) { --k; ++out.terminal_gap; }
+    if (o == OP_D) out.terminal_d = out.terminal_gap;
+  }
+  return true;
+}
+
+// Register-resident variant for the common case k_edits <= KB: only the 2*KB+1 diagonals around the end cell's diagonal can hold an
+// alignment with <= k_edits edits, so one DP row is 2*KB+1 cells kept in registers (compile-time indices); traces are 7 bits per cell
+// (3 predecessor fields + the match bit) packed 4 per word into a small per-thread table.  Values outside the band count as
+// unreachable; every co-optimal path of an accepted end cell lies inside it, hence scores, tie-breaks and traceback are identical to
+// band_align's ("exactness of the band").
+template <int KB, class Fetch>
+CAL_HD bool band_align_k(const GuideSpec& g, const Scores& sc, Fetch fetch, int32_t j, GuideAln& out) {
+  constexpr int B = 2 * KB + 1, TW = (B + 3) / 4;
+  const int n = g.lp;
+  const int base = j - n - KB;                  // cell (i, t) is target column c = i + base + t
+  int32_t d[B], l[B], u[B];
+  uint32_t tr[CALITAS_MAX_PROTOSPACER + 1][TW];
+#pragma unroll
+  for (int t = 0; t < B; ++t) { const int c = base + t; const int32_t v = (c >= 0 && c <= j) ? 0 : NEG_SCORE; d[t] = v; l[t] = v; u[t] = v; }
+  uint64_t win = 0;                             // target codes of the current row's band, one nibble per diagonal
+#pragma unroll
+  for (int t = 0; t < B; ++t) { const int c = 1 + base + t; const uint64_t code = (c >= 1 && c <= j) ? fetch(c) : 0u; win |= code << (4 * t); }
+  const int32_t gI = sc.target_gap, gD = sc.query_gap;
+  for (int i = 1; i <= n; ++i) {
+    const uint32_t qm = g.qmask[i - 1];
+    uint32_t trw[TW];
+#pragma unroll
+    for (int w = 0; w < TW; ++w) trw[w] = 0;
+    int32_t left_d = NEG_SCORE, left_l = NEG_SCORE, left_u = NEG_SCORE;
+#pragma unroll
+    for (int t = 0; t < B; ++t) {
+      const uint32_t code = (uint32_t)(win >> (4 * t)) & 15u;
+      const uint32_t mt = (qm >> code) & 1u;
+      const int32_t add = mt ? sc.match : sc.mismatch;
+      uint32_t cell = mt << 6;
+      int32_t nd, nu, nl;
+      { const int32_t pd = d[t], pl = l[t], pu = u[t];       // Diagonal: predecessor (i-1, c-1) is the same diagonal
+        if (pd >= pl && pd >= pu) { nd = pd + add; cell |= TR_DIAG; } else if (pl >= pu) { nd = pl + add; cell |= TR_LEFT; } else { nd = pu + add; cell |= TR_UP; } }
+      { const int32_t pd = (t + 1 < B ? d[t + 1] : NEG_SCORE) + gI, pu = (t + 1 < B ? u[t + 1] : NEG_SCORE) + gI;     // Up: (i-1, c) is diagonal t+1
+        if (pd >= pu) { nu = pd; cell |= TR_DIAG << 2; } else { nu = pu; cell |= TR_UP << 2; } }
+      { const int32_t pd = left_d + gD, pl = left_l + gD, pu = left_u + gD;                                           // Left: (i, c-1) is diagonal t-1
+        if (pd >= pl && pd >= pu) { nl = pd; cell |= TR_DIAG << 4; } else if (pl >= pu) { nl = pl; cell |= TR_LEFT << 4; } else { nl = pu; cell |= TR_UP << 4; } }
+      d[t] = nd; u[t] = nu; l[t] = nl; left_d = nd; left_l = nl; left_u = nu;
+      trw[t >> 2] |= cell << (8 * (t & 3));
+    }
+#pragma unroll
+    for (int w = 0; w < TW; ++w) tr[i][w] = trw[w];
+    const int cn = (i + 1) + base + (B - 1);                   // slide the band one column to the right
+    const uint64_t code = (cn >= 1 && cn <= j) ? fetch(cn) : 0u;
+    win = (win >> 4) | (code << (4 * (B - 1)));
+  }
+  int32_t best = d[KB]; int dir = TR_DIAG;
+  if (l[KB] > best) { best = l[KB]; dir = TR_LEFT; }
+  if (u[KB] > best) { best = u[KB]; dir = TR_UP; }
+  if (best < g.min_score) return false;
+  int ci = n, ct = KB, cdir = dir, nrev = 0;
+  uint8_t rev[MAX_GUIDE_OPS];
+  for (;;) {
+    int next; uint32_t cell = 0;
+    if (ci == 0) next = TR_DONE;
+    else { cell = (tr[ci][ct >> 2] >> (8 * (ct & 3))) & 0x7Fu; next = cdir == TR_DIAG ? (cell & 3) : (cdir == TR_UP ? ((cell >> 2) & 3) : ((cell >> 4) & 3)); }
+    if (next == TR_DONE) break;
+    if (cdir == TR_DIAG) { rev[nrev++] = (cell >> 6) ? OP_EQ : OP_X; --ci; }
+    else if (cdir == TR_LEFT) { rev[nrev++] = OP_D; --ct; }
+    else { rev[nrev++] = OP_I; --ci; ++ct; }
+    if (ct < 0 || ct >= B) return false;                       // cannot happen for an accepted end cell; keeps indexing safe
+    cdir = next;
+  }
+  out.score = best; out.t_start = ci + base + ct + 1; out.t_end = j; out.n_ops = nrev; out.diffs = 0;
   for (int k = 0; k < nrev; ++k) { uint8_t o = rev[nrev - 1 - k]; out.ops[k] = o; if (o != OP_EQ) ++out.diffs; }
   out.terminal_gap = 0; out.terminal_d = 0;
   if (nrev > 0 && out.ops[nrev - 1] >= OP_I) {

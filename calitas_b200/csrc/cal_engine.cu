@@ -32,6 +32,7 @@ struct ContigDev { int64_t len; int64_t nib_base; /* nibble index of contig base
 struct Tile { int32_t contig; int32_t nwin; int64_t first_k; };
 struct ExplicitWindow { int64_t nib_start; int32_t len; int32_t target_offset; int32_t guide_idx; int32_t contig_idx; };
 
+const int ALIGN_KB = 6;          // k_align keeps a 2*6+1-diagonal DP band in registers when the candidate threshold allows
 const int TILE_WINDOWS = 64;
 const int HALO_WINDOWS = 2;      // windows processed beyond each interior shard cut so that removeOverlaps sees both sides of the cut
 const int SCAN_THREADS = 2 * TILE_WINDOWS;
@@ -82,13 +83,19 @@ struct Emitter {
 
 // One guide of a thread's scan: its match-mask table for the thread's direction (shared memory), threshold, candidate key base.
 struct ScanGuide { const uint32_t* peq; int32_t lp, k_edits; uint64_t key_base; };
+#ifdef CAL_HOSTSIM
+inline int __vimin3_s32(int a, int b, int c) { int m = a < b ? a : b; return m < c ? m : c; }
+inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t n) { n &= 31; return n ? (hi << n) | (lo >> (32 - n)) : hi; }
+#endif
 
 // Scans relative nibble range [rs, re) of the shared-memory tile for NG guides at once (independent Myers chains that share the
 // base-code extraction and give the scheduler instruction-level parallelism).  DIR 0: left to right; DIR 1: right to left, the
 // tables then hold the complemented masks.  Column p = 1.. in scan order.  Whole 8-base words run branch-free: the running
 // minimum of the distance decides, once per word, whether the (rare) per-column emission replay is needed.
 template <int DIR, int NG>
-CAL_D void scan_window(const uint32_t* words, int32_t rs, int32_t re, const ScanGuide* sg, uint64_t* cand, unsigned long long* count, unsigned long long cap) {
+CAL_D void scan_window(const uint32_t* words, int32_t rs, int32_t re, const ScanGuide* sg, const uint32_t* peq_base, uint32_t tbl,
+                       uint64_t* cand, unsigned long long* count, unsigned long long cap) {
+  // peq_base[(tbl + 2 j) * 16 + code] is the match mask of guide j for this direction (== sg[j].peq[code]); guides of a thread are adjacent.
   MyersState st[NG];
 #pragma unroll
   for (int j = 0; j < NG; ++j) myers_init(st[j], sg[j].lp);
@@ -101,13 +108,17 @@ CAL_D void scan_window(const uint32_t* words, int32_t rs, int32_t re, const Scan
       for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, r - rs + 1) }
     for (; r + 8 <= re; r += 8) {
       const uint32_t w = words[r >> 3];
-      MyersState save[NG]; int32_t mn[NG];
+      MyersState save[NG]; int32_t mn[NG], prev[NG];
 #pragma unroll
-      for (int j = 0; j < NG; ++j) { save[j] = st[j]; mn[j] = 0x7FFFFFFF; }
+      for (int j = 0; j < NG; ++j) { save[j] = st[j]; mn[j] = 0x7FFFFFFF; prev[j] = 0x7FFFFFFF; }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { const uint32_t c = (w >> (4 * k)) & 15u;
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t idx = __funnelshift_l(w << (28 - 4 * k), tbl, 4);        // tbl * 16 + code: one ALU instruction, the shift is an IMAD.SHL
 #pragma unroll
-        for (int j = 0; j < NG; ++j) { myers_step(st[j], sg[j].peq[c]); mn[j] = st[j].score < mn[j] ? st[j].score : mn[j]; } }
+        for (int j = 0; j < NG; ++j) {
+          myers_step(st[j], peq_base[idx + 32 * j]);
+          if (k & 1) mn[j] = __vimin3_s32(mn[j], prev[j], st[j].score); else prev[j] = st[j].score;      // one 3-input min per two columns
+        } }
 #pragma unroll
       for (int j = 0; j < NG; ++j) if (mn[j] <= sg[j].k_edits) { MyersState t = save[j]; for (int k = 0; k < 8; ++k) CAL_STEP1(j, t, (w >> (4 * k)) & 15u, r + k - rs + 1) }
     }
@@ -121,13 +132,17 @@ CAL_D void scan_window(const uint32_t* words, int32_t rs, int32_t re, const Scan
       for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, re - r) }
     for (; r - 7 >= rs; r -= 8) {
       const uint32_t w = words[r >> 3];
-      MyersState save[NG]; int32_t mn[NG];
+      MyersState save[NG]; int32_t mn[NG], prev[NG];
 #pragma unroll
-      for (int j = 0; j < NG; ++j) { save[j] = st[j]; mn[j] = 0x7FFFFFFF; }
+      for (int j = 0; j < NG; ++j) { save[j] = st[j]; mn[j] = 0x7FFFFFFF; prev[j] = 0x7FFFFFFF; }
 #pragma unroll
-      for (int k = 7; k >= 0; --k) { const uint32_t c = (w >> (4 * k)) & 15u;
+      for (int k = 7; k >= 0; --k) {
+        const uint32_t idx = __funnelshift_l(w << (28 - 4 * k), tbl, 4);
 #pragma unroll
-        for (int j = 0; j < NG; ++j) { myers_step(st[j], sg[j].peq[c]); mn[j] = st[j].score < mn[j] ? st[j].score : mn[j]; } }
+        for (int j = 0; j < NG; ++j) {
+          myers_step(st[j], peq_base[idx + 32 * j]);
+          if (k & 1) prev[j] = st[j].score; else mn[j] = __vimin3_s32(mn[j], prev[j], st[j].score);
+        } }
 #pragma unroll
       for (int j = 0; j < NG; ++j) if (mn[j] <= sg[j].k_edits) { MyersState t = save[j]; for (int k = 7; k >= 0; --k) CAL_STEP1(j, t, (w >> (4 * k)) & 15u, re - (r - 7 + k)) }
     }
@@ -181,8 +196,9 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
         sg[j].peq = s_peq + (g + j) * 32 + dir * 16; sg[j].lp = s_meta[4 * (g + j)]; sg[j].k_edits = s_meta[4 * (g + j) + 1];
         sg[j].key_base = make_key((uint32_t)(a.g_begin + g + j), wid, (uint32_t)(dir ^ s_meta[4 * (g + j) + 2]), 0);
       }
-      if (cnt == 2) { if (dir == 0) scan_window<0, 2>(s_tile, rs, re, sg, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 2>(s_tile, rs, re, sg, a.cand, a.cand_count, a.cand_cap); }
-      else          { if (dir == 0) scan_window<0, 1>(s_tile, rs, re, sg, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 1>(s_tile, rs, re, sg, a.cand, a.cand_count, a.cand_cap); }
+      const uint32_t tbl = (uint32_t)(2 * g + dir);
+      if (cnt == 2) { if (dir == 0) scan_window<0, 2>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 2>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); }
+      else          { if (dir == 0) scan_window<0, 1>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 1>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); }
     }
   }
 }
@@ -270,8 +286,12 @@ CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) {
   const int64_t base = i * a.slots;
   for (int s = 0; s < a.slots; ++s) a.valid[base + s] = 0;
   GuideAln aln;
-  uint8_t trace[(CALITAS_MAX_PROTOSPACER + 1) * (MAX_SPAN + 1)];
-  if (!band_align(g, a.sc, fetch, col, aln, trace)) return;
+  if (g.k_edits <= ALIGN_KB) {            // register-resident diagonal band (defaults and d = 6 land here)
+    if (!band_align_k<ALIGN_KB>(g, a.sc, fetch, col, aln)) return;
+  } else {                                // wide thresholds / best mode: full rectangle in local memory
+    uint8_t trace[(CALITAS_MAX_PROTOSPACER + 1) * (MAX_SPAN + 1)];
+    if (!band_align(g, a.sc, fetch, col, aln, trace)) return;
+  }
   if (aln.diffs > g.d) return;                                   // SequentialGuideAligner.scala:447,450
   if (g.n_pams == 0) {
     make_hit(g, aln, -1, aln.score, 0, 0u, dir, geom, gidx, contig_idx, (int32_t)wid + a.task_base, a.hits[base]); a.valid[base] = owned;

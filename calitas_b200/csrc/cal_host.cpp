@@ -72,7 +72,11 @@ GuideSpec make_guide_spec(const GuideDef& g, const Scores& sc, const calitas_lim
   s.lp = lp; s.five_prime = g.five_prime ? 1 : 0;
   // The DP keeps the PAM on the right: a 5' PAM guide is aligned as its reverse complement (SequentialGuideAligner.scala:260-262).
   const std::string q = g.five_prime ? revcomp(g.protospacer) : g.protospacer;
-  for (int i = 0; i < lp; ++i) s.q[i] = (uint8_t)iupac_set((uint8_t)q[(size_t)i]);
+  for (int i = 0; i < lp; ++i) {
+    s.q[i] = (uint8_t)iupac_set((uint8_t)q[(size_t)i]);
+    uint16_t m = 0; for (uint32_t code = 0; code < 16; ++code) if (pairs(s.q[i], code)) m |= (uint16_t)(1u << code);
+    s.qmask[i] = m;
+  }
   const bool no_pams = g.pams.empty() || (g.pams.size() == 1 && g.pams[0].empty());   // :446
   s.n_pams = no_pams ? 0 : (int)g.pams.size();
   for (int k = 0; k < s.n_pams; ++k) {
