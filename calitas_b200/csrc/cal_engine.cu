@@ -264,7 +264,8 @@ CAL_D void locate_window(const uint32_t* nib, const ContigDev* contigs, int32_t 
   while (wb < we && nibble_at(nib, c.nib_base + wb) == CODE_N) ++wb;
   while (wb < we && nibble_at(nib, c.nib_base + we - 1) == CODE_N) --we;
 }
-CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) {
+template <bool BANDED>
+CAL_D void align_body(const AlignArgs& a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_cand) return;
   const uint64_t key = a.cand[i];
@@ -286,7 +287,7 @@ CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) {
   const int64_t base = i * a.slots;
   for (int s = 0; s < a.slots; ++s) a.valid[base + s] = 0;
   GuideAln aln;
-  if (g.k_edits <= ALIGN_KB) {            // register-resident diagonal band (defaults and d = 6 land here)
+  if (BANDED) {                           // register-resident diagonal band: every guide of the launch has k_edits <= ALIGN_KB (defaults, d = 6)
     if (!band_align_k<ALIGN_KB>(g, a.sc, fetch, col, aln)) return;
   } else {                                // wide thresholds / best mode: full rectangle in local memory
     uint8_t trace[(CALITAS_MAX_PROTOSPACER + 1) * (MAX_SPAN + 1)];
@@ -304,6 +305,9 @@ CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) {
     }
   }
 }
+
+CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) { align_body<true>(a); }
+CAL_KERNEL __launch_bounds__(128) k_align_wide(AlignArgs a) { align_body<false>(a); }
 
 // ------------------------------------------------------------------------------------------------------------------------------------
 // k_canon: per (guide, window, strand) group — SequentialGuideAligner.scala:315-322
@@ -523,7 +527,7 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
 }
 
 struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> align -> canon -> compaction
-  calitas_engine* e; const GuideSpec* d_specs; int slots; bool explicit_mode;
+  calitas_engine* e; const GuideSpec* d_specs; int slots; bool explicit_mode; bool banded;
   const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base; bool drop_halo;
 };
 
@@ -545,7 +549,9 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows; aa.task_base = P.task_base;
   aa.hits = e->hits.as<calitas_hit>(); aa.valid = e->valid.as<uint8_t>();
   dev::event_record(e->ev[2], s);
-  CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); ++e->launches;
+  if (P.banded) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
+  else { CAL_LAUNCH(k_align_wide, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_wide"); }
+  ++e->launches;
   dev::event_record(e->ev[3], s);
   // 3. canonicalise per (guide, window, strand)
   e->rank.ensure((size_t)n_slots * 4); e->perm.ensure((size_t)n_slots * 4); e->flag.ensure((size_t)n_slots * 4); e->pos.ensure((size_t)n_slots * 4); e->slot_owned.ensure((size_t)n_slots);
@@ -627,7 +633,7 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
   dev::Stream s = e->stream; dev::set_device(e->device);
   e->launches = 0;
   dev::event_record(e->ev[0], s);
-  int slots = 1; for (auto& sp : specs) slots = std::max(slots, sp.slots);
+  int slots = 1; bool banded = true; for (auto& sp : specs) { slots = std::max(slots, sp.slots); if (sp.k_edits > ALIGN_KB) banded = false; }
   e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
   e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
   double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { (int64_t)windows.size(), 0, 0, 0, 0, 0, 0, 0 };
@@ -654,7 +660,7 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
     ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
     counts[1] += (int64_t)n_cand;
     // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
-    Pipeline P{ e, e->specs.as<GuideSpec>(), slots, true, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true };
+    Pipeline P{ e, e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true };
     int64_t n_aln = 0;
     const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
     if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
@@ -809,7 +815,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       size_t t_begin = 0, t_end = ts.tiles.size();
       if (chrom_idx >= 0) { t_begin = t_end = 0; bool in = false; for (size_t t = 0; t < ts.tiles.size(); ++t) { if (ts.tiles[t].contig == chrom_idx) { if (!in) { t_begin = t; in = true; } t_end = t + 1; } } }
       const size_t n_tiles = t_end - t_begin;
-      int slots = 1; for (int g = g0; g < g1; ++g) slots = std::max(slots, specs[(size_t)g].slots);
+      int slots = 1; bool banded = true; for (int g = g0; g < g1; ++g) { slots = std::max(slots, specs[(size_t)g].slots); if (specs[(size_t)g].k_edits > ALIGN_KB) banded = false; }
       const int ng = g1 - g0;
       const int64_t tile_bases = (int64_t)(TILE_WINDOWS - 1) * step + window_size;
       const size_t smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2) * 4;
@@ -834,7 +840,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       if (n_tiles) { ms[1] += dev::event_ms(e->ev[4], e->ev[5]); counts[6] += 1; int64_t nb = 0; for (size_t t = t_begin; t < t_end; ++t) nb += (int64_t)(ts.tiles[t].nwin - 1) * step + window_size; counts[7] += nb; }
       if (g0 == 0) { for (size_t c = 0; c < ts.contigs.size(); ++c) if (chrom_idx < 0 || (int)c == chrom_idx) counts[0] += ts.contigs[c].own_hi - ts.contigs[c].own_lo; }
       counts[1] += (int64_t)n_cand;
-      Pipeline P{ e, e->specs.as<GuideSpec>(), slots, false, ref->d_nib, ts.d_contigs, (int)ts.contigs.size(), window_size, step, nullptr, 0, dedup == 0 };
+      Pipeline P{ e, e->specs.as<GuideSpec>(), slots, false, banded, ref->d_nib, ts.d_contigs, (int)ts.contigs.size(), window_size, step, nullptr, 0, dedup == 0 };
       int64_t n_aln = 0;
       const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
       if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
