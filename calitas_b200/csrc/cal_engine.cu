@@ -371,16 +371,24 @@ CAL_HD int32_t soa_overlap(const int32_t* s_start, const int32_t* s_end, int64_t
   const int32_t hi = s_end[a] < s_end[b] ? s_end[a] : s_end[b], lo = s_start[a] > s_start[b] ? s_start[a] : s_start[b];
   const int32_t o = hi - lo; return o > 0 ? o : 0;
 }
-CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key1, const int32_t* s_start, const int32_t* s_end, const int32_t* s_score, const uint8_t* s_owned, int64_t n, int32_t max_overlap, uint32_t* keep) {
+// One thread per sweep segment.  With segmented != 0 (max_overlap >= 1) a segment starts at a group boundary or where the next hit starts
+// more than CALITAS_MAX_OPS bases after its predecessor: no earlier hit can then overlap it at all, so the reference's sequential sweep
+// restarts there unconditionally and segments are independent.  With max_overlap <= 0 every later hit "overlaps" (>= 0) and the sweep is
+// run per group, as the reference's loop would.
+CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key1, const int32_t* s_start, const int32_t* s_end, const int32_t* s_score, const uint8_t* s_owned, int64_t n, int32_t max_overlap,
+                                          int32_t segmented, uint32_t* keep) {
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i0 >= n) return;
   const uint64_t grp = key1[i0] >> 31;
-  if (i0 > 0 && (key1[i0 - 1] >> 31) == grp) return;
+  if (i0 > 0 && (key1[i0 - 1] >> 31) == grp && !(segmented && s_start[i0] - s_start[i0 - 1] > CALITAS_MAX_OPS)) return;
   int64_t i = i0;
-  while (i < n && (key1[i] >> 31) == grp) {
+  for (;;) {
     const int64_t cur = i++;
     while (i < n && (key1[i] >> 31) == grp && soa_overlap(s_start, s_end, i, cur) >= max_overlap && s_score[i] <= s_score[cur]) { keep[i] = 0; ++i; }
-    keep[cur] = ((i >= n || (key1[i] >> 31) != grp || soa_overlap(s_start, s_end, i, cur) < max_overlap) && s_owned[cur]) ? 1u : 0u;   // halo hits take part, are never reported
+    const bool has_next = i < n && (key1[i] >> 31) == grp;
+    keep[cur] = ((!has_next || soa_overlap(s_start, s_end, i, cur) < max_overlap) && s_owned[cur]) ? 1u : 0u;   // halo hits take part, are never reported
+    if (!has_next) break;
+    if (segmented && s_start[i] - s_start[i - 1] > CALITAS_MAX_OPS) break;                                       // next segment has its own thread
   }
 }
 // compaction of (idx, key) by keep; key is rewritten to the final sort key guide | contig | coordinate_start | strand
@@ -587,7 +595,7 @@ int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out
   // now key1[i], idx[i] sorted by (guide, contig, strand, start, -score, arrival)
   e->sstart.ensure((size_t)n * 4); e->send.ensure((size_t)n * 4); e->sscore.ensure((size_t)n * 4); e->sowned.ensure((size_t)n); e->flag.ensure((size_t)n * 4); e->pos.ensure((size_t)n * 4);
   CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, hits, e->kept_owned.as<uint8_t>(), e->idx.as<uint32_t>(), n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
-  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, e->key1.as<uint64_t>(), e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, max_overlap, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
+  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, e->key1.as<uint64_t>(), e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, max_overlap, max_overlap >= 1 ? 1 : 0, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
   tb = dev::exclusive_sum_u32_tmp((size_t)n); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n, s); ++e->launches;
   uint32_t last_pos = 0, last_flag = 0;
