@@ -22,7 +22,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-OPS_PER_COLUMN = 17          # integer instructions of one Myers column update incl. threshold test (kernel k_scan_tiled)
+# SASS instruction mix of one Myers column update of one guide in k_scan_tiled's branch-free inner loop (counted from cuobjdump -sass,
+# see DESIGN.md "k_scan_tiled"): ALU pipe 7 LOP3 + 2 LEA.HI + 0.5 SHF + 0.5 VIMNMX3; FMA pipe 3 IMAD.IADD + 0.5 IMAD.SHL + 0.5 IMAD; 1 LDS.
+ALU_OPS_PER_COLUMN = 10
+ISSUE_SLOTS_PER_COLUMN = 15
 REF_OPS_PER_BP_GUIDE = 240   # 2 strands x 20 rows x 6 int32 ops of the reference's recurrence
 
 
@@ -249,10 +252,10 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        int_peaks = {k: engine.microbench_int(i) for i, k in enumerate(("alu_lop_add", "fma_imad", "mixed_lop_imad"))}
+        int_peaks = {k: engine.microbench_int(i) for i, k in enumerate(("alu_lop3", "fma_imad", "both_lop3_imad", "fma_imad_hi", "alu_lea_hi"))}
         own0 = sum(oe[c] - ob[c] for c in range(n))
-        scan_ops = own0 * G * 2 * OPS_PER_COLUMN                                # rank 0's shard
-        int_achieved = scan_ops / (st["ms_scan"] * 1e-3) / 1e12
+        columns = own0 * G * 2                                                  # rank 0's shard: one Myers column per base, strand and guide
+        int_achieved = columns * ALU_OPS_PER_COLUMN / (st["ms_scan"] * 1e-3) / 1e12
         out = {
             "metric": "Gbp*guides/s SearchReference (hg38-size synthetic)", "value": value, "unit": "Gbp*guides/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -265,9 +268,12 @@ def main():
                          "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "streaming read of the 4-bit packed shard once per launch; the kernel is integer-ALU-bound (see roofline_int), so the HBM fraction is small by design",
                          "avg_launch_ms": scan_launch_ms, "launches_per_step": launches, "share_of_step": st["ms_scan"] / st["ms_total"]},
-            "roofline_int": {"kernel": "k_scan_tiled", "bound": "int_alu", "achieved": int_achieved, "peak": int_peaks["alu_lop_add"], "unit": "Tiop/s",
-                             "frac": int_achieved / int_peaks["alu_lop_add"] if int_peaks["alu_lop_add"] else None,
-                             "ops_per_column": OPS_PER_COLUMN, "measured_peaks_tiops": int_peaks,
+            "roofline_int": {"kernel": "k_scan_tiled", "bound": "int_alu_pipe", "achieved": int_achieved, "peak": int_peaks["alu_lop3"], "unit": "Tiop/s (ALU-pipe thread instructions)",
+                             "frac": int_achieved / int_peaks["alu_lop3"] if int_peaks["alu_lop3"] else None,
+                             "alu_ops_per_column": ALU_OPS_PER_COLUMN, "issue_slots_per_column": ISSUE_SLOTS_PER_COLUMN,
+                             "issue_frac": columns * ISSUE_SLOTS_PER_COLUMN / (st["ms_scan"] * 1e-3) / 1e12 / int_peaks["both_lop3_imad"] if int_peaks["both_lop3_imad"] else None,
+                             "peak_source": "measured on this GPU by calitas_microbench_int (LOP3 chains; no integer peak in MEASURED_PEAKS.json)",
+                             "measured_peaks_tiops": int_peaks,
                              "reference_equivalent_tiops": bpg * REF_OPS_PER_BP_GUIDE / (dev_ms_max * 1e-3) / 1e12,
                              "gcups_equivalent": value * 40},
             "breakdown_ms": {"scan": st["ms_scan"], "align": st["ms_align"], "sort_canon_dedup": st["ms_other"], "d2h": st["ms_d2h"], "wall": st["wall_ms"]},

@@ -402,28 +402,33 @@ CAL_KERNEL __launch_bounds__(256) k_compact_keepers(const uint64_t* key1, const 
 
 // ------------------------------------------------------------------------------------------------------------------------------------
 // k_int_peak: integer-issue microbenchmark for the roofline denominator (no integer peak in MEASURED_PEAKS.json).
-// kind 0: dependent-free LOP3 + IADD chains (the ALU pipe the scan kernel lives on); kind 1: IMAD chains (FMA pipe); kind 2: both interleaved.
+// Eight chains per thread; every statement reads two other chains, so ptxas cannot fold consecutive operations of a chain into one.
+//   kind 0  LOP3 only            -> ALU-pipe issue rate (the pipe k_scan_tiled is bound by)
+//   kind 1  IMAD only            -> FMA-pipe issue rate
+//   kind 2  LOP3 and IMAD, 1:1   -> both pipes together (scheduler issue limit)
+//   kind 3  IMAD.HI only, kind 4 LEA.HI only: rates of the two candidate instructions for the score update
 // ------------------------------------------------------------------------------------------------------------------------------------
+#ifndef CAL_HOSTSIM
+CAL_D uint32_t pk_lop3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+CAL_D uint32_t pk_imad(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+CAL_D uint32_t pk_imadhi(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+CAL_D uint32_t pk_leahi(uint32_t a, uint32_t b, uint32_t c) { return b + (a >> 31) + (c & 0u); }
+#else
+inline uint32_t pk_lop3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
+inline uint32_t pk_imad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+inline uint32_t pk_imadhi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c; }
+inline uint32_t pk_leahi(uint32_t a, uint32_t b, uint32_t c) { return b + (a >> 31) + (c & 0u); }
+#endif
+#define CAL_PEAK_ROUND(OP_EVEN, OP_ODD) _Pragma("unroll") for (int k = 0; k < 8; ++k) a[k] = (k & 1) ? OP_ODD(a[k], a[(k + 3) & 7], a[(k + 5) & 7]) : OP_EVEN(a[k], a[(k + 3) & 7], a[(k + 5) & 7]);
 CAL_KERNEL __launch_bounds__(256) k_int_peak(uint32_t* out, int iters, int kind, uint32_t seed) {
-  uint32_t a[8], b = seed | 1u, c = seed * 2654435761u + threadIdx.x;
+  uint32_t a[8], c = seed * 2654435761u + threadIdx.x;
 #pragma unroll
   for (int k = 0; k < 8; ++k) a[k] = c + k * 0x9E3779B9u;
-  if (kind == 0) {
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { a[k] = (a[k] & b) ^ c; a[k] = a[k] + b; }      // 1 LOP3 + 1 IADD per statement pair
-    }
-  } else if (kind == 1) {
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { a[k] = a[k] * b + c; a[k] = a[k] * c + b; }     // 2 IMAD
-    }
-  } else {
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { a[k] = (a[k] & b) ^ c; a[k] = a[k] * b + c; }   // 1 LOP3 + 1 IMAD
-    }
-  }
+  if (kind == 0)      for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_lop3, pk_lop3) CAL_PEAK_ROUND(pk_lop3, pk_lop3) }
+  else if (kind == 1) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_imad, pk_imad) CAL_PEAK_ROUND(pk_imad, pk_imad) }
+  else if (kind == 2) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_lop3, pk_imad) CAL_PEAK_ROUND(pk_imad, pk_lop3) }
+  else if (kind == 3) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_imadhi, pk_imadhi) CAL_PEAK_ROUND(pk_imadhi, pk_imadhi) }
+  else                for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_leahi, pk_leahi) CAL_PEAK_ROUND(pk_leahi, pk_leahi) }
   uint32_t r = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) r ^= a[k];
@@ -920,7 +925,7 @@ int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_gui
 
 int calitas_microbench_int(calitas_engine* e, int32_t kind, double* tera_ops_per_s) {
   return guarded([&]() -> int {
-    if (!e || !tera_ops_per_s || kind < 0 || kind > 2) throw InvalidArgument("bad microbench arguments");
+    if (!e || !tera_ops_per_s || kind < 0 || kind > 4) throw InvalidArgument("bad microbench arguments");
     dev::set_device(e->device); dev::Stream s = e->stream;
     const int iters = 4096; const unsigned grid = (unsigned)dev::sm_count(e->device) * 16, block = 256;
     e->tmp.ensure((size_t)grid * block * 4);

@@ -138,7 +138,8 @@ void calitas_hitset_free(calitas_hitset* h);
 int calitas_hitset_stats(const calitas_hitset* h, double ms[8], int64_t counts[8]);
 
 /* Integer-issue microbenchmark used as the roofline denominator of the scan kernel (no integer peak is published or in
- * MEASURED_PEAKS.json).  kind 0: LOP3+IADD chains (ALU pipe), 1: IMAD chains (FMA pipe), 2: LOP3+IMAD interleaved. */
+ * MEASURED_PEAKS.json).  Result = executed thread-level integer instructions per second / 1e12.  kind 0: LOP3 chains (ALU pipe),
+ * 1: IMAD chains (FMA pipe), 2: LOP3 and IMAD 1:1 (both pipes, scheduler issue limit), 3: IMAD.HI, 4: LEA.HI. */
 int calitas_microbench_int(calitas_engine* e, int32_t kind, double* tera_ops_per_s);
 
 /* ---- host-side rendering (ReferenceHit.Builder.build, ReferenceHit.scala:210-254; GuideAlignment.scala:10-50,99-163) ---- */
