@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--guides", type=int, default=100, help="guides per step (north_star: 100 guides, defaults d=5 p=1 g=3)")
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale; 1.0 = 3.1 Gbp with hg38 contig lengths")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lib", default=None, help="alternative build of libcalitas_b200.so (kernel A/B experiments); default = the product library")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -168,7 +169,7 @@ def main():
     import torch
     import torch.distributed as dist
     from calitas_b200 import synth
-    from calitas_b200._capi import Engine, Limits
+    from calitas_b200._capi import Engine, Library, Limits
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
@@ -178,7 +179,7 @@ def main():
     guides = guide_list(args.guides)
     genome = synth.hg38_like_genome(args.scale, guides=guides, sites_per_guide=200)
     n = len(genome.lengths)
-    engine = Engine(local_rank)
+    engine = Engine(local_rank, lib=Library(os.path.abspath(args.lib)) if args.lib else None)
 
     # ---- this rank's contig-range shard: generate only the bases it holds ------------------------------------------------------
     import ctypes as C
