@@ -37,6 +37,13 @@ inline void init(int device) {
 inline void set_device(int device) { check(cudaSetDevice(device), "cudaSetDevice"); }
 inline int sm_count(int device) { int v = 0; check(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device), "attr"); return v; }
 inline Stream stream_create() { Stream s; check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate"); return s; }
+// high != 0: the greatest priority the device offers, else the least (pending thread blocks of a high-priority stream are dispatched first)
+inline Stream stream_create_prio(int high) {
+  int least = 0, greatest = 0; check(cudaDeviceGetStreamPriorityRange(&least, &greatest), "cudaDeviceGetStreamPriorityRange");
+  Stream s; check(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? greatest : least), "cudaStreamCreateWithPriority"); return s;
+}
+inline void stream_wait(Stream s, cudaEvent_t e) { check(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent"); }
+inline void event_sync(cudaEvent_t e) { check(cudaEventSynchronize(e), "cudaEventSynchronize"); }
 inline void stream_destroy(Stream s) { cudaStreamDestroy(s); }
 inline void stream_sync(Stream s) { check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
 inline Event event_create() { Event e; check(cudaEventCreate(&e), "cudaEventCreate"); return e; }
@@ -120,12 +127,15 @@ inline void init(int) {}
 inline void set_device(int) {}
 inline int sm_count(int) { return 4; }
 inline Stream stream_create() { return 0; }
+inline Stream stream_create_prio(int) { return 0; }
 inline void stream_destroy(Stream) {}
 inline void stream_sync(Stream) {}
 inline Event event_create() { return new std::chrono::steady_clock::time_point(); }
 inline void event_destroy(Event e) { delete e; }
 inline void event_record(Event e, Stream) { *e = std::chrono::steady_clock::now(); }
 inline double event_ms(Event a, Event b) { return std::chrono::duration<double, std::milli>(*b - *a).count(); }
+inline void stream_wait(Stream, Event) {}
+inline void event_sync(Event) {}
 inline void* alloc(size_t bytes) { return std::calloc(bytes ? bytes : 1, 1); }
 inline void free_(void* p) { std::free(p); }
 inline void* alloc_host(size_t bytes) { return std::calloc(bytes ? bytes : 1, 1); }

@@ -469,9 +469,18 @@ struct calitas_hitset {
   calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 
+enum { CE_SCAN_B = 0, CE_SCAN_E, CE_COUNT, CE_SORTED, CE_ALIGN_B, CE_ALIGN_E, CE_TAIL_B, CE_TAIL_E, CE_COPY_B, CE_COPY_E, CE_N };
+struct ChunkEvents { dev::Event ev[CE_N]; };
+
 struct calitas_engine {
-  int device = 0; dev::Stream stream; Scores sc; calitas_costs costs;
+  int device = 0; Scores sc; calitas_costs costs;
+  // stream: sort/align/canonicalise/dedup (greatest priority); scan_stream: k_scan_tiled of calitas_search (least priority, so that the tail of
+  // guide chunk c slips in between the blocks of chunk c+1's scan); copy_stream: D2H of finished hit segments
+  dev::Stream stream, scan_stream, copy_stream;
   dev::Event ev[8];
+  std::vector<ChunkEvents> chunk_ev;
+  size_t out_hits_hint = 1u << 16;
+  DBuf cand_b;
   DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, kept, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, kept_owned, sowned;
   unsigned long long* h_count = nullptr;       // pinned
   unsigned long long* d_count = nullptr;
@@ -540,7 +549,8 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
 }
 
 struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> align -> canon -> compaction
-  calitas_engine* e; const GuideSpec* d_specs; int slots; bool explicit_mode; bool banded;
+  calitas_engine* e; const uint64_t* cand; dev::Event ev_sorted, ev_align_b, ev_align_e;   // candidate keys; events recorded after the sort / around k_align
+  const GuideSpec* d_specs; int slots; bool explicit_mode; bool banded;
   const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base; bool drop_halo;
 };
 
@@ -548,12 +558,13 @@ struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> alig
 int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   calitas_engine* e = P.e; dev::Stream s = e->stream;
   n_alignments = 0;
-  if (n_cand == 0) return 0;
+  if (n_cand == 0) { dev::event_record(P.ev_sorted, s); dev::event_record(P.ev_align_b, s); dev::event_record(P.ev_align_e, s); return 0; }
   if (n_cand * (int64_t)P.slots >= (1ll << 32)) throw LimitExceeded("too many candidate alignments in one batch");
   // 1. sort candidate keys -> (guide, window, strand, end column)
   e->cand_sorted.ensure((size_t)n_cand * 8);
   size_t tb = dev::sort_keys_u64_tmp((size_t)n_cand, 0, 64); e->tmp.ensure(tb);
-  dev::sort_keys_u64(e->tmp.p, tb, e->cand.as<uint64_t>(), e->cand_sorted.as<uint64_t>(), (size_t)n_cand, 0, 64, s); ++e->launches;
+  dev::sort_keys_u64(e->tmp.p, tb, P.cand, e->cand_sorted.as<uint64_t>(), (size_t)n_cand, 0, 64, s); ++e->launches;
+  dev::event_record(P.ev_sorted, s);                      // the candidate buffer may be refilled by the next scan from here on
   // 2. align
   const int64_t n_slots = n_cand * P.slots;
   e->hits.ensure((size_t)n_slots * sizeof(calitas_hit)); e->valid.ensure((size_t)n_slots);
@@ -561,11 +572,11 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   aa.cand = e->cand_sorted.as<uint64_t>(); aa.n_cand = n_cand; aa.specs = P.d_specs; aa.sc = e->sc; aa.slots = P.slots; aa.explicit_mode = P.explicit_mode ? 1 : 0;
   aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows; aa.task_base = P.task_base;
   aa.hits = e->hits.as<calitas_hit>(); aa.valid = e->valid.as<uint8_t>();
-  dev::event_record(e->ev[2], s);
+  dev::event_record(P.ev_align_b, s);
   if (P.banded) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
   else { CAL_LAUNCH(k_align_wide, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_wide"); }
   ++e->launches;
-  dev::event_record(e->ev[3], s);
+  dev::event_record(P.ev_align_e, s);
   // 3. canonicalise per (guide, window, strand)
   e->rank.ensure((size_t)n_slots * 4); e->perm.ensure((size_t)n_slots * 4); e->flag.ensure((size_t)n_slots * 4); e->pos.ensure((size_t)n_slots * 4); e->slot_owned.ensure((size_t)n_slots);
   CanonArgs ca; std::memset(&ca, 0, sizeof ca);
@@ -673,7 +684,7 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
     ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
     counts[1] += (int64_t)n_cand;
     // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
-    Pipeline P{ e, e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true };
+    Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true };
     int64_t n_aln = 0;
     const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
     if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
@@ -710,7 +721,7 @@ int calitas_engine_create(int32_t device_id, const calitas_costs* costs, calitas
     dev::init(device_id);
     std::unique_ptr<calitas_engine> e(new calitas_engine());
     e->device = device_id; e->costs = c; e->sc = make_scores(c);
-    e->stream = dev::stream_create();
+    e->stream = dev::stream_create_prio(1); e->scan_stream = dev::stream_create_prio(0); e->copy_stream = dev::stream_create_prio(1);
     for (auto& ev : e->ev) ev = dev::event_create();
     e->h_count = (unsigned long long*)dev::alloc_host(64);
     e->d_count = (unsigned long long*)dev::alloc(64);
@@ -723,13 +734,14 @@ void calitas_engine_destroy(calitas_engine* e) {
   if (!e) return;
   try {
     dev::set_device(e->device);
-    dev::stream_sync(e->stream);
-    for (DBuf* b : { &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->kept, &e->out, &e->tmp, &e->key1, &e->keyA,
+    dev::stream_sync(e->scan_stream); dev::stream_sync(e->stream); dev::stream_sync(e->copy_stream);
+    for (DBuf* b : { &e->cand_b, &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->kept, &e->out, &e->tmp, &e->key1, &e->keyA,
                      &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp, &e->slot_owned, &e->kept_owned, &e->sowned }) b->release();
     for (auto& p : e->pinned_pool) dev::free_host(p.p);
     dev::free_host(e->h_count); dev::free_(e->d_count);
     for (auto& ev : e->ev) dev::event_destroy(ev);
-    dev::stream_destroy(e->stream);
+    for (auto& ce : e->chunk_ev) for (auto& ev : ce.ev) dev::event_destroy(ev);
+    dev::stream_destroy(e->stream); dev::stream_destroy(e->scan_stream); dev::stream_destroy(e->copy_stream);
   } catch (...) {}
   delete e;
 }
@@ -797,77 +809,149 @@ void calitas_reference_free(calitas_engine* e, calitas_reference* r) {
   delete r;
 }
 
+// One guide chunk of a search: consecutive guides sharing the raw guide length, hence the window tiling (SearchReference.scala:528-530).
+struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots; bool banded; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; };
+
 int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
                    int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out) {
   return guarded([&]() -> int {
     if (!e || !ref_c || !out) throw InvalidArgument("bad search arguments");
     *out = nullptr;
     calitas_reference* ref = const_cast<calitas_reference*>(ref_c);
-    dev::set_device(e->device); dev::Stream s = e->stream;
+    dev::set_device(e->device); dev::Stream s = e->stream, ss = e->scan_stream, cs = e->copy_stream;
     std::vector<GuideDef> defs; std::vector<GuideSpec> specs = build_specs(e, n_guides, guides, limits, false, &defs);
     if (window_size <= 0 || (uint32_t)window_size > MAX_WINDOW_LEN) throw InvalidArgument("window size out of range");
     int chrom_idx = -1;
     if (chrom && chrom[0]) { for (size_t c = 0; c < ref->names.size(); ++c) if (ref->names[c] == chrom) chrom_idx = (int)c; if (chrom_idx < 0) throw InvalidArgument(std::string("Unknown chromosome: ") + chrom); }
-    e->launches = 0;
-    dev::event_record(e->ev[0], s);
-    e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
-    double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    counts[4] = (int64_t)(specs.size() * sizeof(GuideSpec));
-    int64_t n_out = 0;
+    // ---- plan: guide chunks and their window tilings ---------------------------------------------------------------------------
     const int G_CHUNK = 16;
-    int g0 = 0;
-    while (g0 < n_guides) {
-      // a chunk = consecutive guides sharing the raw guide length, hence the window tiling (SearchReference.scala:528-530)
-      const int raw_len = (int)defs[(size_t)g0].raw.size();
-      int g1 = g0 + 1; while (g1 < n_guides && g1 - g0 < G_CHUNK && (int)defs[(size_t)g1].raw.size() == raw_len) ++g1;
-      const int overlap = raw_len + limits->max_guide_diffs + limits->max_gaps_between_guide_and_pam - 1;
-      const int step = window_size - overlap;
-      if (step <= 0) throw InvalidArgument("window size must exceed guide length + max-guide-diffs + max-gaps-between-guide-and-pam - 1");
-      calitas_reference::TileSet& ts = tileset_for(e, ref, window_size, step, chrom);
+    std::vector<SearchChunk> chunks;
+    for (int g0 = 0; g0 < n_guides;) {
+      SearchChunk ch; ch.g0 = g0; ch.raw_len = (int)defs[(size_t)g0].raw.size();
+      int g1 = g0 + 1; while (g1 < n_guides && g1 - g0 < G_CHUNK && (int)defs[(size_t)g1].raw.size() == ch.raw_len) ++g1;
+      ch.g1 = g1;
+      const int overlap = ch.raw_len + limits->max_guide_diffs + limits->max_gaps_between_guide_and_pam - 1;
+      ch.step = window_size - overlap;
+      if (ch.step <= 0) throw InvalidArgument("window size must exceed guide length + max-guide-diffs + max-gaps-between-guide-and-pam - 1");
+      ch.ts = &tileset_for(e, ref, window_size, ch.step, chrom);
       // tiles of one contig are contiguous: restrict the launch for -c
-      size_t t_begin = 0, t_end = ts.tiles.size();
-      if (chrom_idx >= 0) { t_begin = t_end = 0; bool in = false; for (size_t t = 0; t < ts.tiles.size(); ++t) { if (ts.tiles[t].contig == chrom_idx) { if (!in) { t_begin = t; in = true; } t_end = t + 1; } } }
-      const size_t n_tiles = t_end - t_begin;
-      int slots = 1; bool banded = true; for (int g = g0; g < g1; ++g) { slots = std::max(slots, specs[(size_t)g].slots); if (specs[(size_t)g].k_edits > ALIGN_KB) banded = false; }
+      ch.t_begin = 0; size_t t_end = ch.ts->tiles.size();
+      if (chrom_idx >= 0) { ch.t_begin = t_end = 0; bool in = false; for (size_t t = 0; t < ch.ts->tiles.size(); ++t) { if (ch.ts->tiles[t].contig == chrom_idx) { if (!in) { ch.t_begin = t; in = true; } t_end = t + 1; } } }
+      ch.n_tiles = t_end - ch.t_begin;
+      ch.slots = 1; ch.banded = true; for (int g = g0; g < g1; ++g) { ch.slots = std::max(ch.slots, specs[(size_t)g].slots); if (specs[(size_t)g].k_edits > ALIGN_KB) ch.banded = false; }
       const int ng = g1 - g0;
-      const int64_t tile_bases = (int64_t)(TILE_WINDOWS - 1) * step + window_size;
-      const size_t smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2) * 4;
-      if (smem > 200 * 1024) throw LimitExceeded("window size too large for the shared-memory tile");
-#ifndef CAL_HOSTSIM
-      dev::check(cudaFuncSetAttribute(k_scan_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
-#endif
-      unsigned long long n_cand = 0;
-      if (n_tiles) for (;;) {
-        e->cand.ensure(e->cand_cap_hint * 8);
-        dev::zero(e->d_count, 8, s);
-        ScanArgs sa{ ref->d_nib, ts.d_contigs, ts.d_tiles + t_begin, e->specs.as<GuideSpec>(), g0, g1, window_size, step, raw_len, e->cand.as<uint64_t>(), e->d_count, (unsigned long long)e->cand_cap_hint };
-        dev::event_record(e->ev[4], s);
-        const int scan_slots = ng >= 8 ? 4 : (ng >= 3 ? 2 : 1);     // guide slots per window: more resident warps when the chunk has enough guides
-        CAL_LAUNCH(k_scan_tiled, (unsigned)n_tiles, SCAN_THREADS * scan_slots, smem, s, 2, sa); dev::launch_check("k_scan_tiled"); ++e->launches;
-        dev::event_record(e->ev[5], s);
-        dev::d2h(e->h_count, e->d_count, 8, s); dev::stream_sync(s);
-        n_cand = *e->h_count;
-        if (n_cand <= e->cand_cap_hint) break;
-        e->cand_cap_hint = (size_t)(n_cand + n_cand / 4);          // pool too small: grow and re-run, never truncate
-      }
-      if (n_tiles) { ms[1] += dev::event_ms(e->ev[4], e->ev[5]); counts[6] += 1; int64_t nb = 0; for (size_t t = t_begin; t < t_end; ++t) nb += (int64_t)(ts.tiles[t].nwin - 1) * step + window_size; counts[7] += nb; }
-      if (g0 == 0) { for (size_t c = 0; c < ts.contigs.size(); ++c) if (chrom_idx < 0 || (int)c == chrom_idx) counts[0] += ts.contigs[c].own_hi - ts.contigs[c].own_lo; }
-      counts[1] += (int64_t)n_cand;
-      Pipeline P{ e, e->specs.as<GuideSpec>(), slots, false, banded, ref->d_nib, ts.d_contigs, (int)ts.contigs.size(), window_size, step, nullptr, 0, dedup == 0 };
-      int64_t n_aln = 0;
-      const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
-      if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
-      counts[2] += n_aln;
-      if (dedup) n_out += run_dedup(e, n_kept, limits->max_overlap, n_out);
-      else if (n_kept) {
-        e->out.ensure_keep((size_t)(n_out + n_kept) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
-        dev::d2d(e->out.as<calitas_hit>() + n_out, e->kept.p, (size_t)n_kept * sizeof(calitas_hit), s);
-        n_out += n_kept;
-      }
+      const int64_t tile_bases = (int64_t)(TILE_WINDOWS - 1) * ch.step + window_size;
+      ch.smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2) * 4;
+      if (ch.smem > 200 * 1024) throw LimitExceeded("window size too large for the shared-memory tile");
+      ch.scan_slots = ng >= 8 ? 4 : (ng >= 3 ? 2 : 1);     // guide slots per window: more resident warps when the chunk has enough guides
+      ch.bases = 0; for (size_t t = ch.t_begin; t < t_end; ++t) ch.bases += (int64_t)(ch.ts->tiles[t].nwin - 1) * ch.step + window_size;
+      chunks.push_back(ch);
       g0 = g1;
     }
+    const size_t n_chunks = chunks.size();
+    while (e->chunk_ev.size() < n_chunks) { ChunkEvents ce; for (auto& ev : ce.ev) ev = dev::event_create(); e->chunk_ev.push_back(ce); }
+    e->launches = 0;
+    dev::event_record(e->ev[0], ss);
+    e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), ss);
+    double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    counts[4] = (int64_t)(specs.size() * sizeof(GuideSpec));
+    { const calitas_reference::TileSet& ts = *chunks[0].ts; for (size_t c = 0; c < ts.contigs.size(); ++c) if (chrom_idx < 0 || (int)c == chrom_idx) counts[0] += ts.contigs[c].own_hi - ts.contigs[c].own_lo; }
+    // ---- pipeline: scan(c+1) runs on the scan stream while sort/align/canon/dedup of chunk c run on the main stream and finished hit
+    //      segments go to pinned host memory on the copy stream -------------------------------------------------------------------
+    DBuf* cand_slot[2] = { &e->cand, &e->cand_b };
+    auto launch_scan = [&](size_t c) {
+      const SearchChunk& ch = chunks[c]; const int slot = (int)(c & 1); ChunkEvents& ce = e->chunk_ev[c];
+      cand_slot[slot]->ensure(e->cand_cap_hint * 8);
+      if (c >= 2) dev::stream_wait(ss, e->chunk_ev[c - 2].ev[CE_SORTED]);       // the previous user of this candidate slot has been sorted away
+      dev::zero(e->d_count + slot, 8, ss);
+      dev::event_record(ce.ev[CE_SCAN_B], ss);
+      if (ch.n_tiles) {
+#ifndef CAL_HOSTSIM
+        dev::check(cudaFuncSetAttribute(k_scan_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem), "cudaFuncSetAttribute");
+#endif
+        ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len,
+                     cand_slot[slot]->as<uint64_t>(), e->d_count + slot, (unsigned long long)e->cand_cap_hint };
+        CAL_LAUNCH(k_scan_tiled, (unsigned)ch.n_tiles, SCAN_THREADS * ch.scan_slots, ch.smem, ss, 2, sa); dev::launch_check("k_scan_tiled"); ++e->launches;
+        counts[6] += 1; counts[7] += ch.bases;
+      }
+      dev::event_record(ce.ev[CE_SCAN_E], ss);
+      dev::d2h(e->h_count + slot, e->d_count + slot, 8, ss);
+      dev::event_record(ce.ev[CE_COUNT], ss);
+    };
+    PinnedBuf pin = take_pinned(e, std::max<size_t>(e->out_hits_hint, 1024) * sizeof(calitas_hit));
+    int64_t n_out = 0; size_t copies = 0;
+    try {
+      launch_scan(0);
+      for (size_t c = 0; c < n_chunks; ++c) {
+        const SearchChunk& ch = chunks[c]; const int slot = (int)(c & 1); ChunkEvents& ce = e->chunk_ev[c];
+        if (c + 1 < n_chunks) launch_scan(c + 1);
+        unsigned long long n_cand = 0;
+        for (;;) {
+          dev::event_sync(ce.ev[CE_COUNT]);
+          n_cand = e->h_count[slot];
+          if (n_cand <= e->cand_cap_hint) break;
+          // pool too small: grow and re-run this chunk's scan (and the one queued behind it), never truncate
+          dev::stream_sync(ss);
+          if (c + 1 < n_chunks) { counts[6] -= chunks[c + 1].n_tiles ? 1 : 0; counts[7] -= chunks[c + 1].bases; }
+          counts[6] -= ch.n_tiles ? 1 : 0; counts[7] -= ch.bases;
+          e->cand_cap_hint = (size_t)(n_cand + n_cand / 4);
+          launch_scan(c); if (c + 1 < n_chunks) launch_scan(c + 1);
+        }
+        counts[1] += (int64_t)n_cand;
+        dev::event_record(ce.ev[CE_TAIL_B], s);
+        Pipeline P{ e, cand_slot[slot]->as<uint64_t>(), ce.ev[CE_SORTED], ce.ev[CE_ALIGN_B], ce.ev[CE_ALIGN_E], e->specs.as<GuideSpec>(), ch.slots, false, ch.banded,
+                    ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, 0, dedup == 0 };
+        int64_t n_aln = 0;
+        const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
+        counts[2] += n_aln;
+        int64_t n_new = 0;
+        if (dedup) n_new = run_dedup(e, n_kept, limits->max_overlap, n_out);
+        else if (n_kept) {
+          e->out.ensure_keep((size_t)(n_out + n_kept) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
+          dev::d2d(e->out.as<calitas_hit>() + n_out, e->kept.p, (size_t)n_kept * sizeof(calitas_hit), s);
+          n_new = n_kept;
+        }
+        dev::event_record(ce.ev[CE_TAIL_E], s);
+        // the finished segment goes to the host while later chunks compute
+        dev::stream_wait(cs, ce.ev[CE_TAIL_E]);
+        dev::event_record(ce.ev[CE_COPY_B], cs);
+        if (n_new) {
+          if ((size_t)(n_out + n_new) * sizeof(calitas_hit) > pin.cap) {
+            dev::stream_sync(cs);
+            PinnedBuf bigger = take_pinned(e, (size_t)(n_out + n_new) * sizeof(calitas_hit) * 3 / 2);
+            std::memcpy(bigger.p, pin.p, (size_t)n_out * sizeof(calitas_hit));
+            e->pinned_pool.push_back(pin); pin = bigger;
+          }
+          dev::d2h((calitas_hit*)pin.p + n_out, e->out.as<calitas_hit>() + n_out, (size_t)n_new * sizeof(calitas_hit), cs);
+          n_out += n_new;
+        }
+        dev::event_record(ce.ev[CE_COPY_E], cs);
+        ++copies;
+      }
+      dev::event_record(e->ev[1], cs);
+      dev::stream_sync(cs); dev::stream_sync(s); dev::stream_sync(ss);
+    } catch (...) {
+      try { dev::stream_sync(ss); dev::stream_sync(s); dev::stream_sync(cs); } catch (...) {}
+      e->pinned_pool.push_back(pin);
+      throw;
+    }
+    for (size_t c = 0; c < n_chunks; ++c) {
+      const ChunkEvents& ce = e->chunk_ev[c];
+      ms[1] += dev::event_ms(ce.ev[CE_SCAN_B], ce.ev[CE_SCAN_E]);
+      const double al = dev::event_ms(ce.ev[CE_ALIGN_B], ce.ev[CE_ALIGN_E]);
+      ms[2] += al;
+      ms[3] += dev::event_ms(ce.ev[CE_TAIL_B], ce.ev[CE_TAIL_E]) - al;
+      ms[4] += dev::event_ms(ce.ev[CE_COPY_B], ce.ev[CE_COPY_E]);
+    }
+    ms[0] = dev::event_ms(e->ev[0], e->ev[1]);
+    ms[5] = ms[0] - ms[1];                                   // time of the call not hidden behind the scan kernels
     counts[3] = e->launches;
-    *out = finish_hitset(e, n_out, ms, counts);
+    counts[5] = (int64_t)((size_t)n_out * sizeof(calitas_hit));
+    e->out_hits_hint = std::max<size_t>(e->out_hits_hint, (size_t)n_out + (size_t)n_out / 8);
+    std::unique_ptr<calitas_hitset> hs(new calitas_hitset());
+    hs->owner = e; hs->n = n_out; hs->buf = pin;
+    for (int i = 0; i < 8; ++i) { hs->ms[i] = ms[i]; hs->counts[i] = counts[i]; }
+    *out = hs.release();
     return CALITAS_OK;
   });
 }

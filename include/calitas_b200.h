@@ -130,9 +130,11 @@ int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_gui
 int64_t calitas_hitset_count(const calitas_hitset* h);
 const calitas_hit* calitas_hitset_data(const calitas_hitset* h);   /* pinned host memory, valid until free */
 void calitas_hitset_free(calitas_hitset* h);
-/* Timings of the call that produced the set, milliseconds between CUDA events on the engine's stream:
- *   ms[0] whole call on the device incl. the final D2H, ms[1] scan kernels, ms[2] align kernels, ms[3] sorts + canonicalise + dedup
- *   (+ host gaps between launches), ms[4] final D2H of the hit records.
+/* Timings of the call that produced the set, milliseconds between CUDA events recorded on the stream each piece runs on:
+ *   ms[0] whole call on the device, first launch to the last byte of the final D2H;
+ *   ms[1] scan kernels (summed over guide chunks), ms[2] align kernels, ms[3] sorts + canonicalise + dedup, ms[4] D2H of hit records.
+ *   calitas_search overlaps the scan of guide chunk c+1 with [2]-[4] of chunk c on separate streams, so [1]-[4] add up to more than [0];
+ *   ms[5] = ms[0] - ms[1], the part of the call not hidden behind the scan kernels (0 for the align_* entry points).
  * counts[0] owned windows, [1] candidate end columns, [2] alignment slots before canonicalisation, [3] kernel launches,
  * [4] bytes copied host->device, [5] bytes copied device->host, [6] scan-kernel launches, [7] reference bases scanned (summed over scan launches). */
 int calitas_hitset_stats(const calitas_hitset* h, double ms[8], int64_t counts[8]);
