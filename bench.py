@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 # see DESIGN.md "k_scan_tiled"): ALU pipe 7 LOP3 + 2 LEA.HI + 0.5 SHF + 0.5 VIMNMX3; FMA pipe 3 IMAD.IADD + 0.5 IMAD.SHL + 0.5 IMAD; 1 LDS.
 ALU_OPS_PER_COLUMN = 10
 ISSUE_SLOTS_PER_COLUMN = 15
+NCU_DRAM_OVER_ALGORITHMIC = 404.0 / 386.0   # k_scan_tiled, profiles/r01b_summary.txt
 REF_OPS_PER_BP_GUIDE = 240   # 2 strands x 20 rows x 6 int32 ops of the reference's recurrence
 
 
@@ -266,7 +267,8 @@ def main():
             "gpu_launches": int(sum(s["launches"] for s in stats)),
             "clocks": clocks,
             "roofline": {"kernel": "k_scan_tiled", "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                         "traffic": alg_bytes * NCU_DRAM_OVER_ALGORITHMIC, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                         "(profiles/r01b_summary.txt: 404.0 MB for 386.0 MB algorithmic), scaled to this launch's algorithmic bytes", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "streaming read of the 4-bit packed shard once per launch; the kernel is integer-ALU-bound (see roofline_int), so the HBM fraction is small by design",
                          "avg_launch_ms": scan_launch_ms, "launches_per_step": launches, "share_of_step": st["ms_scan"] / st["ms_total"]},
             "roofline_int": {"kernel": "k_scan_tiled", "bound": "int_alu_pipe", "achieved": int_achieved, "peak": int_peaks["alu_lop3"], "unit": "Tiop/s (ALU-pipe thread instructions)",
