@@ -34,6 +34,14 @@ class Hit(C.Structure):
                 ("n_ops", C.c_uint8), ("gap_bases", C.c_uint8), ("edits", C.c_uint8), ("ops", C.c_uint32 * 8)]
 
 
+def hit_dtype():
+    """numpy structured dtype of calitas_hit (72 bytes, include/calitas_b200.h)."""
+    import numpy as np
+    return np.dtype([("guide_idx", "<i4"), ("pam_idx", "<i4"), ("contig_idx", "<i4"), ("task_idx", "<i4"), ("start_offset", "<i4"), ("end_offset", "<i4"),
+                     ("guide_start_offset", "<i4"), ("guide_end_offset", "<i4"), ("score", "<i4"), ("strand", "u1"), ("n_ops", "u1"), ("gap_bases", "u1"),
+                     ("edits", "u1"), ("ops", "<u4", (8,))])
+
+
 class RegionTask(C.Structure):
     _fields_ = [("guide_idx", C.c_int32), ("contig_idx", C.c_int32), ("start", C.c_int64), ("length", C.c_int32)]
 
@@ -158,6 +166,10 @@ class HitSet:
         buf = C.cast(self.lib.L.calitas_hitset_data(self.ptr), C.POINTER(C.c_uint8 * (n * C.sizeof(Hit)))).contents
         return np.frombuffer(buf, dtype=np.uint8).reshape(n, C.sizeof(Hit)).copy()
 
+    def records(self):
+        """hit records as a numpy structured array (copy; see hit_dtype())"""
+        return self.as_numpy().view(hit_dtype()).reshape(-1)
+
     def stats(self):
         ms = (C.c_double * 8)()
         cnt = (C.c_int64 * 8)()
@@ -262,6 +274,18 @@ class Engine:
         p = C.c_void_p()
         self.lib.check(self.lib.L.calitas_reference_load(self.ptr, n, cn, cl, ptrs, hb, he, ob, oe, 1 if keep_raw else 0, C.byref(p)))
         return Reference(self, p, None, (cn, cl, arrays))
+
+    def render_alignments(self, records, guides, contigs, upper_case=True):
+        """calitas_render_alignments over a numpy array of hit records (hit_dtype()); contigs = [(name, numpy uint8 array or bytes)] full contigs.
+        Returns the GuideAlignment table text."""
+        import numpy as np
+        rec = np.ascontiguousarray(records, dtype=hit_dtype())
+        arr, keep = make_guides(guides)
+        view, vkeep = self.genome_view(contigs)
+        out = C.c_void_p()
+        self.lib.check(self.lib.L.calitas_render_alignments(C.c_void_p(rec.ctypes.data), C.c_int64(rec.size), len(guides), arr, len(contigs), view.names,
+                                                            C.cast(view.bases, C.POINTER(C.c_void_p)), None, 1 if upper_case else 0, C.byref(out)))
+        return self.lib.take_text(out)
 
     # ---- device entry points -----------------------------------------------------------------------------------------------------
     def search(self, ref, guides, limits, window_size=1000, chrom=None, dedup=True):

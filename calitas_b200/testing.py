@@ -1,4 +1,4 @@
-"""Dict-row facade over the tool-level C ABI (include/calitas_b200_tools.h), shaped like oracle/pyoracle.py so the parity
+"""Dict-row facade over the tool-level C ABI (include/calitas_b200_tools.h), shaped like the CPU oracle binding so the parity
 tests can run the same reference-test bodies against both.  Uses the product library by default."""
 import ctypes as C
 
