@@ -38,15 +38,27 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--guides", type=int, default=100, help="guides per step (north_star: 100 guides, defaults d=5 p=1 g=3)")
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale; 1.0 = 3.1 Gbp with hg38 contig lengths")
+    ap.add_argument("--max-guide-diffs", type=int, default=5)
+    ap.add_argument("--max-pam-mismatches", type=int, default=1)
+    ap.add_argument("--max-gaps", type=int, default=3)
+    ap.add_argument("--pam", default="nrg", help="PAM appended to every guide ('' = PAM-less run of BASELINE configs[3])")
+    ap.add_argument("--aux-pams", default="", help="comma-separated auxiliary PAMs (BASELINE configs[3]: --pam ngg --aux-pams nag)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lib", default=None, help="alternative build of libcalitas_b200.so (kernel A/B experiments); default = the product library")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
 
-def guide_list(n):
+def guide_list(args):
+    """The BASELINE guide's protospacer + random 20-mers (seed 20260103), all with --pam / --aux-pams."""
     from calitas_b200 import synth
-    return [synth.BASELINE_GUIDE] + synth.random_guides(max(0, n - 1))
+    aux = [a for a in args.aux_pams.split(",") if a]
+    seqs = [synth.BASELINE_GUIDE[:20] + args.pam] + synth.random_guides(max(0, args.guides - 1), pam=args.pam)
+    return [(s, aux) for s in seqs] if aux else seqs
+
+
+def guide_text(g):
+    return g if isinstance(g, str) else g[0]
 
 
 class ClockSampler:
@@ -96,7 +108,7 @@ class ClockSampler:
         return out
 
 
-def cpu_sample(genome, guides, threads, target_seconds, sample_bp=8_000_000):
+def cpu_sample(genome, guides, threads, target_seconds, limits_kw, sample_bp=8_000_000):
     """Times the oracle (C++ restatement of the reference algorithm, oracle/) on a bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
@@ -108,7 +120,8 @@ def cpu_sample(genome, guides, threads, target_seconds, sample_bp=8_000_000):
     done, t_total, n_hits = 0, 0.0, 0
     t0 = time.perf_counter()
     while done < len(guides) and (done == 0 or t_total < target_seconds):
-        n, _ = pyoracle.search_reference_count(contigs, guides[done], threads=threads)
+        g = guides[done]
+        n, _ = pyoracle.search_reference_count(contigs, guide_text(g), aux_pams=() if isinstance(g, str) else g[1], threads=threads, **limits_kw)
         n_hits += n
         done += 1
         t_total = time.perf_counter() - t0
@@ -122,8 +135,8 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     from calitas_b200 import synth
-    guides = guide_list(args.guides)
-    genome = synth.hg38_like_genome(args.scale, guides=guides, sites_per_guide=200)
+    guides = guide_list(args)
+    genome = synth.hg38_like_genome(args.scale, guides=[guide_text(g) for g in guides], sites_per_guide=200)
     threads = os.cpu_count() or 1
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
@@ -134,7 +147,9 @@ def run_reference_arm(args, rank, world):
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        pyoracle.search_reference_count(contigs, guides[it % len(guides)], threads=threads)
+        g = guides[it % len(guides)]
+        pyoracle.search_reference_count(contigs, guide_text(g), aux_pams=() if isinstance(g, str) else g[1], threads=threads,
+                                        d=args.max_guide_diffs, p=args.max_pam_mismatches, g=args.max_gaps)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -150,10 +165,12 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_config(args, genome):
-    return {"workload": "SearchReference, %d guides (CTTGCCCCACAGGGCAGTAAnrg + random 20-mers, nrg) vs %.2f Gbp synthetic hg38-sized genome (24 contigs), "
-                        "defaults d=5 p=1 g=3 O=10 w=1000, contig-range sharded" % (args.guides, genome.total() / 1e9),
-            "guides_per_step": args.guides, "genome_bp": genome.total(), "window_size": 1000, "max_guide_diffs": 5, "max_pam_mismatches": 1,
-            "max_gaps_between_guide_and_pam": 3, "max_overlap": 10, "dedup": "removeOverlaps+sort on device",
+    pams = ",".join([args.pam or "(none)"] + [a for a in args.aux_pams.split(",") if a])
+    return {"workload": "SearchReference, %d guides (CTTGCCCCACAGGGCAGTAA + random 20-mers, PAMs %s) vs %.2f Gbp synthetic hg38-sized genome (24 contigs), "
+                        "d=%d p=%d g=%d O=10 w=1000, contig-range sharded" % (args.guides, pams, genome.total() / 1e9, args.max_guide_diffs, args.max_pam_mismatches, args.max_gaps),
+            "guides_per_step": args.guides, "genome_bp": genome.total(), "window_size": 1000, "max_guide_diffs": args.max_guide_diffs,
+            "max_pam_mismatches": args.max_pam_mismatches, "max_gaps_between_guide_and_pam": args.max_gaps, "pams": pams, "max_overlap": 10,
+            "dedup": "removeOverlaps+sort on device",
             "l2": "inputs larger than L2 (packed reference shard per scan launch >> 126 MB)", "parallelism": "contig-range shards, 1 rank per GPU, no collective"}
 
 
@@ -177,8 +194,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    guides = guide_list(args.guides)
-    genome = synth.hg38_like_genome(args.scale, guides=guides, sites_per_guide=200)
+    guides = guide_list(args)
+    genome = synth.hg38_like_genome(args.scale, guides=[guide_text(g) for g in guides], sites_per_guide=200)
     n = len(genome.lengths)
     engine = Engine(local_rank, lib=Library(os.path.abspath(args.lib)) if args.lib else None)
 
@@ -196,7 +213,7 @@ def main():
     t_load = time.perf_counter() - t0
     own_bp = sum(oe[c] - ob[c] for c in range(n))
     del arrays
-    lim = Limits(5, 1, 3, -1, 10)
+    lim = Limits(args.max_guide_diffs, args.max_pam_mismatches, args.max_gaps, -1, 10)
 
     def barrier():
         torch.cuda.synchronize()
@@ -284,7 +301,7 @@ def main():
             "setup_s": {"generate": t_gen, "load_and_pack": t_load},
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_sample(genome, guides, os.cpu_count() or 1, args.cpu_seconds)
+            out["cpu_baseline"] = cpu_sample(genome, guides, os.cpu_count() or 1, args.cpu_seconds, dict(d=args.max_guide_diffs, p=args.max_pam_mismatches, g=args.max_gaps))
         print(json.dumps(out))
     ref.free()
     engine.close()

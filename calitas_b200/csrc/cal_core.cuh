@@ -261,6 +261,80 @@ CAL_HD bool band_align_k(const GuideSpec& g, const Scores& sc, Fetch fetch, int3
   return true;
 }
 
+// Whole-range variant for a GROUP of candidate end columns of one (window, strand), used where nearly every column is a candidate
+// (alignBest / alignToRefBest, SequentialGuideAligner.scala:333-345,402-418: d = protospacer length): columns jlo+1 .. last candidate are
+// filled ONCE — fgbio fills its matrices once per window too — column-major, with the previous column of all three matrices in registers,
+// and each candidate column is traced back as soon as it is complete.  Cells, tie-breaks and tracebacks are those of band_align; every
+// band_align rectangle [j - span, j] is contained in the range filled here, and both equal the whole-window DP on accepted end cells.
+// `col_at(k)` = k-th candidate column (ascending), `emit(k, aln)` receives each accepted alignment.  Requires last - jlo <= GW.
+template <int GW, class Fetch, class ColAt, class Emit>
+CAL_HD void band_align_group(const GuideSpec& g, const Scores& sc, Fetch fetch, int n_cols, ColAt col_at, Emit emit, uint8_t* trace /* (MAX_PROTOSPACER+1)*(GW+1) */) {
+  constexpr int R = CALITAS_MAX_PROTOSPACER, TW = GW + 1;
+  const int n = g.lp;
+  const int first = col_at(0), last = col_at(n_cols - 1);
+  const int jlo = first - g.span > 0 ? first - g.span : 0;
+  const int32_t gI = sc.target_gap, gD = sc.query_gap;
+  int32_t D[R + 1], L[R + 1], U[R + 1];          // previous column; compile-time indices only -> registers
+  uint32_t qm[R / 2];
+#pragma unroll
+  for (int i = 0; i < R / 2; ++i) qm[i] = (uint32_t)g.qmask[2 * i] | ((uint32_t)g.qmask[2 * i + 1] << 16);
+#pragma unroll
+  for (int i = 0; i <= R; ++i) { D[i] = i == 0 ? 0 : NEG_SCORE; L[i] = i == 0 ? 0 : NEG_SCORE; U[i] = i * gI; }      // local column 0: leading insertions only
+  for (int i = 1; i <= n; ++i) trace[i * TW] = (uint8_t)((i == 1 ? TR_DIAG : TR_UP) << 2);
+  int k = 0, next_col = first;
+  for (int c = 1; c <= last - jlo; ++c) {
+    const uint32_t code = fetch(jlo + c);
+    int32_t dgD = 0, dgL = 0, dgU = 0;            // row i-1 of the previous column (row 0 is all zero: free leading target)
+    int32_t upD = 0, upU = 0;                     // row i-1 of this column
+    int32_t lastD = 0, lastL = 0, lastU = 0;
+#pragma unroll
+    for (int i = 1; i <= R; ++i) {
+      if (i <= n) {
+        const int32_t tD = D[i], tL = L[i], tU = U[i];
+        const uint32_t mt = (((qm[(i - 1) >> 1] >> (((i - 1) & 1) * 16)) & 0xFFFFu) >> code) & 1u;
+        const int32_t add = mt ? sc.match : sc.mismatch;
+        uint32_t cell = mt << 6;
+        int32_t nd, nu, nl;
+        if (dgD >= dgL && dgD >= dgU) { nd = dgD + add; cell |= TR_DIAG; } else if (dgL >= dgU) { nd = dgL + add; cell |= TR_LEFT; } else { nd = dgU + add; cell |= TR_UP; }
+        { const int32_t pd = upD + gI, pu = upU + gI; if (pd >= pu) { nu = pd; cell |= TR_DIAG << 2; } else { nu = pu; cell |= TR_UP << 2; } }
+        { const int32_t pd = tD + gD, pl = tL + gD, pu = tU + gD;
+          if (pd >= pl && pd >= pu) { nl = pd; cell |= TR_DIAG << 4; } else if (pl >= pu) { nl = pl; cell |= TR_LEFT << 4; } else { nl = pu; cell |= TR_UP << 4; } }
+        D[i] = nd; L[i] = nl; U[i] = nu; dgD = tD; dgL = tL; dgU = tU; upD = nd; upU = nu;
+        trace[i * TW + c] = (uint8_t)cell;
+        if (i == n) { lastD = nd; lastL = nl; lastU = nu; }
+      }
+    }
+    if (jlo + c != next_col) continue;
+    const int j = next_col, kk = k;
+    ++k; next_col = k < n_cols ? col_at(k) : -1;
+    int32_t best = lastD; int dir = TR_DIAG;
+    if (lastL > best) { best = lastL; dir = TR_LEFT; }
+    if (lastU > best) { best = lastU; dir = TR_UP; }
+    if (best < g.min_score) continue;
+    GuideAln out;
+    int ci = n, cc = c, cdir = dir, nrev = 0;
+    uint8_t rev[MAX_GUIDE_OPS];
+    for (;;) {
+      int next; uint32_t cell = 0;
+      if (ci == 0) next = TR_DONE;
+      else { cell = trace[ci * TW + cc]; next = cdir == TR_DIAG ? (cell & 3) : (cdir == TR_UP ? ((cell >> 2) & 3) : ((cell >> 4) & 3)); }
+      if (next == TR_DONE || nrev >= MAX_GUIDE_OPS) break;
+      if (cdir == TR_DIAG) { rev[nrev++] = (cell >> 6) ? OP_EQ : OP_X; --ci; --cc; }
+      else if (cdir == TR_LEFT) { rev[nrev++] = OP_D; --cc; }
+      else { rev[nrev++] = OP_I; --ci; }
+      cdir = next;
+    }
+    out.score = best; out.t_start = jlo + cc + 1; out.t_end = j; out.n_ops = nrev; out.diffs = 0;
+    for (int q = 0; q < nrev; ++q) { uint8_t o = rev[nrev - 1 - q]; out.ops[q] = o; if (o != OP_EQ) ++out.diffs; }
+    out.terminal_gap = 0; out.terminal_d = 0;
+    if (nrev > 0 && out.ops[nrev - 1] >= OP_I) {
+      uint8_t o = out.ops[nrev - 1]; int q = nrev; while (q > 0 && out.ops[q - 1] == o) { --q; ++out.terminal_gap; }
+      if (o == OP_D) out.terminal_d = out.terminal_gap;
+    }
+    emit(kk, out);
+  }
+}
+
 // ---- 2-bit op packing ------------------------------------------------------------------------------------------------------
 CAL_HD void ops_set(uint32_t* words, int idx, uint32_t op) { words[idx >> 4] |= op << ((idx & 15) * 2); }
 CAL_HD uint32_t ops_get(const uint32_t* words, int idx) { return (words[idx >> 4] >> ((idx & 15) * 2)) & 3u; }

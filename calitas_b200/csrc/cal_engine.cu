@@ -264,45 +264,90 @@ CAL_D void locate_window(const uint32_t* nib, const ContigDev* contigs, int32_t 
   while (wb < we && nibble_at(nib, c.nib_base + wb) == CODE_N) ++wb;
   while (wb < we && nibble_at(nib, c.nib_base + we - 1) == CODE_N) --we;
 }
+// Everything k_align needs to know about the (window, strand) of a candidate key.
+struct CandCtx { int32_t gidx, contig_idx, m, dir; uint32_t wid; WindowGeom geom; int64_t first; uint8_t owned; };
+CAL_D CandCtx decode_candidate(const AlignArgs& a, uint64_t key) {
+  CandCtx x;
+  const uint32_t strandbit = (uint32_t)(key >> KEY_COL_BITS) & 1u;
+  x.wid = (uint32_t)(key >> KEY_WIN_SHIFT); x.gidx = (int32_t)(key >> KEY_GUIDE_SHIFT); x.owned = 1;
+  if (a.explicit_mode) {
+    const ExplicitWindow ew = a.windows[x.wid];
+    x.gidx = ew.guide_idx; x.contig_idx = ew.contig_idx; x.geom.w_begin = ew.target_offset; x.geom.w_end = ew.target_offset + ew.len; x.first = ew.nib_start;
+  } else {
+    int64_t wb, we; locate_window(a.nib, a.contigs, a.n_contigs, a.window_size, a.step, x.wid, x.contig_idx, wb, we);
+    x.geom.w_begin = (int32_t)wb; x.geom.w_end = (int32_t)we; x.first = a.contigs[x.contig_idx].nib_base + wb;
+    x.owned = ((int64_t)x.wid >= a.contigs[x.contig_idx].own_lo && (int64_t)x.wid < a.contigs[x.contig_idx].own_hi) ? 1 : 2;
+  }
+  x.dir = (int)(strandbit ^ (uint32_t)a.specs[x.gidx].five_prime);
+  x.m = x.geom.w_end - x.geom.w_begin;
+  return x;
+}
+// Guide alignment of candidate i -> PAM extension(s) -> hit slots (SequentialGuideAligner.scala:433-492, 505-524).
+CAL_D void post_alignment(const AlignArgs& a, const CandCtx& x, const GuideSpec& g, const NibFetch& fetch, const GuideAln& aln, int64_t i) {
+  if (aln.diffs > g.d) return;                                   // SequentialGuideAligner.scala:447,450
+  const int64_t base = i * a.slots;
+  if (g.n_pams == 0) {
+    make_hit(g, aln, -1, aln.score, 0, 0u, x.dir, x.geom, x.gidx, x.contig_idx, (int32_t)x.wid + a.task_base, a.hits[base]); a.valid[base] = x.owned;
+  } else {
+    for (int pi = 0; pi < g.n_pams; ++pi) {
+      int32_t score = 0, offset = 0; uint32_t xmask = 0;
+      if (extend_pam(g, a.sc, fetch, x.m, aln, pi, score, offset, xmask)) {
+        make_hit(g, aln, pi, score, offset, xmask, x.dir, x.geom, x.gidx, x.contig_idx, (int32_t)x.wid + a.task_base, a.hits[base + pi]); a.valid[base + pi] = x.owned;
+      }
+    }
+  }
+}
 template <bool BANDED>
 CAL_D void align_body(const AlignArgs& a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_cand) return;
   const uint64_t key = a.cand[i];
   const int32_t col = (int32_t)(key & MAX_WINDOW_LEN);
-  const uint32_t strandbit = (uint32_t)(key >> KEY_COL_BITS) & 1u, wid = (uint32_t)(key >> KEY_WIN_SHIFT);
-  int32_t gidx = (int32_t)(key >> KEY_GUIDE_SHIFT), contig_idx; WindowGeom geom; int64_t first; uint8_t owned = 1;
-  if (a.explicit_mode) {
-    const ExplicitWindow ew = a.windows[wid];
-    gidx = ew.guide_idx; contig_idx = ew.contig_idx; geom.w_begin = ew.target_offset; geom.w_end = ew.target_offset + ew.len; first = ew.nib_start;
-  } else {
-    int64_t wb, we; locate_window(a.nib, a.contigs, a.n_contigs, a.window_size, a.step, wid, contig_idx, wb, we);
-    geom.w_begin = (int32_t)wb; geom.w_end = (int32_t)we; first = a.contigs[contig_idx].nib_base + wb;
-    owned = ((int64_t)wid >= a.contigs[contig_idx].own_lo && (int64_t)wid < a.contigs[contig_idx].own_hi) ? 1 : 2;
-  }
-  const GuideSpec& g = a.specs[gidx];
-  const int dir = (int)(strandbit ^ (uint32_t)g.five_prime);
-  const int32_t m = geom.w_end - geom.w_begin;
-  const NibFetch fetch{ a.nib, first, m, dir };
-  const int64_t base = i * a.slots;
-  for (int s = 0; s < a.slots; ++s) a.valid[base + s] = 0;
+  const CandCtx x = decode_candidate(a, key);
+  const GuideSpec& g = a.specs[x.gidx];
+  const NibFetch fetch{ a.nib, x.first, x.m, x.dir };
+  for (int s = 0; s < a.slots; ++s) a.valid[i * a.slots + s] = 0;
   GuideAln aln;
   if (BANDED) {                           // register-resident diagonal band: every guide of the launch has k_edits <= ALIGN_KB (defaults, d = 6)
     if (!band_align_k<ALIGN_KB>(g, a.sc, fetch, col, aln)) return;
-  } else {                                // wide thresholds / best mode: full rectangle in local memory
+  } else {                                // wide thresholds: full rectangle in local memory
     uint8_t trace[(CALITAS_MAX_PROTOSPACER + 1) * (MAX_SPAN + 1)];
     if (!band_align(g, a.sc, fetch, col, aln, trace)) return;
   }
-  if (aln.diffs > g.d) return;                                   // SequentialGuideAligner.scala:447,450
-  if (g.n_pams == 0) {
-    make_hit(g, aln, -1, aln.score, 0, 0u, dir, geom, gidx, contig_idx, (int32_t)wid + a.task_base, a.hits[base]); a.valid[base] = owned;
-  } else {
-    for (int pi = 0; pi < g.n_pams; ++pi) {
-      int32_t score = 0, offset = 0; uint32_t xmask = 0;
-      if (extend_pam(g, a.sc, fetch, m, aln, pi, score, offset, xmask)) {
-        make_hit(g, aln, pi, score, offset, xmask, dir, geom, gidx, contig_idx, (int32_t)wid + a.task_base, a.hits[base + pi]); a.valid[base + pi] = owned;
-      }
-    }
+  post_alignment(a, x, g, fetch, aln, i);
+}
+
+// Wide thresholds on short explicit windows (alignBest / alignToRefBest: every end column is a candidate): one thread per (window, strand)
+// group of consecutive sorted candidates fills the DP once and traces every candidate column (band_align_group).
+const int GROUP_W = 160;
+struct GroupColAt { const uint64_t* cand; int64_t i0; CAL_D int operator()(int k) const { return (int)(cand[i0 + k] & MAX_WINDOW_LEN); } };
+struct GroupEmit { const AlignArgs* a; const CandCtx* x; const GuideSpec* g; const NibFetch* fetch; int64_t i0;
+                   CAL_D void operator()(int k, const GuideAln& aln) const { post_alignment(*a, *x, *g, *fetch, aln, i0 + k); } };
+CAL_KERNEL __launch_bounds__(128) k_mark_groups(const uint64_t* cand, int64_t n, uint32_t* flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || (cand[i - 1] >> KEY_COL_BITS) != (cand[i] >> KEY_COL_BITS)) ? 1u : 0u;
+}
+CAL_KERNEL __launch_bounds__(128) k_group_starts(const uint32_t* flag, const uint32_t* pos, int64_t n, uint32_t* gstart) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) gstart[pos[i]] = (uint32_t)i;
+}
+CAL_KERNEL __launch_bounds__(128) k_align_group(AlignArgs a, const uint32_t* gstart, int64_t n_groups) {
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= n_groups) return;
+  const int64_t i0 = gstart[gi], i1 = gi + 1 < n_groups ? (int64_t)gstart[gi + 1] : a.n_cand;
+  const CandCtx x = decode_candidate(a, a.cand[i0]);
+  const GuideSpec& g = a.specs[x.gidx];
+  const NibFetch fetch{ a.nib, x.first, x.m, x.dir };
+  for (int64_t s = i0 * a.slots; s < i1 * a.slots; ++s) a.valid[s] = 0;
+  uint8_t trace[(CALITAS_MAX_PROTOSPACER + 1) * (GROUP_W + 1)];
+  const GroupColAt col_at{ a.cand, i0 };
+  const int first = col_at(0), last = col_at((int)(i1 - i0) - 1);
+  const int jlo = first - g.span > 0 ? first - g.span : 0;
+  if (last - jlo <= GROUP_W) {
+    const GroupEmit emit{ &a, &x, &g, &fetch, i0 };
+    band_align_group<GROUP_W>(g, a.sc, fetch, (int)(i1 - i0), col_at, emit, trace);
+  } else {                                // long window: candidate by candidate
+    for (int64_t i = i0; i < i1; ++i) { GuideAln aln; if (band_align(g, a.sc, fetch, col_at((int)(i - i0)), aln, trace)) post_alignment(a, x, g, fetch, aln, i); }
   }
 }
 
@@ -574,6 +619,18 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   aa.hits = e->hits.as<calitas_hit>(); aa.valid = e->valid.as<uint8_t>();
   dev::event_record(P.ev_align_b, s);
   if (P.banded) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
+  else if (P.explicit_mode) {             // short windows, nearly every column a candidate: one DP fill per (window, strand)
+    e->flag.ensure((size_t)n_cand * 4); e->pos.ensure((size_t)n_cand * 4); e->idx.ensure((size_t)n_cand * 4);
+    CAL_LAUNCH(k_mark_groups, blocks_for(n_cand, 128), 128, 0, s, 1, aa.cand, n_cand, e->flag.as<uint32_t>()); dev::launch_check("k_mark_groups"); ++e->launches;
+    size_t tb2 = dev::exclusive_sum_u32_tmp((size_t)n_cand); e->tmp.ensure(tb2);
+    dev::exclusive_sum_u32(e->tmp.p, tb2, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n_cand, s); ++e->launches;
+    uint32_t lp = 0, lf = 0;
+    dev::d2h(&lp, e->pos.as<uint32_t>() + (n_cand - 1), 4, s); dev::d2h(&lf, e->flag.as<uint32_t>() + (n_cand - 1), 4, s); dev::stream_sync(s);
+    const int64_t n_groups = (int64_t)lp + lf;
+    CAL_LAUNCH(k_group_starts, blocks_for(n_cand, 128), 128, 0, s, 1, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_cand, e->idx.as<uint32_t>()); dev::launch_check("k_group_starts"); ++e->launches;
+    dev::event_record(P.ev_align_b, s);
+    CAL_LAUNCH(k_align_group, blocks_for(n_groups, 128), 128, 0, s, 1, aa, e->idx.as<uint32_t>(), n_groups); dev::launch_check("k_align_group");
+  }
   else { CAL_LAUNCH(k_align_wide, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_wide"); }
   ++e->launches;
   dev::event_record(P.ev_align_e, s);
