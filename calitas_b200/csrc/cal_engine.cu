@@ -377,6 +377,60 @@ CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
   if (kept == 0) return;
   for (int k = 0; k < n; ++k) { const int32_t r = a.rank[base + k]; if (r >= 0) a.perm[base + r] = (uint32_t)(base + k); }
 }
+#ifndef CAL_HOSTSIM
+// Warp-per-group variant for large groups (best mode: every end column of a window is a candidate, 60-250 alignments per group).  Same
+// result as canon_group: the best undecided alignment in (score desc, gapBases asc, arrival) order is decided next; when it is kept, every
+// undecided alignment overlapping it by more than max_overlap is dropped at once (it would be dropped on its turn anyway, and deciding it
+// early cannot change a later decision because dropped alignments never block anything).  Persistent grid, warps stride over the groups.
+CAL_KERNEL __launch_bounds__(128) k_canon_warp(CanonArgs a, const uint32_t* gstart, const uint32_t* gpos, const uint32_t* gflag) {
+  const int64_t n_groups = (int64_t)gpos[a.n_cand - 1] + gflag[a.n_cand - 1];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t gi = warp; gi < n_groups; gi += n_warps) {
+    const int64_t i0 = gstart[gi], i1 = gi + 1 < n_groups ? (int64_t)gstart[gi + 1] : a.n_cand;
+    const int64_t base = i0 * a.slots; const int n = (int)((i1 - i0) * a.slots);
+    const int32_t gidx = a.explicit_mode ? a.windows[(uint32_t)(a.cand[i0] >> KEY_WIN_SHIFT)].guide_idx : (int32_t)(a.cand[i0] >> KEY_GUIDE_SHIFT);
+    const int32_t max_total = a.specs[gidx].max_total_diffs, max_overlap = a.specs[gidx].max_overlap;
+    bool halo = false;
+    for (int k = lane; k < n; k += 32) { const uint8_t v = a.valid[base + k]; a.rank[base + k] = v ? -2 : -1; halo |= v == 2; }
+    halo = __any_sync(0xFFFFFFFFu, halo);
+    __syncwarp();
+    int kept = 0;
+    for (;;) {
+      unsigned long long best = ~0ull;
+      for (int k = lane; k < n; k += 32) {
+        if (a.rank[base + k] != -2) continue;
+        const calitas_hit& h = a.hits[base + k];
+        const unsigned long long key = ((unsigned long long)(uint32_t)(0x7FFFFFFF - h.score) << 32) | ((unsigned long long)h.gap_bases << 20) | (unsigned long long)k;
+        if (key < best) best = key;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o); if (other < best) best = other; }
+      if (best == ~0ull) break;
+      const int b = (int)(best & 0xFFFFFu);
+      const calitas_hit& hb = a.hits[base + b];
+      const bool keep = hb.edits <= max_total;
+      const int32_t bs = hb.start_offset, be = hb.end_offset;
+      __syncwarp();
+      if (lane == 0) a.rank[base + b] = keep ? kept : -1;
+      if (keep) {
+        ++kept;
+        for (int k = lane; k < n; k += 32) {
+          if (k == b || a.rank[base + k] != -2) continue;
+          const calitas_hit& h = a.hits[base + k];
+          const int32_t lo = h.start_offset > bs ? h.start_offset : bs, hi = h.end_offset < be ? h.end_offset : be;
+          if (hi - lo > max_overlap) a.rank[base + k] = -1;
+        }
+      }
+      __syncwarp();
+    }
+    if (halo && a.drop_halo) kept = 0;
+    for (int k = lane; k < n; k += 32) { a.flag[base + k] = k < kept ? 1u : 0u; a.slot_owned[base + k] = halo ? 0 : 1; }
+    if (kept) for (int k = lane; k < n; k += 32) { const int32_t r = a.rank[base + k]; if (r >= 0) a.perm[base + r] = (uint32_t)(base + k); }
+    __syncwarp();
+  }
+}
+#endif
 // out[pos[s]] = hits[perm[s]] for flagged slots
 CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const calitas_hit* hits, const uint32_t* perm, const uint32_t* flag, const uint32_t* pos, const uint8_t* slot_owned, int64_t n,
                                                    calitas_hit* out, uint8_t* out_owned) {
@@ -620,14 +674,15 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   dev::event_record(P.ev_align_b, s);
   if (P.banded) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
   else if (P.explicit_mode) {             // short windows, nearly every column a candidate: one DP fill per (window, strand)
-    e->flag.ensure((size_t)n_cand * 4); e->pos.ensure((size_t)n_cand * 4); e->idx.ensure((size_t)n_cand * 4);
-    CAL_LAUNCH(k_mark_groups, blocks_for(n_cand, 128), 128, 0, s, 1, aa.cand, n_cand, e->flag.as<uint32_t>()); dev::launch_check("k_mark_groups"); ++e->launches;
+    e->key1.ensure((size_t)n_cand * 4); e->keyA.ensure((size_t)n_cand * 4); e->idx.ensure((size_t)n_cand * 4);   // group flag / group index / group start (u32 views)
+    uint32_t* gflag = e->key1.as<uint32_t>(); uint32_t* gpos = e->keyA.as<uint32_t>();
+    CAL_LAUNCH(k_mark_groups, blocks_for(n_cand, 128), 128, 0, s, 1, aa.cand, n_cand, gflag); dev::launch_check("k_mark_groups"); ++e->launches;
     size_t tb2 = dev::exclusive_sum_u32_tmp((size_t)n_cand); e->tmp.ensure(tb2);
-    dev::exclusive_sum_u32(e->tmp.p, tb2, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n_cand, s); ++e->launches;
+    dev::exclusive_sum_u32(e->tmp.p, tb2, gflag, gpos, (size_t)n_cand, s); ++e->launches;
     uint32_t lp = 0, lf = 0;
-    dev::d2h(&lp, e->pos.as<uint32_t>() + (n_cand - 1), 4, s); dev::d2h(&lf, e->flag.as<uint32_t>() + (n_cand - 1), 4, s); dev::stream_sync(s);
+    dev::d2h(&lp, gpos + (n_cand - 1), 4, s); dev::d2h(&lf, gflag + (n_cand - 1), 4, s); dev::stream_sync(s);
     const int64_t n_groups = (int64_t)lp + lf;
-    CAL_LAUNCH(k_group_starts, blocks_for(n_cand, 128), 128, 0, s, 1, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_cand, e->idx.as<uint32_t>()); dev::launch_check("k_group_starts"); ++e->launches;
+    CAL_LAUNCH(k_group_starts, blocks_for(n_cand, 128), 128, 0, s, 1, gflag, gpos, n_cand, e->idx.as<uint32_t>()); dev::launch_check("k_group_starts"); ++e->launches;
     dev::event_record(P.ev_align_b, s);
     CAL_LAUNCH(k_align_group, blocks_for(n_groups, 128), 128, 0, s, 1, aa, e->idx.as<uint32_t>(), n_groups); dev::launch_check("k_align_group");
   }
@@ -639,7 +694,12 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   CanonArgs ca; std::memset(&ca, 0, sizeof ca);
   ca.cand = aa.cand; ca.n_cand = n_cand; ca.specs = P.d_specs; ca.slots = P.slots; ca.explicit_mode = aa.explicit_mode; ca.windows = P.d_windows;
   ca.hits = aa.hits; ca.valid = aa.valid; ca.rank = e->rank.as<int32_t>(); ca.perm = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>(); ca.slot_owned = e->slot_owned.as<uint8_t>(); ca.drop_halo = P.drop_halo ? 1 : 0;
-  CAL_LAUNCH(k_canon, blocks_for(n_cand, 128), 128, 0, s, 1, ca); dev::launch_check("k_canon"); ++e->launches;
+#ifndef CAL_HOSTSIM
+  if (P.explicit_mode && !P.banded) {     // large groups: a warp per group (group starts, indices and flags were built for k_align_group)
+    CAL_LAUNCH(k_canon_warp, (unsigned)dev::sm_count(e->device) * 16, 128, 0, s, 1, ca, e->idx.as<uint32_t>(), e->keyA.as<uint32_t>(), e->key1.as<uint32_t>()); dev::launch_check("k_canon_warp"); ++e->launches;
+  } else
+#endif
+  { CAL_LAUNCH(k_canon, blocks_for(n_cand, 128), 128, 0, s, 1, ca); dev::launch_check("k_canon"); ++e->launches; }
   tb = dev::exclusive_sum_u32_tmp((size_t)n_slots); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n_slots, s); ++e->launches;
   uint32_t last_pos = 0, last_flag = 0;
