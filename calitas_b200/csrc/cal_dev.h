@@ -93,9 +93,9 @@ inline void exclusive_sum_u32(void* tmp, size_t tmp_bytes, const uint32_t* in, u
 
 namespace cal { namespace sim {
 struct Dim3 { unsigned x = 1, y = 1, z = 1; Dim3() {} Dim3(unsigned a) : x(a) {} };
-extern Dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;
-extern int phase_;
-extern unsigned char smem_[256 * 1024];
+extern thread_local Dim3 threadIdx_, blockIdx_, blockDim_, gridDim_;      // thread_local: engines may be driven from several host threads
+extern thread_local int phase_;
+extern thread_local unsigned char smem_[256 * 1024];
 template <class F> void launch(unsigned grid, unsigned block, int nphases, F f) {
   gridDim_ = Dim3(grid); blockDim_ = Dim3(block);
   for (unsigned b = 0; b < grid; ++b) { blockIdx_ = Dim3(b);

@@ -297,7 +297,7 @@ CAL_D void post_alignment(const AlignArgs& a, const CandCtx& x, const GuideSpec&
     }
   }
 }
-template <bool BANDED>
+template <int KB>                         // KB > 0: register-resident band of 2*KB+1 diagonals; KB == 0: full rectangle in local memory
 CAL_D void align_body(const AlignArgs& a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_cand) return;
@@ -308,8 +308,8 @@ CAL_D void align_body(const AlignArgs& a) {
   const NibFetch fetch{ a.nib, x.first, x.m, x.dir };
   for (int s = 0; s < a.slots; ++s) a.valid[i * a.slots + s] = 0;
   GuideAln aln;
-  if (BANDED) {                           // register-resident diagonal band: every guide of the launch has k_edits <= ALIGN_KB (defaults, d = 6)
-    if (!band_align_k<ALIGN_KB>(g, a.sc, fetch, col, aln)) return;
+  if (KB > 0) {                           // every guide of the launch has k_edits <= KB (defaults: d = 5 -> 5, d = 6 -> 6)
+    if (!band_align_k<(KB > 0 ? KB : 1)>(g, a.sc, fetch, col, aln)) return;
   } else {                                // wide thresholds: full rectangle in local memory
     uint8_t trace[(CALITAS_MAX_PROTOSPACER + 1) * (MAX_SPAN + 1)];
     if (!band_align(g, a.sc, fetch, col, aln, trace)) return;
@@ -351,8 +351,10 @@ CAL_KERNEL __launch_bounds__(128) k_align_group(AlignArgs a, const uint32_t* gst
   }
 }
 
-CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) { align_body<true>(a); }
-CAL_KERNEL __launch_bounds__(128) k_align_wide(AlignArgs a) { align_body<false>(a); }
+CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) { align_body<ALIGN_KB>(a); }
+CAL_KERNEL __launch_bounds__(128) k_align5(AlignArgs a) { align_body<5>(a); }
+CAL_KERNEL __launch_bounds__(128) k_align4(AlignArgs a) { align_body<4>(a); }
+CAL_KERNEL __launch_bounds__(128) k_align_wide(AlignArgs a) { align_body<0>(a); }
 
 // ------------------------------------------------------------------------------------------------------------------------------------
 // k_canon: per (guide, window, strand) group — SequentialGuideAligner.scala:315-322
@@ -579,7 +581,7 @@ struct calitas_engine {
   dev::Event ev[8];
   std::vector<ChunkEvents> chunk_ev;
   size_t out_hits_hint = 1u << 16;
-  DBuf cand_b;
+  DBuf cand_b, cand_c;
   DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, kept, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, kept_owned, sowned;
   unsigned long long* h_count = nullptr;       // pinned
   unsigned long long* d_count = nullptr;
@@ -649,7 +651,7 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
 
 struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> align -> canon -> compaction
   calitas_engine* e; const uint64_t* cand; dev::Event ev_sorted, ev_align_b, ev_align_e;   // candidate keys; events recorded after the sort / around k_align
-  const GuideSpec* d_specs; int slots; bool explicit_mode; bool banded;
+  const GuideSpec* d_specs; int slots; bool explicit_mode; int banded;   // banded: 0 = wide thresholds, else the largest k_edits of the launch (<= ALIGN_KB)
   const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base; bool drop_halo;
 };
 
@@ -672,7 +674,9 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows; aa.task_base = P.task_base;
   aa.hits = e->hits.as<calitas_hit>(); aa.valid = e->valid.as<uint8_t>();
   dev::event_record(P.ev_align_b, s);
-  if (P.banded) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
+  if (P.banded > 5) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
+  else if (P.banded == 5) { CAL_LAUNCH(k_align5, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align5"); }
+  else if (P.banded > 0) { CAL_LAUNCH(k_align4, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align4"); }
   else if (P.explicit_mode) {             // short windows, nearly every column a candidate: one DP fill per (window, strand)
     e->key1.ensure((size_t)n_cand * 4); e->keyA.ensure((size_t)n_cand * 4); e->idx.ensure((size_t)n_cand * 4);   // group flag / group index / group start (u32 views)
     uint32_t* gflag = e->key1.as<uint32_t>(); uint32_t* gpos = e->keyA.as<uint32_t>();
@@ -774,7 +778,8 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
   dev::Stream s = e->stream; dev::set_device(e->device);
   e->launches = 0;
   dev::event_record(e->ev[0], s);
-  int slots = 1; bool banded = true; for (auto& sp : specs) { slots = std::max(slots, sp.slots); if (sp.k_edits > ALIGN_KB) banded = false; }
+  int slots = 1, banded = 1; for (auto& sp : specs) { slots = std::max(slots, sp.slots); banded = std::max(banded, sp.k_edits); }
+  if (banded > ALIGN_KB) banded = 0;
   e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
   e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
   double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { (int64_t)windows.size(), 0, 0, 0, 0, 0, 0, 0 };
@@ -852,7 +857,7 @@ void calitas_engine_destroy(calitas_engine* e) {
   try {
     dev::set_device(e->device);
     dev::stream_sync(e->scan_stream); dev::stream_sync(e->stream); dev::stream_sync(e->copy_stream);
-    for (DBuf* b : { &e->cand_b, &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->kept, &e->out, &e->tmp, &e->key1, &e->keyA,
+    for (DBuf* b : { &e->cand_b, &e->cand_c, &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->kept, &e->out, &e->tmp, &e->key1, &e->keyA,
                      &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp, &e->slot_owned, &e->kept_owned, &e->sowned }) b->release();
     for (auto& p : e->pinned_pool) dev::free_host(p.p);
     dev::free_host(e->h_count); dev::free_(e->d_count);
@@ -927,7 +932,7 @@ void calitas_reference_free(calitas_engine* e, calitas_reference* r) {
 }
 
 // One guide chunk of a search: consecutive guides sharing the raw guide length, hence the window tiling (SearchReference.scala:528-530).
-struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots; bool banded; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; };
+struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; };
 
 int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
                    int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out) {
@@ -955,7 +960,8 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       ch.t_begin = 0; size_t t_end = ch.ts->tiles.size();
       if (chrom_idx >= 0) { ch.t_begin = t_end = 0; bool in = false; for (size_t t = 0; t < ch.ts->tiles.size(); ++t) { if (ch.ts->tiles[t].contig == chrom_idx) { if (!in) { ch.t_begin = t; in = true; } t_end = t + 1; } } }
       ch.n_tiles = t_end - ch.t_begin;
-      ch.slots = 1; ch.banded = true; for (int g = g0; g < g1; ++g) { ch.slots = std::max(ch.slots, specs[(size_t)g].slots); if (specs[(size_t)g].k_edits > ALIGN_KB) ch.banded = false; }
+      ch.slots = 1; ch.banded = 1; for (int g = g0; g < g1; ++g) { ch.slots = std::max(ch.slots, specs[(size_t)g].slots); ch.banded = std::max(ch.banded, specs[(size_t)g].k_edits); }
+      if (ch.banded > ALIGN_KB) ch.banded = 0;
       const int ng = g1 - g0;
       const int64_t tile_bases = (int64_t)(TILE_WINDOWS - 1) * ch.step + window_size;
       ch.smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2) * 4;
@@ -975,11 +981,14 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     { const calitas_reference::TileSet& ts = *chunks[0].ts; for (size_t c = 0; c < ts.contigs.size(); ++c) if (chrom_idx < 0 || (int)c == chrom_idx) counts[0] += ts.contigs[c].own_hi - ts.contigs[c].own_lo; }
     // ---- pipeline: scan(c+1) runs on the scan stream while sort/align/canon/dedup of chunk c run on the main stream and finished hit
     //      segments go to pinned host memory on the copy stream -------------------------------------------------------------------
-    DBuf* cand_slot[2] = { &e->cand, &e->cand_b };
+    // Three candidate slots: two scans are always queued ahead of the chunk whose tail the host is driving, so the scan stream never
+    // waits for the host (the tail's small dependent launches and counter read-backs are slow while a scan kernel holds the SMs).
+    const int N_SLOTS = 3;
+    DBuf* cand_slot[N_SLOTS] = { &e->cand, &e->cand_b, &e->cand_c };
     auto launch_scan = [&](size_t c) {
-      const SearchChunk& ch = chunks[c]; const int slot = (int)(c & 1); ChunkEvents& ce = e->chunk_ev[c];
+      const SearchChunk& ch = chunks[c]; const int slot = (int)(c % N_SLOTS); ChunkEvents& ce = e->chunk_ev[c];
       cand_slot[slot]->ensure(e->cand_cap_hint * 8);
-      if (c >= 2) dev::stream_wait(ss, e->chunk_ev[c - 2].ev[CE_SORTED]);       // the previous user of this candidate slot has been sorted away
+      if (c >= (size_t)N_SLOTS) dev::stream_wait(ss, e->chunk_ev[c - N_SLOTS].ev[CE_SORTED]);       // the previous user of this candidate slot has been sorted away
       dev::zero(e->d_count + slot, 8, ss);
       dev::event_record(ce.ev[CE_SCAN_B], ss);
       if (ch.n_tiles) {
@@ -998,10 +1007,10 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     PinnedBuf pin = take_pinned(e, std::max<size_t>(e->out_hits_hint, 1024) * sizeof(calitas_hit));
     int64_t n_out = 0; size_t copies = 0;
     try {
-      launch_scan(0);
+      for (size_t c = 0; c < (size_t)(N_SLOTS - 1) && c < n_chunks; ++c) launch_scan(c);
       for (size_t c = 0; c < n_chunks; ++c) {
-        const SearchChunk& ch = chunks[c]; const int slot = (int)(c & 1); ChunkEvents& ce = e->chunk_ev[c];
-        if (c + 1 < n_chunks) launch_scan(c + 1);
+        const SearchChunk& ch = chunks[c]; const int slot = (int)(c % N_SLOTS); ChunkEvents& ce = e->chunk_ev[c];
+        if (c + N_SLOTS - 1 < n_chunks) launch_scan(c + N_SLOTS - 1);
         unsigned long long n_cand = 0;
         for (;;) {
           dev::event_sync(ce.ev[CE_COUNT]);
@@ -1009,10 +1018,8 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
           if (n_cand <= e->cand_cap_hint) break;
           // pool too small: grow and re-run this chunk's scan (and the one queued behind it), never truncate
           dev::stream_sync(ss);
-          if (c + 1 < n_chunks) { counts[6] -= chunks[c + 1].n_tiles ? 1 : 0; counts[7] -= chunks[c + 1].bases; }
-          counts[6] -= ch.n_tiles ? 1 : 0; counts[7] -= ch.bases;
           e->cand_cap_hint = (size_t)(n_cand + n_cand / 4);
-          launch_scan(c); if (c + 1 < n_chunks) launch_scan(c + 1);
+          for (size_t r = c; r < c + N_SLOTS && r < n_chunks; ++r) { counts[6] -= chunks[r].n_tiles ? 1 : 0; counts[7] -= chunks[r].bases; launch_scan(r); }
         }
         counts[1] += (int64_t)n_cand;
         dev::event_record(ce.ev[CE_TAIL_B], s);
@@ -1186,5 +1193,5 @@ void calitas_free_text(char* text) { std::free(text); }
 }  // extern "C"
 
 #ifdef CAL_HOSTSIM
-namespace cal { namespace sim { Dim3 threadIdx_, blockIdx_, blockDim_, gridDim_; int phase_ = 0; unsigned char smem_[256 * 1024]; } }
+namespace cal { namespace sim { thread_local Dim3 threadIdx_, blockIdx_, blockDim_, gridDim_; thread_local int phase_ = 0; thread_local unsigned char smem_[256 * 1024]; } }
 #endif

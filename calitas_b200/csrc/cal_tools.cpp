@@ -4,8 +4,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/calitas_b200_tools.h"
@@ -337,57 +339,109 @@ int calitas_tool_align_to_ref(calitas_engine* e, const calitas_reference* ref, c
 
 int calitas_tool_search_reference(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, const calitas_guide* guide,
                                   const calitas_search_options* opt, char** out_tsv, int64_t* n_hits) {
+  const char* id = opt ? opt->guide_id : nullptr;
+  return calitas_tool_search_reference_batch(1, &e, &ref, genome, 1, guide, &id, opt, out_tsv, n_hits);
+}
+
+// SearchReference.execute for a batch of guides over 1..N engines (one per GPU, each holding a contig-range shard of the same genome,
+// calitas_shard_plan): the engines run concurrently on host threads, shards are independent, the host concatenates per guide in shard order.
+int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
+                                        int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
+                                        char** out_tsv, int64_t* n_hits) {
   return guarded([&]() -> int {
-    if (!e || !ref || !genome || !guide || !opt || !out_tsv) bad("bad arguments");
+    if (n_engines <= 0 || !engines || !refs || !genome || n_guides <= 0 || !guides || !opt || !out_tsv) bad("bad arguments");
+    for (int s = 0; s < n_engines; ++s) if (!engines[s] || !refs[s]) bad("engine or reference is NULL");
     *out_tsv = nullptr;
-    GuideDef gd = parse_guide(*guide);
-    calitas_costs costs; ck(calitas_engine_get_costs(e, &costs));
-    RowContext cx; cx.genome = genome; cx.guide_id = opt->guide_id ? opt->guide_id : ""; cx.aligner_id = "CALITAS:SearchReference";
-    cx.arguments = core_parameters_search(*opt, costs); cx.time_stamp = opt->time_stamp ? opt->time_stamp : ""; cx.version = opt->aligner_version ? opt->aligner_version : "calitas-b200";
-    cx.has_vcf = opt->vcf_text != nullptr; cx.vcf_id = opt->vcf_id ? opt->vcf_id : "";
+    std::vector<GuideDef> defs; for (int g = 0; g < n_guides; ++g) defs.push_back(parse_guide(guides[g]));
+    calitas_costs costs; ck(calitas_engine_get_costs(engines[0], &costs));
+    std::vector<RowContext> cxs((size_t)n_guides);
+    for (int g = 0; g < n_guides; ++g) {
+      RowContext& cx = cxs[(size_t)g]; cx.genome = genome; cx.aligner_id = "CALITAS:SearchReference";
+      cx.guide_id = (guide_ids && guide_ids[g]) ? guide_ids[g] : (opt->guide_id ? opt->guide_id : "");
+      cx.arguments = core_parameters_search(*opt, costs); cx.time_stamp = opt->time_stamp ? opt->time_stamp : ""; cx.version = opt->aligner_version ? opt->aligner_version : "calitas-b200";
+      cx.has_vcf = opt->vcf_text != nullptr; cx.vcf_id = opt->vcf_id ? opt->vcf_id : "";
+    }
     int chrom_idx = -1;
     if (opt->chrom && opt->chrom[0]) { chrom_idx = contig_index(*genome, opt->chrom); if (chrom_idx < 0) bad(Str("Unknown chromosome: ") + opt->chrom); }
     const bool with_vcf = opt->vcf_text != nullptr;
-    std::vector<Row> rows;
+    std::vector<std::vector<Row>> rows((size_t)n_guides);
+    // every engine's work runs on its own host thread; errors travel back as (code, message)
+    auto run_all = [&](const std::function<void(int)>& job) {
+      std::vector<int> rc((size_t)n_engines, CALITAS_OK); std::vector<Str> msg((size_t)n_engines);
+      auto body = [&](int s) { try { job(s); } catch (const ToolError& te) { rc[(size_t)s] = te.code; msg[(size_t)s] = te.msg; } catch (const std::exception& ex) { rc[(size_t)s] = CALITAS_ESTATE; msg[(size_t)s] = ex.what(); } };
+      if (n_engines == 1) body(0);
+      else { std::vector<std::thread> th; for (int s = 0; s < n_engines; ++s) th.emplace_back(body, s); for (auto& t : th) t.join(); }
+      for (int s = 0; s < n_engines; ++s) if (rc[(size_t)s] != CALITAS_OK) throw ToolError{ rc[(size_t)s], msg[(size_t)s] };
+    };
     {  // reference windows: SearchReference.scala:527-564 (+ removeOverlaps/sort on the device when there is no VCF)
-      HitSet hs; ck(calitas_search(e, ref, 1, guide, &opt->limits, opt->window_size, opt->chrom, with_vcf ? 0 : 1, &hs.h));
+      std::vector<HitSet> hs((size_t)n_engines);
+      run_all([&](int s) { ck(calitas_search(engines[s], refs[s], n_guides, guides, &opt->limits, opt->window_size, opt->chrom, with_vcf ? 0 : 1, &hs[(size_t)s].h)); });
       const Flanks none;
-      for (int64_t i = 0; i < hs.n(); ++i) {
-        const calitas_hit& h = hs.data()[i];
-        Rendered r = render_hit(h, gd, contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), true);     // windows are upper-cased, SearchReference.scala:67
-        rows.push_back(make_row(cx, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none));
+      std::vector<int64_t> cursor((size_t)n_engines, 0);          // every hit set is guide-major
+      for (int g = 0; g < n_guides; ++g) for (int s = 0; s < n_engines; ++s) {
+        int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s];
+        for (; i < h_.n() && h_.data()[i].guide_idx == g; ++i) {
+          const calitas_hit& h = h_.data()[i];
+          Rendered r = render_hit(h, defs[(size_t)g], contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), true);     // windows are upper-cased, SearchReference.scala:67
+          rows[(size_t)g].push_back(make_row(cxs[(size_t)g], h, r, defs[(size_t)g], h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none));
+        }
       }
+      for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "hit set is not guide-major" };
     }
     if (with_vcf) {  // SearchReference.scala:570-630
       std::vector<VcfRecord> recs = parse_vcf(opt->vcf_text);
-      const int padding = gd.length() - 1 + opt->limits.max_guide_diffs + opt->limits.max_gaps_between_guide_and_pam;     // :575
-      std::vector<VariantWindow> windows = variant_windows(*genome, recs, chrom_idx, padding, opt->max_variants);
-      std::vector<calitas_target_task> tasks;
-      for (auto& w : windows) tasks.push_back(calitas_target_task{ 0, (const uint8_t*)w.bases.data(), (int32_t)w.bases.size(), 0 });
-      HitSet hs; if (!tasks.empty()) ck(calitas_align_targets(e, 1, guide, (int64_t)tasks.size(), tasks.data(), &opt->limits, 0, &hs.h));
-      for (int64_t i = 0; i < hs.n(); ++i) {
-        const calitas_hit& h = hs.data()[i]; const VariantWindow& w = windows[(size_t)h.task_idx];
-        Rendered r = render_hit(h, gd, w.bases.substr((size_t)h.start_offset, (size_t)(h.end_offset - h.start_offset)), false);
-        const int wl = (int)w.bases.size();
-        Flanks raw;   // window-orientation flanks (:599-602)
-        if (h.guide_start_offset >= 10) { raw.has[0] = true; raw.v[0] = w.bases.substr((size_t)h.guide_start_offset - 10, 10); }
-        if (wl - h.guide_end_offset >= 10) { raw.has[1] = true; raw.v[1] = w.bases.substr((size_t)h.guide_end_offset, 10); }
-        if (h.start_offset >= 8) { raw.has[2] = true; raw.v[2] = w.bases.substr((size_t)h.start_offset - 8, 8); }
-        if (wl - h.end_offset >= 8) { raw.has[3] = true; raw.v[3] = w.bases.substr((size_t)h.end_offset, 8); }
-        Flanks fl = raw;
-        if (h.strand == '-') {   // :604-612
-          fl.has[0] = raw.has[1]; fl.v[0] = revcomp(raw.v[1]); fl.has[1] = raw.has[0]; fl.v[1] = revcomp(raw.v[0]);
-          fl.has[2] = raw.has[3]; fl.v[2] = revcomp(raw.v[3]); fl.has[3] = raw.has[2]; fl.v[3] = revcomp(raw.v[2]);
-        }
-        const int so = w.ref_offset_at(h.start_offset, true), eo = w.ref_offset_at(h.end_offset, false);             // :615-620
-        const int gso = w.ref_offset_at(h.guide_start_offset, true), geo = w.ref_offset_at(h.guide_end_offset, false);
-        rows.push_back(make_row(cx, h, r, gd, w.contig, so, eo, gso, geo, w.alleles, fl));
+      // variant windows depend on the guide only through the padding (Guide.length, :575): build once per distinct padding
+      std::map<int, std::vector<VariantWindow>> by_padding;
+      std::vector<const std::vector<VariantWindow>*> windows_of((size_t)n_guides);
+      for (int g = 0; g < n_guides; ++g) {
+        const int padding = defs[(size_t)g].length() - 1 + opt->limits.max_guide_diffs + opt->limits.max_gaps_between_guide_and_pam;
+        auto it = by_padding.find(padding);
+        if (it == by_padding.end()) it = by_padding.emplace(padding, variant_windows(*genome, recs, chrom_idx, padding, opt->max_variants)).first;
+        windows_of[(size_t)g] = &it->second;
       }
-      rows = remove_overlaps_host(rows, opt->limits.max_overlap);                                                     // :641
-      sort_rows(rows);                                                                                                // :647
+      struct TaskRef { int guide; int window; };
+      std::vector<std::vector<calitas_target_task>> tasks((size_t)n_engines); std::vector<std::vector<TaskRef>> task_ref((size_t)n_engines);
+      int64_t rr = 0;
+      for (int g = 0; g < n_guides; ++g) { const auto& ws = *windows_of[(size_t)g];
+        for (size_t w = 0; w < ws.size(); ++w, ++rr) { const size_t s = (size_t)(rr % n_engines);
+          tasks[s].push_back(calitas_target_task{ g, (const uint8_t*)ws[w].bases.data(), (int32_t)ws[w].bases.size(), 0 }); task_ref[s].push_back(TaskRef{ g, (int)w }); } }
+      std::vector<HitSet> hs((size_t)n_engines);
+      run_all([&](int s) { if (!tasks[(size_t)s].empty()) ck(calitas_align_targets(engines[s], n_guides, guides, (int64_t)tasks[(size_t)s].size(), tasks[(size_t)s].data(), &opt->limits, 0, &hs[(size_t)s].h)); });
+      // rows must arrive in the reference's window order per guide (it decides ties in removeOverlaps): walk tasks in global order
+      std::vector<int64_t> cursor((size_t)n_engines, 0); std::vector<int64_t> next_task((size_t)n_engines, 0);
+      rr = 0;
+      for (int g = 0; g < n_guides; ++g) { const auto& ws = *windows_of[(size_t)g];
+        for (size_t wi = 0; wi < ws.size(); ++wi, ++rr) {
+          const size_t s = (size_t)(rr % n_engines); const int64_t t = next_task[s]++; int64_t& i = cursor[s]; const HitSet& h_ = hs[s];
+          const VariantWindow& w = ws[wi]; const GuideDef& gd = defs[(size_t)g];
+          for (; i < h_.n() && h_.data()[i].task_idx == t; ++i) {
+            const calitas_hit& h = h_.data()[i];
+            Rendered r = render_hit(h, gd, w.bases.substr((size_t)h.start_offset, (size_t)(h.end_offset - h.start_offset)), false);
+            const int wl = (int)w.bases.size();
+            Flanks raw;   // window-orientation flanks (:599-602)
+            if (h.guide_start_offset >= 10) { raw.has[0] = true; raw.v[0] = w.bases.substr((size_t)h.guide_start_offset - 10, 10); }
+            if (wl - h.guide_end_offset >= 10) { raw.has[1] = true; raw.v[1] = w.bases.substr((size_t)h.guide_end_offset, 10); }
+            if (h.start_offset >= 8) { raw.has[2] = true; raw.v[2] = w.bases.substr((size_t)h.start_offset - 8, 8); }
+            if (wl - h.end_offset >= 8) { raw.has[3] = true; raw.v[3] = w.bases.substr((size_t)h.end_offset, 8); }
+            Flanks fl = raw;
+            if (h.strand == '-') {   // :604-612
+              fl.has[0] = raw.has[1]; fl.v[0] = revcomp(raw.v[1]); fl.has[1] = raw.has[0]; fl.v[1] = revcomp(raw.v[0]);
+              fl.has[2] = raw.has[3]; fl.v[2] = revcomp(raw.v[3]); fl.has[3] = raw.has[2]; fl.v[3] = revcomp(raw.v[2]);
+            }
+            const int so = w.ref_offset_at(h.start_offset, true), eo = w.ref_offset_at(h.end_offset, false);             // :615-620
+            const int gso = w.ref_offset_at(h.guide_start_offset, true), geo = w.ref_offset_at(h.guide_end_offset, false);
+            rows[(size_t)g].push_back(make_row(cxs[(size_t)g], h, r, gd, w.contig, so, eo, gso, geo, w.alleles, fl));
+          }
+        } }
+      for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "variant hit set is not task-major" };
+      for (int g = 0; g < n_guides; ++g) {
+        rows[(size_t)g] = remove_overlaps_host(rows[(size_t)g], opt->limits.max_overlap);                                 // :641
+        sort_rows(rows[(size_t)g]);                                                                                      // :647
+      }
     }
-    Str text = hit_header(); for (auto& r : rows) text += r.line;
-    if (n_hits) *n_hits = (int64_t)rows.size();
+    Str text = hit_header(); int64_t total = 0;
+    for (auto& v : rows) { for (auto& r : v) text += r.line; total += (int64_t)v.size(); }
+    if (n_hits) *n_hits = total;
     *out_tsv = dup_text(text);
     return CALITAS_OK;
   });

@@ -92,6 +92,31 @@ class Facade:
         text = self._text(out)
         return text if raw else _table(text, _INT_HIT)
 
+    def search_reference_batch(self, contigs, guides, guide_ids=None, n_shards=1, chrom=None, vcf_text=None, vcf_name="variants.vcf", assembly=None,
+                               max_variants=16, window_size=1000, d=5, p=1, g=3, D=None, O=10, costs=_capi.DEFAULT_COSTS):
+        """calitas_tool_search_reference_batch: guides = [str | (str, [aux pams])]; n_shards engines, each over its contig-range shard (here all on
+        this facade's device; in production one per GPU).  Returns the TSV text."""
+        from ._capi import make_guides
+        engines = [self.engine(costs)] + [Engine(self.device, costs, self.lib) for _ in range(n_shards - 1)]
+        refs = [e.load_reference(contigs, shard=None if n_shards == 1 else (s, n_shards, 4 * window_size)) for s, e in enumerate(engines)]
+        try:
+            view, keep = Engine.genome_view(contigs, assembly)
+            arr, gkeep = make_guides(guides)
+            ids = [_b(x) for x in (guide_ids or ["g%d" % i for i in range(len(guides))])]
+            id_arr = (C.c_char_p * len(ids))(*ids)
+            opt = SearchOptions(None, max_variants, window_size, Limits(d, p, g, -1 if D is None else D, O), _b(chrom), _b(vcf_text), _b(vcf_name), b"", b"oracle")
+            e_arr = (C.c_void_p * n_shards)(*[e.ptr for e in engines])
+            r_arr = (C.c_void_p * n_shards)(*[r.ptr for r in refs])
+            out = C.c_void_p()
+            n = C.c_int64(0)
+            self.lib.check(self.lib.L.calitas_tool_search_reference_batch(n_shards, e_arr, r_arr, C.byref(view), len(guides), arr, id_arr, C.byref(opt), C.byref(out), C.byref(n)))
+            return self._text(out)
+        finally:
+            for r in refs:
+                r.free()
+            for e in engines[1:]:
+                e.close()
+
     def align_to_reference(self, contigs, tasks, window_size=None, d=None, p=None, g=3, D=None, O=None, costs=_capi.DEFAULT_COSTS, threads=1, assembly=None, raw=False):
         e = self.engine(costs)
         ref, _ = self._ref(e, contigs)

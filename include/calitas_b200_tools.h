@@ -48,6 +48,13 @@ typedef struct calitas_search_options {      /* SearchReference.scala:452-470 */
 int calitas_tool_search_reference(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, const calitas_guide* guide,
                                   const calitas_search_options* opt, char** out_tsv, int64_t* n_hits);
 
+/* The same for a batch of guides over n_engines engines (one per GPU; engine s holds shard s of calitas_shard_plan(.., s, n_engines, ..) in refs[s]).
+ * The reference runs one guide per process; the engine batches guides per scan and the shards run concurrently on host threads.
+ * Rows come guide by guide, each guide's block exactly as the single-guide call produces it; guide_ids[g] is that guide's -I. */
+int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
+                                        int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
+                                        char** out_tsv, int64_t* n_hits);
+
 typedef struct calitas_a2r_task { const char* id; const char* query; const char* chrom; int32_t position; } calitas_a2r_task;   /* AlignToReference.scala:97-102 */
 typedef struct calitas_a2r_options {         /* AlignToReference.scala:35-50; -1 = not given */
   int32_t window_size, max_guide_diffs, max_pam_mismatches, max_gaps_between_guide_and_pam, max_total_diffs, max_overlap;

@@ -1,0 +1,141 @@
+"""The `calitas` command line (SearchReference.scala:452-470, AlignToReference.scala:35-50 flags) end to end: FASTA + .fai + .dict (+ VCF, task table)
+on disk -> hit table on disk, compared line by line with the oracle.  Here the CLI is linked against the test-only host simulation; the -m gpu
+twin runs the product binary calitas_b200/calitas on the B200."""
+import hashlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import pyoracle
+from calitas_b200 import synth
+
+BINARIES = ["hostsim", pytest.param("gpu", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(scope="module", params=BINARIES)
+def calitas(request):
+    if request.param == "hostsim":
+        d = os.path.join(ROOT, "tests", "hostsim")
+        subprocess.check_call(["make", "-C", d, "-s", "all"])
+        return os.path.join(d, "_build", "calitas_hostsim")
+    path = os.path.join(ROOT, "calitas_b200", "calitas")
+    assert os.path.exists(path), "run __graft_entry__.build() first"
+    return path
+
+
+@pytest.fixture(scope="module")
+def ref_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("ref")
+    g = synth.config1_genome(scale=0.02, n_sites=60)
+    contigs = [(n, bytes(b)) for n, b in g.contigs()]
+    # soft-masked stretch: SearchReference upper-cases windows, AlignToReference does not (SequentialGuideAligner.scala:374)
+    name0, b0 = contigs[0]
+    contigs[0] = (name0, b0[:30000] + b0[30000:30400].lower() + b0[30400:])
+    fa = d / "ref.fa"
+    off, fai = 0, []
+    with open(fa, "wb") as f:
+        for n, b in contigs:
+            hdr = (">%s some description\n" % n).encode()
+            f.write(hdr)
+            off += len(hdr)
+            fai.append("%s\t%d\t%d\t60\t61" % (n, len(b), off))
+            for i in range(0, len(b), 60):
+                f.write(b[i:i + 60] + b"\n")
+            off += len(b) + (len(b) + 59) // 60
+    open(str(fa) + ".fai", "w").write("\n".join(fai) + "\n")
+    open(d / "ref.dict", "w").write("@HD\tVN:1.5\n" + "".join("@SQ\tSN:%s\tLN:%d\tAS:SYN10M\n" % (n, len(b)) for n, b in contigs))
+    return d, g, contigs
+
+
+def run(calitas, *args):
+    p = subprocess.run([calitas] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    return p
+
+
+def lines(text):
+    return [l for l in text.split("\n") if l]
+
+
+def test_search_reference_cli(calitas, ref_dir):
+    d, g, contigs = ref_dir
+    out = d / "hits.tsv"
+    p = run(calitas, "SearchReference", "-i", synth.BASELINE_GUIDE, "-I", "guide1", "-r", d / "ref.fa", "-o", out, "--time-stamp", "", "--aligner-version", "oracle", "--stats")
+    assert p.returncode == 0, p.stderr
+    exp = lines(pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, guide_id="guide1", assembly="SYN10M", raw=True))
+    assert len(exp) > 40 and lines(open(out).read()) == exp
+    assert "hits" in p.stderr
+
+
+def test_search_reference_cli_flags_and_vcf(calitas, ref_dir):
+    d, g, contigs = ref_dir
+    arrays = [np.frombuffer(b.upper(), dtype=np.uint8) for _, b in contigs]
+    vcf = synth.synthetic_vcf(g, arrays, 600)
+    vpath = d / "vars.vcf"
+    open(vpath, "w").write(vcf)
+    vid = "vars.vcf:" + hashlib.md5(vcf.encode()).hexdigest()
+    out = d / "hits2.tsv"
+    p = run(calitas, "SearchReference", "--guide=" + synth.BASELINE_GUIDE, "--guide-id", "g2", "-r", d / "ref.fa", "-v", vpath, "-o", out, "-O", "5", "-w", "500", "-V", "3", "-t", "4",
+            "--time-stamp", "", "--aligner-version", "oracle")
+    assert p.returncode == 0, p.stderr
+    exp = lines(pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, guide_id="g2", vcf_text=vcf, vcf_name=vid, assembly="SYN10M", raw=True, O=5, window_size=500, max_variants=3))
+    got = lines(open(out).read())
+    assert got == exp and any("+variants" in l and vid in l for l in got)
+    p = run(calitas, "SearchReference", "-i", "CTTGCCCCACAGGGCAGTAAngg", "-I", "g3", "-x", "nag", "nga", "-r", d / "ref.fa", "-o", out, "-d", "4", "-g", "2", "-p", "1", "-D", "5", "-c", "chr2",
+            "-m", "-110", "-M=-250", "-b", "-125", "-B", "-119", "--time-stamp", "", "--aligner-version", "oracle")
+    assert p.returncode == 0, p.stderr
+    exp = lines(pyoracle.search_reference(contigs, "CTTGCCCCACAGGGCAGTAAngg", guide_id="g3", aux_pams=["nag", "nga"], chrom="chr2", assembly="SYN10M", raw=True, d=4, g=2, p=1, D=5,
+                                          costs=(-110, -125, -119, -250)))
+    assert lines(open(out).read()) == exp and len(exp) > 3
+
+
+def test_search_reference_cli_guide_batch_and_stdout(calitas, ref_dir):
+    d, g, contigs = ref_dir
+    gf = d / "guides.tsv"
+    open(gf, "w").write("# id\tguide\taux\na\t%s\nb\tCTTGCCCCACAGGGCAGTAAngg\tnag\nc\tGGGGCCACTAGGGACAGGAT\n" % synth.BASELINE_GUIDE)
+    p = run(calitas, "SearchReference", "--guides-file", gf, "-r", d / "ref.fa", "--time-stamp", "", "--aligner-version", "oracle")
+    assert p.returncode == 0, p.stderr
+    exp = []
+    for gid, seq, aux in (("a", synth.BASELINE_GUIDE, []), ("b", "CTTGCCCCACAGGGCAGTAAngg", ["nag"]), ("c", "GGGGCCACTAGGGACAGGAT", [])):
+        l = lines(pyoracle.search_reference(contigs, seq, guide_id=gid, aux_pams=aux, assembly="SYN10M", raw=True))
+        exp += l if not exp else l[1:]
+    assert lines(p.stdout) == exp
+
+
+def test_align_to_reference_cli(calitas, ref_dir):
+    d, g, contigs = ref_dir
+    guides = [synth.BASELINE_GUIDE] + synth.random_guides(2)
+    tasks = synth.a2r_tasks(g, guides, 60)
+    tasks[5] = (tasks[5][0], tasks[5][1], "chr1", 30200)                  # inside the soft-masked stretch
+    tp = d / "tasks.tsv"
+    open(tp, "w").write("id\tquery\tchrom\tposition\n" + "".join("%s\t%s\t%s\t%d\n" % t for t in tasks))
+    for flags, kw in ((["-w", "60"], dict(window_size=60)), (["-w", "60", "-d", "5", "-p", "1", "-O", "10"], dict(window_size=60, d=5, p=1, O=10)), ([], dict())):
+        out = d / "a2r.tsv"
+        p = run(calitas, "AlignToReference", "-i", tp, "-r", d / "ref.fa", "-o", out, "--time-stamp", "", "--aligner-version", "oracle", *flags)
+        assert p.returncode == 0, p.stderr
+        exp = lines(pyoracle.align_to_reference(contigs, tasks, assembly="SYN10M", raw=True, **kw))
+        assert lines(open(out).read()) == exp, flags
+
+
+def test_cli_errors_mirror_the_reference(calitas, ref_dir, tmp_path):
+    d, g, contigs = ref_dir
+    p = run(calitas, "AlignToReference", "-i", d / "nope.tsv", "-r", d / "ref.fa")
+    assert p.returncode != 0 and "non-existent" in p.stderr
+    tp = tmp_path / "t.tsv"
+    open(tp, "w").write("query\tchrom\tposition\nCTTGCCCCACAGGGCAGTAAnrg\tchr1\t5000\n")
+    p = run(calitas, "AlignToReference", "-i", tp, "-r", d / "ref.fa", "-d", "3")
+    assert p.returncode != 0 and "Must specify all or none of" in p.stderr                        # AlignToReference.scala:88-92
+    p = run(calitas, "SearchReference", "-i", "cttgccccacagggcagtaa", "-I", "x", "-r", d / "ref.fa")
+    assert p.returncode != 0 and "cannot be all lower case" in p.stderr                           # SequentialGuideAligner.scala:84-87
+    p = run(calitas, "SearchReference", "-i", synth.BASELINE_GUIDE, "-I", "x", "-r", d / "ref.fa", "-c", "chrZ")
+    assert p.returncode != 0 and "Unknown chromosome" in p.stderr
+    bare = tmp_path / "bare.fa"
+    open(bare, "w").write(">c\nACGTACGTACGTACGTACGTACGTACGTACGT\n")
+    p = run(calitas, "SearchReference", "-i", synth.BASELINE_GUIDE, "-I", "x", "-r", bare)
+    assert p.returncode != 0 and "sequence dictionary" in p.stderr                                # SearchReference.scala:478-484
+    p = run(calitas, "SearchReference", "-I", "x", "-r", d / "ref.fa")
+    assert p.returncode != 0 and "required" in p.stderr

@@ -161,3 +161,20 @@ def test_align_to_reference(eng, small_genome):
         exp = _lines(pyoracle.align_to_reference(contigs, tasks, raw=True, **kw))
         got = _lines(eng.align_to_reference(contigs, tasks, raw=True, **kw))
         assert got == exp, kw
+
+
+@pytest.mark.parametrize("n_shards", [1, 3])
+def test_search_reference_batch_over_shards(eng, small_genome, n_shards):
+    """A batch of guides over 1 or 3 engines (contig-range shards driven from host threads) = the oracle's per-guide tables, concatenated."""
+    g, contigs = small_genome
+    guides = [synth.BASELINE_GUIDE, ("CTTGCCCCACAGGGCAGTAAngg", ["nag"]), "tttvCTTGCCCCACAGGGCAGTAA", "GGGGCCACTAGGGACAGGAT"]
+    ids = ["a", "b", "c", "d"]
+    arrays = [np.frombuffer(b, dtype=np.uint8) for _, b in contigs]
+    for vcf in (None, synth.synthetic_vcf(g, arrays, 300)):
+        exp = []
+        for gd, gid in zip(guides, ids):
+            seq, aux = (gd, []) if isinstance(gd, str) else gd
+            lines = _lines(pyoracle.search_reference(contigs, seq, guide_id=gid, aux_pams=aux, vcf_text=vcf, raw=True))
+            exp += lines if not exp else lines[1:]
+        got = _lines(eng.t.search_reference_batch(contigs, guides, ids, n_shards=n_shards, vcf_text=vcf))
+        assert got == exp, (n_shards, vcf is not None)
