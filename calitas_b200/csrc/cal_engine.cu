@@ -907,9 +907,24 @@ int calitas_reference_load(calitas_engine* e, int32_t n_contigs, const char* con
     r->d_raw = (uint8_t*)dev::alloc((size_t)off);
     r->d_nib = (uint32_t*)dev::alloc((size_t)off / 2);
     dev::zero(r->d_raw, (size_t)off, e->stream);
-    for (int c = 0; c < n_contigs; ++c) {
-      const int64_t n = r->have_e[(size_t)c] - r->have_b[(size_t)c];
-      if (n > 0) { if (!bases[c]) throw InvalidArgument("bases pointer is NULL"); dev::h2d(r->d_raw + r->nib_off[(size_t)c], bases[c], (size_t)n, e->stream); }
+    {  // caller memory is pageable: stage through two pinned buffers so that the host copy of chunk k+1 overlaps the H2D of chunk k
+      const size_t STAGE = 32u << 20;
+      void* stage[2] = { dev::alloc_host(STAGE), dev::alloc_host(STAGE) }; int turn = 0; bool used[2] = { false, false };
+      try {
+        for (int c = 0; c < n_contigs; ++c) {
+          const int64_t n = r->have_e[(size_t)c] - r->have_b[(size_t)c];
+          if (n > 0 && !bases[c]) throw InvalidArgument("bases pointer is NULL");
+          for (int64_t off2 = 0; off2 < n; off2 += (int64_t)STAGE) {
+            const size_t len = (size_t)std::min<int64_t>((int64_t)STAGE, n - off2);
+            if (used[turn]) dev::event_sync(e->ev[4 + turn]);
+            std::memcpy(stage[turn], bases[c] + off2, len);
+            dev::h2d(r->d_raw + r->nib_off[(size_t)c] + off2, stage[turn], len, e->stream);
+            dev::event_record(e->ev[4 + turn], e->stream); used[turn] = true; turn ^= 1;
+          }
+        }
+        dev::stream_sync(e->stream);
+      } catch (...) { try { dev::stream_sync(e->stream); } catch (...) {} dev::free_host(stage[0]); dev::free_host(stage[1]); dev::free_(r->d_raw); dev::free_(r->d_nib); throw; }
+      dev::free_host(stage[0]); dev::free_host(stage[1]);
     }
     const int64_t n_words = off / 8;
     const unsigned grid = (unsigned)std::min<int64_t>((n_words + 255) / 256, (int64_t)dev::sm_count(e->device) * 16);

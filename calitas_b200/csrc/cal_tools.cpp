@@ -39,6 +39,21 @@ struct HitSet {   // RAII over calitas_hitset
   int64_t n() const { return calitas_hitset_count(h); } const calitas_hit* data() const { return calitas_hitset_data(h); }
 };
 
+// Row rendering is the host-side bottleneck once the search takes milliseconds: rows are independent, so they are
+// rendered on all host threads.  fn(begin, end) must only touch its own index range.
+template <class F> void parallel_for(int64_t n, int64_t grain, F fn) {
+  const int64_t want = (n + grain - 1) / grain;
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()))));
+  if (nt <= 1) { fn((int64_t)0, n); return; }
+  std::vector<std::thread> th; std::vector<Str> err((size_t)nt); std::vector<int> code((size_t)nt, 0);
+  for (int t = 0; t < nt; ++t) th.emplace_back([&, t]() {
+    try { fn(n * t / nt, n * (t + 1) / nt); }
+    catch (const ToolError& e) { code[(size_t)t] = e.code; err[(size_t)t] = e.msg; }
+    catch (const std::exception& e) { code[(size_t)t] = CALITAS_ESTATE; err[(size_t)t] = e.what(); } });
+  for (auto& t : th) t.join();
+  for (int t = 0; t < nt; ++t) if (code[(size_t)t]) throw ToolError{ code[(size_t)t], err[(size_t)t] };
+}
+
 int contig_index(const calitas_genome_view& g, const Str& name) { for (int i = 0; i < g.n_contigs; ++i) if (name == g.names[i]) return i; return -1; }
 
 // ---- GuideAlignment ordering (GuideAlignment.scala:125-129): stable sort by score desc, gap bases asc ----
@@ -378,13 +393,17 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
       run_all([&](int s) { ck(calitas_search(engines[s], refs[s], n_guides, guides, &opt->limits, opt->window_size, opt->chrom, with_vcf ? 0 : 1, &hs[(size_t)s].h)); });
       const Flanks none;
       std::vector<int64_t> cursor((size_t)n_engines, 0);          // every hit set is guide-major
-      for (int g = 0; g < n_guides; ++g) for (int s = 0; s < n_engines; ++s) {
-        int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s];
-        for (; i < h_.n() && h_.data()[i].guide_idx == g; ++i) {
-          const calitas_hit& h = h_.data()[i];
-          Rendered r = render_hit(h, defs[(size_t)g], contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), true);     // windows are upper-cased, SearchReference.scala:67
-          rows[(size_t)g].push_back(make_row(cxs[(size_t)g], h, r, defs[(size_t)g], h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none));
-        }
+      for (int g = 0; g < n_guides; ++g) {
+        std::vector<const calitas_hit*> order;                    // this guide's hits: shard 0's, then shard 1's, ... = ReferenceHit.sort order
+        for (int s = 0; s < n_engines; ++s) { int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s]; for (; i < h_.n() && h_.data()[i].guide_idx == g; ++i) order.push_back(h_.data() + i); }
+        std::vector<Row>& out = rows[(size_t)g]; out.resize(order.size());
+        const GuideDef& gd = defs[(size_t)g]; const RowContext& cx = cxs[(size_t)g];
+        parallel_for((int64_t)order.size(), 2048, [&](int64_t b, int64_t e_) {
+          for (int64_t k = b; k < e_; ++k) {
+            const calitas_hit& h = *order[(size_t)k];
+            Rendered r = render_hit(h, gd, contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), true);     // windows are upper-cased, SearchReference.scala:67
+            out[(size_t)k] = make_row(cx, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none);
+          } });
       }
       for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "hit set is not guide-major" };
     }
@@ -439,10 +458,14 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
         sort_rows(rows[(size_t)g]);                                                                                      // :647
       }
     }
-    Str text = hit_header(); int64_t total = 0;
-    for (auto& v : rows) { for (auto& r : v) text += r.line; total += (int64_t)v.size(); }
+    const Str header = hit_header(); int64_t total = 0; size_t bytes = header.size();
+    for (auto& v : rows) { for (auto& r : v) bytes += r.line.size(); total += (int64_t)v.size(); }
+    char* text = (char*)std::malloc(bytes + 1); if (!text) throw ToolError{ CALITAS_ESTATE, "out of memory for the hit table" };
+    char* w = text; std::memcpy(w, header.data(), header.size()); w += header.size();
+    for (auto& v : rows) for (auto& r : v) { std::memcpy(w, r.line.data(), r.line.size()); w += r.line.size(); }
+    *w = 0;
     if (n_hits) *n_hits = total;
-    *out_tsv = dup_text(text);
+    *out_tsv = text;
     return CALITAS_OK;
   });
 }
