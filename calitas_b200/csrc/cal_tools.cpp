@@ -1,6 +1,7 @@
 // cal_tools.cpp — host-side mirror of the reference's operators (see include/calitas_b200_tools.h).
 // Alignments are computed only by the device engine (calitas_search / calitas_align_regions / calitas_align_targets).
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -41,6 +42,12 @@ struct HitSet {   // RAII over calitas_hitset
 
 // Row rendering is the host-side bottleneck once the search takes milliseconds: rows are independent, so they are
 // rendered on all host threads.  fn(begin, end) must only touch its own index range.
+// CALITAS_TOOL_TIMING=1: phase timings of the tool layer on stderr
+struct PhaseTimer {
+  bool on = std::getenv("CALITAS_TOOL_TIMING") != nullptr; std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) { if (!on) return; auto n = std::chrono::steady_clock::now(); std::fprintf(stderr, "[calitas tool] %-28s %8.3f s\n", what, std::chrono::duration<double>(n - t).count()); t = n; }
+};
+
 template <class F> void parallel_for(int64_t n, int64_t grain, F fn) {
   const int64_t want = (n + grain - 1) / grain;
   const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()))));
@@ -207,9 +214,12 @@ void allele_vectors(const std::vector<int>& counts, std::vector<std::vector<int>
   for (size_t r = 0; r < total; ++r) { size_t rem = r; for (size_t i = counts.size(); i-- > 0;) { out[r][i] = (int)(rem % (size_t)counts[i]); rem /= (size_t)counts[i]; } }
 }
 
-VariantWindow build_variant_window(const std::vector<const VcfRecord*>& vars, const std::vector<int>& alleles, int contig, const Str& upper_bases, int padding) {
-  const int ws = std::max(1, vars.front()->pos - padding), we = (int)std::min<int64_t>((int64_t)upper_bases.size(), (int64_t)vars.back()->end() + padding);
-  VariantWindow w; w.contig = contig; w.start = ws; w.bases = upper_bases.substr((size_t)ws - 1, (size_t)(we - ws + 1));
+// Contig bases as the variant iterator sees them: upper-cased (SearchReference.scala:225); only the window is copied.
+struct ContigRef { const char* p; int64_t len; };
+VariantWindow build_variant_window(const std::vector<const VcfRecord*>& vars, const std::vector<int>& alleles, int contig, const ContigRef& ref, int padding) {
+  const int ws = std::max(1, vars.front()->pos - padding), we = (int)std::min<int64_t>(ref.len, (int64_t)vars.back()->end() + padding);
+  VariantWindow w; w.contig = contig; w.start = ws;
+  if (ws <= we) { w.bases.assign(ref.p + ws - 1, (size_t)(we - ws + 1)); for (auto& c : w.bases) c = (char)std::toupper((unsigned char)c); }
   for (size_t i = 0; i < vars.size(); ++i) {
     const VcfRecord* v = vars[i]; const int a = alleles[i];
     const float af = (v->has_af && a - 1 < (int)v->afs.size()) ? v->afs[(size_t)a - 1] : 0.0f;     // SearchReference.scala:199
@@ -217,6 +227,7 @@ VariantWindow build_variant_window(const std::vector<const VcfRecord*>& vars, co
   }
   for (size_t k = w.alleles.size(); k-- > 0;) {   // right to left (:270-279)
     const VariantAllele& a = w.alleles[k]; const size_t at = (size_t)(a.pos - ws);
+    if (at > w.bases.size()) bad("variant lies outside its contig: " + a.id);
     if (a.ref.size() == a.alt.size()) w.bases.replace(at, a.alt.size(), a.alt);
     else w.bases = w.bases.substr(0, at) + a.alt + (at + a.ref.size() < w.bases.size() ? w.bases.substr(at + a.ref.size()) : Str());
   }
@@ -236,37 +247,53 @@ VariantWindow build_variant_window(const std::vector<const VcfRecord*>& vars, co
   return w;
 }
 
-std::vector<VariantWindow> variant_windows(const calitas_genome_view& g, const std::vector<VcfRecord>& all, int chrom_idx, int padding, int max_variants) {
-  std::vector<VariantWindow> out;
-  std::vector<const VcfRecord*> vs;
-  for (auto& v : all) if (chrom_idx < 0 || v.chrom == g.names[chrom_idx]) vs.push_back(&v);
-  std::map<int, Str> upper_cache;
-  int ref_idx = chrom_idx >= 0 ? chrom_idx : 0;
-  for (size_t i = 0; i < vs.size();) {
-    std::vector<const VcfRecord*> cluster; const VcfRecord* last = vs[i++]; cluster.push_back(last);          // nextChunk :326-337
-    while (i < vs.size() && vs[i]->chrom == last->chrom && vs[i]->pos <= last->end() + padding) { last = vs[i++]; cluster.push_back(last); }
-    while (cluster.front()->chrom != g.names[ref_idx]) { if (++ref_idx >= g.n_contigs) bad("VCF contig " + cluster.front()->chrom + " not found in FASTA order"); upper_cache.clear(); }   // :251
-    if (!upper_cache.count(ref_idx)) upper_cache[ref_idx] = to_upper(Str((const char*)g.bases[ref_idx], (size_t)g.lengths[ref_idx]));   // :225
-    const Str& ub = upper_cache[ref_idx];
-    for (size_t t = 0; t < cluster.size(); ++t) {                                                            // reChunk :343-347
-      std::vector<const VcfRecord*> sub;
-      for (size_t u = t; u < cluster.size() && cluster[u]->pos - cluster[t]->end() <= padding; ++u) sub.push_back(cluster[u]);
-      if ((int)sub.size() > max_variants) {                                                                  // :352-356
-        for (size_t a = 0; a < sub[0]->alts.size(); ++a) out.push_back(build_variant_window({ sub[0] }, { (int)a + 1 }, ref_idx, ub, padding));
-        continue;
-      }
-      std::vector<int> counts; for (auto* v : sub) counts.push_back(1 + (int)v->alts.size());
-      std::vector<std::vector<int>> combos; allele_vectors(counts, combos);
-      for (auto& combo : combos) {
-        std::vector<const VcfRecord*> sv; std::vector<int> sa;
-        for (size_t k = 0; k < sub.size(); ++k) if (combo[k] != 0) { sv.push_back(sub[k]); sa.push_back(combo[k]); }
-        if (sv.empty()) continue;
-        bool valid = true;                                                                                   // VariantSet.isValid :182-193
-        for (size_t k = 0; k + 1 < sv.size() && valid; ++k) if (sv[k]->pos <= sv[k + 1]->end() && sv[k + 1]->pos <= sv[k]->end()) valid = false;
-        if (valid) out.push_back(build_variant_window(sv, sa, ref_idx, ub, padding));
-      }
+// Every window of one cluster of nearby variants, in the reference's order: reChunk (:343-347) x alleleCombos (:351-369, 377-399).
+void cluster_windows(const std::vector<const VcfRecord*>& cluster, int ref_idx, const ContigRef& ref, int padding, int max_variants, std::vector<VariantWindow>& out) {
+  for (size_t t = 0; t < cluster.size(); ++t) {
+    std::vector<const VcfRecord*> sub;
+    for (size_t u = t; u < cluster.size() && cluster[u]->pos - cluster[t]->end() <= padding; ++u) sub.push_back(cluster[u]);
+    if ((int)sub.size() > max_variants) {                                                                  // :352-356
+      for (size_t a = 0; a < sub[0]->alts.size(); ++a) out.push_back(build_variant_window({ sub[0] }, { (int)a + 1 }, ref_idx, ref, padding));
+      continue;
+    }
+    std::vector<int> counts; for (auto* v : sub) counts.push_back(1 + (int)v->alts.size());
+    std::vector<std::vector<int>> combos; allele_vectors(counts, combos);
+    for (auto& combo : combos) {
+      std::vector<const VcfRecord*> sv; std::vector<int> sa;
+      for (size_t k = 0; k < sub.size(); ++k) if (combo[k] != 0) { sv.push_back(sub[k]); sa.push_back(combo[k]); }
+      if (sv.empty()) continue;
+      bool valid = true;                                                                                   // VariantSet.isValid :182-193
+      for (size_t k = 0; k + 1 < sv.size() && valid; ++k) if (sv[k]->pos <= sv[k + 1]->end() && sv[k + 1]->pos <= sv[k]->end()) valid = false;
+      if (valid) out.push_back(build_variant_window(sv, sa, ref_idx, ref, padding));
     }
   }
+}
+
+std::vector<VariantWindow> variant_windows(const calitas_genome_view& g, const std::vector<VcfRecord>& all, int chrom_idx, int padding, int max_variants) {
+  std::vector<const VcfRecord*> vs;
+  for (auto& v : all) if (chrom_idx < 0 || v.chrom == g.names[chrom_idx]) vs.push_back(&v);
+  // pass 1 (sequential, cheap): clusters of variants within `padding` of each other, each on its contig — nextChunk :326-337, contig walk :251
+  struct Cluster { int ref_idx; size_t begin, end; };
+  std::vector<Cluster> clusters;
+  int ref_idx = chrom_idx >= 0 ? chrom_idx : 0;
+  for (size_t i = 0; i < vs.size();) {
+    const size_t first = i; const VcfRecord* last = vs[i++];
+    while (i < vs.size() && vs[i]->chrom == last->chrom && vs[i]->pos <= last->end() + padding) last = vs[i++];
+    while (vs[first]->chrom != g.names[ref_idx]) { if (++ref_idx >= g.n_contigs) bad("VCF contig " + vs[first]->chrom + " not found in FASTA order"); }
+    clusters.push_back(Cluster{ ref_idx, first, i });
+  }
+  // pass 2: clusters are independent -> built on all host threads, concatenated in order
+  std::vector<std::vector<VariantWindow>> per((size_t)clusters.size());
+  parallel_for((int64_t)clusters.size(), 512, [&](int64_t b, int64_t e) {
+    for (int64_t c = b; c < e; ++c) {
+      const Cluster& cl = clusters[(size_t)c];
+      std::vector<const VcfRecord*> cluster(vs.begin() + (long)cl.begin, vs.begin() + (long)cl.end);
+      const ContigRef ref{ (const char*)g.bases[cl.ref_idx], g.lengths[cl.ref_idx] };
+      cluster_windows(cluster, cl.ref_idx, ref, padding, max_variants, per[(size_t)c]);
+    } });
+  size_t total = 0; for (auto& v : per) total += v.size();
+  std::vector<VariantWindow> out; out.reserve(total);
+  for (auto& v : per) for (auto& w : v) out.push_back(std::move(w));
   return out;
 }
 
@@ -380,6 +407,7 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
     if (opt->chrom && opt->chrom[0]) { chrom_idx = contig_index(*genome, opt->chrom); if (chrom_idx < 0) bad(Str("Unknown chromosome: ") + opt->chrom); }
     const bool with_vcf = opt->vcf_text != nullptr;
     std::vector<std::vector<Row>> rows((size_t)n_guides);
+    PhaseTimer pt;
     // every engine's work runs on its own host thread; errors travel back as (code, message)
     auto run_all = [&](const std::function<void(int)>& job) {
       std::vector<int> rc((size_t)n_engines, CALITAS_OK); std::vector<Str> msg((size_t)n_engines);
@@ -391,6 +419,7 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
     {  // reference windows: SearchReference.scala:527-564 (+ removeOverlaps/sort on the device when there is no VCF)
       std::vector<HitSet> hs((size_t)n_engines);
       run_all([&](int s) { ck(calitas_search(engines[s], refs[s], n_guides, guides, &opt->limits, opt->window_size, opt->chrom, with_vcf ? 0 : 1, &hs[(size_t)s].h)); });
+      pt.lap("reference search (device)");
       const Flanks none;
       std::vector<int64_t> cursor((size_t)n_engines, 0);          // every hit set is guide-major
       for (int g = 0; g < n_guides; ++g) {
@@ -406,9 +435,11 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
           } });
       }
       for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "hit set is not guide-major" };
+      pt.lap("reference rows");
     }
     if (with_vcf) {  // SearchReference.scala:570-630
       std::vector<VcfRecord> recs = parse_vcf(opt->vcf_text);
+      pt.lap("parse vcf");
       // variant windows depend on the guide only through the padding (Guide.length, :575): build once per distinct padding
       std::map<int, std::vector<VariantWindow>> by_padding;
       std::vector<const std::vector<VariantWindow>*> windows_of((size_t)n_guides);
@@ -418,6 +449,7 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
         if (it == by_padding.end()) it = by_padding.emplace(padding, variant_windows(*genome, recs, chrom_idx, padding, opt->max_variants)).first;
         windows_of[(size_t)g] = &it->second;
       }
+      pt.lap("variant windows");
       struct TaskRef { int guide; int window; };
       std::vector<std::vector<calitas_target_task>> tasks((size_t)n_engines); std::vector<std::vector<TaskRef>> task_ref((size_t)n_engines);
       int64_t rr = 0;
@@ -426,6 +458,7 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
           tasks[s].push_back(calitas_target_task{ g, (const uint8_t*)ws[w].bases.data(), (int32_t)ws[w].bases.size(), 0 }); task_ref[s].push_back(TaskRef{ g, (int)w }); } }
       std::vector<HitSet> hs((size_t)n_engines);
       run_all([&](int s) { if (!tasks[(size_t)s].empty()) ck(calitas_align_targets(engines[s], n_guides, guides, (int64_t)tasks[(size_t)s].size(), tasks[(size_t)s].data(), &opt->limits, 0, &hs[(size_t)s].h)); });
+      pt.lap("variant windows (device)");
       // rows must arrive in the reference's window order per guide (it decides ties in removeOverlaps): walk tasks in global order
       std::vector<int64_t> cursor((size_t)n_engines, 0); std::vector<int64_t> next_task((size_t)n_engines, 0);
       rr = 0;
@@ -453,10 +486,12 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
           }
         } }
       for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "variant hit set is not task-major" };
+      pt.lap("variant rows");
       for (int g = 0; g < n_guides; ++g) {
         rows[(size_t)g] = remove_overlaps_host(rows[(size_t)g], opt->limits.max_overlap);                                 // :641
         sort_rows(rows[(size_t)g]);                                                                                      // :647
       }
+      pt.lap("removeOverlaps + sort (host)");
     }
     const Str header = hit_header(); int64_t total = 0; size_t bytes = header.size();
     for (auto& v : rows) { for (auto& r : v) bytes += r.line.size(); total += (int64_t)v.size(); }
