@@ -193,7 +193,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the first communicator comes up; the contract is ONE JSON line on stdout,
+        # so stdout is pointed at stderr while the process group initialises.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     guides = guide_list(args)
     genome = synth.hg38_like_genome(args.scale, guides=[guide_text(g) for g in guides], sites_per_guide=200)
     n = len(genome.lengths)

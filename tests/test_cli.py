@@ -106,6 +106,27 @@ def test_search_reference_cli_guide_batch_and_stdout(calitas, ref_dir):
     assert lines(p.stdout) == exp
 
 
+def test_search_reference_cli_sharded_over_devices(calitas, ref_dir):
+    """--devices a,b,c: one engine per device, contig-range shards driven from host threads; output identical to the single-device table."""
+    d, g, contigs = ref_dir
+    if calitas.endswith("hostsim"):
+        devices = "0,0,0"                                  # the host simulation ignores device ids; three shards all the same
+    else:
+        import torch
+        n = min(3, torch.cuda.device_count())
+        if n < 2:
+            pytest.skip("needs at least 2 GPUs")
+        devices = ",".join(str(i) for i in range(n))
+    gf = d / "guides2.tsv"
+    open(gf, "w").write("a\t%s\nb\tCTTGCCCCACAGGGCAGTAAngg\tnag\n" % synth.BASELINE_GUIDE)
+    outs = []
+    for dev in ("0", devices):
+        p = run(calitas, "SearchReference", "--guides-file", gf, "-r", d / "ref.fa", "--devices", dev, "--time-stamp", "", "--aligner-version", "oracle")
+        assert p.returncode == 0, p.stderr
+        outs.append(p.stdout)
+    assert outs[0] == outs[1] and len(lines(outs[0])) > 80
+
+
 def test_align_to_reference_cli(calitas, ref_dir):
     d, g, contigs = ref_dir
     guides = [synth.BASELINE_GUIDE] + synth.random_guides(2)
