@@ -36,6 +36,10 @@ const int ALIGN_KB = 6;          // k_align keeps a 2*6+1-diagonal DP band in re
 const int TILE_WINDOWS = 64;
 const int HALO_WINDOWS = 2;      // windows processed beyond each interior shard cut so that removeOverlaps sees both sides of the cut
 const int SCAN_THREADS = 2 * TILE_WINDOWS;
+#ifndef CAL_SCAN_NG
+#define CAL_SCAN_NG 2
+#endif
+const int SCAN_NG = CAL_SCAN_NG;     // guides a scan thread advances together (independent dependency chains sharing the base-code extraction)
 const int KEY_COL_BITS = 17, KEY_WIN_SHIFT = 18, KEY_GUIDE_SHIFT = 50;
 const uint32_t MAX_WINDOW_LEN = (1u << KEY_COL_BITS) - 1;
 const int MAX_GUIDES_PER_CALL = 1 << 14;
@@ -189,16 +193,19 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
     const int32_t m = re - rs;
     if (m <= 0 || m < a.min_len) return;                              // SearchReference.scala:536
     const uint32_t wid = (uint32_t)(ctg.win_base + tile.first_k + kk);
-    for (int g = 2 * slot; g < ng; g += 2 * n_slots) {
-      ScanGuide sg[2];
-      const int cnt = g + 1 < ng ? 2 : 1;
+    for (int g = SCAN_NG * slot; g < ng; g += SCAN_NG * n_slots) {
+      ScanGuide sg[SCAN_NG];
+      const int cnt = ng - g < SCAN_NG ? ng - g : SCAN_NG;
       for (int j = 0; j < cnt; ++j) {
         sg[j].peq = s_peq + (g + j) * 32 + dir * 16; sg[j].lp = s_meta[4 * (g + j)]; sg[j].k_edits = s_meta[4 * (g + j) + 1];
         sg[j].key_base = make_key((uint32_t)(a.g_begin + g + j), wid, (uint32_t)(dir ^ s_meta[4 * (g + j) + 2]), 0);
       }
       const uint32_t tbl = (uint32_t)(2 * g + dir);
-      if (cnt == 2) { if (dir == 0) scan_window<0, 2>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 2>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); }
-      else          { if (dir == 0) scan_window<0, 1>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 1>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); }
+#define CAL_SCAN_CALL(N) { if (dir == 0) scan_window<0, N>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); else scan_window<1, N>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); }
+      if (cnt == SCAN_NG) CAL_SCAN_CALL(SCAN_NG)
+      else if (cnt >= 2) { CAL_SCAN_CALL(2) if (cnt == 3) { sg[0] = sg[2]; const uint32_t tbl3 = tbl + 4; if (dir == 0) scan_window<0, 1>(s_tile, rs, re, sg, s_peq, tbl3, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 1>(s_tile, rs, re, sg, s_peq, tbl3, a.cand, a.cand_count, a.cand_cap); } }
+      else CAL_SCAN_CALL(1)
+#undef CAL_SCAN_CALL
     }
   }
 }
@@ -981,7 +988,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       const int64_t tile_bases = (int64_t)(TILE_WINDOWS - 1) * ch.step + window_size;
       ch.smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2) * 4;
       if (ch.smem > 200 * 1024) throw LimitExceeded("window size too large for the shared-memory tile");
-      ch.scan_slots = ng >= 8 ? 4 : (ng >= 3 ? 2 : 1);     // guide slots per window: more resident warps when the chunk has enough guides
+      ch.scan_slots = std::min(4, std::max(1, (ng + SCAN_NG - 1) / SCAN_NG));     // guide slots per window: more resident warps when the chunk has enough guides
       ch.bases = 0; for (size_t t = ch.t_begin; t < t_end; ++t) ch.bases += (int64_t)(ch.ts->tiles[t].nwin - 1) * ch.step + window_size;
       chunks.push_back(ch);
       g0 = g1;
