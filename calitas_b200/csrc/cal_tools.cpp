@@ -568,6 +568,42 @@ int calitas_tool_align_to_reference(calitas_engine* e, const calitas_reference* 
   });
 }
 
+// PairwiseAlignSequences.execute (PairwiseAlignSequences.scala:44-83): alignBest of each (query, upper-cased target) pair, 11 columns.
+// The reference calls alignBest(guide, target) without forwarding its own -g/-O flags, so the gap limit is always the default 3.
+int calitas_tool_pairwise_align(calitas_engine* e, int64_t n_pairs, const char* const* queries, const char* const* targets, char** out_tsv) {
+  return guarded([&]() -> int {
+    if (!e || !out_tsv || n_pairs < 0 || (n_pairs && (!queries || !targets))) bad("bad arguments");
+    *out_tsv = nullptr;
+    Str text = "query\ttarget\tscore\tquery_start\ttarget_start\tcigar\tmismatches\tgap_bases\tpadded_query\talignment\tpadded_target\n";
+    calitas_limits lim{ 0, 0, 3, -1, 0 };
+    for (int64_t b0 = 0; b0 < n_pairs; b0 += 10000) {                                                  // :63
+      const int64_t b1 = std::min<int64_t>(n_pairs, b0 + 10000);
+      std::map<Str, int> guide_of; std::vector<Str> qs; std::vector<GuideDef> defs; std::vector<Str> ups; std::vector<calitas_target_task> tasks;
+      for (int64_t i = b0; i < b1; ++i) {
+        if (!queries[i] || !targets[i]) bad("query/target is NULL");
+        auto it = guide_of.find(queries[i]);
+        if (it == guide_of.end()) { it = guide_of.emplace(queries[i], (int)qs.size()).first; qs.push_back(queries[i]); defs.push_back(parse_guide(queries[i], {})); }
+        ups.push_back(to_upper(targets[i]));                                                           // :53
+      }
+      for (int64_t i = b0; i < b1; ++i) { const Str& t = ups[(size_t)(i - b0)]; tasks.push_back(calitas_target_task{ guide_of[queries[i]], (const uint8_t*)t.data(), (int32_t)t.size(), 0 }); }
+      std::vector<calitas_guide> cg; for (auto& q : qs) cg.push_back(calitas_guide{ q.c_str(), nullptr, 0 });
+      HitSet hs; ck(calitas_align_targets(e, (int32_t)cg.size(), cg.data(), (int64_t)tasks.size(), tasks.data(), &lim, 1, &hs.h));
+      int64_t i = 0;
+      for (int64_t t = 0; t < (int64_t)tasks.size(); ++t) {
+        const calitas_hit* best = nullptr;
+        for (; i < hs.n() && hs.data()[i].task_idx == t; ++i) if (!best || hs.data()[i].score > best->score) best = hs.data() + i;     // maxBy keeps the first maximum (:344)
+        if (!best) throw ToolError{ CALITAS_ESTATE, Str("empty.maxBy: no alignment for ") + queries[b0 + t] };
+        const Str& tgt = ups[(size_t)t]; const GuideDef& gd = defs[(size_t)tasks[(size_t)t].guide_idx];
+        Rendered r = render_hit(*best, gd, tgt.substr((size_t)best->start_offset, (size_t)(best->end_offset - best->start_offset)), false);
+        text += Str(queries[b0 + t]) + "\t" + tgt + "\t" + std::to_string(best->score) + "\t1\t" + std::to_string(best->start_offset) + "\t" + r.cigar + "\t" +
+                std::to_string(r.mismatches) + "\t" + std::to_string(r.gap_bases) + "\t" + r.padded_guide + "\t" + r.padded_alignment + "\t" + r.padded_target + "\n";
+      }
+    }
+    *out_tsv = dup_text(text);
+    return CALITAS_OK;
+  });
+}
+
 int calitas_tool_variant_windows(const calitas_genome_view* genome, const char* vcf_text, const char* chrom, int32_t padding, int32_t max_variants, char** out_text) {
   return guarded([&]() -> int {
     if (!genome || !vcf_text || !out_text) bad("bad arguments");

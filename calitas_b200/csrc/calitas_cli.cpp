@@ -6,6 +6,7 @@
 // --guides-file (a batch of guides in one run: `id<TAB>guide[<TAB>auxPam,auxPam]` per line; the engine scans 16 guides per pass),
 // --time-stamp / --aligner-version (fix the two run-dependent columns, for reproducible comparisons), --stats (timings to stderr).
 // -t/--threads is accepted and ignored (the reference's CPU thread count).
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -185,11 +186,38 @@ int align_to_reference(int argc, char** argv) {
   return 0;
 }
 
+int pairwise_align(int argc, char** argv) {           // PairwiseAlignSequences.scala:24-36
+  std::vector<FlagDef> defs = { { 'i', "input", false }, { 'o', "output", false }, { 't', "threads", false }, { 'g', "max-gaps-between-guide-and-pam", false }, { 'O', "max-overlap", false },
+                                { 'm', "guide-mismatch-net-cost", false }, { 'M', "pam-mismatch-net-cost", false }, { 'b', "genome-gap-net-cost", false }, { 'B', "guide-gap-net-cost", false }, { 0, "devices", false } };
+  Flags f{ parse_flags(argc, argv, 2, defs) };
+  const Str text = read_file(f.required("input"));
+  std::vector<Str> qs, ts; size_t a = 0;
+  while (a < text.size()) {
+    size_t b = text.find('\n', a); if (b == Str::npos) b = text.size();
+    const Str line = text.substr(a, b - a); a = b + 1;
+    std::vector<Str> fields; size_t x = 0;
+    while (x < line.size()) { while (x < line.size() && std::isspace((unsigned char)line[x])) ++x; size_t y = x; while (y < line.size() && !std::isspace((unsigned char)line[y])) ++y; if (y > x) fields.push_back(line.substr(x, y - x)); x = y; }
+    if (fields.empty()) continue;
+    if (fields.size() != 2) { Str joined; for (auto& s : fields) { if (!joined.empty()) joined += ' '; joined += s; } throw UsageError{ "requirement failed: Line found with " + std::to_string(fields.size()) + " fields: " + joined }; }
+    qs.push_back(fields[0]); ts.push_back(fields[1]);
+  }
+  calitas_costs costs{ f.integer("guide-mismatch-net-cost", -120), f.integer("genome-gap-net-cost", -122), f.integer("guide-gap-net-cost", -121), f.integer("pam-mismatch-net-cost", -260) };
+  calitas_engine* e = nullptr; ck(calitas_engine_create(parse_devices(f.str("devices", "0"))[0], &costs, &e));
+  std::vector<const char*> qp, tp; for (size_t i = 0; i < qs.size(); ++i) { qp.push_back(qs[i].c_str()); tp.push_back(ts[i].c_str()); }
+  char* tsv = nullptr; const int rc = calitas_tool_pairwise_align(e, (int64_t)qs.size(), qp.data(), tp.data(), &tsv);
+  const Str err = rc ? calitas_last_error() : "";
+  if (!rc) { write_file(f.str("output", "-"), tsv, std::strlen(tsv)); calitas_free_text(tsv); }
+  calitas_engine_destroy(e);
+  if (rc) throw UsageError{ err };
+  return 0;
+}
+
 void usage() {
   std::fprintf(stderr,
     "calitas (B200 engine)\nUSAGE: calitas SearchReference -i GUIDEpam -I ID -r ref.fa [-x pam ...] [-v variants.vcf] [-V 16] [-o out.tsv] [-w 1000] [-d 5] [-p 1] [-g 3] [-D n] [-O 10]\n"
     "                               [-m -120] [-M -260] [-b -122] [-B -121] [-c chrom] [--devices 0,1,...] [--guides-file file]\n"
-    "       calitas AlignToReference -i tasks.tsv -r ref.fa [-o out.tsv] [-w n] [-d n -p n -O n] [-g 3] [-D n] [-m -M -b -B]\n");
+    "       calitas AlignToReference -i tasks.tsv -r ref.fa [-o out.tsv] [-w n] [-d n -p n -O n] [-g 3] [-D n] [-m -M -b -B]\n"
+    "       calitas PairwiseAlignSequences -i pairs.txt [-o out.tsv] [-m -M -b -B]\n");
 }
 
 }  // namespace
@@ -200,6 +228,7 @@ int main(int argc, char** argv) {
     const Str tool = argv[1];
     if (tool == "SearchReference") return search_reference(argc, argv);
     if (tool == "AlignToReference") return align_to_reference(argc, argv);
+    if (tool == "PairwiseAlignSequences") return pairwise_align(argc, argv);
     usage(); std::fprintf(stderr, "Unknown tool: %s\n", argv[1]); return 1;
   } catch (const UsageError& e) { std::fprintf(stderr, "calitas: %s\n", e.msg.c_str()); return 2; }
   catch (const IoError& e) { std::fprintf(stderr, "calitas: %s\n", e.msg.c_str()); return 2; }

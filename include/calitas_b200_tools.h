@@ -8,6 +8,7 @@
  *   calitas_tool_align_to_ref       alignToRef / alignToRefBest           (:359-418)
  *   calitas_tool_search_reference   SearchReference.execute               (SearchReference.scala:513-649)
  *   calitas_tool_align_to_reference AlignToReference.execute              (AlignToReference.scala:95-147)
+ *   calitas_tool_pairwise_align     PairwiseAlignSequences.execute        (PairwiseAlignSequences.scala:44-83)
  * All computation of alignments happens on the device through calitas_search / calitas_align_regions / calitas_align_targets;
  * this layer parses, builds windows for variants, renders text and (for VCF runs) merges reference and variant hits.
  * Text results are malloc'd; release with calitas_free_text.  Alignment rows use the columns of calitas_render_alignments;
@@ -62,6 +63,9 @@ typedef struct calitas_a2r_options {         /* AlignToReference.scala:35-50; -1
 } calitas_a2r_options;
 int calitas_tool_align_to_reference(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, int64_t n_tasks,
                                     const calitas_a2r_task* tasks, const calitas_a2r_options* opt, char** out_tsv, int64_t* n_hits);
+
+/* PairwiseAlignSequences.execute (PairwiseAlignSequences.scala:44-83): one alignBest per (query, target) pair; 11-column table with header. */
+int calitas_tool_pairwise_align(calitas_engine* e, int64_t n_pairs, const char* const* queries, const char* const* targets, char** out_tsv);
 
 /* Inspection hook for the variant path (SearchReference.scala:217-399): one line per variant window
  * "chrom \t start \t cigar \t bases \t id:pos:ref>alt;..." in iterator order. */

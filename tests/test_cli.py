@@ -160,3 +160,29 @@ def test_cli_errors_mirror_the_reference(calitas, ref_dir, tmp_path):
     assert p.returncode != 0 and "sequence dictionary" in p.stderr                                # SearchReference.scala:478-484
     p = run(calitas, "SearchReference", "-I", "x", "-r", d / "ref.fa")
     assert p.returncode != 0 and "required" in p.stderr
+
+
+def test_pairwise_align_sequences_cli(calitas, tmp_path):
+    """PairwiseAlignSequences.scala:44-83: `query target` lines -> alignBest -> 11 columns."""
+    rng = np.random.default_rng(11)
+    pairs = [("AACCGGTTAACCGGTTAACC", "TTAACCGGGTTAACCGGTTAACCTT"), ("AACCGGTTAACCGGTTAACC", "ttaaccgttaaccggttaacctt"), ("CTTGCCCCACAGGGCAGTAAnrg", "GGCTTGCCCCACAGGGCAGTAACGGTT"),
+             ("tttvCTTGCCCCACAGGGCAGTAA", "AATTTACTTGCCCCACTGGGCAGTAAGG")]
+    for _ in range(40):
+        q = "".join(rng.choice(list("ACGT"), size=int(rng.integers(8, 24))))
+        t = list(rng.choice(list("ACGT"), size=int(rng.integers(30, 80))))
+        p = int(rng.integers(0, len(t) - len(q) + 1))
+        t[p:p + len(q)] = list(synth.mutate_protospacer(rng, q.encode(), int(rng.integers(0, 4))).decode())[:len(q)]
+        pairs.append((q + ("ngg" if rng.random() < 0.5 else ""), "".join(t)))
+    inp = tmp_path / "pairs.txt"
+    open(inp, "w").write("\n".join("%s  %s" % p for p in pairs) + "\n\n")
+    out = tmp_path / "pairs.tsv"
+    p = run(calitas, "PairwiseAlignSequences", "-i", inp, "-o", out, "-t", "2")
+    assert p.returncode == 0, p.stderr
+    exp = ["query\ttarget\tscore\tquery_start\ttarget_start\tcigar\tmismatches\tgap_bases\tpadded_query\talignment\tpadded_target"]
+    for q, t in pairs:
+        a = pyoracle.align_best(q, t.upper())
+        exp.append("\t".join(str(x) for x in (q, t.upper(), a["score"], 1, a["startOffset"], a["cigar"], a["mismatches"], a["gapBases"], a["paddedGuide"], a["paddedAlignment"], a["paddedTarget"])))
+    assert lines(open(out).read()) == exp
+    open(inp, "w").write("AAA CCC GGG\n")
+    p = run(calitas, "PairwiseAlignSequences", "-i", inp)
+    assert p.returncode != 0 and "Line found with 3 fields" in p.stderr
