@@ -172,6 +172,35 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
   const int64_t nib0 = ctg.nib_base + tile_start;
   const int64_t word0 = nib0 >> 3;
   const int32_t n_words = (int32_t)(((ctg.nib_base + tile_end + 7) >> 3) - word0);
+#ifndef CAL_HOSTSIM
+  // The tile's packed bases (~31 KB) come in with one TMA bulk copy (cp.async.bulk, completion on an mbarrier) issued by one thread, while
+  // all threads stage the guides' mask tables: no per-thread LDG/STS loop, no address arithmetic on the ALU pipe this kernel is bound by.
+  __shared__ __align__(8) unsigned long long s_mbar;
+  {
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    const int64_t word0a = word0 & ~3ll;                                // 16-byte aligned source; the tile starts `lead` words in
+    const int32_t lead = (int32_t)(word0 - word0a);
+    const uint32_t bytes = (uint32_t)((((uint32_t)(n_words + lead)) * 4u + 15u) & ~15u);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"((uint32_t)__cvta_generic_to_shared(s_tile)), "l"(a.nib + word0a), "r"(bytes), "r"(mbar) : "memory");
+    }
+    for (int i = threadIdx.x; i < ng * 32; i += blockDim.x) s_peq[i] = a.specs[a.g_begin + (i >> 5)].peq[(i >> 4) & 1][i & 15];
+    for (int i = threadIdx.x; i < ng; i += blockDim.x) {
+      const GuideSpec& sp = a.specs[a.g_begin + i];
+      s_meta[4 * i] = sp.lp; s_meta[4 * i + 1] = sp.k_edits; s_meta[4 * i + 2] = sp.five_prime; s_meta[4 * i + 3] = 0;
+    }
+    asm volatile("{\n\t.reg .pred p;\n\tTILE_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0, 0x989680;\n\t@p bra TILE_DONE;\n\tbra TILE_WAIT;\n\tTILE_DONE:\n\t}" :: "r"(mbar) : "memory");
+    s_tile += lead;
+  }
+  __syncthreads();
+#else
   CAL_PHASE(0) {
     for (int i = threadIdx.x; i < n_words; i += blockDim.x) s_tile[i] = __ldg(a.nib + word0 + i);
     for (int i = threadIdx.x; i < ng * 32; i += blockDim.x) s_peq[i] = a.specs[a.g_begin + (i >> 5)].peq[(i >> 4) & 1][i & 15];
@@ -181,6 +210,7 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
     }
   }
   __syncthreads();
+#endif
   CAL_PHASE(1) {
     const int kk = threadIdx.x % TILE_WINDOWS, dir = (threadIdx.x / TILE_WINDOWS) & 1, slot = threadIdx.x / SCAN_THREADS, n_slots = blockDim.x / SCAN_THREADS;
     if (kk >= tile.nwin) return;
@@ -986,7 +1016,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       if (ch.banded > ALIGN_KB) ch.banded = 0;
       const int ng = g1 - g0;
       const int64_t tile_bases = (int64_t)(TILE_WINDOWS - 1) * ch.step + window_size;
-      ch.smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2) * 4;
+      ch.smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2 + 8) * 4;          // + lead-in and rounding of the 16-byte-granular bulk copy
       if (ch.smem > 200 * 1024) throw LimitExceeded("window size too large for the shared-memory tile");
       ch.scan_slots = std::min(4, std::max(1, (ng + SCAN_NG - 1) / SCAN_NG));     // guide slots per window: more resident warps when the chunk has enough guides
       ch.bases = 0; for (size_t t = ch.t_begin; t < t_end; ++t) ch.bases += (int64_t)(ch.ts->tiles[t].nwin - 1) * ch.step + window_size;
