@@ -519,48 +519,57 @@ int calitas_tool_align_to_reference(calitas_engine* e, const calitas_reference* 
     calitas_limits lim{ best ? 0 : opt->max_guide_diffs, best ? 0 : opt->max_pam_mismatches, opt->max_gaps_between_guide_and_pam,
                         best ? -1 : (opt->max_total_diffs >= 0 ? opt->max_total_diffs : opt->max_guide_diffs + opt->max_gaps_between_guide_and_pam + opt->max_pam_mismatches),
                         best ? 0 : opt->max_overlap };
+    // One device call per span of tasks (bounded only by the engine's guide table): the reference's batches of 10 000 rows
+    // (AlignToReference.scala:110) matter for the ORDER of the output — each batch is sorted on its own (:141) — not for how the work is cut.
     Str text = hit_header(); int64_t total = 0;
     const Flanks none;
-    for (int64_t b0 = 0; b0 < n_tasks; b0 += 10000) {                                                 // AlignToReference.scala:110
-      const int64_t b1 = std::min<int64_t>(n_tasks, b0 + 10000);
-      // distinct query strings of the batch share one device guide descriptor
-      std::map<Str, int> guide_of; std::vector<Str> queries; std::vector<GuideDef> defs;
-      std::vector<calitas_region_task> rt; std::vector<int64_t> task_of;
-      for (int64_t i = b0; i < b1; ++i) {
-        const calitas_a2r_task& t = tasks[i];
+    const int64_t MAX_DISTINCT = 16000;
+    for (int64_t s0 = 0; s0 < n_tasks;) {
+      std::map<Str, int> guide_of; std::vector<Str> queries; std::vector<GuideDef> defs; std::vector<calitas_region_task> rt;
+      int64_t s1 = s0;
+      for (; s1 < n_tasks; ++s1) {
+        const calitas_a2r_task& t = tasks[s1];
         if (!t.query || !t.chrom) bad("task query/chrom is NULL");
         auto it = guide_of.find(t.query);
-        if (it == guide_of.end()) { it = guide_of.emplace(t.query, (int)queries.size()).first; queries.push_back(t.query); defs.push_back(parse_guide(t.query, {})); }   // :112
+        if (it == guide_of.end()) {
+          if ((int64_t)queries.size() >= MAX_DISTINCT && (s1 - s0) % 10000 == 0) break;                  // cut only on a batch boundary
+          it = guide_of.emplace(t.query, (int)queries.size()).first; queries.push_back(t.query); defs.push_back(parse_guide(t.query, {}));   // :112
+        }
         const GuideDef& gd = defs[(size_t)it->second];
         const int ci = contig_index(*genome, t.chrom);
         if (ci < 0) bad(Str("requirement failed: Unknown chromosome: ") + t.chrom);
         const int padding = opt->window_size >= 0 ? opt->window_size / 2 : gd.length() * 2;
         const int64_t rs = std::max<int64_t>((int64_t)t.position - padding, 1), re = std::min<int64_t>((int64_t)t.position + padding, genome->lengths[ci]);
-        rt.push_back(calitas_region_task{ it->second, ci, rs - 1, (int32_t)std::max<int64_t>(0, re - rs + 1) }); task_of.push_back(i);
+        rt.push_back(calitas_region_task{ it->second, ci, rs - 1, (int32_t)std::max<int64_t>(0, re - rs + 1) });
       }
       std::vector<calitas_guide> cg; for (auto& q : queries) cg.push_back(calitas_guide{ q.c_str(), nullptr, 0 });
       HitSet hs; ck(calitas_align_regions(e, ref, (int32_t)cg.size(), cg.data(), (int64_t)rt.size(), rt.data(), &lim, best ? 1 : 0, &hs.h));
-      // hits arrive grouped by task in retval order; apply `.sorted` (+ `.head` in best mode) per task, then ReferenceHit.sort per batch (:141)
-      std::vector<Row> rows;
-      for (int64_t i = 0; i < hs.n();) {
-        int64_t j = i; while (j < hs.n() && hs.data()[j].task_idx == hs.data()[i].task_idx) ++j;
-        std::vector<calitas_hit> alns(hs.data() + i, hs.data() + j); sort_alignments(alns);
-        if (best) alns.resize(1);
-        const int64_t ti = task_of[(size_t)hs.data()[i].task_idx]; const GuideDef& gd = defs[(size_t)rt[(size_t)hs.data()[i].task_idx].guide_idx];
-        RowContext c2 = cx; c2.guide_id = tasks[ti].id ? tasks[ti].id : tasks[ti].query;                // :100
-        for (auto& h : alns) {
-          Rendered r = render_hit(h, gd, contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), false);   // region is not upper-cased (SequentialGuideAligner.scala:374)
-          rows.push_back(make_row(c2, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none));
-        }
-        i = j;
+      // hits arrive grouped by task in retval order: per task apply `.sorted` (+ `.head` in best mode), render on all host threads
+      const int64_t nt = s1 - s0;
+      std::vector<int64_t> first((size_t)nt + 1, 0);
+      { int64_t i = 0; for (int64_t t = 0; t < nt; ++t) { first[(size_t)t] = i; while (i < hs.n() && hs.data()[i].task_idx == t) ++i; } first[(size_t)nt] = i; if (i != hs.n()) throw ToolError{ CALITAS_ESTATE, "hit set is not task-major" }; }
+      if (best) for (int64_t t = 0; t < nt; ++t) if (first[(size_t)t] == first[(size_t)t + 1])          // alignToRefBest(...).head on an empty result throws in the reference
+        throw ToolError{ CALITAS_ESTATE, Str("head of empty list: no alignment for query ") + tasks[s0 + t].query };
+      std::vector<std::vector<Row>> task_rows((size_t)nt);
+      parallel_for(nt, 256, [&](int64_t tb, int64_t te) {
+        for (int64_t t = tb; t < te; ++t) {
+          std::vector<calitas_hit> alns(hs.data() + first[(size_t)t], hs.data() + first[(size_t)t + 1]); sort_alignments(alns);
+          if (best) alns.resize(1);
+          const GuideDef& gd = defs[(size_t)rt[(size_t)t].guide_idx];
+          RowContext c2 = cx; c2.guide_id = tasks[s0 + t].id ? tasks[s0 + t].id : tasks[s0 + t].query;    // :100
+          for (auto& h : alns) {
+            Rendered r = render_hit(h, gd, contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), false);   // region is not upper-cased (SequentialGuideAligner.scala:374)
+            task_rows[(size_t)t].push_back(make_row(c2, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none));
+          }
+        } });
+      for (int64_t b0 = 0; b0 < nt; b0 += 10000) {                                                     // ReferenceHit.sort per batch of 10 000 input rows (:110,141)
+        std::vector<Row> rows;
+        for (int64_t t = b0; t < std::min<int64_t>(nt, b0 + 10000); ++t) for (auto& r : task_rows[(size_t)t]) rows.push_back(std::move(r));
+        sort_rows(rows);
+        for (auto& r : rows) text += r.line;
+        total += (int64_t)rows.size();
       }
-      if (best) {   // alignToRefBest(...).head on an empty result throws in the reference
-        std::vector<char> seen(rt.size(), 0); for (int64_t i = 0; i < hs.n(); ++i) seen[(size_t)hs.data()[i].task_idx] = 1;
-        for (size_t k = 0; k < seen.size(); ++k) if (!seen[k]) throw ToolError{ CALITAS_ESTATE, Str("head of empty list: no alignment for query ") + tasks[task_of[k]].query };
-      }
-      sort_rows(rows);
-      for (auto& r : rows) text += r.line;
-      total += (int64_t)rows.size();
+      s0 = s1;
     }
     if (n_hits) *n_hits = total;
     *out_tsv = dup_text(text);

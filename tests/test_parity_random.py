@@ -178,3 +178,16 @@ def test_search_reference_batch_over_shards(eng, small_genome, n_shards):
             exp += lines if not exp else lines[1:]
         got = _lines(eng.t.search_reference_batch(contigs, guides, ids, n_shards=n_shards, vcf_text=vcf))
         assert got == exp, (n_shards, vcf is not None)
+
+
+def test_align_to_reference_batches_of_10000_are_sorted_separately(eng, small_genome):
+    """AlignToReference.scala:110,141: output is ReferenceHit.sort-ed per batch of 10 000 input rows, not globally."""
+    g, contigs = small_genome
+    guides = [synth.BASELINE_GUIDE] + synth.random_guides(2)
+    tasks = synth.a2r_tasks(g, guides, 21000, near_fraction=0.9)
+    kw = dict(window_size=60, d=5, p=1, O=10)
+    exp = _lines(pyoracle.align_to_reference(contigs, tasks, raw=True, threads=8, **kw))
+    got = _lines(eng.align_to_reference(contigs, tasks, raw=True, **kw))
+    assert len(exp) > 3000 and got == exp
+    starts = [int(l.split("\t")[4]) for l in exp[1:]]
+    assert starts != sorted(starts)                       # three separately sorted batches
