@@ -263,6 +263,12 @@ def main():
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([dev_ms, scan_ms, float(stats[-1]["candidates"])], dtype=torch.float64, device="cuda")
+        allr = torch.zeros(world * 3, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = allr.view(world, 3).tolist()
     dev_ms_max, wall_ms_max, scan_ms_max = [float(x) for x in red.tolist()]
     total_hits, total_bp, total_cand = [float(x) for x in tot.tolist()]
 
@@ -312,6 +318,8 @@ def main():
             "counts": {"hits": total_hits, "candidates": total_cand, "windows_rank0": st["windows"], "genome_bp": genome.total(), "shard_bp_sum": total_bp},
             "setup_s": {"generate": t_gen, "load_and_pack": t_load},
         }
+        if per_rank is not None:
+            out["per_rank"] = {"ms_per_step": [round(r[0], 3) for r in per_rank], "scan_ms": [round(r[1], 3) for r in per_rank], "candidates": [int(r[2]) for r in per_rank]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_sample(genome, guides, os.cpu_count() or 1, args.cpu_seconds, dict(d=args.max_guide_diffs, p=args.max_pam_mismatches, g=args.max_gaps))
         print(json.dumps(out))
