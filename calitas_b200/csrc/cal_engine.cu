@@ -73,7 +73,7 @@ CAL_KERNEL __launch_bounds__(256) k_pack(const uint8_t* __restrict__ raw, uint32
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct ScanArgs {
   const uint32_t* nib; const ContigDev* contigs; const Tile* tiles; const GuideSpec* specs;
-  int32_t g_begin, g_end, window_size, step, min_len;
+  int32_t g_begin, g_end, window_size, step, min_len, scan_slots;
   uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap;
 };
 
@@ -89,82 +89,69 @@ struct Emitter {
 struct ScanGuide { const uint32_t* peq; int32_t lp, k_edits; uint64_t key_base; };
 #ifdef CAL_HOSTSIM
 inline int __vimin3_s32(int a, int b, int c) { int m = a < b ? a : b; return m < c ? m : c; }
-inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t n) { n &= 31; return n ? (hi << n) | (lo >> (32 - n)) : hi; }
 #endif
 
-// Scans relative nibble range [rs, re) of the shared-memory tile for NG guides at once (independent Myers chains that share the
-// base-code extraction and give the scheduler instruction-level parallelism).  DIR 0: left to right; DIR 1: right to left, the
-// tables then hold the complemented masks.  Column p = 1.. in scan order.  Whole 8-base words run branch-free: the running
-// minimum of the distance decides, once per word, whether the (rare) per-column emission replay is needed.
+// Scans window [tb + rs, tb + re) of the shared-memory byte tile for NG guides at once (independent Myers chains that share the base fetch
+// and give the scheduler instruction-level parallelism).  The tile holds one byte per base, already scaled to the byte offset of that base's
+// entry in a 16-word mask table (code * 4): a column costs one LDS.U8 and one add (FMA pipe) before the table lookups, nothing on the ALU pipe
+// the kernel is bound by (the packed-nibble form needed a shift and a funnel shift per column and ran 7 % slower).  DIR 0: left to right;
+// DIR 1: right to left, the tables then hold the complemented masks.  Column p = 1.. in scan order.  Blocks of 8 columns run branch-free:
+// the running minimum of the distance decides, once per block, whether the (rare) per-column emission replay is needed.  Tables of a
+// thread's guides are adjacent (32 words apart).
 template <int DIR, int NG>
-CAL_D void scan_window(const uint32_t* words, int32_t rs, int32_t re, const ScanGuide* sg, const uint32_t* peq_base, uint32_t tbl,
-                       uint64_t* cand, unsigned long long* count, unsigned long long cap) {
-  // peq_base[(tbl + 2 j) * 16 + code] is the match mask of guide j for this direction (== sg[j].peq[code]); guides of a thread are adjacent.
+CAL_D void scan_window(const uint8_t* tb, int32_t rs, int32_t re, int32_t c_lo, int32_t c_hi, const ScanGuide* sg, uint64_t* cand, unsigned long long* count, unsigned long long cap) {
+  // Columns [c_lo, c_hi) (0-based, scan order) of the window are this thread's; when c_lo > 0 the chains are warmed up over the lp + k_edits
+  // columns before c_lo from the fresh state: an alignment with <= k_edits edits that ends at or after c_lo starts inside that stretch, and a
+  // later start can only raise distances, so "distance <= k_edits" comes out exactly as in a scan from the window's first column.
+  const uint8_t* t0 = reinterpret_cast<const uint8_t*>(sg[0].peq);
   MyersState st[NG];
 #pragma unroll
   for (int j = 0; j < NG; ++j) myers_init(st[j], sg[j].lp);
-  // single column with emission test (partial words at both ends, and replays)
-#define CAL_STEP1(J, STATE, CODE, COL) { myers_step(STATE, sg[J].peq[CODE]); if (STATE.score <= sg[J].k_edits) { Emitter em{ cand, count, cap, sg[J].key_base }; em(COL); } }
-  if (DIR == 0) {
-    int32_t r = rs;
-    for (; r < re && (r & 7); ++r) { const uint32_t c = nibble_at(words, r);
+  const int32_t n = c_hi;
+  const uint8_t* p = DIR == 0 ? tb + rs : tb + (re - 1);
+#define CAL_EQ(J, B) (*reinterpret_cast<const uint32_t*>(t0 + 128 * (J) + (B)))
+#define CAL_STEP1(J, STATE, B, COL) { myers_step(STATE, CAL_EQ(J, B)); if (STATE.score <= sg[J].k_edits) { Emitter em{ cand, count, cap, sg[J].key_base }; em(COL); } }
+  int32_t c = c_lo;
+  if (c_lo > 0) {
+    int32_t warm = 0;
 #pragma unroll
-      for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, r - rs + 1) }
-    for (; r + 8 <= re; r += 8) {
-      const uint32_t w = words[r >> 3];
-      MyersState save[NG]; int32_t mn[NG], prev[NG];
+    for (int j = 0; j < NG; ++j) { const int32_t w = sg[j].lp + sg[j].k_edits; warm = w > warm ? w : warm; }
+    for (int32_t w = c_lo - warm > 0 ? c_lo - warm : 0; w < c_lo; ++w) { const uint32_t b = DIR == 0 ? p[w] : p[-w];
 #pragma unroll
-      for (int j = 0; j < NG; ++j) { save[j] = st[j]; mn[j] = 0x7FFFFFFF; prev[j] = 0x7FFFFFFF; }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t idx = __funnelshift_l(w << (28 - 4 * k), tbl, 4);        // tbl * 16 + code: one ALU instruction, the shift is an IMAD.SHL
-#pragma unroll
-        for (int j = 0; j < NG; ++j) {
-          myers_step(st[j], peq_base[idx + 32 * j]);
-          if (k & 1) mn[j] = __vimin3_s32(mn[j], prev[j], st[j].score); else prev[j] = st[j].score;      // one 3-input min per two columns
-        } }
-#pragma unroll
-      for (int j = 0; j < NG; ++j) if (mn[j] <= sg[j].k_edits) { MyersState t = save[j]; for (int k = 0; k < 8; ++k) CAL_STEP1(j, t, (w >> (4 * k)) & 15u, r + k - rs + 1) }
-    }
-    for (; r < re; ++r) { const uint32_t c = nibble_at(words, r);
-#pragma unroll
-      for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, r - rs + 1) }
-  } else {
-    int32_t r = re - 1;
-    for (; r >= rs && (r & 7) != 7; --r) { const uint32_t c = nibble_at(words, r);
-#pragma unroll
-      for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, re - r) }
-    for (; r - 7 >= rs; r -= 8) {
-      const uint32_t w = words[r >> 3];
-      MyersState save[NG]; int32_t mn[NG], prev[NG];
-#pragma unroll
-      for (int j = 0; j < NG; ++j) { save[j] = st[j]; mn[j] = 0x7FFFFFFF; prev[j] = 0x7FFFFFFF; }
-#pragma unroll
-      for (int k = 7; k >= 0; --k) {
-        const uint32_t idx = __funnelshift_l(w << (28 - 4 * k), tbl, 4);
-#pragma unroll
-        for (int j = 0; j < NG; ++j) {
-          myers_step(st[j], peq_base[idx + 32 * j]);
-          if (k & 1) prev[j] = st[j].score; else mn[j] = __vimin3_s32(mn[j], prev[j], st[j].score);
-        } }
-#pragma unroll
-      for (int j = 0; j < NG; ++j) if (mn[j] <= sg[j].k_edits) { MyersState t = save[j]; for (int k = 7; k >= 0; --k) CAL_STEP1(j, t, (w >> (4 * k)) & 15u, re - (r - 7 + k)) }
-    }
-    for (; r >= rs; --r) { const uint32_t c = nibble_at(words, r);
-#pragma unroll
-      for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], c, re - r) }
+      for (int j = 0; j < NG; ++j) myers_step(st[j], CAL_EQ(j, b)); }
   }
+  for (; c + 8 <= n; c += 8) {
+    const uint8_t* q = DIR == 0 ? p + c : p - c;
+    MyersState save[NG]; int32_t mn[NG], prev[NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) { save[j] = st[j]; mn[j] = 0x7FFFFFFF; prev[j] = 0x7FFFFFFF; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t b = DIR == 0 ? q[k] : q[-k];
+#pragma unroll
+      for (int j = 0; j < NG; ++j) {
+        myers_step(st[j], CAL_EQ(j, b));
+        if (k & 1) mn[j] = __vimin3_s32(mn[j], prev[j], st[j].score); else prev[j] = st[j].score;      // one 3-input min per two columns
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NG; ++j) if (mn[j] <= sg[j].k_edits) { MyersState t = save[j]; for (int k = 0; k < 8; ++k) { const uint32_t b = DIR == 0 ? q[k] : q[-k]; CAL_STEP1(j, t, b, c + k + 1) } }
+  }
+  for (; c < n; ++c) { const uint32_t b = DIR == 0 ? p[c] : p[-c];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], b, c + 1) }
 #undef CAL_STEP1
+#undef CAL_EQ
 }
 
-// Block = TILE_WINDOWS windows x 2 directions x `slots` guide slots (blockDim.x = 128 * slots); a thread owns one window, one
-// direction and every slots-th pair of guides of the chunk.
+// Block = TILE_WINDOWS windows x 2 directions x 4 (guide slot, window part) pairs = 512 threads; a thread owns one window part, one
+// direction and every scan_slots-th pair of guides of the chunk.
 CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
   CAL_SHARED_DYN(uint32_t, smem);
   const int ng = a.g_end - a.g_begin;
   uint32_t* s_peq = smem;                       // ng * 32 words
   int32_t* s_meta = (int32_t*)(smem + ng * 32); // ng * 4: lp, k_edits, five_prime, pad
-  uint32_t* s_tile = smem + ng * 36;
+  uint32_t* s_tile = smem + ng * 36 + ((((TILE_WINDOWS - 1) * a.step + a.window_size + 16 + 15) & ~15) >> 2);      // packed words are staged behind the byte tile (which is word-aligned with them: + 2 words)
   const Tile tile = a.tiles[blockIdx.x];
   const ContigDev ctg = a.contigs[tile.contig];
   const int64_t tile_start = tile.first_k * (int64_t)a.step;
@@ -211,17 +198,37 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
   }
   __syncthreads();
 #endif
+  // expand the packed words into the byte tile: byte = code * 4.  The byte tile is laid out word-aligned with the packed words (byte 8 i + q
+  // holds nibble q of word i), so a word becomes two aligned 32-bit stores; the tile's first base sits r_off0 bytes in.
+  const int32_t r_off0 = (int32_t)(nib0 & 7);
+  uint8_t* s_bytes = reinterpret_cast<uint8_t*>(smem + ng * 36) + 0;
   CAL_PHASE(1) {
-    const int kk = threadIdx.x % TILE_WINDOWS, dir = (threadIdx.x / TILE_WINDOWS) & 1, slot = threadIdx.x / SCAN_THREADS, n_slots = blockDim.x / SCAN_THREADS;
+    uint32_t* out = smem + ng * 36;
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) {
+      const uint32_t w = s_tile[i];
+      const uint32_t lo = (w & 0x0F0F0F0Fu) << 2, hi = ((w >> 4) & 0x0F0F0F0Fu) << 2;      // even / odd nibbles, one per byte, already scaled by 4
+#ifndef CAL_HOSTSIM
+      out[2 * i] = __byte_perm(lo, hi, 0x5140); out[2 * i + 1] = __byte_perm(lo, hi, 0x7362);
+#else
+      out[2 * i] = (lo & 0xFFu) | ((hi & 0xFFu) << 8) | ((lo & 0xFF00u) << 8) | ((hi & 0xFF00u) << 16);
+      out[2 * i + 1] = ((lo >> 16) & 0xFFu) | (((hi >> 16) & 0xFFu) << 8) | (((lo >> 24) & 0xFFu) << 16) | (((hi >> 24) & 0xFFu) << 24);
+#endif
+    }
+  }
+  __syncthreads();
+  CAL_PHASE(2) {
+    // thread = (window, direction, guide slot, window part): with few guides the block keeps its 512 threads by cutting each window into parts
+    const int n_slots = a.scan_slots, n_parts = (int)(blockDim.x / SCAN_THREADS) / n_slots;
+    const int kk = threadIdx.x % TILE_WINDOWS, dir = (threadIdx.x / TILE_WINDOWS) & 1, sp = threadIdx.x / SCAN_THREADS, slot = sp % n_slots, part = sp / n_slots;
     if (kk >= tile.nwin) return;
     const int64_t ws = (tile.first_k + kk) * (int64_t)a.step;
     int64_t we = ws + a.window_size; if (we > ctg.len) we = ctg.len;
-    const int32_t r_off = (int32_t)(nib0 & 7);
-    int32_t rs = r_off + (int32_t)(ws - tile_start), re = r_off + (int32_t)(we - tile_start);
-    while (rs < re && nibble_at(s_tile, rs) == CODE_N) ++rs;         // SearchReference.scala:58-59
-    while (rs < re && nibble_at(s_tile, re - 1) == CODE_N) --re;
+    int32_t rs = r_off0 + (int32_t)(ws - tile_start), re = r_off0 + (int32_t)(we - tile_start);
+    while (rs < re && s_bytes[rs] == (CODE_N << 2)) ++rs;            // SearchReference.scala:58-59
+    while (rs < re && s_bytes[re - 1] == (CODE_N << 2)) --re;
     const int32_t m = re - rs;
     if (m <= 0 || m < a.min_len) return;                              // SearchReference.scala:536
+    const int32_t c_lo = (int32_t)((int64_t)m * part / n_parts), c_hi = (int32_t)((int64_t)m * (part + 1) / n_parts);
     const uint32_t wid = (uint32_t)(ctg.win_base + tile.first_k + kk);
     for (int g = SCAN_NG * slot; g < ng; g += SCAN_NG * n_slots) {
       ScanGuide sg[SCAN_NG];
@@ -230,10 +237,9 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
         sg[j].peq = s_peq + (g + j) * 32 + dir * 16; sg[j].lp = s_meta[4 * (g + j)]; sg[j].k_edits = s_meta[4 * (g + j) + 1];
         sg[j].key_base = make_key((uint32_t)(a.g_begin + g + j), wid, (uint32_t)(dir ^ s_meta[4 * (g + j) + 2]), 0);
       }
-      const uint32_t tbl = (uint32_t)(2 * g + dir);
-#define CAL_SCAN_CALL(N) { if (dir == 0) scan_window<0, N>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); else scan_window<1, N>(s_tile, rs, re, sg, s_peq, tbl, a.cand, a.cand_count, a.cand_cap); }
+#define CAL_SCAN_CALL(N) { if (dir == 0) scan_window<0, N>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); else scan_window<1, N>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); }
       if (cnt == SCAN_NG) CAL_SCAN_CALL(SCAN_NG)
-      else if (cnt >= 2) { CAL_SCAN_CALL(2) if (cnt == 3) { sg[0] = sg[2]; const uint32_t tbl3 = tbl + 4; if (dir == 0) scan_window<0, 1>(s_tile, rs, re, sg, s_peq, tbl3, a.cand, a.cand_count, a.cand_cap); else scan_window<1, 1>(s_tile, rs, re, sg, s_peq, tbl3, a.cand, a.cand_count, a.cand_cap); } }
+      else if (cnt >= 2) { CAL_SCAN_CALL(2) if (cnt == 3) { sg[0] = sg[2]; CAL_SCAN_CALL(1) } }
       else CAL_SCAN_CALL(1)
 #undef CAL_SCAN_CALL
     }
@@ -1017,8 +1023,9 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       const int ng = g1 - g0;
       const int64_t tile_bases = (int64_t)(TILE_WINDOWS - 1) * ch.step + window_size;
       ch.smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2 + 8) * 4;          // + lead-in and rounding of the 16-byte-granular bulk copy
+      ch.smem += (size_t)((tile_bases + 16 + 15) & ~15ll);                                // one byte per base in front of the packed words
       if (ch.smem > 200 * 1024) throw LimitExceeded("window size too large for the shared-memory tile");
-      ch.scan_slots = std::min(4, std::max(1, (ng + SCAN_NG - 1) / SCAN_NG));     // guide slots per window: more resident warps when the chunk has enough guides
+      { const int want = (ng + SCAN_NG - 1) / SCAN_NG; ch.scan_slots = want >= 3 ? 4 : (want == 2 ? 2 : 1); }     // guide slots per window (1, 2 or 4); the rest of the block's 4 slots split the window into parts
       ch.bases = 0; for (size_t t = ch.t_begin; t < t_end; ++t) ch.bases += (int64_t)(ch.ts->tiles[t].nwin - 1) * ch.step + window_size;
       chunks.push_back(ch);
       g0 = g1;
@@ -1047,9 +1054,9 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
 #ifndef CAL_HOSTSIM
         dev::check(cudaFuncSetAttribute(k_scan_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem), "cudaFuncSetAttribute");
 #endif
-        ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len,
+        ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len, ch.scan_slots,
                      cand_slot[slot]->as<uint64_t>(), e->d_count + slot, (unsigned long long)e->cand_cap_hint };
-        CAL_LAUNCH(k_scan_tiled, (unsigned)ch.n_tiles, SCAN_THREADS * ch.scan_slots, ch.smem, ss, 2, sa); dev::launch_check("k_scan_tiled"); ++e->launches;
+        CAL_LAUNCH(k_scan_tiled, (unsigned)ch.n_tiles, SCAN_THREADS * 4, ch.smem, ss, 3, sa);        // always 512 threads: 4 / scan_slots window parts per guide slot dev::launch_check("k_scan_tiled"); ++e->launches;
         counts[6] += 1; counts[7] += ch.bases;
       }
       dev::event_record(ce.ev[CE_SCAN_E], ss);

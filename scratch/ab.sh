@@ -1,11 +1,9 @@
 cd $GRAFT_REPO_ROOT
-for cfg in "16 0" "16 4" "8 0" "8 4" "12 4"; do
-  set -- $cfg
-  for sc in 0.125 1.0; do
-  CALITAS_CHUNK=$1 CALITAS_FIRST_CHUNK=$2 timeout 300 python bench.py --guides 100 --scale $sc --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ab.json 2> gpurun_out/ab.err
+for v in base bytes; do
+  lib=""; [ $v != base ] && lib="--lib scratch/lib_$v.so"
+  timeout 300 python bench.py --guides 16 --scale 0.5 --steps 3 --warmup 2 --no-cpu-baseline $lib > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err; tail -2 gpurun_out/ab_$v.err
   python - <<PY
 import json
-d=json.load(open("gpurun_out/ab.json")); print("chunk $1 first $2 scale $sc:", round(d["value"],1), round(d["ms_per_step"],2), {k: round(v,1) for k,v in d["breakdown_ms"].items()}, d["counts"]["hits"])
+d=json.load(open("gpurun_out/ab_$v.json")); print("$v", round(d["value"],1), d["breakdown_ms"], d["counts"]["hits"], d["counts"]["candidates"])
 PY
-  done
 done

@@ -1,10 +1,9 @@
 cd $GRAFT_REPO_ROOT
-timeout 120 python -m pytest tests/test_parity_random.py -m gpu -x -q -k "search_reference_defaults" 2>&1 | tail -3
-timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for g in 100 16; do
+timeout 500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for g in 100 16 4 2 1; do
 timeout 300 python bench.py --guides $g --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/p_$g.json 2> gpurun_out/p_$g.err; tail -3 gpurun_out/p_$g.err
 python - <<PY
 import json
-d=json.load(open("gpurun_out/p_$g.json")); print($g, round(d["value"],1), round(d["e2e"]["value"],1), d["ms_per_step"], d["breakdown_ms"], d["counts"]["hits"])
+d=json.load(open("gpurun_out/p_$g.json")); print($g, round(d["value"],1), round(d["e2e"]["value"],1), round(d["ms_per_step"],2), {k: round(v,2) for k,v in d["breakdown_ms"].items()}, d["counts"]["hits"])
 PY
 done
