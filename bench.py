@@ -22,11 +22,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# SASS instruction mix of one Myers column update of one guide in k_scan_tiled's branch-free inner loop (counted from cuobjdump -sass,
-# see DESIGN.md "k_scan_tiled"): ALU pipe 7 LOP3 + 2 LEA.HI + 0.5 SHF + 0.5 VIMNMX3; FMA pipe 3 IMAD.IADD + 0.5 IMAD.SHL + 0.5 IMAD; 1 LDS.
-ALU_OPS_PER_COLUMN = 10
-ISSUE_SLOTS_PER_COLUMN = 15
-NCU_DRAM_OVER_ALGORITHMIC = 404.0 / 386.0   # k_scan_tiled, profiles/r01b_summary.txt
+# SASS instruction mix of one Myers column update of one guide in k_scan_tiled's branch-free inner loop (counted from cuobjdump -sass of the
+# shipped library, see DESIGN.md "k_scan_tiled"; per 8 columns x 2 guides: 112 LOP3 + 32 LEA.HI + 8 VIMNMX3 | 56 IMAD.IADD | 16 LDS + 8 LDS.U8):
+# ALU pipe 7 LOP3 + 2 LEA.HI + 0.5 VIMNMX3; FMA pipe 3.5 IMAD.IADD; LSU 1 LDS + 0.5 LDS.U8.
+ALU_OPS_PER_COLUMN = 9.5
+ISSUE_SLOTS_PER_COLUMN = 14.5
+NCU_DRAM_OVER_ALGORITHMIC = 404.0 / 386.0   # k_scan_tiled, profiles/r01d_summary.txt
 REF_OPS_PER_BP_GUIDE = 240   # 2 strands x 20 rows x 6 int32 ops of the reference's recurrence
 
 
@@ -306,7 +307,7 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "k_scan_tiled", "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                          "traffic": alg_bytes * NCU_DRAM_OVER_ALGORITHMIC, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                         "(profiles/r01b_summary.txt: 404.0 MB for 386.0 MB algorithmic), scaled to this launch's algorithmic bytes", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                         "(profiles/r01d_summary.txt: 387.1 + 16.9 = 404.0 MB for 386.0 MB algorithmic), scaled to this launch's algorithmic bytes", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "streaming read of the 4-bit packed shard once per launch; the kernel is integer-ALU-bound (see roofline_int), so the HBM fraction is small by design",
                          "avg_launch_ms": scan_launch_ms, "launches_per_step": launches, "share_of_step": st["ms_scan"] / st["ms_total"]},
             "roofline_int": {"kernel": "k_scan_tiled", "bound": "int_alu_pipe", "achieved": int_achieved, "peak": int_peaks["alu_lop3"], "unit": "Tiop/s (ALU-pipe thread instructions)",
