@@ -165,6 +165,25 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "Gbp*guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """One process per GPU: keep the rank's host threads (and therefore its pinned buffers and its launch/read-back round trips) on the CPUs
+    that are local to its GPU.  Returns the CPU list used, or None when the driver's affinity mask does not intersect the allowed CPUs."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        allowed = sorted(os.sched_getaffinity(0))
+        n = max(allowed) + 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        local = [c for c in allowed if (mask[c // 64] >> (c % 64)) & 1]
+        if local and len(local) < len(allowed):
+            os.sched_setaffinity(0, local)
+            return local
+    except Exception:
+        pass
+    return None
+
+
 def workload_config(args, genome):
     pams = ",".join([args.pam or "(none)"] + [a for a in args.aux_pams.split(",") if a])
     return {"workload": "SearchReference, %d guides (CTTGCCCCACAGGGCAGTAA + random 20-mers, PAMs %s) vs %.2f Gbp synthetic hg38-sized genome (24 contigs), "
@@ -184,6 +203,8 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # the version banner would land on stdout next to the one JSON line
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -193,6 +214,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         # NCCL prints its version banner on stdout when the first communicator comes up; the contract is ONE JSON line on stdout,
         # so stdout is pointed at stderr while the process group initialises.
@@ -205,6 +227,11 @@ def main():
             torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
+            try:
+                import ctypes
+                ctypes.CDLL(None).fflush(None)        # NCCL printf()s into the C stdio buffer: drain it while fd 1 still points at stderr
+            except Exception:
+                pass
             os.dup2(saved, 1)
             os.close(saved)
     guides = guide_list(args)
@@ -322,6 +349,7 @@ def main():
             "counts": {"hits": total_hits, "candidates": total_cand, "windows_rank0": st["windows"], "genome_bp": genome.total(), "shard_bp_sum": total_bp},
             "setup_s": {"generate": t_gen, "load_and_pack": t_load},
         }
+        out["config"]["cpu_binding_rank0"] = ("cpus %d-%d (GPU-local NUMA node)" % (numa[0], numa[-1])) if numa else "none"
         if per_rank is not None:
             out["per_rank"] = {"ms_per_step": [round(r[0], 3) for r in per_rank], "scan_ms": [round(r[1], 3) for r in per_rank], "candidates": [int(r[2]) for r in per_rank]}
         if world == 1 and not args.no_cpu_baseline:
