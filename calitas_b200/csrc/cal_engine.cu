@@ -1004,7 +1004,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     int chrom_idx = -1;
     if (chrom && chrom[0]) { for (size_t c = 0; c < ref->names.size(); ++c) if (ref->names[c] == chrom) chrom_idx = (int)c; if (chrom_idx < 0) throw InvalidArgument(std::string("Unknown chromosome: ") + chrom); }
     // ---- plan: guide chunks and their window tilings ---------------------------------------------------------------------------
-    const int G_CHUNK = 16;
+    const int G_CHUNK = 16;      // measured on B200: chunks of 25-50 guides shorten the contended tails at 1/8 genome scale but expose a longer last tail (-2 to -5 % at full scale)
     std::vector<SearchChunk> chunks;
     for (int g0 = 0; g0 < n_guides;) {
       SearchChunk ch; ch.g0 = g0; ch.raw_len = (int)defs[(size_t)g0].raw.size();
@@ -1127,6 +1127,16 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       ms[4] += dev::event_ms(ce.ev[CE_COPY_B], ce.ev[CE_COPY_E]);
     }
     ms[0] = dev::event_ms(e->ev[0], e->ev[1]);
+    if (std::getenv("CALITAS_TRACE")) {       // per-chunk timeline (ms since the start of the call) on stderr
+      for (size_t c = 0; c < n_chunks; ++c) {
+        const ChunkEvents& ce = e->chunk_ev[c];
+        std::fprintf(stderr, "[calitas trace] chunk %zu guides %d-%d: scan %.2f-%.2f  tail %.2f-%.2f (sorted %.2f, align %.2f-%.2f)  copy %.2f-%.2f\n", c, chunks[c].g0, chunks[c].g1,
+                     dev::event_ms(e->ev[0], ce.ev[CE_SCAN_B]), dev::event_ms(e->ev[0], ce.ev[CE_SCAN_E]), dev::event_ms(e->ev[0], ce.ev[CE_TAIL_B]), dev::event_ms(e->ev[0], ce.ev[CE_TAIL_E]),
+                     dev::event_ms(e->ev[0], ce.ev[CE_SORTED]), dev::event_ms(e->ev[0], ce.ev[CE_ALIGN_B]), dev::event_ms(e->ev[0], ce.ev[CE_ALIGN_E]),
+                     dev::event_ms(e->ev[0], ce.ev[CE_COPY_B]), dev::event_ms(e->ev[0], ce.ev[CE_COPY_E]));
+      }
+      std::fprintf(stderr, "[calitas trace] total %.2f ms\n", ms[0]);
+    }
     ms[5] = ms[0] - ms[1];                                   // time of the call not hidden behind the scan kernels
     counts[3] = e->launches;
     counts[5] = (int64_t)((size_t)n_out * sizeof(calitas_hit));
