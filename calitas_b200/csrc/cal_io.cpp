@@ -9,6 +9,7 @@
 #include <cstring>
 #include <ctime>
 #include <thread>
+#include <zlib.h>
 
 namespace cal { namespace io {
 
@@ -38,6 +39,30 @@ void write_file(const std::string& path, const char* data, size_t n) {
   if (std::fclose(f) != 0 || put != n) throw IoError{ "Short write to " + path };
 }
 
+std::string gunzip_if_needed(const std::string& raw) {
+  if (raw.size() < 2 || (unsigned char)raw[0] != 0x1f || (unsigned char)raw[1] != 0x8b) return raw;
+  std::string out; out.reserve(raw.size() * 4);
+  z_stream zs; std::memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, 16 + MAX_WBITS) != Z_OK) throw IoError{ "zlib: inflateInit2 failed" };
+  zs.next_in = (Bytef*)raw.data(); zs.avail_in = (uInt)std::min<size_t>(raw.size(), 1u << 30);
+  size_t consumed = 0; std::vector<char> buf(1 << 20);
+  for (;;) {
+    zs.next_out = (Bytef*)buf.data(); zs.avail_out = (uInt)buf.size();
+    const uInt in_before = zs.avail_in;
+    const int rc = inflate(&zs, Z_NO_FLUSH);
+    consumed += in_before - zs.avail_in;
+    out.append(buf.data(), buf.size() - zs.avail_out);
+    if (rc == Z_STREAM_END) {                                   // end of one member: BGZF and `cat a.gz b.gz` continue with the next
+      if (consumed >= raw.size()) break;
+      if (inflateReset(&zs) != Z_OK) { inflateEnd(&zs); throw IoError{ "zlib: inflateReset failed" }; }
+    } else if (rc != Z_OK && !(rc == Z_BUF_ERROR && zs.avail_out == 0)) { inflateEnd(&zs); throw IoError{ "corrupt gzip data" }; }
+    if (zs.avail_in == 0 && consumed < raw.size()) { zs.next_in = (Bytef*)raw.data() + consumed; zs.avail_in = (uInt)std::min<size_t>(raw.size() - consumed, 1u << 30); }
+    else if (zs.avail_in == 0 && rc != Z_STREAM_END && zs.avail_out != 0) { inflateEnd(&zs); throw IoError{ "truncated gzip data" }; }
+  }
+  inflateEnd(&zs);
+  return out;
+}
+
 static bool exists(const std::string& path) { FILE* f = std::fopen(path.c_str(), "rb"); if (!f) return false; std::fclose(f); return true; }
 
 static std::vector<std::string> split_tabs(const std::string& line) {
@@ -60,7 +85,7 @@ static void strip_newlines(const char* p, const char* end, std::string& out) {
 Genome load_fasta(const std::string& path) {
   Genome g;
   double t0 = now_s();
-  const std::string text = read_file(path);
+  const std::string text = gunzip_if_needed(read_file(path));
   g.read_s = now_s() - t0; t0 = now_s();
   struct Span { const char* b; const char* e; };
   std::vector<Span> spans;
@@ -127,7 +152,7 @@ Genome load_fasta(const std::string& path) {
 }
 
 std::vector<A2RRow> load_a2r_tasks(const std::string& path) {
-  const std::string text = read_file(path);
+  const std::string text = gunzip_if_needed(read_file(path));
   std::vector<A2RRow> rows; std::vector<std::string> hdr; size_t a = 0; int ci = -1, cq = -1, cc = -1, cp = -1;
   while (a < text.size()) {
     size_t b = text.find('\n', a); if (b == std::string::npos) b = text.size();

@@ -11,6 +11,8 @@ struct IoError { std::string msg; };
 
 std::string read_file(const std::string& path);                       // whole file; throws IoError
 void write_file(const std::string& path, const char* data, size_t n); // "-" or "" = stdout
+// gzip / bgzip (BGZF is a series of gzip members) -> text; anything else is returned unchanged.  fgbio's VcfSource reads .vcf and .vcf.gz alike.
+std::string gunzip_if_needed(const std::string& raw);
 
 // A reference genome as SearchReference / AlignToReference see it (htsjdk ReferenceSequenceFile + SAMSequenceDictionary):
 // contig name = header up to the first white space; bases exactly as in the file (case kept, line ends removed).

@@ -144,7 +144,10 @@ int search_reference(int argc, char** argv) {
   opt.max_variants = f.integer("max-variants", 16); opt.window_size = f.integer("window-size", 1000);
   opt.limits = calitas_limits{ f.integer("max-guide-diffs", 5), f.integer("max-pam-mismatches", 1), f.integer("max-gaps-between-guide-and-pam", 3), f.integer("max-total-diffs", -1), f.integer("max-overlap", 10) };
   const Str chrom = f.str("chrom"); opt.chrom = chrom.empty() ? nullptr : chrom.c_str();
-  Str vcf_text, vcf_id; if (f.has("variants")) { vcf_text = read_file(f.str("variants")); vcf_id = file_name_of(f.str("variants")) + ":" + md5_hex(vcf_text); opt.vcf_text = vcf_text.c_str(); opt.vcf_id = vcf_id.c_str(); }
+  Str vcf_text, vcf_id; if (f.has("variants")) {                                  // .vcf or .vcf.gz / bgzip; the id carries the MD5 of the file as stored (ReferenceHit.scala:175-183)
+    const Str raw = read_file(f.str("variants")); vcf_id = file_name_of(f.str("variants")) + ":" + md5_hex(raw); vcf_text = gunzip_if_needed(raw);
+    opt.vcf_text = vcf_text.c_str(); opt.vcf_id = vcf_id.c_str();
+  }
   const Str stamp = f.str("time-stamp", utc_time_stamp()), version = f.str("aligner-version", "calitas-b200-0.1");
   opt.time_stamp = stamp.c_str(); opt.aligner_version = version.c_str();
   Session S; open_session(S, f, false, 4 * opt.window_size);

@@ -85,6 +85,16 @@ def test_search_reference_cli_flags_and_vcf(calitas, ref_dir):
     exp = lines(pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, guide_id="g2", vcf_text=vcf, vcf_name=vid, assembly="SYN10M", raw=True, O=5, window_size=500, max_variants=3))
     got = lines(open(out).read())
     assert got == exp and any("+variants" in l and vid in l for l in got)
+    # the same VCF gzip-compressed (two members, as bgzip writes): parsed alike, the id carries the MD5 of the compressed file
+    import gzip
+    half = vcf.index("\n", len(vcf) // 2) + 1
+    gz = gzip.compress(vcf[:half].encode()) + gzip.compress(vcf[half:].encode())
+    open(d / "vars.vcf.gz", "wb").write(gz)
+    p = run(calitas, "SearchReference", "-i", synth.BASELINE_GUIDE, "-I", "g2", "-r", d / "ref.fa", "-v", d / "vars.vcf.gz", "-o", out, "-O", "5", "-w", "500", "-V", "3",
+            "--time-stamp", "", "--aligner-version", "oracle")
+    assert p.returncode == 0, p.stderr
+    vid_gz = "vars.vcf.gz:" + hashlib.md5(gz).hexdigest()
+    assert lines(open(out).read()) == [l.replace(vid, vid_gz) for l in exp]
     p = run(calitas, "SearchReference", "-i", "CTTGCCCCACAGGGCAGTAAngg", "-I", "g3", "-x", "nag", "nga", "-r", d / "ref.fa", "-o", out, "-d", "4", "-g", "2", "-p", "1", "-D", "5", "-c", "chr2",
             "-m", "-110", "-M=-250", "-b", "-125", "-B", "-119", "--time-stamp", "", "--aligner-version", "oracle")
     assert p.returncode == 0, p.stderr
