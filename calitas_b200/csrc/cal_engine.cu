@@ -33,7 +33,7 @@ struct Tile { int32_t contig; int32_t nwin; int64_t first_k; };
 struct ExplicitWindow { int64_t nib_start; int32_t len; int32_t target_offset; int32_t guide_idx; int32_t contig_idx; };
 
 const int ALIGN_KB = 6;          // k_align keeps a 2*6+1-diagonal DP band in registers when the candidate threshold allows
-const int TILE_WINDOWS = 64;
+const int TILE_WINDOWS = 64;      // windows per scan tile at the default window size; halved until the tile fits shared memory for larger -w
 const int HALO_WINDOWS = 2;      // windows processed beyond each interior shard cut so that removeOverlaps sees both sides of the cut
 const int SCAN_THREADS = 2 * TILE_WINDOWS;
 #ifndef CAL_SCAN_NG
@@ -73,7 +73,7 @@ CAL_KERNEL __launch_bounds__(256) k_pack(const uint8_t* __restrict__ raw, uint32
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct ScanArgs {
   const uint32_t* nib; const ContigDev* contigs; const Tile* tiles; const GuideSpec* specs;
-  int32_t g_begin, g_end, window_size, step, min_len, scan_slots;
+  int32_t g_begin, g_end, window_size, step, min_len, scan_slots, tile_windows;
   uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap;
 };
 
@@ -151,7 +151,7 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
   const int ng = a.g_end - a.g_begin;
   uint32_t* s_peq = smem;                       // ng * 32 words
   int32_t* s_meta = (int32_t*)(smem + ng * 32); // ng * 4: lp, k_edits, five_prime, pad
-  uint32_t* s_tile = smem + ng * 36 + ((((TILE_WINDOWS - 1) * a.step + a.window_size + 16 + 15) & ~15) >> 2);      // packed words are staged behind the byte tile (which is word-aligned with them: + 2 words)
+  uint32_t* s_tile = smem + ng * 36 + ((((a.tile_windows - 1) * a.step + a.window_size + 16 + 15) & ~15) >> 2);      // packed words are staged behind the byte tile (which is word-aligned with them: + 2 words)
   const Tile tile = a.tiles[blockIdx.x];
   const ContigDev ctg = a.contigs[tile.contig];
   const int64_t tile_start = tile.first_k * (int64_t)a.step;
@@ -218,8 +218,8 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
   __syncthreads();
   CAL_PHASE(2) {
     // thread = (window, direction, guide slot, window part): with few guides the block keeps its 512 threads by cutting each window into parts
-    const int n_slots = a.scan_slots, n_parts = (int)(blockDim.x / SCAN_THREADS) / n_slots;
-    const int kk = threadIdx.x % TILE_WINDOWS, dir = (threadIdx.x / TILE_WINDOWS) & 1, sp = threadIdx.x / SCAN_THREADS, slot = sp % n_slots, part = sp / n_slots;
+    const int tw = a.tile_windows, n_slots = a.scan_slots, n_parts = (int)(blockDim.x / (2 * tw)) / n_slots;
+    const int kk = threadIdx.x % tw, dir = (threadIdx.x / tw) & 1, sp = threadIdx.x / (2 * tw), slot = sp % n_slots, part = sp / n_slots;
     if (kk >= tile.nwin) return;
     const int64_t ws = (tile.first_k + kk) * (int64_t)a.step;
     int64_t we = ws + a.window_size; if (we > ctg.len) we = ctg.len;
@@ -605,7 +605,7 @@ struct calitas_reference {
   calitas_engine* owner = nullptr;
   std::vector<std::string> names; std::vector<int64_t> len, have_b, have_e, own_b, own_e, nib_off;
   uint32_t* d_nib = nullptr; uint8_t* d_raw = nullptr; int64_t total_padded = 0;
-  struct TileSet { std::vector<Tile> tiles; std::vector<ContigDev> contigs; Tile* d_tiles = nullptr; ContigDev* d_contigs = nullptr; int64_t n_windows = 0; };
+  struct TileSet { std::vector<Tile> tiles; std::vector<ContigDev> contigs; Tile* d_tiles = nullptr; ContigDev* d_contigs = nullptr; int64_t n_windows = 0; int tile_windows = TILE_WINDOWS; };
   std::map<std::pair<int, int>, TileSet> tilesets;   // (window_size, step)
 };
 
@@ -653,12 +653,21 @@ PinnedBuf take_pinned(calitas_engine* e, size_t bytes) {
   PinnedBuf b; b.cap = bytes + bytes / 4 + 4096; b.p = dev::alloc_host(b.cap); return b;
 }
 
+// Dynamic shared memory of one k_scan_tiled CTA: mask tables + meta, the byte tile (word-aligned with the packed words), the staged packed
+// words incl. the lead-in and rounding of the 16-byte-granular bulk copy.
+size_t scan_smem_bytes(int ng, int tile_windows, int window_size, int step) {
+  const int64_t tile_bases = (int64_t)(tile_windows - 1) * step + window_size;
+  return (size_t)ng * 36 * 4 + (size_t)((tile_bases + 16 + 15) & ~15ll) + (size_t)((tile_bases + 7) / 8 + 2 + 8) * 4;
+}
+
 // Builds (or returns the cached) tiling of the owned reference windows for (window_size, step): SearchReference.scala:52-53.
 calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r, int window_size, int step, const char* chrom) {
   auto key = std::make_pair(window_size, step);
   auto it = r->tilesets.find(key);
   if (it == r->tilesets.end()) {
     calitas_reference::TileSet ts;
+    // windows per tile: as many (<= 64, power of two) as keep the byte tile + staged packed words + 16 guides' tables within shared memory
+    while (ts.tile_windows > 1 && scan_smem_bytes(16, ts.tile_windows, window_size, step) > 200 * 1024) ts.tile_windows /= 2;
     int64_t win_base = 0;
     for (size_t c = 0; c < r->len.size(); ++c) {
       const int64_t len = r->len[c];
@@ -676,7 +685,7 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
         if (p_lo * step < r->have_b[c] || last_end > r->have_e[c])
           throw InvalidArgument("reference shard of contig " + r->names[c] + " does not hold the bases of its owned windows plus " + std::to_string(HALO_WINDOWS) + " halo windows per cut");
       }
-      for (int64_t k = p_lo; k < p_hi; k += TILE_WINDOWS) ts.tiles.push_back(Tile{ (int32_t)c, (int32_t)std::min<int64_t>(TILE_WINDOWS, p_hi - k), k });
+      for (int64_t k = p_lo; k < p_hi; k += ts.tile_windows) ts.tiles.push_back(Tile{ (int32_t)c, (int32_t)std::min<int64_t>(ts.tile_windows, p_hi - k), k });
       ts.n_windows += std::max<int64_t>(0, k_hi - k_lo);
       win_base += n_win;
     }
@@ -1021,9 +1030,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       ch.slots = 1; ch.banded = 1; for (int g = g0; g < g1; ++g) { ch.slots = std::max(ch.slots, specs[(size_t)g].slots); ch.banded = std::max(ch.banded, specs[(size_t)g].k_edits); }
       if (ch.banded > ALIGN_KB) ch.banded = 0;
       const int ng = g1 - g0;
-      const int64_t tile_bases = (int64_t)(TILE_WINDOWS - 1) * ch.step + window_size;
-      ch.smem = (size_t)ng * 36 * 4 + (size_t)((tile_bases + 7) / 8 + 2 + 8) * 4;          // + lead-in and rounding of the 16-byte-granular bulk copy
-      ch.smem += (size_t)((tile_bases + 16 + 15) & ~15ll);                                // one byte per base in front of the packed words
+      ch.smem = scan_smem_bytes(ng, ch.ts->tile_windows, window_size, ch.step);
       if (ch.smem > 200 * 1024) throw LimitExceeded("window size too large for the shared-memory tile");
       { const int want = (ng + SCAN_NG - 1) / SCAN_NG; ch.scan_slots = want >= 3 ? 4 : (want == 2 ? 2 : 1); }     // guide slots per window (1, 2 or 4); the rest of the block's 4 slots split the window into parts
       ch.bases = 0; for (size_t t = ch.t_begin; t < t_end; ++t) ch.bases += (int64_t)(ch.ts->tiles[t].nwin - 1) * ch.step + window_size;
@@ -1054,9 +1061,9 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
 #ifndef CAL_HOSTSIM
         dev::check(cudaFuncSetAttribute(k_scan_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem), "cudaFuncSetAttribute");
 #endif
-        ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len, ch.scan_slots,
+        ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len, ch.scan_slots, ch.ts->tile_windows,
                      cand_slot[slot]->as<uint64_t>(), e->d_count + slot, (unsigned long long)e->cand_cap_hint };
-        CAL_LAUNCH(k_scan_tiled, (unsigned)ch.n_tiles, SCAN_THREADS * 4, ch.smem, ss, 3, sa);        // always 512 threads: 4 / scan_slots window parts per guide slot dev::launch_check("k_scan_tiled"); ++e->launches;
+        CAL_LAUNCH(k_scan_tiled, (unsigned)ch.n_tiles, 2 * ch.ts->tile_windows * 4, ch.smem, ss, 3, sa);        // always 512 threads: 4 / scan_slots window parts per guide slot dev::launch_check("k_scan_tiled"); ++e->launches;
         counts[6] += 1; counts[7] += ch.bases;
       }
       dev::event_record(ce.ev[CE_SCAN_E], ss);

@@ -128,6 +128,10 @@ def test_search_reference_defaults(eng, small_genome):
     ("CTTGCCCCACAGGGCAGTAA", [], dict(d=6, g=2, p=1)),
     ("tttvCTTGCCCCACAGGGCAGTAA", [], dict(d=4, g=1, p=1, O=0)),
     ("CTTGCCCCACAGGGCAGTAAnrg", [], dict(d=3, g=3, p=2, D=4, window_size=300, O=100)),
+    ("CTTGCCCCACAGGGCAGTAAnrg", [], dict(window_size=3000)),            # 32 windows per scan tile
+    ("CTTGCCCCACAGGGCAGTAAnrg", [], dict(window_size=20000, d=4)),      # 4 windows per scan tile
+    ("CTTGCCCCACAGGGCAGTAAnrg", [], dict(window_size=120000)),          # one window per tile, close to the engine's window limit
+    ("CTTGCCCCACAGGGCAGTAAnrg", [], dict(window_size=40)),              # step 10: every base is scanned four times
 ])
 def test_search_reference_variants_of_the_call(eng, small_genome, guide, aux, kw):
     g, contigs = small_genome
