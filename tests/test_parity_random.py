@@ -97,7 +97,8 @@ def test_align_best_random_cases(eng):
 
 def test_non_default_costs(eng):
     rng = np.random.default_rng(9)
-    for costs in [(-100, -130, -110, -200), (-120, -121, -122, -260), (90, 95, 100, 300)]:
+    # the last two sets break  target_gap + query_gap <= mismatch  (band_align_h's condition): they must take the three-matrix kernels
+    for costs in [(-100, -130, -110, -200), (-120, -121, -122, -260), (90, 95, 100, 300), (-400, -100, -100, -260), (-250, -120, -120, -260)]:      # (-250,-120,-120): k_edits = 2 d, so d <= 3 stays on the banded three-matrix kernel
         for k in range(40):
             guide, aux, target, kw = random_case(rng)
             exp = pyoracle.align(guide, target, aux_pams=aux, costs=costs, **kw)
