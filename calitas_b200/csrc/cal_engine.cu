@@ -219,7 +219,12 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
   CAL_PHASE(2) {
     // thread = (window, direction, guide slot, window part): with few guides the block keeps its 512 threads by cutting each window into parts
     const int tw = a.tile_windows, n_slots = a.scan_slots, n_parts = (int)(blockDim.x / (2 * tw)) / n_slots;
-    const int kk = threadIdx.x % tw, dir = (threadIdx.x / tw) & 1, sp = threadIdx.x / (2 * tw), slot = sp % n_slots, part = sp / n_slots;
+    // A warp takes 32 windows of the same parity: consecutive windows are `step` bytes apart in the byte tile, and with the default step (970 =
+    // 2 x 485) windows 2m lie 1940 m bytes apart = 485 m words, 485 m mod 32 = 5 m mod 32 is a permutation, so the 32 LDS.U8 of a column
+    // hit 32 different banks (consecutive windows in one warp collide pairwise: measured 7x the bank conflicts).
+    const int x = threadIdx.x % tw;
+    const int kk = tw == 64 ? (((x & 31) << 1) | (x >> 5)) : x;
+    const int dir = (threadIdx.x / tw) & 1, sp = threadIdx.x / (2 * tw), slot = sp % n_slots, part = sp / n_slots;
     if (kk >= tile.nwin) return;
     const int64_t ws = (tile.first_k + kk) * (int64_t)a.step;
     int64_t we = ws + a.window_size; if (we > ctg.len) we = ctg.len;

@@ -196,3 +196,33 @@ def test_align_to_reference_batches_of_10000_are_sorted_separately(eng, small_ge
     assert len(exp) > 3000 and got == exp
     starts = [int(l.split("\t")[4]) for l in exp[1:]]
     assert starts != sorted(starts)                       # three separately sorted batches
+
+
+def test_search_reference_many_small_contigs(eng):
+    """Hundreds of contigs from 1 base to a few windows long, with N runs, lower case and IUPAC codes: tile and window bookkeeping at contig
+    edges (Range(0, len-1, step) yields nothing for a 1-base contig; windows shorter than the guide are dropped; upper-case N is trimmed, n is not)."""
+    rng = np.random.default_rng(2026)
+    site = "CTTGCCCCACAGGGCAGTAA"
+    contigs = []
+    for i in range(260):
+        n = int(rng.choice([1, 2, 5, 19, 22, 23, 24, 40, 969, 970, 971, 1000, 1001, 1940, 2500, int(rng.integers(1, 3000))]))
+        b = list(rng.choice(list("ACGT"), size=n))
+        if n > 60 and rng.random() < 0.7:
+            p = int(rng.integers(0, n - 30))
+            s = synth.mutate_protospacer(rng, site.encode(), int(rng.integers(0, 4))).decode() + "TGG"
+            if rng.random() < 0.5:
+                s = rc(s)
+            b[p:p + len(s)] = list(s)[:max(0, n - p)]
+        for _ in range(int(rng.integers(0, 3))):
+            if n > 4:
+                p = int(rng.integers(0, n)); k = int(rng.integers(1, 40)); ch = str(rng.choice(["N", "N", "n", "R", "a"]))
+                for q in range(p, min(n, p + k)):
+                    b[q] = ch if ch != "a" else b[q].lower()
+        if rng.random() < 0.1:
+            b[:min(n, 15)] = ["N"] * min(n, 15)
+        contigs.append(("ctg%d" % i, "".join(b[:n]).encode()))
+    for guide, kw in ((synth.BASELINE_GUIDE, {}), ("CTTGCCCCRCAGGGCAGTAAngg", dict(d=4, O=0)), ("ccnCTTGCCCCACAGGGCAGTAA", dict(window_size=200, g=1))):
+        exp = _lines(pyoracle.search_reference(contigs, guide, raw=True, **kw))
+        got = _lines(eng.search_reference(contigs, guide, raw=True, **kw))
+        assert got == exp, guide
+        assert len(exp) > 20
