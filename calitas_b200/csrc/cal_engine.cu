@@ -1018,7 +1018,9 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     int chrom_idx = -1;
     if (chrom && chrom[0]) { for (size_t c = 0; c < ref->names.size(); ++c) if (ref->names[c] == chrom) chrom_idx = (int)c; if (chrom_idx < 0) throw InvalidArgument(std::string("Unknown chromosome: ") + chrom); }
     // ---- plan: guide chunks and their window tilings ---------------------------------------------------------------------------
-    const int G_CHUNK = 16;      // measured on B200: chunks of 25-50 guides shorten the contended tails at 1/8 genome scale but expose a longer last tail (-2 to -5 % at full scale)
+    // measured on B200: chunks of 25-50 guides, or one tail per group of 4 chunks, shorten nothing at 1/8 genome scale (a tail that shares the SMs with
+    // a scan kernel slows down in proportion to its work) and expose a longer last tail at full scale (-2 to -5 %)
+    const int G_CHUNK = 16;
     std::vector<SearchChunk> chunks;
     for (int g0 = 0; g0 < n_guides;) {
       SearchChunk ch; ch.g0 = g0; ch.raw_len = (int)defs[(size_t)g0].raw.size();
@@ -1068,7 +1070,9 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
 #endif
         ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len, ch.scan_slots, ch.ts->tile_windows,
                      cand_slot[slot]->as<uint64_t>(), e->d_count + slot, (unsigned long long)e->cand_cap_hint };
-        CAL_LAUNCH(k_scan_tiled, (unsigned)ch.n_tiles, 2 * ch.ts->tile_windows * 4, ch.smem, ss, 3, sa);        // always 512 threads: 4 / scan_slots window parts per guide slot dev::launch_check("k_scan_tiled"); ++e->launches;
+        // always 2 * tile_windows * 4 threads (512 at the default window size): 4 / scan_slots window parts per guide slot
+        CAL_LAUNCH(k_scan_tiled, (unsigned)ch.n_tiles, 2 * ch.ts->tile_windows * 4, ch.smem, ss, 3, sa);
+        dev::launch_check("k_scan_tiled"); ++e->launches;
         counts[6] += 1; counts[7] += ch.bases;
       }
       dev::event_record(ce.ev[CE_SCAN_E], ss);
