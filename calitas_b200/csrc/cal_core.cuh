@@ -367,8 +367,11 @@ CAL_HD bool extend_pam(const GuideSpec& g, const Scores& sc, Fetch fetch, int32_
 }
 
 // Builds the hit for guide alignment `a` extended with PAM `pam_idx` (or PAM-less when pam_idx < 0).
+// The record is assembled in thread-local storage and stored once: `out` usually lives in global memory, and setting ~30 two-bit ops there
+// one read-modify-write at a time is what made this the second-largest part of k_align.
 CAL_HD void make_hit(const GuideSpec& g, const GuideAln& a, int pam_idx, int32_t score, int32_t offset, uint32_t xmask, int dir,
-                     const WindowGeom& w, int32_t guide_idx, int32_t contig_idx, int32_t task_idx, calitas_hit& h) {
+                     const WindowGeom& w, int32_t guide_idx, int32_t contig_idx, int32_t task_idx, calitas_hit& out) {
+  calitas_hit h;
   const int pam_len = pam_idx >= 0 ? g.pam_len[pam_idx] : 0;
   const int n_ops = a.n_ops + (pam_idx >= 0 ? offset + pam_len : 0);
   h.guide_idx = guide_idx; h.pam_idx = pam_idx; h.contig_idx = contig_idx; h.task_idx = task_idx; h.score = score;
@@ -397,6 +400,7 @@ CAL_HD void make_hit(const GuideSpec& g, const GuideAln& a, int pam_idx, int32_t
     h.start_offset = w.w_end - e0; h.end_offset = w.w_end - s0; h.guide_start_offset = w.w_end - ge0; h.guide_end_offset = w.w_end - gs0;
   }
   h.strand = (uint8_t)((dir ^ g.five_prime) ? '-' : '+');
+  out = h;
 }
 
 // ---- per-window canonicalisation (SequentialGuideAligner.scala:315-322) ---------------------------------------------------
