@@ -33,6 +33,7 @@ struct Tile { int32_t contig; int32_t nwin; int64_t first_k; };
 struct ExplicitWindow { int64_t nib_start; int32_t len; int32_t target_offset; int32_t guide_idx; int32_t contig_idx; };
 
 const int ALIGN_KB = 6;          // k_align keeps a 2*6+1-diagonal DP band in registers when the candidate threshold allows
+const int SCAN_SMEM_LIMIT = 200 * 1024;   // dynamic shared memory a k_scan_tiled CTA may ask for
 const int TILE_WINDOWS = 64;      // windows per scan tile at the default window size; halved until the tile fits shared memory for larger -w
 const int HALO_WINDOWS = 2;      // windows processed beyond each interior shard cut so that removeOverlaps sees both sides of the cut
 const int SCAN_THREADS = 2 * TILE_WINDOWS;
@@ -672,7 +673,7 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
   if (it == r->tilesets.end()) {
     calitas_reference::TileSet ts;
     // windows per tile: as many (<= 64, power of two) as keep the byte tile + staged packed words + 16 guides' tables within shared memory
-    while (ts.tile_windows > 1 && scan_smem_bytes(16, ts.tile_windows, window_size, step) > 200 * 1024) ts.tile_windows /= 2;
+    while (ts.tile_windows > 1 && scan_smem_bytes(16, ts.tile_windows, window_size, step) > (size_t)SCAN_SMEM_LIMIT) ts.tile_windows /= 2;
     int64_t win_base = 0;
     for (size_t c = 0; c < r->len.size(); ++c) {
       const int64_t len = r->len[c];
@@ -901,6 +902,11 @@ int calitas_engine_create(int32_t device_id, const calitas_costs* costs, calitas
     std::unique_ptr<calitas_engine> e(new calitas_engine());
     e->device = device_id; e->costs = c; e->sc = make_scores(c);
     e->stream = dev::stream_create_prio(1); e->scan_stream = dev::stream_create_prio(0); e->copy_stream = dev::stream_create_prio(1);
+#ifndef CAL_HOSTSIM
+    // once, to the most any launch asks for (SCAN_SMEM_LIMIT): the attribute is per device and function, and engines of several host threads
+    // share it — setting it per launch let one thread lower it under another's launch
+    dev::check(cudaFuncSetAttribute(k_scan_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_LIMIT), "cudaFuncSetAttribute");
+#endif
     for (auto& ev : e->ev) ev = dev::event_create();
     e->h_count = (unsigned long long*)dev::alloc_host(64);
     e->d_count = (unsigned long long*)dev::alloc(64);
@@ -1038,7 +1044,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       if (ch.banded > ALIGN_KB) ch.banded = 0;
       const int ng = g1 - g0;
       ch.smem = scan_smem_bytes(ng, ch.ts->tile_windows, window_size, ch.step);
-      if (ch.smem > 200 * 1024) throw LimitExceeded("window size too large for the shared-memory tile");
+      if (ch.smem > (size_t)SCAN_SMEM_LIMIT) throw LimitExceeded("window size too large for the shared-memory tile");
       { const int want = (ng + SCAN_NG - 1) / SCAN_NG; ch.scan_slots = want >= 3 ? 4 : (want == 2 ? 2 : 1); }     // guide slots per window (1, 2 or 4); the rest of the block's 4 slots split the window into parts
       ch.bases = 0; for (size_t t = ch.t_begin; t < t_end; ++t) ch.bases += (int64_t)(ch.ts->tiles[t].nwin - 1) * ch.step + window_size;
       chunks.push_back(ch);
@@ -1065,9 +1071,6 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       dev::zero(e->d_count + slot, 8, ss);
       dev::event_record(ce.ev[CE_SCAN_B], ss);
       if (ch.n_tiles) {
-#ifndef CAL_HOSTSIM
-        dev::check(cudaFuncSetAttribute(k_scan_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ch.smem), "cudaFuncSetAttribute");
-#endif
         ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len, ch.scan_slots, ch.ts->tile_windows,
                      cand_slot[slot]->as<uint64_t>(), e->d_count + slot, (unsigned long long)e->cand_cap_hint };
         // always 2 * tile_windows * 4 threads (512 at the default window size): 4 / scan_slots window parts per guide slot
