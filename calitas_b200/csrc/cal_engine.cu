@@ -41,13 +41,31 @@ const int SCAN_THREADS = 2 * TILE_WINDOWS;
 #define CAL_SCAN_NG 2
 #endif
 const int SCAN_NG = CAL_SCAN_NG;     // guides a scan thread advances together (independent dependency chains sharing the base-code extraction)
-const int KEY_COL_BITS = 17, KEY_WIN_SHIFT = 18, KEY_GUIDE_SHIFT = 50;
-const uint32_t MAX_WINDOW_LEN = (1u << KEY_COL_BITS) - 1;
+const int KEY_COL_BITS_MAX = 17;
+const uint32_t MAX_WINDOW_LEN = (1u << KEY_COL_BITS_MAX) - 1;
 const int MAX_GUIDES_PER_CALL = 1 << 14;
 
-CAL_HD uint64_t make_key(uint32_t guide, uint32_t window, uint32_t strandbit, uint32_t col) {
-  return ((uint64_t)guide << KEY_GUIDE_SHIFT) | ((uint64_t)window << KEY_WIN_SHIFT) | ((uint64_t)strandbit << KEY_COL_BITS) | col;
+// Candidate key = guide | window | strand | end column, each field only as wide as the call needs (<= 14 + 32 + 1 + 17 bits), so that the
+// LSD radix sort of the keys runs over `bits` bits: 5 eight-bit passes instead of 8 for 100 guides x hg38 at -w 1000.  Every pass is a
+// dependent launch that has to find room on SMs held by the next chunk's scan kernel.
+struct KeyLayout { int32_t col_bits, win_shift, guide_shift, bits; };
+CAL_HD int bit_length(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
+inline KeyLayout make_key_layout(uint32_t max_col, uint64_t n_windows, uint32_t n_guides) {
+  KeyLayout L; L.col_bits = bit_length(max_col); if (L.col_bits < 1) L.col_bits = 1;
+  L.win_shift = L.col_bits + 1;
+  int wb = bit_length(n_windows > 0 ? n_windows - 1 : 0); if (wb < 1) wb = 1;
+  L.guide_shift = L.win_shift + wb;
+  L.bits = L.guide_shift + bit_length(n_guides > 0 ? n_guides - 1 : 0);
+  return L;
 }
+CAL_HD uint64_t make_key(const KeyLayout& L, uint32_t guide, uint32_t window, uint32_t strandbit, uint32_t col) {
+  return ((uint64_t)guide << L.guide_shift) | ((uint64_t)window << L.win_shift) | ((uint64_t)strandbit << L.col_bits) | col;
+}
+CAL_HD int32_t key_col(const KeyLayout& L, uint64_t key) { return (int32_t)(key & ((1ull << L.col_bits) - 1)); }
+CAL_HD uint32_t key_strandbit(const KeyLayout& L, uint64_t key) { return (uint32_t)(key >> L.col_bits) & 1u; }
+CAL_HD uint32_t key_window(const KeyLayout& L, uint64_t key) { return (uint32_t)((key >> L.win_shift) & ((1ull << (L.guide_shift - L.win_shift)) - 1)); }
+CAL_HD int32_t key_guide(const KeyLayout& L, uint64_t key) { return (int32_t)(key >> L.guide_shift); }
+CAL_HD uint64_t key_group(const KeyLayout& L, uint64_t key) { return key >> L.col_bits; }      // (guide, window, strand)
 CAL_HD uint32_t nibble_at(const uint32_t* words, int64_t idx) { return (words[idx >> 3] >> ((uint32_t)(idx & 7) * 4)) & 15u; }
 
 // ------------------------------------------------------------------------------------------------------------------------------------
@@ -75,7 +93,7 @@ CAL_KERNEL __launch_bounds__(256) k_pack(const uint8_t* __restrict__ raw, uint32
 struct ScanArgs {
   const uint32_t* nib; const ContigDev* contigs; const Tile* tiles; const GuideSpec* specs;
   int32_t g_begin, g_end, window_size, step, min_len, scan_slots, tile_windows;
-  uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap;
+  uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap; KeyLayout key;
 };
 
 struct Emitter {
@@ -241,7 +259,7 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
       const int cnt = ng - g < SCAN_NG ? ng - g : SCAN_NG;
       for (int j = 0; j < cnt; ++j) {
         sg[j].peq = s_peq + (g + j) * 32 + dir * 16; sg[j].lp = s_meta[4 * (g + j)]; sg[j].k_edits = s_meta[4 * (g + j) + 1];
-        sg[j].key_base = make_key((uint32_t)(a.g_begin + g + j), wid, (uint32_t)(dir ^ s_meta[4 * (g + j) + 2]), 0);
+        sg[j].key_base = make_key(a.key, (uint32_t)(a.g_begin + g + j), wid, (uint32_t)(dir ^ s_meta[4 * (g + j) + 2]), 0);
       }
 #define CAL_SCAN_CALL(N) { if (dir == 0) scan_window<0, N>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); else scan_window<1, N>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); }
       if (cnt == SCAN_NG) CAL_SCAN_CALL(SCAN_NG)
@@ -257,7 +275,7 @@ CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct ScanExplicitArgs {
   const uint32_t* nib; const ExplicitWindow* windows; int64_t n_windows; const GuideSpec* specs;
-  uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap;
+  uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap; KeyLayout key;
 };
 struct GlobalWords {   // word accessor over global memory with nibble base offset
   const uint32_t* nib; int64_t base;
@@ -279,7 +297,7 @@ CAL_KERNEL __launch_bounds__(128) k_scan_explicit(ScanExplicitArgs a) {
   const GuideSpec& s = a.specs[ew.guide_idx];
   GlobalWords words{ a.nib, ew.nib_start >> 3 };
   const int32_t rs = (int32_t)(ew.nib_start & 7), re = rs + ew.len;
-  Emitter emit{ a.cand, a.cand_count, a.cand_cap, make_key(0, (uint32_t)w, (uint32_t)(dir ^ s.five_prime), 0) };
+  Emitter emit{ a.cand, a.cand_count, a.cand_cap, make_key(a.key, 0, (uint32_t)w, (uint32_t)(dir ^ s.five_prime), 0) };
   scan_range_generic(words, rs, re, dir, s.peq[dir], s.lp, s.k_edits, emit);
 }
 
@@ -292,7 +310,7 @@ struct AlignArgs {
   const uint32_t* nib;
   const ContigDev* contigs; int32_t n_contigs; int32_t window_size, step;     // tiled
   const ExplicitWindow* windows; int32_t task_base;                          // explicit (window ids are relative to task_base)
-  calitas_hit* hits; uint8_t* valid;
+  calitas_hit* hits; uint8_t* valid; KeyLayout key;
 };
 struct NibFetch {
   const uint32_t* nib; int64_t first; int32_t m; int dir;
@@ -317,8 +335,8 @@ CAL_D void locate_window(const uint32_t* nib, const ContigDev* contigs, int32_t 
 struct CandCtx { int32_t gidx, contig_idx, m, dir; uint32_t wid; WindowGeom geom; int64_t first; uint8_t owned; };
 CAL_D CandCtx decode_candidate(const AlignArgs& a, uint64_t key) {
   CandCtx x;
-  const uint32_t strandbit = (uint32_t)(key >> KEY_COL_BITS) & 1u;
-  x.wid = (uint32_t)(key >> KEY_WIN_SHIFT); x.gidx = (int32_t)(key >> KEY_GUIDE_SHIFT); x.owned = 1;
+  const uint32_t strandbit = key_strandbit(a.key, key);
+  x.wid = key_window(a.key, key); x.gidx = key_guide(a.key, key); x.owned = 1;
   if (a.explicit_mode) {
     const ExplicitWindow ew = a.windows[x.wid];
     x.gidx = ew.guide_idx; x.contig_idx = ew.contig_idx; x.geom.w_begin = ew.target_offset; x.geom.w_end = ew.target_offset + ew.len; x.first = ew.nib_start;
@@ -351,7 +369,7 @@ CAL_D void align_body(const AlignArgs& a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_cand) return;
   const uint64_t key = a.cand[i];
-  const int32_t col = (int32_t)(key & MAX_WINDOW_LEN);
+  const int32_t col = key_col(a.key, key);
   const CandCtx x = decode_candidate(a, key);
   const GuideSpec& g = a.specs[x.gidx];
   const NibFetch fetch{ a.nib, x.first, x.m, x.dir };
@@ -369,12 +387,12 @@ CAL_D void align_body(const AlignArgs& a) {
 // Wide thresholds on short explicit windows (alignBest / alignToRefBest: every end column is a candidate): one thread per (window, strand)
 // group of consecutive sorted candidates fills the DP once and traces every candidate column (band_align_group).
 const int GROUP_W = 160;
-struct GroupColAt { const uint64_t* cand; int64_t i0; CAL_D int operator()(int k) const { return (int)(cand[i0 + k] & MAX_WINDOW_LEN); } };
+struct GroupColAt { const uint64_t* cand; int64_t i0; KeyLayout key; CAL_D int operator()(int k) const { return (int)key_col(key, cand[i0 + k]); } };
 struct GroupEmit { const AlignArgs* a; const CandCtx* x; const GuideSpec* g; const NibFetch* fetch; int64_t i0;
                    CAL_D void operator()(int k, const GuideAln& aln) const { post_alignment(*a, *x, *g, *fetch, aln, i0 + k); } };
-CAL_KERNEL __launch_bounds__(128) k_mark_groups(const uint64_t* cand, int64_t n, uint32_t* flag) {
+CAL_KERNEL __launch_bounds__(128) k_mark_groups(const uint64_t* cand, int64_t n, int32_t col_bits, uint32_t* flag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = (i == 0 || (cand[i - 1] >> KEY_COL_BITS) != (cand[i] >> KEY_COL_BITS)) ? 1u : 0u;
+  if (i < n) flag[i] = (i == 0 || (cand[i - 1] >> col_bits) != (cand[i] >> col_bits)) ? 1u : 0u;
 }
 CAL_KERNEL __launch_bounds__(128) k_group_starts(const uint32_t* flag, const uint32_t* pos, int64_t n, uint32_t* gstart) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,7 +407,7 @@ CAL_KERNEL __launch_bounds__(128) k_align_group(AlignArgs a, const uint32_t* gst
   const NibFetch fetch{ a.nib, x.first, x.m, x.dir };
   for (int64_t s = i0 * a.slots; s < i1 * a.slots; ++s) a.valid[s] = 0;
   uint8_t trace[(CALITAS_MAX_PROTOSPACER + 1) * (GROUP_W + 1)];
-  const GroupColAt col_at{ a.cand, i0 };
+  const GroupColAt col_at{ a.cand, i0, a.key };
   const int first = col_at(0), last = col_at((int)(i1 - i0) - 1);
   const int jlo = first - g.span > 0 ? first - g.span : 0;
   if (last - jlo <= GROUP_W) {
@@ -410,16 +428,16 @@ CAL_KERNEL __launch_bounds__(128) k_align_wide(AlignArgs a) { align_body<0>(a); 
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct CanonArgs {
   const uint64_t* cand; int64_t n_cand; const GuideSpec* specs; int32_t slots; int32_t explicit_mode; const ExplicitWindow* windows;
-  const calitas_hit* hits; const uint8_t* valid; int32_t* rank; uint32_t* perm; uint32_t* flag; uint8_t* slot_owned; int32_t drop_halo;
+  const calitas_hit* hits; const uint8_t* valid; int32_t* rank; uint32_t* perm; uint32_t* flag; uint8_t* slot_owned; int32_t drop_halo; KeyLayout key;
 };
 CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_cand) return;
-  const uint64_t grp = a.cand[i] >> KEY_COL_BITS;
-  if (i > 0 && (a.cand[i - 1] >> KEY_COL_BITS) == grp) return;
-  int64_t j = i + 1; while (j < a.n_cand && (a.cand[j] >> KEY_COL_BITS) == grp) ++j;
+  const uint64_t grp = key_group(a.key, a.cand[i]);
+  if (i > 0 && key_group(a.key, a.cand[i - 1]) == grp) return;
+  int64_t j = i + 1; while (j < a.n_cand && key_group(a.key, a.cand[j]) == grp) ++j;
   const int64_t base = i * a.slots; const int n = (int)((j - i) * a.slots);
-  const int32_t gidx = a.explicit_mode ? a.windows[(uint32_t)(a.cand[i] >> KEY_WIN_SHIFT)].guide_idx : (int32_t)(a.cand[i] >> KEY_GUIDE_SHIFT);
+  const int32_t gidx = a.explicit_mode ? a.windows[key_window(a.key, a.cand[i])].guide_idx : key_guide(a.key, a.cand[i]);
   const GuideSpec& g = a.specs[gidx];
   int kept = canon_group(a.hits + base, a.valid + base, a.rank + base, n, g.max_total_diffs, g.max_overlap);
   bool owned = true; for (int k = 0; k < n; ++k) if (a.valid[base + k] == 2) owned = false;     // a group is one window: all halo or all owned
@@ -440,7 +458,7 @@ CAL_KERNEL __launch_bounds__(128) k_canon_warp(CanonArgs a, const uint32_t* gsta
   for (int64_t gi = warp; gi < n_groups; gi += n_warps) {
     const int64_t i0 = gstart[gi], i1 = gi + 1 < n_groups ? (int64_t)gstart[gi + 1] : a.n_cand;
     const int64_t base = i0 * a.slots; const int n = (int)((i1 - i0) * a.slots);
-    const int32_t gidx = a.explicit_mode ? a.windows[(uint32_t)(a.cand[i0] >> KEY_WIN_SHIFT)].guide_idx : (int32_t)(a.cand[i0] >> KEY_GUIDE_SHIFT);
+    const int32_t gidx = a.explicit_mode ? a.windows[key_window(a.key, a.cand[i0])].guide_idx : key_guide(a.key, a.cand[i0]);
     const int32_t max_total = a.specs[gidx].max_total_diffs, max_overlap = a.specs[gidx].max_overlap;
     bool halo = false;
     for (int k = lane; k < n; k += 32) { const uint8_t v = a.valid[base + k]; a.rank[base + k] = v ? -2 : -1; halo |= v == 2; }
@@ -497,14 +515,19 @@ CAL_KERNEL __launch_bounds__(256) k_gather(const calitas_hit* hits, const uint32
 // ------------------------------------------------------------------------------------------------------------------------------------
 // dedup: removeOverlaps (SearchReference.scala:653-675) + ReferenceHit.sort (ReferenceHit.scala:276-287)
 // ------------------------------------------------------------------------------------------------------------------------------------
-// key1 = guide | contig | strand | coordinate_start ; keyA = -score (biased).  Arrival order is the array index.
-CAL_KERNEL __launch_bounds__(256) k_dedup_keys(const calitas_hit* hits, int64_t n, uint64_t* key1, uint64_t* keyA, uint32_t* idx) {
+// key1 = guide (relative to the chunk) | contig | strand | coordinate_start, each field only as wide as the call needs (38 bits for a
+// 16-guide chunk on hg38 instead of 64: 5 radix passes instead of 8); keyA = score_hi - score in score_bits bits.  Arrival order is the
+// array index.  A value outside its field would mis-sort silently, so it raises *overflow, which the host reads with the sweep's counters.
+struct DedupLayout { int32_t start_bits, contig_shift, guide_shift, bits, g0, score_hi, score_bits; };
+CAL_KERNEL __launch_bounds__(256) k_dedup_keys(const calitas_hit* hits, int64_t n, DedupLayout L, uint64_t* key1, uint64_t* keyA, uint32_t* idx, uint32_t* overflow) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const calitas_hit& h = hits[i];
-  key1[i] = ((uint64_t)(uint32_t)h.guide_idx << KEY_GUIDE_SHIFT) | ((uint64_t)((uint32_t)h.contig_idx & 0x3FFFFu) << 32) | ((uint64_t)(h.strand == '-' ? 1u : 0u) << 31) |
-            ((uint32_t)h.guide_start_offset & 0x7FFFFFFFu);
-  keyA[i] = (uint64_t)(uint32_t)(0x7FFFFFFF - h.score);
+  const int64_t start = h.guide_start_offset, sc = (int64_t)L.score_hi - h.score, g = (int64_t)h.guide_idx - L.g0, c = h.contig_idx;
+  if (start < 0 || (start >> L.start_bits) != 0 || sc < 0 || (sc >> L.score_bits) != 0 || g < 0 || c < 0 ||
+      (uint64_t)c >= (1ull << (L.guide_shift - L.contig_shift)) || (L.bits < 64 && ((uint64_t)g >> (L.bits - L.guide_shift)) != 0)) *overflow = 1u;
+  key1[i] = ((uint64_t)g << L.guide_shift) | ((uint64_t)c << L.contig_shift) | ((uint64_t)(h.strand == '-' ? 1u : 0u) << L.start_bits) | (uint64_t)start;
+  keyA[i] = (uint64_t)sc;
   idx[i] = (uint32_t)i;
 }
 CAL_KERNEL __launch_bounds__(256) k_gather_u64(const uint64_t* in, const uint32_t* idx, int64_t n, uint64_t* out) {
@@ -526,27 +549,27 @@ CAL_HD int32_t soa_overlap(const int32_t* s_start, const int32_t* s_end, int64_t
 // restarts there unconditionally and segments are independent.  With max_overlap <= 0 every later hit "overlaps" (>= 0) and the sweep is
 // run per group, as the reference's loop would.
 CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key1, const int32_t* s_start, const int32_t* s_end, const int32_t* s_score, const uint8_t* s_owned, int64_t n, int32_t max_overlap,
-                                          int32_t segmented, uint32_t* keep) {
+                                          int32_t segmented, int32_t gshift /* key1 >> gshift = (guide, contig, strand) */, uint32_t* keep) {
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i0 >= n) return;
-  const uint64_t grp = key1[i0] >> 31;
-  if (i0 > 0 && (key1[i0 - 1] >> 31) == grp && !(segmented && s_start[i0] - s_start[i0 - 1] > CALITAS_MAX_OPS)) return;
+  const uint64_t grp = key1[i0] >> gshift;
+  if (i0 > 0 && (key1[i0 - 1] >> gshift) == grp && !(segmented && s_start[i0] - s_start[i0 - 1] > CALITAS_MAX_OPS)) return;
   int64_t i = i0;
   for (;;) {
     const int64_t cur = i++;
-    while (i < n && (key1[i] >> 31) == grp && soa_overlap(s_start, s_end, i, cur) >= max_overlap && s_score[i] <= s_score[cur]) { keep[i] = 0; ++i; }
-    const bool has_next = i < n && (key1[i] >> 31) == grp;
+    while (i < n && (key1[i] >> gshift) == grp && soa_overlap(s_start, s_end, i, cur) >= max_overlap && s_score[i] <= s_score[cur]) { keep[i] = 0; ++i; }
+    const bool has_next = i < n && (key1[i] >> gshift) == grp;
     keep[cur] = ((!has_next || soa_overlap(s_start, s_end, i, cur) < max_overlap) && s_owned[cur]) ? 1u : 0u;   // halo hits take part, are never reported
     if (!has_next) break;
     if (segmented && s_start[i] - s_start[i - 1] > CALITAS_MAX_OPS) break;                                       // next segment has its own thread
   }
 }
 // compaction of (idx, key) by keep; key is rewritten to the final sort key guide | contig | coordinate_start | strand
-CAL_KERNEL __launch_bounds__(256) k_compact_keepers(const uint64_t* key1, const uint32_t* idx, const uint32_t* keep, const uint32_t* pos, int64_t n, uint64_t* key3, uint32_t* idx_out) {
+CAL_KERNEL __launch_bounds__(256) k_compact_keepers(const uint64_t* key1, const uint32_t* idx, const uint32_t* keep, const uint32_t* pos, int64_t n, int32_t start_bits, uint64_t* key3, uint32_t* idx_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !keep[i]) return;
-  const uint64_t k = key1[i];
-  key3[pos[i]] = (k & 0xFFFFFFFF00000000ull) | ((k & 0x7FFFFFFFull) << 1) | ((k >> 31) & 1ull);
+  const uint64_t k = key1[i], lo = (1ull << start_bits) - 1;
+  key3[pos[i]] = ((k >> (start_bits + 1)) << (start_bits + 1)) | ((k & lo) << 1) | ((k >> start_bits) & 1ull);
   idx_out[pos[i]] = idx[i];
 }
 
@@ -611,7 +634,7 @@ struct calitas_reference {
   calitas_engine* owner = nullptr;
   std::vector<std::string> names; std::vector<int64_t> len, have_b, have_e, own_b, own_e, nib_off;
   uint32_t* d_nib = nullptr; uint8_t* d_raw = nullptr; int64_t total_padded = 0;
-  struct TileSet { std::vector<Tile> tiles; std::vector<ContigDev> contigs; Tile* d_tiles = nullptr; ContigDev* d_contigs = nullptr; int64_t n_windows = 0; int tile_windows = TILE_WINDOWS; };
+  struct TileSet { std::vector<Tile> tiles; std::vector<ContigDev> contigs; Tile* d_tiles = nullptr; ContigDev* d_contigs = nullptr; int64_t n_windows = 0, total_windows = 0; int tile_windows = TILE_WINDOWS; };
   std::map<std::pair<int, int>, TileSet> tilesets;   // (window_size, step)
 };
 
@@ -696,6 +719,7 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
       win_base += n_win;
     }
     if (win_base >= (1ll << 32)) throw LimitExceeded("more than 2^32 reference windows");
+    ts.total_windows = win_base;
     ts.d_tiles = (Tile*)dev::alloc(ts.tiles.size() * sizeof(Tile));
     ts.d_contigs = (ContigDev*)dev::alloc(ts.contigs.size() * sizeof(ContigDev));
     dev::h2d(ts.d_tiles, ts.tiles.data(), ts.tiles.size() * sizeof(Tile), e->stream);
@@ -711,6 +735,7 @@ struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> alig
   calitas_engine* e; const uint64_t* cand; dev::Event ev_sorted, ev_align_b, ev_align_e;   // candidate keys; events recorded after the sort / around k_align
   const GuideSpec* d_specs; int slots; bool explicit_mode; int banded;   // banded: 0 = wide thresholds, else the largest k_edits of the launch (<= ALIGN_KB)
   const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base; bool drop_halo;
+  KeyLayout key;
 };
 
 // Runs sort/align/canon on e->cand[0..n_cand) and leaves the kept hits, in arrival order, in e->kept; returns their number.
@@ -721,8 +746,8 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   if (n_cand * (int64_t)P.slots >= (1ll << 32)) throw LimitExceeded("too many candidate alignments in one batch");
   // 1. sort candidate keys -> (guide, window, strand, end column)
   e->cand_sorted.ensure((size_t)n_cand * 8);
-  size_t tb = dev::sort_keys_u64_tmp((size_t)n_cand, 0, 64); e->tmp.ensure(tb);
-  dev::sort_keys_u64(e->tmp.p, tb, P.cand, e->cand_sorted.as<uint64_t>(), (size_t)n_cand, 0, 64, s); ++e->launches;
+  size_t tb = dev::sort_keys_u64_tmp((size_t)n_cand, 0, P.key.bits); e->tmp.ensure(tb);
+  dev::sort_keys_u64(e->tmp.p, tb, P.cand, e->cand_sorted.as<uint64_t>(), (size_t)n_cand, 0, P.key.bits, s); ++e->launches;
   dev::event_record(P.ev_sorted, s);                      // the candidate buffer may be refilled by the next scan from here on
   // 2. align
   const int64_t n_slots = n_cand * P.slots;
@@ -730,7 +755,7 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   AlignArgs aa; std::memset(&aa, 0, sizeof aa);
   aa.cand = e->cand_sorted.as<uint64_t>(); aa.n_cand = n_cand; aa.specs = P.d_specs; aa.sc = e->sc; aa.slots = P.slots; aa.explicit_mode = P.explicit_mode ? 1 : 0;
   aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows; aa.task_base = P.task_base;
-  aa.hits = e->hits.as<calitas_hit>(); aa.valid = e->valid.as<uint8_t>();
+  aa.hits = e->hits.as<calitas_hit>(); aa.valid = e->valid.as<uint8_t>(); aa.key = P.key;
   dev::event_record(P.ev_align_b, s);
   if (P.banded > 5) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
   else if (P.banded == 5) { CAL_LAUNCH(k_align5, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align5"); }
@@ -738,7 +763,7 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   else if (P.explicit_mode) {             // short windows, nearly every column a candidate: one DP fill per (window, strand)
     e->key1.ensure((size_t)n_cand * 4); e->keyA.ensure((size_t)n_cand * 4); e->idx.ensure((size_t)n_cand * 4);   // group flag / group index / group start (u32 views)
     uint32_t* gflag = e->key1.as<uint32_t>(); uint32_t* gpos = e->keyA.as<uint32_t>();
-    CAL_LAUNCH(k_mark_groups, blocks_for(n_cand, 128), 128, 0, s, 1, aa.cand, n_cand, gflag); dev::launch_check("k_mark_groups"); ++e->launches;
+    CAL_LAUNCH(k_mark_groups, blocks_for(n_cand, 128), 128, 0, s, 1, aa.cand, n_cand, P.key.col_bits, gflag); dev::launch_check("k_mark_groups"); ++e->launches;
     size_t tb2 = dev::exclusive_sum_u32_tmp((size_t)n_cand); e->tmp.ensure(tb2);
     dev::exclusive_sum_u32(e->tmp.p, tb2, gflag, gpos, (size_t)n_cand, s); ++e->launches;
     uint32_t lp = 0, lf = 0;
@@ -755,7 +780,7 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   e->rank.ensure((size_t)n_slots * 4); e->perm.ensure((size_t)n_slots * 4); e->flag.ensure((size_t)n_slots * 4); e->pos.ensure((size_t)n_slots * 4); e->slot_owned.ensure((size_t)n_slots);
   CanonArgs ca; std::memset(&ca, 0, sizeof ca);
   ca.cand = aa.cand; ca.n_cand = n_cand; ca.specs = P.d_specs; ca.slots = P.slots; ca.explicit_mode = aa.explicit_mode; ca.windows = P.d_windows;
-  ca.hits = aa.hits; ca.valid = aa.valid; ca.rank = e->rank.as<int32_t>(); ca.perm = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>(); ca.slot_owned = e->slot_owned.as<uint8_t>(); ca.drop_halo = P.drop_halo ? 1 : 0;
+  ca.hits = aa.hits; ca.valid = aa.valid; ca.rank = e->rank.as<int32_t>(); ca.perm = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>(); ca.slot_owned = e->slot_owned.as<uint8_t>(); ca.drop_halo = P.drop_halo ? 1 : 0; ca.key = P.key;
 #ifndef CAL_HOSTSIM
   if (P.explicit_mode && !P.banded) {     // large groups: a warp per group (group starts, indices and flags were built for k_align_group)
     CAL_LAUNCH(k_canon_warp, (unsigned)dev::sm_count(e->device) * 16, 128, 0, s, 1, ca, e->idx.as<uint32_t>(), e->keyA.as<uint32_t>(), e->key1.as<uint32_t>()); dev::launch_check("k_canon_warp"); ++e->launches;
@@ -775,32 +800,34 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
 }
 
 // removeOverlaps + final sort over e->kept[0..n) -> appended to e->out at out_n; returns number of keepers.
-int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out_n) {
+int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out_n, const DedupLayout& L) {
   dev::Stream s = e->stream;
   if (n == 0) return 0;
   if (n >= (1ll << 32)) throw LimitExceeded("too many hits in one batch");
   const calitas_hit* hits = e->kept.as<calitas_hit>();
   e->key1.ensure((size_t)n * 8); e->keyA.ensure((size_t)n * 8); e->key_b.ensure((size_t)n * 8); e->idx.ensure((size_t)n * 4); e->idx2.ensure((size_t)n * 4);
-  CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>()); dev::launch_check("k_dedup_keys"); ++e->launches;
+  CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + 7)); dev::launch_check("k_dedup_keys"); ++e->launches;
   size_t tb = dev::sort_pairs_u64_tmp((size_t)n, 0, 64); e->tmp.ensure(tb);
   // stable by -score (arrival order = index order), then stable by (guide, contig, strand, start)
-  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, 32, s); ++e->launches;
+  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, L.score_bits, s); ++e->launches;
   CAL_LAUNCH(k_gather_u64, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), n, e->keyA.as<uint64_t>()); dev::launch_check("k_gather_u64"); ++e->launches;
-  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)n, 0, 64, s); ++e->launches;
+  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)n, 0, L.bits, s); ++e->launches;
   // now key1[i], idx[i] sorted by (guide, contig, strand, start, -score, arrival)
   e->sstart.ensure((size_t)n * 4); e->send.ensure((size_t)n * 4); e->sscore.ensure((size_t)n * 4); e->sowned.ensure((size_t)n); e->flag.ensure((size_t)n * 4); e->pos.ensure((size_t)n * 4);
   CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, hits, e->kept_owned.as<uint8_t>(), e->idx.as<uint32_t>(), n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
-  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, e->key1.as<uint64_t>(), e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, max_overlap, max_overlap >= 1 ? 1 : 0, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
+  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, e->key1.as<uint64_t>(), e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, max_overlap, max_overlap >= 1 ? 1 : 0, L.start_bits, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
   tb = dev::exclusive_sum_u32_tmp((size_t)n); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n, s); ++e->launches;
   uint32_t last_pos = 0, last_flag = 0;
   dev::d2h(&last_pos, e->pos.as<uint32_t>() + (n - 1), 4, s); dev::d2h(&last_flag, e->flag.as<uint32_t>() + (n - 1), 4, s);
+  dev::d2h(e->h_count + 7, e->d_count + 7, 8, s);
   dev::stream_sync(s);
+  if (e->h_count[7]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in removeOverlaps");
   const int64_t nk = (int64_t)last_pos + last_flag;
   if (nk == 0) return 0;
-  CAL_LAUNCH(k_compact_keepers, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n, e->keyA.as<uint64_t>(), e->idx2.as<uint32_t>()); dev::launch_check("k_compact_keepers"); ++e->launches;
+  CAL_LAUNCH(k_compact_keepers, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n, L.start_bits, e->keyA.as<uint64_t>(), e->idx2.as<uint32_t>()); dev::launch_check("k_compact_keepers"); ++e->launches;
   tb = dev::sort_pairs_u64_tmp((size_t)nk, 0, 64); e->tmp.ensure(tb);
-  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)nk, 0, 64, s); ++e->launches;
+  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)nk, 0, L.bits, s); ++e->launches;
   e->out.ensure_keep((size_t)(out_n + nk) * sizeof(calitas_hit), (size_t)out_n * sizeof(calitas_hit), s);
   CAL_LAUNCH(k_gather, blocks_for(nk, 256), 256, 0, s, 1, hits, e->idx.as<uint32_t>(), nk, e->out.as<calitas_hit>() + out_n); dev::launch_check("k_gather"); ++e->launches;
   return nk;
@@ -846,13 +873,15 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
   const int64_t n_windows = (int64_t)windows.size();
   // batches bound the candidate buffer: in best mode every column of every window is a candidate
   int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_windows, 1 << 18));
+  uint32_t max_len = 1; for (auto& w : windows) if (w.len > 0 && (uint32_t)w.len > max_len) max_len = (uint32_t)w.len;
+  const KeyLayout key = make_key_layout(max_len, (uint64_t)batch, 1);       // window ids are relative to the batch; the guide comes from the window
   for (int64_t w0 = 0; w0 < n_windows; w0 += batch) {
     const int64_t nw = std::min(batch, n_windows - w0);
     unsigned long long n_cand = 0;
     for (;;) {
       e->cand.ensure(e->cand_cap_hint * 8);
       dev::zero(e->d_count, 8, s);
-      ScanExplicitArgs sa{ d_nib, e->windows.as<ExplicitWindow>() + w0, nw, e->specs.as<GuideSpec>(), e->cand.as<uint64_t>(), e->d_count, (unsigned long long)e->cand_cap_hint };
+      ScanExplicitArgs sa{ d_nib, e->windows.as<ExplicitWindow>() + w0, nw, e->specs.as<GuideSpec>(), e->cand.as<uint64_t>(), e->d_count, (unsigned long long)e->cand_cap_hint, key };
       dev::event_record(e->ev[4], s);
       CAL_LAUNCH(k_scan_explicit, blocks_for(2 * nw, 128), 128, 0, s, 1, sa); dev::launch_check("k_scan_explicit"); ++e->launches;
       dev::event_record(e->ev[5], s);
@@ -864,7 +893,7 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
     ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
     counts[1] += (int64_t)n_cand;
     // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
-    Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true };
+    Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true, key };
     int64_t n_aln = 0;
     const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
     if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
@@ -1010,7 +1039,7 @@ void calitas_reference_free(calitas_engine* e, calitas_reference* r) {
 }
 
 // One guide chunk of a search: consecutive guides sharing the raw guide length, hence the window tiling (SearchReference.scala:528-530).
-struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; };
+struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; KeyLayout key; DedupLayout dedup; };
 
 int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
                    int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out) {
@@ -1046,6 +1075,27 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       ch.smem = scan_smem_bytes(ng, ch.ts->tile_windows, window_size, ch.step);
       if (ch.smem > (size_t)SCAN_SMEM_LIMIT) throw LimitExceeded("window size too large for the shared-memory tile");
       { const int want = (ng + SCAN_NG - 1) / SCAN_NG; ch.scan_slots = want >= 3 ? 4 : (want == 2 ? 2 : 1); }     // guide slots per window (1, 2 or 4); the rest of the block's 4 slots split the window into parts
+      ch.key = make_key_layout((uint32_t)window_size, (uint64_t)ch.ts->total_windows, (uint32_t)n_guides);
+      {   // removeOverlaps sort keys: field widths from the reference and the chunk; score bounds from the guides' thresholds and costs
+        DedupLayout& D = ch.dedup; const Scores& sc = e->sc;
+        int64_t max_len = 1; for (int64_t l : ref->len) max_len = std::max(max_len, l);
+        D.start_bits = std::min(31, bit_length((uint64_t)max_len)); D.contig_shift = D.start_bits + 1;
+        D.guide_shift = D.contig_shift + bit_length((uint64_t)(ref->len.size() - 1)); D.g0 = g0; D.bits = D.guide_shift + bit_length((uint64_t)(g1 - g0 - 1));
+        // a hit's score = guide alignment (min_score ... lp rows each worth at most a match or an inserted base) + PAM bases + offset * queryGap
+        int64_t hi = 0, lo = 0; bool first = true;
+        for (int g = g0; g < g1; ++g) {
+          const GuideSpec& sp = specs[(size_t)g];
+          int pam_len = 0; for (int k = 0; k < sp.n_pams; ++k) pam_len = std::max<int>(pam_len, sp.pam_len[k]);
+          const int64_t per_row = std::max<int64_t>(std::max<int64_t>(sc.match, sc.target_gap), 0), per_pam = std::max<int64_t>(iabs(sc.pam_match), iabs(sc.pam_mismatch));
+          const int64_t h = per_row * sp.lp + per_pam * pam_len + (int64_t)std::max(0, sp.g) * std::max<int64_t>(sc.query_gap, 0);
+          const int64_t l = (int64_t)sp.min_score - per_pam * pam_len - (int64_t)std::max(0, sp.g) * iabs(sc.query_gap);
+          if (first || h > hi) hi = h;
+          if (first || l < lo) lo = l;
+          first = false;
+        }
+        if (hi - lo >= (1ll << 31) || hi > 0x7FFFFFFFll || hi < -0x7FFFFFFFll) { D.score_hi = 0x7FFFFFFF; D.score_bits = 33; }   // 0x7FFFFFFF - score fits 33 bits for any int32 score
+        else { D.score_hi = (int32_t)hi; D.score_bits = std::max(1, bit_length((uint64_t)(hi - lo))); }
+      }
       ch.bases = 0; for (size_t t = ch.t_begin; t < t_end; ++t) ch.bases += (int64_t)(ch.ts->tiles[t].nwin - 1) * ch.step + window_size;
       chunks.push_back(ch);
       g0 = g1;
@@ -1053,6 +1103,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     const size_t n_chunks = chunks.size();
     while (e->chunk_ev.size() < n_chunks) { ChunkEvents ce; for (auto& ev : ce.ev) ev = dev::event_create(); e->chunk_ev.push_back(ce); }
     e->launches = 0;
+    dev::zero(e->d_count + 7, 8, s);                         // field-overflow flag of k_dedup_keys
     dev::event_record(e->ev[0], ss);
     e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), ss);
     double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -1072,7 +1123,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       dev::event_record(ce.ev[CE_SCAN_B], ss);
       if (ch.n_tiles) {
         ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len, ch.scan_slots, ch.ts->tile_windows,
-                     cand_slot[slot]->as<uint64_t>(), e->d_count + slot, (unsigned long long)e->cand_cap_hint };
+                     cand_slot[slot]->as<uint64_t>(), e->d_count + slot, (unsigned long long)e->cand_cap_hint, ch.key };
         // always 2 * tile_windows * 4 threads (512 at the default window size): 4 / scan_slots window parts per guide slot
         CAL_LAUNCH(k_scan_tiled, (unsigned)ch.n_tiles, 2 * ch.ts->tile_windows * 4, ch.smem, ss, 3, sa);
         dev::launch_check("k_scan_tiled"); ++e->launches;
@@ -1102,12 +1153,12 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         counts[1] += (int64_t)n_cand;
         dev::event_record(ce.ev[CE_TAIL_B], s);
         Pipeline P{ e, cand_slot[slot]->as<uint64_t>(), ce.ev[CE_SORTED], ce.ev[CE_ALIGN_B], ce.ev[CE_ALIGN_E], e->specs.as<GuideSpec>(), ch.slots, false, ch.banded,
-                    ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, 0, dedup == 0 };
+                    ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, 0, dedup == 0, ch.key };
         int64_t n_aln = 0;
         const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
         counts[2] += n_aln;
         int64_t n_new = 0;
-        if (dedup) n_new = run_dedup(e, n_kept, limits->max_overlap, n_out);
+        if (dedup) n_new = run_dedup(e, n_kept, limits->max_overlap, n_out, ch.dedup);
         else if (n_kept) {
           e->out.ensure_keep((size_t)(n_out + n_kept) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
           dev::d2d(e->out.as<calitas_hit>() + n_out, e->kept.p, (size_t)n_kept * sizeof(calitas_hit), s);
