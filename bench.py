@@ -66,14 +66,16 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
+    def __init__(self, gpu_indices):
+        self.gpu = ",".join(str(i) for i in gpu_indices)       # rank 0 samples every GPU of the job with ONE nvidia-smi process
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
 
     def start(self):
+        if not self.gpu:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpu, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -271,7 +273,7 @@ def main():
         hs.free()
         return st
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(range(world) if rank == 0 else [])
     sampler.start()                      # nvidia-smi needs ~1 s to start: launched before the warm-up so that it is sampling during the timed steps
     for _ in range(args.warmup):
         step()

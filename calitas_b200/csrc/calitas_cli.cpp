@@ -1,4 +1,4 @@
-// calitas_cli.cpp — `calitas SearchReference ...` / `calitas AlignToReference ...` on the B200 engine.
+// calitas_cli.cpp — `calitas SearchReference ...` / `AlignToReference ...` / `PairwiseAlignSequences ...` on the B200 engine, and `PrepareVcf`.
 //
 // Keeps the reference's command-line surface (SearchReference.scala:452-470, AlignToReference.scala:35-50: same flags, defaults and
 // validation messages) and its 34-column hit table; underneath, the whole FASTA is read into memory, packed into HBM and searched
@@ -17,6 +17,7 @@
 
 #include "../../include/calitas_b200_tools.h"
 #include "cal_io.h"
+#include "cal_vcf.h"
 
 using namespace cal::io;
 typedef std::string Str;
@@ -44,7 +45,10 @@ std::map<Str, std::vector<Str>> parse_flags(int argc, char** argv, int first, co
       if (!cur) throw UsageError{ "No option found with name '" + name + "'" };
       std::vector<Str>& v = out[cur->long_name];
       if (has_value) v.push_back(value);
-      else if (cur->boolean) v.push_back("true");
+      else if (cur->boolean) {             // sopt booleans: bare flag = true, or an explicit true/false value
+        const Str nx = i + 1 < argc ? argv[i + 1] : "";
+        if (nx == "true" || nx == "false" || nx == "True" || nx == "False" || nx == "T" || nx == "F" || nx == "yes" || nx == "no") { v.push_back(nx); ++i; } else v.push_back("true");
+      }
       else if (i + 1 < argc && !(std::strlen(argv[i + 1]) >= 2 && argv[i + 1][0] == '-' && !(argv[i + 1][1] >= '0' && argv[i + 1][1] <= '9'))) v.push_back(argv[++i]);
       else if (!cur->multi) throw UsageError{ Str("Option '") + cur->long_name + "' requires a value" };
     } else {
@@ -215,12 +219,26 @@ int pairwise_align(int argc, char** argv) {           // PairwiseAlignSequences.
   return 0;
 }
 
+int prepare_vcf_tool(int argc, char** argv) {       // PrepareVcf.scala:32-38
+  std::vector<FlagDef> defs = { { 'i', "input", true }, { 'o', "output", false }, { 'f', "min-af", false }, { 'd', "dict", false }, { 'c', "add-chr-prefix", false, true }, { 0, "stats", false, true } };
+  Flags f{ parse_flags(argc, argv, 2, defs) };
+  if (!f.has("input")) throw UsageError{ "Argument 'input' is required" };
+  double min_af = 0.01;
+  if (f.has("min-af")) { const Str s = f.str("min-af"); char* e = nullptr; min_af = std::strtod(s.c_str(), &e); if (e == s.c_str() || *e) throw UsageError{ "Value for 'min-af' is not a number: " + s }; }
+  const Str c = f.str("add-chr-prefix", "true");
+  const bool add_chr = !(c == "false" || c == "False" || c == "F" || c == "no");
+  const PrepareVcfStats st = prepare_vcf(f.list("input"), f.required("output"), min_af, f.str("dict"), add_chr);
+  if (f.has("stats")) std::fprintf(stderr, "calitas-b200 PrepareVcf: %lld of %lld records kept\n", st.records_out, st.records_in);
+  return 0;
+}
+
 void usage() {
   std::fprintf(stderr,
     "calitas (B200 engine)\nUSAGE: calitas SearchReference -i GUIDEpam -I ID -r ref.fa [-x pam ...] [-v variants.vcf] [-V 16] [-o out.tsv] [-w 1000] [-d 5] [-p 1] [-g 3] [-D n] [-O 10]\n"
     "                               [-m -120] [-M -260] [-b -122] [-B -121] [-c chrom] [--devices 0,1,...] [--guides-file file]\n"
     "       calitas AlignToReference -i tasks.tsv -r ref.fa [-o out.tsv] [-w n] [-d n -p n -O n] [-g 3] [-D n] [-m -M -b -B]\n"
-    "       calitas PairwiseAlignSequences -i pairs.txt [-o out.tsv] [-m -M -b -B]\n");
+    "       calitas PairwiseAlignSequences -i pairs.txt [-o out.tsv] [-m -M -b -B]\n"
+    "       calitas PrepareVcf -i in.vcf[.gz] [more.vcf ...] -o out.vcf[.gz] [-f 0.01] [-d ref.dict] [-c true|false]\n");
 }
 
 }  // namespace
@@ -232,6 +250,7 @@ int main(int argc, char** argv) {
     if (tool == "SearchReference") return search_reference(argc, argv);
     if (tool == "AlignToReference") return align_to_reference(argc, argv);
     if (tool == "PairwiseAlignSequences") return pairwise_align(argc, argv);
+    if (tool == "PrepareVcf") return prepare_vcf_tool(argc, argv);
     usage(); std::fprintf(stderr, "Unknown tool: %s\n", argv[1]); return 1;
   } catch (const UsageError& e) { std::fprintf(stderr, "calitas: %s\n", e.msg.c_str()); return 2; }
   catch (const IoError& e) { std::fprintf(stderr, "calitas: %s\n", e.msg.c_str()); return 2; }

@@ -195,3 +195,72 @@ def align_to_reference(contigs, tasks, window_size=None, d=None, p=None, g=3, D=
     text = _take(lib().oracle_align_to_reference(len(contigs), names, lens, ptrs, _b(assembly) if assembly else None, len(tasks),
                                                  _strarr([t[0] for t in tasks]), _strarr([t[1] for t in tasks]), _strarr([t[2] for t in tasks]), pos, ip))
     return text if raw else hits_table(text)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# PrepareVcf (PrepareVcf.scala:43-91) — pure-Python restatement; the records it keeps and rewrites, as (CHROM, POS, ID, REF, [ALT], QUAL, [AF]).
+# Parity unpinned beyond the reference's one test (PrepareVcfTest.scala:10-43: samples removed, 10 of 10 records kept): the number
+# formatting is htsjdk's VCFEncoder.formatVCFDouble / formatQualValue restated from its published source, not run here.
+# ---------------------------------------------------------------------------------------------------------------------------------------
+_CHROMS_TO_FIX = {str(i) for i in range(1, 23)} | {"X", "Y"}          # PrepareVcf.scala:13-15
+
+
+def _java_round(value, places):
+    """java.util.Formatter rounds HALF_UP on the shortest decimal form of the double."""
+    from decimal import Decimal, ROUND_HALF_UP
+    return Decimal(repr(float(value))).quantize(Decimal(1).scaleb(-places), rounding=ROUND_HALF_UP)
+
+
+def format_vcf_double(d):
+    """htsjdk VCFEncoder.formatVCFDouble."""
+    from decimal import Decimal, ROUND_HALF_UP
+    if d < 1:
+        if d < 0.01:
+            if abs(d) >= 1e-20:
+                dec = Decimal(repr(float(d)))
+                exp = dec.adjusted()
+                mant = (dec.scaleb(-exp)).quantize(Decimal("0.001"), rounding=ROUND_HALF_UP)
+                if abs(mant) >= 10:
+                    mant = (mant / 10).quantize(Decimal("0.001"))
+                    exp += 1
+                return "%se%s%02d" % (mant, "-" if exp < 0 else "+", abs(exp))
+            return "0.00"
+        return str(_java_round(d, 3))
+    return str(_java_round(d, 2))
+
+
+def format_qual(q):
+    """htsjdk VCFEncoder.formatQualValue."""
+    s = str(_java_round(q, 2))
+    return s[:-3] if s.endswith(".00") else s
+
+
+def prepare_vcf(texts, min_af=0.01, add_chr_prefix=True):
+    """texts: the input VCFs' contents in order.  Returns (header_has_samples_removed_chrom_line, records)."""
+    import numpy as np
+    records = []
+    for text in texts:
+        for line in text.split("\n"):
+            line = line.rstrip("\r")
+            if not line or line.startswith("#"):
+                continue
+            f = line.split("\t")
+            if f[6] != "PASS":                                                          # :73
+                continue
+            af = None
+            for kv in f[7].split(";"):
+                if kv.startswith("AF="):
+                    af = [float("nan") if x == "." else float(np.float32(x)) for x in kv[3:].split(",")]   # ArrayAttr[Float]
+            if af is None:
+                raise KeyError("AF")                                                    # :74 apply() on a missing key
+            if not any(x >= min_af for x in af):                                        # :74
+                continue
+            alts = f[4].split(",")
+            simple = lambda a: len(a) > 0 and all(c in "ACGTNacgtn" for c in a)         # fgbio SimpleAllele
+            if not (simple(f[3]) and all(simple(a) for a in alts)):                     # :75
+                continue
+            kept = [(a, x) for a, x in zip(alts, af) if x >= min_af]                    # :77
+            chrom = "chr" + f[0] if add_chr_prefix and f[0] in _CHROMS_TO_FIX else f[0]  # :79,91
+            qual = f[5] if f[5] == "." else format_qual(float(f[5]))
+            records.append((chrom, f[1], f[2], f[3], [a for a, _ in kept], qual, [format_vcf_double(x) for _, x in kept]))
+    return records

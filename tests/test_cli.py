@@ -103,6 +103,46 @@ def test_search_reference_cli_flags_and_vcf(calitas, ref_dir):
     assert lines(open(out).read()) == exp and len(exp) > 3
 
 
+def test_prepare_vcf_then_search_reference(calitas, ref_dir):
+    """The reference's two-step use: PrepareVcf (PrepareVcf.scala:43-91) on a raw call set -- genotypes, extra INFO keys, failing filters, rare and
+    symbolic alleles -- then SearchReference -v on its output; expected = the oracle searching the oracle-prepared records."""
+    d, g, contigs = ref_dir
+    arrays = [np.frombuffer(b.upper(), dtype=np.uint8) for _, b in contigs]
+    clean = [l for l in synth.synthetic_vcf(g, arrays, 300, seed=77).split("\n") if l and not l.startswith("#")]
+    rng = np.random.default_rng(5)
+    raw_rows = []
+    for i, l in enumerate(clean):
+        f = l.split("\t")
+        k = int(rng.integers(10))
+        if k == 0:
+            f[6] = "LowQual"
+        elif k == 1:
+            f[4] += ",<DEL>"; f[7] += ",0.2"
+        elif k == 2:
+            f[7] = "AF=" + ",".join("0.004" for _ in f[4].split(","))
+        elif k == 3 and "," not in f[4]:
+            f[4] += "," + ("A" if f[4][0] != "A" else "C") + f[4][1:] + "T"; f[7] += ",0.003"     # second allele below the threshold: dropped, the first kept
+        f[7] = "DP=%d;%s;DB" % (i, f[7])
+        raw_rows.append("\t".join(f + ["GT", "0/1"]))
+    head = "##fileformat=VCFv4.2\n##INFO=<ID=AF,Number=A,Type=Float,Description=\"af\">\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts1\n"
+    raw_text = head + "\n".join(raw_rows) + "\n"
+    open(d / "raw.vcf", "w").write(raw_text)
+    prepared = d / "prepared.vcf.gz"
+    p = run(calitas, "PrepareVcf", "-i", d / "raw.vcf", "-o", prepared, "-d", d / "ref.dict", "-c", "false")
+    assert p.returncode == 0, p.stderr
+    recs = pyoracle.prepare_vcf([raw_text], add_chr_prefix=False)
+    assert 100 < len(recs) < len(clean)
+    exp_vcf = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n" + "".join(
+        "%s\t%s\t%s\t%s\t%s\t%s\tPASS\tAF=%s\n" % (c, pos, vid, ref, ",".join(alts), q, ",".join(afs)) for c, pos, vid, ref, alts, q, afs in recs)
+    out = d / "hits_prepared.tsv"
+    p = run(calitas, "SearchReference", "-i", synth.BASELINE_GUIDE, "-I", "g5", "-r", d / "ref.fa", "-v", prepared, "-o", out, "--time-stamp", "", "--aligner-version", "oracle")
+    assert p.returncode == 0, p.stderr
+    vid = "prepared.vcf.gz:" + hashlib.md5(open(prepared, "rb").read()).hexdigest()
+    exp = lines(pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, guide_id="g5", vcf_text=exp_vcf, vcf_name=vid, assembly="SYN10M", raw=True))
+    got = lines(open(out).read())
+    assert got == exp and any("+variants" in l for l in got)
+
+
 def test_search_reference_cli_guide_batch_and_stdout(calitas, ref_dir):
     d, g, contigs = ref_dir
     gf = d / "guides.tsv"
