@@ -1158,6 +1158,10 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
         counts[2] += n_aln;
         int64_t n_new = 0;
+        if (dedup && n_kept) {      // room for the keepers: at most n_kept here, and the rest of the call projected from the guides done so far
+          const size_t projected = (size_t)((double)(n_out + n_kept) * (double)n_guides / (double)std::max(1, ch.g1) * 1.15) + 4096;
+          if ((size_t)(n_out + n_kept) * sizeof(calitas_hit) > e->out.cap) e->out.ensure_keep(std::max((size_t)(n_out + n_kept), projected) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
+        }
         if (dedup) n_new = run_dedup(e, n_kept, limits->max_overlap, n_out, ch.dedup);
         else if (n_kept) {
           e->out.ensure_keep((size_t)(n_out + n_kept) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
@@ -1171,7 +1175,10 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         if (n_new) {
           if ((size_t)(n_out + n_new) * sizeof(calitas_hit) > pin.cap) {
             dev::stream_sync(cs);
-            PinnedBuf bigger = take_pinned(e, (size_t)(n_out + n_new) * sizeof(calitas_hit) * 3 / 2);
+            // first call on this engine: size the result buffer once from the hits per guide seen so far (page-locking gigabytes is slow,
+            // so growing it chunk by chunk cost seconds); later calls start from the previous call's total
+            const size_t projected = (size_t)((double)(n_out + n_new) * (double)n_guides / (double)std::max(1, ch.g1) * 1.15) + 4096;
+            PinnedBuf bigger = take_pinned(e, std::max((size_t)(n_out + n_new) * 3 / 2, projected) * sizeof(calitas_hit));
             std::memcpy(bigger.p, pin.p, (size_t)n_out * sizeof(calitas_hit));
             e->pinned_pool.push_back(pin); pin = bigger;
           }

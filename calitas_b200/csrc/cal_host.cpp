@@ -117,44 +117,49 @@ GuideSpec make_guide_spec(const GuideDef& g, const Scores& sc, const calitas_lim
   return s;
 }
 
-static std::string cigar_text(const std::string& ops) {
-  std::string out;
-  for (size_t i = 0; i < ops.size();) { size_t j = i; while (j < ops.size() && ops[j] == ops[i]) ++j; out += std::to_string(j - i); out += ops[i]; i = j; }
-  return out;
-}
-
-Rendered render_hit(const calitas_hit& h, const GuideDef& g, const std::string& target_fwd, bool upper_case) {
-  Rendered r;
-  r.guide = g.with_pam(h.pam_idx);
-  std::string t = h.strand == '-' ? revcomp(target_fwd) : target_fwd;
-  if (upper_case) for (auto& c : t) c = (char)std::toupper((unsigned char)c);
+// Allocation-free core of the rendering: every ReferenceHit row goes through it (tens of millions per run), so it works on fixed arrays.
+// `guide` = guide + PAM text in guide orientation (GuideDef::with_pam); `target_fwd` = the hit's bases as stored, forward orientation.
+void render_hit_fix(const calitas_hit& h, const char* guide, int guide_len, const char* target_fwd, int target_len, bool upper_case, RenderedFix& r) {
   static const char kOps[4] = { '=', 'X', 'I', 'D' };
-  std::string ops; size_t qi = 0, ti = 0;
-  for (int k = 0; k < h.n_ops; ++k) {
-    const uint32_t op = ops_get(h.ops, k); ops += kOps[op];
+  const bool neg = h.strand == '-';
+  const int n = h.n_ops;
+  if (n > CALITAS_MAX_OPS) throw std::runtime_error("hit has more alignment columns than CALITAS_MAX_OPS");
+  r.n = n; r.cigar_len = 0; r.unpadded_len = 0;
+  r.mismatches = r.gap_bases = r.guide_mm = r.guide_gaps = r.pam_mm = r.pam_gaps = 0;
+  int qi = 0, ti = 0, run = 0; char run_op = 0;
+  char* pg = r.padded_guide; char* pa = r.padded_alignment; char* pt = r.padded_target;
+  auto flush_run = [&] { if (run) { char tmp[12]; int k = 0, v = run; do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v); while (k) r.cigar[r.cigar_len++] = tmp[--k]; r.cigar[r.cigar_len++] = run_op; } };
+  for (int k = 0; k < n; ++k) {
+    const uint32_t op = ops_get(h.ops, k);
     const bool has_q = op != OP_D, has_t = op != OP_I;
-    if ((has_q && qi >= r.guide.size()) || (has_t && ti >= t.size())) throw std::runtime_error("hit ops do not fit the guide/target");
-    r.padded_guide += has_q ? r.guide[qi++] : '-';
-    r.padded_target += has_t ? t[ti++] : '-';
-    r.padded_alignment += op == OP_EQ ? '|' : (op == OP_X ? '.' : '~');
+    if ((has_q && qi >= guide_len) || (has_t && ti >= target_len)) throw std::runtime_error("hit ops do not fit the guide/target");
+    pg[k] = has_q ? guide[qi++] : '-';
+    if (has_t) {
+      char c = neg ? complement_base(target_fwd[target_len - 1 - ti]) : target_fwd[ti];
+      ++ti;
+      if (upper_case) c = (char)std::toupper((unsigned char)c);
+      pt[k] = c;
+    } else pt[k] = '-';
+    pa[k] = op == OP_EQ ? '|' : (op == OP_X ? '.' : '~');
+    if (kOps[op] != run_op) { flush_run(); run_op = kOps[op]; run = 0; }
+    ++run;
   }
-  if (qi != r.guide.size() || ti != t.size()) throw std::runtime_error("hit ops do not cover the guide/target");
-  r.cigar = cigar_text(ops);
+  flush_run();
+  if (qi != guide_len || ti != target_len) throw std::runtime_error("hit ops do not cover the guide/target");
   // counters of GuideAlignment.scala:99-108,139-163, computed per column
-  const int n = h.n_ops; const std::string& pg = r.padded_guide;
   int first_upper = -1, last_upper = -1;
-  for (int i = 0; i < n; ++i) if (is_upper(pg[(size_t)i])) { if (first_upper < 0) first_upper = i; last_upper = i; }
+  for (int i = 0; i < n; ++i) if (is_upper(pg[i])) { if (first_upper < 0) first_upper = i; last_upper = i; }
   for (int i = 0; i < n; ++i) {
-    const char a = r.padded_alignment[(size_t)i], q = pg[(size_t)i];
+    const char a = pa[i], q = pg[i];
     if (a == '.') { ++r.mismatches; if (is_lower(q)) ++r.pam_mm; else ++r.guide_mm; }
     else if (a == '~') {
       ++r.gap_bases;
       bool in_guide, in_pam;
       if (q != '-') { in_guide = !is_lower(q); in_pam = is_lower(q); }
       else {
-        int lo = i; while (lo > 0 && pg[(size_t)lo] == '-') --lo;
-        int hi = i; while (hi < n - 1 && pg[(size_t)hi] == '-') ++hi;
-        const char prev = pg[(size_t)lo], next = pg[(size_t)hi];
+        int lo = i; while (lo > 0 && pg[lo] == '-') --lo;
+        int hi = i; while (hi < n - 1 && pg[hi] == '-') ++hi;
+        const char prev = pg[lo], next = pg[hi];
         in_guide = (is_alpha(prev) && !is_lower(prev)) || (is_alpha(next) && !is_lower(next));
         in_pam = (prev == '-' || is_lower(prev)) && (next == '-' || is_lower(next));
       }
@@ -164,7 +169,17 @@ Rendered render_hit(const calitas_hit& h, const GuideDef& g, const std::string& 
   }
   r.edits = r.mismatches + r.gap_bases;
   r.guide_mm_plus_gaps = r.guide_mm + r.guide_gaps; r.pam_mm_plus_gaps = r.pam_mm + r.pam_gaps;
-  if (first_upper >= 0) for (int i = first_upper; i <= last_upper; ++i) if (is_alpha(r.padded_target[(size_t)i])) r.unpadded_target_without_pam += r.padded_target[(size_t)i];
+  if (first_upper >= 0) for (int i = first_upper; i <= last_upper; ++i) if (is_alpha(pt[i])) r.unpadded[r.unpadded_len++] = pt[i];
+}
+
+Rendered render_hit(const calitas_hit& h, const GuideDef& g, const std::string& target_fwd, bool upper_case) {
+  Rendered r; RenderedFix f;
+  r.guide = g.with_pam(h.pam_idx);
+  render_hit_fix(h, r.guide.data(), (int)r.guide.size(), target_fwd.data(), (int)target_fwd.size(), upper_case, f);
+  r.padded_guide.assign(f.padded_guide, (size_t)f.n); r.padded_alignment.assign(f.padded_alignment, (size_t)f.n); r.padded_target.assign(f.padded_target, (size_t)f.n);
+  r.cigar.assign(f.cigar, (size_t)f.cigar_len); r.unpadded_target_without_pam.assign(f.unpadded, (size_t)f.unpadded_len);
+  r.mismatches = f.mismatches; r.gap_bases = f.gap_bases; r.edits = f.edits; r.guide_mm = f.guide_mm; r.guide_gaps = f.guide_gaps; r.guide_mm_plus_gaps = f.guide_mm_plus_gaps;
+  r.pam_mm = f.pam_mm; r.pam_gaps = f.pam_gaps; r.pam_mm_plus_gaps = f.pam_mm_plus_gaps;
   return r;
 }
 

@@ -37,6 +37,14 @@ struct Rendered {
   std::string guide, padded_guide, padded_alignment, padded_target, cigar, unpadded_target_without_pam;
   int mismatches = 0, gap_bases = 0, edits = 0, guide_mm = 0, guide_gaps = 0, guide_mm_plus_gaps = 0, pam_mm = 0, pam_gaps = 0, pam_mm_plus_gaps = 0;
 };
+// The same without allocations (fixed arrays, explicit lengths): the ReferenceHit row writer renders tens of millions of hits through it.
+struct RenderedFix {
+  char padded_guide[CALITAS_MAX_OPS], padded_alignment[CALITAS_MAX_OPS], padded_target[CALITAS_MAX_OPS]; int n;
+  char cigar[CALITAS_MAX_OPS * 4]; int cigar_len;
+  char unpadded[CALITAS_MAX_OPS]; int unpadded_len;
+  int mismatches, gap_bases, edits, guide_mm, guide_gaps, guide_mm_plus_gaps, pam_mm, pam_gaps, pam_mm_plus_gaps;
+};
+void render_hit_fix(const calitas_hit& h, const char* guide, int guide_len, const char* target_fwd, int target_len, bool upper_case, RenderedFix& r);
 // `target` = bases [start_offset, end_offset) of the hit in forward orientation (as stored); rendered in guide orientation.
 Rendered render_hit(const calitas_hit& h, const GuideDef& g, const std::string& target_fwd, bool upper_case);
 std::string alignment_header();

@@ -9,6 +9,11 @@
 #include <cstring>
 #include <ctime>
 #include <thread>
+#include <vector>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 namespace cal { namespace io {
@@ -33,10 +38,27 @@ std::string read_file(const std::string& path) {
 
 void write_file(const std::string& path, const char* data, size_t n) {
   if (path.empty() || path == "-" || path == "/dev/stdout") { std::fwrite(data, 1, n, stdout); std::fflush(stdout); return; }
-  FILE* f = std::fopen(path.c_str(), "wb");
-  if (!f) throw IoError{ "Cannot write to path: " + path };
-  const size_t put = std::fwrite(data, 1, n, f);
-  if (std::fclose(f) != 0 || put != n) throw IoError{ "Short write to " + path };
+  const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+  if (fd < 0) throw IoError{ "Cannot write to path: " + path };
+  struct stat st;
+  if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {                      // pipe, /dev/null, ...: sequential writes
+    size_t off = 0; while (off < n) { const ssize_t put = ::write(fd, data + off, n - off); if (put <= 0) { ::close(fd); throw IoError{ "Short write to " + path }; } off += (size_t)put; }
+    ::close(fd); return;
+  }
+  // a 100-guide hit table is ~18 GB: slices go out on several threads (pwrite), a small file on one
+  const size_t SLICE = 64u << 20;
+  const size_t n_slices = (n + SLICE - 1) / SLICE;
+  const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, n_slices), std::max(1u, std::thread::hardware_concurrency())));
+  std::atomic_size_t next(0); std::atomic_bool failed(false);
+  auto work = [&]() {
+    for (;;) {
+      const size_t k = next.fetch_add(1); if (k >= n_slices || failed.load()) return;
+      size_t off = k * SLICE; const size_t stop = std::min(n, off + SLICE);
+      while (off < stop) { const ssize_t put = pwrite(fd, data + off, stop - off, (off_t)off); if (put <= 0) { failed.store(true); return; } off += (size_t)put; }
+    } };
+  std::vector<std::thread> th; for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+  work(); for (auto& t : th) t.join();
+  if (::close(fd) != 0 || failed.load()) throw IoError{ "Short write to " + path };
 }
 
 std::string gunzip_if_needed(const std::string& raw) {
@@ -82,14 +104,33 @@ static void strip_newlines(const char* p, const char* end, std::string& out) {
   }
 }
 
+// The FASTA text: a read-only mapping of a plain regular file (no 3-GB copy; the pages are touched by the stripping threads), else the
+// file's contents read and, if gzip-compressed, inflated.
+struct TextView {
+  const char* data = nullptr; size_t size = 0; std::string owned; void* map = nullptr; size_t map_len = 0;
+  ~TextView() { if (map) munmap(map, map_len); }
+};
+static void open_text(const std::string& path, TextView& v) {
+  const int fd = ::open(path.c_str(), O_RDONLY);
+  if (fd < 0) throw IoError{ "Cannot read non-existent path: " + path };
+  struct stat st; unsigned char magic[2] = { 0, 0 };
+  const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0;
+  if (regular && pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b)) {
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m != MAP_FAILED) { madvise(m, (size_t)st.st_size, MADV_WILLNEED); v.map = m; v.map_len = (size_t)st.st_size; v.data = (const char*)m; v.size = v.map_len; ::close(fd); return; }
+  }
+  ::close(fd);
+  v.owned = gunzip_if_needed(read_file(path)); v.data = v.owned.data(); v.size = v.owned.size();
+}
+
 Genome load_fasta(const std::string& path) {
   Genome g;
   double t0 = now_s();
-  const std::string text = gunzip_if_needed(read_file(path));
+  TextView text; open_text(path, text);
   g.read_s = now_s() - t0; t0 = now_s();
   struct Span { const char* b; const char* e; };
   std::vector<Span> spans;
-  const char* p = text.data(); const char* end = p + text.size();
+  const char* p = text.data; const char* end = p + text.size;
   while (p < end) {
     if (*p != '>') { const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p)); p = nl ? nl + 1 : end; continue; }   // text before the first header
     {
@@ -111,9 +152,11 @@ Genome load_fasta(const std::string& path) {
   if (g.names.empty()) throw IoError{ "No sequences in FASTA: " + path };
   g.seqs.resize(g.names.size());
   {  // contigs are independent: strip line ends on a few threads
-    const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<size_t> order(spans.size()); for (size_t i = 0; i < order.size(); ++i) order[i] = i;                      // longest contig first: the tail of the schedule is short
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return spans[a].e - spans[a].b > spans[b].e - spans[b].b; });
     std::vector<std::thread> th; std::atomic_size_t* next = new std::atomic_size_t(0);
-    auto work = [&]() { for (;;) { const size_t i = next->fetch_add(1); if (i >= spans.size()) return; strip_newlines(spans[i].b, spans[i].e, g.seqs[i]); } };
+    auto work = [&]() { for (;;) { const size_t k = next->fetch_add(1); if (k >= spans.size()) return; const size_t i = order[k]; strip_newlines(spans[i].b, spans[i].e, g.seqs[i]); } };
     for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
     work(); for (auto& t : th) t.join(); delete next;
   }

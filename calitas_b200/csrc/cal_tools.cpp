@@ -99,35 +99,82 @@ Str fetch_bases(const calitas_genome_view& g, int contig, int start1, int end1, 
 
 struct Flanks { bool has[4] = { false, false, false, false }; Str v[4]; };   // left10, right10, left8, right8 in guide orientation
 
-Row make_row(const RowContext& cx, const calitas_hit& h, const Rendered& r, const GuideDef& gd, int contig, int so, int eo, int gso, int geo,
+// ---- the row writer: one pass, no per-field strings (a 100-guide run renders 3 x 10^7 rows) -----------------------------------------
+inline void put_int(Str& out, int v) {
+  char tmp[12]; int k = 0; unsigned u = v < 0 ? 0u - (unsigned)v : (unsigned)v;
+  do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+  if (v < 0) tmp[k++] = '-';
+  char rev[12]; for (int i = 0; i < k; ++i) rev[i] = tmp[k - 1 - i];
+  out.append(rev, (size_t)k);
+}
+// fetch_bases straight into the row: bases [start1, end1] (1-based inclusive), N beyond the contig ends, reverse-complemented for '-', upper case
+inline void put_flank(Str& out, const calitas_genome_view& g, int contig, int start1, int end1, bool rc) {
+  const int64_t len = g.lengths[contig]; const char* b = (const char*)g.bases[contig];
+  char buf[32]; const int n = end1 - start1 + 1;
+  if (n <= 0 || n > 32) { out += fetch_bases(g, contig, start1, end1, rc); return; }
+  for (int i = 0; i < n; ++i) { const int64_t p = (int64_t)start1 + i; buf[i] = (p >= 1 && p <= len) ? b[p - 1] : 'N'; }
+  if (rc) { for (int i = 0; i < n / 2; ++i) { const char t = buf[i]; buf[i] = buf[n - 1 - i]; buf[n - 1 - i] = t; } for (int i = 0; i < n; ++i) buf[i] = complement_base(buf[i]); }
+  for (int i = 0; i < n; ++i) buf[i] = (char)std::toupper((unsigned char)buf[i]);
+  out.append(buf, (size_t)n);
+}
+// Per-guide constants of the 34 columns (ReferenceHit.scala:99-132): columns 1-2 and 28, 30-34.
+struct RowConst {
+  Str head;        // guide_id \t unpadded_guide_sequence \t
+  Str proto_len;   // unpadded_guide_sequence_length
+  Str tail;        // \t aligner \t aligner_version \t aligner_search_pam \t aligner_other_parameters \t time_stamp \n
+  Str build_ref, build_var;
+  std::vector<Str> guide_text;   // guide + PAM per pam index; [n_pams] = PAM-less
+};
+RowConst make_row_const(const RowContext& cx, const GuideDef& gd) {
+  RowConst rc; rc.head = cx.guide_id + "\t" + gd.protospacer + "\t"; rc.proto_len = std::to_string(gd.protospacer.size());
+  Str pams; for (size_t i = 0; i < gd.pams.size(); ++i) { if (i) pams += ','; pams += gd.pams[i]; }                       // ReferenceHit.scala:207
+  rc.tail = "\t" + cx.aligner_id + "\t" + cx.version + "\t" + pams + "\t" + cx.arguments + "\t" + cx.time_stamp + "\n";
+  const calitas_genome_view& g = *cx.genome;
+  rc.build_ref = (g.assembly && g.assembly[0]) ? g.assembly : "unknown"; rc.build_var = rc.build_ref + "+variants";
+  for (size_t i = 0; i < gd.pams.size(); ++i) rc.guide_text.push_back(gd.with_pam((int)i));
+  rc.guide_text.push_back(gd.with_pam(-1));
+  return rc;
+}
+const Str& guide_text_of(const RowConst& rc, int pam_idx) { return pam_idx >= 0 ? rc.guide_text[(size_t)pam_idx] : rc.guide_text.back(); }
+
+// Appends one ReferenceHit line (ReferenceHit.scala:210-254).  `var` = variant columns (id, description, vcf, allele frequency), or NULL.
+void write_row(Str& out, const RowContext& cx, const RowConst& rc, const GuideDef& gd, const calitas_hit& h, const RenderedFix& r, int contig, int so, int eo, int gso, int geo,
+               const Str* var /* [4] */, const Flanks& fl) {
+  const calitas_genome_view& g = *cx.genome;
+  const bool neg = h.strand == '-';
+  out += rc.head; out += var ? rc.build_var : rc.build_ref; out += '\t'; out += g.names[contig]; out += '\t'; put_int(out, gso); out += '\t'; put_int(out, geo); out += '\t';
+  out += (char)h.strand; out += '\t'; out.append(r.unpadded, (size_t)r.unpadded_len); out += '\t';
+  // ten bases 5' / 3' of the protospacer span, eight of the full span, in guide orientation (ReferenceHit.scala:226-249)
+  if (fl.has[0]) out += fl.v[0]; else if (neg) put_flank(out, g, contig, geo + 1, geo + 10, true); else put_flank(out, g, contig, gso + 1 - 10, gso, false);
+  out += '\t';
+  if (fl.has[1]) out += fl.v[1]; else if (neg) put_flank(out, g, contig, gso + 1 - 10, gso, true); else put_flank(out, g, contig, geo + 1, geo + 10, false);
+  out += '\t';
+  if (h.pam_idx >= 0) out += gd.pams[(size_t)h.pam_idx];
+  out += '\t';
+  if (var) { out += var[0]; out += '\t'; out += var[1]; out += '\t'; out += var[2]; out += '\t'; out += var[3]; out += '\t'; } else out.append("\t\t\t\t", 4);
+  put_int(out, h.score); out += '\t'; put_int(out, r.guide_mm); out += '\t'; put_int(out, r.guide_gaps); out += '\t'; put_int(out, r.guide_mm_plus_gaps); out += '\t';
+  put_int(out, r.pam_mm); out += '\t'; put_int(out, r.edits); out += '\t';
+  out.append(r.padded_guide, (size_t)r.n); out += '\t'; out.append(r.padded_alignment, (size_t)r.n); out += '\t'; out.append(r.padded_target, (size_t)r.n); out += '\t';
+  if (fl.has[2]) out += fl.v[2]; else if (neg) put_flank(out, g, contig, eo + 1, eo + 8, true); else put_flank(out, g, contig, so + 1 - 8, so, false);
+  out += '\t';
+  if (fl.has[3]) out += fl.v[3]; else if (neg) put_flank(out, g, contig, so + 1 - 8, so, true); else put_flank(out, g, contig, eo + 1, eo + 8, false);
+  out += '\t';
+  out.append(r.cigar, (size_t)r.cigar_len); out += '\t'; out += rc.proto_len; out += '\t'; put_int(out, r.unpadded_len); out += rc.tail;
+}
+
+// A row with what removeOverlaps / sort on the host need (VCF runs only: variant-window hits are merged with reference hits there).
+Row make_row(const RowContext& cx, const RowConst& rc, const calitas_hit& h, const RenderedFix& r, const GuideDef& gd, int contig, int so, int eo, int gso, int geo,
              const std::vector<VariantAllele>& variants, const Flanks& fl) {
   const calitas_genome_view& g = *cx.genome;
   std::vector<const VariantAllele*> vs;
   for (auto& v : variants) if (v.pos - 1 >= so && v.pos - 1 <= eo) vs.push_back(&v);       // ReferenceHit.scala:211
-  const bool neg = h.strand == '-';
-  auto ten_left = [&] { return fetch_bases(g, contig, gso + 1 - 10, gso, neg); };
-  auto ten_right = [&] { return fetch_bases(g, contig, geo + 1, geo + 10, neg); };
-  auto eight_left = [&] { return fetch_bases(g, contig, so + 1 - 8, so, neg); };
-  auto eight_right = [&] { return fetch_bases(g, contig, eo + 1, eo + 8, neg); };
-  Str build = (g.assembly && g.assembly[0]) ? g.assembly : "unknown";
-  if (!vs.empty()) build += "+variants";
-  Str pam_used; for (char c : r.guide) if (c >= 'a' && c <= 'z') pam_used += c;
-  Str vid, vdesc; float min_af = 0;
-  for (size_t i = 0; i < vs.size(); ++i) { if (i) { vid += ';'; vdesc += ';'; } vid += vs[i]->id; vdesc += variant_display(*vs[i]); if (i == 0 || vs[i]->af < min_af) min_af = vs[i]->af; }
-  auto I = [](int v) { return std::to_string(v); };
-  std::vector<Str> f = {
-    cx.guide_id, gd.protospacer, build, g.names[contig], I(gso), I(geo), Str(1, (char)h.strand), r.unpadded_target_without_pam,
-    fl.has[0] ? fl.v[0] : (neg ? ten_right() : ten_left()), fl.has[1] ? fl.v[1] : (neg ? ten_left() : ten_right()),
-    pam_used, vid, vdesc, (!vs.empty() && cx.has_vcf) ? cx.vcf_id : Str(), vs.empty() ? Str() : format_af((double)min_af),
-    I(h.score), I(r.guide_mm), I(r.guide_gaps), I(r.guide_mm_plus_gaps), I(r.pam_mm), I(r.edits), r.padded_guide, r.padded_alignment, r.padded_target,
-    fl.has[2] ? fl.v[2] : (neg ? eight_right() : eight_left()), fl.has[3] ? fl.v[3] : (neg ? eight_left() : eight_right()),
-    r.cigar, I((int)gd.protospacer.size()), I((int)r.unpadded_target_without_pam.size()), cx.aligner_id, cx.version, Str(), cx.arguments, cx.time_stamp };
-  { Str pams; for (size_t i = 0; i < gd.pams.size(); ++i) { if (i) pams += ','; pams += gd.pams[i]; } f[31] = pams; }   // ReferenceHit.scala:207
+  Str var[4]; float min_af = 0;
+  for (size_t i = 0; i < vs.size(); ++i) { if (i) { var[0] += ';'; var[1] += ';'; } var[0] += vs[i]->id; var[1] += variant_display(*vs[i]); if (i == 0 || vs[i]->af < min_af) min_af = vs[i]->af; }
+  if (!vs.empty()) { if (cx.has_vcf) var[2] = cx.vcf_id; var[3] = format_af((double)min_af); }
   Row row; row.contig = contig; row.start = gso; row.strand = (char)h.strand; row.score = h.score;
   row.sweep_end = gso + (h.end_offset - h.start_offset) - 1;           // ReferenceHit.scala:135-138 (cigar.lengthOnTarget is window-relative span)
-  row.key = Str("{") + g.names[contig] + ":" + (char)h.strand + ":" + vdesc;
-  for (size_t i = 0; i < f.size(); ++i) { if (i) row.line += '\t'; row.line += f[i]; }
-  row.line += '\n';
+  row.key = Str("{") + g.names[contig] + ":" + (char)h.strand + ":" + var[1];
+  write_row(row.line, cx, rc, gd, h, r, contig, so, eo, gso, geo, vs.empty() ? nullptr : var, fl);
   return row;
 }
 
@@ -407,6 +454,8 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
     if (opt->chrom && opt->chrom[0]) { chrom_idx = contig_index(*genome, opt->chrom); if (chrom_idx < 0) bad(Str("Unknown chromosome: ") + opt->chrom); }
     const bool with_vcf = opt->vcf_text != nullptr;
     std::vector<std::vector<Row>> rows((size_t)n_guides);
+    std::vector<RowConst> rcs; for (int g = 0; g < n_guides; ++g) rcs.push_back(make_row_const(cxs[(size_t)g], defs[(size_t)g]));
+    const int64_t ROW_BLOCK = 2048; std::vector<std::vector<Str>> row_text((size_t)n_guides); int64_t n_final = 0;      // plain runs: rendered text blocks per guide
     PhaseTimer pt;
     // every engine's work runs on its own host thread; errors travel back as (code, message)
     auto run_all = [&](const std::function<void(int)>& job) {
@@ -425,14 +474,24 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
       for (int g = 0; g < n_guides; ++g) {
         std::vector<const calitas_hit*> order;                    // this guide's hits: shard 0's, then shard 1's, ... = ReferenceHit.sort order
         for (int s = 0; s < n_engines; ++s) { int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s]; for (; i < h_.n() && h_.data()[i].guide_idx == g; ++i) order.push_back(h_.data() + i); }
-        std::vector<Row>& out = rows[(size_t)g]; out.resize(order.size());
-        const GuideDef& gd = defs[(size_t)g]; const RowContext& cx = cxs[(size_t)g];
-        parallel_for((int64_t)order.size(), 2048, [&](int64_t b, int64_t e_) {
+        const GuideDef& gd = defs[(size_t)g]; const RowContext& cx = cxs[(size_t)g]; const RowConst& rc = rcs[(size_t)g];
+        // without a VCF the device has already de-duplicated and sorted: rows are final, rendered straight into text blocks of ROW_BLOCK rows
+        std::vector<Row>& out = rows[(size_t)g]; if (with_vcf) out.resize(order.size());
+        std::vector<Str>& blocks = row_text[(size_t)g]; if (!with_vcf) blocks.resize((order.size() + ROW_BLOCK - 1) / ROW_BLOCK);
+        n_final += with_vcf ? 0 : (int64_t)order.size();
+        auto render = [&](int64_t b, int64_t e_, Str* blk) {
+          if (blk) blk->reserve((size_t)(e_ - b) * 640);
+          RenderedFix r;
           for (int64_t k = b; k < e_; ++k) {
             const calitas_hit& h = *order[(size_t)k];
-            Rendered r = render_hit(h, gd, contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), true);     // windows are upper-cased, SearchReference.scala:67
-            out[(size_t)k] = make_row(cx, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none);
-          } });
+            const Str& gt = guide_text_of(rc, h.pam_idx);
+            render_hit_fix(h, gt.data(), (int)gt.size(), (const char*)genome->bases[h.contig_idx] + h.start_offset, h.end_offset - h.start_offset, true, r);   // windows are upper-cased, SearchReference.scala:67
+            if (blk) write_row(*blk, cx, rc, gd, h, r, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, nullptr, none);
+            else out[(size_t)k] = make_row(cx, rc, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none);
+          } };
+        const int64_t n_rows = (int64_t)order.size();
+        if (with_vcf) parallel_for(n_rows, ROW_BLOCK, [&](int64_t b, int64_t e_) { render(b, e_, nullptr); });
+        else parallel_for((int64_t)blocks.size(), 1, [&](int64_t bb, int64_t be) { for (int64_t k = bb; k < be; ++k) render(k * ROW_BLOCK, std::min(n_rows, (k + 1) * ROW_BLOCK), &blocks[(size_t)k]); });
       }
       for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "hit set is not guide-major" };
       pt.lap("reference rows");
@@ -468,7 +527,8 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
           const VariantWindow& w = ws[wi]; const GuideDef& gd = defs[(size_t)g];
           for (; i < h_.n() && h_.data()[i].task_idx == t; ++i) {
             const calitas_hit& h = h_.data()[i];
-            Rendered r = render_hit(h, gd, w.bases.substr((size_t)h.start_offset, (size_t)(h.end_offset - h.start_offset)), false);
+            const Str& gt = guide_text_of(rcs[(size_t)g], h.pam_idx);
+            RenderedFix r; render_hit_fix(h, gt.data(), (int)gt.size(), w.bases.data() + h.start_offset, h.end_offset - h.start_offset, false, r);
             const int wl = (int)w.bases.size();
             Flanks raw;   // window-orientation flanks (:599-602)
             if (h.guide_start_offset >= 10) { raw.has[0] = true; raw.v[0] = w.bases.substr((size_t)h.guide_start_offset - 10, 10); }
@@ -482,7 +542,7 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
             }
             const int so = w.ref_offset_at(h.start_offset, true), eo = w.ref_offset_at(h.end_offset, false);             // :615-620
             const int gso = w.ref_offset_at(h.guide_start_offset, true), geo = w.ref_offset_at(h.guide_end_offset, false);
-            rows[(size_t)g].push_back(make_row(cxs[(size_t)g], h, r, gd, w.contig, so, eo, gso, geo, w.alleles, fl));
+            rows[(size_t)g].push_back(make_row(cxs[(size_t)g], rcs[(size_t)g], h, r, gd, w.contig, so, eo, gso, geo, w.alleles, fl));
           }
         } }
       for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "variant hit set is not task-major" };
@@ -493,12 +553,16 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
       }
       pt.lap("removeOverlaps + sort (host)");
     }
-    const Str header = hit_header(); int64_t total = 0; size_t bytes = header.size();
+    const Str header = hit_header(); int64_t total = n_final; size_t bytes = header.size();
     for (auto& v : rows) { for (auto& r : v) bytes += r.line.size(); total += (int64_t)v.size(); }
+    std::vector<Str*> blocks; std::vector<size_t> at;                                                                    // text blocks of the plain run, in table order
+    for (auto& v : row_text) for (auto& b : v) { blocks.push_back(&b); at.push_back(bytes); bytes += b.size(); }
     char* text = (char*)std::malloc(bytes + 1); if (!text) throw ToolError{ CALITAS_ESTATE, "out of memory for the hit table" };
     char* w = text; std::memcpy(w, header.data(), header.size()); w += header.size();
     for (auto& v : rows) for (auto& r : v) { std::memcpy(w, r.line.data(), r.line.size()); w += r.line.size(); }
-    *w = 0;
+    parallel_for((int64_t)blocks.size(), 16, [&](int64_t b, int64_t e_) { for (int64_t k = b; k < e_; ++k) { Str& s = *blocks[(size_t)k]; std::memcpy(text + at[(size_t)k], s.data(), s.size()); Str().swap(s); } });
+    text[bytes] = 0;
+    pt.lap("table assembly");
     if (n_hits) *n_hits = total;
     *out_tsv = text;
     return CALITAS_OK;
@@ -557,9 +621,12 @@ int calitas_tool_align_to_reference(calitas_engine* e, const calitas_reference* 
           if (best) alns.resize(1);
           const GuideDef& gd = defs[(size_t)rt[(size_t)t].guide_idx];
           RowContext c2 = cx; c2.guide_id = tasks[s0 + t].id ? tasks[s0 + t].id : tasks[s0 + t].query;    // :100
+          const RowConst rc = make_row_const(c2, gd);
+          RenderedFix r;
           for (auto& h : alns) {
-            Rendered r = render_hit(h, gd, contig_slice(*genome, h.contig_idx, h.start_offset, h.end_offset), false);   // region is not upper-cased (SequentialGuideAligner.scala:374)
-            task_rows[(size_t)t].push_back(make_row(c2, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none));
+            const Str& gt = guide_text_of(rc, h.pam_idx);
+            render_hit_fix(h, gt.data(), (int)gt.size(), (const char*)genome->bases[h.contig_idx] + h.start_offset, h.end_offset - h.start_offset, false, r);   // region is not upper-cased (SequentialGuideAligner.scala:374)
+            task_rows[(size_t)t].push_back(make_row(c2, rc, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none));
           }
         } });
       for (int64_t b0 = 0; b0 < nt; b0 += 10000) {                                                     // ReferenceHit.sort per batch of 10 000 input rows (:110,141)
