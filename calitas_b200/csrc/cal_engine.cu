@@ -507,27 +507,28 @@ CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const calitas_hit* hits, cons
   if (s >= n || !flag[s]) return;
   out[pos[s]] = hits[perm[s]]; out_owned[pos[s]] = slot_owned[s];
 }
-CAL_KERNEL __launch_bounds__(256) k_gather(const calitas_hit* hits, const uint32_t* idx, int64_t n, calitas_hit* out) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < n) out[s] = hits[idx[s]];
-}
 
 // ------------------------------------------------------------------------------------------------------------------------------------
 // dedup: removeOverlaps (SearchReference.scala:653-675) + ReferenceHit.sort (ReferenceHit.scala:276-287)
 // ------------------------------------------------------------------------------------------------------------------------------------
-// key1 = guide (relative to the chunk) | contig | strand | coordinate_start, each field only as wide as the call needs (38 bits for a
-// 16-guide chunk on hg38 instead of 64: 5 radix passes instead of 8); keyA = score_hi - score in score_bits bits.  Arrival order is the
-// array index.  A value outside its field would mis-sort silently, so it raises *overflow, which the host reads with the sweep's counters.
-struct DedupLayout { int32_t start_bits, contig_shift, guide_shift, bits, g0, score_hi, score_bits; };
-CAL_KERNEL __launch_bounds__(256) k_dedup_keys(const calitas_hit* hits, int64_t n, DedupLayout L, uint64_t* key1, uint64_t* keyA, uint32_t* idx, uint32_t* overflow) {
+// Sort key = guide (relative to the chunk) | contig | coordinate_start | strand | score_hi - score, each field only as wide as the call needs
+// (49 bits for a 16-guide chunk on hg38 with the default costs).  ONE stable radix sort over it yields the order
+// (guide, contig, start, strand, -score, arrival): that is ReferenceHit.sort's order already, and within it the hits of one
+// (guide, contig, strand) group -- what removeOverlaps sweeps -- appear by (start, -score, arrival), interleaved with the other strand's.
+// So the sweep runs the two strands' chains side by side and no second sort follows.  When the fields do not fit 64 bits (not reachable with
+// real genomes and costs) the score goes into keyA instead and two stable sorts give the same order.  Arrival order is the array index.
+// A value outside its field would mis-sort silently, so it raises *overflow, which the host reads with the sweep's counters.
+struct DedupLayout { int32_t start_bits, contig_shift, guide_shift, bits /* without the score */, g0, score_hi, score_bits, merged; };
+CAL_KERNEL __launch_bounds__(256) k_dedup_keys(const calitas_hit* hits, int64_t n, DedupLayout L, uint64_t* key, uint64_t* keyA, uint32_t* idx, uint32_t* overflow) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const calitas_hit& h = hits[i];
   const int64_t start = h.guide_start_offset, sc = (int64_t)L.score_hi - h.score, g = (int64_t)h.guide_idx - L.g0, c = h.contig_idx;
   if (start < 0 || (start >> L.start_bits) != 0 || sc < 0 || (sc >> L.score_bits) != 0 || g < 0 || c < 0 ||
       (uint64_t)c >= (1ull << (L.guide_shift - L.contig_shift)) || (L.bits < 64 && ((uint64_t)g >> (L.bits - L.guide_shift)) != 0)) *overflow = 1u;
-  key1[i] = ((uint64_t)g << L.guide_shift) | ((uint64_t)c << L.contig_shift) | ((uint64_t)(h.strand == '-' ? 1u : 0u) << L.start_bits) | (uint64_t)start;
-  keyA[i] = (uint64_t)sc;
+  const uint64_t k = ((uint64_t)g << L.guide_shift) | ((uint64_t)c << L.contig_shift) | ((uint64_t)start << 1) | (uint64_t)(h.strand == '-' ? 1u : 0u);
+  if (L.merged) key[i] = (k << L.score_bits) | (uint64_t)sc;
+  else { key[i] = k; keyA[i] = (uint64_t)sc; }
   idx[i] = (uint32_t)i;
 }
 CAL_KERNEL __launch_bounds__(256) k_gather_u64(const uint64_t* in, const uint32_t* idx, int64_t n, uint64_t* out) {
@@ -544,33 +545,36 @@ CAL_HD int32_t soa_overlap(const int32_t* s_start, const int32_t* s_end, int64_t
   const int32_t hi = s_end[a] < s_end[b] ? s_end[a] : s_end[b], lo = s_start[a] > s_start[b] ? s_start[a] : s_start[b];
   const int32_t o = hi - lo; return o > 0 ? o : 0;
 }
-// One thread per sweep segment.  With segmented != 0 (max_overlap >= 1) a segment starts at a group boundary or where the next hit starts
-// more than CALITAS_MAX_OPS bases after its predecessor: no earlier hit can then overlap it at all, so the reference's sequential sweep
-// restarts there unconditionally and segments are independent.  With max_overlap <= 0 every later hit "overlaps" (>= 0) and the sweep is
-// run per group, as the reference's loop would.
-CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key1, const int32_t* s_start, const int32_t* s_end, const int32_t* s_score, const uint8_t* s_owned, int64_t n, int32_t max_overlap,
-                                          int32_t segmented, int32_t gshift /* key1 >> gshift = (guide, contig, strand) */, uint32_t* keep) {
+// One thread per sweep segment of a (guide, contig) run of the sorted list.  The two strands are separate removeOverlaps groups
+// (SearchReference.scala:656) whose hits interleave here by start, so the thread keeps one "current hit" per strand.  Per strand the
+// reference's loop (:662-672) is: take cur; skip the following hits while they overlap cur by >= max_overlap and score no more; the hit that
+// ends the skipping decides cur (kept iff it overlaps cur by < max_overlap, or there is none) and becomes the next cur.
+// With segmented != 0 (max_overlap >= 1) a segment also starts where a hit begins more than CALITAS_MAX_OPS bases after its predecessor in the
+// list: no earlier hit of either strand can then overlap it at all, so both chains restart there unconditionally and segments are
+// independent.  With max_overlap <= 0 every later hit "overlaps" (>= 0) and a (guide, contig) run is swept by one thread.
+CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key, const int32_t* s_start, const int32_t* s_end, const int32_t* s_score, const uint8_t* s_owned, int64_t n, int32_t max_overlap,
+                                          int32_t segmented, int32_t strand_shift /* bit of the strand; the (guide, contig) run is key >> (strand_shift + 1 + start_bits) */, int32_t start_bits,
+                                          uint32_t* keep) {
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i0 >= n) return;
-  const uint64_t grp = key1[i0] >> gshift;
-  if (i0 > 0 && (key1[i0 - 1] >> gshift) == grp && !(segmented && s_start[i0] - s_start[i0 - 1] > CALITAS_MAX_OPS)) return;
-  int64_t i = i0;
-  for (;;) {
-    const int64_t cur = i++;
-    while (i < n && (key1[i] >> gshift) == grp && soa_overlap(s_start, s_end, i, cur) >= max_overlap && s_score[i] <= s_score[cur]) { keep[i] = 0; ++i; }
-    const bool has_next = i < n && (key1[i] >> gshift) == grp;
-    keep[cur] = ((!has_next || soa_overlap(s_start, s_end, i, cur) < max_overlap) && s_owned[cur]) ? 1u : 0u;   // halo hits take part, are never reported
-    if (!has_next) break;
-    if (segmented && s_start[i] - s_start[i - 1] > CALITAS_MAX_OPS) break;                                       // next segment has its own thread
+  const int gshift = strand_shift + 1 + start_bits;
+  const uint64_t grp = key[i0] >> gshift;
+  if (i0 > 0 && (key[i0 - 1] >> gshift) == grp && !(segmented && s_start[i0] - s_start[i0 - 1] > CALITAS_MAX_OPS)) return;
+  int64_t cur[2] = { -1, -1 };
+  for (int64_t i = i0; i < n; ++i) {
+    if (i > i0 && ((key[i] >> gshift) != grp || (segmented && s_start[i] - s_start[i - 1] > CALITAS_MAX_OPS))) break;
+    const int st = (int)((key[i] >> strand_shift) & 1ull);
+    const int64_t c = cur[st];
+    if (c < 0) cur[st] = i;
+    else if (soa_overlap(s_start, s_end, i, c) >= max_overlap && s_score[i] <= s_score[c]) keep[i] = 0;
+    else { keep[c] = (soa_overlap(s_start, s_end, i, c) < max_overlap && s_owned[c]) ? 1u : 0u; cur[st] = i; }      // halo hits take part, are never reported
   }
+  for (int st = 0; st < 2; ++st) if (cur[st] >= 0) keep[cur[st]] = s_owned[cur[st]] ? 1u : 0u;
 }
-// compaction of (idx, key) by keep; key is rewritten to the final sort key guide | contig | coordinate_start | strand
-CAL_KERNEL __launch_bounds__(256) k_compact_keepers(const uint64_t* key1, const uint32_t* idx, const uint32_t* keep, const uint32_t* pos, int64_t n, int32_t start_bits, uint64_t* key3, uint32_t* idx_out) {
+// out[pos[i]] = hits[idx[i]] for the keepers: the sorted order is the final order
+CAL_KERNEL __launch_bounds__(256) k_gather_keepers(const calitas_hit* hits, const uint32_t* idx, const uint32_t* keep, const uint32_t* pos, int64_t n, calitas_hit* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !keep[i]) return;
-  const uint64_t k = key1[i], lo = (1ull << start_bits) - 1;
-  key3[pos[i]] = ((k >> (start_bits + 1)) << (start_bits + 1)) | ((k & lo) << 1) | ((k >> start_bits) & 1ull);
-  idx_out[pos[i]] = idx[i];
+  if (i < n && keep[i]) out[pos[i]] = hits[idx[i]];
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------------
@@ -799,23 +803,31 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   return n_kept;
 }
 
-// removeOverlaps + final sort over e->kept[0..n) -> appended to e->out at out_n; returns number of keepers.
+// removeOverlaps + ReferenceHit.sort over e->kept[0..n) -> appended to e->out at out_n; returns number of keepers.
 int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out_n, const DedupLayout& L) {
   dev::Stream s = e->stream;
   if (n == 0) return 0;
   if (n >= (1ll << 32)) throw LimitExceeded("too many hits in one batch");
   const calitas_hit* hits = e->kept.as<calitas_hit>();
-  e->key1.ensure((size_t)n * 8); e->keyA.ensure((size_t)n * 8); e->key_b.ensure((size_t)n * 8); e->idx.ensure((size_t)n * 4); e->idx2.ensure((size_t)n * 4);
-  CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + 7)); dev::launch_check("k_dedup_keys"); ++e->launches;
+  e->key1.ensure((size_t)n * 8); e->keyA.ensure((size_t)n * 8); e->idx.ensure((size_t)n * 4); e->idx2.ensure((size_t)n * 4);
   size_t tb = dev::sort_pairs_u64_tmp((size_t)n, 0, 64); e->tmp.ensure(tb);
-  // stable by -score (arrival order = index order), then stable by (guide, contig, strand, start)
-  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, L.score_bits, s); ++e->launches;
-  CAL_LAUNCH(k_gather_u64, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), n, e->keyA.as<uint64_t>()); dev::launch_check("k_gather_u64"); ++e->launches;
-  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)n, 0, L.bits, s); ++e->launches;
-  // now key1[i], idx[i] sorted by (guide, contig, strand, start, -score, arrival)
+  const uint64_t* skey; const uint32_t* sidx; int strand_shift;
+  if (L.merged) {
+    CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->keyA.as<uint64_t>(), (uint64_t*)nullptr, e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + 7)); dev::launch_check("k_dedup_keys"); ++e->launches;
+    dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, L.bits + L.score_bits, s); ++e->launches;
+    skey = e->key1.as<uint64_t>(); sidx = e->idx2.as<uint32_t>(); strand_shift = L.score_bits;
+  } else {      // stable by -score (arrival order = index order), then stable by (guide, contig, start, strand)
+    e->key_b.ensure((size_t)n * 8);
+    CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + 7)); dev::launch_check("k_dedup_keys"); ++e->launches;
+    dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, L.score_bits, s); ++e->launches;
+    CAL_LAUNCH(k_gather_u64, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), n, e->keyA.as<uint64_t>()); dev::launch_check("k_gather_u64"); ++e->launches;
+    dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)n, 0, L.bits, s); ++e->launches;
+    skey = e->key1.as<uint64_t>(); sidx = e->idx.as<uint32_t>(); strand_shift = 0;
+  }
+  // skey[i], sidx[i] sorted by (guide, contig, start, strand, -score, arrival)
   e->sstart.ensure((size_t)n * 4); e->send.ensure((size_t)n * 4); e->sscore.ensure((size_t)n * 4); e->sowned.ensure((size_t)n); e->flag.ensure((size_t)n * 4); e->pos.ensure((size_t)n * 4);
-  CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, hits, e->kept_owned.as<uint8_t>(), e->idx.as<uint32_t>(), n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
-  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, e->key1.as<uint64_t>(), e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, max_overlap, max_overlap >= 1 ? 1 : 0, L.start_bits, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
+  CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, hits, e->kept_owned.as<uint8_t>(), sidx, n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
+  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, skey, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, max_overlap, max_overlap >= 1 ? 1 : 0, strand_shift, L.start_bits, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
   tb = dev::exclusive_sum_u32_tmp((size_t)n); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n, s); ++e->launches;
   uint32_t last_pos = 0, last_flag = 0;
@@ -825,11 +837,8 @@ int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out
   if (e->h_count[7]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in removeOverlaps");
   const int64_t nk = (int64_t)last_pos + last_flag;
   if (nk == 0) return 0;
-  CAL_LAUNCH(k_compact_keepers, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n, L.start_bits, e->keyA.as<uint64_t>(), e->idx2.as<uint32_t>()); dev::launch_check("k_compact_keepers"); ++e->launches;
-  tb = dev::sort_pairs_u64_tmp((size_t)nk, 0, 64); e->tmp.ensure(tb);
-  dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)nk, 0, L.bits, s); ++e->launches;
   e->out.ensure_keep((size_t)(out_n + nk) * sizeof(calitas_hit), (size_t)out_n * sizeof(calitas_hit), s);
-  CAL_LAUNCH(k_gather, blocks_for(nk, 256), 256, 0, s, 1, hits, e->idx.as<uint32_t>(), nk, e->out.as<calitas_hit>() + out_n); dev::launch_check("k_gather"); ++e->launches;
+  CAL_LAUNCH(k_gather_keepers, blocks_for(n, 256), 256, 0, s, 1, hits, sidx, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n, e->out.as<calitas_hit>() + out_n); dev::launch_check("k_gather_keepers"); ++e->launches;
   return nk;
 }
 
@@ -1079,7 +1088,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       {   // removeOverlaps sort keys: field widths from the reference and the chunk; score bounds from the guides' thresholds and costs
         DedupLayout& D = ch.dedup; const Scores& sc = e->sc;
         int64_t max_len = 1; for (int64_t l : ref->len) max_len = std::max(max_len, l);
-        D.start_bits = std::min(31, bit_length((uint64_t)max_len)); D.contig_shift = D.start_bits + 1;
+        D.start_bits = std::min(31, bit_length((uint64_t)max_len)); D.contig_shift = D.start_bits + 1;        // bit 0 = strand, then the start
         D.guide_shift = D.contig_shift + bit_length((uint64_t)(ref->len.size() - 1)); D.g0 = g0; D.bits = D.guide_shift + bit_length((uint64_t)(g1 - g0 - 1));
         // a hit's score = guide alignment (min_score ... lp rows each worth at most a match or an inserted base) + PAM bases + offset * queryGap
         int64_t hi = 0, lo = 0; bool first = true;
@@ -1095,6 +1104,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         }
         if (hi - lo >= (1ll << 31) || hi > 0x7FFFFFFFll || hi < -0x7FFFFFFFll) { D.score_hi = 0x7FFFFFFF; D.score_bits = 33; }   // 0x7FFFFFFF - score fits 33 bits for any int32 score
         else { D.score_hi = (int32_t)hi; D.score_bits = std::max(1, bit_length((uint64_t)(hi - lo))); }
+        D.merged = (D.bits + D.score_bits <= 64 && !std::getenv("CALITAS_DEDUP_TWO_SORTS")) ? 1 : 0;      // the variable forces the wide-key path in tests
       }
       ch.bases = 0; for (size_t t = ch.t_begin; t < t_end; ++t) ch.bases += (int64_t)(ch.ts->tiles[t].nwin - 1) * ch.step + window_size;
       chunks.push_back(ch);
