@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 # ALU pipe 7 LOP3 + 2 LEA.HI + 0.5 VIMNMX3; FMA pipe 3.5 IMAD.IADD; LSU 1 LDS + 0.5 LDS.U8.
 ALU_OPS_PER_COLUMN = 9.5
 ISSUE_SLOTS_PER_COLUMN = 14.5
-NCU_DRAM_OVER_ALGORITHMIC = 404.0 / 386.0   # k_scan_tiled, profiles/r01d_summary.txt
+NCU_DRAM_OVER_ALGORITHMIC = 406.4 / 386.2   # k_scan_tiled, profiles/r01f_summary.txt
 REF_OPS_PER_BP_GUIDE = 240   # 2 strands x 20 rows x 6 int32 ops of the reference's recurrence
 
 
@@ -216,7 +216,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("CALITAS_BENCH_BIND", "1") != "0" else None
+    if os.environ.get("CALITAS_BENCH_VERBOSE"):
+        print("[bench] rank %d cpus %s" % (rank, sorted(os.sched_getaffinity(0))), file=sys.stderr)
     if world > 1:
         # NCCL prints its version banner on stdout when the first communicator comes up; the contract is ONE JSON line on stdout,
         # so stdout is pointed at stderr while the process group initialises.
@@ -336,7 +338,7 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "k_scan_tiled", "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                          "traffic": alg_bytes * NCU_DRAM_OVER_ALGORITHMIC, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                         "(profiles/r01d_summary.txt: 387.1 + 16.9 = 404.0 MB for 386.0 MB algorithmic), scaled to this launch's algorithmic bytes", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                         "(profiles/r01f_summary.txt: 388.2 + 18.1 = 406.4 MB for 386.2 MB algorithmic), scaled to this launch's algorithmic bytes", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "streaming read of the 4-bit packed shard once per launch; the kernel is integer-ALU-bound (see roofline_int), so the HBM fraction is small by design",
                          "avg_launch_ms": scan_launch_ms, "launches_per_step": launches, "share_of_step": st["ms_scan"] / st["ms_total"]},
             "roofline_int": {"kernel": "k_scan_tiled", "bound": "int_alu_pipe", "achieved": int_achieved, "peak": int_peaks["alu_lop3"], "unit": "Tiop/s (ALU-pipe thread instructions)",
