@@ -141,6 +141,44 @@ def test_search_reference_variants_of_the_call(eng, small_genome, guide, aux, kw
     assert got == exp
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(O=0), dict(O=1), dict(d=6, g=2), dict(window_size=200, O=25)])
+def test_search_reference_repeats_on_both_strands(eng, kw):
+    """Dense, overlapping hits on both strands: tandem copies of the target (guide + PAM), some edited, and of its reverse complement, packed
+    closer than an alignment is long.  Stresses the per-window overlap filter, the two-strand removeOverlaps sweep (chains interleave by start,
+    equal starts on both strands occur), sort ties and traceback choices in repeats."""
+    rng = np.random.default_rng(11)
+    site = "CTTGCCCCACAGGGCAGTAA"
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    def edited(s):
+        s = list(s)
+        for _ in range(int(rng.integers(0, 3))):
+            i = int(rng.integers(len(s)))
+            r = rng.random()
+            if r < 0.5:
+                s[i] = "ACGT"[int(rng.integers(4))]
+            elif r < 0.75:
+                del s[i]
+            else:
+                s.insert(i, "ACGT"[int(rng.integers(4))])
+        return "".join(s)
+    contigs = []
+    for c in range(3):
+        parts = ["".join("ACGT"[i] for i in rng.integers(0, 4, 40))]
+        for _ in range(120):
+            unit = edited(site) + ["AGG", "TGG", "CAG", "GGG", "TGA"][int(rng.integers(5))]
+            if rng.random() < 0.5:
+                unit = "".join(comp[b] for b in reversed(unit))
+            parts.append(unit)
+            parts.append("".join("ACGT"[i] for i in rng.integers(0, 4, int(rng.integers(0, 9)))))      # 0-8 bases between copies
+            if rng.random() < 0.05:
+                parts.append("N" * int(rng.integers(1, 40)))
+        contigs.append(("rep%d" % c, "".join(parts).encode()))
+    exp = _lines(pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, raw=True, **kw))
+    got = _lines(eng.search_reference(contigs, synth.BASELINE_GUIDE, raw=True, **kw))
+    assert len(exp) > (3 if kw.get("O") == 0 else 150)          # -O 0: every later hit of a group "overlaps" (>= 0), the sweep keeps a handful
+    assert got == exp
+
+
 def test_search_single_chrom(eng, small_genome):
     g, contigs = small_genome
     exp = _lines(pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, chrom="chr2", raw=True))
