@@ -288,32 +288,30 @@ CAL_HD void band_align_group(const GuideSpec& g, const Scores& sc, Fetch fetch, 
   const int n = g.lp;
   const int first = col_at(0), last = col_at(n_cols - 1);
   const int jlo = first - g.span > 0 ? first - g.span : 0;
-  const int32_t gI = sc.target_gap, gD = sc.query_gap;
+  // tagged scores as in band_align_k: 4 * score + (3 Diagonal, 2 Left, 1 Up); one integer max picks score and predecessor matrix in the reference's tie order
+  const int32_t gI4 = 4 * sc.target_gap, gD4 = 4 * sc.query_gap, mis4 = 4 * sc.mismatch, dmatch4 = 4 * (sc.match - sc.mismatch), NEG4 = 4 * NEG_SCORE;
   int32_t D[R + 1], L[R + 1], U[R + 1];          // previous column; compile-time indices only -> registers
   uint32_t qm[R / 2];
 #pragma unroll
   for (int i = 0; i < R / 2; ++i) qm[i] = (uint32_t)g.qmask[2 * i] | ((uint32_t)g.qmask[2 * i + 1] << 16);
 #pragma unroll
-  for (int i = 0; i <= R; ++i) { D[i] = i == 0 ? 0 : NEG_SCORE; L[i] = i == 0 ? 0 : NEG_SCORE; U[i] = i * gI; }      // local column 0: leading insertions only
-  for (int i = 1; i <= n; ++i) trace[i * TW] = (uint8_t)((i == 1 ? TR_DIAG : TR_UP) << 2);
+  for (int i = 0; i <= R; ++i) { D[i] = (i == 0 ? 0 : NEG4) + TG_DIAG; L[i] = (i == 0 ? 0 : NEG4) + TG_LEFT; U[i] = i * gI4 + TG_UP; }      // local column 0: leading insertions only
+  for (int i = 1; i <= n; ++i) trace[i * TW] = (uint8_t)((i == 1 ? TG_DIAG : TG_UP) << 2);
   int k = 0, next_col = first;
   for (int c = 1; c <= last - jlo; ++c) {
     const uint32_t code = fetch(jlo + c);
-    int32_t dgD = 0, dgL = 0, dgU = 0;            // row i-1 of the previous column (row 0 is all zero: free leading target)
-    int32_t upD = 0, upU = 0;                     // row i-1 of this column
-    int32_t lastD = 0, lastL = 0, lastU = 0;
+    int32_t dgD = TG_DIAG, dgL = TG_LEFT, dgU = TG_UP;   // row i-1 of the previous column (row 0 is all zero: free leading target)
+    int32_t upD = TG_DIAG, upU = TG_UP;                  // row i-1 of this column
+    int32_t lastD = TG_DIAG, lastL = TG_LEFT, lastU = TG_UP;
 #pragma unroll
     for (int i = 1; i <= R; ++i) {
       if (i <= n) {
         const int32_t tD = D[i], tL = L[i], tU = U[i];
         const uint32_t mt = (((qm[(i - 1) >> 1] >> (((i - 1) & 1) * 16)) & 0xFFFFu) >> code) & 1u;
-        const int32_t add = mt ? sc.match : sc.mismatch;
-        uint32_t cell = mt << 6;
-        int32_t nd, nu, nl;
-        if (dgD >= dgL && dgD >= dgU) { nd = dgD + add; cell |= TR_DIAG; } else if (dgL >= dgU) { nd = dgL + add; cell |= TR_LEFT; } else { nd = dgU + add; cell |= TR_UP; }
-        { const int32_t pd = upD + gI, pu = upU + gI; if (pd >= pu) { nu = pd; cell |= TR_DIAG << 2; } else { nu = pu; cell |= TR_UP << 2; } }
-        { const int32_t pd = tD + gD, pl = tL + gD, pu = tU + gD;
-          if (pd >= pl && pd >= pu) { nl = pd; cell |= TR_DIAG << 4; } else if (pl >= pu) { nl = pl; cell |= TR_LEFT << 4; } else { nl = pu; cell |= TR_UP << 4; } }
+        const int32_t add4 = mis4 + (int32_t)mt * dmatch4;
+        const int32_t md = max3_s32(dgD, dgL, dgU), mu = upD > upU ? upD : upU, ml = max3_s32(tD, tL, tU);
+        const int32_t nd = (md | 3) + add4, nu = ((mu & ~3) | TG_UP) + gI4, nl = ((ml & ~3) | TG_LEFT) + gD4;
+        const uint32_t cell = ((uint32_t)md & 3u) + ((uint32_t)mu & 3u) * 4u + ((uint32_t)ml & 3u) * 16u + mt * 64u;
         D[i] = nd; L[i] = nl; U[i] = nu; dgD = tD; dgL = tL; dgU = tU; upD = nd; upU = nu;
         trace[i * TW + c] = (uint8_t)cell;
         if (i == n) { lastD = nd; lastL = nl; lastU = nu; }
@@ -322,20 +320,18 @@ CAL_HD void band_align_group(const GuideSpec& g, const Scores& sc, Fetch fetch, 
     if (jlo + c != next_col) continue;
     const int j = next_col, kk = k;
     ++k; next_col = k < n_cols ? col_at(k) : -1;
-    int32_t best = lastD; int dir = TR_DIAG;
-    if (lastL > best) { best = lastL; dir = TR_LEFT; }
-    if (lastU > best) { best = lastU; dir = TR_UP; }
+    const int32_t mbest = max3_s32(lastD, lastL, lastU);
+    const int32_t best = mbest >> 2;
     if (best < g.min_score) continue;
     GuideAln out;
-    int ci = n, cc = c, cdir = dir, nrev = 0;
+    int ci = n, cc = c, cdir = mbest & 3, nrev = 0;
     uint8_t rev[MAX_GUIDE_OPS];
     for (;;) {
-      int next; uint32_t cell = 0;
-      if (ci == 0) next = TR_DONE;
-      else { cell = trace[ci * TW + cc]; next = cdir == TR_DIAG ? (cell & 3) : (cdir == TR_UP ? ((cell >> 2) & 3) : ((cell >> 4) & 3)); }
-      if (next == TR_DONE || nrev >= MAX_GUIDE_OPS) break;
-      if (cdir == TR_DIAG) { rev[nrev++] = (cell >> 6) ? OP_EQ : OP_X; --ci; --cc; }
-      else if (cdir == TR_LEFT) { rev[nrev++] = OP_D; --cc; }
+      if (ci == 0 || nrev >= MAX_GUIDE_OPS) break;
+      const uint32_t cell = trace[ci * TW + cc];
+      const int next = (int)(cdir == TG_DIAG ? (cell & 3) : (cdir == TG_UP ? ((cell >> 2) & 3) : ((cell >> 4) & 3)));
+      if (cdir == TG_DIAG) { rev[nrev++] = (cell >> 6) ? OP_EQ : OP_X; --ci; --cc; }
+      else if (cdir == TG_LEFT) { rev[nrev++] = OP_D; --cc; }
       else { rev[nrev++] = OP_I; --ci; }
       cdir = next;
     }
