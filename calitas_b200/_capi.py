@@ -74,7 +74,7 @@ EXPORTS = [
     "calitas_shard_plan", "calitas_search", "calitas_align_regions", "calitas_align_targets", "calitas_hitset_count", "calitas_hitset_data",
     "calitas_hitset_free", "calitas_hitset_stats", "calitas_render_alignments", "calitas_free_text", "calitas_microbench_int",
     # include/calitas_b200_tools.h
-    "calitas_tool_align", "calitas_tool_align_best", "calitas_tool_align_to_ref", "calitas_tool_search_reference", "calitas_tool_search_reference_batch", "calitas_tool_align_to_reference",
+    "calitas_tool_align", "calitas_tool_align_best", "calitas_tool_align_to_ref", "calitas_tool_search_reference", "calitas_tool_search_reference_batch", "calitas_tool_search_reference_batch_fd", "calitas_tool_align_to_reference",
     "calitas_tool_variant_windows", "calitas_tool_pairwise_align",
 ]
 

@@ -1,7 +1,11 @@
 // cal_tools.cpp — host-side mirror of the reference's operators (see include/calitas_b200_tools.h).
 // Alignments are computed only by the device engine (calitas_search / calitas_align_regions / calitas_align_targets).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -176,6 +180,48 @@ Row make_row(const RowContext& cx, const RowConst& rc, const calitas_hit& h, con
   row.key = Str("{") + g.names[contig] + ":" + (char)h.strand + ":" + var[1];
   write_row(row.line, cx, rc, gd, h, r, contig, so, eo, gso, geo, vs.empty() ? nullptr : var, fl);
   return row;
+}
+
+// Writes all of `data` to a file descriptor (sequential: works for files, pipes and terminals alike).
+void write_all(int fd, const char* data, size_t n) {
+  size_t off = 0;
+  while (off < n) { const ssize_t put = ::write(fd, data + off, n - off); if (put <= 0) throw ToolError{ CALITAS_ESTATE, "short write to the output" }; off += (size_t)put; }
+}
+// Renders n_blocks text blocks on all host threads and hands them to `consume` strictly in order on the calling thread, while later blocks are
+// still being rendered: the table goes to disk as it is produced instead of being assembled in memory first (18 GB for 100 guides on hg38).
+// Blocks are claimed in index order and a worker never runs more than `lookahead` blocks ahead of the consumer, which bounds the memory held.
+template <class Render, class Consume> void ordered_pipeline(int64_t n_blocks, int64_t lookahead, Render render, Consume consume) {
+  if (n_blocks <= 0) return;
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_blocks, std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()))));
+  std::vector<Str> blocks((size_t)n_blocks); std::vector<char> ready((size_t)n_blocks, 0);
+  std::mutex mu; std::condition_variable cv; int64_t next = 0, consumed = 0; bool failed = false; Str err; int err_code = CALITAS_ESTATE;
+  auto worker = [&]() {
+    for (;;) {
+      int64_t k;
+      { std::unique_lock<std::mutex> lk(mu);
+        k = next++;
+        if (k >= n_blocks) return;
+        cv.wait(lk, [&] { return failed || k < consumed + lookahead; });
+        if (failed) return; }
+      try { render(k, blocks[(size_t)k]); }
+      catch (const ToolError& e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.msg; err_code = e.code; }
+      catch (const std::exception& e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.what(); }
+      { std::lock_guard<std::mutex> lk(mu); ready[(size_t)k] = 1; }
+      cv.notify_all();
+    } };
+  std::vector<std::thread> th; for (int t = 0; t < nt; ++t) th.emplace_back(worker);
+  try {
+    for (int64_t k = 0; k < n_blocks; ++k) {
+      { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return failed || ready[(size_t)k]; }); if (failed) break; }
+      consume(blocks[(size_t)k]); Str().swap(blocks[(size_t)k]);
+      { std::lock_guard<std::mutex> lk(mu); consumed = k + 1; }
+      cv.notify_all();
+    }
+  } catch (const ToolError& e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.msg; err_code = e.code; }
+  { std::lock_guard<std::mutex> lk(mu); if (failed) next = n_blocks; }
+  cv.notify_all();
+  for (auto& t : th) t.join();
+  if (failed) throw ToolError{ err_code, err };
 }
 
 Str hit_header() {
@@ -434,13 +480,16 @@ int calitas_tool_search_reference(calitas_engine* e, const calitas_reference* re
 
 // SearchReference.execute for a batch of guides over 1..N engines (one per GPU, each holding a contig-range shard of the same genome,
 // calitas_shard_plan): the engines run concurrently on host threads, shards are independent, the host concatenates per guide in shard order.
-int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
-                                        int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
-                                        char** out_tsv, int64_t* n_hits) {
+// out_fd >= 0: the table is written to that descriptor (streamed block by block when there is no VCF) and *out_tsv stays NULL.
+static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
+                                       int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
+                                       int out_fd, char** out_tsv, int64_t* n_hits, int64_t* n_bytes) {
   return guarded([&]() -> int {
-    if (n_engines <= 0 || !engines || !refs || !genome || n_guides <= 0 || !guides || !opt || !out_tsv) bad("bad arguments");
+    if (n_engines <= 0 || !engines || !refs || !genome || n_guides <= 0 || !guides || !opt || (out_fd < 0 && !out_tsv)) bad("bad arguments");
     for (int s = 0; s < n_engines; ++s) if (!engines[s] || !refs[s]) bad("engine or reference is NULL");
-    *out_tsv = nullptr;
+    if (out_tsv) *out_tsv = nullptr;
+    const bool stream = out_fd >= 0 && opt->vcf_text == nullptr;
+    int64_t streamed_bytes = 0;
     std::vector<GuideDef> defs; for (int g = 0; g < n_guides; ++g) defs.push_back(parse_guide(guides[g]));
     calitas_costs costs; ck(calitas_engine_get_costs(engines[0], &costs));
     std::vector<RowContext> cxs((size_t)n_guides);
@@ -455,7 +504,8 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
     const bool with_vcf = opt->vcf_text != nullptr;
     std::vector<std::vector<Row>> rows((size_t)n_guides);
     std::vector<RowConst> rcs; for (int g = 0; g < n_guides; ++g) rcs.push_back(make_row_const(cxs[(size_t)g], defs[(size_t)g]));
-    const int64_t ROW_BLOCK = 2048; std::vector<std::vector<Str>> row_text((size_t)n_guides); int64_t n_final = 0;      // plain runs: rendered text blocks per guide
+    const int64_t ROW_BLOCK = std::getenv("CALITAS_ROW_BLOCK") ? std::max(1, std::atoi(std::getenv("CALITAS_ROW_BLOCK"))) : 2048;   // rows per rendered text block (the variable lets tests force many blocks)
+    std::vector<std::vector<Str>> row_text((size_t)n_guides); int64_t n_final = 0;      // plain runs: rendered text blocks per guide
     PhaseTimer pt;
     // every engine's work runs on its own host thread; errors travel back as (code, message)
     auto run_all = [&](const std::function<void(int)>& job) {
@@ -477,7 +527,7 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
         const GuideDef& gd = defs[(size_t)g]; const RowContext& cx = cxs[(size_t)g]; const RowConst& rc = rcs[(size_t)g];
         // without a VCF the device has already de-duplicated and sorted: rows are final, rendered straight into text blocks of ROW_BLOCK rows
         std::vector<Row>& out = rows[(size_t)g]; if (with_vcf) out.resize(order.size());
-        std::vector<Str>& blocks = row_text[(size_t)g]; if (!with_vcf) blocks.resize((order.size() + ROW_BLOCK - 1) / ROW_BLOCK);
+        std::vector<Str>& blocks = row_text[(size_t)g]; if (!with_vcf && !stream) blocks.resize((order.size() + ROW_BLOCK - 1) / ROW_BLOCK);
         n_final += with_vcf ? 0 : (int64_t)order.size();
         auto render = [&](int64_t b, int64_t e_, Str* blk) {
           if (blk) blk->reserve((size_t)(e_ - b) * 640);
@@ -491,6 +541,12 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
           } };
         const int64_t n_rows = (int64_t)order.size();
         if (with_vcf) parallel_for(n_rows, ROW_BLOCK, [&](int64_t b, int64_t e_) { render(b, e_, nullptr); });
+        else if (stream) {
+          if (g == 0) { const Str header = hit_header(); write_all(out_fd, header.data(), header.size()); streamed_bytes += (int64_t)header.size(); }
+          ordered_pipeline((n_rows + ROW_BLOCK - 1) / ROW_BLOCK, 256,
+                           [&](int64_t k, Str& blk) { render(k * ROW_BLOCK, std::min(n_rows, (k + 1) * ROW_BLOCK), &blk); },
+                           [&](const Str& blk) { write_all(out_fd, blk.data(), blk.size()); streamed_bytes += (int64_t)blk.size(); });
+        }
         else parallel_for((int64_t)blocks.size(), 1, [&](int64_t bb, int64_t be) { for (int64_t k = bb; k < be; ++k) render(k * ROW_BLOCK, std::min(n_rows, (k + 1) * ROW_BLOCK), &blocks[(size_t)k]); });
       }
       for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "hit set is not guide-major" };
@@ -553,6 +609,7 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
       }
       pt.lap("removeOverlaps + sort (host)");
     }
+    if (stream) { if (n_hits) *n_hits = n_final; if (n_bytes) *n_bytes = streamed_bytes; return CALITAS_OK; }
     const Str header = hit_header(); int64_t total = n_final; size_t bytes = header.size();
     for (auto& v : rows) { for (auto& r : v) bytes += r.line.size(); total += (int64_t)v.size(); }
     std::vector<Str*> blocks; std::vector<size_t> at;                                                                    // text blocks of the plain run, in table order
@@ -564,9 +621,23 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
     text[bytes] = 0;
     pt.lap("table assembly");
     if (n_hits) *n_hits = total;
-    *out_tsv = text;
+    if (n_bytes) *n_bytes = (int64_t)bytes;
+    if (out_fd >= 0) { write_all(out_fd, text, bytes); std::free(text); }
+    else *out_tsv = text;
     return CALITAS_OK;
   });
+}
+
+int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
+                                        int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
+                                        char** out_tsv, int64_t* n_hits) {
+  return search_reference_batch_impl(n_engines, engines, refs, genome, n_guides, guides, guide_ids, opt, -1, out_tsv, n_hits, nullptr);
+}
+int calitas_tool_search_reference_batch_fd(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
+                                           int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
+                                           int32_t out_fd, int64_t* n_hits, int64_t* n_bytes) {
+  if (out_fd < 0) return calitas_tools_set_error(CALITAS_EINVAL, "bad output descriptor");
+  return search_reference_batch_impl(n_engines, engines, refs, genome, n_guides, guides, guide_ids, opt, out_fd, nullptr, n_hits, n_bytes);
 }
 
 int calitas_tool_align_to_reference(calitas_engine* e, const calitas_reference* ref, const calitas_genome_view* genome, int64_t n_tasks,

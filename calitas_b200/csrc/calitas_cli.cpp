@@ -7,6 +7,8 @@
 // --time-stamp / --aligner-version (fix the two run-dependent columns, for reproducible comparisons), --stats (timings to stderr).
 // -t/--threads is accepted and ignored (the reference's CPU thread count).
 #include <cctype>
+#include <fcntl.h>
+#include <unistd.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -157,17 +159,23 @@ int search_reference(int argc, char** argv) {
   Session S; open_session(S, f, false, 4 * opt.window_size);
   std::vector<calitas_guide> guides; std::vector<std::vector<const char*>> aux_ptr(seqs.size()); std::vector<const char*> id_ptr;
   for (size_t i = 0; i < seqs.size(); ++i) { for (auto& a : aux[i]) aux_ptr[i].push_back(a.c_str()); guides.push_back(calitas_guide{ seqs[i].c_str(), aux_ptr[i].empty() ? nullptr : aux_ptr[i].data(), (int32_t)aux_ptr[i].size() }); id_ptr.push_back(ids[i].c_str()); }
-  char* tsv = nullptr; int64_t n_hits = 0;
+  int64_t n_hits = 0, n_bytes = 0;
+  // the table leaves through a descriptor while it is rendered (stdout for "-")
+  const Str out_path = f.str("output", "-");
+  const bool to_stdout = out_path.empty() || out_path == "-" || out_path == "/dev/stdout";
+  int fd = 1;
+  if (to_stdout) std::fflush(stdout);
+  else { fd = ::open(out_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666); if (fd < 0) throw IoError{ "Cannot write to path: " + out_path }; }
   double t0 = now_s();
-  ck(calitas_tool_search_reference_batch((int32_t)S.engines.size(), S.engines.data(), (const calitas_reference* const*)S.refs.data(), &S.view, (int32_t)guides.size(), guides.data(),
-                                         id_ptr.data(), &opt, &tsv, &n_hits));
-  const double search_s = now_s() - t0; t0 = now_s();
-  write_file(f.str("output", "-"), tsv, std::strlen(tsv));
-  const double write_s = now_s() - t0;
-  calitas_free_text(tsv);
+  const int rc = calitas_tool_search_reference_batch_fd((int32_t)S.engines.size(), S.engines.data(), (const calitas_reference* const*)S.refs.data(), &S.view, (int32_t)guides.size(), guides.data(),
+                                                        id_ptr.data(), &opt, fd, &n_hits, &n_bytes);
+  const Str err = rc ? calitas_last_error() : "";
+  if (!to_stdout && ::close(fd) != 0 && !rc) throw IoError{ "Short write to " + out_path };
+  if (rc) throw UsageError{ err };
+  const double search_s = now_s() - t0;
   if (f.has("stats"))
-    std::fprintf(stderr, "calitas-b200 SearchReference: %zu guide(s), %lld hits; fasta read %.3f s + parse %.3f s, CUDA init %.3f s, upload+pack %.3f s on %zu GPU(s), search+render %.3f s, write %.3f s\n",
-                 guides.size(), (long long)n_hits, S.genome.read_s, S.genome.parse_s, S.init_s, S.pack_s, S.engines.size(), search_s, write_s);
+    std::fprintf(stderr, "calitas-b200 SearchReference: %zu guide(s), %lld hits, %lld bytes; fasta read %.3f s + parse %.3f s, CUDA init %.3f s, upload+pack %.3f s on %zu GPU(s), search+render+write %.3f s\n",
+                 guides.size(), (long long)n_hits, (long long)n_bytes, S.genome.read_s, S.genome.parse_s, S.init_s, S.pack_s, S.engines.size(), search_s);
   return 0;
 }
 

@@ -56,6 +56,13 @@ int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const
                                         int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
                                         char** out_tsv, int64_t* n_hits);
 
+/* The same, with the table written to an open file descriptor instead of returned: without a VCF the rows are rendered on all host threads and
+ * leave block by block, in order, while later blocks are still being rendered (the 100-guide hg38 table is 18 GB; it never sits in memory whole).
+ * Replaces Metric.writer over the keepers (SearchReference.scala:646-648).  *n_bytes = bytes written. */
+int calitas_tool_search_reference_batch_fd(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
+                                           int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
+                                           int32_t out_fd, int64_t* n_hits, int64_t* n_bytes);
+
 typedef struct calitas_a2r_task { const char* id; const char* query; const char* chrom; int32_t position; } calitas_a2r_task;   /* AlignToReference.scala:97-102 */
 typedef struct calitas_a2r_options {         /* AlignToReference.scala:35-50; -1 = not given */
   int32_t window_size, max_guide_diffs, max_pam_mismatches, max_gaps_between_guide_and_pam, max_total_diffs, max_overlap;

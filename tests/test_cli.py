@@ -143,6 +143,30 @@ def test_prepare_vcf_then_search_reference(calitas, ref_dir):
     assert got == exp and any("+variants" in l for l in got)
 
 
+def test_search_reference_cli_streams_many_blocks_in_order(calitas, ref_dir):
+    """The table leaves the tool block by block while later blocks are rendered: with 3 rows per block and d=6 the run has dozens of blocks per
+    guide; the file must still be the oracle's table, row for row, and the same through stdout."""
+    d, g, contigs = ref_dir
+    gf = d / "guides_stream.tsv"
+    open(gf, "w").write("a\tCTTGCCCCACAGGGCAGTAA\nb\t%s\n" % synth.BASELINE_GUIDE)
+    exp = None
+    for gid, guide in (("a", "CTTGCCCCACAGGGCAGTAA"), ("b", synth.BASELINE_GUIDE)):
+        t = lines(pyoracle.search_reference(contigs, guide, guide_id=gid, assembly="SYN10M", raw=True, d=6, g=2))
+        exp = t if exp is None else exp + t[1:]
+    assert len(exp) > 150
+    env = dict(os.environ, CALITAS_ROW_BLOCK="3")
+    out = d / "hits_stream.tsv"
+    args = [calitas, "SearchReference", "--guides-file", str(gf), "-r", str(d / "ref.fa"), "-d", "6", "-g", "2", "--time-stamp", "", "--aligner-version", "oracle"]
+    p = subprocess.run(args + ["-o", str(out)], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr
+    assert lines(open(out).read()) == exp
+    p = subprocess.run(args, capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0 and lines(p.stdout) == exp
+    # an unwritable output is an error, not a silent truncation
+    p = subprocess.run(args + ["-o", str(d / "no_such_dir" / "x.tsv")], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 2 and "Cannot write" in p.stderr
+
+
 def test_search_reference_cli_guide_batch_and_stdout(calitas, ref_dir):
     d, g, contigs = ref_dir
     gf = d / "guides.tsv"
