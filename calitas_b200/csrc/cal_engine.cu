@@ -646,6 +646,7 @@ struct calitas_hitset {
   calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 
+enum { CNT_DEDUP_OVERFLOW = 7 };
 enum { CE_SCAN_B = 0, CE_SCAN_E, CE_COUNT, CE_SORTED, CE_ALIGN_B, CE_ALIGN_E, CE_TAIL_B, CE_TAIL_E, CE_COPY_B, CE_COPY_E, CE_N };
 struct ChunkEvents { dev::Event ev[CE_N]; };
 
@@ -659,6 +660,8 @@ struct calitas_engine {
   size_t out_hits_hint = 1u << 16;
   DBuf cand_b, cand_c;
   DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, kept, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, kept_owned, sowned;
+  // eight 64-bit device counters and their pinned host mirror: slots 0..2 = candidate counts of the three scan buffers (run_explicit uses 0),
+  // slot CNT_DEDUP_OVERFLOW = k_dedup_keys' "a field does not fit its sort-key width" flag
   unsigned long long* h_count = nullptr;       // pinned
   unsigned long long* d_count = nullptr;
   std::vector<PinnedBuf> pinned_pool;
@@ -813,12 +816,12 @@ int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out
   size_t tb = dev::sort_pairs_u64_tmp((size_t)n, 0, 64); e->tmp.ensure(tb);
   const uint64_t* skey; const uint32_t* sidx; int strand_shift;
   if (L.merged) {
-    CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->keyA.as<uint64_t>(), (uint64_t*)nullptr, e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + 7)); dev::launch_check("k_dedup_keys"); ++e->launches;
+    CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->keyA.as<uint64_t>(), (uint64_t*)nullptr, e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + CNT_DEDUP_OVERFLOW)); dev::launch_check("k_dedup_keys"); ++e->launches;
     dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, L.bits + L.score_bits, s); ++e->launches;
     skey = e->key1.as<uint64_t>(); sidx = e->idx2.as<uint32_t>(); strand_shift = L.score_bits;
   } else {      // stable by -score (arrival order = index order), then stable by (guide, contig, start, strand)
     e->key_b.ensure((size_t)n * 8);
-    CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + 7)); dev::launch_check("k_dedup_keys"); ++e->launches;
+    CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + CNT_DEDUP_OVERFLOW)); dev::launch_check("k_dedup_keys"); ++e->launches;
     dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, L.score_bits, s); ++e->launches;
     CAL_LAUNCH(k_gather_u64, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), n, e->keyA.as<uint64_t>()); dev::launch_check("k_gather_u64"); ++e->launches;
     dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)n, 0, L.bits, s); ++e->launches;
@@ -832,9 +835,9 @@ int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n, s); ++e->launches;
   uint32_t last_pos = 0, last_flag = 0;
   dev::d2h(&last_pos, e->pos.as<uint32_t>() + (n - 1), 4, s); dev::d2h(&last_flag, e->flag.as<uint32_t>() + (n - 1), 4, s);
-  dev::d2h(e->h_count + 7, e->d_count + 7, 8, s);
+  dev::d2h(e->h_count + CNT_DEDUP_OVERFLOW, e->d_count + CNT_DEDUP_OVERFLOW, 8, s);
   dev::stream_sync(s);
-  if (e->h_count[7]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in removeOverlaps");
+  if (e->h_count[CNT_DEDUP_OVERFLOW]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in removeOverlaps");
   const int64_t nk = (int64_t)last_pos + last_flag;
   if (nk == 0) return 0;
   e->out.ensure_keep((size_t)(out_n + nk) * sizeof(calitas_hit), (size_t)out_n * sizeof(calitas_hit), s);
@@ -1113,7 +1116,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     const size_t n_chunks = chunks.size();
     while (e->chunk_ev.size() < n_chunks) { ChunkEvents ce; for (auto& ev : ce.ev) ev = dev::event_create(); e->chunk_ev.push_back(ce); }
     e->launches = 0;
-    dev::zero(e->d_count + 7, 8, s);                         // field-overflow flag of k_dedup_keys
+    dev::zero(e->d_count + CNT_DEDUP_OVERFLOW, 8, s);                         // field-overflow flag of k_dedup_keys
     dev::event_record(e->ev[0], ss);
     e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), ss);
     double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
