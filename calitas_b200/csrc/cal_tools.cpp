@@ -516,40 +516,58 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
       for (int s = 0; s < n_engines; ++s) if (rc[(size_t)s] != CALITAS_OK) throw ToolError{ rc[(size_t)s], msg[(size_t)s] };
     };
     {  // reference windows: SearchReference.scala:527-564 (+ removeOverlaps/sort on the device when there is no VCF)
+      // The streaming path searches GUIDE_BATCH guides per device call and renders a batch while the next one is searched on a helper thread:
+      // the first call's buffer set-up (page-locking the result buffer costs ~0.5 s per GB) shrinks with the batch and hides behind rendering,
+      // and the pinned result memory is two batches instead of the whole run.  Other paths search all guides in one call.
+      const int GUIDE_BATCH = stream ? 32 : n_guides;
+      auto search_batch = [&](int g0, int g1, std::vector<HitSet>& into) {
+        run_all([&](int s) { ck(calitas_search(engines[s], refs[s], g1 - g0, guides + g0, &opt->limits, opt->window_size, opt->chrom, with_vcf ? 0 : 1, &into[(size_t)s].h)); });
+      };
       std::vector<HitSet> hs((size_t)n_engines);
-      run_all([&](int s) { ck(calitas_search(engines[s], refs[s], n_guides, guides, &opt->limits, opt->window_size, opt->chrom, with_vcf ? 0 : 1, &hs[(size_t)s].h)); });
-      pt.lap("reference search (device)");
-      const Flanks none;
-      std::vector<int64_t> cursor((size_t)n_engines, 0);          // every hit set is guide-major
-      for (int g = 0; g < n_guides; ++g) {
-        std::vector<const calitas_hit*> order;                    // this guide's hits: shard 0's, then shard 1's, ... = ReferenceHit.sort order
-        for (int s = 0; s < n_engines; ++s) { int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s]; for (; i < h_.n() && h_.data()[i].guide_idx == g; ++i) order.push_back(h_.data() + i); }
-        const GuideDef& gd = defs[(size_t)g]; const RowContext& cx = cxs[(size_t)g]; const RowConst& rc = rcs[(size_t)g];
-        // without a VCF the device has already de-duplicated and sorted: rows are final, rendered straight into text blocks of ROW_BLOCK rows
-        std::vector<Row>& out = rows[(size_t)g]; if (with_vcf) out.resize(order.size());
-        std::vector<Str>& blocks = row_text[(size_t)g]; if (!with_vcf && !stream) blocks.resize((order.size() + ROW_BLOCK - 1) / ROW_BLOCK);
-        n_final += with_vcf ? 0 : (int64_t)order.size();
-        auto render = [&](int64_t b, int64_t e_, Str* blk) {
-          if (blk) blk->reserve((size_t)(e_ - b) * 640);
-          RenderedFix r;
-          for (int64_t k = b; k < e_; ++k) {
-            const calitas_hit& h = *order[(size_t)k];
-            const Str& gt = guide_text_of(rc, h.pam_idx);
-            render_hit_fix(h, gt.data(), (int)gt.size(), (const char*)genome->bases[h.contig_idx] + h.start_offset, h.end_offset - h.start_offset, true, r);   // windows are upper-cased, SearchReference.scala:67
-            if (blk) write_row(*blk, cx, rc, gd, h, r, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, nullptr, none);
-            else out[(size_t)k] = make_row(cx, rc, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none);
-          } };
-        const int64_t n_rows = (int64_t)order.size();
-        if (with_vcf) parallel_for(n_rows, ROW_BLOCK, [&](int64_t b, int64_t e_) { render(b, e_, nullptr); });
-        else if (stream) {
-          if (g == 0) { const Str header = hit_header(); write_all(out_fd, header.data(), header.size()); streamed_bytes += (int64_t)header.size(); }
-          ordered_pipeline((n_rows + ROW_BLOCK - 1) / ROW_BLOCK, 256,
-                           [&](int64_t k, Str& blk) { render(k * ROW_BLOCK, std::min(n_rows, (k + 1) * ROW_BLOCK), &blk); },
-                           [&](const Str& blk) { write_all(out_fd, blk.data(), blk.size()); streamed_bytes += (int64_t)blk.size(); });
+      search_batch(0, std::min(GUIDE_BATCH, n_guides), hs);
+      pt.lap("reference search (device, first batch)");
+      for (int g0 = 0; g0 < n_guides; g0 += GUIDE_BATCH) {
+        const int g1 = std::min(n_guides, g0 + GUIDE_BATCH);
+        std::vector<HitSet> next_hs((size_t)n_engines); std::thread prefetch; int pf_code = CALITAS_OK; Str pf_msg;
+        if (g1 < n_guides) prefetch = std::thread([&]() {
+          try { search_batch(g1, std::min(n_guides, g1 + GUIDE_BATCH), next_hs); }
+          catch (const ToolError& te) { pf_code = te.code; pf_msg = te.msg; } catch (const std::exception& ex) { pf_code = CALITAS_ESTATE; pf_msg = ex.what(); } });
+        struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{ prefetch };      // an exception below must not leave the helper running
+        const Flanks none;
+        std::vector<int64_t> cursor((size_t)n_engines, 0);          // every hit set is guide-major; guide_idx counts from the batch's first guide
+        for (int g = g0; g < g1; ++g) {
+          std::vector<const calitas_hit*> order;                    // this guide's hits: shard 0's, then shard 1's, ... = ReferenceHit.sort order
+          for (int s = 0; s < n_engines; ++s) { int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s]; for (; i < h_.n() && h_.data()[i].guide_idx == g - g0; ++i) order.push_back(h_.data() + i); }
+          const GuideDef& gd = defs[(size_t)g]; const RowContext& cx = cxs[(size_t)g]; const RowConst& rc = rcs[(size_t)g];
+          // without a VCF the device has already de-duplicated and sorted: rows are final, rendered straight into text blocks of ROW_BLOCK rows
+          std::vector<Row>& out = rows[(size_t)g]; if (with_vcf) out.resize(order.size());
+          std::vector<Str>& blocks = row_text[(size_t)g]; if (!with_vcf && !stream) blocks.resize((order.size() + ROW_BLOCK - 1) / ROW_BLOCK);
+          n_final += with_vcf ? 0 : (int64_t)order.size();
+          auto render = [&](int64_t b, int64_t e_, Str* blk) {
+            if (blk) blk->reserve((size_t)(e_ - b) * 640);
+            RenderedFix r;
+            for (int64_t k = b; k < e_; ++k) {
+              const calitas_hit& h = *order[(size_t)k];
+              const Str& gt = guide_text_of(rc, h.pam_idx);
+              render_hit_fix(h, gt.data(), (int)gt.size(), (const char*)genome->bases[h.contig_idx] + h.start_offset, h.end_offset - h.start_offset, true, r);   // windows are upper-cased, SearchReference.scala:67
+              if (blk) write_row(*blk, cx, rc, gd, h, r, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, nullptr, none);
+              else out[(size_t)k] = make_row(cx, rc, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none);
+            } };
+          const int64_t n_rows = (int64_t)order.size();
+          if (with_vcf) parallel_for(n_rows, ROW_BLOCK, [&](int64_t b, int64_t e_) { render(b, e_, nullptr); });
+          else if (stream) {
+            if (g == 0) { const Str header = hit_header(); write_all(out_fd, header.data(), header.size()); streamed_bytes += (int64_t)header.size(); }
+            ordered_pipeline((n_rows + ROW_BLOCK - 1) / ROW_BLOCK, 256,
+                             [&](int64_t k, Str& blk) { render(k * ROW_BLOCK, std::min(n_rows, (k + 1) * ROW_BLOCK), &blk); },
+                             [&](const Str& blk) { write_all(out_fd, blk.data(), blk.size()); streamed_bytes += (int64_t)blk.size(); });
+          }
+          else parallel_for((int64_t)blocks.size(), 1, [&](int64_t bb, int64_t be) { for (int64_t k = bb; k < be; ++k) render(k * ROW_BLOCK, std::min(n_rows, (k + 1) * ROW_BLOCK), &blocks[(size_t)k]); });
         }
-        else parallel_for((int64_t)blocks.size(), 1, [&](int64_t bb, int64_t be) { for (int64_t k = bb; k < be; ++k) render(k * ROW_BLOCK, std::min(n_rows, (k + 1) * ROW_BLOCK), &blocks[(size_t)k]); });
+        for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "hit set is not guide-major" };
+        if (prefetch.joinable()) prefetch.join();                  // the engines are idle again: only now may this batch's hit sets go back to their pools
+        if (pf_code != CALITAS_OK) throw ToolError{ pf_code, pf_msg };
+        for (int s = 0; s < n_engines; ++s) std::swap(hs[(size_t)s].h, next_hs[(size_t)s].h);
       }
-      for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "hit set is not guide-major" };
       pt.lap("reference rows");
     }
     if (with_vcf) {  // SearchReference.scala:570-630

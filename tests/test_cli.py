@@ -167,6 +167,24 @@ def test_search_reference_cli_streams_many_blocks_in_order(calitas, ref_dir):
     assert p.returncode == 2 and "Cannot write" in p.stderr
 
 
+def test_search_reference_cli_forty_guides_two_device_batches(calitas, ref_dir):
+    """The streaming command line searches 32 guides per device call and renders one batch while a helper thread searches the next: 40 guides span
+    two batches (guide indices restart in the second); the table must be the concatenation of the per-guide oracle tables."""
+    d, g, contigs = ref_dir
+    guides = [synth.BASELINE_GUIDE] + synth.random_guides(39)
+    gf = d / "guides40.tsv"
+    open(gf, "w").write("".join("id%d\t%s\n" % (i, s) for i, s in enumerate(guides)))
+    out = d / "hits40.tsv"
+    p = run(calitas, "SearchReference", "--guides-file", gf, "-r", d / "ref.fa", "-o", out, "--time-stamp", "", "--aligner-version", "oracle")
+    assert p.returncode == 0, p.stderr
+    exp = None
+    for i, s in enumerate(guides):
+        t = lines(pyoracle.search_reference(contigs, s, guide_id="id%d" % i, assembly="SYN10M", raw=True))
+        exp = t if exp is None else exp + t[1:]
+    got = lines(open(out).read())
+    assert got == exp and len({l.split("\t")[0] for l in got[1:]}) >= 30
+
+
 def test_search_reference_cli_guide_batch_and_stdout(calitas, ref_dir):
     d, g, contigs = ref_dir
     gf = d / "guides.tsv"
