@@ -166,6 +166,24 @@ void write_row(Str& out, const RowContext& cx, const RowConst& rc, const GuideDe
   out.append(r.cigar, (size_t)r.cigar_len); out += '\t'; out += rc.proto_len; out += '\t'; put_int(out, r.unpadded_len); out += rc.tail;
 }
 
+// ReferenceHit.sort order (ReferenceHit.scala:276-287) on hit records: contig, coordinate_start, strand ("+" < "-"), score descending.
+bool hit_sorts_before(const calitas_hit* a, const calitas_hit* b) {
+  if (a->contig_idx != b->contig_idx) return a->contig_idx < b->contig_idx;
+  if (a->guide_start_offset != b->guide_start_offset) return a->guide_start_offset < b->guide_start_offset;
+  if (a->strand != b->strand) return a->strand < b->strand;
+  return a->score > b->score;
+}
+// order[0, seg) and order[seg, end) are each sorted (one guide's hits of the shards so far, and of the next shard).  Shards are ascending base
+// ranges, but consecutive windows overlap by guide length + d + g - 1 bases, so the last window of one shard and the first of the next can
+// report hits whose starts interleave (whenever removeOverlaps does not collapse them, e.g. a large -O).  Only that stretch is merged: stable,
+// the earlier shard first on equal keys, which is the single engine's arrival order.
+void merge_at_cut(std::vector<const calitas_hit*>& order, size_t seg) {
+  if (seg == 0 || seg >= order.size() || !hit_sorts_before(order[seg], order[seg - 1])) return;
+  auto first = std::upper_bound(order.begin(), order.begin() + (long)seg, order[seg], hit_sorts_before);                 // prefix elements <= the segment's first stay put
+  auto last = std::lower_bound(order.begin() + (long)seg, order.end(), order[seg - 1], hit_sorts_before);                // segment elements >= the prefix's last stay put
+  std::inplace_merge(first, order.begin() + (long)seg, last, hit_sorts_before);
+}
+
 // A row with what removeOverlaps / sort on the host need (VCF runs only: variant-window hits are merged with reference hits there).
 Row make_row(const RowContext& cx, const RowConst& rc, const calitas_hit& h, const RenderedFix& r, const GuideDef& gd, int contig, int so, int eo, int gso, int geo,
              const std::vector<VariantAllele>& variants, const Flanks& fl) {
@@ -488,7 +506,11 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
     if (n_engines <= 0 || !engines || !refs || !genome || n_guides <= 0 || !guides || !opt || (out_fd < 0 && !out_tsv)) bad("bad arguments");
     for (int s = 0; s < n_engines; ++s) if (!engines[s] || !refs[s]) bad("engine or reference is NULL");
     if (out_tsv) *out_tsv = nullptr;
-    const bool stream = out_fd >= 0 && opt->vcf_text == nullptr;
+    // removeOverlaps + sort run on the device per engine, except (i) with a VCF, where variant-window hits join the same groups, and (ii) with
+    // -O <= 0 on several engines: every later hit of a group then "overlaps" (>= 0), the reference's sweep (SearchReference.scala:662-672) has
+    // unbounded reach, and no halo can make a shard's sweep see what it would need; both cases gather raw hits and de-duplicate on the host.
+    const bool host_dedup = opt->vcf_text != nullptr || (n_engines > 1 && opt->limits.max_overlap <= 0);
+    const bool stream = out_fd >= 0 && !host_dedup;
     int64_t streamed_bytes = 0;
     std::vector<GuideDef> defs; for (int g = 0; g < n_guides; ++g) defs.push_back(parse_guide(guides[g]));
     calitas_costs costs; ck(calitas_engine_get_costs(engines[0], &costs));
@@ -521,7 +543,7 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
       // and the pinned result memory is two batches instead of the whole run.  Other paths search all guides in one call.
       const int GUIDE_BATCH = stream ? 32 : n_guides;
       auto search_batch = [&](int g0, int g1, std::vector<HitSet>& into) {
-        run_all([&](int s) { ck(calitas_search(engines[s], refs[s], g1 - g0, guides + g0, &opt->limits, opt->window_size, opt->chrom, with_vcf ? 0 : 1, &into[(size_t)s].h)); });
+        run_all([&](int s) { ck(calitas_search(engines[s], refs[s], g1 - g0, guides + g0, &opt->limits, opt->window_size, opt->chrom, host_dedup ? 0 : 1, &into[(size_t)s].h)); });
       };
       std::vector<HitSet> hs((size_t)n_engines);
       search_batch(0, std::min(GUIDE_BATCH, n_guides), hs);
@@ -537,12 +559,16 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
         std::vector<int64_t> cursor((size_t)n_engines, 0);          // every hit set is guide-major; guide_idx counts from the batch's first guide
         for (int g = g0; g < g1; ++g) {
           std::vector<const calitas_hit*> order;                    // this guide's hits: shard 0's, then shard 1's, ... = ReferenceHit.sort order
-          for (int s = 0; s < n_engines; ++s) { int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s]; for (; i < h_.n() && h_.data()[i].guide_idx == g - g0; ++i) order.push_back(h_.data() + i); }
+          for (int s = 0; s < n_engines; ++s) {
+            int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s]; const size_t seg = order.size();
+            for (; i < h_.n() && h_.data()[i].guide_idx == g - g0; ++i) order.push_back(h_.data() + i);
+            if (!host_dedup) merge_at_cut(order, seg);
+          }
           const GuideDef& gd = defs[(size_t)g]; const RowContext& cx = cxs[(size_t)g]; const RowConst& rc = rcs[(size_t)g];
           // without a VCF the device has already de-duplicated and sorted: rows are final, rendered straight into text blocks of ROW_BLOCK rows
-          std::vector<Row>& out = rows[(size_t)g]; if (with_vcf) out.resize(order.size());
-          std::vector<Str>& blocks = row_text[(size_t)g]; if (!with_vcf && !stream) blocks.resize((order.size() + ROW_BLOCK - 1) / ROW_BLOCK);
-          n_final += with_vcf ? 0 : (int64_t)order.size();
+          std::vector<Row>& out = rows[(size_t)g]; if (host_dedup) out.resize(order.size());
+          std::vector<Str>& blocks = row_text[(size_t)g]; if (!host_dedup && !stream) blocks.resize((order.size() + ROW_BLOCK - 1) / ROW_BLOCK);
+          n_final += host_dedup ? 0 : (int64_t)order.size();
           auto render = [&](int64_t b, int64_t e_, Str* blk) {
             if (blk) blk->reserve((size_t)(e_ - b) * 640);
             RenderedFix r;
@@ -554,7 +580,7 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
               else out[(size_t)k] = make_row(cx, rc, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none);
             } };
           const int64_t n_rows = (int64_t)order.size();
-          if (with_vcf) parallel_for(n_rows, ROW_BLOCK, [&](int64_t b, int64_t e_) { render(b, e_, nullptr); });
+          if (host_dedup) parallel_for(n_rows, ROW_BLOCK, [&](int64_t b, int64_t e_) { render(b, e_, nullptr); });
           else if (stream) {
             if (g == 0) { const Str header = hit_header(); write_all(out_fd, header.data(), header.size()); streamed_bytes += (int64_t)header.size(); }
             ordered_pipeline((n_rows + ROW_BLOCK - 1) / ROW_BLOCK, 256,
@@ -621,6 +647,8 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
         } }
       for (int s = 0; s < n_engines; ++s) if (cursor[(size_t)s] != hs[(size_t)s].n()) throw ToolError{ CALITAS_ESTATE, "variant hit set is not task-major" };
       pt.lap("variant rows");
+    }
+    if (host_dedup) {
       for (int g = 0; g < n_guides; ++g) {
         rows[(size_t)g] = remove_overlaps_host(rows[(size_t)g], opt->limits.max_overlap);                                 // :641
         sort_rows(rows[(size_t)g]);                                                                                      // :647

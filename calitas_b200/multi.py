@@ -1,16 +1,24 @@
 """Host-side gather for the one-process-per-GPU launch: contig-range shards are independent, so the only multi-rank step is
-concatenating the per-rank hit lists.  There is no collective on the compute path; this runs after calitas_search has returned on every rank.
+merging the per-rank hit lists.  There is no collective on the compute path; this runs after calitas_search has returned on every rank.
 
 Each rank's list is ordered (guide, contig, coordinate_start, strand, -score) and the shards are contiguous, ascending base ranges, so the global
-ReferenceHit.sort order (ReferenceHit.scala:276-287) per guide is rank 0's hits of that guide, then rank 1's, ... — no re-sort and no further
-de-duplication (hits near a cut are resolved identically on both sides thanks to the halo windows, and reported only by the owner)."""
+ReferenceHit.sort order (ReferenceHit.scala:276-287) per guide is ALMOST rank 0's hits of that guide, then rank 1's, ...: consecutive windows overlap
+by guide length + d + g - 1 bases, so around a cut the last window of one shard and the first window of the next can both report hits whose starts
+interleave (they do when -O is too large for removeOverlaps to collapse them).  The lists are therefore merged by the sort key, stably in shard
+order -- which is the single engine's arrival order for equal keys.  No further de-duplication is needed (hits near a cut are resolved identically on
+both sides thanks to the halo windows, and reported only by the owner).
+
+Limit: with max_overlap <= 0 every later hit of a (contig, strand) group "overlaps" (>= 0), so the reference's sweep has unbounded reach and no
+halo makes a shard's result exact; search with dedup=False then and de-duplicate the gathered hits on one host, as the C++ tool layer does
+(calitas_tool_search_reference_batch with several engines)."""
 import numpy as np
 
 from ._capi import hit_dtype
 
 
-def merge_shard_records(per_rank):
-    """per_rank: list (shard order) of structured arrays from HitSet.records() -> one array in single-engine order."""
+def merge_shard_records(per_rank, dedup=True):
+    """per_rank: list (shard order) of structured arrays from HitSet.records() -> one array in single-engine order.
+    dedup=False: the lists of a search without removeOverlaps/sort (arrival order: guide, window, strand, rank) are concatenated per guide."""
     dt = hit_dtype()
     per_rank = [np.asarray(r, dtype=dt) for r in per_rank]
     if not per_rank:
@@ -20,7 +28,10 @@ def merge_shard_records(per_rank):
         return allr
     rank_of = np.concatenate([np.full(r.size, i, dtype=np.int64) for i, r in enumerate(per_rank)])
     pos = np.concatenate([np.arange(r.size, dtype=np.int64) for r in per_rank])
-    order = np.lexsort((pos, rank_of, allr["guide_idx"]))          # guide-major, then shard order, then each shard's own order
+    if not dedup:
+        order = np.lexsort((pos, rank_of, allr["guide_idx"]))      # guide-major, then shard order, then each shard's own order
+    else:                                                          # ReferenceHit.sort key, ties in shard order then each shard's own order
+        order = np.lexsort((pos, rank_of, -allr["score"].astype(np.int64), allr["strand"], allr["guide_start_offset"], allr["contig_idx"], allr["guide_idx"]))
     return allr[order]
 
 

@@ -223,6 +223,40 @@ def test_search_reference_batch_over_shards(eng, small_genome, n_shards):
         assert got == exp, (n_shards, vcf is not None)
 
 
+def _tandem_repeat_contigs(seed, n_units):
+    rng = np.random.default_rng(seed)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    parts = []
+    for _ in range(n_units):
+        s = list("CTTGCCCCACAGGGCAGTAA")
+        for _ in range(int(rng.integers(0, 3))):
+            s[int(rng.integers(len(s)))] = "ACGT"[int(rng.integers(4))]
+        unit = "".join(s) + ["AGG", "TGG", "CAG", "GGG"][int(rng.integers(4))]
+        if rng.random() < 0.5:
+            unit = "".join(comp[b] for b in reversed(unit))
+        parts.append(unit)
+        parts.append("".join("ACGT"[i] for i in rng.integers(0, 4, int(rng.integers(0, 8)))))
+    return [("rep0", "".join(parts).encode())]
+
+
+@pytest.mark.parametrize("O", [10, 25, 0])
+def test_shard_cuts_inside_dense_repeats(eng, O):
+    """Consecutive windows overlap by 30 bases, so around a shard cut both neighbours report hits whose starts interleave whenever removeOverlaps
+    does not collapse them (-O 25 exceeds every alignment's length: nothing is removed).  The host must merge the shard lists by the sort key
+    at the cuts, not just concatenate them."""
+    contigs = _tandem_repeat_contigs(503, 160)
+    guides = [synth.BASELINE_GUIDE, ("CTTGCCCCACAGGGCAGTAAngg", ["nag"])]
+    exp = []
+    for gd, gid in zip(guides, "ab"):
+        seq, aux = (gd, []) if isinstance(gd, str) else gd
+        lines = _lines(pyoracle.search_reference(contigs, seq, guide_id=gid, aux_pams=aux, raw=True, O=O))
+        exp += lines if not exp else lines[1:]
+    assert len(exp) > {0: 3, 10: 300, 25: 1000}[O]        # -O 0: the sweep has unbounded reach (every later hit of a group "overlaps"), the tool de-duplicates on the host then
+    for n_shards in (2, 3, 5):
+        got = _lines(eng.t.search_reference_batch(contigs, guides, ["a", "b"], n_shards=n_shards, O=O))
+        assert got == exp, n_shards
+
+
 def test_align_to_reference_batches_of_10000_are_sorted_separately(eng, small_genome):
     """AlignToReference.scala:110,141: output is ReferenceHit.sort-ed per batch of 10 000 input rows, not globally."""
     g, contigs = small_genome

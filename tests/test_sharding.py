@@ -51,6 +51,33 @@ def test_shards_union_equals_whole(lib, dedup):
     e.close()
 
 
+@pytest.mark.parametrize("max_overlap", [10, 25, 1])
+def test_merge_shard_records_at_cuts_in_dense_repeats(lib, max_overlap):
+    """calitas_b200.multi.merge_shard_records (the one-process-per-GPU gather): merged per-shard records == the single-engine records, also where
+    the window overlap makes hits of neighbouring shards interleave by start (large -O: removeOverlaps collapses nothing)."""
+    from calitas_b200 import multi
+    import test_parity_random as T
+    contigs = [(n, np.frombuffer(b, dtype=np.uint8)) for n, b in T._tandem_repeat_contigs(507, 200)]
+    guides = [synth.BASELINE_GUIDE, ("CTTGCCCCACAGGGCAGTAAngg", ["nag"])]
+    lim = Limits(5, 1, 3, -1, max_overlap)
+    e = Engine(0, lib=lib)
+    ref = e.load_reference(contigs)
+    whole = e.search(ref, guides, lim, dedup=True).records()
+    ref.free()
+    assert whole.size > 300
+    for n_shards in (2, 3, 5):
+        parts = []
+        for s in range(n_shards):
+            r = e.load_reference(contigs, shard=(s, n_shards, 4000))
+            parts.append(e.search(r, guides, lim, dedup=True).records())
+            r.free()
+        merged = multi.merge_shard_records(parts)
+        drop = "task_idx"                                                  # window ids are engine-local bookkeeping
+        keep = [n for n in whole.dtype.names if n != drop]
+        assert merged.size == whole.size and all((merged[n] == whole[n]).all() for n in keep), n_shards
+    e.close()
+
+
 def test_shard_plan_covers_genome(lib):
     import ctypes as C
     lengths = [1000, 5, 123456, 1, 777]
