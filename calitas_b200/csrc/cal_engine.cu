@@ -1062,6 +1062,10 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     dev::set_device(e->device); dev::Stream s = e->stream, ss = e->scan_stream, cs = e->copy_stream;
     std::vector<GuideDef> defs; std::vector<GuideSpec> specs = build_specs(e, n_guides, guides, limits, false, &defs);
     if (window_size <= 0 || (uint32_t)window_size > MAX_WINDOW_LEN) throw InvalidArgument("window size out of range");
+    if (dedup && limits->max_overlap <= 0) {      // every later hit of a group then "overlaps" (>= 0): the sweep has unbounded reach, no halo makes a shard exact
+      for (size_t c = 0; c < ref->len.size(); ++c) if (ref->own_b[c] != 0 || ref->own_e[c] != ref->len[c])
+        throw InvalidArgument("max_overlap <= 0 cannot be de-duplicated per shard: search with dedup = 0 and run removeOverlaps over the gathered hits");
+    }
     int chrom_idx = -1;
     if (chrom && chrom[0]) { for (size_t c = 0; c < ref->names.size(); ++c) if (ref->names[c] == chrom) chrom_idx = (int)c; if (chrom_idx < 0) throw InvalidArgument(std::string("Unknown chromosome: ") + chrom); }
     // ---- plan: guide chunks and their window tilings ---------------------------------------------------------------------------

@@ -109,7 +109,10 @@ int calitas_shard_plan(int32_t n_contigs, const int64_t* lengths, int32_t shard,
 /* ---- SearchReference hot path ---------------------------------------------------------------------------------
  * Replaces the window loop of SearchReference.execute (SearchReference.scala:527-564): windowIterator + one
  * SequentialGuideAligner.align per window, for every guide of the batch, then (dedup != 0) removeOverlaps + ReferenceHit.sort
- * (SearchReference.scala:641-648, 653-675; ReferenceHit.scala:276-287).  chrom may be NULL (all contigs, -c absent). */
+ * (SearchReference.scala:641-648, 653-675; ReferenceHit.scala:276-287).  chrom may be NULL (all contigs, -c absent).
+ * On a sharded reference (own ranges that do not cover every contig) dedup != 0 requires max_overlap >= 1: with max_overlap <= 0 every later
+ * hit of a group "overlaps", the reference's sweep reaches across the whole contig and a shard cannot reproduce it (CALITAS_EINVAL; search with
+ * dedup = 0 and run removeOverlaps over the gathered hits, as calitas_tool_search_reference_batch does). */
 int calitas_search(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
                    const calitas_limits* limits, int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out);
 

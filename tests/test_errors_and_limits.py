@@ -91,3 +91,22 @@ def test_empty_and_tiny_inputs(eng):
     contigs = [("tiny", b"A"), ("short", b"ACGTACGTAC"), ("n", b"N" * 2000)]
     assert [l for l in eng.search_reference(contigs, synth.BASELINE_GUIDE, raw=True).split("\n") if l] == \
            [l for l in pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, raw=True).split("\n") if l]
+
+
+def test_per_shard_dedup_with_nonpositive_max_overlap_is_refused(eng):
+    """-O <= 0 makes every later hit of a group "overlap": the reference's sweep (SearchReference.scala:662-672) then reaches across the whole
+    contig and a shard cannot reproduce it.  calitas_search says so instead of returning a table that only looks right; a whole reference, or
+    dedup = 0 on a shard, is fine."""
+    g = synth.config1_genome(scale=0.01, n_sites=20)
+    contigs = [(n, b) for n, b in g.contigs()]
+    e = Engine(0, lib=eng.t.lib)
+    shard = e.load_reference(contigs, shard=(0, 2, 4000))
+    c, m = code_of(lambda: e.search(shard, [synth.BASELINE_GUIDE], Limits(5, 1, 3, -1, 0), dedup=True))
+    assert c == 1 and "max_overlap <= 0" in m
+    assert len(e.search(shard, [synth.BASELINE_GUIDE], Limits(5, 1, 3, -1, 0), dedup=False)) >= 0
+    assert len(e.search(shard, [synth.BASELINE_GUIDE], Limits(5, 1, 3, -1, 1), dedup=True)) >= 0
+    shard.free()
+    whole = e.load_reference(contigs)
+    assert len(e.search(whole, [synth.BASELINE_GUIDE], Limits(5, 1, 3, -1, 0), dedup=True)) >= 1
+    whole.free()
+    e.close()
