@@ -275,7 +275,9 @@ def main():
         hs.free()
         return st
 
-    sampler = ClockSampler(range(world) if rank == 0 else [])
+    # rank 0 samples the job's GPUs: CUDA_VISIBLE_DEVICES entries (indices or UUIDs, both accepted by nvidia-smi -i) when the launcher set it
+    visible = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+    sampler = ClockSampler((visible[:world] if len(visible) >= world else range(world)) if rank == 0 else [])
     sampler.start()                      # nvidia-smi needs ~1 s to start: launched before the warm-up so that it is sampling during the timed steps
     for _ in range(args.warmup):
         step()
