@@ -236,6 +236,7 @@ template <class Render, class Consume> void ordered_pipeline(int64_t n_blocks, i
       cv.notify_all();
     }
   } catch (const ToolError& e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.msg; err_code = e.code; }
+  catch (const std::exception& e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.what(); }       // the workers must be joined before anything propagates
   { std::lock_guard<std::mutex> lk(mu); if (failed) next = n_blocks; }
   cv.notify_all();
   for (auto& t : th) t.join();
