@@ -83,6 +83,7 @@ struct GuideSpec {
   int32_t  min_score;                        // :239-243
   int32_t  k_edits;                          // candidate threshold of the bit-parallel scan: unit edits <= k_edits is necessary for score >= min_score
   int32_t  span;                             // max target columns any co-optimal alignment of an accepted end column can cover
+  int32_t  band_k;                           // max gap bases of either kind on such an alignment (== k_edits unless k_edits was capped at lp): decides the banded kernels
   int32_t  slots;                            // alignment slots per candidate end column = max(1, n_pams)
 };
 

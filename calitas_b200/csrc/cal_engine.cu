@@ -488,7 +488,8 @@ CAL_KERNEL __launch_bounds__(128) k_canon_warp(CanonArgs a, const uint32_t* gsta
           if (k == b || a.rank[base + k] != -2) continue;
           const calitas_hit& h = a.hits[base + k];
           const int32_t lo = h.start_offset > bs ? h.start_offset : bs, hi = h.end_offset < be ? h.end_offset : be;
-          if (hi - lo > max_overlap) a.rank[base + k] = -1;
+          int32_t ov = hi - lo; if (ov < 0) ov = 0;           // GuideAlignment.overlap clamps at 0, as canon_group does
+          if (ov > max_overlap) a.rank[base + k] = -1;
         }
       }
       __syncwarp();
@@ -577,6 +578,22 @@ CAL_KERNEL __launch_bounds__(256) k_gather_keepers(const calitas_hit* hits, cons
   if (i < n && keep[i]) out[pos[i]] = hits[idx[i]];
 }
 
+// Counters the host waits for are stored straight into mapped pinned host memory by these one-thread kernels (see dev::alloc_host_mapped).
+CAL_KERNEL k_publish_u64(const unsigned long long* src, unsigned long long* dst_host) {
+  *(volatile unsigned long long*)dst_host = *src;
+#ifndef CAL_HOSTSIM
+  __threadfence_system();
+#endif
+}
+// dst_host[0] = *a + *b (last exclusive-scan position + last flag = number of flagged items); dst_host[1] = *c when c is given
+CAL_KERNEL k_publish_sum(const uint32_t* a, const uint32_t* b, const unsigned long long* c, unsigned long long* dst_host) {
+  ((volatile unsigned long long*)dst_host)[0] = (unsigned long long)*a + (unsigned long long)*b;
+  if (c) ((volatile unsigned long long*)dst_host)[1] = *c;
+#ifndef CAL_HOSTSIM
+  __threadfence_system();
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------------------------------------------
 // k_int_peak: integer-issue microbenchmark for the roofline denominator (no integer peak in MEASURED_PEAKS.json).
 // Eight chains per thread; every statement reads two other chains, so ptxas cannot fold consecutive operations of a chain into one.
@@ -646,7 +663,7 @@ struct calitas_hitset {
   calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 
-enum { CNT_DEDUP_OVERFLOW = 7 };
+enum { CNT_GROUPS = 3, CNT_KEPT = 4, CNT_KEEPERS = 5 /* + 6: overflow flag as published */, CNT_DEDUP_OVERFLOW = 7 };
 enum { CE_SCAN_B = 0, CE_SCAN_E, CE_COUNT, CE_SORTED, CE_ALIGN_B, CE_ALIGN_E, CE_TAIL_B, CE_TAIL_E, CE_COPY_B, CE_COPY_E, CE_N };
 struct ChunkEvents { dev::Event ev[CE_N]; };
 
@@ -662,7 +679,8 @@ struct calitas_engine {
   DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, kept, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, kept_owned, sowned;
   // eight 64-bit device counters and their pinned host mirror: slots 0..2 = candidate counts of the three scan buffers (run_explicit uses 0),
   // slot CNT_DEDUP_OVERFLOW = k_dedup_keys' "a field does not fit its sort-key width" flag
-  unsigned long long* h_count = nullptr;       // pinned
+  unsigned long long* h_count = nullptr;       // pinned + mapped: the device stores into it through h_count_dev (no copy engine involved)
+  unsigned long long* h_count_dev = nullptr;   // device alias of h_count
   unsigned long long* d_count = nullptr;
   std::vector<PinnedBuf> pinned_pool;
   size_t cand_cap_hint = 1u << 20;
@@ -773,9 +791,8 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
     CAL_LAUNCH(k_mark_groups, blocks_for(n_cand, 128), 128, 0, s, 1, aa.cand, n_cand, P.key.col_bits, gflag); dev::launch_check("k_mark_groups"); ++e->launches;
     size_t tb2 = dev::exclusive_sum_u32_tmp((size_t)n_cand); e->tmp.ensure(tb2);
     dev::exclusive_sum_u32(e->tmp.p, tb2, gflag, gpos, (size_t)n_cand, s); ++e->launches;
-    uint32_t lp = 0, lf = 0;
-    dev::d2h(&lp, gpos + (n_cand - 1), 4, s); dev::d2h(&lf, gflag + (n_cand - 1), 4, s); dev::stream_sync(s);
-    const int64_t n_groups = (int64_t)lp + lf;
+    CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, gpos + (n_cand - 1), gflag + (n_cand - 1), (const unsigned long long*)nullptr, e->h_count_dev + CNT_GROUPS); dev::launch_check("k_publish_sum"); dev::stream_sync(s);
+    const int64_t n_groups = (int64_t)((volatile unsigned long long*)e->h_count)[CNT_GROUPS];
     CAL_LAUNCH(k_group_starts, blocks_for(n_cand, 128), 128, 0, s, 1, gflag, gpos, n_cand, e->idx.as<uint32_t>()); dev::launch_check("k_group_starts"); ++e->launches;
     dev::event_record(P.ev_align_b, s);
     CAL_LAUNCH(k_align_group, blocks_for(n_groups, 128), 128, 0, s, 1, aa, e->idx.as<uint32_t>(), n_groups); dev::launch_check("k_align_group");
@@ -796,10 +813,9 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   { CAL_LAUNCH(k_canon, blocks_for(n_cand, 128), 128, 0, s, 1, ca); dev::launch_check("k_canon"); ++e->launches; }
   tb = dev::exclusive_sum_u32_tmp((size_t)n_slots); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n_slots, s); ++e->launches;
-  uint32_t last_pos = 0, last_flag = 0;
-  dev::d2h(&last_pos, e->pos.as<uint32_t>() + (n_slots - 1), 4, s); dev::d2h(&last_flag, e->flag.as<uint32_t>() + (n_slots - 1), 4, s);
+  CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, e->pos.as<uint32_t>() + (n_slots - 1), e->flag.as<uint32_t>() + (n_slots - 1), (const unsigned long long*)nullptr, e->h_count_dev + CNT_KEPT); dev::launch_check("k_publish_sum");
   dev::stream_sync(s);
-  const int64_t n_kept = (int64_t)last_pos + last_flag;
+  const int64_t n_kept = (int64_t)((volatile unsigned long long*)e->h_count)[CNT_KEPT];
   n_alignments = n_slots;
   e->kept.ensure((size_t)n_kept * sizeof(calitas_hit)); e->kept_owned.ensure((size_t)n_kept);
   if (n_kept) { CAL_LAUNCH(k_gather_flagged, blocks_for(n_slots, 256), 256, 0, s, 1, aa.hits, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), e->slot_owned.as<uint8_t>(), n_slots, e->kept.as<calitas_hit>(), e->kept_owned.as<uint8_t>()); dev::launch_check("k_gather_flagged"); ++e->launches; }
@@ -833,12 +849,10 @@ int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out
   CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, skey, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, max_overlap, max_overlap >= 1 ? 1 : 0, strand_shift, L.start_bits, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
   tb = dev::exclusive_sum_u32_tmp((size_t)n); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n, s); ++e->launches;
-  uint32_t last_pos = 0, last_flag = 0;
-  dev::d2h(&last_pos, e->pos.as<uint32_t>() + (n - 1), 4, s); dev::d2h(&last_flag, e->flag.as<uint32_t>() + (n - 1), 4, s);
-  dev::d2h(e->h_count + CNT_DEDUP_OVERFLOW, e->d_count + CNT_DEDUP_OVERFLOW, 8, s);
+  CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, e->pos.as<uint32_t>() + (n - 1), e->flag.as<uint32_t>() + (n - 1), (const unsigned long long*)(e->d_count + CNT_DEDUP_OVERFLOW), e->h_count_dev + CNT_KEEPERS); dev::launch_check("k_publish_sum");
   dev::stream_sync(s);
-  if (e->h_count[CNT_DEDUP_OVERFLOW]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in removeOverlaps");
-  const int64_t nk = (int64_t)last_pos + last_flag;
+  if (((volatile unsigned long long*)e->h_count)[CNT_KEEPERS + 1]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in removeOverlaps");
+  const int64_t nk = (int64_t)((volatile unsigned long long*)e->h_count)[CNT_KEEPERS];
   if (nk == 0) return 0;
   e->out.ensure_keep((size_t)(out_n + nk) * sizeof(calitas_hit), (size_t)out_n * sizeof(calitas_hit), s);
   CAL_LAUNCH(k_gather_keepers, blocks_for(n, 256), 256, 0, s, 1, hits, sidx, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n, e->out.as<calitas_hit>() + out_n); dev::launch_check("k_gather_keepers"); ++e->launches;
@@ -875,7 +889,7 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
   dev::Stream s = e->stream; dev::set_device(e->device);
   e->launches = 0;
   dev::event_record(e->ev[0], s);
-  int slots = 1, banded = 1; for (auto& sp : specs) { slots = std::max(slots, sp.slots); banded = std::max(banded, sp.k_edits); }
+  int slots = 1, banded = 1; for (auto& sp : specs) { slots = std::max(slots, sp.slots); banded = std::max(banded, std::max(sp.k_edits, sp.band_k)); }
   if (banded > ALIGN_KB) banded = 0;
   e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
   e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
@@ -897,8 +911,8 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
       dev::event_record(e->ev[4], s);
       CAL_LAUNCH(k_scan_explicit, blocks_for(2 * nw, 128), 128, 0, s, 1, sa); dev::launch_check("k_scan_explicit"); ++e->launches;
       dev::event_record(e->ev[5], s);
-      dev::d2h(e->h_count, e->d_count, 8, s); dev::stream_sync(s);
-      n_cand = *e->h_count;
+      CAL_LAUNCH(k_publish_u64, 1, 1, 0, s, 1, e->d_count, e->h_count_dev); dev::launch_check("k_publish_u64"); dev::stream_sync(s);
+      n_cand = *(volatile unsigned long long*)e->h_count;
       if (n_cand <= e->cand_cap_hint) break;
       e->cand_cap_hint = (size_t)(n_cand + n_cand / 4);
     }
@@ -949,7 +963,7 @@ int calitas_engine_create(int32_t device_id, const calitas_costs* costs, calitas
     dev::check(cudaFuncSetAttribute(k_scan_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_LIMIT), "cudaFuncSetAttribute");
 #endif
     for (auto& ev : e->ev) ev = dev::event_create();
-    e->h_count = (unsigned long long*)dev::alloc_host(64);
+    { void* alias = nullptr; e->h_count = (unsigned long long*)dev::alloc_host_mapped(128, &alias); e->h_count_dev = (unsigned long long*)alias; }
     e->d_count = (unsigned long long*)dev::alloc(64);
     *out = e.release();
     return CALITAS_OK;
@@ -1085,7 +1099,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       ch.t_begin = 0; size_t t_end = ch.ts->tiles.size();
       if (chrom_idx >= 0) { ch.t_begin = t_end = 0; bool in = false; for (size_t t = 0; t < ch.ts->tiles.size(); ++t) { if (ch.ts->tiles[t].contig == chrom_idx) { if (!in) { ch.t_begin = t; in = true; } t_end = t + 1; } } }
       ch.n_tiles = t_end - ch.t_begin;
-      ch.slots = 1; ch.banded = 1; for (int g = g0; g < g1; ++g) { ch.slots = std::max(ch.slots, specs[(size_t)g].slots); ch.banded = std::max(ch.banded, specs[(size_t)g].k_edits); }
+      ch.slots = 1; ch.banded = 1; for (int g = g0; g < g1; ++g) { ch.slots = std::max(ch.slots, specs[(size_t)g].slots); ch.banded = std::max(ch.banded, std::max(specs[(size_t)g].k_edits, specs[(size_t)g].band_k)); }
       if (ch.banded > ALIGN_KB) ch.banded = 0;
       const int ng = g1 - g0;
       ch.smem = scan_smem_bytes(ng, ch.ts->tile_windows, window_size, ch.step);
@@ -1147,7 +1161,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         counts[6] += 1; counts[7] += ch.bases;
       }
       dev::event_record(ce.ev[CE_SCAN_E], ss);
-      dev::d2h(e->h_count + slot, e->d_count + slot, 8, ss);
+      CAL_LAUNCH(k_publish_u64, 1, 1, 0, ss, 1, e->d_count + slot, e->h_count_dev + slot); dev::launch_check("k_publish_u64");
       dev::event_record(ce.ev[CE_COUNT], ss);
     };
     PinnedBuf pin = take_pinned(e, std::max<size_t>(e->out_hits_hint, 1024) * sizeof(calitas_hit));
@@ -1160,7 +1174,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         unsigned long long n_cand = 0;
         for (;;) {
           dev::event_sync(ce.ev[CE_COUNT]);
-          n_cand = e->h_count[slot];
+          n_cand = ((volatile unsigned long long*)e->h_count)[slot];
           if (n_cand <= e->cand_cap_hint) break;
           // pool too small: grow and re-run this chunk's scan (and the one queued behind it), never truncate
           dev::stream_sync(ss);

@@ -105,15 +105,20 @@ GuideSpec make_guide_spec(const GuideDef& g, const Scores& sc, const calitas_lim
   // min_cost, so it has at most k_edits edits, hence unit edit distance <= k_edits (lossless prefilter, exact for the default costs).
   int min_cost = sc.abs_mm; if (sc.abs_genome_gap < min_cost) min_cost = sc.abs_genome_gap; if (sc.abs_guide_gap < min_cost) min_cost = sc.abs_guide_gap;
   if (min_cost <= 0 || sc.abs_guide_gap <= 0) throw LimitExceeded("net costs must be non-zero");
-  long long k = (long long)(-sc.worst_guide_diff) * s.d / min_cost;
+  const long long budget = (long long)(-sc.worst_guide_diff) * s.d;      // net cost an accepted alignment can spend
+  const long long k = budget / min_cost;
   s.k_edits = k > lp ? lp : (int)k;
-  // Deletions (genome bases opposite a guide gap) any co-optimal alignment can hold: never more than k_edits for an accepted
-  // column, and never so many that inserting the whole guide (score lp * target_gap) would beat it.
-  long long del_max = (long long)lp * sc.abs_genome_gap / sc.abs_guide_gap;
-  long long span = lp + (s.k_edits < del_max ? s.k_edits : del_max);
+  // Deletions (genome bases opposite a guide gap) any co-optimal alignment of an accepted end column can hold: each costs |guideGap|, so never
+  // more than budget / |guideGap| (NOT the capped k_edits: with a cheap guide gap an accepted alignment can hold more than lp of them), and never
+  // so many that inserting the whole guide (score lp * target_gap) would beat it.  Insertions: at most lp rows, each costing |genomeGap|.
+  const long long del_cost = budget / sc.abs_guide_gap, del_max = (long long)lp * sc.abs_genome_gap / sc.abs_guide_gap;
+  const long long dels = del_cost < del_max ? del_cost : del_max;
+  long long ins = budget / sc.abs_genome_gap; if (ins > lp) ins = lp;
+  const long long span = lp + dels;
   if (span > MAX_SPAN) throw LimitExceeded("costs/limits need a DP band wider than this build supports");
   s.span = (int)span;
-  if (lp + s.k_edits + s.g + g.pam_length() > CALITAS_MAX_OPS) throw LimitExceeded("alignment longer than CALITAS_MAX_OPS columns");
+  s.band_k = (int)(dels > ins ? dels : ins);   // a co-optimal path of an accepted end cell never leaves the 2 * band_k + 1 diagonals around the end cell's
+  if (lp + dels + s.g + g.pam_length() > CALITAS_MAX_OPS) throw LimitExceeded("alignment longer than CALITAS_MAX_OPS columns");
   return s;
 }
 

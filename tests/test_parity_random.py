@@ -298,3 +298,79 @@ def test_search_reference_many_small_contigs(eng):
         got = _lines(eng.search_reference(contigs, guide, raw=True, **kw))
         assert got == exp, guide
         assert len(exp) > 20
+
+
+def test_search_reference_cheap_guide_gap_costs(eng):
+    """Cost sets where one gap kind is far cheaper than the rest: an accepted alignment can then hold more than lp gap bases, so the DP rectangle
+    (GuideSpec.span) and the banded-kernel decision must follow the uncapped cost budget, not k_edits capped at lp.  With (-30,-30,-3,-60), d=3 the
+    fgbio-optimal alignment of guide[:10] + 15 A + mutated guide[:10] + guide[10:] holds 15 deletions, is filtered by diffs <= d, and nothing may be
+    reported in its place (the reference takes the optimal path, then filters)."""
+    rng = np.random.default_rng(31)
+    guide = "CTTGCCCCACAGGGCAGTAAngg"
+    proto = guide[:20]
+    second = list(proto[:10])
+    for i in (1, 4, 7):
+        second[i] = "ACGT"[("ACGT".index(second[i]) + 1) % 4]
+    site = proto[:10] + "A" * 15 + "".join(second) + proto[10:] + "AGG"
+    b = list(rng.choice(list("ACGT"), size=6000))
+    b[3000:3000 + len(site)] = list(site)
+    for k in range(12):                                   # plus ordinary sites, some with gaps
+        p = 200 + 450 * k
+        s = synth.mutate_protospacer(rng, proto.encode(), int(rng.integers(0, 4))).decode() + "TGG"
+        if k % 2:
+            s = rc(s)
+        if not (3000 - 60 < p < 3000 + 120):
+            b[p:p + len(s)] = list(s)
+    contigs = [("c", "".join(b).encode())]
+    for costs, d in (((-30, -30, -3, -60), 3), ((-30, -3, -30, -60), 3), ((-100, -100, -10, -200), 2), ((-120, -122, -121, -260), 5)):
+        exp = _lines(pyoracle.search_reference(contigs, guide, raw=True, costs=costs, d=d, window_size=1000))
+        got = _lines(eng.search_reference(contigs, guide, raw=True, costs=costs, d=d, window_size=1000))
+        assert got == exp, (costs, d)
+        target = "".join(b[2950:3150])
+        kw = dict(max_guide_diffs=d, max_pam_diffs=1, max_gaps=3, max_total_diffs=d + 4, max_overlap=10)
+        assert eng.align(guide, target, costs=costs, **kw) == pyoracle.align(guide, target, costs=costs, **kw), (costs, d)
+
+
+@pytest.mark.parametrize("period,O", [(7, 5), (10, 10), (11, 15), (13, 10)])
+def test_shard_cuts_inside_short_period_repeats(eng, period, O):
+    """removeOverlaps chains across a shard cut: a perfect-ish tandem repeat with a period SHORTER than an alignment, several kb long (longer than the
+    two halo windows), so that hits overlap their neighbours by >= -O and the greedy chain (A dropped for B, B for C, ...) runs through the cut.
+    Units are mutated now and then so that scores vary along the chain."""
+    rng = np.random.default_rng(1000 + period)
+    unit = "CTTGCCCCACAGGGCAGTAA"[:period]
+    n_units = 6500 // period
+    parts = []
+    for _ in range(n_units):
+        u = list(unit)
+        if rng.random() < 0.08:
+            u[int(rng.integers(period))] = "ACGT"[int(rng.integers(4))]
+        parts.append("".join(u))
+    head = "".join("ACGT"[i] for i in rng.integers(0, 4, 700))
+    contigs = [("rep0", (head + "".join(parts) + head[::-1]).encode())]
+    proto = (unit * 4)[:20]                                # the repeat itself is the best guide for dense, chained hits
+    guides = [proto + "nrg", proto]
+    exp = []
+    for gd, gid in zip(guides, "ab"):
+        lines = _lines(pyoracle.search_reference(contigs, gd, guide_id=gid, raw=True, O=O, p=3))
+        exp += lines if not exp else lines[1:]
+    assert len(exp) > 50
+    for n_shards in (2, 3, 5):
+        got = _lines(eng.t.search_reference_batch(contigs, guides, ["a", "b"], n_shards=n_shards, O=O, p=3))
+        assert got == exp, (period, O, n_shards)
+
+
+def test_align_best_mode_negative_overlap_cannot_happen_but_wide_costs_clamp(eng):
+    """Explicit mode with wide thresholds takes the warp-per-group canonicaliser on the GPU (k_canon_warp); max_overlap < 0 must behave like
+    GuideAlignment.overlap's clamp at 0 (nothing overlaps by less than 0, so every alignment after the first is dropped ... except disjoint ones,
+    whose clamped overlap 0 > -1 drops them too)."""
+    rng = np.random.default_rng(77)
+    guide = "CTTGCCCCACAGGGCAGTAAngg"
+    for k in range(6):
+        t = list(rng.choice(list("ACGT"), size=150))
+        for p in (10, 80):
+            s = synth.mutate_protospacer(rng, guide[:20].encode(), int(rng.integers(0, 3))).decode() + "TGG"
+            t[p:p + len(s)] = list(s)
+        target = "".join(t)
+        for O in (-1, 0, 3):
+            kw = dict(max_guide_diffs=8, max_pam_diffs=1, max_gaps=3, max_total_diffs=12, max_overlap=O)     # d = 8 -> k_edits > 6: the wide kernels
+            assert eng.align(guide, target, **kw) == pyoracle.align(guide, target, **kw), (k, O)
