@@ -3,20 +3,22 @@
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                      (CPU arm: the oracle restatement of the reference on the host cores)
+    python bench.py --workload config4 ...                    (the other BASELINE.json configurations: config1 .. config5, see WORKLOADS)
 
-One step = one calitas_search call (include/calitas_b200.h) of G guides against this rank's contig-range shard of the 3.1-Gbp genome:
-guides go host->device, every kernel of the path runs (scan, sort, align, canonicalise, removeOverlaps + sort), final hit records
-come device->host.  Shards are independent: no collective on the data path.
-  value  = genome bp x guides / device time of the step (CUDA events on the engine's stream, max over ranks)
+default workload: one step = one calitas_search call (include/calitas_b200.h) of 100 guides against this rank's contig-range shard of the
+3.1-Gbp genome: guides go host->device, every kernel of the path runs (scan, sort, align, canonicalise, removeOverlaps + sort), final hit
+records come device->host.  Shards are independent: no collective on the data path.
+  value  = genome bp x guides / device time of the step (CUDA events on the engine's streams, max over ranks)
   e2e    = same, wall clock around the C-ABI call with host buffers (guide strings in, hit records out), max over ranks
+  parity_check = the GPU hits of the timed step inside the cpu_baseline sample region, rendered and compared row by row with the oracle
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -26,9 +28,20 @@ sys.path.insert(0, ROOT)
 # shipped library, see DESIGN.md "k_scan_tiled"; per 8 columns x 2 guides: 112 LOP3 + 32 LEA.HI + 8 VIMNMX3 | 56 IMAD.IADD | 16 LDS + 8 LDS.U8):
 # ALU pipe 7 LOP3 + 2 LEA.HI + 0.5 VIMNMX3; FMA pipe 3.5 IMAD.IADD; LSU 1 LDS + 0.5 LDS.U8.
 ALU_OPS_PER_COLUMN = 9.5
-ISSUE_SLOTS_PER_COLUMN = 14.5
-NCU_DRAM_OVER_ALGORITHMIC = 406.4 / 386.2   # k_scan_tiled, profiles/r01f_summary.txt
+NCU_SCAN = {"dram_over_algorithmic": 406.4 / 386.2, "alu_pipe_pct": 88.6, "issue_active_pct": 71.9, "fma_pipe_pct": 17.9,
+            "source": "profiles/r01f_summary.txt (ncu --set full of k_scan_tiled, d=5); d=6: profiles/r02a_summary.txt (85.9 / 72.8 / 17.6)"}
 REF_OPS_PER_BP_GUIDE = 240   # 2 strands x 20 rows x 6 int32 ops of the reference's recurrence
+
+# BASELINE.json configs; "default" is the north_star target (100 guides, defaults) the headline metric is quoted on
+WORKLOADS = {
+    "default": dict(kind="search", genome="hg38", guides=100, d=5, p=1, g=3, pam="nrg", aux=""),
+    "config1": dict(kind="search", genome="config1", guides=1, d=5, p=1, g=3, pam="nrg", aux=""),
+    "config2": dict(kind="a2r", genome="hg38", guides=100, tasks=1_000_000, window=60),
+    "config3": dict(kind="search", genome="hg38", guides=1, d=5, p=1, g=3, pam="nrg", aux=""),
+    "config4": dict(kind="search", genome="hg38", guides=100, d=6, p=1, g=2, pam="ngg", aux="nag"),
+    "config5": dict(kind="vcf", genome="hg38", guides=1, d=5, p=1, g=3, pam="nrg", aux="", records=3_000_000),
+}
+METRIC = "Gbp*guides/s SearchReference (hg38-size synthetic)"
 
 
 def parse_args():
@@ -37,29 +50,53 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--guides", type=int, default=100, help="guides per step (north_star: 100 guides, defaults d=5 p=1 g=3)")
+    ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS))
+    ap.add_argument("--guides", type=int, default=None, help="guides per step (north_star: 100 guides, defaults d=5 p=1 g=3)")
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale; 1.0 = 3.1 Gbp with hg38 contig lengths")
-    ap.add_argument("--max-guide-diffs", type=int, default=5)
-    ap.add_argument("--max-pam-mismatches", type=int, default=1)
-    ap.add_argument("--max-gaps", type=int, default=3)
-    ap.add_argument("--pam", default="nrg", help="PAM appended to every guide ('' = PAM-less run of BASELINE configs[3])")
-    ap.add_argument("--aux-pams", default="", help="comma-separated auxiliary PAMs (BASELINE configs[3]: --pam ngg --aux-pams nag)")
+    ap.add_argument("--max-guide-diffs", type=int, default=None)
+    ap.add_argument("--max-pam-mismatches", type=int, default=None)
+    ap.add_argument("--max-gaps", type=int, default=None)
+    ap.add_argument("--pam", default=None, help="PAM appended to every guide ('' = PAM-less run of BASELINE configs[3])")
+    ap.add_argument("--aux-pams", default=None, help="comma-separated auxiliary PAMs (BASELINE configs[3]: --pam ngg --aux-pams nag)")
+    ap.add_argument("--tasks", type=int, default=None, help="config2: (guide, locus) pairs per step")
+    ap.add_argument("--records", type=int, default=None, help="config5: VCF records genome-wide")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--lib", default=None, help="alternative build of libcalitas_b200.so (kernel A/B experiments); default = the product library")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
-    return ap.parse_args()
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    for key, val in (("guides", args.guides), ("d", args.max_guide_diffs), ("p", args.max_pam_mismatches), ("g", args.max_gaps), ("pam", args.pam), ("aux", args.aux_pams),
+                     ("tasks", args.tasks), ("records", args.records)):
+        if val is not None:
+            w[key] = val
+    args.w = w
+    return args
 
 
-def guide_list(args):
-    """The BASELINE guide's protospacer + random 20-mers (seed 20260103), all with --pam / --aux-pams."""
+def guide_list(w):
+    """The BASELINE guide's protospacer + random 20-mers (seed 20260103), all with the workload's PAM / auxiliary PAMs."""
     from calitas_b200 import synth
-    aux = [a for a in args.aux_pams.split(",") if a]
-    seqs = [synth.BASELINE_GUIDE[:20] + args.pam] + synth.random_guides(max(0, args.guides - 1), pam=args.pam)
+    pam = w.get("pam", "nrg")
+    aux = [a for a in w.get("aux", "").split(",") if a]
+    seqs = [synth.BASELINE_GUIDE[:20] + pam] + synth.random_guides(max(0, w["guides"] - 1), pam=pam)
     return [(s, aux) for s in seqs] if aux else seqs
 
 
 def guide_text(g):
     return g if isinstance(g, str) else g[0]
+
+
+def guide_aux(g):
+    return () if isinstance(g, str) else tuple(g[1])
+
+
+def make_genome(w, scale, guides):
+    from calitas_b200 import synth
+    texts = [guide_text(g) for g in guides]
+    if w["genome"] == "config1":
+        return synth.config1_genome(scale=scale, n_sites=200, guides=texts)
+    return synth.hg38_like_genome(scale, guides=texts, sites_per_guide=200)
 
 
 class ClockSampler:
@@ -111,60 +148,146 @@ class ClockSampler:
         return out
 
 
-def cpu_sample(genome, guides, threads, target_seconds, limits_kw, sample_bp=8_000_000):
-    """Times the oracle (C++ restatement of the reference algorithm, oracle/) on a bounded sample of the same workload."""
+def limits_kw(w):
+    return dict(d=w["d"], p=w["p"], g=w["g"])
+
+
+def oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
     pyoracle.build()
-    # sample: the first contig's bases after the telomere N block
-    length = min(genome.lengths[0], sample_bp + 20000)
-    bases = bytes(genome.range(0, 0, length))
-    contigs = [(genome.names[0], bases)]
+    return pyoracle
+
+
+def _row_tuples_oracle(rows, offset=0):
+    return [(r["coordinate_start"] + offset, r["coordinate_end"] + offset, r["strand"], r["score"], r["cigar"], r["padded_guide"], r["padded_alignment"], r["padded_target"],
+             r["total_mm_plus_gaps"], r["pam_used"]) for r in rows]
+
+
+def _row_tuples_engine(engine, records, guides, contigs):
+    from calitas_b200 import testing
+    text = engine.render_alignments(records, guides, contigs, upper_case=True)
+    rows = testing._table(text, testing._INT_GA)
+    return [(x["guideStartOffset"], x["guideEndOffset"], x["strand"], x["score"], x["cigar"], x["paddedGuide"], x["paddedAlignment"], x["paddedTarget"], x["edits"],
+             "".join(ch for ch in x["guide"] if ch.islower())) for x in rows]
+
+
+def cpu_sample_search(genome, w, guides, threads, target_seconds, sample_bp, records=None, engine=None):
+    """Times the oracle (C++ restatement of the reference algorithm, oracle/) on a bounded sample of the same workload: the first sample_bp bases
+    of the first contig, one guide after the other until target_seconds have passed.  With `records` (the GPU hits of the timed step) the
+    oracle's rows inside the sample are compared with the engine's, all alignment columns: parity_check."""
+    import numpy as np
+    po = oracle()
+    length = min(genome.lengths[0], sample_bp)
+    bases = genome.range(0, 0, length)
+    contigs = [(genome.names[0], bytes(bases))]
     done, t_total, n_hits = 0, 0.0, 0
-    t0 = time.perf_counter()
+    parity = {"checked_rows": 0, "guides": 0, "equal": True, "region": "%s:1500-%d" % (genome.names[0], length - 1500)} if records is not None else None
+    h_gpu, h_cpu = hashlib.sha256(), hashlib.sha256()
+    kw = limits_kw(w)
     while done < len(guides) and (done == 0 or t_total < target_seconds):
         g = guides[done]
-        n, _ = pyoracle.search_reference_count(contigs, guide_text(g), aux_pams=() if isinstance(g, str) else g[1], threads=threads, **limits_kw)
-        n_hits += n
+        t0 = time.perf_counter()
+        text = po.search_reference(contigs, guide_text(g), aux_pams=guide_aux(g), threads=threads, raw=True, **kw)
+        t_total += time.perf_counter() - t0
+        rows = po.hits_table(text)
+        n_hits += len(rows)
+        if parity is not None:
+            exp = [t for t in _row_tuples_oracle(rows) if t[0] >= 1500 and t[1] <= length - 1500]
+            m = records[(records["guide_idx"] == done) & (records["contig_idx"] == 0) & (records["guide_start_offset"] >= 1500) & (records["guide_end_offset"] <= length - 1500)]
+            got = _row_tuples_engine(engine, m, guides, [(genome.names[0], bases)] + [(n, np.zeros(0, dtype=np.uint8)) for n in genome.names[1:]])
+            parity["checked_rows"] += len(exp)
+            parity["guides"] += 1
+            parity["equal"] = parity["equal"] and got == exp
+            h_gpu.update(repr(got).encode()); h_cpu.update(repr(exp).encode())
         done += 1
-        t_total = time.perf_counter() - t0
     value = len(bases) * done / t_total / 1e9
+    if parity is not None:
+        parity["sha256_gpu"], parity["sha256_oracle"] = h_gpu.hexdigest()[:16], h_cpu.hexdigest()[:16]
     return {"value": value, "unit": "Gbp*guides/s", "cores": threads, "kind": "port",
             "sample": "%d guide(s) x first %.1f Mbp of %s, same windows/limits, %d threads, %.1f s; C++ restatement of the reference algorithm (the JVM reference cannot run here)"
-                      % (done, len(bases) / 1e6, genome.names[0], threads, t_total), "hits": n_hits}
+                      % (done, len(bases) / 1e6, genome.names[0], threads, t_total), "hits": n_hits}, parity
 
 
+def workload_config(args, genome, guides):
+    w = args.w
+    if w["kind"] == "a2r":
+        return {"workload": "AlignToReference batch (BASELINE configs[1]): %d (guide, locus) pairs, --window-size %d, best mode, %d distinct guides, %.2f Gbp synthetic hg38-sized genome"
+                            % (w["tasks"], w["window"], w["guides"], genome.total() / 1e9), "name": args.workload, "tasks_per_step": w["tasks"], "window_size": w["window"],
+                "genome_bp": genome.total(), "l2": "task list and hit records larger than L2 per step; the packed reference (1.55 GB) is read at random loci",
+                "parallelism": "tasks split evenly across ranks, 1 rank per GPU, no collective"}
+    pams = ",".join([w["pam"] or "(none)"] + [a for a in w["aux"].split(",") if a])
+    cfg = {"workload": "SearchReference, %d guide%s (CTTGCCCCACAGGGCAGTAA%s, PAMs %s) vs %.2f Gbp synthetic %s genome (%d contigs), d=%d p=%d g=%d O=10 w=1000, contig-range sharded"
+                       % (w["guides"], "s" if w["guides"] > 1 else "", " + random 20-mers" if w["guides"] > 1 else "", pams, genome.total() / 1e9,
+                          "hg38-sized" if w["genome"] == "hg38" else "config-1", len(genome.lengths), w["d"], w["p"], w["g"]),
+           "name": args.workload, "guides_per_step": w["guides"], "genome_bp": genome.total(), "window_size": 1000, "max_guide_diffs": w["d"],
+           "max_pam_mismatches": w["p"], "max_gaps_between_guide_and_pam": w["g"], "pams": pams, "max_overlap": 10, "dedup": "removeOverlaps+sort on device",
+           "l2": "inputs larger than L2 (packed reference shard per scan launch >> 126 MB)" if genome.total() > 5e8 else "L2 flushed between steps by a 256-MB device write",
+           "parallelism": "contig-range shards, 1 rank per GPU, no collective"}
+    if w["kind"] == "vcf":
+        cfg["workload"] += "; -v synthetic PrepareVcf-shaped VCF, %d records genome-wide, max-variants 16" % w["records"]
+        cfg["vcf_records"] = w["records"]
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------------
+# reference arm: the oracle port on the host cores, a bounded sample of the workload per step
+# ------------------------------------------------------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     from calitas_b200 import synth
-    guides = guide_list(args)
-    genome = synth.hg38_like_genome(args.scale, guides=[guide_text(g) for g in guides], sites_per_guide=200)
+    w = args.w
+    guides = guide_list(w)
+    genome = make_genome(w, args.scale, guides)
     threads = os.cpu_count() or 1
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import pyoracle
-    pyoracle.build()
-    sample_bp = 4_000_000
-    length = min(genome.lengths[0], sample_bp + 20000)
-    contigs = [(genome.names[0], bytes(genome.range(0, 0, length)))]
+    po = oracle()
     times = []
-    for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        g = guides[it % len(guides)]
-        pyoracle.search_reference_count(contigs, guide_text(g), aux_pams=() if isinstance(g, str) else g[1], threads=threads,
-                                        d=args.max_guide_diffs, p=args.max_pam_mismatches, g=args.max_gaps)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    value = length / (ms * 1e-3) / 1e9
-    sample = "each step: 1 guide x first %.1f Mbp of %s (bounded sample of the workload), oracle C++ restatement, %d host threads" % (length / 1e6, genome.names[0], threads)
+    if w["kind"] == "a2r":
+        metric, unit = "M pairs/s AlignToReference (window 60, best mode)", "Mpairs/s"
+        n_sample = 4000
+        length = min(genome.lengths[0], 20_000_000)
+        sub = synth.Genome([genome.names[0]], [length], genome.seed, [[b for b in genome.n_blocks[0] if b[1] <= length]], [[p for p in genome.planted[0] if p[0] + 64 < length]])
+        contigs = [(genome.names[0], bytes(genome.range(0, 0, length)))]
+        tasks = synth.a2r_tasks(sub, [guide_text(g) for g in guides], n_sample)
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            po.align_to_reference(contigs, tasks, window_size=w["window"], threads=threads, raw=True)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * sum(times) / len(times)
+        value = n_sample / (ms * 1e-3) / 1e6
+        sample = "each step: %d (guide, locus) pairs on the first %.0f Mbp of %s (bounded sample), oracle C++ restatement, %d host threads" % (n_sample, length / 1e6, genome.names[0], threads)
+    else:
+        metric, unit = METRIC, "Gbp*guides/s"
+        sample_bp = 4_000_000
+        length = min(genome.lengths[0], sample_bp + 20000)
+        bases = genome.range(0, 0, length)
+        contigs = [(genome.names[0], bytes(bases))]
+        vcf = None
+        if w["kind"] == "vcf":
+            vcf = synth.synthetic_vcf(synth.Genome([genome.names[0]], [length], genome.seed), [bases], max(1, int(w["records"] * length / genome.total())))
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            g = guides[it % len(guides)]
+            if vcf is None:
+                po.search_reference_count(contigs, guide_text(g), aux_pams=guide_aux(g), threads=threads, **limits_kw(w))
+            else:
+                po.search_reference(contigs, guide_text(g), aux_pams=guide_aux(g), threads=threads, vcf_text=vcf, raw=True, **limits_kw(w))
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * sum(times) / len(times)
+        value = length / (ms * 1e-3) / 1e9
+        sample = "each step: 1 guide x first %.1f Mbp of %s%s (bounded sample of the workload), oracle C++ restatement, %d host threads" % (
+            length / 1e6, genome.names[0], " with its share of the VCF records" if vcf else "", threads)
     print(json.dumps({
-        "impl": "reference", "metric": "Gbp*guides/s SearchReference (hg38-size synthetic)", "value": value, "unit": "Gbp*guides/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
-        "data": "synthetic", "config": workload_config(args, genome),
-        "cpu_baseline": {"value": value, "unit": "Gbp*guides/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "Gbp*guides/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "data": "synthetic", "config": workload_config(args, genome, guides),
+        "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def bind_to_gpu_numa_node(gpu_index):
@@ -186,65 +309,116 @@ def bind_to_gpu_numa_node(gpu_index):
     return None
 
 
-def workload_config(args, genome):
-    pams = ",".join([args.pam or "(none)"] + [a for a in args.aux_pams.split(",") if a])
-    return {"workload": "SearchReference, %d guides (CTTGCCCCACAGGGCAGTAA + random 20-mers, PAMs %s) vs %.2f Gbp synthetic hg38-sized genome (24 contigs), "
-                        "d=%d p=%d g=%d O=10 w=1000, contig-range sharded" % (args.guides, pams, genome.total() / 1e9, args.max_guide_diffs, args.max_pam_mismatches, args.max_gaps),
-            "guides_per_step": args.guides, "genome_bp": genome.total(), "window_size": 1000, "max_guide_diffs": args.max_guide_diffs,
-            "max_pam_mismatches": args.max_pam_mismatches, "max_gaps_between_guide_and_pam": args.max_gaps, "pams": pams, "max_overlap": 10,
-            "dedup": "removeOverlaps+sort on device",
-            "l2": "inputs larger than L2 (packed reference shard per scan launch >> 126 MB)", "parallelism": "contig-range shards, 1 rank per GPU, no collective"}
+class Job:
+    """Process-group plumbing shared by the workloads: barrier + synchronize on both sides of the timed region, max/sum over ranks."""
 
-
-def main():
-    args = parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference_arm(args, rank, world)
-        return
-
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # the version banner would land on stdout next to the one JSON line
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from calitas_b200 import synth
-    from calitas_b200._capi import Engine, Library, Limits
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("CALITAS_BENCH_BIND", "1") != "0" else None
-    if os.environ.get("CALITAS_BENCH_VERBOSE"):
-        print("[bench] rank %d cpus %s" % (rank, sorted(os.sched_getaffinity(0))), file=sys.stderr)
-    if world > 1:
-        # NCCL prints its version banner on stdout when the first communicator comes up; the contract is ONE JSON line on stdout,
-        # so stdout is pointed at stderr while the process group initialises.
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.numa = bind_to_gpu_numa_node(self.local_rank) if self.world > 1 and os.environ.get("CALITAS_BENCH_BIND", "1") != "0" else None
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            # NCCL prints its version banner on stdout when the first communicator comes up; the contract is ONE JSON line on stdout,
+            # so stdout is pointed at stderr while the process group initialises.
             sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
             try:
-                import ctypes
-                ctypes.CDLL(None).fflush(None)        # NCCL printf()s into the C stdio buffer: drain it while fd 1 still points at stderr
-            except Exception:
-                pass
-            os.dup2(saved, 1)
-            os.close(saved)
-    guides = guide_list(args)
-    genome = synth.hg38_like_genome(args.scale, guides=[guide_text(g) for g in guides], sites_per_guide=200)
-    n = len(genome.lengths)
-    engine = Engine(local_rank, lib=Library(os.path.abspath(args.lib)) if args.lib else None)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                try:
+                    import ctypes
+                    ctypes.CDLL(None).fflush(None)        # NCCL printf()s into the C stdio buffer: drain it while fd 1 still points at stderr
+                except Exception:
+                    pass
+                os.dup2(saved, 1)
+                os.close(saved)
+        visible = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+        self.sampler = ClockSampler((visible[:self.world] if len(visible) >= self.world else range(self.world)) if self.rank == 0 else [])
+        self._flush = None
 
-    # ---- this rank's contig-range shard: generate only the bases it holds ------------------------------------------------------
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def flush_l2(self):
+        """256-MB device write between steps, for workloads whose inputs fit the 126-MB L2."""
+        if self._flush is None:
+            self._flush = self.torch.empty(256 << 20, dtype=self.torch.uint8, device="cuda")
+        self._flush.add_(1)
+
+    def reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def gather(self, values):
+        if not self.dist:
+            return None
+        mine = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        allr = self.torch.zeros(self.world * len(values), dtype=self.torch.float64, device="cuda")
+        self.dist.all_gather_into_tensor(allr, mine)
+        return allr.view(self.world, len(values)).tolist()
+
+    def timed(self, step, warmup, steps, flush=False):
+        """W untimed steps, then exactly K steps between barrier + synchronize; returns (per-step stats, local wall seconds of the K steps, clocks)."""
+        self.sampler.start()                 # nvidia-smi needs ~1 s to start: launched before the warm-up so that it is sampling during the timed steps
+        for _ in range(warmup):
+            if flush:
+                self.flush_l2()
+            step()
+        self.barrier()
+        t_begin = time.perf_counter()
+        stats = []
+        for _ in range(steps):
+            if flush:
+                self.flush_l2()
+            stats.append(step())
+        self.torch.cuda.synchronize()
+        t_local = time.perf_counter() - t_begin
+        self.barrier()
+        return stats, t_local, self.sampler.stop()
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def peaks_file():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------------
+# SearchReference workloads (default, config1, config3, config4)
+# ------------------------------------------------------------------------------------------------------------------------------------------
+def run_search(args, job):
     import ctypes as C
+    import numpy as np
+    from calitas_b200._capi import Engine, Library, Limits
+    w = args.w
+    rank, world = job.rank, job.world
+    guides = guide_list(w)
+    genome = make_genome(w, args.scale, guides)
+    n = len(genome.lengths)
+    engine = Engine(job.local_rank, lib=Library(os.path.abspath(args.lib)) if args.lib else None)
+    # ---- this rank's contig-range shard: generate only the bases it holds ------------------------------------------------------
     L = (C.c_int64 * n)(*genome.lengths)
     ob, oe, hb, he = [(C.c_int64 * n)() for _ in range(4)]
     halo = 4 * 1000
@@ -257,54 +431,34 @@ def main():
     t_load = time.perf_counter() - t0
     own_bp = sum(oe[c] - ob[c] for c in range(n))
     del arrays
-    lim = Limits(args.max_guide_diffs, args.max_pam_mismatches, args.max_gaps, -1, 10)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    lim = Limits(w["d"], w["p"], w["g"], -1, 10)
+    keep_records = rank == 0 and not args.no_parity_check
+    last = {}
 
     def step():
+        old = last.pop("hs", None)           # the previous step's result set goes back to the engine's pinned pool before the call, as a caller's loop would do
+        if old is not None:
+            old.free()
         t0 = time.perf_counter()
         hs = engine.search(ref, guides, lim, window_size=1000, dedup=True)
         wall = time.perf_counter() - t0
         st = hs.stats()
         st["hits"] = len(hs)
         st["wall_ms"] = wall * 1e3
-        hs.free()
+        if keep_records:
+            last["hs"] = hs                  # the last timed step's hits are what parity_check compares with the oracle
+        else:
+            hs.free()
         return st
 
-    # rank 0 samples the job's GPUs: CUDA_VISIBLE_DEVICES entries (indices or UUIDs, both accepted by nvidia-smi -i) when the launcher set it
-    visible = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
-    sampler = ClockSampler((visible[:world] if len(visible) >= world else range(world)) if rank == 0 else [])
-    sampler.start()                      # nvidia-smi needs ~1 s to start: launched before the warm-up so that it is sampling during the timed steps
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    t_begin = time.perf_counter()
-    stats = [step() for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    t_local = time.perf_counter() - t_begin
-    barrier()
-    clocks = sampler.stop()
-
+    small = genome.total() < 5e8
+    stats, t_local, clocks = job.timed(step, args.warmup, args.steps, flush=small)
     dev_ms = sum(s["ms_total"] for s in stats) / args.steps        # CUDA events, whole step on the device incl. D2H of hits
-    wall_ms = 1e3 * t_local / args.steps
+    wall_ms = sum(s["wall_ms"] for s in stats) / args.steps if small else 1e3 * t_local / args.steps
     scan_ms = sum(s["ms_scan"] for s in stats) / args.steps
-    red = torch.tensor([dev_ms, wall_ms, scan_ms], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(stats[-1]["hits"]), float(own_bp), float(stats[-1]["candidates"])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    per_rank = None
-    if world > 1:
-        mine = torch.tensor([dev_ms, scan_ms, float(stats[-1]["candidates"])], dtype=torch.float64, device="cuda")
-        allr = torch.zeros(world * 3, dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(allr, mine)
-        per_rank = allr.view(world, 3).tolist()
-    dev_ms_max, wall_ms_max, scan_ms_max = [float(x) for x in red.tolist()]
-    total_hits, total_bp, total_cand = [float(x) for x in tot.tolist()]
+    dev_ms_max, wall_ms_max, scan_ms_max = job.reduce([dev_ms, wall_ms, scan_ms], "max")
+    total_hits, total_bp, total_cand = job.reduce([float(stats[-1]["hits"]), float(own_bp), float(stats[-1]["candidates"])], "sum")
+    per_rank = job.gather([dev_ms, scan_ms, float(stats[-1]["candidates"])])
 
     if rank == 0:
         G = len(guides)
@@ -312,25 +466,19 @@ def main():
         value = bpg / (dev_ms_max * 1e-3) / 1e9
         e2e = bpg / (wall_ms_max * 1e-3) / 1e9
         st = stats[-1]
-        # dominant kernel: k_scan_tiled (rank 0's launches)
-        launches = max(1, st["scan_launches"])
+        launches = max(1, st["scan_launches"])     # dominant kernel: k_scan_tiled (rank 0's launches)
         scan_launch_ms = st["ms_scan"] / launches
         alg_bytes = st["bases_scanned"] / launches * 0.5                     # 4-bit packed reference, read once per launch
         hbm_achieved = alg_bytes / (scan_launch_ms * 1e-3) / 1e9
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = peaks_file()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         int_peaks = {k: engine.microbench_int(i) for i, k in enumerate(("alu_lop3", "fma_imad", "both_lop3_imad", "fma_imad_hi", "alu_lea_hi"))}
-        own0 = sum(oe[c] - ob[c] for c in range(n))
-        columns = own0 * G * 2                                                  # rank 0's shard: one Myers column per base, strand and guide
+        columns = own_bp * G * 2                                                # rank 0's shard: one Myers column per base, strand and guide
         int_achieved = columns * ALU_OPS_PER_COLUMN / (st["ms_scan"] * 1e-3) / 1e12
         out = {
-            "metric": "Gbp*guides/s SearchReference (hg38-size synthetic)", "value": value, "unit": "Gbp*guides/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": "Gbp*guides/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": workload_config(args, genome),
+            "config": workload_config(args, genome, guides),
             "e2e": {"value": e2e, "unit": "Gbp*guides/s", "ms_per_step": wall_ms_max, "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
                     "api": "calitas_search (C ABI): guide strings + limits in host memory -> deduplicated, sorted hit records in pinned host memory",
                     "reference": "the packed reference shard stays resident in HBM between calls, like the reference's in-memory FASTA; uploading and packing it "
@@ -339,32 +487,189 @@ def main():
             "gpu_launches": int(sum(s["launches"] for s in stats)),
             "clocks": clocks,
             "roofline": {"kernel": "k_scan_tiled", "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
-                         "traffic": alg_bytes * NCU_DRAM_OVER_ALGORITHMIC, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                         "traffic": alg_bytes * NCU_SCAN["dram_over_algorithmic"], "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
                          "(profiles/r01f_summary.txt: 388.2 + 18.1 = 406.4 MB for 386.2 MB algorithmic), scaled to this launch's algorithmic bytes", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "streaming read of the 4-bit packed shard once per launch; the kernel is integer-ALU-bound (see roofline_int), so the HBM fraction is small by design",
                          "avg_launch_ms": scan_launch_ms, "launches_per_step": launches, "share_of_step": st["ms_scan"] / st["ms_total"]},
             "roofline_int": {"kernel": "k_scan_tiled", "bound": "int_alu_pipe", "achieved": int_achieved, "peak": int_peaks["alu_lop3"], "unit": "Tiop/s (ALU-pipe thread instructions)",
                              "frac": int_achieved / int_peaks["alu_lop3"] if int_peaks["alu_lop3"] else None,
-                             "alu_ops_per_column": ALU_OPS_PER_COLUMN, "issue_slots_per_column": ISSUE_SLOTS_PER_COLUMN,
-                             "issue_frac": columns * ISSUE_SLOTS_PER_COLUMN / (st["ms_scan"] * 1e-3) / 1e12 / int_peaks["both_lop3_imad"] if int_peaks["both_lop3_imad"] else None,
+                             "alu_ops_per_column": ALU_OPS_PER_COLUMN,
                              "peak_source": "measured on this GPU by calitas_microbench_int (LOP3 chains; no integer peak in MEASURED_PEAKS.json)",
-                             "measured_peaks_tiops": int_peaks,
+                             "measured_peaks_tiops": int_peaks, "ncu": NCU_SCAN,
                              "reference_equivalent_tiops": bpg * REF_OPS_PER_BP_GUIDE / (dev_ms_max * 1e-3) / 1e12,
                              "gcups_equivalent": value * 40},
             "breakdown_ms": {"scan": st["ms_scan"], "align": st["ms_align"], "sort_canon_dedup": st["ms_other"], "d2h": st["ms_d2h"], "wall": st["wall_ms"]},
             "counts": {"hits": total_hits, "candidates": total_cand, "windows_rank0": st["windows"], "genome_bp": genome.total(), "shard_bp_sum": total_bp},
             "setup_s": {"generate": t_gen, "load_and_pack": t_load},
         }
-        out["config"]["cpu_binding_rank0"] = ("cpus %d-%d (GPU-local NUMA node)" % (numa[0], numa[-1])) if numa else "none"
+        out["config"]["cpu_binding_rank0"] = ("cpus %d-%d (GPU-local NUMA node)" % (job.numa[0], job.numa[-1])) if job.numa else "none"
         if per_rank is not None:
             out["per_rank"] = {"ms_per_step": [round(r[0], 3) for r in per_rank], "scan_ms": [round(r[1], 3) for r in per_rank], "candidates": [int(r[2]) for r in per_rank]}
+        records = last["hs"].records() if keep_records and "hs" in last else None
+        threads = os.cpu_count() or 1
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_sample(genome, guides, os.cpu_count() or 1, args.cpu_seconds, dict(d=args.max_guide_diffs, p=args.max_pam_mismatches, g=args.max_gaps))
+            # a 100-Mbp slice of the genome (and the whole 10-Mbp genome for config1), all host cores
+            out["cpu_baseline"], out["parity_check"] = cpu_sample_search(genome, w, guides, threads, args.cpu_seconds, 100_000_000, records, engine)
+        elif records is not None:              # N > 1 (or no baseline wanted): a light check on rank 0's first 2 Mbp, one guide
+            _, out["parity_check"] = cpu_sample_search(genome, w, guides[:1], threads, 0.0, 2_000_000, records, engine)
+        print(json.dumps(out))
+    if "hs" in last:
+        last["hs"].free()
+    ref.free()
+    engine.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------------
+# config2: AlignToReference batch
+# ------------------------------------------------------------------------------------------------------------------------------------------
+def a2r_region_tasks(genome, n_guides, n, pad, seed=20260105):
+    """(guide, locus) pairs of BASELINE configs[1]: half at planted sites +/- U(-10, 10), half uniform; regions [pos - pad, pos + pad] (AlignToReference.scala:116-134)."""
+    import numpy as np
+    from calitas_b200._capi import RegionTask
+    rng = np.random.default_rng(seed)
+    sites = np.array([(c, pos + len(seq) // 2) for c, lst in enumerate(genome.planted) for (pos, seq) in lst], dtype=np.int64)
+    lengths = np.array(genome.lengths, dtype=np.int64)
+    near = rng.random(n) < 0.5
+    si = rng.integers(0, len(sites), size=n)
+    jit = rng.integers(-10, 11, size=n)
+    cont = rng.choice(len(lengths), size=n, p=lengths / lengths.sum())
+    u = rng.random(n)
+    gidx = rng.integers(0, n_guides, size=n).astype(np.int32)
+    c = np.where(near, sites[si, 0], cont)
+    p = np.where(near, sites[si, 1] + jit, 1 + (u * (lengths[cont] - 1)).astype(np.int64))
+    p = np.clip(p, 1, lengths[c])
+    rs, re_ = np.maximum(p - pad, 1), np.minimum(p + pad, lengths[c])
+    arr = np.zeros(n, dtype=np.dtype([("guide_idx", "<i4"), ("contig_idx", "<i4"), ("start", "<i8"), ("length", "<i4"), ("_pad", "<i4")]))
+    arr["guide_idx"], arr["contig_idx"], arr["start"], arr["length"] = gidx, c, rs - 1, re_ - rs + 1
+    import ctypes as C
+    assert arr.dtype.itemsize == C.sizeof(RegionTask)
+    return arr
+
+
+def run_a2r(args, job):
+    import ctypes as C
+    import numpy as np
+    from calitas_b200._capi import Engine, Library, Limits, RegionTask
+    w = args.w
+    rank, world = job.rank, job.world
+    guides = guide_list(dict(w, pam="nrg", aux=""))
+    genome = make_genome(w, args.scale, guides)
+    engine = Engine(job.local_rank, lib=Library(os.path.abspath(args.lib)) if args.lib else None)
+    t0 = time.perf_counter()
+    arrays = [genome.contig(c) for c in range(len(genome.lengths))]       # tasks land anywhere: every rank holds the whole packed reference (1.55 GB)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ref = engine.load_reference(list(zip(genome.names, arrays)))
+    t_load = time.perf_counter() - t0
+    all_tasks = a2r_region_tasks(genome, len(guides), w["tasks"], w["window"] // 2)
+    lo, hi = w["tasks"] * rank // world, w["tasks"] * (rank + 1) // world
+    mine = np.ascontiguousarray(all_tasks[lo:hi])
+    tasks = (RegionTask * len(mine)).from_buffer(mine)
+    lim = Limits(0, 0, 3, -1, 0)
+    last = {}
+
+    def step():
+        t0 = time.perf_counter()
+        hs = engine.align_regions(ref, guides, tasks, lim, best=True)
+        wall = time.perf_counter() - t0
+        st = hs.stats(); st["hits"] = len(hs); st["wall_ms"] = wall * 1e3
+        if rank == 0 and "rec" not in last and not args.no_parity_check:
+            last["rec"] = hs.records()
+        hs.free()
+        return st
+
+    stats, t_local, clocks = job.timed(step, args.warmup, args.steps)
+    dev_ms = sum(s["ms_total"] for s in stats) / args.steps
+    wall_ms = 1e3 * t_local / args.steps
+    dev_ms_max, wall_ms_max = job.reduce([dev_ms, wall_ms], "max")
+    total_hits, total_cand = job.reduce([float(stats[-1]["hits"]), float(stats[-1]["candidates"])], "sum")
+    if rank == 0:
+        st = stats[-1]
+        n = w["tasks"]
+        value, e2e = n / (dev_ms_max * 1e-3) / 1e6, n / (wall_ms_max * 1e-3) / 1e6
+        peaks = peaks_file()
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        # dominant kernel: the grouped DP (k_align_group).  Algorithmic bytes per task: 2 strands x 61 columns x 1 slot x one hit record written + the 61 packed bases read
+        rec = 32
+        alg_bytes = len(mine) * (2 * (w["window"] + 1) * rec + (w["window"] + 1) * 0.5)
+        cells = len(mine) * 2.0 * (w["window"] + 1) * 20
+        out = {"metric": "M pairs/s AlignToReference (window 60, best mode)", "value": value, "unit": "Mpairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+               "config": workload_config(args, genome, guides),
+               "e2e": {"value": e2e, "unit": "Mpairs/s", "ms_per_step": wall_ms_max, "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
+                       "api": "calitas_align_regions(best=1) (C ABI): task array + guide strings in host memory -> per-task alignments in pinned host memory"},
+               "gpu_launches": int(sum(s["launches"] for s in stats)), "clocks": clocks,
+               "roofline": {"kernel": "k_align_group", "bound": "hbm", "achieved": alg_bytes / (st["ms_align"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": alg_bytes / (st["ms_align"] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "avg_launch_ms": st["ms_align"], "share_of_step": st["ms_align"] / st["ms_total"],
+                            "note": "algorithmic bytes = one record per end column and strand written + the packed region read; the kernel is integer-ALU-bound (DP cells), see roofline_int"},
+               "roofline_int": {"kernel": "k_align_group", "bound": "int_alu_pipe", "unit": "G DP cells/s (3 matrices per cell)", "achieved": cells / (st["ms_align"] * 1e-3) / 1e9,
+                                "cells_per_task": 2 * (w["window"] + 1) * 20},
+               "breakdown_ms": {"scan": st["ms_scan"], "align": st["ms_align"], "sort_canon_dedup": st["ms_other"], "d2h": st["ms_d2h"], "wall": st["wall_ms"]},
+               "counts": {"alignments": total_hits, "candidates": total_cand, "tasks": n}, "setup_s": {"generate": t_gen, "load_and_pack": t_load}}
+        if "rec" in last or not args.no_cpu_baseline:
+            # bounded sample: the first 3000 tasks of rank 0 through the oracle (all columns of the best alignment per task)
+            po = oracle()
+            from calitas_b200 import testing
+            k = min(3000, len(mine))
+            sub = mine[:k]
+            names = genome.names
+            tl = [("t%d" % i, guide_text(guides[int(t["guide_idx"])]), names[int(t["contig_idx"])], int(t["start"]) + 1 + w["window"] // 2) for i, t in enumerate(sub)]
+            # the oracle needs the bases around each task only: cut one small contig per task
+            ok, checked = True, 0
+            threads = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            small_contigs, small_tasks = [], []
+            for i, t in enumerate(sub):
+                c, s0, ln = int(t["contig_idx"]), int(t["start"]), int(t["length"])
+                small_contigs.append(("r%d" % i, bytes(arrays[c][s0:s0 + ln])))
+                small_tasks.append(("t%d" % i, tl[i][1], "r%d" % i, w["window"] // 2 + 1))      # region = [max(pos - 30, 1), min(pos + 30, len)] = the whole cut-out
+            text = po.align_to_reference(small_contigs, small_tasks, window_size=w["window"], threads=threads, raw=True)
+            t_cpu = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": k / t_cpu / 1e6, "unit": "Mpairs/s", "cores": threads, "kind": "port",
+                                   "sample": "%d of the step's pairs (each region cut out as its own contig), %d threads, %.1f s; C++ restatement of the reference algorithm" % (k, threads, t_cpu)}
+            if "rec" in last:
+                rows = po.hits_table(text)
+                exp = {}
+                for r in rows:
+                    exp[int(r["chromosome"][1:])] = (r["strand"], r["score"], r["cigar"], r["padded_guide"], r["padded_alignment"], r["padded_target"])
+                rec_ = last["rec"]
+                m = rec_[rec_["task_idx"] < k]
+                got_rows = _row_tuples_engine(engine, m, guides, list(zip(genome.names, arrays)))
+                best = {}
+                for h, r in zip(m, got_rows):            # AlignToReference best mode keeps `.sorted.head` per task: max score, then fewest gap bases, first in retval order
+                    ti = int(h["task_idx"])
+                    keyv = (-r[3], int(h["gap_bases"]))
+                    if ti not in best or keyv < best[ti][0]:
+                        best[ti] = (keyv, (r[2], r[3], r[4], r[5], r[6], r[7]))
+                checked = len(exp)
+                ok = all(ti in best and best[ti][1] == exp[ti] for ti in exp) and len(exp) == k
+                out["parity_check"] = {"checked_rows": checked, "equal": bool(ok), "what": "best alignment of the first %d tasks vs the oracle: strand, score, cigar, padded strings" % k}
         print(json.dumps(out))
     ref.free()
     engine.close()
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # the version banner would land on stdout next to the one JSON line
+    job = Job(args)
+    if os.environ.get("CALITAS_BENCH_VERBOSE"):
+        print("[bench] rank %d cpus %s" % (rank, sorted(os.sched_getaffinity(0))), file=sys.stderr)
+    kind = args.w["kind"]
+    if kind == "search":
+        run_search(args, job)
+    elif kind == "a2r":
+        run_a2r(args, job)
+    else:
+        from bench_vcf import run_vcf
+        run_vcf(args, job)
+    job.close()
 
 
 if __name__ == "__main__":

@@ -7,33 +7,40 @@ import com.editasmedicine.aligner.SequentialGuideAligner.Guide
 import com.fulcrumgenomics.alignment.Cigar
 import com.fulcrumgenomics.util.Sequences
 
-/** Decodes the 72-byte `calitas_hit` records (include/calitas_b200.h) the engine returns into the reference's GuideAlignment.
+/** Decodes the packed hit records (include/calitas_b200.h) the engine returns into the reference's GuideAlignment.
   *
-  * Record layout (little endian): 0 guide_idx, 4 pam_idx, 8 contig_idx, 12 task_idx, 16 start_offset, 20 end_offset,
-  * 24 guide_start_offset, 28 guide_end_offset, 32 score (all Int); 36 strand ('+'/'-'), 37 n_ops, 38 gap_bases, 39 edits (bytes);
-  * 40.. ops, 2 bits per alignment column in guide orientation: 0 '=', 1 'X', 2 'I' (guide base opposite a genome gap),
-  * 3 'D' (genome base opposite a guide gap).
+  * A result set holds records of one size, `stride` = calitas_hitset_stride(): 32 bytes (calitas_hit, up to 48 alignment columns) or
+  * 64 bytes (calitas_hit_wide, up to 176).  Both start with the same 20-byte header (little endian):
+  *   0 start_offset, 4 task_idx, 8 score (Int);
+  *   12 where: bits 0-12 guide_idx, bits 13-30 contig_idx + 1 (0 = none), bit 31 strand ('-' = 1);
+  *   16 shape: bits 0-7 n_ops, 8-15 end_offset - start_offset, 16-21 guide_start_offset - start_offset,
+  *             22-27 end_offset - guide_end_offset, 28-31 pam_idx + 1;
+  *   20.. ops, 2 bits per alignment column in guide orientation: 0 '=', 1 'X', 2 'I' (guide base opposite a genome gap),
+  *   3 'D' (genome base opposite a guide gap).
   *
   * The padded strings are rebuilt exactly as fgbio's Alignment.paddedString(gapChar = '~') + SequentialGuideAligner.toGuideAlignment
   * (SequentialGuideAligner.scala:505-524) produce them: the C++ host code does the same in render_hit_fix (calitas_b200/csrc/cal_host.cpp),
   * which the parity tests compare with the oracle column by column.  Uncompiled here (no scalac in this image).
   */
 object HitDecoder {
-  val RecordBytes = 72
+  val HeaderBytes = 20
   private val OpChars = Array('=', 'X', 'I', 'D')
 
   final case class Raw(guideIdx: Int, pamIdx: Int, contigIdx: Int, taskIdx: Int, startOffset: Int, endOffset: Int,
                        guideStartOffset: Int, guideEndOffset: Int, score: Int, strand: Char, ops: Array[Int])
 
-  def count(buf: ByteBuffer): Int = buf.capacity / RecordBytes
+  def count(buf: ByteBuffer, stride: Int): Int = buf.capacity / stride
 
-  def raw(buf: ByteBuffer, i: Int): Raw = {
+  def raw(buf: ByteBuffer, i: Int, stride: Int): Raw = {
     val b = buf.duplicate().order(ByteOrder.LITTLE_ENDIAN)
-    val o = i * RecordBytes
-    val nOps = b.get(o + 37) & 0xff
-    val ops  = Array.tabulate(nOps)(k => (b.getInt(o + 40 + 4 * (k >> 4)) >>> ((k & 15) * 2)) & 3)
-    Raw(b.getInt(o), b.getInt(o + 4), b.getInt(o + 8), b.getInt(o + 12), b.getInt(o + 16), b.getInt(o + 20),
-        b.getInt(o + 24), b.getInt(o + 28), b.getInt(o + 32), b.get(o + 36).toChar, ops)
+    val o = i * stride
+    val start = b.getInt(o); val where = b.getInt(o + 12); val shape = b.getInt(o + 16)
+    val nOps  = shape & 0xFF
+    val end   = start + ((shape >>> 8) & 0xFF)
+    val ops   = Array.tabulate(nOps)(k => (b.getInt(o + HeaderBytes + 4 * (k >> 4)) >>> ((k & 15) * 2)) & 3)
+    Raw(guideIdx = where & 0x1FFF, pamIdx = (shape >>> 28) - 1, contigIdx = ((where >>> 13) & 0x3FFFF) - 1, taskIdx = b.getInt(o + 4),
+        startOffset = start, endOffset = end, guideStartOffset = start + ((shape >>> 16) & 0x3F), guideEndOffset = end - ((shape >>> 22) & 0x3F),
+        score = b.getInt(o + 8), strand = if ((where >>> 31) != 0) '-' else '+', ops = ops)
   }
 
   /** @param guide  the guide the hit belongs to (guides(raw.guideIdx) of the call)

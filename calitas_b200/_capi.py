@@ -29,17 +29,71 @@ class Guide(C.Structure):
 
 
 class Hit(C.Structure):
-    _fields_ = [("guide_idx", C.c_int32), ("pam_idx", C.c_int32), ("contig_idx", C.c_int32), ("task_idx", C.c_int32), ("start_offset", C.c_int32),
-                ("end_offset", C.c_int32), ("guide_start_offset", C.c_int32), ("guide_end_offset", C.c_int32), ("score", C.c_int32), ("strand", C.c_uint8),
-                ("n_ops", C.c_uint8), ("gap_bases", C.c_uint8), ("edits", C.c_uint8), ("ops", C.c_uint32 * 8)]
+    """calitas_hit: 32 bytes, 48 alignment columns (include/calitas_b200.h)"""
+    _fields_ = [("start_offset", C.c_int32), ("task_idx", C.c_int32), ("score", C.c_int32), ("where", C.c_uint32), ("shape", C.c_uint32), ("ops", C.c_uint32 * 3)]
+
+
+class HitWide(C.Structure):
+    """calitas_hit_wide: the same header, 176 alignment columns"""
+    _fields_ = [("start_offset", C.c_int32), ("task_idx", C.c_int32), ("score", C.c_int32), ("where", C.c_uint32), ("shape", C.c_uint32), ("ops", C.c_uint32 * 11)]
+
+
+HIT_WORDS, HIT_WIDE_WORDS, HIT_HEADER_WORDS = 8, 16, 5        # include/calitas_b200.h: calitas_hit = 32 bytes, calitas_hit_wide = 64 bytes, both with a 5-word header
+MAX_OP_WORDS = HIT_WIDE_WORDS - HIT_HEADER_WORDS
 
 
 def hit_dtype():
-    """numpy structured dtype of calitas_hit (72 bytes, include/calitas_b200.h)."""
+    """numpy structured dtype of a DECODED hit: every logical field of a calitas_hit / calitas_hit_wide spelled out (see decode_hits)."""
     import numpy as np
     return np.dtype([("guide_idx", "<i4"), ("pam_idx", "<i4"), ("contig_idx", "<i4"), ("task_idx", "<i4"), ("start_offset", "<i4"), ("end_offset", "<i4"),
                      ("guide_start_offset", "<i4"), ("guide_end_offset", "<i4"), ("score", "<i4"), ("strand", "u1"), ("n_ops", "u1"), ("gap_bases", "u1"),
-                     ("edits", "u1"), ("ops", "<u4", (8,))])
+                     ("edits", "u1"), ("ops", "<u4", (MAX_OP_WORDS,))])
+
+
+def decode_hits(raw_words):
+    """raw_words: uint32 array of shape (n, 8) or (n, 16), the packed records of a hit set -> structured array of hit_dtype() (the accessors of
+    include/calitas_b200.h, vectorised)."""
+    import numpy as np
+    w = np.asarray(raw_words, dtype=np.uint32)
+    n, rw = w.shape
+    out = np.zeros(n, dtype=hit_dtype())
+    where, shape = w[:, 3], w[:, 4]
+    out["start_offset"] = w[:, 0].view(np.int32)
+    out["task_idx"] = w[:, 1].view(np.int32)
+    out["score"] = w[:, 2].view(np.int32)
+    out["guide_idx"] = where & 0x1FFF
+    out["contig_idx"] = ((where >> 13) & 0x3FFFF).astype(np.int32) - 1
+    out["strand"] = np.where(where >> 31, ord("-"), ord("+"))
+    out["n_ops"] = shape & 0xFF
+    out["end_offset"] = out["start_offset"] + ((shape >> 8) & 0xFF).astype(np.int32)
+    out["guide_start_offset"] = out["start_offset"] + ((shape >> 16) & 0x3F).astype(np.int32)
+    out["guide_end_offset"] = out["end_offset"] - ((shape >> 22) & 0x3F).astype(np.int32)
+    out["pam_idx"] = (shape >> 28).astype(np.int32) - 1
+    ops = w[:, HIT_HEADER_WORDS:]
+    out["ops"][:, :rw - HIT_HEADER_WORDS] = ops
+    bits = np.unpackbits(ops.view(np.uint8), axis=1) if n else np.zeros((0, 0), dtype=np.uint8)
+    if n:
+        hi = (ops & np.uint32(0xAAAAAAAA))
+        anyb = ((ops | (ops >> 1)) & np.uint32(0x55555555))
+        out["gap_bases"] = np.unpackbits(hi.view(np.uint8), axis=1).sum(axis=1)
+        out["edits"] = np.unpackbits(anyb.view(np.uint8), axis=1).sum(axis=1)
+    del bits
+    return out
+
+
+def encode_hits(records):
+    """Decoded hits (hit_dtype()) -> packed calitas_hit_wide records, uint32 array of shape (n, 16) (what calitas_render_alignments takes)."""
+    import numpy as np
+    r = np.asarray(records, dtype=hit_dtype()).reshape(-1)
+    w = np.zeros((r.size, HIT_WIDE_WORDS), dtype=np.uint32)
+    w[:, 0] = r["start_offset"].view(np.uint32)
+    w[:, 1] = r["task_idx"].view(np.uint32)
+    w[:, 2] = r["score"].view(np.uint32)
+    w[:, 3] = r["guide_idx"].astype(np.uint32) | ((r["contig_idx"] + 1).astype(np.uint32) << 13) | ((r["strand"] == ord("-")).astype(np.uint32) << 31)
+    w[:, 4] = (r["n_ops"].astype(np.uint32) | ((r["end_offset"] - r["start_offset"]).astype(np.uint32) << 8) | ((r["guide_start_offset"] - r["start_offset"]).astype(np.uint32) << 16)
+               | ((r["end_offset"] - r["guide_end_offset"]).astype(np.uint32) << 22) | ((r["pam_idx"] + 1).astype(np.uint32) << 28))
+    w[:, HIT_HEADER_WORDS:] = r["ops"]
+    return w
 
 
 class RegionTask(C.Structure):
@@ -71,7 +125,7 @@ class A2ROptions(C.Structure):
 EXPORTS = [
     # include/calitas_b200.h
     "calitas_engine_create", "calitas_engine_destroy", "calitas_engine_get_costs", "calitas_last_error", "calitas_reference_load", "calitas_reference_free",
-    "calitas_shard_plan", "calitas_search", "calitas_align_regions", "calitas_align_targets", "calitas_hitset_count", "calitas_hitset_data",
+    "calitas_shard_plan", "calitas_search", "calitas_align_regions", "calitas_align_targets", "calitas_hitset_count", "calitas_hitset_data", "calitas_hitset_stride",
     "calitas_hitset_free", "calitas_hitset_stats", "calitas_render_alignments", "calitas_free_text", "calitas_microbench_int",
     # include/calitas_b200_tools.h
     "calitas_tool_align", "calitas_tool_align_best", "calitas_tool_align_to_ref", "calitas_tool_search_reference", "calitas_tool_search_reference_batch", "calitas_tool_search_reference_batch_fd", "calitas_tool_align_to_reference",
@@ -98,8 +152,10 @@ class Library:
         L.calitas_last_error.restype = C.c_char_p
         L.calitas_hitset_count.restype = C.c_int64
         L.calitas_hitset_count.argtypes = [C.c_void_p]
-        L.calitas_hitset_data.restype = C.POINTER(Hit)
+        L.calitas_hitset_data.restype = C.c_void_p
         L.calitas_hitset_data.argtypes = [C.c_void_p]
+        L.calitas_hitset_stride.restype = C.c_int32
+        L.calitas_hitset_stride.argtypes = [C.c_void_p]
         L.calitas_hitset_free.argtypes = [C.c_void_p]
         L.calitas_hitset_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.calitas_engine_destroy.argtypes = [C.c_void_p]
@@ -153,22 +209,26 @@ class HitSet:
     def __len__(self):
         return self.lib.L.calitas_hitset_count(self.ptr)
 
-    def hits(self):
-        n = len(self)
-        data = self.lib.L.calitas_hitset_data(self.ptr)
-        return [data[i] for i in range(n)]
+    def stride(self):
+        return self.lib.L.calitas_hitset_stride(self.ptr)
 
-    def as_numpy(self):
+    def raw_words(self):
+        """the packed records as a uint32 array of shape (n, stride / 4) (copy)"""
         import numpy as np
-        n = len(self)
+        n, stride = len(self), self.stride()
         if n == 0:
-            return np.zeros((0, C.sizeof(Hit)), dtype=np.uint8)
-        buf = C.cast(self.lib.L.calitas_hitset_data(self.ptr), C.POINTER(C.c_uint8 * (n * C.sizeof(Hit)))).contents
-        return np.frombuffer(buf, dtype=np.uint8).reshape(n, C.sizeof(Hit)).copy()
+            return np.zeros((0, stride // 4), dtype=np.uint32)
+        buf = C.cast(self.lib.L.calitas_hitset_data(self.ptr), C.POINTER(C.c_uint8 * (n * stride))).contents
+        return np.frombuffer(buf, dtype=np.uint32).reshape(n, stride // 4).copy()
 
     def records(self):
-        """hit records as a numpy structured array (copy; see hit_dtype())"""
-        return self.as_numpy().view(hit_dtype()).reshape(-1)
+        """hit records decoded into a numpy structured array (copy; see hit_dtype() / decode_hits)"""
+        return decode_hits(self.raw_words())
+
+    def hits(self):
+        """decoded hits as a list of numpy records (attribute access: h.score, h.ops, ...)"""
+        import numpy as np
+        return list(self.records().view(np.recarray))
 
     def stats(self):
         ms = (C.c_double * 8)()
@@ -279,11 +339,11 @@ class Engine:
         """calitas_render_alignments over a numpy array of hit records (hit_dtype()); contigs = [(name, numpy uint8 array or bytes)] full contigs.
         Returns the GuideAlignment table text."""
         import numpy as np
-        rec = np.ascontiguousarray(records, dtype=hit_dtype())
+        rec = np.ascontiguousarray(encode_hits(records))
         arr, keep = make_guides(guides)
         view, vkeep = self.genome_view(contigs)
         out = C.c_void_p()
-        self.lib.check(self.lib.L.calitas_render_alignments(C.c_void_p(rec.ctypes.data), C.c_int64(rec.size), len(guides), arr, len(contigs), view.names,
+        self.lib.check(self.lib.L.calitas_render_alignments(C.c_void_p(rec.ctypes.data), C.c_int64(rec.shape[0]), HIT_WIDE_WORDS * 4, len(guides), arr, len(contigs), view.names,
                                                             C.cast(view.bases, C.POINTER(C.c_void_p)), None, 1 if upper_case else 0, C.byref(out)))
         return self.lib.take_text(out)
 

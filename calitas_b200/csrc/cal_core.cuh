@@ -46,6 +46,54 @@ CAL_HD uint32_t comp_code(uint32_t c) { return ((c & 1) << 3) | ((c & 2) << 1) |
 // does a query base set pair with a target code?  (scorePairing: N never matches)
 CAL_HD bool pairs(uint32_t qset, uint32_t tcode) { return tcode != CODE_N && (qset & tcode) != 0; }
 
+// ---- hit records ---------------------------------------------------------------------------------------------------------------------
+// HitX: one alignment with every field spelled out (host-side code and the generic device paths work on it).  The device pipeline and the
+// C ABI move the packed form of include/calitas_b200.h instead: `rw` 32-bit words per record (8 = calitas_hit, 16 = calitas_hit_wide), five
+// header words + 2-bit ops.  Unused op bits are zero, so gap and edit counts are population counts over the op words.
+struct HitX {
+  int32_t guide_idx, pam_idx, contig_idx, task_idx, start_offset, end_offset, guide_start_offset, guide_end_offset, score;
+  uint8_t strand, n_ops, gap_bases, edits;
+  uint32_t ops[CALITAS_MAX_OPS / 16];
+};
+CAL_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+CAL_HD uint32_t rec_make_where(int32_t guide_idx, int32_t contig_idx, bool neg) { return (uint32_t)guide_idx | ((uint32_t)(contig_idx + 1) << 13) | (neg ? 0x80000000u : 0u); }
+CAL_HD uint32_t rec_make_shape(int n_ops, int span, int lead, int trail, int pam_idx) {
+  return (uint32_t)n_ops | ((uint32_t)span << 8) | ((uint32_t)lead << 16) | ((uint32_t)trail << 22) | ((uint32_t)(pam_idx + 1) << 28);
+}
+CAL_HD int32_t rec_start(const uint32_t* r) { return (int32_t)r[0]; }
+CAL_HD int32_t rec_task(const uint32_t* r) { return (int32_t)r[1]; }
+CAL_HD int32_t rec_score(const uint32_t* r) { return (int32_t)r[2]; }
+CAL_HD int32_t rec_guide(const uint32_t* r) { return (int32_t)(r[3] & 0x1FFFu); }
+CAL_HD int32_t rec_contig(const uint32_t* r) { return (int32_t)((r[3] >> 13) & 0x3FFFFu) - 1; }
+CAL_HD uint32_t rec_neg(const uint32_t* r) { return r[3] >> 31; }
+CAL_HD int32_t rec_nops(const uint32_t* r) { return (int32_t)(r[4] & 0xFFu); }
+CAL_HD int32_t rec_span(const uint32_t* r) { return (int32_t)((r[4] >> 8) & 0xFFu); }
+CAL_HD int32_t rec_end(const uint32_t* r) { return (int32_t)r[0] + rec_span(r); }
+CAL_HD int32_t rec_gstart(const uint32_t* r) { return (int32_t)r[0] + (int32_t)((r[4] >> 16) & 0x3Fu); }
+CAL_HD int32_t rec_gend(const uint32_t* r) { return rec_end(r) - (int32_t)((r[4] >> 22) & 0x3Fu); }
+CAL_HD int32_t rec_pam(const uint32_t* r) { return (int32_t)(r[4] >> 28) - 1; }
+CAL_HD int32_t rec_gap_bases(const uint32_t* r, int rw) { int c = 0; for (int k = CALITAS_HIT_HEADER_WORDS; k < rw; ++k) c += popc32(r[k] & 0xAAAAAAAAu); return c; }
+CAL_HD int32_t rec_edits(const uint32_t* r, int rw) { int c = 0; for (int k = CALITAS_HIT_HEADER_WORDS; k < rw; ++k) c += popc32((r[k] | (r[k] >> 1)) & 0x55555555u); return c; }
+CAL_HD void pack_hit(const HitX& h, uint32_t* r, int rw) {
+  r[0] = (uint32_t)h.start_offset; r[1] = (uint32_t)h.task_idx; r[2] = (uint32_t)h.score; r[3] = rec_make_where(h.guide_idx, h.contig_idx, h.strand == '-');
+  r[4] = rec_make_shape(h.n_ops, h.end_offset - h.start_offset, h.guide_start_offset - h.start_offset, h.end_offset - h.guide_end_offset, h.pam_idx);
+  for (int k = CALITAS_HIT_HEADER_WORDS; k < rw; ++k) { const int w = k - CALITAS_HIT_HEADER_WORDS; r[k] = w < CALITAS_MAX_OPS / 16 ? h.ops[w] : 0u; }
+}
+CAL_HD void unpack_hit(const uint32_t* r, int rw, HitX& h) {
+  h.start_offset = rec_start(r); h.task_idx = rec_task(r); h.score = rec_score(r); h.guide_idx = rec_guide(r); h.contig_idx = rec_contig(r); h.strand = (uint8_t)(rec_neg(r) ? '-' : '+');
+  h.n_ops = (uint8_t)rec_nops(r); h.end_offset = rec_end(r); h.guide_start_offset = rec_gstart(r); h.guide_end_offset = rec_gend(r); h.pam_idx = rec_pam(r);
+  h.gap_bases = (uint8_t)rec_gap_bases(r, rw); h.edits = (uint8_t)rec_edits(r, rw);
+  for (int w = 0; w < CALITAS_MAX_OPS / 16; ++w) h.ops[w] = w + CALITAS_HIT_HEADER_WORDS < rw ? r[w + CALITAS_HIT_HEADER_WORDS] : 0u;
+}
+// 32-byte records (rw = 8) hold 48 alignment columns, 64-byte records 176
+CAL_HD int rec_words_for(int max_columns) { return max_columns <= 16 * (CALITAS_HIT_WORDS - CALITAS_HIT_HEADER_WORDS) ? CALITAS_HIT_WORDS : CALITAS_HIT_WIDE_WORDS; }
+
 // ---- scores (SequentialGuideAligner.scala:192-208, 213) ---------------------------------------------------------
 struct Scores {
   int32_t match, mismatch, pam_match, pam_mismatch, query_gap /* cigar D */, target_gap /* cigar I */, worst_guide_diff;
@@ -85,6 +133,7 @@ struct GuideSpec {
   int32_t  span;                             // max target columns any co-optimal alignment of an accepted end column can cover
   int32_t  band_k;                           // max gap bases of either kind on such an alignment (== k_edits unless k_edits was capped at lp): decides the banded kernels
   int32_t  slots;                            // alignment slots per candidate end column = max(1, n_pams)
+  int32_t  max_cols;                         // most alignment columns a hit of this guide can have (decides the record size of a call)
 };
 
 // ---- bit-parallel candidate scan (Myers/Hyyro, semi-global: free target start) ----------------------------------------
@@ -382,8 +431,8 @@ CAL_HD bool extend_pam(const GuideSpec& g, const Scores& sc, Fetch fetch, int32_
 // The record is assembled in thread-local storage and stored once: `out` usually lives in global memory, and setting ~30 two-bit ops there
 // one read-modify-write at a time is what made this the second-largest part of k_align.
 CAL_HD void make_hit(const GuideSpec& g, const GuideAln& a, int pam_idx, int32_t score, int32_t offset, uint32_t xmask, int dir,
-                     const WindowGeom& w, int32_t guide_idx, int32_t contig_idx, int32_t task_idx, calitas_hit& out) {
-  calitas_hit h;
+                     const WindowGeom& w, int32_t guide_idx, int32_t contig_idx, int32_t task_idx, HitX& out) {
+  HitX h;
   const int pam_len = pam_idx >= 0 ? g.pam_len[pam_idx] : 0;
   const int n_ops = a.n_ops + (pam_idx >= 0 ? offset + pam_len : 0);
   h.guide_idx = guide_idx; h.pam_idx = pam_idx; h.contig_idx = contig_idx; h.task_idx = task_idx; h.score = score;
@@ -418,23 +467,29 @@ CAL_HD void make_hit(const GuideSpec& g, const GuideAln& a, int pam_idx, int32_t
 // ---- per-window canonicalisation (SequentialGuideAligner.scala:315-322) ---------------------------------------------------
 // `hits[0..n)` are the alignments of one (guide, window, strand) in emission order (end column, then PAM index); `valid[i]` marks
 // filled slots.  On return rank[i] >= 0 is the position of a kept alignment in the reference's retval for this strand, -1 = dropped.
-CAL_HD int canon_group(const calitas_hit* hits, const uint8_t* valid, int32_t* rank, int n, int32_t max_total_diffs, int32_t max_overlap) {
+CAL_HD int canon_group(const uint32_t* recs, int rw, const uint8_t* valid, int32_t* rank, int n, int32_t max_total_diffs, int32_t max_overlap) {
   // rank doubles as state: -2 = not yet visited, -1 = dropped, >= 0 kept
   for (int i = 0; i < n; ++i) rank[i] = valid[i] ? -2 : -1;
   int kept = 0;
   for (;;) {
-    int b = -1;    // next in stable (score desc, gapBases asc) order
+    int b = -1; int32_t bscore = 0, bgaps = 0;    // next in stable (score desc, gapBases asc) order
     for (int i = 0; i < n; ++i) {
       if (rank[i] != -2) continue;
-      if (b < 0 || hits[i].score > hits[b].score || (hits[i].score == hits[b].score && hits[i].gap_bases < hits[b].gap_bases)) b = i;
+      const uint32_t* r = recs + (int64_t)i * rw; const int32_t sc = rec_score(r);
+      if (b >= 0 && sc < bscore) continue;
+      const int32_t gp = rec_gap_bases(r, rw);
+      if (b < 0 || sc > bscore || gp < bgaps) { b = i; bscore = sc; bgaps = gp; }
     }
     if (b < 0) break;
-    bool keep = hits[b].edits <= max_total_diffs;
+    const uint32_t* rb = recs + (int64_t)b * rw;
+    bool keep = rec_edits(rb, rw) <= max_total_diffs;
     if (keep) {
+      const int32_t bs = rec_start(rb), be = rec_end(rb);
       for (int i = 0; i < n && keep; ++i) {
         if (rank[i] < 0) continue;
-        int32_t lo = hits[i].start_offset > hits[b].start_offset ? hits[i].start_offset : hits[b].start_offset;
-        int32_t hi = hits[i].end_offset < hits[b].end_offset ? hits[i].end_offset : hits[b].end_offset;
+        const uint32_t* r = recs + (int64_t)i * rw;
+        int32_t lo = rec_start(r) > bs ? rec_start(r) : bs;
+        int32_t hi = rec_end(r) < be ? rec_end(r) : be;
         int32_t ov = hi - lo; if (ov < 0) ov = 0;
         if (ov > max_overlap) keep = false;
       }
@@ -446,21 +501,6 @@ CAL_HD int canon_group(const calitas_hit* hits, const uint8_t* valid, int32_t* r
 
 // ---- genome-wide sweep (SearchReference.scala:653-675) --------------------------------------------------------------------------
 // ReferenceHit.end (ReferenceHit.scala:135-138): coordinate_start + cigar.lengthOnTarget - 1, with coordinate_start the guide-only start.
-CAL_HD int32_t hit_sweep_end(const calitas_hit& h) { return h.guide_start_offset + (h.end_offset - h.start_offset) - 1; }
-CAL_HD int32_t hit_sweep_overlap(const calitas_hit& a, const calitas_hit& b) {
-  int32_t ea = hit_sweep_end(a), eb = hit_sweep_end(b);
-  int32_t hi = ea < eb ? ea : eb, lo = a.guide_start_offset > b.guide_start_offset ? a.guide_start_offset : b.guide_start_offset;
-  int32_t o = hi - lo; return o > 0 ? o : 0;
-}
-// hits[idx[0..n)] is one (guide, contig, strand) group sorted by (coordinate_start, -score, arrival); keep[i] set for keepers.
-CAL_HD void sweep_group(const calitas_hit* hits, const uint32_t* idx, uint8_t* keep, int64_t n, int32_t max_overlap) {
-  int64_t i = 0;
-  while (i < n) {
-    const calitas_hit& hit = hits[idx[i]];
-    int64_t cur = i++;
-    while (i < n && hit_sweep_overlap(hits[idx[i]], hit) >= max_overlap && hits[idx[i]].score <= hit.score) { keep[i] = 0; ++i; }
-    keep[cur] = (i >= n || hit_sweep_overlap(hits[idx[i]], hit) < max_overlap) ? 1 : 0;
-  }
-}
+CAL_HD int32_t rec_sweep_end(const uint32_t* r) { return rec_gstart(r) + rec_span(r) - 1; }
 
 }  // namespace cal

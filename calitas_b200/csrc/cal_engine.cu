@@ -43,7 +43,7 @@ const int SCAN_THREADS = 2 * TILE_WINDOWS;
 const int SCAN_NG = CAL_SCAN_NG;     // guides a scan thread advances together (independent dependency chains sharing the base-code extraction)
 const int KEY_COL_BITS_MAX = 17;
 const uint32_t MAX_WINDOW_LEN = (1u << KEY_COL_BITS_MAX) - 1;
-const int MAX_GUIDES_PER_CALL = 1 << 14;
+const int MAX_GUIDES_PER_CALL = CALITAS_MAX_GUIDES;     // 13 bits of the hit record
 
 // Candidate key = guide | window | strand | end column, each field only as wide as the call needs (<= 14 + 32 + 1 + 17 bits), so that the
 // LSD radix sort of the keys runs over `bits` bits: 5 eight-bit passes instead of 8 for 100 guides x hg38 at -w 1000.  Every pass is a
@@ -310,7 +310,7 @@ struct AlignArgs {
   const uint32_t* nib;
   const ContigDev* contigs; int32_t n_contigs; int32_t window_size, step;     // tiled
   const ExplicitWindow* windows; int32_t task_base;                          // explicit (window ids are relative to task_base)
-  calitas_hit* hits; uint8_t* valid; KeyLayout key;
+  uint32_t* recs; int32_t rw; uint8_t* valid; KeyLayout key;     // packed hit records, rw words each (cal_core.cuh)
 };
 struct NibFetch {
   const uint32_t* nib; int64_t first; int32_t m; int dir;
@@ -353,13 +353,14 @@ CAL_D CandCtx decode_candidate(const AlignArgs& a, uint64_t key) {
 CAL_D void post_alignment(const AlignArgs& a, const CandCtx& x, const GuideSpec& g, const NibFetch& fetch, const GuideAln& aln, int64_t i) {
   if (aln.diffs > g.d) return;                                   // SequentialGuideAligner.scala:447,450
   const int64_t base = i * a.slots;
+  HitX h;
   if (g.n_pams == 0) {
-    make_hit(g, aln, -1, aln.score, 0, 0u, x.dir, x.geom, x.gidx, x.contig_idx, (int32_t)x.wid + a.task_base, a.hits[base]); a.valid[base] = x.owned;
+    make_hit(g, aln, -1, aln.score, 0, 0u, x.dir, x.geom, x.gidx, x.contig_idx, (int32_t)x.wid + a.task_base, h); pack_hit(h, a.recs + base * a.rw, a.rw); a.valid[base] = x.owned;
   } else {
     for (int pi = 0; pi < g.n_pams; ++pi) {
       int32_t score = 0, offset = 0; uint32_t xmask = 0;
       if (extend_pam(g, a.sc, fetch, x.m, aln, pi, score, offset, xmask)) {
-        make_hit(g, aln, pi, score, offset, xmask, x.dir, x.geom, x.gidx, x.contig_idx, (int32_t)x.wid + a.task_base, a.hits[base + pi]); a.valid[base + pi] = x.owned;
+        make_hit(g, aln, pi, score, offset, xmask, x.dir, x.geom, x.gidx, x.contig_idx, (int32_t)x.wid + a.task_base, h); pack_hit(h, a.recs + (base + pi) * a.rw, a.rw); a.valid[base + pi] = x.owned;
       }
     }
   }
@@ -428,7 +429,7 @@ CAL_KERNEL __launch_bounds__(128) k_align_wide(AlignArgs a) { align_body<0>(a); 
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct CanonArgs {
   const uint64_t* cand; int64_t n_cand; const GuideSpec* specs; int32_t slots; int32_t explicit_mode; const ExplicitWindow* windows;
-  const calitas_hit* hits; const uint8_t* valid; int32_t* rank; uint32_t* perm; uint32_t* flag; uint8_t* slot_owned; int32_t drop_halo; KeyLayout key;
+  const uint32_t* recs; int32_t rw; const uint8_t* valid; int32_t* rank; uint32_t* perm; uint32_t* flag; uint8_t* slot_owned; int32_t drop_halo; KeyLayout key;
 };
 CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -439,7 +440,7 @@ CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
   const int64_t base = i * a.slots; const int n = (int)((j - i) * a.slots);
   const int32_t gidx = a.explicit_mode ? a.windows[key_window(a.key, a.cand[i])].guide_idx : key_guide(a.key, a.cand[i]);
   const GuideSpec& g = a.specs[gidx];
-  int kept = canon_group(a.hits + base, a.valid + base, a.rank + base, n, g.max_total_diffs, g.max_overlap);
+  int kept = canon_group(a.recs + base * a.rw, a.rw, a.valid + base, a.rank + base, n, g.max_total_diffs, g.max_overlap);
   bool owned = true; for (int k = 0; k < n; ++k) if (a.valid[base + k] == 2) owned = false;     // a group is one window: all halo or all owned
   if (!owned && a.drop_halo) kept = 0;
   for (int k = 0; k < n; ++k) { a.flag[base + k] = k < kept ? 1u : 0u; a.slot_owned[base + k] = owned ? 1 : 0; }
@@ -469,25 +470,25 @@ CAL_KERNEL __launch_bounds__(128) k_canon_warp(CanonArgs a, const uint32_t* gsta
       unsigned long long best = ~0ull;
       for (int k = lane; k < n; k += 32) {
         if (a.rank[base + k] != -2) continue;
-        const calitas_hit& h = a.hits[base + k];
-        const unsigned long long key = ((unsigned long long)(uint32_t)(0x7FFFFFFF - h.score) << 32) | ((unsigned long long)h.gap_bases << 20) | (unsigned long long)k;
+        const uint32_t* h = a.recs + (base + k) * a.rw;
+        const unsigned long long key = ((unsigned long long)(uint32_t)(0x7FFFFFFF - rec_score(h)) << 32) | ((unsigned long long)rec_gap_bases(h, a.rw) << 20) | (unsigned long long)k;
         if (key < best) best = key;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o); if (other < best) best = other; }
       if (best == ~0ull) break;
       const int b = (int)(best & 0xFFFFFu);
-      const calitas_hit& hb = a.hits[base + b];
-      const bool keep = hb.edits <= max_total;
-      const int32_t bs = hb.start_offset, be = hb.end_offset;
+      const uint32_t* hb = a.recs + (base + b) * a.rw;
+      const bool keep = rec_edits(hb, a.rw) <= max_total;
+      const int32_t bs = rec_start(hb), be = rec_end(hb);
       __syncwarp();
       if (lane == 0) a.rank[base + b] = keep ? kept : -1;
       if (keep) {
         ++kept;
         for (int k = lane; k < n; k += 32) {
           if (k == b || a.rank[base + k] != -2) continue;
-          const calitas_hit& h = a.hits[base + k];
-          const int32_t lo = h.start_offset > bs ? h.start_offset : bs, hi = h.end_offset < be ? h.end_offset : be;
+          const uint32_t* h = a.recs + (base + k) * a.rw;
+          const int32_t lo = rec_start(h) > bs ? rec_start(h) : bs, hi = rec_end(h) < be ? rec_end(h) : be;
           int32_t ov = hi - lo; if (ov < 0) ov = 0;           // GuideAlignment.overlap clamps at 0, as canon_group does
           if (ov > max_overlap) a.rank[base + k] = -1;
         }
@@ -501,12 +502,20 @@ CAL_KERNEL __launch_bounds__(128) k_canon_warp(CanonArgs a, const uint32_t* gsta
   }
 }
 #endif
-// out[pos[s]] = hits[perm[s]] for flagged slots
-CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const calitas_hit* hits, const uint32_t* perm, const uint32_t* flag, const uint32_t* pos, const uint8_t* slot_owned, int64_t n,
-                                                   calitas_hit* out, uint8_t* out_owned) {
+// record copy: rw words as 16-byte pieces (records are 32 or 64 bytes, 32-byte aligned)
+CAL_D void copy_rec(uint32_t* dst, const uint32_t* src, int rw) {
+#ifndef CAL_HOSTSIM
+  const uint4* s4 = reinterpret_cast<const uint4*>(src); uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (int k = 0; k < rw / 4; ++k) d4[k] = s4[k];
+#else
+  for (int k = 0; k < rw; ++k) dst[k] = src[k];
+#endif
+}
+// out[pos[s]] = recs[perm[s]] for flagged slots (the kept alignments of every group, in retval order)
+CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const uint32_t* recs, int32_t rw, const uint32_t* perm, const uint32_t* flag, const uint32_t* pos, int64_t n, uint32_t* out) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n || !flag[s]) return;
-  out[pos[s]] = hits[perm[s]]; out_owned[pos[s]] = slot_owned[s];
+  copy_rec(out + (int64_t)pos[s] * rw, recs + (int64_t)perm[s] * rw, rw);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------------
@@ -520,27 +529,39 @@ CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const calitas_hit* hits, cons
 // real genomes and costs) the score goes into keyA instead and two stable sorts give the same order.  Arrival order is the array index.
 // A value outside its field would mis-sort silently, so it raises *overflow, which the host reads with the sweep's counters.
 struct DedupLayout { int32_t start_bits, contig_shift, guide_shift, bits /* without the score */, g0, score_hi, score_bits, merged; };
-CAL_KERNEL __launch_bounds__(256) k_dedup_keys(const calitas_hit* hits, int64_t n, DedupLayout L, uint64_t* key, uint64_t* keyA, uint32_t* idx, uint32_t* overflow) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const calitas_hit& h = hits[i];
-  const int64_t start = h.guide_start_offset, sc = (int64_t)L.score_hi - h.score, g = (int64_t)h.guide_idx - L.g0, c = h.contig_idx;
+// One thread per alignment slot: the kept ones (flag) get their sort key at pos[s] (their arrival rank: group order, then retval order), with the
+// slot of the record as the sort value; nothing is copied until the keepers are known.
+CAL_KERNEL __launch_bounds__(256) k_dedup_keys(const uint32_t* recs, int32_t rw, const uint32_t* perm, const uint32_t* flag, const uint32_t* pos, int64_t n_slots, DedupLayout L,
+                                               uint64_t* key, uint64_t* keyA, uint32_t* idx, uint32_t* overflow) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || !flag[s]) return;
+  const int64_t i = pos[s]; const uint32_t src = perm[s];
+  const uint32_t* h = recs + (int64_t)src * rw;
+  const int64_t start = rec_gstart(h), sc = (int64_t)L.score_hi - rec_score(h), g = (int64_t)rec_guide(h) - L.g0, c = rec_contig(h);
   if (start < 0 || (start >> L.start_bits) != 0 || sc < 0 || (sc >> L.score_bits) != 0 || g < 0 || c < 0 ||
       (uint64_t)c >= (1ull << (L.guide_shift - L.contig_shift)) || (L.bits < 64 && ((uint64_t)g >> (L.bits - L.guide_shift)) != 0)) *overflow = 1u;
-  const uint64_t k = ((uint64_t)g << L.guide_shift) | ((uint64_t)c << L.contig_shift) | ((uint64_t)start << 1) | (uint64_t)(h.strand == '-' ? 1u : 0u);
+  const uint64_t k = ((uint64_t)g << L.guide_shift) | ((uint64_t)c << L.contig_shift) | ((uint64_t)start << 1) | (uint64_t)rec_neg(h);
   if (L.merged) key[i] = (k << L.score_bits) | (uint64_t)sc;
   else { key[i] = k; keyA[i] = (uint64_t)sc; }
-  idx[i] = (uint32_t)i;
+  idx[i] = src;
 }
 CAL_KERNEL __launch_bounds__(256) k_gather_u64(const uint64_t* in, const uint32_t* idx, int64_t n, uint64_t* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[idx[i]];
 }
-CAL_KERNEL __launch_bounds__(256) k_sweep_prepare(const calitas_hit* hits, const uint8_t* owned, const uint32_t* idx, int64_t n, int32_t* s_start, int32_t* s_end, int32_t* s_score, uint8_t* s_owned) {
+CAL_KERNEL __launch_bounds__(256) k_gather_u32(const uint32_t* in, const uint32_t* idx, int64_t n, uint32_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+CAL_KERNEL __launch_bounds__(256) k_iota_u32(uint32_t* out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)i;
+}
+CAL_KERNEL __launch_bounds__(256) k_sweep_prepare(const uint32_t* recs, int32_t rw, const uint8_t* owned, const uint32_t* idx, int64_t n, int32_t* s_start, int32_t* s_end, int32_t* s_score, uint8_t* s_owned) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const calitas_hit& h = hits[idx[i]];
-  s_start[i] = h.guide_start_offset; s_end[i] = hit_sweep_end(h); s_score[i] = h.score; s_owned[i] = owned[idx[i]];
+  const uint32_t* h = recs + (int64_t)idx[i] * rw;
+  s_start[i] = rec_gstart(h); s_end[i] = rec_sweep_end(h); s_score[i] = rec_score(h); s_owned[i] = owned[idx[i]];
 }
 CAL_HD int32_t soa_overlap(const int32_t* s_start, const int32_t* s_end, int64_t a, int64_t b) {
   const int32_t hi = s_end[a] < s_end[b] ? s_end[a] : s_end[b], lo = s_start[a] > s_start[b] ? s_start[a] : s_start[b];
@@ -573,9 +594,9 @@ CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key, const int32_t* s_
   for (int st = 0; st < 2; ++st) if (cur[st] >= 0) keep[cur[st]] = s_owned[cur[st]] ? 1u : 0u;
 }
 // out[pos[i]] = hits[idx[i]] for the keepers: the sorted order is the final order
-CAL_KERNEL __launch_bounds__(256) k_gather_keepers(const calitas_hit* hits, const uint32_t* idx, const uint32_t* keep, const uint32_t* pos, int64_t n, calitas_hit* out) {
+CAL_KERNEL __launch_bounds__(256) k_gather_keepers(const uint32_t* recs, int32_t rw, const uint32_t* idx, const uint32_t* keep, const uint32_t* pos, int64_t n, uint32_t* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && keep[i]) out[pos[i]] = hits[idx[i]];
+  if (i < n && keep[i]) copy_rec(out + (int64_t)pos[i] * rw, recs + (int64_t)idx[i] * rw, rw);
 }
 
 // Counters the host waits for are stored straight into mapped pinned host memory by these one-thread kernels (see dev::alloc_host_mapped).
@@ -660,7 +681,7 @@ struct calitas_reference {
 };
 
 struct calitas_hitset {
-  calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; int32_t stride = CALITAS_HIT_WORDS * 4; double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 
 enum { CNT_GROUPS = 3, CNT_KEPT = 4, CNT_KEEPERS = 5 /* + 6: overflow flag as published */, CNT_DEDUP_OVERFLOW = 7 };
@@ -676,7 +697,7 @@ struct calitas_engine {
   std::vector<ChunkEvents> chunk_ev;
   size_t out_hits_hint = 1u << 16;
   DBuf cand_b, cand_c;
-  DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, kept, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, kept_owned, sowned;
+  DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, sowned;
   // eight 64-bit device counters and their pinned host mirror: slots 0..2 = candidate counts of the three scan buffers (run_explicit uses 0),
   // slot CNT_DEDUP_OVERFLOW = k_dedup_keys' "a field does not fit its sort-key width" flag
   unsigned long long* h_count = nullptr;       // pinned + mapped: the device stores into it through h_count_dev (no copy engine involved)
@@ -756,16 +777,24 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
   return it->second;
 }
 
-struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> align -> canon -> compaction
+struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> align -> canon -> (removeOverlaps + sort | compaction) -> e->out
   calitas_engine* e; const uint64_t* cand; dev::Event ev_sorted, ev_align_b, ev_align_e;   // candidate keys; events recorded after the sort / around k_align
   const GuideSpec* d_specs; int slots; bool explicit_mode; int banded;   // banded: 0 = wide thresholds, else the largest k_edits of the launch (<= ALIGN_KB)
   const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base; bool drop_halo;
-  KeyLayout key;
+  KeyLayout key; int rw;                                                   // rw: 32-bit words per hit record of this call
+  const DedupLayout* dedup; int32_t max_overlap;                           // dedup != nullptr: removeOverlaps + ReferenceHit.sort over the kept alignments
 };
 
-// Runs sort/align/canon on e->cand[0..n_cand) and leaves the kept hits, in arrival order, in e->kept; returns their number.
-int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
-  calitas_engine* e = P.e; dev::Stream s = e->stream;
+// e->out must hold (out_n + more) records; the first out_n are kept
+void ensure_out(calitas_engine* e, int rw, int64_t out_n, int64_t more, size_t projected_total) {
+  const size_t need = (size_t)(out_n + more) * rw * 4;
+  if (need > e->out.cap) e->out.ensure_keep(std::max(need, projected_total * rw * 4), (size_t)out_n * rw * 4, e->stream);
+}
+
+// Runs sort/align/canon on the candidate keys, then either removeOverlaps + sort (P.dedup) or a plain compaction, appending the surviving records to
+// e->out at out_n (arrival order without dedup: group order, then retval order).  Returns their number; n_alignments = alignment slots examined.
+int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projected_total, int64_t& n_alignments) {
+  calitas_engine* e = P.e; dev::Stream s = e->stream; const int rw = P.rw;
   n_alignments = 0;
   if (n_cand == 0) { dev::event_record(P.ev_sorted, s); dev::event_record(P.ev_align_b, s); dev::event_record(P.ev_align_e, s); return 0; }
   if (n_cand * (int64_t)P.slots >= (1ll << 32)) throw LimitExceeded("too many candidate alignments in one batch");
@@ -776,11 +805,11 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   dev::event_record(P.ev_sorted, s);                      // the candidate buffer may be refilled by the next scan from here on
   // 2. align
   const int64_t n_slots = n_cand * P.slots;
-  e->hits.ensure((size_t)n_slots * sizeof(calitas_hit)); e->valid.ensure((size_t)n_slots);
+  e->hits.ensure((size_t)n_slots * rw * 4); e->valid.ensure((size_t)n_slots);
   AlignArgs aa; std::memset(&aa, 0, sizeof aa);
   aa.cand = e->cand_sorted.as<uint64_t>(); aa.n_cand = n_cand; aa.specs = P.d_specs; aa.sc = e->sc; aa.slots = P.slots; aa.explicit_mode = P.explicit_mode ? 1 : 0;
   aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows; aa.task_base = P.task_base;
-  aa.hits = e->hits.as<calitas_hit>(); aa.valid = e->valid.as<uint8_t>(); aa.key = P.key;
+  aa.recs = e->hits.as<uint32_t>(); aa.rw = rw; aa.valid = e->valid.as<uint8_t>(); aa.key = P.key;
   dev::event_record(P.ev_align_b, s);
   if (P.banded > 5) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
   else if (P.banded == 5) { CAL_LAUNCH(k_align5, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align5"); }
@@ -804,7 +833,7 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   e->rank.ensure((size_t)n_slots * 4); e->perm.ensure((size_t)n_slots * 4); e->flag.ensure((size_t)n_slots * 4); e->pos.ensure((size_t)n_slots * 4); e->slot_owned.ensure((size_t)n_slots);
   CanonArgs ca; std::memset(&ca, 0, sizeof ca);
   ca.cand = aa.cand; ca.n_cand = n_cand; ca.specs = P.d_specs; ca.slots = P.slots; ca.explicit_mode = aa.explicit_mode; ca.windows = P.d_windows;
-  ca.hits = aa.hits; ca.valid = aa.valid; ca.rank = e->rank.as<int32_t>(); ca.perm = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>(); ca.slot_owned = e->slot_owned.as<uint8_t>(); ca.drop_halo = P.drop_halo ? 1 : 0; ca.key = P.key;
+  ca.recs = aa.recs; ca.rw = rw; ca.valid = aa.valid; ca.rank = e->rank.as<int32_t>(); ca.perm = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>(); ca.slot_owned = e->slot_owned.as<uint8_t>(); ca.drop_halo = P.drop_halo ? 1 : 0; ca.key = P.key;
 #ifndef CAL_HOSTSIM
   if (P.explicit_mode && !P.banded) {     // large groups: a warp per group (group starts, indices and flags were built for k_align_group)
     CAL_LAUNCH(k_canon_warp, (unsigned)dev::sm_count(e->device) * 16, 128, 0, s, 1, ca, e->idx.as<uint32_t>(), e->keyA.as<uint32_t>(), e->key1.as<uint32_t>()); dev::launch_check("k_canon_warp"); ++e->launches;
@@ -815,69 +844,74 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t& n_alignments) {
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n_slots, s); ++e->launches;
   CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, e->pos.as<uint32_t>() + (n_slots - 1), e->flag.as<uint32_t>() + (n_slots - 1), (const unsigned long long*)nullptr, e->h_count_dev + CNT_KEPT); dev::launch_check("k_publish_sum");
   dev::stream_sync(s);
-  const int64_t n_kept = (int64_t)((volatile unsigned long long*)e->h_count)[CNT_KEPT];
+  const int64_t n = (int64_t)((volatile unsigned long long*)e->h_count)[CNT_KEPT];      // kept alignments
   n_alignments = n_slots;
-  e->kept.ensure((size_t)n_kept * sizeof(calitas_hit)); e->kept_owned.ensure((size_t)n_kept);
-  if (n_kept) { CAL_LAUNCH(k_gather_flagged, blocks_for(n_slots, 256), 256, 0, s, 1, aa.hits, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), e->slot_owned.as<uint8_t>(), n_slots, e->kept.as<calitas_hit>(), e->kept_owned.as<uint8_t>()); dev::launch_check("k_gather_flagged"); ++e->launches; }
-  return n_kept;
-}
-
-// removeOverlaps + ReferenceHit.sort over e->kept[0..n) -> appended to e->out at out_n; returns number of keepers.
-int64_t run_dedup(calitas_engine* e, int64_t n, int32_t max_overlap, int64_t out_n, const DedupLayout& L) {
-  dev::Stream s = e->stream;
   if (n == 0) return 0;
+  if (!P.dedup) {                          // plain compaction straight into the output
+    ensure_out(e, rw, out_n, n, projected_total);
+    CAL_LAUNCH(k_gather_flagged, blocks_for(n_slots, 256), 256, 0, s, 1, aa.recs, rw, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, e->out.as<uint32_t>() + out_n * rw); dev::launch_check("k_gather_flagged"); ++e->launches;
+    return n;
+  }
+  // 4. removeOverlaps (SearchReference.scala:653-675) + ReferenceHit.sort: keys of the kept slots, ONE stable radix sort (two when the fields do not fit
+  //    64 bits), the two-strand sweep, and only then a copy: the keepers go from their alignment slots straight to the output.
+  const DedupLayout& L = *P.dedup;
   if (n >= (1ll << 32)) throw LimitExceeded("too many hits in one batch");
-  const calitas_hit* hits = e->kept.as<calitas_hit>();
   e->key1.ensure((size_t)n * 8); e->keyA.ensure((size_t)n * 8); e->idx.ensure((size_t)n * 4); e->idx2.ensure((size_t)n * 4);
-  size_t tb = dev::sort_pairs_u64_tmp((size_t)n, 0, 64); e->tmp.ensure(tb);
+  tb = dev::sort_pairs_u64_tmp((size_t)n, 0, 64); e->tmp.ensure(tb);
   const uint64_t* skey; const uint32_t* sidx; int strand_shift;
+  uint32_t* d_overflow = (uint32_t*)(e->d_count + CNT_DEDUP_OVERFLOW);
   if (L.merged) {
-    CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->keyA.as<uint64_t>(), (uint64_t*)nullptr, e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + CNT_DEDUP_OVERFLOW)); dev::launch_check("k_dedup_keys"); ++e->launches;
+    CAL_LAUNCH(k_dedup_keys, blocks_for(n_slots, 256), 256, 0, s, 1, aa.recs, rw, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, L, e->keyA.as<uint64_t>(), (uint64_t*)nullptr, e->idx.as<uint32_t>(), d_overflow); dev::launch_check("k_dedup_keys"); ++e->launches;
     dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, L.bits + L.score_bits, s); ++e->launches;
     skey = e->key1.as<uint64_t>(); sidx = e->idx2.as<uint32_t>(); strand_shift = L.score_bits;
-  } else {      // stable by -score (arrival order = index order), then stable by (guide, contig, start, strand)
-    e->key_b.ensure((size_t)n * 8);
-    CAL_LAUNCH(k_dedup_keys, blocks_for(n, 256), 256, 0, s, 1, hits, n, L, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>(), (uint32_t*)(e->d_count + CNT_DEDUP_OVERFLOW)); dev::launch_check("k_dedup_keys"); ++e->launches;
-    dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, L.score_bits, s); ++e->launches;
+  } else {      // stable by -score (arrival order = input order), then stable by (guide, contig, start, strand)
+    e->key_b.ensure((size_t)n * 8); e->sstart.ensure((size_t)n * 4);
+    uint32_t* ord = e->sstart.as<uint32_t>();    // positions 0..n-1, carried through the first sort to permute the second sort's keys
+    CAL_LAUNCH(k_dedup_keys, blocks_for(n_slots, 256), 256, 0, s, 1, aa.recs, rw, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, L, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>(), d_overflow); dev::launch_check("k_dedup_keys"); ++e->launches;
+    CAL_LAUNCH(k_iota_u32, blocks_for(n, 256), 256, 0, s, 1, ord, n); dev::launch_check("k_iota_u32"); ++e->launches;
+    dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), ord, e->idx2.as<uint32_t>(), (size_t)n, 0, L.score_bits, s); ++e->launches;
     CAL_LAUNCH(k_gather_u64, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), n, e->keyA.as<uint64_t>()); dev::launch_check("k_gather_u64"); ++e->launches;
-    dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), e->idx.as<uint32_t>(), (size_t)n, 0, L.bits, s); ++e->launches;
+    CAL_LAUNCH(k_gather_u32, blocks_for(n, 256), 256, 0, s, 1, e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), n, ord); dev::launch_check("k_gather_u32"); ++e->launches;
+    dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), ord, e->idx.as<uint32_t>(), (size_t)n, 0, L.bits, s); ++e->launches;
     skey = e->key1.as<uint64_t>(); sidx = e->idx.as<uint32_t>(); strand_shift = 0;
   }
-  // skey[i], sidx[i] sorted by (guide, contig, start, strand, -score, arrival)
-  e->sstart.ensure((size_t)n * 4); e->send.ensure((size_t)n * 4); e->sscore.ensure((size_t)n * 4); e->sowned.ensure((size_t)n); e->flag.ensure((size_t)n * 4); e->pos.ensure((size_t)n * 4);
-  CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, hits, e->kept_owned.as<uint8_t>(), sidx, n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
-  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, skey, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, max_overlap, max_overlap >= 1 ? 1 : 0, strand_shift, L.start_bits, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
+  // skey[i], sidx[i] (= alignment slot) sorted by (guide, contig, start, strand, -score, arrival)
+  e->sstart.ensure((size_t)n * 4); e->send.ensure((size_t)n * 4); e->sscore.ensure((size_t)n * 4); e->sowned.ensure((size_t)n);
+  e->key_b.ensure((size_t)n * 4);
+  uint32_t* keep = e->rank.as<uint32_t>(); uint32_t* kpos = e->key_b.as<uint32_t>();   // rank (one word per slot) is free again after k_canon
+  CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, aa.recs, rw, e->slot_owned.as<uint8_t>(), sidx, n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
+  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, skey, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, P.max_overlap, P.max_overlap >= 1 ? 1 : 0, strand_shift, L.start_bits, keep); dev::launch_check("k_sweep"); ++e->launches;
   tb = dev::exclusive_sum_u32_tmp((size_t)n); e->tmp.ensure(tb);
-  dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n, s); ++e->launches;
-  CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, e->pos.as<uint32_t>() + (n - 1), e->flag.as<uint32_t>() + (n - 1), (const unsigned long long*)(e->d_count + CNT_DEDUP_OVERFLOW), e->h_count_dev + CNT_KEEPERS); dev::launch_check("k_publish_sum");
+  dev::exclusive_sum_u32(e->tmp.p, tb, keep, kpos, (size_t)n, s); ++e->launches;
+  CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, kpos + (n - 1), keep + (n - 1), (const unsigned long long*)(e->d_count + CNT_DEDUP_OVERFLOW), e->h_count_dev + CNT_KEEPERS); dev::launch_check("k_publish_sum");
   dev::stream_sync(s);
   if (((volatile unsigned long long*)e->h_count)[CNT_KEEPERS + 1]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in removeOverlaps");
   const int64_t nk = (int64_t)((volatile unsigned long long*)e->h_count)[CNT_KEEPERS];
   if (nk == 0) return 0;
-  e->out.ensure_keep((size_t)(out_n + nk) * sizeof(calitas_hit), (size_t)out_n * sizeof(calitas_hit), s);
-  CAL_LAUNCH(k_gather_keepers, blocks_for(n, 256), 256, 0, s, 1, hits, sidx, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n, e->out.as<calitas_hit>() + out_n); dev::launch_check("k_gather_keepers"); ++e->launches;
+  ensure_out(e, rw, out_n, nk, projected_total);
+  CAL_LAUNCH(k_gather_keepers, blocks_for(n, 256), 256, 0, s, 1, aa.recs, rw, sidx, keep, kpos, n, e->out.as<uint32_t>() + out_n * rw); dev::launch_check("k_gather_keepers"); ++e->launches;
   return nk;
 }
 
-calitas_hitset* finish_hitset(calitas_engine* e, int64_t n_out, const double ms[8], const int64_t counts[8]) {
+calitas_hitset* finish_hitset(calitas_engine* e, int64_t n_out, int rw, const double ms[8], const int64_t counts[8]) {
   std::unique_ptr<calitas_hitset> hs(new calitas_hitset());
-  hs->owner = e; hs->n = n_out;
-  hs->buf = take_pinned(e, (size_t)std::max<int64_t>(1, n_out) * sizeof(calitas_hit));
+  hs->owner = e; hs->n = n_out; hs->stride = rw * 4;
+  hs->buf = take_pinned(e, (size_t)std::max<int64_t>(1, n_out) * rw * 4);
   dev::event_record(e->ev[6], e->stream);
-  dev::d2h(hs->buf.p, e->out.p, (size_t)n_out * sizeof(calitas_hit), e->stream);
+  dev::d2h(hs->buf.p, e->out.p, (size_t)n_out * rw * 4, e->stream);
   dev::event_record(e->ev[1], e->stream);
   dev::stream_sync(e->stream);
   for (int i = 0; i < 8; ++i) { hs->ms[i] = ms[i]; hs->counts[i] = counts[i]; }
   hs->ms[0] = dev::event_ms(e->ev[0], e->ev[1]);
   hs->ms[4] = dev::event_ms(e->ev[6], e->ev[1]);
   hs->ms[3] = hs->ms[0] - hs->ms[1] - hs->ms[2] - hs->ms[4];
-  hs->counts[5] += (int64_t)((size_t)n_out * sizeof(calitas_hit));
+  hs->counts[5] += (int64_t)((size_t)n_out * rw * 4);
   return hs.release();
 }
 
 std::vector<GuideSpec> build_specs(calitas_engine* e, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits, bool best, std::vector<GuideDef>* defs_out) {
   if (n_guides <= 0 || !guides) throw InvalidArgument("no guides given");
-  if (n_guides > MAX_GUIDES_PER_CALL) throw LimitExceeded("more than 16384 guides in one call");
+  if (n_guides > MAX_GUIDES_PER_CALL) throw LimitExceeded("more than " + std::to_string(MAX_GUIDES_PER_CALL) + " guides in one call");
   if (!limits) throw InvalidArgument("limits is NULL");
   std::vector<GuideSpec> specs;
   for (int i = 0; i < n_guides; ++i) { GuideDef d = parse_guide(guides[i]); specs.push_back(make_guide_spec(d, e->sc, *limits, best)); if (defs_out) defs_out->push_back(d); }
@@ -889,7 +923,8 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
   dev::Stream s = e->stream; dev::set_device(e->device);
   e->launches = 0;
   dev::event_record(e->ev[0], s);
-  int slots = 1, banded = 1; for (auto& sp : specs) { slots = std::max(slots, sp.slots); banded = std::max(banded, std::max(sp.k_edits, sp.band_k)); }
+  int slots = 1, banded = 1, max_cols = 1; for (auto& sp : specs) { slots = std::max(slots, sp.slots); banded = std::max(banded, std::max(sp.k_edits, sp.band_k)); max_cols = std::max(max_cols, sp.max_cols); }
+  const int rw = rec_words_for(max_cols);
   if (banded > ALIGN_KB) banded = 0;
   e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
   e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
@@ -919,19 +954,15 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
     ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
     counts[1] += (int64_t)n_cand;
     // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
-    Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true, key };
+    Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true, key, rw, nullptr, 0 };
     int64_t n_aln = 0;
-    const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
+    const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_out, 0, n_aln);
     if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
     counts[2] += n_aln;
-    if (n_kept) {
-      e->out.ensure_keep((size_t)(n_out + n_kept) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
-      dev::d2d(e->out.as<calitas_hit>() + n_out, e->kept.p, (size_t)n_kept * sizeof(calitas_hit), s);
-    }
     n_out += n_kept;
   }
   counts[3] = e->launches;
-  return finish_hitset(e, n_out, ms, counts);
+  return finish_hitset(e, n_out, rw, ms, counts);
 }
 
 }  // namespace
@@ -975,8 +1006,8 @@ void calitas_engine_destroy(calitas_engine* e) {
   try {
     dev::set_device(e->device);
     dev::stream_sync(e->scan_stream); dev::stream_sync(e->stream); dev::stream_sync(e->copy_stream);
-    for (DBuf* b : { &e->cand_b, &e->cand_c, &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->kept, &e->out, &e->tmp, &e->key1, &e->keyA,
-                     &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp, &e->slot_owned, &e->kept_owned, &e->sowned }) b->release();
+    for (DBuf* b : { &e->cand_b, &e->cand_c, &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->out, &e->tmp, &e->key1, &e->keyA,
+                     &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp, &e->slot_owned, &e->sowned }) b->release();
     for (auto& p : e->pinned_pool) dev::free_host(p.p);
     dev::free_host(e->h_count); dev::free_(e->d_count);
     for (auto& ev : e->ev) dev::event_destroy(ev);
@@ -1164,7 +1195,9 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       CAL_LAUNCH(k_publish_u64, 1, 1, 0, ss, 1, e->d_count + slot, e->h_count_dev + slot); dev::launch_check("k_publish_u64");
       dev::event_record(ce.ev[CE_COUNT], ss);
     };
-    PinnedBuf pin = take_pinned(e, std::max<size_t>(e->out_hits_hint, 1024) * sizeof(calitas_hit));
+    int max_cols = 1; for (auto& sp : specs) max_cols = std::max(max_cols, sp.max_cols);
+    const int rw = rec_words_for(max_cols); const size_t rec_bytes = (size_t)rw * 4;
+    PinnedBuf pin = take_pinned(e, std::max<size_t>(e->out_hits_hint, 1024) * rec_bytes);
     int64_t n_out = 0; size_t copies = 0;
     try {
       for (size_t c = 0; c < (size_t)(N_SLOTS - 1) && c < n_chunks; ++c) launch_scan(c);
@@ -1184,36 +1217,27 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         counts[1] += (int64_t)n_cand;
         dev::event_record(ce.ev[CE_TAIL_B], s);
         Pipeline P{ e, cand_slot[slot]->as<uint64_t>(), ce.ev[CE_SORTED], ce.ev[CE_ALIGN_B], ce.ev[CE_ALIGN_E], e->specs.as<GuideSpec>(), ch.slots, false, ch.banded,
-                    ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, 0, dedup == 0, ch.key };
+                    ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, 0, dedup == 0, ch.key, rw, dedup ? &ch.dedup : nullptr, limits->max_overlap };
         int64_t n_aln = 0;
-        const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_aln);
+        // room in e->out: what this chunk adds, and (when it has to grow) the rest of the call projected from the hits per guide so far
+        const size_t projected = ch.g0 > 0 ? (size_t)((double)n_out * (double)n_guides / (double)ch.g0 * 1.15) + 4096 : e->out_hits_hint;
+        const int64_t n_new = run_tail(P, (int64_t)n_cand, n_out, projected, n_aln);
         counts[2] += n_aln;
-        int64_t n_new = 0;
-        if (dedup && n_kept) {      // room for the keepers: at most n_kept here, and the rest of the call projected from the guides done so far
-          const size_t projected = (size_t)((double)(n_out + n_kept) * (double)n_guides / (double)std::max(1, ch.g1) * 1.15) + 4096;
-          if ((size_t)(n_out + n_kept) * sizeof(calitas_hit) > e->out.cap) e->out.ensure_keep(std::max((size_t)(n_out + n_kept), projected) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
-        }
-        if (dedup) n_new = run_dedup(e, n_kept, limits->max_overlap, n_out, ch.dedup);
-        else if (n_kept) {
-          e->out.ensure_keep((size_t)(n_out + n_kept) * sizeof(calitas_hit), (size_t)n_out * sizeof(calitas_hit), s);
-          dev::d2d(e->out.as<calitas_hit>() + n_out, e->kept.p, (size_t)n_kept * sizeof(calitas_hit), s);
-          n_new = n_kept;
-        }
         dev::event_record(ce.ev[CE_TAIL_E], s);
         // the finished segment goes to the host while later chunks compute
         dev::stream_wait(cs, ce.ev[CE_TAIL_E]);
         dev::event_record(ce.ev[CE_COPY_B], cs);
         if (n_new) {
-          if ((size_t)(n_out + n_new) * sizeof(calitas_hit) > pin.cap) {
+          if ((size_t)(n_out + n_new) * rec_bytes > pin.cap) {
             dev::stream_sync(cs);
             // first call on this engine: size the result buffer once from the hits per guide seen so far (page-locking gigabytes is slow,
             // so growing it chunk by chunk cost seconds); later calls start from the previous call's total
             const size_t projected = (size_t)((double)(n_out + n_new) * (double)n_guides / (double)std::max(1, ch.g1) * 1.15) + 4096;
-            PinnedBuf bigger = take_pinned(e, std::max((size_t)(n_out + n_new) * 3 / 2, projected) * sizeof(calitas_hit));
-            std::memcpy(bigger.p, pin.p, (size_t)n_out * sizeof(calitas_hit));
+            PinnedBuf bigger = take_pinned(e, std::max((size_t)(n_out + n_new) * 3 / 2, projected) * rec_bytes);
+            std::memcpy(bigger.p, pin.p, (size_t)n_out * rec_bytes);
             e->pinned_pool.push_back(pin); pin = bigger;
           }
-          dev::d2h((calitas_hit*)pin.p + n_out, e->out.as<calitas_hit>() + n_out, (size_t)n_new * sizeof(calitas_hit), cs);
+          dev::d2h((char*)pin.p + (size_t)n_out * rec_bytes, e->out.as<char>() + (size_t)n_out * rec_bytes, (size_t)n_new * rec_bytes, cs);
           n_out += n_new;
         }
         dev::event_record(ce.ev[CE_COPY_E], cs);
@@ -1247,10 +1271,10 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     }
     ms[5] = ms[0] - ms[1];                                   // time of the call not hidden behind the scan kernels
     counts[3] = e->launches;
-    counts[5] = (int64_t)((size_t)n_out * sizeof(calitas_hit));
+    counts[5] = (int64_t)((size_t)n_out * rec_bytes);
     e->out_hits_hint = std::max<size_t>(e->out_hits_hint, (size_t)n_out + (size_t)n_out / 8);
     std::unique_ptr<calitas_hitset> hs(new calitas_hitset());
-    hs->owner = e; hs->n = n_out; hs->buf = pin;
+    hs->owner = e; hs->n = n_out; hs->buf = pin; hs->stride = (int32_t)rec_bytes;
     for (int i = 0; i < 8; ++i) { hs->ms[i] = ms[i]; hs->counts[i] = counts[i]; }
     *out = hs.release();
     return CALITAS_OK;
@@ -1330,6 +1354,7 @@ int calitas_microbench_int(calitas_engine* e, int32_t kind, double* tera_ops_per
 
 int64_t calitas_hitset_count(const calitas_hitset* h) { return h ? h->n : 0; }
 const calitas_hit* calitas_hitset_data(const calitas_hitset* h) { return h ? (const calitas_hit*)h->buf.p : nullptr; }
+int32_t calitas_hitset_stride(const calitas_hitset* h) { return h ? h->stride : CALITAS_HIT_WORDS * 4; }
 void calitas_hitset_free(calitas_hitset* h) { if (!h) return; if (h->owner) h->owner->pinned_pool.push_back(h->buf); delete h; }
 int calitas_hitset_stats(const calitas_hitset* h, double ms[8], int64_t counts[8]) {
   if (!h) return set_error(CALITAS_EINVAL, "hitset is NULL");
@@ -1337,15 +1362,15 @@ int calitas_hitset_stats(const calitas_hitset* h, double ms[8], int64_t counts[8
   return CALITAS_OK;
 }
 
-int calitas_render_alignments(const calitas_hit* hits, int64_t n_hits, int32_t n_guides, const calitas_guide* guides, int32_t n_contigs, const char* const* names,
+int calitas_render_alignments(const void* hits, int64_t n_hits, int32_t stride, int32_t n_guides, const calitas_guide* guides, int32_t n_contigs, const char* const* names,
                               const uint8_t* const* contig_bases, const calitas_target_task* targets, int32_t upper_case, char** out_text) {
   return guarded([&]() -> int {
-    if (!out_text || (n_hits && !hits) || !guides) throw InvalidArgument("bad render arguments");
+    if (!out_text || (n_hits && !hits) || !guides || (stride != CALITAS_HIT_WORDS * 4 && stride != CALITAS_HIT_WIDE_WORDS * 4)) throw InvalidArgument("bad render arguments");
     *out_text = nullptr;
     std::vector<GuideDef> defs; for (int i = 0; i < n_guides; ++i) defs.push_back(parse_guide(guides[i]));
     std::string text = alignment_header();
     for (int64_t i = 0; i < n_hits; ++i) {
-      const calitas_hit& h = hits[i];
+      HitX h; unpack_hit(reinterpret_cast<const uint32_t*>((const char*)hits + (size_t)i * stride), stride / 4, h);
       if (h.guide_idx < 0 || h.guide_idx >= n_guides) throw InvalidArgument("hit guide_idx out of range");
       std::string fwd, chrom = "n/a";
       const int32_t len = h.end_offset - h.start_offset;

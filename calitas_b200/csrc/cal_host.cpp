@@ -119,12 +119,14 @@ GuideSpec make_guide_spec(const GuideDef& g, const Scores& sc, const calitas_lim
   s.span = (int)span;
   s.band_k = (int)(dels > ins ? dels : ins);   // a co-optimal path of an accepted end cell never leaves the 2 * band_k + 1 diagonals around the end cell's
   if (lp + dels + s.g + g.pam_length() > CALITAS_MAX_OPS) throw LimitExceeded("alignment longer than CALITAS_MAX_OPS columns");
+  if (dels + s.g + g.pam_length() > 63) throw LimitExceeded("trailing deletions + guide-PAM gap + PAM longer than 63 bases do not fit the hit record");
+  s.max_cols = (int)(lp + dels + (s.n_pams > 0 ? s.g + g.pam_length() : 0));
   return s;
 }
 
 // Allocation-free core of the rendering: every ReferenceHit row goes through it (tens of millions per run), so it works on fixed arrays.
 // `guide` = guide + PAM text in guide orientation (GuideDef::with_pam); `target_fwd` = the hit's bases as stored, forward orientation.
-void render_hit_fix(const calitas_hit& h, const char* guide, int guide_len, const char* target_fwd, int target_len, bool upper_case, RenderedFix& r) {
+void render_hit_fix(const HitX& h, const char* guide, int guide_len, const char* target_fwd, int target_len, bool upper_case, RenderedFix& r) {
   static const char kOps[4] = { '=', 'X', 'I', 'D' };
   const bool neg = h.strand == '-';
   const int n = h.n_ops;
@@ -177,7 +179,7 @@ void render_hit_fix(const calitas_hit& h, const char* guide, int guide_len, cons
   if (first_upper >= 0) for (int i = first_upper; i <= last_upper; ++i) if (is_alpha(pt[i])) r.unpadded[r.unpadded_len++] = pt[i];
 }
 
-Rendered render_hit(const calitas_hit& h, const GuideDef& g, const std::string& target_fwd, bool upper_case) {
+Rendered render_hit(const HitX& h, const GuideDef& g, const std::string& target_fwd, bool upper_case) {
   Rendered r; RenderedFix f;
   r.guide = g.with_pam(h.pam_idx);
   render_hit_fix(h, r.guide.data(), (int)r.guide.size(), target_fwd.data(), (int)target_fwd.size(), upper_case, f);
@@ -192,7 +194,7 @@ std::string alignment_header() {
   return "guide\tchrom\tstartOffset\tendOffset\tguideStartOffset\tguideEndOffset\tstrand\tscore\tcigar\tpaddedGuide\tpaddedAlignment\tpaddedTarget\t"
          "mismatches\tgapBases\tedits\tguideMismatches\tguideGapBases\tguideMmsPlusGaps\tpamMismatches\tpamGapBases\tpamMmsPlusGaps\tunpaddedTargetWithoutPam\n";
 }
-std::string alignment_row(const calitas_hit& h, const Rendered& r, const std::string& chrom) {
+std::string alignment_row(const HitX& h, const Rendered& r, const std::string& chrom) {
   std::string s = r.guide; auto add = [&](const std::string& v) { s += '\t'; s += v; }; auto I = [](int v) { return std::to_string(v); };
   add(chrom); add(I(h.start_offset)); add(I(h.end_offset)); add(I(h.guide_start_offset)); add(I(h.guide_end_offset)); add(std::string(1, (char)h.strand));
   add(I(h.score)); add(r.cigar); add(r.padded_guide); add(r.padded_alignment); add(r.padded_target); add(I(r.mismatches)); add(I(r.gap_bases)); add(I(r.edits));

@@ -44,10 +44,10 @@ struct RenderedFix {
   char unpadded[CALITAS_MAX_OPS]; int unpadded_len;
   int mismatches, gap_bases, edits, guide_mm, guide_gaps, guide_mm_plus_gaps, pam_mm, pam_gaps, pam_mm_plus_gaps;
 };
-void render_hit_fix(const calitas_hit& h, const char* guide, int guide_len, const char* target_fwd, int target_len, bool upper_case, RenderedFix& r);
+void render_hit_fix(const HitX& h, const char* guide, int guide_len, const char* target_fwd, int target_len, bool upper_case, RenderedFix& r);
 // `target` = bases [start_offset, end_offset) of the hit in forward orientation (as stored); rendered in guide orientation.
-Rendered render_hit(const calitas_hit& h, const GuideDef& g, const std::string& target_fwd, bool upper_case);
+Rendered render_hit(const HitX& h, const GuideDef& g, const std::string& target_fwd, bool upper_case);
 std::string alignment_header();
-std::string alignment_row(const calitas_hit& h, const Rendered& r, const std::string& chrom);
+std::string alignment_row(const HitX& h, const Rendered& r, const std::string& chrom);
 
 }  // namespace cal

@@ -41,7 +41,11 @@ Str to_upper(Str s) { for (auto& c : s) c = (char)std::toupper((unsigned char)c)
 
 struct HitSet {   // RAII over calitas_hitset
   calitas_hitset* h = nullptr; ~HitSet() { calitas_hitset_free(h); }
-  int64_t n() const { return calitas_hitset_count(h); } const calitas_hit* data() const { return calitas_hitset_data(h); }
+  int64_t n() const { return calitas_hitset_count(h); }
+  // record i of the set (packed, calitas_hitset_stride() bytes apart) and its expanded form
+  const calitas_hit* at(int64_t i) const { return reinterpret_cast<const calitas_hit*>(reinterpret_cast<const char*>(calitas_hitset_data(h)) + (size_t)i * (size_t)calitas_hitset_stride(h)); }
+  HitX x(int64_t i) const { HitX v; unpack_hit(reinterpret_cast<const uint32_t*>(at(i)), calitas_hitset_stride(h) / 4, v); return v; }
+  std::vector<HitX> all() const { std::vector<HitX> v((size_t)n()); for (int64_t i = 0; i < n(); ++i) v[(size_t)i] = x(i); return v; }
 };
 
 // Row rendering is the host-side bottleneck once the search takes milliseconds: rows are independent, so they are
@@ -68,8 +72,8 @@ template <class F> void parallel_for(int64_t n, int64_t grain, F fn) {
 int contig_index(const calitas_genome_view& g, const Str& name) { for (int i = 0; i < g.n_contigs; ++i) if (name == g.names[i]) return i; return -1; }
 
 // ---- GuideAlignment ordering (GuideAlignment.scala:125-129): stable sort by score desc, gap bases asc ----
-void sort_alignments(std::vector<calitas_hit>& v) {
-  std::stable_sort(v.begin(), v.end(), [](const calitas_hit& a, const calitas_hit& b) { return a.score != b.score ? a.score > b.score : a.gap_bases < b.gap_bases; });
+void sort_alignments(std::vector<HitX>& v) {
+  std::stable_sort(v.begin(), v.end(), [](const HitX& a, const HitX& b) { return a.score != b.score ? a.score > b.score : a.gap_bases < b.gap_bases; });
 }
 
 // ---- ReferenceHit rows (ReferenceHit.scala:99-132, 210-254) ----------------------------------------------------------------------
@@ -142,7 +146,7 @@ RowConst make_row_const(const RowContext& cx, const GuideDef& gd) {
 const Str& guide_text_of(const RowConst& rc, int pam_idx) { return pam_idx >= 0 ? rc.guide_text[(size_t)pam_idx] : rc.guide_text.back(); }
 
 // Appends one ReferenceHit line (ReferenceHit.scala:210-254).  `var` = variant columns (id, description, vcf, allele frequency), or NULL.
-void write_row(Str& out, const RowContext& cx, const RowConst& rc, const GuideDef& gd, const calitas_hit& h, const RenderedFix& r, int contig, int so, int eo, int gso, int geo,
+void write_row(Str& out, const RowContext& cx, const RowConst& rc, const GuideDef& gd, const HitX& h, const RenderedFix& r, int contig, int so, int eo, int gso, int geo,
                const Str* var /* [4] */, const Flanks& fl) {
   const calitas_genome_view& g = *cx.genome;
   const bool neg = h.strand == '-';
@@ -168,9 +172,9 @@ void write_row(Str& out, const RowContext& cx, const RowConst& rc, const GuideDe
 
 // ReferenceHit.sort order (ReferenceHit.scala:276-287) on hit records: contig, coordinate_start, strand ("+" < "-"), score descending.
 bool hit_sorts_before(const calitas_hit* a, const calitas_hit* b) {
-  if (a->contig_idx != b->contig_idx) return a->contig_idx < b->contig_idx;
-  if (a->guide_start_offset != b->guide_start_offset) return a->guide_start_offset < b->guide_start_offset;
-  if (a->strand != b->strand) return a->strand < b->strand;
+  const int ca = calitas_hit_contig_idx(a), cb = calitas_hit_contig_idx(b); if (ca != cb) return ca < cb;
+  const int sa = calitas_hit_guide_start_offset(a), sb = calitas_hit_guide_start_offset(b); if (sa != sb) return sa < sb;
+  const char ta = calitas_hit_strand(a), tb = calitas_hit_strand(b); if (ta != tb) return ta < tb;
   return a->score > b->score;
 }
 // order[0, seg) and order[seg, end) are each sorted (one guide's hits of the shards so far, and of the next shard).  Shards are ascending base
@@ -185,7 +189,7 @@ void merge_at_cut(std::vector<const calitas_hit*>& order, size_t seg) {
 }
 
 // A row with what removeOverlaps / sort on the host need (VCF runs only: variant-window hits are merged with reference hits there).
-Row make_row(const RowContext& cx, const RowConst& rc, const calitas_hit& h, const RenderedFix& r, const GuideDef& gd, int contig, int so, int eo, int gso, int geo,
+Row make_row(const RowContext& cx, const RowConst& rc, const HitX& h, const RenderedFix& r, const GuideDef& gd, int contig, int so, int eo, int gso, int geo,
              const std::vector<VariantAllele>& variants, const Flanks& fl) {
   const calitas_genome_view& g = *cx.genome;
   std::vector<const VariantAllele*> vs;
@@ -426,7 +430,7 @@ Str core_parameters_a2r(const calitas_a2r_options& o, const calitas_costs& c) { 
   std::sort(kv.begin(), kv.end()); Str s; for (size_t i = 0; i < kv.size(); ++i) { if (i) s += ';'; s += kv[i]; } return s;
 }
 
-Str render_rows(const std::vector<calitas_hit>& hits, const GuideDef& gd, const Str& chrom, const Str& target_fwd_base, int target_offset, const calitas_genome_view* genome) {
+Str render_rows(const std::vector<HitX>& hits, const GuideDef& gd, const Str& chrom, const Str& target_fwd_base, int target_offset, const calitas_genome_view* genome) {
   Str text = alignment_header();
   for (auto& h : hits) {
     Str fwd;
@@ -450,7 +454,7 @@ int calitas_tool_align(calitas_engine* e, const calitas_guide* guide, const uint
     GuideDef gd = parse_guide(*guide);
     calitas_target_task task{ 0, target, target_len, target_offset };
     HitSet hs; ck(calitas_align_targets(e, 1, guide, 1, &task, limits, 0, &hs.h));
-    std::vector<calitas_hit> hits(hs.data(), hs.data() + hs.n());
+    std::vector<HitX> hits = hs.all();
     *out_text = dup_text(render_rows(hits, gd, target_name ? target_name : "n/a", Str((const char*)target, (size_t)target_len), target_offset, nullptr));
     return CALITAS_OK;
   });
@@ -465,8 +469,8 @@ int calitas_tool_align_best(calitas_engine* e, const calitas_guide* guide, const
     calitas_target_task task{ 0, target, target_len, 0 };
     HitSet hs; ck(calitas_align_targets(e, 1, guide, 1, &task, &lim, 1, &hs.h));
     if (hs.n() == 0) throw ToolError{ CALITAS_ESTATE, "empty.maxBy" };                               // SequentialGuideAligner.scala:344
-    const calitas_hit* best = hs.data(); for (int64_t i = 1; i < hs.n(); ++i) if (hs.data()[i].score > best->score) best = hs.data() + i;   // maxBy keeps the first maximum
-    *out_text = dup_text(render_rows({ *best }, gd, "n/a", Str((const char*)target, (size_t)target_len), 0, nullptr));
+    int64_t best = 0; for (int64_t i = 1; i < hs.n(); ++i) if (hs.at(i)->score > hs.at(best)->score) best = i;   // maxBy keeps the first maximum
+    *out_text = dup_text(render_rows({ hs.x(best) }, gd, "n/a", Str((const char*)target, (size_t)target_len), 0, nullptr));
     return CALITAS_OK;
   });
 }
@@ -483,7 +487,7 @@ int calitas_tool_align_to_ref(calitas_engine* e, const calitas_reference* ref, c
     const int64_t rs = std::max<int64_t>((int64_t)pos - padding, 1), re = std::min<int64_t>((int64_t)pos + padding, genome->lengths[ci]);   // :373
     calitas_region_task task{ 0, ci, rs - 1, (int32_t)std::max<int64_t>(0, re - rs + 1) };
     HitSet hs; ck(calitas_align_regions(e, ref, 1, guide, 1, &task, limits, best, &hs.h));
-    std::vector<calitas_hit> hits(hs.data(), hs.data() + hs.n());
+    std::vector<HitX> hits = hs.all();
     sort_alignments(hits);                                                                           // :386
     if (best) { if (hits.empty()) throw ToolError{ CALITAS_ESTATE, "head of empty list" }; hits.resize(1); }   // :417
     *out_text = dup_text(render_rows(hits, gd, chrom, Str(), 0, genome));
@@ -558,11 +562,12 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
         struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{ prefetch };      // an exception below must not leave the helper running
         const Flanks none;
         std::vector<int64_t> cursor((size_t)n_engines, 0);          // every hit set is guide-major; guide_idx counts from the batch's first guide
+        const int rec_words = calitas_hitset_stride(hs[0].h) / 4;     // one record size per call: the same guides and limits went to every engine
         for (int g = g0; g < g1; ++g) {
           std::vector<const calitas_hit*> order;                    // this guide's hits: shard 0's, then shard 1's, ... = ReferenceHit.sort order
           for (int s = 0; s < n_engines; ++s) {
             int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s]; const size_t seg = order.size();
-            for (; i < h_.n() && h_.data()[i].guide_idx == g - g0; ++i) order.push_back(h_.data() + i);
+            for (; i < h_.n() && calitas_hit_guide_idx(h_.at(i)) == g - g0; ++i) order.push_back(h_.at(i));
             if (!host_dedup) merge_at_cut(order, seg);
           }
           const GuideDef& gd = defs[(size_t)g]; const RowContext& cx = cxs[(size_t)g]; const RowConst& rc = rcs[(size_t)g];
@@ -574,7 +579,7 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
             if (blk) blk->reserve((size_t)(e_ - b) * 640);
             RenderedFix r;
             for (int64_t k = b; k < e_; ++k) {
-              const calitas_hit& h = *order[(size_t)k];
+              HitX h; unpack_hit(reinterpret_cast<const uint32_t*>(order[(size_t)k]), rec_words, h);
               const Str& gt = guide_text_of(rc, h.pam_idx);
               render_hit_fix(h, gt.data(), (int)gt.size(), (const char*)genome->bases[h.contig_idx] + h.start_offset, h.end_offset - h.start_offset, true, r);   // windows are upper-cased, SearchReference.scala:67
               if (blk) write_row(*blk, cx, rc, gd, h, r, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, nullptr, none);
@@ -626,8 +631,8 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
         for (size_t wi = 0; wi < ws.size(); ++wi, ++rr) {
           const size_t s = (size_t)(rr % n_engines); const int64_t t = next_task[s]++; int64_t& i = cursor[s]; const HitSet& h_ = hs[s];
           const VariantWindow& w = ws[wi]; const GuideDef& gd = defs[(size_t)g];
-          for (; i < h_.n() && h_.data()[i].task_idx == t; ++i) {
-            const calitas_hit& h = h_.data()[i];
+          for (; i < h_.n() && h_.at(i)->task_idx == t; ++i) {
+            const HitX h = h_.x(i);
             const Str& gt = guide_text_of(rcs[(size_t)g], h.pam_idx);
             RenderedFix r; render_hit_fix(h, gt.data(), (int)gt.size(), w.bases.data() + h.start_offset, h.end_offset - h.start_offset, false, r);
             const int wl = (int)w.bases.size();
@@ -729,13 +734,14 @@ int calitas_tool_align_to_reference(calitas_engine* e, const calitas_reference* 
       // hits arrive grouped by task in retval order: per task apply `.sorted` (+ `.head` in best mode), render on all host threads
       const int64_t nt = s1 - s0;
       std::vector<int64_t> first((size_t)nt + 1, 0);
-      { int64_t i = 0; for (int64_t t = 0; t < nt; ++t) { first[(size_t)t] = i; while (i < hs.n() && hs.data()[i].task_idx == t) ++i; } first[(size_t)nt] = i; if (i != hs.n()) throw ToolError{ CALITAS_ESTATE, "hit set is not task-major" }; }
+      { int64_t i = 0; for (int64_t t = 0; t < nt; ++t) { first[(size_t)t] = i; while (i < hs.n() && hs.at(i)->task_idx == t) ++i; } first[(size_t)nt] = i; if (i != hs.n()) throw ToolError{ CALITAS_ESTATE, "hit set is not task-major" }; }
       if (best) for (int64_t t = 0; t < nt; ++t) if (first[(size_t)t] == first[(size_t)t + 1])          // alignToRefBest(...).head on an empty result throws in the reference
         throw ToolError{ CALITAS_ESTATE, Str("head of empty list: no alignment for query ") + tasks[s0 + t].query };
       std::vector<std::vector<Row>> task_rows((size_t)nt);
       parallel_for(nt, 256, [&](int64_t tb, int64_t te) {
         for (int64_t t = tb; t < te; ++t) {
-          std::vector<calitas_hit> alns(hs.data() + first[(size_t)t], hs.data() + first[(size_t)t + 1]); sort_alignments(alns);
+          std::vector<HitX> alns; for (int64_t i = first[(size_t)t]; i < first[(size_t)t + 1]; ++i) alns.push_back(hs.x(i));
+          sort_alignments(alns);
           if (best) alns.resize(1);
           const GuideDef& gd = defs[(size_t)rt[(size_t)t].guide_idx];
           RowContext c2 = cx; c2.guide_id = tasks[s0 + t].id ? tasks[s0 + t].id : tasks[s0 + t].query;    // :100
@@ -784,9 +790,10 @@ int calitas_tool_pairwise_align(calitas_engine* e, int64_t n_pairs, const char* 
       HitSet hs; ck(calitas_align_targets(e, (int32_t)cg.size(), cg.data(), (int64_t)tasks.size(), tasks.data(), &lim, 1, &hs.h));
       int64_t i = 0;
       for (int64_t t = 0; t < (int64_t)tasks.size(); ++t) {
-        const calitas_hit* best = nullptr;
-        for (; i < hs.n() && hs.data()[i].task_idx == t; ++i) if (!best || hs.data()[i].score > best->score) best = hs.data() + i;     // maxBy keeps the first maximum (:344)
-        if (!best) throw ToolError{ CALITAS_ESTATE, Str("empty.maxBy: no alignment for ") + queries[b0 + t] };
+        int64_t best_i = -1;
+        for (; i < hs.n() && hs.at(i)->task_idx == t; ++i) if (best_i < 0 || hs.at(i)->score > hs.at(best_i)->score) best_i = i;     // maxBy keeps the first maximum (:344)
+        if (best_i < 0) throw ToolError{ CALITAS_ESTATE, Str("empty.maxBy: no alignment for ") + queries[b0 + t] };
+        const HitX best_hit = hs.x(best_i); const HitX* best = &best_hit;
         const Str& tgt = ups[(size_t)t]; const GuideDef& gd = defs[(size_t)tasks[(size_t)t].guide_idx];
         Rendered r = render_hit(*best, gd, tgt.substr((size_t)best->start_offset, (size_t)(best->end_offset - best->start_offset)), false);
         text += Str(queries[b0 + t]) + "\t" + tgt + "\t" + std::to_string(best->score) + "\t1\t" + std::to_string(best->start_offset) + "\t" + r.cigar + "\t" +

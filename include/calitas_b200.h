@@ -33,7 +33,8 @@ extern "C" {
 #define CALITAS_MAX_PROTOSPACER 32
 #define CALITAS_MAX_PAM_LEN     16
 #define CALITAS_MAX_PAMS        8
-#define CALITAS_MAX_OPS         128   /* alignment columns per hit */
+#define CALITAS_MAX_OPS         128   /* alignment columns per hit (48 in a calitas_hit, more in a calitas_hit_wide) */
+#define CALITAS_MAX_GUIDES      8192  /* guides per call (13 bits of calitas_hit.where) */
 
 typedef struct calitas_engine calitas_engine;
 typedef struct calitas_reference calitas_reference;
@@ -63,26 +64,42 @@ typedef struct calitas_guide {
   int32_t n_aux_pams;
 } calitas_guide;
 
-/* One alignment: the POD image of GuideAlignment (GuideAlignment.scala:72-88).  Strings (padded guide / alignment /
- * target, cigar text, the derived counters of GuideAlignment.scala:99-163) are rendered on the host from `ops`
- * and the reference bases by calitas_render_*; ops are in guide orientation, 2 bits per alignment column:
- * 0 '=', 1 'X', 2 'I' (guide base opposite a genome gap), 3 'D' (genome base opposite a guide gap). */
+/* One alignment: the POD image of GuideAlignment (GuideAlignment.scala:72-88), 32 bytes.  Strings (padded guide / alignment / target, cigar
+ * text, the derived counters of GuideAlignment.scala:99-163) are rendered on the host from `ops` and the reference bases by
+ * calitas_render_*; ops are in guide orientation, 2 bits per alignment column, column k in bits 2(k mod 16) of ops[k / 16]:
+ * 0 '=', 1 'X', 2 'I' (guide base opposite a genome gap), 3 'D' (genome base opposite a guide gap).
+ * A result set holds records of ONE size, calitas_hitset_stride(): 32 bytes (calitas_hit, up to 48 alignment columns) when no guide of the
+ * call can produce a longer alignment, else 64 bytes (calitas_hit_wide: the same 20-byte header, up to 176 columns).  Record i starts at
+ * (const char*)calitas_hitset_data(h) + i * stride; the accessors below work on either form. */
+#define CALITAS_HIT_WORDS       8    /* 32-bit words of a calitas_hit */
+#define CALITAS_HIT_WIDE_WORDS 16    /* 32-bit words of a calitas_hit_wide */
+#define CALITAS_HIT_HEADER_WORDS 5
 typedef struct calitas_hit {
-  int32_t guide_idx;          /* index into the guides array of the call */
-  int32_t pam_idx;            /* index into that guide's PAM list (primary = 0); -1 for a PAM-less guide */
-  int32_t contig_idx;         /* contig of the loaded reference; -1 for calitas_align_targets */
-  int32_t task_idx;           /* window index (search) or task index (align_regions / align_targets) */
-  int32_t start_offset;       /* guide+PAM span */
-  int32_t end_offset;
-  int32_t guide_start_offset; /* protospacer-only span: coordinate_start / coordinate_end of ReferenceHit.scala:223-224 */
-  int32_t guide_end_offset;
-  int32_t score;
-  uint8_t strand;             /* '+' or '-' */
-  uint8_t n_ops;
-  uint8_t gap_bases;          /* GuideAlignment.gapBases */
-  uint8_t edits;              /* GuideAlignment.edits */
-  uint32_t ops[CALITAS_MAX_OPS / 16];
+  int32_t  start_offset;      /* guide+PAM span [start_offset, end_offset) */
+  int32_t  task_idx;          /* window index (search) or task index (align_regions / align_targets) */
+  int32_t  score;
+  uint32_t where;             /* bits 0-12 guide_idx (index into the guides array of the call); bits 13-30 contig_idx + 1 (0: none, calitas_align_targets); bit 31 strand ('-' = 1) */
+  uint32_t shape;             /* bits 0-7 n_ops; 8-15 end_offset - start_offset; 16-21 guide_start_offset - start_offset; 22-27 end_offset - guide_end_offset; 28-31 pam_idx + 1 */
+  uint32_t ops[CALITAS_HIT_WORDS - CALITAS_HIT_HEADER_WORDS];
 } calitas_hit;
+typedef struct calitas_hit_wide {
+  int32_t start_offset, task_idx, score; uint32_t where, shape;
+  uint32_t ops[CALITAS_HIT_WIDE_WORDS - CALITAS_HIT_HEADER_WORDS];
+} calitas_hit_wide;
+static inline int32_t calitas_hit_guide_idx(const calitas_hit* h) { return (int32_t)(h->where & 0x1FFFu); }
+static inline int32_t calitas_hit_contig_idx(const calitas_hit* h) { return (int32_t)((h->where >> 13) & 0x3FFFFu) - 1; }
+static inline char    calitas_hit_strand(const calitas_hit* h) { return (h->where >> 31) ? '-' : '+'; }
+static inline int32_t calitas_hit_n_ops(const calitas_hit* h) { return (int32_t)(h->shape & 0xFFu); }
+static inline int32_t calitas_hit_end_offset(const calitas_hit* h) { return h->start_offset + (int32_t)((h->shape >> 8) & 0xFFu); }
+/* protospacer-only span: coordinate_start / coordinate_end of ReferenceHit.scala:223-224 */
+static inline int32_t calitas_hit_guide_start_offset(const calitas_hit* h) { return h->start_offset + (int32_t)((h->shape >> 16) & 0x3Fu); }
+static inline int32_t calitas_hit_guide_end_offset(const calitas_hit* h) { return calitas_hit_end_offset(h) - (int32_t)((h->shape >> 22) & 0x3Fu); }
+/* index into that guide's PAM list (primary = 0); -1 for a PAM-less guide */
+static inline int32_t calitas_hit_pam_idx(const calitas_hit* h) { return (int32_t)(h->shape >> 28) - 1; }
+static inline uint32_t calitas_hit_op(const calitas_hit* h, int32_t k) { return (h->ops[k >> 4] >> ((k & 15) * 2)) & 3u; }
+/* GuideAlignment.gapBases (columns with op I or D) and GuideAlignment.edits (columns with op != '=') */
+static inline int32_t calitas_hit_gap_bases(const calitas_hit* h) { int32_t n = calitas_hit_n_ops(h), c = 0, k; for (k = 0; k < n; ++k) c += calitas_hit_op(h, k) >= 2u; return c; }
+static inline int32_t calitas_hit_edits(const calitas_hit* h) { int32_t n = calitas_hit_n_ops(h), c = 0, k; for (k = 0; k < n; ++k) c += calitas_hit_op(h, k) != 0u; return c; }
 
 /* ---- engine ------------------------------------------------------------------------------------------- */
 /* Replaces `new SequentialGuideAligner(costs)` (SearchReference.scala:486-491, AlignToReference.scala:64-70). */
@@ -131,7 +148,8 @@ int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_gui
  * Hits are ordered as the reference would emit them: search with dedup: ReferenceHit.sort order per guide;
  * otherwise by (guide, window/task, '+' before '-', rank in the per-window retval of SequentialGuideAligner.scala:315-322). */
 int64_t calitas_hitset_count(const calitas_hitset* h);
-const calitas_hit* calitas_hitset_data(const calitas_hitset* h);   /* pinned host memory, valid until free */
+const calitas_hit* calitas_hitset_data(const calitas_hitset* h);   /* pinned host memory, valid until free; records are calitas_hitset_stride() bytes apart */
+int32_t calitas_hitset_stride(const calitas_hitset* h);            /* 32 (calitas_hit) or 64 (calitas_hit_wide) */
 void calitas_hitset_free(calitas_hitset* h);
 /* Timings of the call that produced the set, milliseconds between CUDA events recorded on the stream each piece runs on:
  *   ms[0] whole call on the device, first launch to the last byte of the final D2H;
@@ -152,7 +170,7 @@ int calitas_microbench_int(calitas_engine* e, int32_t kind, double* tera_ops_per
  * point at base 0 of contig c (NULL allowed for contigs without hits); for align_targets pass the task bases through
  * `target_bases[task]` instead.  upper_case != 0 upper-cases target bases (SearchReference windows, SearchReference.scala:67).
  * *out_text is malloc'd; release with calitas_free_text. */
-int calitas_render_alignments(const calitas_hit* hits, int64_t n_hits, int32_t n_guides, const calitas_guide* guides,
+int calitas_render_alignments(const void* hits, int64_t n_hits, int32_t stride, int32_t n_guides, const calitas_guide* guides,
                               int32_t n_contigs, const char* const* names, const uint8_t* const* contig_bases,
                               const calitas_target_task* targets, int32_t upper_case, char** out_text);
 void calitas_free_text(char* text);

@@ -26,13 +26,38 @@ def test_jni_shim_compiles_and_matches_native_scala(tmp_path):
 
 def test_hit_decoder_offsets_match_the_struct():
     from calitas_b200 import _capi
-    H = _capi.Hit
-    assert C.sizeof(H) == 72
+    H, W = _capi.Hit, _capi.HitWide
+    assert C.sizeof(H) == 32 and C.sizeof(W) == 64
     scala = open(os.path.join(B, "scala", "com", "editasmedicine", "aligner", "b200", "HitDecoder.scala")).read()
-    assert "RecordBytes = 72" in scala
-    want = {"guide_idx": 0, "pam_idx": 4, "contig_idx": 8, "task_idx": 12, "start_offset": 16, "end_offset": 20, "guide_start_offset": 24,
-            "guide_end_offset": 28, "score": 32, "strand": 36, "n_ops": 37, "gap_bases": 38, "edits": 39, "ops": 40}
+    assert "HeaderBytes = 20" in scala
+    want = {"start_offset": 0, "task_idx": 4, "score": 8, "where": 12, "shape": 16, "ops": 20}
     for name, off in want.items():
-        assert getattr(H, name).offset == off, name
-    for off in (4, 8, 12, 16, 20, 24, 28, 32, 36, 37):
+        assert getattr(H, name).offset == off and getattr(W, name).offset == off, name
+    for off in (4, 8, 12, 16):
         assert ("o + %d" % off) in scala
+    header = open(os.path.join(ROOT, "include", "calitas_b200.h")).read()
+    # the bit fields the Scala decoder unpacks are the header's
+    for sc, hd in (("where & 0x1FFF", "h->where & 0x1FFFu"), ("(where >>> 13) & 0x3FFFF", "(h->where >> 13) & 0x3FFFFu"), ("(where >>> 31)", "(h->where >> 31)"),
+                   ("shape & 0xFF", "h->shape & 0xFFu"), ("(shape >>> 8) & 0xFF", "(h->shape >> 8) & 0xFFu"), ("(shape >>> 16) & 0x3F", "(h->shape >> 16) & 0x3Fu"),
+                   ("(shape >>> 22) & 0x3F", "(h->shape >> 22) & 0x3Fu"), ("(shape >>> 28) - 1", "(h->shape >> 28) - 1")):
+        assert sc in scala and hd in header, (sc, hd)
+
+
+def test_decode_encode_round_trip():
+    import numpy as np
+    from calitas_b200 import _capi
+    rng = np.random.default_rng(5)
+    n = 200
+    w = np.zeros((n, 16), dtype=np.uint32)
+    w[:, 0] = rng.integers(0, 1 << 30, n); w[:, 1] = rng.integers(0, 1 << 30, n); w[:, 2] = rng.integers(-5000, 5000, n).astype(np.int32).view(np.uint32)
+    w[:, 3] = rng.integers(0, 8192, n) | (rng.integers(0, 1 << 18, n) << 13) | (rng.integers(0, 2, n) << 31)
+    nops = rng.integers(1, 129, n)
+    w[:, 4] = nops | (rng.integers(0, 129, n) << 8) | (rng.integers(0, 64, n) << 16) | (rng.integers(0, 64, n) << 22) | (rng.integers(0, 10, n) << 28)
+    for i in range(n):
+        for k in range(int(nops[i])):
+            w[i, 5 + (k >> 4)] |= np.uint32(int(rng.integers(0, 4)) << ((k & 15) * 2))
+    rec = _capi.decode_hits(w)
+    assert np.array_equal(_capi.encode_hits(rec), w)
+    for i in (0, 7, 100):
+        ops = [(int(w[i, 5 + (k >> 4)]) >> ((k & 15) * 2)) & 3 for k in range(int(nops[i]))]
+        assert rec["gap_bases"][i] == sum(o >= 2 for o in ops) and rec["edits"][i] == sum(o != 0 for o in ops)

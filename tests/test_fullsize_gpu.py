@@ -107,8 +107,8 @@ def test_dedup_output_is_a_subset_of_the_raw_output(world):
     def keyset(a):
         v = a.copy()
         v["task_idx"] = 0                                  # the same locus found from two overlapping windows differs only in the window id
-        b = v.tobytes()
-        return {b[i:i + 72] for i in range(0, len(b), 72)}
+        b, sz = v.tobytes(), v.dtype.itemsize
+        return {b[i:i + sz] for i in range(0, len(b), sz)}
     ks_raw, ks_ded = keyset(raw), keyset(ded)
     assert ks_ded <= ks_raw
 
