@@ -467,7 +467,7 @@ CAL_HD void make_hit(const GuideSpec& g, const GuideAln& a, int pam_idx, int32_t
 // ---- per-window canonicalisation (SequentialGuideAligner.scala:315-322) ---------------------------------------------------
 // `hits[0..n)` are the alignments of one (guide, window, strand) in emission order (end column, then PAM index); `valid[i]` marks
 // filled slots.  On return rank[i] >= 0 is the position of a kept alignment in the reference's retval for this strand, -1 = dropped.
-CAL_HD int canon_group(const uint32_t* recs, int rw, const uint8_t* valid, int32_t* rank, int n, int32_t max_total_diffs, int32_t max_overlap) {
+CAL_HD int canon_group_generic(const uint32_t* recs, int rw, const uint8_t* valid, int32_t* rank, int n, int32_t max_total_diffs, int32_t max_overlap) {
   // rank doubles as state: -2 = not yet visited, -1 = dropped, >= 0 kept
   for (int i = 0; i < n; ++i) rank[i] = valid[i] ? -2 : -1;
   int kept = 0;
@@ -496,6 +496,38 @@ CAL_HD int canon_group(const uint32_t* recs, int rw, const uint8_t* valid, int32
     }
     rank[b] = keep ? kept++ : -1;
   }
+  return kept;
+}
+// The same for the group sizes the genome search produces (one or a few adjacent end columns x PAMs): every record is read once, the
+// selection runs on registers / thread-local words.  A single alignment (the usual case at the default limits) is one comparison.
+CAL_HD int canon_group(const uint32_t* recs, int rw, const uint8_t* valid, int32_t* rank, int n, int32_t max_total_diffs, int32_t max_overlap) {
+  constexpr int SMALL = 12;
+  if (n == 1) { const bool keep = valid[0] && rec_edits(recs, rw) <= max_total_diffs; rank[0] = keep ? 0 : -1; return keep ? 1 : 0; }
+  if (n > SMALL) return canon_group_generic(recs, rw, valid, rank, n, max_total_diffs, max_overlap);
+  int32_t start[SMALL], end[SMALL], state[SMALL]; int64_t order[SMALL];      // order key: larger = earlier in the stable (score desc, gapBases asc, arrival) order
+  uint32_t too_many = 0;                                                       // bit i: edits > max_total_diffs
+  for (int i = 0; i < n; ++i) {
+    const uint32_t* r = recs + (int64_t)i * rw;
+    if (!valid[i]) { state[i] = -1; order[i] = 0; start[i] = 0; end[i] = 0; continue; }
+    state[i] = -2; start[i] = rec_start(r); end[i] = rec_end(r);
+    order[i] = ((int64_t)rec_score(r) << 16) | (int64_t)((255 - rec_gap_bases(r, rw)) << 8) | (int64_t)(255 - i);
+    if (rec_edits(r, rw) > max_total_diffs) too_many |= 1u << i;
+  }
+  int kept = 0;
+  for (;;) {
+    int b = -1;
+    for (int i = 0; i < n; ++i) if (state[i] == -2 && (b < 0 || order[i] > order[b])) b = i;
+    if (b < 0) break;
+    bool keep = !((too_many >> b) & 1u);
+    for (int i = 0; i < n && keep; ++i) {
+      if (state[i] < 0) continue;
+      const int32_t lo = start[i] > start[b] ? start[i] : start[b], hi = end[i] < end[b] ? end[i] : end[b];
+      int32_t ov = hi - lo; if (ov < 0) ov = 0;
+      if (ov > max_overlap) keep = false;
+    }
+    state[b] = keep ? kept++ : -1;
+  }
+  for (int i = 0; i < n; ++i) rank[i] = state[i];
   return kept;
 }
 

@@ -311,6 +311,7 @@ struct AlignArgs {
   const ContigDev* contigs; int32_t n_contigs; int32_t window_size, step;     // tiled
   const ExplicitWindow* windows; int32_t task_base;                          // explicit (window ids are relative to task_base)
   uint32_t* recs; int32_t rw; uint8_t* valid; KeyLayout key;     // packed hit records, rw words each (cal_core.cuh)
+  int64_t nib_last_word;                                        // last valid word of `nib` (align_fast clamps its nine loads to it)
 };
 struct NibFetch {
   const uint32_t* nib; int64_t first; int32_t m; int dir;
@@ -384,6 +385,188 @@ CAL_D void align_body(const AlignArgs& a) {
   }
   post_alignment(a, x, g, fetch, aln, i);
 }
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// align_fast: the hot-path form of align_body<KB> for the common shapes (lp + KB + g + longest PAM <= 64 columns).  Same cells, scores,
+// tie-breaks and traceback as band_align_k (tagged scores, see cal_core.cuh), same extension rule as extend_pam, same record as make_hit —
+// but nothing goes through byte arrays in local memory:
+//   * the 64 target codes the candidate can touch (band + PAM extension) are loaded once as nine 32-bit words and kept in registers; the reverse
+//     strand costs one BREV per word (reversing the bits of a word reverses the order of its 4-bit codes AND complements each code: A=1 <-> T=8,
+//     C=2 <-> G=4) instead of a complement per fetched base; per DP row the 256-bit window slides by one code (eight funnel shifts);
+//   * the traceback shifts each 2-bit op straight into a 128-bit register pair (first column ends up in the low bits = guide orientation for a
+//     3' PAM; a 5' PAM reverses the fields at the end), counts and the terminal gap run are taken on the way;
+//   * the extension appends the guide-PAM gap and the PAM ops with shifts, and the record leaves as two (four) 16-byte stores.
+// Codes outside the window never matter: columns < 1 only feed cells whose predecessors are unreachable, columns > j are never on a path to
+// the end cell, and the extension checks t_off + pam_len <= m before it looks at a base.
+// ------------------------------------------------------------------------------------------------------------------------------------
+CAL_D uint32_t brev32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __brev(v);
+#else
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1); v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2); v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+  return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
+#endif
+}
+CAL_D uint64_t rev_fields2(uint64_t v) {     // reverses the order of the 32 two-bit fields of v
+  const uint32_t lo = brev32((uint32_t)v), hi = brev32((uint32_t)(v >> 32));
+  const uint64_t r = ((uint64_t)lo << 32) | hi;                                        // all 64 bits reversed
+  return ((r & 0x5555555555555555ull) << 1) | ((r >> 1) & 0x5555555555555555ull);      // put the two bits of each field back in order
+}
+struct Ops128 { uint64_t lo, hi; };
+CAL_D Ops128 shl128(Ops128 v, int s) {        // 0 <= s < 128
+  if (s == 0) return v;
+  if (s >= 64) return Ops128{ 0ull, v.lo << (s - 64) };
+  return Ops128{ v.lo << s, (v.hi << s) | (v.lo >> (64 - s)) };
+}
+CAL_D Ops128 shr128(Ops128 v, int s) {
+  if (s == 0) return v;
+  if (s >= 64) return Ops128{ v.hi >> (s - 64), 0ull };
+  return Ops128{ (v.lo >> s) | (v.hi << (64 - s)), v.hi >> s };
+}
+CAL_D uint32_t spread_bits16(uint32_t v) {    // bit i of v -> bit 2 i
+  v &= 0xFFFFu; v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu; v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+template <int KB>
+CAL_D void align_fast(const AlignArgs& a) {
+  constexpr int B = 2 * KB + 1;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_cand) return;
+  const uint64_t key = a.cand[i];
+  const int32_t j = key_col(a.key, key);
+  const CandCtx x = decode_candidate(a, key);
+  const GuideSpec& g = a.specs[x.gidx];
+  for (int s = 0; s < a.slots; ++s) a.valid[i * a.slots + s] = 0;
+  const int n = g.lp;
+  const int base = j - n - KB;                       // cell (i, t) is target column c = i + base + t; the register window starts at column base + 1
+  // ---- the 64 codes from column base + 1 on, in scan order -----------------------------------------------------------------------------
+  uint32_t A[8];
+  {
+    const int64_t q_lo = x.dir == 0 ? x.first + base : x.first + x.m - (base + 1) - 63;       // lowest nibble index of the stretch
+    const int64_t w0 = q_lo >> 3; const int sh = (int)(q_lo & 7) * 4;
+    uint32_t W[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { int64_t w = w0 + k; w = w < 0 ? 0 : (w > a.nib_last_word ? a.nib_last_word : w); W[k] = __ldg(a.nib + w); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const uint32_t v = shift_in_low_bits(W[k], W[k + 1], sh); if (x.dir == 0) A[k] = v; else A[7 - k] = brev32(v); }
+  }
+  // ---- DP fill: band_align_k's recurrence with the codes taken from the sliding window --------------------------------------------------
+  const Scores& sc = a.sc;
+  const int32_t NEG4 = 4 * NEG_SCORE;
+  int32_t d[B], l[B], u[B];
+  uint32_t trd[CALITAS_MAX_PROTOSPACER + 1], tru[CALITAS_MAX_PROTOSPACER + 1], trl[CALITAS_MAX_PROTOSPACER + 1], trm[CALITAS_MAX_PROTOSPACER + 1];
+#pragma unroll
+  for (int t = 0; t < B; ++t) { const int c = base + t; const int32_t v = (c >= 0 && c <= j) ? 0 : NEG4; d[t] = v + TG_DIAG; l[t] = v + TG_LEFT; u[t] = v + TG_UP; }
+  const int32_t gI4 = 4 * sc.target_gap, gD4 = 4 * sc.query_gap, mis4 = 4 * sc.mismatch, dmatch4 = 4 * (sc.match - sc.mismatch);
+  for (int r = 1; r <= n; ++r) {
+    const uint32_t qm = g.qmask[r - 1];
+    const uint64_t win = (uint64_t)A[0] | ((uint64_t)A[1] << 32);        // codes of columns r + base .. : diagonal t of this row is code t
+    uint32_t wd = 0, wu = 0, wl = 0, wm = 0;
+    int32_t left_d = NEG4 + TG_DIAG, left_l = NEG4 + TG_LEFT, left_u = NEG4 + TG_UP;
+#pragma unroll
+    for (int t = 0; t < B; ++t) {
+      const uint32_t code = (uint32_t)(win >> (4 * t)) & 15u;
+      const uint32_t mt = (qm >> code) & 1u;
+      const int32_t add4 = mis4 + (int32_t)mt * dmatch4;
+      const int32_t md = max3_s32(d[t], l[t], u[t]);
+      const int32_t mu = t + 1 < B ? (d[t + 1] > u[t + 1] ? d[t + 1] : u[t + 1]) : NEG4 + TG_DIAG;
+      const int32_t ml = max3_s32(left_d, left_l, left_u);
+      const int32_t nd = (md | 3) + add4, nu = ((mu & ~3) | TG_UP) + gI4, nl = ((ml & ~3) | TG_LEFT) + gD4;
+      wd = shift_in_low_bits(wd, (uint32_t)md, 2); wu = shift_in_low_bits(wu, (uint32_t)mu, 2); wl = shift_in_low_bits(wl, (uint32_t)ml, 2); wm = shift_in_low_bits(wm, mt, 1);
+      d[t] = nd; u[t] = nu; l[t] = nl; left_d = nd; left_l = nl; left_u = nu;
+    }
+    trd[r] = wd; tru[r] = wu; trl[r] = wl; trm[r] = wm;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) A[k] = shift_in_low_bits(A[k], A[k + 1], 4);   // slide the window one column to the right
+    A[7] >>= 4;
+  }
+  const int32_t mbest = max3_s32(d[KB], l[KB], u[KB]);
+  const int32_t best = mbest >> 2;
+  if (best < g.min_score) return;
+  // ---- traceback: ops shifted into a register pair, first alignment column in the low bits ------------------------------------------------
+  Ops128 ops{ 0ull, 0ull };
+  int ci = n, ct = KB, cdir = mbest & 3, n_g = 0, term = 0, term_op = 0;
+  while (ci > 0) {
+    const int shb = 32 - 2 * B + 2 * ct;
+    const int next = (int)(((cdir == TG_DIAG ? trd[ci] : (cdir == TG_UP ? tru[ci] : trl[ci])) >> shb) & 3u);
+    uint32_t op;
+    if (cdir == TG_DIAG) { op = ((trm[ci] >> (32 - B + ct)) & 1u) ? OP_EQ : OP_X; --ci; }
+    else if (cdir == TG_LEFT) { op = OP_D; --ct; }
+    else { op = OP_I; --ci; ++ct; }
+    if (ct < 0 || ct >= B) return;                       // cannot happen for an accepted end cell; keeps indexing safe
+    if (n_g == term && op >= OP_I && (term == 0 || (int)op == term_op)) { ++term; term_op = (int)op; }     // trailing run of one gap kind (:452)
+    ops.hi = (ops.hi << 2) | (ops.lo >> 62); ops.lo = (ops.lo << 2) | op;
+    ++n_g;
+    cdir = next;
+  }
+  const int diffs = popc32((uint32_t)((ops.lo | (ops.lo >> 1)) & 0x55555555u)) + popc32((uint32_t)(((ops.lo | (ops.lo >> 1)) >> 32) & 0x55555555u)) +
+                    popc32((uint32_t)((ops.hi | (ops.hi >> 1)) & 0x55555555u)) + popc32((uint32_t)(((ops.hi | (ops.hi >> 1)) >> 32) & 0x55555555u));
+  if (diffs > g.d) return;                               // SequentialGuideAligner.scala:447,450
+  const int t_start = base + ct + 1;                     // 1-based first target column
+  const int terminal_d = term_op == OP_D ? term : 0;
+  // after n slides code k of the window is column j - KB + 1 + k: the base right of the alignment (column j + 1) is code KB
+  const uint64_t e0 = (uint64_t)A[0] | ((uint64_t)A[1] << 32), e1 = (uint64_t)A[2] | ((uint64_t)A[3] << 32);
+  const int64_t slot0 = i * a.slots;
+  const int n_pams = g.n_pams;
+  for (int pi = 0; pi < (n_pams > 0 ? n_pams : 1); ++pi) {
+    int32_t score = best, offset = 0; uint32_t xmask = 0; int pam_len = 0;
+    if (n_pams > 0) {                                    // extend_pam (SequentialGuideAligner.scala:433-492)
+      pam_len = g.pam_len[pi];
+      int max_extra = g.g - term; const int alt = g.max_tot_filter - diffs; if (alt < max_extra) max_extra = alt;
+      bool have = false;
+      for (int off = 0; off <= max_extra; ++off) {
+        int limit = g.p; const int l2 = g.max_tot_filter - diffs - off; if (l2 < limit) limit = l2;
+        if (j + off + pam_len > x.m || limit < 0) continue;
+        int32_t ps = 0; int nx = 0; uint32_t xm = 0;
+        for (int q = 0; q < pam_len; ++q) {
+          const int idx = KB + off + q;
+          const uint32_t code = (uint32_t)((idx < 16 ? e0 >> (4 * idx) : e1 >> (4 * (idx - 16))) & 15u);
+          const bool pr = pairs(g.pam[pi][q], code);
+          ps += pr ? sc.pam_match : sc.pam_mismatch;
+          if (!((pr ? sc.pam_match : sc.pam_mismatch) > 0)) { ++nx; xm |= 1u << q; }                // op '=' iff addend > 0 (:468)
+        }
+        if (nx > limit) continue;
+        const int32_t total = best + ps + off * sc.query_gap;
+        if (!have || total > score) { have = true; score = total; offset = off; xmask = xm; }      // maxBy keeps the first maximum
+      }
+      if (!have) continue;
+    }
+    const int tail = n_pams > 0 ? offset + pam_len : 0;
+    const int n_ops = n_g + tail;
+    Ops128 all = ops;
+    if (tail) {
+      Ops128 ext = shl128(Ops128{ (uint64_t)spread_bits16(xmask), 0ull }, 2 * offset);       // the PAM columns (X = 1, '=' = 0) ...
+      ext.lo |= offset ? ((1ull << (2 * offset)) - 1) : 0ull;                                 // ... behind offset x D (3): the guide-PAM gap (offset <= 26)
+      ext = shl128(ext, 2 * n_g);
+      all.lo |= ext.lo; all.hi |= ext.hi;
+    }
+    if (g.five_prime) {                                  // Cigar.reverse (:267,284): reverse the n_ops fields
+      Ops128 r{ rev_fields2(all.hi), rev_fields2(all.lo) };
+      all = shr128(r, 2 * (64 - n_ops));
+    }
+    const int32_t s0 = t_start - 1, e0c = j + tail, trail_dp = terminal_d + tail;
+    int32_t start; int lead, trail;
+    if (x.dir == 0) { start = x.geom.w_begin + s0; lead = 0; trail = trail_dp; }
+    else { start = x.geom.w_end - e0c; lead = trail_dp; trail = 0; }                               // flip about the window (:271-274, 305-308)
+    uint32_t* rec = a.recs + (slot0 + pi) * a.rw;
+    const uint32_t where = rec_make_where(x.gidx, x.contig_idx, (x.dir ^ g.five_prime) != 0);
+    const uint32_t shape = rec_make_shape(n_ops, e0c - s0, lead, trail, n_pams > 0 ? pi : -1);
+#ifndef CAL_HOSTSIM
+    uint4* r4 = reinterpret_cast<uint4*>(rec);
+    r4[0] = make_uint4((uint32_t)start, (uint32_t)((int32_t)x.wid + a.task_base), (uint32_t)score, where);
+    r4[1] = make_uint4(shape, (uint32_t)all.lo, (uint32_t)(all.lo >> 32), (uint32_t)all.hi);
+    if (a.rw > CALITAS_HIT_WORDS) { r4[2] = make_uint4((uint32_t)(all.hi >> 32), 0u, 0u, 0u); r4[3] = make_uint4(0u, 0u, 0u, 0u); }
+#else
+    rec[0] = (uint32_t)start; rec[1] = (uint32_t)((int32_t)x.wid + a.task_base); rec[2] = (uint32_t)score; rec[3] = where; rec[4] = shape;
+    rec[5] = (uint32_t)all.lo; rec[6] = (uint32_t)(all.lo >> 32); rec[7] = (uint32_t)all.hi;
+    if (a.rw > CALITAS_HIT_WORDS) { rec[8] = (uint32_t)(all.hi >> 32); for (int k = 9; k < a.rw; ++k) rec[k] = 0u; }
+#endif
+    a.valid[slot0 + pi] = x.owned;
+  }
+}
+CAL_KERNEL __launch_bounds__(128) k_align_fast6(AlignArgs a) { align_fast<6>(a); }
+CAL_KERNEL __launch_bounds__(128) k_align_fast5(AlignArgs a) { align_fast<5>(a); }
+CAL_KERNEL __launch_bounds__(128) k_align_fast4(AlignArgs a) { align_fast<4>(a); }
 
 // Wide thresholds on short explicit windows (alignBest / alignToRefBest: every end column is a candidate): one thread per (window, strand)
 // group of consecutive sorted candidates fills the DP once and traces every candidate column (band_align_group).
@@ -782,8 +965,16 @@ struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> alig
   const GuideSpec* d_specs; int slots; bool explicit_mode; int banded;   // banded: 0 = wide thresholds, else the largest k_edits of the launch (<= ALIGN_KB)
   const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base; bool drop_halo;
   KeyLayout key; int rw;                                                   // rw: 32-bit words per hit record of this call
+  bool fast; int64_t nib_words;                                            // fast: every guide of the launch fits align_fast's 64-column window; nib_words: size of `nib`
   const DedupLayout* dedup; int32_t max_overlap;                           // dedup != nullptr: removeOverlaps + ReferenceHit.sort over the kept alignments
 };
+
+// align_fast<KB> keeps 64 target codes per candidate in registers: band + guide-PAM gap + longest PAM must fit, and the extension indexes 32 of them
+bool fits_align_fast(const GuideSpec& sp, int banded) {
+  const int kb = banded > 5 ? 6 : (banded == 5 ? 5 : 4);
+  int pam = 0; for (int k = 0; k < sp.n_pams; ++k) pam = std::max<int>(pam, sp.pam_len[k]);
+  return !std::getenv("CALITAS_NO_ALIGN_FAST") && sp.lp + kb + sp.g + pam <= 64 && kb + sp.g + pam <= 32;
+}
 
 // e->out must hold (out_n + more) records; the first out_n are kept
 void ensure_out(calitas_engine* e, int rw, int64_t out_n, int64_t more, size_t projected_total) {
@@ -809,9 +1000,14 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
   AlignArgs aa; std::memset(&aa, 0, sizeof aa);
   aa.cand = e->cand_sorted.as<uint64_t>(); aa.n_cand = n_cand; aa.specs = P.d_specs; aa.sc = e->sc; aa.slots = P.slots; aa.explicit_mode = P.explicit_mode ? 1 : 0;
   aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows; aa.task_base = P.task_base;
-  aa.recs = e->hits.as<uint32_t>(); aa.rw = rw; aa.valid = e->valid.as<uint8_t>(); aa.key = P.key;
+  aa.recs = e->hits.as<uint32_t>(); aa.rw = rw; aa.valid = e->valid.as<uint8_t>(); aa.key = P.key; aa.nib_last_word = P.nib_words - 1;
   dev::event_record(P.ev_align_b, s);
-  if (P.banded > 5) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
+  if (P.banded > 0 && P.fast) {
+    if (P.banded > 5) { CAL_LAUNCH(k_align_fast6, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_fast6"); }
+    else if (P.banded == 5) { CAL_LAUNCH(k_align_fast5, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_fast5"); }
+    else { CAL_LAUNCH(k_align_fast4, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_fast4"); }
+  }
+  else if (P.banded > 5) { CAL_LAUNCH(k_align, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align"); }
   else if (P.banded == 5) { CAL_LAUNCH(k_align5, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align5"); }
   else if (P.banded > 0) { CAL_LAUNCH(k_align4, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align4"); }
   else if (P.explicit_mode) {             // short windows, nearly every column a candidate: one DP fill per (window, strand)
@@ -919,13 +1115,14 @@ std::vector<GuideSpec> build_specs(calitas_engine* e, int32_t n_guides, const ca
 }
 
 // explicit-window path shared by align_regions / align_targets
-calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std::vector<ExplicitWindow>& windows, const std::vector<GuideSpec>& specs) {
+calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, const std::vector<ExplicitWindow>& windows, const std::vector<GuideSpec>& specs) {
   dev::Stream s = e->stream; dev::set_device(e->device);
   e->launches = 0;
   dev::event_record(e->ev[0], s);
   int slots = 1, banded = 1, max_cols = 1; for (auto& sp : specs) { slots = std::max(slots, sp.slots); banded = std::max(banded, std::max(sp.k_edits, sp.band_k)); max_cols = std::max(max_cols, sp.max_cols); }
   const int rw = rec_words_for(max_cols);
   if (banded > ALIGN_KB) banded = 0;
+  bool fast = banded > 0; for (auto& sp : specs) fast = fast && fits_align_fast(sp, banded);
   e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
   e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
   double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { (int64_t)windows.size(), 0, 0, 0, 0, 0, 0, 0 };
@@ -954,7 +1151,7 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, const std
     ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
     counts[1] += (int64_t)n_cand;
     // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
-    Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true, key, rw, nullptr, 0 };
+    Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true, key, rw, fast, nib_words, nullptr, 0 };
     int64_t n_aln = 0;
     const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_out, 0, n_aln);
     if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
@@ -1096,7 +1293,7 @@ void calitas_reference_free(calitas_engine* e, calitas_reference* r) {
 }
 
 // One guide chunk of a search: consecutive guides sharing the raw guide length, hence the window tiling (SearchReference.scala:528-530).
-struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; KeyLayout key; DedupLayout dedup; };
+struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded; bool fast; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; KeyLayout key; DedupLayout dedup; };
 
 int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
                    int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out) {
@@ -1132,6 +1329,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
       ch.n_tiles = t_end - ch.t_begin;
       ch.slots = 1; ch.banded = 1; for (int g = g0; g < g1; ++g) { ch.slots = std::max(ch.slots, specs[(size_t)g].slots); ch.banded = std::max(ch.banded, std::max(specs[(size_t)g].k_edits, specs[(size_t)g].band_k)); }
       if (ch.banded > ALIGN_KB) ch.banded = 0;
+      ch.fast = ch.banded > 0; for (int g = g0; g < g1; ++g) ch.fast = ch.fast && fits_align_fast(specs[(size_t)g], ch.banded);
       const int ng = g1 - g0;
       ch.smem = scan_smem_bytes(ng, ch.ts->tile_windows, window_size, ch.step);
       if (ch.smem > (size_t)SCAN_SMEM_LIMIT) throw LimitExceeded("window size too large for the shared-memory tile");
@@ -1217,7 +1415,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         counts[1] += (int64_t)n_cand;
         dev::event_record(ce.ev[CE_TAIL_B], s);
         Pipeline P{ e, cand_slot[slot]->as<uint64_t>(), ce.ev[CE_SORTED], ce.ev[CE_ALIGN_B], ce.ev[CE_ALIGN_E], e->specs.as<GuideSpec>(), ch.slots, false, ch.banded,
-                    ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, 0, dedup == 0, ch.key, rw, dedup ? &ch.dedup : nullptr, limits->max_overlap };
+                    ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, 0, dedup == 0, ch.key, rw, ch.fast, ref->total_padded / 8, dedup ? &ch.dedup : nullptr, limits->max_overlap };
         int64_t n_aln = 0;
         // room in e->out: what this chunk adds, and (when it has to grow) the rest of the call projected from the hits per guide so far
         const size_t projected = ch.g0 > 0 ? (size_t)((double)n_out * (double)n_guides / (double)ch.g0 * 1.15) + 4096 : e->out_hits_hint;
@@ -1298,7 +1496,7 @@ int calitas_align_regions(calitas_engine* e, const calitas_reference* ref, int32
       if (t.start < ref->have_b[c] || t.start + t.length > ref->have_e[c]) throw InvalidArgument("region outside the loaded bases of contig " + ref->names[c]);
       windows[(size_t)i] = ExplicitWindow{ ref->nib_off[c] - ref->have_b[c] + t.start, t.length, (int32_t)t.start, t.guide_idx, t.contig_idx };
     }
-    *out = run_explicit(e, ref->d_nib, windows, specs);
+    *out = run_explicit(e, ref->d_nib, ref->total_padded / 8, windows, specs);
     return CALITAS_OK;
   });
 }
@@ -1327,7 +1525,7 @@ int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_gui
       for (int32_t k = 0; k < t.length; ++k) words[(size_t)((b + k) >> 3)] |= target_code(t.bases[k]) << (((b + k) & 7) * 4);
     }
     e->nib_tmp.ensure(words.size() * 4); dev::h2d(e->nib_tmp.p, words.data(), words.size() * 4, e->stream); dev::stream_sync(e->stream);
-    *out = run_explicit(e, e->nib_tmp.as<uint32_t>(), windows, specs);
+    *out = run_explicit(e, e->nib_tmp.as<uint32_t>(), (int64_t)words.size(), windows, specs);
     return CALITAS_OK;
   });
 }
