@@ -465,69 +465,61 @@ CAL_HD void make_hit(const GuideSpec& g, const GuideAln& a, int pam_idx, int32_t
 }
 
 // ---- per-window canonicalisation (SequentialGuideAligner.scala:315-322) ---------------------------------------------------
-// `hits[0..n)` are the alignments of one (guide, window, strand) in emission order (end column, then PAM index); `valid[i]` marks
-// filled slots.  On return rank[i] >= 0 is the position of a kept alignment in the reference's retval for this strand, -1 = dropped.
-CAL_HD int canon_group_generic(const uint32_t* recs, int rw, const uint8_t* valid, int32_t* rank, int n, int32_t max_total_diffs, int32_t max_overlap) {
-  // rank doubles as state: -2 = not yet visited, -1 = dropped, >= 0 kept
-  for (int i = 0; i < n; ++i) rank[i] = valid[i] ? -2 : -1;
-  int kept = 0;
-  for (;;) {
-    int b = -1; int32_t bscore = 0, bgaps = 0;    // next in stable (score desc, gapBases asc) order
-    for (int i = 0; i < n; ++i) {
-      if (rank[i] != -2) continue;
-      const uint32_t* r = recs + (int64_t)i * rw; const int32_t sc = rec_score(r);
-      if (b >= 0 && sc < bscore) continue;
-      const int32_t gp = rec_gap_bases(r, rw);
-      if (b < 0 || sc > bscore || gp < bgaps) { b = i; bscore = sc; bgaps = gp; }
-    }
-    if (b < 0) break;
-    const uint32_t* rb = recs + (int64_t)b * rw;
-    bool keep = rec_edits(rb, rw) <= max_total_diffs;
-    if (keep) {
-      const int32_t bs = rec_start(rb), be = rec_end(rb);
-      for (int i = 0; i < n && keep; ++i) {
-        if (rank[i] < 0) continue;
-        const uint32_t* r = recs + (int64_t)i * rw;
-        int32_t lo = rec_start(r) > bs ? rec_start(r) : bs;
-        int32_t hi = rec_end(r) < be ? rec_end(r) : be;
-        int32_t ov = hi - lo; if (ov < 0) ov = 0;
-        if (ov > max_overlap) keep = false;
-      }
-    }
-    rank[b] = keep ? kept++ : -1;
-  }
-  return kept;
+// The alignments of one (guide, window, strand) in emission order (end column, then PAM index) are stably sorted by (score desc, gapBases asc)
+// and taken greedily: one is kept iff edits <= maxTotalDiffs and it overlaps no alignment kept before it by more than maxOverlap.
+// The align kernels leave a 16-byte canon key per alignment slot, so this step never touches the records.
+struct CKey { int32_t score, start, end; uint32_t w; };      // w = gap bases | edits << 8 | state << 16 (0: empty slot, 1: owned window, 2: halo window)
+CAL_HD CKey ckey_make(int32_t score, int32_t start, int32_t end, int gaps, int edits, int state) { return CKey{ score, start, end, (uint32_t)gaps | ((uint32_t)edits << 8) | ((uint32_t)state << 16) }; }
+CAL_HD int ck_gaps(const CKey& k) { return (int)(k.w & 255u); }
+CAL_HD int ck_edits(const CKey& k) { return (int)((k.w >> 8) & 255u); }
+CAL_HD int ck_state(const CKey& k) { return (int)(k.w >> 16); }
+CAL_HD bool ck_before(const CKey& a, int ia, const CKey& b, int ib) {      // a sorts before b in the stable (score desc, gapBases asc, arrival) order
+  if (a.score != b.score) return a.score > b.score;
+  if (ck_gaps(a) != ck_gaps(b)) return ck_gaps(a) < ck_gaps(b);
+  return ia < ib;
 }
-// The same for the group sizes the genome search produces (one or a few adjacent end columns x PAMs): every record is read once, the
-// selection runs on registers / thread-local words.  A single alignment (the usual case at the default limits) is one comparison.
-CAL_HD int canon_group(const uint32_t* recs, int rw, const uint8_t* valid, int32_t* rank, int n, int32_t max_total_diffs, int32_t max_overlap) {
-  constexpr int SMALL = 12;
-  if (n == 1) { const bool keep = valid[0] && rec_edits(recs, rw) <= max_total_diffs; rank[0] = keep ? 0 : -1; return keep ? 1 : 0; }
-  if (n > SMALL) return canon_group_generic(recs, rw, valid, rank, n, max_total_diffs, max_overlap);
-  int32_t start[SMALL], end[SMALL], state[SMALL]; int64_t order[SMALL];      // order key: larger = earlier in the stable (score desc, gapBases asc, arrival) order
-  uint32_t too_many = 0;                                                       // bit i: edits > max_total_diffs
+CAL_HD int32_t ck_overlap(const CKey& a, const CKey& b) {                  // GuideAlignment.overlap (GuideAlignment.scala:119-123), clamped at 0
+  const int32_t lo = a.start > b.start ? a.start : b.start, hi = a.end < b.end ? a.end : b.end;
+  const int32_t ov = hi - lo; return ov < 0 ? 0 : ov;
+}
+// Position of slot k in the kept list of its group keys[0..n), or -1 when it is dropped; n <= 32.  Every slot's thread can call this on its own:
+// the usual group is a few adjacent end columns of one site, where the best acceptable alignment is kept and everything else overlaps it, which
+// takes one pass over the keys; only a slot that clears the best one replays the greedy selection (state in two bit masks).
+CAL_HD int canon_slot_rank(const CKey* keys, int n, int k, int32_t max_total_diffs, int32_t max_overlap) {
+  const CKey me = keys[k];
+  if (ck_state(me) == 0 || ck_edits(me) > max_total_diffs) return -1;
+  int b = -1; CKey best = me;
   for (int i = 0; i < n; ++i) {
-    const uint32_t* r = recs + (int64_t)i * rw;
-    if (!valid[i]) { state[i] = -1; order[i] = 0; start[i] = 0; end[i] = 0; continue; }
-    state[i] = -2; start[i] = rec_start(r); end[i] = rec_end(r);
-    order[i] = ((int64_t)rec_score(r) << 16) | (int64_t)((255 - rec_gap_bases(r, rw)) << 8) | (int64_t)(255 - i);
-    if (rec_edits(r, rw) > max_total_diffs) too_many |= 1u << i;
+    const CKey c = keys[i];
+    if (ck_state(c) == 0 || ck_edits(c) > max_total_diffs) continue;
+    if (b < 0 || ck_before(c, i, best, b)) { b = i; best = c; }
   }
+  if (b == k) return 0;                                    // nothing acceptable sorts before it
+  if (ck_overlap(me, best) > max_overlap) return -1;       // the first kept alignment already rules it out
+  uint32_t decided = 0, kept = 0; int n_kept = 0;
+  for (int i = 0; i < n; ++i) { const CKey c = keys[i]; if (ck_state(c) == 0 || ck_edits(c) > max_total_diffs) decided |= 1u << i; }
+  for (;;) {
+    int p = -1; CKey pk = me;
+    for (int i = 0; i < n; ++i) { if ((decided >> i) & 1u) continue; const CKey c = keys[i]; if (p < 0 || ck_before(c, i, pk, p)) { p = i; pk = c; } }
+    if (p < 0) return -1;                                  // unreachable: slot k itself is undecided until it is picked
+    bool keep = true;
+    for (int i = 0; i < n && keep; ++i) if (((kept >> i) & 1u) && ck_overlap(keys[i], pk) > max_overlap) keep = false;
+    if (p == k) return keep ? n_kept : -1;
+    decided |= 1u << p; if (keep) { kept |= 1u << p; ++n_kept; }
+  }
+}
+// Any group size, one thread for the whole group: rank[i] = position in the kept list or -1 (rank doubles as state while running).
+CAL_HD int canon_group(const CKey* keys, int32_t* rank, int n, int32_t max_total_diffs, int32_t max_overlap) {
+  for (int i = 0; i < n; ++i) rank[i] = (ck_state(keys[i]) == 0 || ck_edits(keys[i]) > max_total_diffs) ? -1 : -2;      // -2 = not yet visited
   int kept = 0;
   for (;;) {
     int b = -1;
-    for (int i = 0; i < n; ++i) if (state[i] == -2 && (b < 0 || order[i] > order[b])) b = i;
+    for (int i = 0; i < n; ++i) if (rank[i] == -2 && (b < 0 || ck_before(keys[i], i, keys[b], b))) b = i;
     if (b < 0) break;
-    bool keep = !((too_many >> b) & 1u);
-    for (int i = 0; i < n && keep; ++i) {
-      if (state[i] < 0) continue;
-      const int32_t lo = start[i] > start[b] ? start[i] : start[b], hi = end[i] < end[b] ? end[i] : end[b];
-      int32_t ov = hi - lo; if (ov < 0) ov = 0;
-      if (ov > max_overlap) keep = false;
-    }
-    state[b] = keep ? kept++ : -1;
+    bool keep = true;
+    for (int i = 0; i < n && keep; ++i) if (rank[i] >= 0 && ck_overlap(keys[i], keys[b]) > max_overlap) keep = false;
+    rank[b] = keep ? kept++ : -1;
   }
-  for (int i = 0; i < n; ++i) rank[i] = state[i];
   return kept;
 }
 

@@ -30,7 +30,7 @@ namespace cal {
 struct ContigDev { int64_t len; int64_t nib_base; /* nibble index of contig base 0 */ int64_t win_base; /* global index of window 0 */
                    int64_t own_lo, own_hi; /* global ids of the windows this engine owns; windows outside are halo (processed, never reported) */ };
 struct Tile { int32_t contig; int32_t nwin; int64_t first_k; };
-struct ExplicitWindow { int64_t nib_start; int32_t len; int32_t target_offset; int32_t guide_idx; int32_t contig_idx; };
+struct ExplicitWindow { int64_t nib_start; int32_t len; int32_t target_offset; int32_t guide_idx; int32_t contig_idx; int32_t task_id /* task_idx of the hits */; int32_t owned /* 0: halo, hits take part in removeOverlaps and are never reported */; };
 
 const int ALIGN_KB = 6;          // k_align keeps a 2*6+1-diagonal DP band in registers when the candidate threshold allows
 const int SCAN_SMEM_LIMIT = 200 * 1024;   // dynamic shared memory a k_scan_tiled CTA may ask for
@@ -309,8 +309,8 @@ struct AlignArgs {
   int32_t explicit_mode;
   const uint32_t* nib;
   const ContigDev* contigs; int32_t n_contigs; int32_t window_size, step;     // tiled
-  const ExplicitWindow* windows; int32_t task_base;                          // explicit (window ids are relative to task_base)
-  uint32_t* recs; int32_t rw; uint8_t* valid; KeyLayout key;     // packed hit records, rw words each (cal_core.cuh)
+  const ExplicitWindow* windows;                                             // explicit (window ids index this array)
+  uint32_t* recs; int32_t rw; CKey* ckeys; KeyLayout key;        // packed hit records, rw words each, and one canon key per alignment slot (cal_core.cuh)
   int64_t nib_last_word;                                        // last valid word of `nib` (align_fast clamps its nine loads to it)
 };
 struct NibFetch {
@@ -333,7 +333,7 @@ CAL_D void locate_window(const uint32_t* nib, const ContigDev* contigs, int32_t 
   while (wb < we && nibble_at(nib, c.nib_base + we - 1) == CODE_N) --we;
 }
 // Everything k_align needs to know about the (window, strand) of a candidate key.
-struct CandCtx { int32_t gidx, contig_idx, m, dir; uint32_t wid; WindowGeom geom; int64_t first; uint8_t owned; };
+struct CandCtx { int32_t gidx, contig_idx, m, dir, task; uint32_t wid; WindowGeom geom; int64_t first; uint8_t owned; };
 CAL_D CandCtx decode_candidate(const AlignArgs& a, uint64_t key) {
   CandCtx x;
   const uint32_t strandbit = key_strandbit(a.key, key);
@@ -341,10 +341,12 @@ CAL_D CandCtx decode_candidate(const AlignArgs& a, uint64_t key) {
   if (a.explicit_mode) {
     const ExplicitWindow ew = a.windows[x.wid];
     x.gidx = ew.guide_idx; x.contig_idx = ew.contig_idx; x.geom.w_begin = ew.target_offset; x.geom.w_end = ew.target_offset + ew.len; x.first = ew.nib_start;
+    x.task = ew.task_id; x.owned = ew.owned ? 1 : 2;
   } else {
     int64_t wb, we; locate_window(a.nib, a.contigs, a.n_contigs, a.window_size, a.step, x.wid, x.contig_idx, wb, we);
     x.geom.w_begin = (int32_t)wb; x.geom.w_end = (int32_t)we; x.first = a.contigs[x.contig_idx].nib_base + wb;
     x.owned = ((int64_t)x.wid >= a.contigs[x.contig_idx].own_lo && (int64_t)x.wid < a.contigs[x.contig_idx].own_hi) ? 1 : 2;
+    x.task = (int32_t)x.wid;
   }
   x.dir = (int)(strandbit ^ (uint32_t)a.specs[x.gidx].five_prime);
   x.m = x.geom.w_end - x.geom.w_begin;
@@ -356,12 +358,14 @@ CAL_D void post_alignment(const AlignArgs& a, const CandCtx& x, const GuideSpec&
   const int64_t base = i * a.slots;
   HitX h;
   if (g.n_pams == 0) {
-    make_hit(g, aln, -1, aln.score, 0, 0u, x.dir, x.geom, x.gidx, x.contig_idx, (int32_t)x.wid + a.task_base, h); pack_hit(h, a.recs + base * a.rw, a.rw); a.valid[base] = x.owned;
+    make_hit(g, aln, -1, aln.score, 0, 0u, x.dir, x.geom, x.gidx, x.contig_idx, x.task, h); pack_hit(h, a.recs + base * a.rw, a.rw);
+    a.ckeys[base] = ckey_make(h.score, h.start_offset, h.end_offset, h.gap_bases, h.edits, x.owned);
   } else {
     for (int pi = 0; pi < g.n_pams; ++pi) {
       int32_t score = 0, offset = 0; uint32_t xmask = 0;
       if (extend_pam(g, a.sc, fetch, x.m, aln, pi, score, offset, xmask)) {
-        make_hit(g, aln, pi, score, offset, xmask, x.dir, x.geom, x.gidx, x.contig_idx, (int32_t)x.wid + a.task_base, h); pack_hit(h, a.recs + (base + pi) * a.rw, a.rw); a.valid[base + pi] = x.owned;
+        make_hit(g, aln, pi, score, offset, xmask, x.dir, x.geom, x.gidx, x.contig_idx, x.task, h); pack_hit(h, a.recs + (base + pi) * a.rw, a.rw);
+        a.ckeys[base + pi] = ckey_make(h.score, h.start_offset, h.end_offset, h.gap_bases, h.edits, x.owned);
       }
     }
   }
@@ -375,7 +379,7 @@ CAL_D void align_body(const AlignArgs& a) {
   const CandCtx x = decode_candidate(a, key);
   const GuideSpec& g = a.specs[x.gidx];
   const NibFetch fetch{ a.nib, x.first, x.m, x.dir };
-  for (int s = 0; s < a.slots; ++s) a.valid[i * a.slots + s] = 0;
+  for (int s = 0; s < a.slots; ++s) a.ckeys[i * a.slots + s] = CKey{ 0, 0, 0, 0u };
   GuideAln aln;
   if (KB > 0) {                           // every guide of the launch has k_edits <= KB (defaults: d = 5 -> 5, d = 6 -> 6)
     if (!band_align_k<(KB > 0 ? KB : 1)>(g, a.sc, fetch, col, aln)) return;
@@ -436,7 +440,7 @@ CAL_D void align_fast(const AlignArgs& a) {
   const int32_t j = key_col(a.key, key);
   const CandCtx x = decode_candidate(a, key);
   const GuideSpec& g = a.specs[x.gidx];
-  for (int s = 0; s < a.slots; ++s) a.valid[i * a.slots + s] = 0;
+  for (int s = 0; s < a.slots; ++s) a.ckeys[i * a.slots + s] = CKey{ 0, 0, 0, 0u };
   const int n = g.lp;
   const int base = j - n - KB;                       // cell (i, t) is target column c = i + base + t; the register window starts at column base + 1
   // ---- the 64 codes from column base + 1 on, in scan order -----------------------------------------------------------------------------
@@ -553,15 +557,17 @@ CAL_D void align_fast(const AlignArgs& a) {
     const uint32_t shape = rec_make_shape(n_ops, e0c - s0, lead, trail, n_pams > 0 ? pi : -1);
 #ifndef CAL_HOSTSIM
     uint4* r4 = reinterpret_cast<uint4*>(rec);
-    r4[0] = make_uint4((uint32_t)start, (uint32_t)((int32_t)x.wid + a.task_base), (uint32_t)score, where);
+    r4[0] = make_uint4((uint32_t)start, (uint32_t)(x.task), (uint32_t)score, where);
     r4[1] = make_uint4(shape, (uint32_t)all.lo, (uint32_t)(all.lo >> 32), (uint32_t)all.hi);
     if (a.rw > CALITAS_HIT_WORDS) { r4[2] = make_uint4((uint32_t)(all.hi >> 32), 0u, 0u, 0u); r4[3] = make_uint4(0u, 0u, 0u, 0u); }
 #else
-    rec[0] = (uint32_t)start; rec[1] = (uint32_t)((int32_t)x.wid + a.task_base); rec[2] = (uint32_t)score; rec[3] = where; rec[4] = shape;
+    rec[0] = (uint32_t)start; rec[1] = (uint32_t)(x.task); rec[2] = (uint32_t)score; rec[3] = where; rec[4] = shape;
     rec[5] = (uint32_t)all.lo; rec[6] = (uint32_t)(all.lo >> 32); rec[7] = (uint32_t)all.hi;
     if (a.rw > CALITAS_HIT_WORDS) { rec[8] = (uint32_t)(all.hi >> 32); for (int k = 9; k < a.rw; ++k) rec[k] = 0u; }
 #endif
-    a.valid[slot0 + pi] = x.owned;
+    const int gaps = popc32((uint32_t)all.lo & 0xAAAAAAAAu) + popc32((uint32_t)(all.lo >> 32) & 0xAAAAAAAAu) + popc32((uint32_t)all.hi & 0xAAAAAAAAu) + popc32((uint32_t)(all.hi >> 32) & 0xAAAAAAAAu);
+    const int edits = diffs + offset + popc32(xmask);    // non-'=' columns: the guide part, the guide-PAM gap, the PAM mismatches
+    a.ckeys[slot0 + pi] = ckey_make(score, start, start + (e0c - s0), gaps, edits, x.owned);
   }
 }
 CAL_KERNEL __launch_bounds__(128) k_align_fast6(AlignArgs a) { align_fast<6>(a); }
@@ -589,7 +595,7 @@ CAL_KERNEL __launch_bounds__(128) k_align_group(AlignArgs a, const uint32_t* gst
   const CandCtx x = decode_candidate(a, a.cand[i0]);
   const GuideSpec& g = a.specs[x.gidx];
   const NibFetch fetch{ a.nib, x.first, x.m, x.dir };
-  for (int64_t s = i0 * a.slots; s < i1 * a.slots; ++s) a.valid[s] = 0;
+  for (int64_t s = i0 * a.slots; s < i1 * a.slots; ++s) a.ckeys[s] = CKey{ 0, 0, 0, 0u };
   uint8_t trace[(CALITAS_MAX_PROTOSPACER + 1) * (GROUP_W + 1)];
   const GroupColAt col_at{ a.cand, i0, a.key };
   const int first = col_at(0), last = col_at((int)(i1 - i0) - 1);
@@ -612,23 +618,37 @@ CAL_KERNEL __launch_bounds__(128) k_align_wide(AlignArgs a) { align_body<0>(a); 
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct CanonArgs {
   const uint64_t* cand; int64_t n_cand; const GuideSpec* specs; int32_t slots; int32_t explicit_mode; const ExplicitWindow* windows;
-  const uint32_t* recs; int32_t rw; const uint8_t* valid; int32_t* rank; uint32_t* perm; uint32_t* flag; uint8_t* slot_owned; int32_t drop_halo; KeyLayout key;
+  const CKey* ckeys; int32_t* rank; uint32_t* gbase; uint32_t* flag; uint8_t* slot_owned; int32_t drop_halo; KeyLayout key;
 };
+// One thread per candidate: it finds its group's extent among its neighbours' keys and decides its own slots (canon_slot_rank); results per slot:
+// rank (position in the group's kept list or -1), gbase (first slot of the group), flag (kept and reported), slot_owned.  The r-th kept alignment of
+// a group later goes to output position pos[gbase] + r (pos = exclusive scan of flag), i.e. groups in candidate order, retval order inside a group.
+// Groups of more than 32 slots are decided by their first candidate's thread alone (canon_group).
 CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_cand) return;
   const uint64_t grp = key_group(a.key, a.cand[i]);
-  if (i > 0 && key_group(a.key, a.cand[i - 1]) == grp) return;
-  int64_t j = i + 1; while (j < a.n_cand && key_group(a.key, a.cand[j]) == grp) ++j;
-  const int64_t base = i * a.slots; const int n = (int)((j - i) * a.slots);
+  int64_t i0 = i; while (i0 > 0 && key_group(a.key, a.cand[i0 - 1]) == grp) --i0;
+  int64_t i1 = i + 1; while (i1 < a.n_cand && key_group(a.key, a.cand[i1]) == grp) ++i1;
+  const int64_t base = i0 * a.slots; const int64_t n = (i1 - i0) * a.slots;
   const int32_t gidx = a.explicit_mode ? a.windows[key_window(a.key, a.cand[i])].guide_idx : key_guide(a.key, a.cand[i]);
-  const GuideSpec& g = a.specs[gidx];
-  int kept = canon_group(a.recs + base * a.rw, a.rw, a.valid + base, a.rank + base, n, g.max_total_diffs, g.max_overlap);
-  bool owned = true; for (int k = 0; k < n; ++k) if (a.valid[base + k] == 2) owned = false;     // a group is one window: all halo or all owned
-  if (!owned && a.drop_halo) kept = 0;
-  for (int k = 0; k < n; ++k) { a.flag[base + k] = k < kept ? 1u : 0u; a.slot_owned[base + k] = owned ? 1 : 0; }
-  if (kept == 0) return;
-  for (int k = 0; k < n; ++k) { const int32_t r = a.rank[base + k]; if (r >= 0) a.perm[base + r] = (uint32_t)(base + k); }
+  const int32_t max_total = a.specs[gidx].max_total_diffs, max_overlap = a.specs[gidx].max_overlap;
+  const CKey* keys = a.ckeys + base;
+  if (n > 32) {
+    if (i != i0) return;
+    canon_group(keys, a.rank + base, (int)n, max_total, max_overlap);
+    for (int64_t k = 0; k < n; ++k) {
+      const int st = ck_state(keys[k]); const bool halo = st == 2;
+      a.gbase[base + k] = (uint32_t)base; a.slot_owned[base + k] = halo ? 0 : 1; a.flag[base + k] = (a.rank[base + k] >= 0 && !(halo && a.drop_halo)) ? 1u : 0u;
+    }
+    return;
+  }
+  for (int q = 0; q < a.slots; ++q) {
+    const int k = (int)(i - i0) * a.slots + q; const int64_t s = base + k;
+    const int st = ck_state(keys[k]); const bool halo = st == 2;
+    const int r = st == 0 ? -1 : canon_slot_rank(keys, (int)n, k, max_total, max_overlap);
+    a.rank[s] = r; a.gbase[s] = (uint32_t)base; a.slot_owned[s] = halo ? 0 : 1; a.flag[s] = (r >= 0 && !(halo && a.drop_halo)) ? 1u : 0u;
+  }
 }
 #ifndef CAL_HOSTSIM
 // Warp-per-group variant for large groups (best mode: every end column of a window is a candidate, 60-250 alignments per group).  Same
@@ -644,8 +664,9 @@ CAL_KERNEL __launch_bounds__(128) k_canon_warp(CanonArgs a, const uint32_t* gsta
     const int64_t base = i0 * a.slots; const int n = (int)((i1 - i0) * a.slots);
     const int32_t gidx = a.explicit_mode ? a.windows[key_window(a.key, a.cand[i0])].guide_idx : key_guide(a.key, a.cand[i0]);
     const int32_t max_total = a.specs[gidx].max_total_diffs, max_overlap = a.specs[gidx].max_overlap;
+    const CKey* keys = a.ckeys + base;
     bool halo = false;
-    for (int k = lane; k < n; k += 32) { const uint8_t v = a.valid[base + k]; a.rank[base + k] = v ? -2 : -1; halo |= v == 2; }
+    for (int k = lane; k < n; k += 32) { const int st = ck_state(keys[k]); a.rank[base + k] = (st == 0 || ck_edits(keys[k]) > max_total) ? -1 : -2; halo |= st == 2; }
     halo = __any_sync(0xFFFFFFFFu, halo);
     __syncwarp();
     int kept = 0;
@@ -653,34 +674,24 @@ CAL_KERNEL __launch_bounds__(128) k_canon_warp(CanonArgs a, const uint32_t* gsta
       unsigned long long best = ~0ull;
       for (int k = lane; k < n; k += 32) {
         if (a.rank[base + k] != -2) continue;
-        const uint32_t* h = a.recs + (base + k) * a.rw;
-        const unsigned long long key = ((unsigned long long)(uint32_t)(0x7FFFFFFF - rec_score(h)) << 32) | ((unsigned long long)rec_gap_bases(h, a.rw) << 20) | (unsigned long long)k;
+        const unsigned long long key = ((unsigned long long)(uint32_t)(0x7FFFFFFF - keys[k].score) << 32) | ((unsigned long long)ck_gaps(keys[k]) << 20) | (unsigned long long)k;
         if (key < best) best = key;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o); if (other < best) best = other; }
       if (best == ~0ull) break;
       const int b = (int)(best & 0xFFFFFu);
-      const uint32_t* hb = a.recs + (base + b) * a.rw;
-      const bool keep = rec_edits(hb, a.rw) <= max_total;
-      const int32_t bs = rec_start(hb), be = rec_end(hb);
+      const CKey hb = keys[b];
       __syncwarp();
-      if (lane == 0) a.rank[base + b] = keep ? kept : -1;
-      if (keep) {
-        ++kept;
-        for (int k = lane; k < n; k += 32) {
-          if (k == b || a.rank[base + k] != -2) continue;
-          const uint32_t* h = a.recs + (base + k) * a.rw;
-          const int32_t lo = rec_start(h) > bs ? rec_start(h) : bs, hi = rec_end(h) < be ? rec_end(h) : be;
-          int32_t ov = hi - lo; if (ov < 0) ov = 0;           // GuideAlignment.overlap clamps at 0, as canon_group does
-          if (ov > max_overlap) a.rank[base + k] = -1;
-        }
+      if (lane == 0) a.rank[base + b] = kept;                 // nothing kept so far overlaps it: those would have dropped it when they were kept
+      ++kept;
+      for (int k = lane; k < n; k += 32) {
+        if (k == b || a.rank[base + k] != -2) continue;
+        if (ck_overlap(keys[k], hb) > max_overlap) a.rank[base + k] = -1;
       }
       __syncwarp();
     }
-    if (halo && a.drop_halo) kept = 0;
-    for (int k = lane; k < n; k += 32) { a.flag[base + k] = k < kept ? 1u : 0u; a.slot_owned[base + k] = halo ? 0 : 1; }
-    if (kept) for (int k = lane; k < n; k += 32) { const int32_t r = a.rank[base + k]; if (r >= 0) a.perm[base + r] = (uint32_t)(base + k); }
+    for (int k = lane; k < n; k += 32) { a.gbase[base + k] = (uint32_t)base; a.slot_owned[base + k] = halo ? 0 : 1; a.flag[base + k] = (a.rank[base + k] >= 0 && !(halo && a.drop_halo)) ? 1u : 0u; }
     __syncwarp();
   }
 }
@@ -694,11 +705,14 @@ CAL_D void copy_rec(uint32_t* dst, const uint32_t* src, int rw) {
   for (int k = 0; k < rw; ++k) dst[k] = src[k];
 #endif
 }
-// out[pos[s]] = recs[perm[s]] for flagged slots (the kept alignments of every group, in retval order)
-CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const uint32_t* recs, int32_t rw, const uint32_t* perm, const uint32_t* flag, const uint32_t* pos, int64_t n, uint32_t* out) {
+// flagged slot s -> output position pos[gbase[s]] + rank[s]: groups in candidate order, the kept alignments of a group in retval order
+CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const uint32_t* recs, int32_t rw, const int32_t* rank, const uint32_t* gbase, const uint32_t* flag, const uint32_t* pos, int64_t n, uint32_t* out,
+                                                   const uint8_t* slot_owned, uint8_t* out_owned) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n || !flag[s]) return;
-  copy_rec(out + (int64_t)pos[s] * rw, recs + (int64_t)perm[s] * rw, rw);
+  const int64_t at = (int64_t)pos[gbase[s]] + rank[s];
+  copy_rec(out + at * rw, recs + s * rw, rw);
+  if (out_owned) out_owned[at] = slot_owned[s];
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------------
@@ -714,11 +728,11 @@ CAL_KERNEL __launch_bounds__(256) k_gather_flagged(const uint32_t* recs, int32_t
 struct DedupLayout { int32_t start_bits, contig_shift, guide_shift, bits /* without the score */, g0, score_hi, score_bits, merged; };
 // One thread per alignment slot: the kept ones (flag) get their sort key at pos[s] (their arrival rank: group order, then retval order), with the
 // slot of the record as the sort value; nothing is copied until the keepers are known.
-CAL_KERNEL __launch_bounds__(256) k_dedup_keys(const uint32_t* recs, int32_t rw, const uint32_t* perm, const uint32_t* flag, const uint32_t* pos, int64_t n_slots, DedupLayout L,
+CAL_KERNEL __launch_bounds__(256) k_dedup_keys(const uint32_t* recs, int32_t rw, const int32_t* rank, const uint32_t* gbase, const uint32_t* flag, const uint32_t* pos, int64_t n_slots, DedupLayout L,
                                                uint64_t* key, uint64_t* keyA, uint32_t* idx, uint32_t* overflow) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots || !flag[s]) return;
-  const int64_t i = pos[s]; const uint32_t src = perm[s];
+  const int64_t i = (int64_t)pos[gbase[s]] + rank[s]; const uint32_t src = (uint32_t)s;
   const uint32_t* h = recs + (int64_t)src * rw;
   const int64_t start = rec_gstart(h), sc = (int64_t)L.score_hi - rec_score(h), g = (int64_t)rec_guide(h) - L.g0, c = rec_contig(h);
   if (start < 0 || (start >> L.start_bits) != 0 || sc < 0 || (sc >> L.score_bits) != 0 || g < 0 || c < 0 ||
@@ -780,6 +794,92 @@ CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key, const int32_t* s_
 CAL_KERNEL __launch_bounds__(256) k_gather_keepers(const uint32_t* recs, int32_t rw, const uint32_t* idx, const uint32_t* keep, const uint32_t* pos, int64_t n, uint32_t* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && keep[i]) copy_rec(out + (int64_t)pos[i] * rw, recs + (int64_t)idx[i] * rw, rw);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// SearchReference -v on the device (SearchReference.scala:570-630, 641-648, 653-675): hits of the reference windows and of the variant windows are
+// merged, de-duplicated per (guide, contig, strand, variant set) and sorted here; the host only builds the windows and renders the keepers.
+// ------------------------------------------------------------------------------------------------------------------------------------
+struct VarWindowDev { int64_t nib_start; int32_t length, contig_idx, ref_start /* 1-based */, n_alleles, first_allele, first_set, owned, pad_; };
+struct VarInfo { int32_t window_idx, start_offset, end_offset, guide_start_offset, guide_end_offset, set_rank; };      // == calitas_variant_hit_info
+// VariantWindow.refOffsetAtBaseOffset (SearchReference.scala:133-156) from the allele list: the window's cigar is, per allele in position order, an
+// M run up to the allele, then M x len (same length) | M + I x (alt - 1) | M + D x (ref - 1) | D x ref + I x alt (:282-319), then an M tail.
+CAL_D int32_t var_ref_offset(const VarWindowDev& w, const calitas_variant_allele* al, int32_t offset, bool preceding) {
+  int32_t ref_off = w.ref_start - 1, base_off = 0, ref_pos = w.ref_start;
+  // one cigar element; returns true when `offset` falls into it
+#define CAL_VSTEP(OP, LEN) { const int32_t len_ = (LEN); const int32_t onq_ = (OP) == 2 ? 0 : len_, onr_ = (OP) == 1 ? 0 : len_; \
+    if (offset < base_off + onq_ && offset < w.length) return (OP) == 1 ? (preceding ? ref_off - 1 : ref_off) : ref_off + (offset - base_off); \
+    ref_off += onr_; base_off += onq_; }
+  for (int k = 0; k < w.n_alleles; ++k) {
+    const calitas_variant_allele a = al[w.first_allele + k];
+    const int32_t pre = a.pos - ref_pos;
+    if (pre > 0) { CAL_VSTEP(0, pre) ref_pos += pre; }
+    if (a.ref_len == a.alt_len) { CAL_VSTEP(0, a.ref_len) }
+    else if (a.ref_len == 1) { CAL_VSTEP(0, 1) CAL_VSTEP(1, a.alt_len - 1) }
+    else if (a.alt_len == 1) { CAL_VSTEP(0, 1) CAL_VSTEP(2, a.ref_len - 1) }
+    else { CAL_VSTEP(2, a.ref_len) CAL_VSTEP(1, a.alt_len) }
+    ref_pos += a.ref_len;
+  }
+  CAL_VSTEP(0, w.length - base_off)
+#undef CAL_VSTEP
+  return ref_off;                           // offset == window length: start - 1 + cigar.lengthOnTarget (:134-136)
+}
+struct VarKeyLayout { int32_t set_bits, contig_bits, score_hi, score_bits, start_bits; };
+// What calitas_search_variants adds to a search: the variant windows whose hits are merged with the reference windows' hits.
+struct VariantPlan {
+  int64_t n_windows; const calitas_variant_window* windows; const int32_t* guide_class; const calitas_variant_allele* alleles; int64_t n_alleles;
+  const uint32_t* set_rank; int64_t n_sets;
+};
+// One thread per merged hit (reference hits first, then variant-window hits, each in arrival order): reference coordinates, the variant set the hit
+// overlaps (ReferenceHit.scala:211), and the two sort keys of the sweep order: major = guide | contig | set, minor = start | strand | score_hi - score.
+CAL_KERNEL __launch_bounds__(256) k_variant_keys(const uint32_t* recs, int32_t rw, int64_t n_ref, int64_t n, const VarWindowDev* windows, const calitas_variant_allele* alleles,
+                                                 const uint32_t* set_rank, VarKeyLayout L, VarInfo* info, uint64_t* major, uint64_t* minor, uint32_t* idx, uint32_t* overflow) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* h = recs + i * rw;
+  VarInfo v;
+  if (i < n_ref) { v.window_idx = -1; v.start_offset = rec_start(h); v.end_offset = rec_end(h); v.guide_start_offset = rec_gstart(h); v.guide_end_offset = rec_gend(h); v.set_rank = 0; }
+  else {
+    v.window_idx = rec_task(h);
+    const VarWindowDev w = windows[v.window_idx];
+    v.start_offset = var_ref_offset(w, alleles, rec_start(h), true); v.end_offset = var_ref_offset(w, alleles, rec_end(h), false);                 // SearchReference.scala:615-620
+    v.guide_start_offset = var_ref_offset(w, alleles, rec_gstart(h), true); v.guide_end_offset = var_ref_offset(w, alleles, rec_gend(h), false);
+    int a = 0; while (a < w.n_alleles && alleles[w.first_allele + a].pos - 1 < v.start_offset) ++a;                                               // ReferenceHit.scala:211: pos - 1 in [start, end]
+    int b = a; while (b < w.n_alleles && alleles[w.first_allele + b].pos - 1 <= v.end_offset) ++b;
+    v.set_rank = b > a ? (int32_t)set_rank[w.first_set + a * w.n_alleles - a * (a - 1) / 2 + (b - a - 1)] : 0;
+  }
+  info[i] = v;
+  const int64_t sc = (int64_t)L.score_hi - rec_score(h), start = v.guide_start_offset, c = rec_contig(h);
+  if (start < 0 || (start >> L.start_bits) != 0 || sc < 0 || (sc >> L.score_bits) != 0 || c < 0 || (c >> L.contig_bits) != 0 || ((uint64_t)(uint32_t)v.set_rank >> L.set_bits) != 0) *overflow = 1u;
+  major[i] = (((uint64_t)rec_guide(h) << L.contig_bits | (uint64_t)c) << L.set_bits) | (uint64_t)(uint32_t)v.set_rank;
+  minor[i] = ((((uint64_t)start << 1) | (uint64_t)rec_neg(h)) << L.score_bits) | (uint64_t)sc;
+  idx[i] = (uint32_t)i;
+}
+// sorted position i -> what k_sweep reads: key = major << 1 | strand (group = key >> 1), start, sweep end (ReferenceHit.scala:135-138: the hit's own span), score, owned
+CAL_KERNEL __launch_bounds__(256) k_variant_sweep_prepare(const uint32_t* recs, int32_t rw, const VarInfo* info, const uint8_t* owned, const uint64_t* major_sorted, const uint32_t* idx, int64_t n,
+                                                          uint64_t* key, int32_t* s_start, int32_t* s_end, int32_t* s_score, uint8_t* s_owned) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t src = idx[i]; const uint32_t* h = recs + (int64_t)src * rw;
+  key[i] = (major_sorted[i] << 1) | (uint64_t)rec_neg(h);
+  s_start[i] = info[src].guide_start_offset; s_end[i] = info[src].guide_start_offset + rec_span(h) - 1; s_score[i] = rec_score(h); s_owned[i] = owned[src];
+}
+// keepers, in sweep order: their final sort key (ReferenceHit.sort: guide, contig, coordinate_start, strand, -score) and their index into the merged list
+CAL_KERNEL __launch_bounds__(256) k_variant_final_keys(const uint32_t* recs, int32_t rw, const VarInfo* info, const uint32_t* idx, const uint32_t* keep, const uint32_t* pos, int64_t n, DedupLayout L,
+                                                       uint64_t* key, uint32_t* out_idx, uint32_t* overflow) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  const uint32_t src = idx[i]; const uint32_t* h = recs + (int64_t)src * rw;
+  const int64_t start = info[src].guide_start_offset, sc = (int64_t)L.score_hi - rec_score(h), g = rec_guide(h), c = rec_contig(h);
+  if (start < 0 || (start >> L.start_bits) != 0 || sc < 0 || (sc >> L.score_bits) != 0 || c < 0 || (uint64_t)c >= (1ull << (L.guide_shift - L.contig_shift))) *overflow = 1u;
+  const uint64_t k = ((uint64_t)g << L.guide_shift) | ((uint64_t)c << L.contig_shift) | ((uint64_t)start << 1) | (uint64_t)rec_neg(h);
+  key[pos[i]] = (k << L.score_bits) | (uint64_t)sc;
+  out_idx[pos[i]] = src;
+}
+CAL_KERNEL __launch_bounds__(256) k_variant_gather(const uint32_t* recs, int32_t rw, const VarInfo* info, const uint32_t* idx, int64_t n, uint32_t* out, VarInfo* out_info) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  copy_rec(out + i * rw, recs + (int64_t)idx[i] * rw, rw); out_info[i] = info[idx[i]];
 }
 
 // Counters the host waits for are stored straight into mapped pinned host memory by these one-thread kernels (see dev::alloc_host_mapped).
@@ -864,7 +964,7 @@ struct calitas_reference {
 };
 
 struct calitas_hitset {
-  calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; int32_t stride = CALITAS_HIT_WORDS * 4; double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; int32_t stride = CALITAS_HIT_WORDS * 4; PinnedBuf info; /* calitas_variant_hit_info per hit, search_variants only */ double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 
 enum { CNT_GROUPS = 3, CNT_KEPT = 4, CNT_KEEPERS = 5 /* + 6: overflow flag as published */, CNT_DEDUP_OVERFLOW = 7 };
@@ -875,12 +975,12 @@ struct calitas_engine {
   int device = 0; Scores sc; calitas_costs costs;
   // stream: sort/align/canonicalise/dedup (greatest priority); scan_stream: k_scan_tiled of calitas_search (least priority, so that the tail of
   // guide chunk c slips in between the blocks of chunk c+1's scan); copy_stream: D2H of finished hit segments
-  dev::Stream stream, scan_stream, copy_stream;
+  dev::Stream stream, scan_stream, scan_stream2, copy_stream, pub_stream;   // scans alternate between the two scan streams: the next chunk's blocks fill the SMs the previous scan's last wave leaves idle
   dev::Event ev[8];
   std::vector<ChunkEvents> chunk_ev;
   size_t out_hits_hint = 1u << 16;
   DBuf cand_b, cand_c;
-  DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, sowned;
+  DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, sowned, out_owned, var_windows, var_alleles, var_sets, var_info, var_info2, var_nib, var_raw, out2, vk1, vk2, vk3, vi1, vi2, vi3;
   // eight 64-bit device counters and their pinned host mirror: slots 0..2 = candidate counts of the three scan buffers (run_explicit uses 0),
   // slot CNT_DEDUP_OVERFLOW = k_dedup_keys' "a field does not fit its sort-key width" flag
   unsigned long long* h_count = nullptr;       // pinned + mapped: the device stores into it through h_count_dev (no copy engine involved)
@@ -963,10 +1063,11 @@ calitas_reference::TileSet& tileset_for(calitas_engine* e, calitas_reference* r,
 struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> align -> canon -> (removeOverlaps + sort | compaction) -> e->out
   calitas_engine* e; const uint64_t* cand; dev::Event ev_sorted, ev_align_b, ev_align_e;   // candidate keys; events recorded after the sort / around k_align
   const GuideSpec* d_specs; int slots; bool explicit_mode; int banded;   // banded: 0 = wide thresholds, else the largest k_edits of the launch (<= ALIGN_KB)
-  const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; int32_t task_base; bool drop_halo;
+  const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; bool drop_halo;
   KeyLayout key; int rw;                                                   // rw: 32-bit words per hit record of this call
   bool fast; int64_t nib_words;                                            // fast: every guide of the launch fits align_fast's 64-column window; nib_words: size of `nib`
   const DedupLayout* dedup; int32_t max_overlap;                           // dedup != nullptr: removeOverlaps + ReferenceHit.sort over the kept alignments
+  DBuf* out_owned;                                                         // plain compaction only: when given, one byte per output record (1 = owned, 0 = halo) goes here
 };
 
 // align_fast<KB> keeps 64 target codes per candidate in registers: band + guide-PAM gap + longest PAM must fit, and the extension indexes 32 of them
@@ -996,11 +1097,11 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
   dev::event_record(P.ev_sorted, s);                      // the candidate buffer may be refilled by the next scan from here on
   // 2. align
   const int64_t n_slots = n_cand * P.slots;
-  e->hits.ensure((size_t)n_slots * rw * 4); e->valid.ensure((size_t)n_slots);
+  e->hits.ensure((size_t)n_slots * rw * 4); e->valid.ensure((size_t)n_slots * sizeof(CKey));
   AlignArgs aa; std::memset(&aa, 0, sizeof aa);
   aa.cand = e->cand_sorted.as<uint64_t>(); aa.n_cand = n_cand; aa.specs = P.d_specs; aa.sc = e->sc; aa.slots = P.slots; aa.explicit_mode = P.explicit_mode ? 1 : 0;
-  aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows; aa.task_base = P.task_base;
-  aa.recs = e->hits.as<uint32_t>(); aa.rw = rw; aa.valid = e->valid.as<uint8_t>(); aa.key = P.key; aa.nib_last_word = P.nib_words - 1;
+  aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows;
+  aa.recs = e->hits.as<uint32_t>(); aa.rw = rw; aa.ckeys = e->valid.as<CKey>(); aa.key = P.key; aa.nib_last_word = P.nib_words - 1;
   dev::event_record(P.ev_align_b, s);
   if (P.banded > 0 && P.fast) {
     if (P.banded > 5) { CAL_LAUNCH(k_align_fast6, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_fast6"); }
@@ -1029,7 +1130,7 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
   e->rank.ensure((size_t)n_slots * 4); e->perm.ensure((size_t)n_slots * 4); e->flag.ensure((size_t)n_slots * 4); e->pos.ensure((size_t)n_slots * 4); e->slot_owned.ensure((size_t)n_slots);
   CanonArgs ca; std::memset(&ca, 0, sizeof ca);
   ca.cand = aa.cand; ca.n_cand = n_cand; ca.specs = P.d_specs; ca.slots = P.slots; ca.explicit_mode = aa.explicit_mode; ca.windows = P.d_windows;
-  ca.recs = aa.recs; ca.rw = rw; ca.valid = aa.valid; ca.rank = e->rank.as<int32_t>(); ca.perm = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>(); ca.slot_owned = e->slot_owned.as<uint8_t>(); ca.drop_halo = P.drop_halo ? 1 : 0; ca.key = P.key;
+  ca.ckeys = aa.ckeys; ca.rank = e->rank.as<int32_t>(); ca.gbase = e->perm.as<uint32_t>(); ca.flag = e->flag.as<uint32_t>(); ca.slot_owned = e->slot_owned.as<uint8_t>(); ca.drop_halo = P.drop_halo ? 1 : 0; ca.key = P.key;
 #ifndef CAL_HOSTSIM
   if (P.explicit_mode && !P.banded) {     // large groups: a warp per group (group starts, indices and flags were built for k_align_group)
     CAL_LAUNCH(k_canon_warp, (unsigned)dev::sm_count(e->device) * 16, 128, 0, s, 1, ca, e->idx.as<uint32_t>(), e->keyA.as<uint32_t>(), e->key1.as<uint32_t>()); dev::launch_check("k_canon_warp"); ++e->launches;
@@ -1045,7 +1146,10 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
   if (n == 0) return 0;
   if (!P.dedup) {                          // plain compaction straight into the output
     ensure_out(e, rw, out_n, n, projected_total);
-    CAL_LAUNCH(k_gather_flagged, blocks_for(n_slots, 256), 256, 0, s, 1, aa.recs, rw, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, e->out.as<uint32_t>() + out_n * rw); dev::launch_check("k_gather_flagged"); ++e->launches;
+    uint8_t* oo = nullptr;
+    if (P.out_owned) { P.out_owned->ensure_keep((size_t)(out_n + n), (size_t)out_n, s); oo = P.out_owned->as<uint8_t>() + out_n; }
+    CAL_LAUNCH(k_gather_flagged, blocks_for(n_slots, 256), 256, 0, s, 1, aa.recs, rw, e->rank.as<int32_t>(), e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, e->out.as<uint32_t>() + out_n * rw,
+               (const uint8_t*)e->slot_owned.as<uint8_t>(), oo); dev::launch_check("k_gather_flagged"); ++e->launches;
     return n;
   }
   // 4. removeOverlaps (SearchReference.scala:653-675) + ReferenceHit.sort: keys of the kept slots, ONE stable radix sort (two when the fields do not fit
@@ -1057,13 +1161,13 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
   const uint64_t* skey; const uint32_t* sidx; int strand_shift;
   uint32_t* d_overflow = (uint32_t*)(e->d_count + CNT_DEDUP_OVERFLOW);
   if (L.merged) {
-    CAL_LAUNCH(k_dedup_keys, blocks_for(n_slots, 256), 256, 0, s, 1, aa.recs, rw, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, L, e->keyA.as<uint64_t>(), (uint64_t*)nullptr, e->idx.as<uint32_t>(), d_overflow); dev::launch_check("k_dedup_keys"); ++e->launches;
+    CAL_LAUNCH(k_dedup_keys, blocks_for(n_slots, 256), 256, 0, s, 1, aa.recs, rw, e->rank.as<int32_t>(), e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, L, e->keyA.as<uint64_t>(), (uint64_t*)nullptr, e->idx.as<uint32_t>(), d_overflow); dev::launch_check("k_dedup_keys"); ++e->launches;
     dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key1.as<uint64_t>(), e->idx.as<uint32_t>(), e->idx2.as<uint32_t>(), (size_t)n, 0, L.bits + L.score_bits, s); ++e->launches;
     skey = e->key1.as<uint64_t>(); sidx = e->idx2.as<uint32_t>(); strand_shift = L.score_bits;
   } else {      // stable by -score (arrival order = input order), then stable by (guide, contig, start, strand)
     e->key_b.ensure((size_t)n * 8); e->sstart.ensure((size_t)n * 4);
     uint32_t* ord = e->sstart.as<uint32_t>();    // positions 0..n-1, carried through the first sort to permute the second sort's keys
-    CAL_LAUNCH(k_dedup_keys, blocks_for(n_slots, 256), 256, 0, s, 1, aa.recs, rw, e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, L, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>(), d_overflow); dev::launch_check("k_dedup_keys"); ++e->launches;
+    CAL_LAUNCH(k_dedup_keys, blocks_for(n_slots, 256), 256, 0, s, 1, aa.recs, rw, e->rank.as<int32_t>(), e->perm.as<uint32_t>(), e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n_slots, L, e->key1.as<uint64_t>(), e->keyA.as<uint64_t>(), e->idx.as<uint32_t>(), d_overflow); dev::launch_check("k_dedup_keys"); ++e->launches;
     CAL_LAUNCH(k_iota_u32, blocks_for(n, 256), 256, 0, s, 1, ord, n); dev::launch_check("k_iota_u32"); ++e->launches;
     dev::sort_pairs_u64(e->tmp.p, tb, e->keyA.as<uint64_t>(), e->key_b.as<uint64_t>(), ord, e->idx2.as<uint32_t>(), (size_t)n, 0, L.score_bits, s); ++e->launches;
     CAL_LAUNCH(k_gather_u64, blocks_for(n, 256), 256, 0, s, 1, e->key1.as<uint64_t>(), e->idx2.as<uint32_t>(), n, e->keyA.as<uint64_t>()); dev::launch_check("k_gather_u64"); ++e->launches;
@@ -1115,23 +1219,24 @@ std::vector<GuideSpec> build_specs(calitas_engine* e, int32_t n_guides, const ca
 }
 
 // explicit-window path shared by align_regions / align_targets
-calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, const std::vector<ExplicitWindow>& windows, const std::vector<GuideSpec>& specs) {
-  dev::Stream s = e->stream; dev::set_device(e->device);
-  e->launches = 0;
-  dev::event_record(e->ev[0], s);
-  int slots = 1, banded = 1, max_cols = 1; for (auto& sp : specs) { slots = std::max(slots, sp.slots); banded = std::max(banded, std::max(sp.k_edits, sp.band_k)); max_cols = std::max(max_cols, sp.max_cols); }
-  const int rw = rec_words_for(max_cols);
-  if (banded > ALIGN_KB) banded = 0;
-  bool fast = banded > 0; for (auto& sp : specs) fast = fast && fits_align_fast(sp, banded);
-  e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
-  e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
-  double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { (int64_t)windows.size(), 0, 0, 0, 0, 0, 0, 0 };
-  counts[4] = (int64_t)(specs.size() * sizeof(GuideSpec) + windows.size() * sizeof(ExplicitWindow));
-  int64_t n_out = 0;
-  const int64_t n_windows = (int64_t)windows.size();
+// Shape of a launch over a set of guides: alignment slots per candidate, which align kernel, record size.
+struct LaunchShape { int slots, banded, rw; bool fast; };
+LaunchShape launch_shape(const std::vector<GuideSpec>& specs, size_t g0, size_t g1, int rw_all) {
+  LaunchShape L{ 1, 1, rw_all, true };
+  for (size_t g = g0; g < g1; ++g) { L.slots = std::max(L.slots, specs[g].slots); L.banded = std::max(L.banded, std::max(specs[g].k_edits, specs[g].band_k)); }
+  if (L.banded > ALIGN_KB) L.banded = 0;
+  L.fast = L.banded > 0; for (size_t g = g0; g < g1; ++g) L.fast = L.fast && fits_align_fast(specs[g], L.banded);
+  return L;
+}
+int rec_words_of(const std::vector<GuideSpec>& specs) { int m = 1; for (auto& sp : specs) m = std::max(m, sp.max_cols); return rec_words_for(m); }
+
+// Explicit windows already on the device (e->windows[0..n_windows), guide table in e->specs): scan + tail in batches, the kept alignments are appended
+// to e->out at n_out in (window, strand, retval) order.  drop_halo / out_owned as in Pipeline.
+void explicit_core(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, int64_t n_windows, uint32_t max_len, const LaunchShape& L, bool drop_halo, DBuf* out_owned,
+                   int64_t& n_out, double ms[8], int64_t counts[8]) {
+  dev::Stream s = e->stream;
   // batches bound the candidate buffer: in best mode every column of every window is a candidate
-  int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_windows, 1 << 18));
-  uint32_t max_len = 1; for (auto& w : windows) if (w.len > 0 && (uint32_t)w.len > max_len) max_len = (uint32_t)w.len;
+  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_windows, L.banded ? (1 << 22) : (1 << 18)));
   const KeyLayout key = make_key_layout(max_len, (uint64_t)batch, 1);       // window ids are relative to the batch; the guide comes from the window
   for (int64_t w0 = 0; w0 < n_windows; w0 += batch) {
     const int64_t nw = std::min(batch, n_windows - w0);
@@ -1151,15 +1256,156 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, int64_t n
     ms[1] += dev::event_ms(e->ev[4], e->ev[5]);
     counts[1] += (int64_t)n_cand;
     // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
-    Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), slots, true, banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, (int32_t)w0, true, key, rw, fast, nib_words, nullptr, 0 };
+    Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), L.slots, true, L.banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, drop_halo, key, L.rw, L.fast, nib_words, nullptr, 0, out_owned };
     int64_t n_aln = 0;
     const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_out, 0, n_aln);
     if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
     counts[2] += n_aln;
     n_out += n_kept;
   }
+}
+
+// explicit-window path shared by align_regions / align_targets
+calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, const std::vector<ExplicitWindow>& windows, const std::vector<GuideSpec>& specs) {
+  dev::Stream s = e->stream; dev::set_device(e->device);
+  e->launches = 0;
+  dev::event_record(e->ev[0], s);
+  const LaunchShape L = launch_shape(specs, 0, specs.size(), rec_words_of(specs));
+  e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
+  e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
+  double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { (int64_t)windows.size(), 0, 0, 0, 0, 0, 0, 0 };
+  counts[4] = (int64_t)(specs.size() * sizeof(GuideSpec) + windows.size() * sizeof(ExplicitWindow));
+  int64_t n_out = 0;
+  uint32_t max_len = 1; for (auto& w : windows) if (w.len > 0 && (uint32_t)w.len > max_len) max_len = (uint32_t)w.len;
+  explicit_core(e, d_nib, nib_words, (int64_t)windows.size(), max_len, L, true, nullptr, n_out, ms, counts);
   counts[3] = e->launches;
-  return finish_hitset(e, n_out, rw, ms, counts);
+  return finish_hitset(e, n_out, L.rw, ms, counts);
+}
+
+// Score bounds of the hits a set of guides can produce (for the width of the score field in the sort keys): a hit's score = guide alignment
+// (min_score ... lp rows each worth at most a match or an inserted base) + PAM bases + offset * queryGap.
+void score_bounds(const std::vector<GuideSpec>& specs, size_t g0, size_t g1, const Scores& sc, int32_t& score_hi, int32_t& score_bits) {
+  int64_t hi = 0, lo = 0; bool first = true;
+  for (size_t g = g0; g < g1; ++g) {
+    const GuideSpec& sp = specs[g];
+    int pam_len = 0; for (int k = 0; k < sp.n_pams; ++k) pam_len = std::max<int>(pam_len, sp.pam_len[k]);
+    const int64_t per_row = std::max<int64_t>(std::max<int64_t>(sc.match, sc.target_gap), 0), per_pam = std::max<int64_t>(iabs(sc.pam_match), iabs(sc.pam_mismatch));
+    const int64_t h = per_row * sp.lp + per_pam * pam_len + (int64_t)std::max(0, sp.g) * std::max<int64_t>(sc.query_gap, 0);
+    const int64_t l = (int64_t)sp.min_score - per_pam * pam_len - (int64_t)std::max(0, sp.g) * iabs(sc.query_gap);
+    if (first || h > hi) hi = h;
+    if (first || l < lo) lo = l;
+    first = false;
+  }
+  if (hi - lo >= (1ll << 31) || hi > 0x7FFFFFFFll || hi < -0x7FFFFFFFll) { score_hi = 0x7FFFFFFF; score_bits = 33; }   // 0x7FFFFFFF - score fits 33 bits for any int32 score
+  else { score_hi = (int32_t)hi; score_bits = std::max(1, bit_length((uint64_t)(hi - lo))); }
+}
+
+// Variant windows of a SearchReference -v run (SearchReference.scala:570-630): aligned like any explicit target, then merged with the n_ref reference
+// hits already in e->out (arrival order; e->out_owned says which are reported), de-duplicated per (guide, contig, strand, variant set) and put in
+// ReferenceHit.sort order (:641-648, 653-675).  Result: records in e->out2, annotations in e->var_info2; returns their number.
+int64_t merge_variant_hits(calitas_engine* e, const VariantPlan& vp, const std::vector<GuideSpec>& specs, const calitas_limits* limits, const calitas_reference* ref, int rw, int64_t n_ref,
+                           double ms[8], int64_t counts[8]) {
+  dev::Stream s = e->stream;
+  const int64_t n_w = vp.n_windows;
+  int64_t n = n_ref;
+  if (n_w > 0) {
+    // ---- window bases: concatenated at multiples of 8 with a gap, uploaded raw and packed on the device like the reference --------------------------
+    std::vector<VarWindowDev> wd((size_t)n_w); std::vector<int64_t> off((size_t)n_w);
+    int64_t total = 64; uint32_t max_len = 1;
+    for (int64_t w = 0; w < n_w; ++w) {
+      const calitas_variant_window& v = vp.windows[w];
+      if (v.length < 0 || (uint32_t)v.length > MAX_WINDOW_LEN || (v.length && !v.bases) || v.n_alleles < 0 || v.first_allele < 0 || v.first_allele + (int64_t)v.n_alleles > vp.n_alleles ||
+          v.first_set < 0 || v.first_set + (int64_t)v.n_alleles * (v.n_alleles + 1) / 2 > vp.n_sets || v.contig_idx < 0 || v.contig_idx >= (int)ref->len.size())
+        throw InvalidArgument("bad variant window");
+      off[(size_t)w] = total; max_len = std::max<uint32_t>(max_len, (uint32_t)v.length);
+      wd[(size_t)w] = VarWindowDev{ total, v.length, v.contig_idx, v.ref_start, v.n_alleles, v.first_allele, v.first_set, v.owned ? 1 : 0, 0 };
+      total += (v.length + 7) / 8 * 8 + 8;
+    }
+    total += 64;
+    {
+      std::vector<uint8_t> raw((size_t)total, 0);
+      for (int64_t w = 0; w < n_w; ++w) if (vp.windows[w].length) std::memcpy(raw.data() + off[(size_t)w], vp.windows[w].bases, (size_t)vp.windows[w].length);
+      e->var_raw.ensure((size_t)total); e->var_nib.ensure((size_t)total / 2 + 8);
+      dev::h2d(e->var_raw.p, raw.data(), (size_t)total, s);
+      const int64_t n_words = total / 8;
+      const unsigned grid = (unsigned)std::min<int64_t>((n_words + 255) / 256, (int64_t)dev::sm_count(e->device) * 16);
+      CAL_LAUNCH(k_pack, grid, 256, 256, s, 2, e->var_raw.as<uint8_t>(), e->var_nib.as<uint32_t>(), n_words); dev::launch_check("k_pack"); ++e->launches;
+      dev::stream_sync(s);                                 // `raw` goes out of scope
+      counts[4] += total;
+    }
+    e->var_windows.ensure(wd.size() * sizeof(VarWindowDev)); dev::h2d(e->var_windows.p, wd.data(), wd.size() * sizeof(VarWindowDev), s);
+    e->var_alleles.ensure(std::max<size_t>(1, (size_t)vp.n_alleles) * sizeof(calitas_variant_allele)); dev::h2d(e->var_alleles.p, vp.alleles, (size_t)vp.n_alleles * sizeof(calitas_variant_allele), s);
+    e->var_sets.ensure(std::max<size_t>(1, (size_t)vp.n_sets) * 4); dev::h2d(e->var_sets.p, vp.set_rank, (size_t)vp.n_sets * 4, s);
+    counts[4] += (int64_t)(wd.size() * sizeof(VarWindowDev) + (size_t)vp.n_alleles * sizeof(calitas_variant_allele) + (size_t)vp.n_sets * 4);
+    // ---- tasks: every guide against the windows of its class, guides in spans that keep a task list under 2^25 entries ---------------------------
+    const LaunchShape L = launch_shape(specs, 0, specs.size(), rw);
+    std::vector<ExplicitWindow> tasks;
+    const size_t TASK_SPAN = (size_t)1 << 25;
+    for (size_t g = 0; g < specs.size(); ++g) {
+      for (int64_t w = 0; w < n_w; ++w) {
+        const calitas_variant_window& v = vp.windows[w];
+        if (v.guide_class != vp.guide_class[g]) continue;
+        tasks.push_back(ExplicitWindow{ off[(size_t)w], v.length, 0, (int32_t)g, v.contig_idx, (int32_t)w, v.owned ? 1 : 0 });
+      }
+      if (tasks.size() >= TASK_SPAN || (g + 1 == specs.size() && !tasks.empty())) {
+        e->windows.ensure(tasks.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, tasks.data(), tasks.size() * sizeof(ExplicitWindow), s); dev::stream_sync(s);
+        counts[4] += (int64_t)(tasks.size() * sizeof(ExplicitWindow));
+        explicit_core(e, e->var_nib.as<uint32_t>(), total / 8, (int64_t)tasks.size(), max_len, L, false, &e->out_owned, n, ms, counts);
+        tasks.clear();
+      }
+    }
+  }
+  if (n == 0) return 0;
+  if (n >= (1ll << 32)) throw LimitExceeded("too many hits in one batch");
+  // ---- keys: sweep order = (guide, contig, variant set | start, strand, -score, arrival) via two stable sorts, minor key first ---------------------------
+  VarKeyLayout V; DedupLayout F;
+  {
+    uint32_t max_rank = 0; for (int64_t k = 0; k < vp.n_sets; ++k) max_rank = std::max(max_rank, vp.set_rank[k]);
+    int64_t max_clen = 1; for (int64_t l : ref->len) max_clen = std::max(max_clen, l);
+    V.set_bits = std::max(1, bit_length(max_rank)); V.contig_bits = std::max(1, bit_length((uint64_t)(ref->len.size() - 1))); V.start_bits = std::min(31, bit_length((uint64_t)max_clen));
+    score_bounds(specs, 0, specs.size(), e->sc, V.score_hi, V.score_bits);
+    const int guide_bits = std::max(1, bit_length((uint64_t)(specs.size() - 1)));
+    if (guide_bits + V.contig_bits + V.set_bits > 64 || V.start_bits + 1 + V.score_bits > 64) throw LimitExceeded("variant sort keys do not fit 64 bits");
+    F.start_bits = V.start_bits; F.contig_shift = F.start_bits + 1; F.guide_shift = F.contig_shift + V.contig_bits; F.g0 = 0; F.bits = F.guide_shift + guide_bits;
+    F.score_hi = V.score_hi; F.score_bits = V.score_bits; F.merged = 1;
+    if (F.bits + F.score_bits > 64) throw LimitExceeded("final sort key does not fit 64 bits");
+  }
+  const size_t nn = (size_t)n;
+  e->var_info.ensure(nn * sizeof(VarInfo)); e->vk1.ensure(nn * 8); e->vk2.ensure(nn * 8); e->vk3.ensure(nn * 8); e->vi1.ensure(nn * 4); e->vi2.ensure(nn * 4); e->vi3.ensure(nn * 4);
+  e->out_owned.ensure_keep(nn, nn, s);
+  uint32_t* d_overflow = (uint32_t*)(e->d_count + CNT_DEDUP_OVERFLOW);
+  const uint32_t* recs = e->out.as<uint32_t>();
+  uint64_t* major = e->vk1.as<uint64_t>(); uint64_t* minor = e->vk2.as<uint64_t>(); uint64_t* ktmp = e->vk3.as<uint64_t>();
+  uint32_t* i1 = e->vi1.as<uint32_t>(); uint32_t* i2 = e->vi2.as<uint32_t>(); uint32_t* i3 = e->vi3.as<uint32_t>();
+  CAL_LAUNCH(k_variant_keys, blocks_for(n, 256), 256, 0, s, 1, recs, rw, n_ref, n, e->var_windows.as<VarWindowDev>(), e->var_alleles.as<calitas_variant_allele>(), e->var_sets.as<uint32_t>(), V,
+             e->var_info.as<VarInfo>(), major, minor, i1, d_overflow); dev::launch_check("k_variant_keys"); ++e->launches;
+  size_t tb = dev::sort_pairs_u64_tmp(nn, 0, 64); e->tmp.ensure(tb);
+  dev::sort_pairs_u64(e->tmp.p, tb, minor, ktmp, i1, i2, nn, 0, V.start_bits + 1 + V.score_bits, s); ++e->launches;          // i2: merged-list index, in minor order
+  CAL_LAUNCH(k_gather_u64, blocks_for(n, 256), 256, 0, s, 1, major, i2, n, minor); dev::launch_check("k_gather_u64"); ++e->launches;                 // minor := major keys in minor order
+  const int guide_bits = F.bits - F.guide_shift;
+  dev::sort_pairs_u64(e->tmp.p, tb, minor, ktmp, i2, i3, nn, 0, guide_bits + V.contig_bits + V.set_bits, s); ++e->launches;  // ktmp: sorted major keys, i3: merged-list index
+  // ---- sweep ------------------------------------------------------------------------------------------------------------------------------------
+  e->sstart.ensure(nn * 4); e->send.ensure(nn * 4); e->sscore.ensure(nn * 4); e->sowned.ensure(nn); e->flag.ensure(nn * 4); e->pos.ensure(nn * 4);
+  CAL_LAUNCH(k_variant_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, recs, rw, e->var_info.as<VarInfo>(), e->out_owned.as<uint8_t>(), ktmp, i3, n, major,
+             e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_variant_sweep_prepare"); ++e->launches;
+  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, major, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, limits->max_overlap,
+             limits->max_overlap >= 1 ? 1 : 0, 0, 0, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
+  tb = dev::exclusive_sum_u32_tmp(nn); e->tmp.ensure(tb);
+  dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), nn, s); ++e->launches;
+  CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, e->pos.as<uint32_t>() + (n - 1), e->flag.as<uint32_t>() + (n - 1), (const unsigned long long*)nullptr, e->h_count_dev + CNT_KEEPERS); dev::launch_check("k_publish_sum");
+  dev::stream_sync(s);
+  const int64_t nk = (int64_t)((volatile unsigned long long*)e->h_count)[CNT_KEEPERS];
+  if (nk == 0) return 0;
+  // ---- final order: ReferenceHit.sort over the keepers, stable on the sweep order (variant set rank, then arrival) -----------------------------------
+  CAL_LAUNCH(k_variant_final_keys, blocks_for(n, 256), 256, 0, s, 1, recs, rw, e->var_info.as<VarInfo>(), i3, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), n, F, minor, i1, d_overflow); dev::launch_check("k_variant_final_keys"); ++e->launches;
+  tb = dev::sort_pairs_u64_tmp((size_t)nk, 0, 64); e->tmp.ensure(tb);
+  dev::sort_pairs_u64(e->tmp.p, tb, minor, ktmp, i1, i2, (size_t)nk, 0, F.bits + F.score_bits, s); ++e->launches;
+  e->out2.ensure((size_t)nk * rw * 4); e->var_info2.ensure((size_t)nk * sizeof(VarInfo));
+  CAL_LAUNCH(k_variant_gather, blocks_for(nk, 256), 256, 0, s, 1, recs, rw, e->var_info.as<VarInfo>(), i2, nk, e->out2.as<uint32_t>(), e->var_info2.as<VarInfo>()); dev::launch_check("k_variant_gather"); ++e->launches;
+  CAL_LAUNCH(k_publish_u64, 1, 1, 0, s, 1, e->d_count + CNT_DEDUP_OVERFLOW, e->h_count_dev + CNT_KEEPERS + 1); dev::launch_check("k_publish_u64");
+  dev::stream_sync(s);
+  if (((volatile unsigned long long*)e->h_count)[CNT_KEEPERS + 1]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in the variant merge");
+  return nk;
 }
 
 }  // namespace
@@ -1184,7 +1430,7 @@ int calitas_engine_create(int32_t device_id, const calitas_costs* costs, calitas
     dev::init(device_id);
     std::unique_ptr<calitas_engine> e(new calitas_engine());
     e->device = device_id; e->costs = c; e->sc = make_scores(c);
-    e->stream = dev::stream_create_prio(1); e->scan_stream = dev::stream_create_prio(0); e->copy_stream = dev::stream_create_prio(1);
+    e->stream = dev::stream_create_prio(1); e->scan_stream = dev::stream_create_prio(0); e->scan_stream2 = dev::stream_create_prio(0); e->pub_stream = dev::stream_create_prio(1); e->copy_stream = dev::stream_create_prio(1);
 #ifndef CAL_HOSTSIM
     // once, to the most any launch asks for (SCAN_SMEM_LIMIT): the attribute is per device and function, and engines of several host threads
     // share it — setting it per launch let one thread lower it under another's launch
@@ -1202,14 +1448,14 @@ void calitas_engine_destroy(calitas_engine* e) {
   if (!e) return;
   try {
     dev::set_device(e->device);
-    dev::stream_sync(e->scan_stream); dev::stream_sync(e->stream); dev::stream_sync(e->copy_stream);
+    dev::stream_sync(e->scan_stream); dev::stream_sync(e->scan_stream2); dev::stream_sync(e->pub_stream); dev::stream_sync(e->stream); dev::stream_sync(e->copy_stream);
     for (DBuf* b : { &e->cand_b, &e->cand_c, &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->out, &e->tmp, &e->key1, &e->keyA,
-                     &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp, &e->slot_owned, &e->sowned }) b->release();
+                     &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp, &e->slot_owned, &e->sowned, &e->out_owned, &e->var_windows, &e->var_alleles, &e->var_sets, &e->var_info, &e->var_info2, &e->var_nib, &e->var_raw, &e->out2, &e->vk1, &e->vk2, &e->vk3, &e->vi1, &e->vi2, &e->vi3 }) b->release();
     for (auto& p : e->pinned_pool) dev::free_host(p.p);
     dev::free_host(e->h_count); dev::free_(e->d_count);
     for (auto& ev : e->ev) dev::event_destroy(ev);
     for (auto& ce : e->chunk_ev) for (auto& ev : ce.ev) dev::event_destroy(ev);
-    dev::stream_destroy(e->stream); dev::stream_destroy(e->scan_stream); dev::stream_destroy(e->copy_stream);
+    dev::stream_destroy(e->stream); dev::stream_destroy(e->scan_stream); dev::stream_destroy(e->scan_stream2); dev::stream_destroy(e->pub_stream); dev::stream_destroy(e->copy_stream);
   } catch (...) {}
   delete e;
 }
@@ -1295,13 +1541,15 @@ void calitas_reference_free(calitas_engine* e, calitas_reference* r) {
 // One guide chunk of a search: consecutive guides sharing the raw guide length, hence the window tiling (SearchReference.scala:528-530).
 struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded; bool fast; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; KeyLayout key; DedupLayout dedup; };
 
-int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
-                   int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out) {
+static int search_impl(calitas_engine* e, const calitas_reference* ref_c, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
+                       int32_t window_size, const char* chrom, int32_t dedup, const VariantPlan* vp, calitas_hitset** out) {
   return guarded([&]() -> int {
     if (!e || !ref_c || !out) throw InvalidArgument("bad search arguments");
     *out = nullptr;
     calitas_reference* ref = const_cast<calitas_reference*>(ref_c);
-    dev::set_device(e->device); dev::Stream s = e->stream, ss = e->scan_stream, cs = e->copy_stream;
+    dev::set_device(e->device); dev::Stream s = e->stream, ss0 = e->scan_stream, cs = e->copy_stream;
+    const bool two_scan_streams = !std::getenv("CALITAS_ONE_SCAN_STREAM");
+    dev::Stream scan_streams[2] = { e->scan_stream, two_scan_streams ? e->scan_stream2 : e->scan_stream };
     std::vector<GuideDef> defs; std::vector<GuideSpec> specs = build_specs(e, n_guides, guides, limits, false, &defs);
     if (window_size <= 0 || (uint32_t)window_size > MAX_WINDOW_LEN) throw InvalidArgument("window size out of range");
     if (dedup && limits->max_overlap <= 0) {      // every later hit of a group then "overlaps" (>= 0): the sweep has unbounded reach, no halo makes a shard exact
@@ -1313,10 +1561,13 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     // ---- plan: guide chunks and their window tilings ---------------------------------------------------------------------------
     // measured on B200: chunks of 25-50 guides, or one tail per group of 4 chunks, shorten nothing at 1/8 genome scale (a tail that shares the SMs with
     // a scan kernel slows down in proportion to its work) and expose a longer last tail at full scale (-2 to -5 %)
-    const int G_CHUNK = 16;
+    std::vector<int> plan;                                      // guides per chunk, in order; the last entry repeats.  CALITAS_CHUNK_PLAN=24,24,16,8,4 overrides (A/B runs)
+    if (const char* pl = std::getenv("CALITAS_CHUNK_PLAN")) { for (const char* q = pl; *q;) { const int v = std::atoi(q); if (v > 0) plan.push_back(std::min(v, 64)); while (*q && *q != ',') ++q; if (*q) ++q; } }
+    if (plan.empty()) plan.push_back(16);
     std::vector<SearchChunk> chunks;
     for (int g0 = 0; g0 < n_guides;) {
       SearchChunk ch; ch.g0 = g0; ch.raw_len = (int)defs[(size_t)g0].raw.size();
+      const int G_CHUNK = plan[std::min(chunks.size(), plan.size() - 1)];
       int g1 = g0 + 1; while (g1 < n_guides && g1 - g0 < G_CHUNK && (int)defs[(size_t)g1].raw.size() == ch.raw_len) ++g1;
       ch.g1 = g1;
       const int overlap = ch.raw_len + limits->max_guide_diffs + limits->max_gaps_between_guide_and_pam - 1;
@@ -1340,20 +1591,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         int64_t max_len = 1; for (int64_t l : ref->len) max_len = std::max(max_len, l);
         D.start_bits = std::min(31, bit_length((uint64_t)max_len)); D.contig_shift = D.start_bits + 1;        // bit 0 = strand, then the start
         D.guide_shift = D.contig_shift + bit_length((uint64_t)(ref->len.size() - 1)); D.g0 = g0; D.bits = D.guide_shift + bit_length((uint64_t)(g1 - g0 - 1));
-        // a hit's score = guide alignment (min_score ... lp rows each worth at most a match or an inserted base) + PAM bases + offset * queryGap
-        int64_t hi = 0, lo = 0; bool first = true;
-        for (int g = g0; g < g1; ++g) {
-          const GuideSpec& sp = specs[(size_t)g];
-          int pam_len = 0; for (int k = 0; k < sp.n_pams; ++k) pam_len = std::max<int>(pam_len, sp.pam_len[k]);
-          const int64_t per_row = std::max<int64_t>(std::max<int64_t>(sc.match, sc.target_gap), 0), per_pam = std::max<int64_t>(iabs(sc.pam_match), iabs(sc.pam_mismatch));
-          const int64_t h = per_row * sp.lp + per_pam * pam_len + (int64_t)std::max(0, sp.g) * std::max<int64_t>(sc.query_gap, 0);
-          const int64_t l = (int64_t)sp.min_score - per_pam * pam_len - (int64_t)std::max(0, sp.g) * iabs(sc.query_gap);
-          if (first || h > hi) hi = h;
-          if (first || l < lo) lo = l;
-          first = false;
-        }
-        if (hi - lo >= (1ll << 31) || hi > 0x7FFFFFFFll || hi < -0x7FFFFFFFll) { D.score_hi = 0x7FFFFFFF; D.score_bits = 33; }   // 0x7FFFFFFF - score fits 33 bits for any int32 score
-        else { D.score_hi = (int32_t)hi; D.score_bits = std::max(1, bit_length((uint64_t)(hi - lo))); }
+        score_bounds(specs, (size_t)g0, (size_t)g1, sc, D.score_hi, D.score_bits);
         D.merged = (D.bits + D.score_bits <= 64 && !std::getenv("CALITAS_DEDUP_TWO_SORTS")) ? 1 : 0;      // the variable forces the wide-key path in tests
       }
       ch.bases = 0; for (size_t t = ch.t_begin; t < t_end; ++t) ch.bases += (int64_t)(ch.ts->tiles[t].nwin - 1) * ch.step + window_size;
@@ -1364,8 +1602,9 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     while (e->chunk_ev.size() < n_chunks) { ChunkEvents ce; for (auto& ev : ce.ev) ev = dev::event_create(); e->chunk_ev.push_back(ce); }
     e->launches = 0;
     dev::zero(e->d_count + CNT_DEDUP_OVERFLOW, 8, s);                         // field-overflow flag of k_dedup_keys
-    dev::event_record(e->ev[0], ss);
-    e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), ss);
+    dev::event_record(e->ev[0], ss0);
+    e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), ss0);
+    dev::event_record(e->ev[2], ss0); dev::stream_wait(scan_streams[1], e->ev[2]);      // the guide table is uploaded on the first scan stream
     double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     counts[4] = (int64_t)(specs.size() * sizeof(GuideSpec));
     { const calitas_reference::TileSet& ts = *chunks[0].ts; for (size_t c = 0; c < ts.contigs.size(); ++c) if (chrom_idx < 0 || (int)c == chrom_idx) counts[0] += ts.contigs[c].own_hi - ts.contigs[c].own_lo; }
@@ -1377,6 +1616,7 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     DBuf* cand_slot[N_SLOTS] = { &e->cand, &e->cand_b, &e->cand_c };
     auto launch_scan = [&](size_t c) {
       const SearchChunk& ch = chunks[c]; const int slot = (int)(c % N_SLOTS); ChunkEvents& ce = e->chunk_ev[c];
+      dev::Stream ss = scan_streams[c & 1];
       cand_slot[slot]->ensure(e->cand_cap_hint * 8);
       if (c >= (size_t)N_SLOTS) dev::stream_wait(ss, e->chunk_ev[c - N_SLOTS].ev[CE_SORTED]);       // the previous user of this candidate slot has been sorted away
       dev::zero(e->d_count + slot, 8, ss);
@@ -1390,12 +1630,16 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         counts[6] += 1; counts[7] += ch.bases;
       }
       dev::event_record(ce.ev[CE_SCAN_E], ss);
-      CAL_LAUNCH(k_publish_u64, 1, 1, 0, ss, 1, e->d_count + slot, e->h_count_dev + slot); dev::launch_check("k_publish_u64");
-      dev::event_record(ce.ev[CE_COUNT], ss);
+      // the count is published from a stream of its own with the greatest priority: on a scan stream the one-thread kernel would queue behind every
+      // pending block of the next chunk's scan (same priority, other stream) and the tail would start a whole scan late
+      dev::stream_wait(e->pub_stream, ce.ev[CE_SCAN_E]);
+      CAL_LAUNCH(k_publish_u64, 1, 1, 0, e->pub_stream, 1, e->d_count + slot, e->h_count_dev + slot); dev::launch_check("k_publish_u64");
+      dev::event_record(ce.ev[CE_COUNT], e->pub_stream);
     };
     int max_cols = 1; for (auto& sp : specs) max_cols = std::max(max_cols, sp.max_cols);
     const int rw = rec_words_for(max_cols); const size_t rec_bytes = (size_t)rw * 4;
     PinnedBuf pin = take_pinned(e, std::max<size_t>(e->out_hits_hint, 1024) * rec_bytes);
+    PinnedBuf var_info_pin;
     int64_t n_out = 0; size_t copies = 0;
     try {
       for (size_t c = 0; c < (size_t)(N_SLOTS - 1) && c < n_chunks; ++c) launch_scan(c);
@@ -1408,14 +1652,14 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
           n_cand = ((volatile unsigned long long*)e->h_count)[slot];
           if (n_cand <= e->cand_cap_hint) break;
           // pool too small: grow and re-run this chunk's scan (and the one queued behind it), never truncate
-          dev::stream_sync(ss);
+          dev::stream_sync(scan_streams[0]); dev::stream_sync(scan_streams[1]); dev::stream_sync(e->pub_stream);
           e->cand_cap_hint = (size_t)(n_cand + n_cand / 4);
           for (size_t r = c; r < c + N_SLOTS && r < n_chunks; ++r) { counts[6] -= chunks[r].n_tiles ? 1 : 0; counts[7] -= chunks[r].bases; launch_scan(r); }
         }
         counts[1] += (int64_t)n_cand;
         dev::event_record(ce.ev[CE_TAIL_B], s);
         Pipeline P{ e, cand_slot[slot]->as<uint64_t>(), ce.ev[CE_SORTED], ce.ev[CE_ALIGN_B], ce.ev[CE_ALIGN_E], e->specs.as<GuideSpec>(), ch.slots, false, ch.banded,
-                    ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, 0, dedup == 0, ch.key, rw, ch.fast, ref->total_padded / 8, dedup ? &ch.dedup : nullptr, limits->max_overlap };
+                    ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, dedup == 0 && !vp, ch.key, rw, ch.fast, ref->total_padded / 8, (dedup && !vp) ? &ch.dedup : nullptr, limits->max_overlap, vp ? &e->out_owned : nullptr };
         int64_t n_aln = 0;
         // room in e->out: what this chunk adds, and (when it has to grow) the rest of the call projected from the hits per guide so far
         const size_t projected = ch.g0 > 0 ? (size_t)((double)n_out * (double)n_guides / (double)ch.g0 * 1.15) + 4096 : e->out_hits_hint;
@@ -1425,7 +1669,8 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         // the finished segment goes to the host while later chunks compute
         dev::stream_wait(cs, ce.ev[CE_TAIL_E]);
         dev::event_record(ce.ev[CE_COPY_B], cs);
-        if (n_new) {
+        if (vp) n_out += n_new;                                    // with variant windows the hits stay on the device until the merge below
+        else if (n_new) {
           if ((size_t)(n_out + n_new) * rec_bytes > pin.cap) {
             dev::stream_sync(cs);
             // first call on this engine: size the result buffer once from the hits per guide seen so far (page-locking gigabytes is slow,
@@ -1441,16 +1686,33 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
         dev::event_record(ce.ev[CE_COPY_E], cs);
         ++copies;
       }
+      PinnedBuf info_pin;
+      if (vp) {        // variant windows: align, merge with the reference hits, removeOverlaps + sort, then one copy of records and annotations
+        dev::stream_sync(cs); dev::stream_sync(s);
+        n_out = merge_variant_hits(e, *vp, specs, limits, ref, rw, n_out, ms, counts);
+        if ((size_t)n_out * rec_bytes > pin.cap) { e->pinned_pool.push_back(pin); pin = take_pinned(e, (size_t)n_out * rec_bytes); }
+        info_pin = take_pinned(e, std::max<size_t>(1, (size_t)n_out) * sizeof(calitas_variant_hit_info));
+        dev::event_record(e->ev[6], s);
+        dev::d2h(pin.p, e->out2.p, (size_t)n_out * rec_bytes, s);
+        dev::d2h(info_pin.p, e->var_info2.p, (size_t)n_out * sizeof(calitas_variant_hit_info), s);
+        dev::event_record(e->ev[7], s);
+        dev::stream_wait(cs, e->ev[7]);
+        counts[5] += (int64_t)((size_t)n_out * sizeof(calitas_variant_hit_info));
+      }
+      var_info_pin = info_pin;
       dev::event_record(e->ev[1], cs);
-      dev::stream_sync(cs); dev::stream_sync(s); dev::stream_sync(ss);
+      dev::stream_sync(cs); dev::stream_sync(s); dev::stream_sync(scan_streams[0]); dev::stream_sync(scan_streams[1]); dev::stream_sync(e->pub_stream);
+      if (vp) ms[4] += dev::event_ms(e->ev[6], e->ev[7]);
     } catch (...) {
-      try { dev::stream_sync(ss); dev::stream_sync(s); dev::stream_sync(cs); } catch (...) {}
+      try { dev::stream_sync(scan_streams[0]); dev::stream_sync(scan_streams[1]); dev::stream_sync(e->pub_stream); dev::stream_sync(s); dev::stream_sync(cs); } catch (...) {}
       e->pinned_pool.push_back(pin);
       throw;
     }
+    double scan_until = 0;                                      // scans of consecutive chunks overlap at their ends (two scan streams): ms[1] is the union of the intervals
     for (size_t c = 0; c < n_chunks; ++c) {
       const ChunkEvents& ce = e->chunk_ev[c];
-      ms[1] += dev::event_ms(ce.ev[CE_SCAN_B], ce.ev[CE_SCAN_E]);
+      const double sb = std::max(scan_until, dev::event_ms(e->ev[0], ce.ev[CE_SCAN_B])), se = dev::event_ms(e->ev[0], ce.ev[CE_SCAN_E]);
+      if (se > sb) { ms[1] += se - sb; scan_until = se; }
       const double al = dev::event_ms(ce.ev[CE_ALIGN_B], ce.ev[CE_ALIGN_E]);
       ms[2] += al;
       ms[3] += dev::event_ms(ce.ev[CE_TAIL_B], ce.ev[CE_TAIL_E]) - al;
@@ -1469,14 +1731,27 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref_c, int32_t n_
     }
     ms[5] = ms[0] - ms[1];                                   // time of the call not hidden behind the scan kernels
     counts[3] = e->launches;
-    counts[5] = (int64_t)((size_t)n_out * rec_bytes);
+    counts[5] += (int64_t)((size_t)n_out * rec_bytes);
     e->out_hits_hint = std::max<size_t>(e->out_hits_hint, (size_t)n_out + (size_t)n_out / 8);
     std::unique_ptr<calitas_hitset> hs(new calitas_hitset());
-    hs->owner = e; hs->n = n_out; hs->buf = pin; hs->stride = (int32_t)rec_bytes;
+    hs->owner = e; hs->n = n_out; hs->buf = pin; hs->stride = (int32_t)rec_bytes; hs->info = var_info_pin;
     for (int i = 0; i < 8; ++i) { hs->ms[i] = ms[i]; hs->counts[i] = counts[i]; }
     *out = hs.release();
     return CALITAS_OK;
   });
+}
+
+int calitas_search(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
+                   int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out) {
+  return search_impl(e, ref, n_guides, guides, limits, window_size, chrom, dedup, nullptr, out);
+}
+
+int calitas_search_variants(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides, const int32_t* guide_class, const calitas_limits* limits,
+                            int32_t window_size, const char* chrom, int64_t n_windows, const calitas_variant_window* windows, int64_t n_alleles, const calitas_variant_allele* alleles,
+                            int64_t n_sets, const uint32_t* set_rank, calitas_hitset** out) {
+  if (n_windows < 0 || (n_windows && (!windows || !guide_class)) || n_alleles < 0 || (n_alleles && !alleles) || n_sets < 0 || (n_sets && !set_rank)) return set_error(CALITAS_EINVAL, "bad variant arguments");
+  VariantPlan vp{ n_windows, windows, guide_class, alleles, n_alleles, set_rank, n_sets };
+  return search_impl(e, ref, n_guides, guides, limits, window_size, chrom, 1, &vp, out);
 }
 
 int calitas_align_regions(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides, int64_t n_tasks,
@@ -1494,7 +1769,7 @@ int calitas_align_regions(calitas_engine* e, const calitas_reference* ref, int32
       const size_t c = (size_t)t.contig_idx;
       if (t.length < 0 || (uint32_t)t.length > MAX_WINDOW_LEN) throw InvalidArgument("region length out of range");
       if (t.start < ref->have_b[c] || t.start + t.length > ref->have_e[c]) throw InvalidArgument("region outside the loaded bases of contig " + ref->names[c]);
-      windows[(size_t)i] = ExplicitWindow{ ref->nib_off[c] - ref->have_b[c] + t.start, t.length, (int32_t)t.start, t.guide_idx, t.contig_idx };
+      windows[(size_t)i] = ExplicitWindow{ ref->nib_off[c] - ref->have_b[c] + t.start, t.length, (int32_t)t.start, t.guide_idx, t.contig_idx, (int32_t)i, 1 };
     }
     *out = run_explicit(e, ref->d_nib, ref->total_padded / 8, windows, specs);
     return CALITAS_OK;
@@ -1515,7 +1790,7 @@ int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_gui
       const calitas_target_task& t = tasks[i];
       if (t.guide_idx < 0 || t.guide_idx >= n_guides) throw InvalidArgument("task guide_idx out of range");
       if (t.length < 0 || (uint32_t)t.length > MAX_WINDOW_LEN || (t.length && !t.bases)) throw InvalidArgument("target length out of range");
-      windows[(size_t)i] = ExplicitWindow{ total, t.length, t.target_offset, t.guide_idx, -1 };
+      windows[(size_t)i] = ExplicitWindow{ total, t.length, t.target_offset, t.guide_idx, -1, (int32_t)i, 1 };
       total += (t.length + 7) / 8 * 8 + 8;
     }
     // targets are small: pack on the host into the same 4-bit code words the device packer produces
@@ -1553,7 +1828,8 @@ int calitas_microbench_int(calitas_engine* e, int32_t kind, double* tera_ops_per
 int64_t calitas_hitset_count(const calitas_hitset* h) { return h ? h->n : 0; }
 const calitas_hit* calitas_hitset_data(const calitas_hitset* h) { return h ? (const calitas_hit*)h->buf.p : nullptr; }
 int32_t calitas_hitset_stride(const calitas_hitset* h) { return h ? h->stride : CALITAS_HIT_WORDS * 4; }
-void calitas_hitset_free(calitas_hitset* h) { if (!h) return; if (h->owner) h->owner->pinned_pool.push_back(h->buf); delete h; }
+void calitas_hitset_free(calitas_hitset* h) { if (!h) return; if (h->owner) { h->owner->pinned_pool.push_back(h->buf); if (h->info.p) h->owner->pinned_pool.push_back(h->info); } delete h; }
+const calitas_variant_hit_info* calitas_hitset_variant_info(const calitas_hitset* h) { return h ? (const calitas_variant_hit_info*)h->info.p : nullptr; }
 int calitas_hitset_stats(const calitas_hitset* h, double ms[8], int64_t counts[8]) {
   if (!h) return set_error(CALITAS_EINVAL, "hitset is NULL");
   for (int i = 0; i < 8; ++i) { if (ms) ms[i] = h->ms[i]; if (counts) counts[i] = h->counts[i]; }

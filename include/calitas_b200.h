@@ -133,6 +133,36 @@ int calitas_shard_plan(int32_t n_contigs, const int64_t* lengths, int32_t shard,
 int calitas_search(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
                    const calitas_limits* limits, int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out);
 
+/* ---- SearchReference -v: reference windows and variant windows, merged on the device -------------------------------------------------------
+ * Replaces the variant loop of SearchReference.execute (SearchReference.scala:570-630) together with removeOverlaps + ReferenceHit.sort over the union
+ * of both hit lists (:641-648, 653-675).  The host builds the variant windows (VariantWindow / VariantSet, :101-400); the engine aligns every guide g
+ * against the windows w with windows[w].guide_class == guide_class[g] (windows depend on the guide only through its padding, :575), maps each hit back
+ * to reference coordinates (VariantWindow.refOffsetAtBaseOffset, :133-156), names the variant set it overlaps (ReferenceHit.scala:211) and
+ * de-duplicates per (guide, contig, strand, variant set).
+ *   alleles[]   the chosen allele of each variant of each window, windows refer to runs of it (position order);
+ *   set_rank[]  for a window with m alleles, set_rank[first_set + a*m - a*(a-1)/2 + (b-a-1)] names the variant set alleles[a..b) (0 <= a < b <= m): equal
+ *               sets carry equal values > 0, and the values order the groups the way the caller wants rows that tie on (contig, start, strand, score)
+ *               ordered (the reference's own order among such rows is a HashMap's);
+ *   owned = 0   marks a halo window of a sharded run: its hits take part in removeOverlaps and are never reported.
+ * The result set holds records in ReferenceHit.sort order per guide, and one calitas_variant_hit_info per record (calitas_hitset_variant_info):
+ * hits of variant windows keep window-relative offsets in the record (task_idx = window index) and carry the reference offsets here. */
+typedef struct calitas_variant_allele { int32_t pos /* 1-based POS */, ref_len, alt_len; } calitas_variant_allele;
+typedef struct calitas_variant_window {
+  const uint8_t* bases; int32_t length;     /* the window's bases with its alleles applied (upper case) */
+  int32_t contig_idx; int32_t ref_start;    /* 1-based reference position of the first base */
+  int32_t n_alleles; int32_t first_allele; int32_t first_set; int32_t guide_class; int32_t owned;
+} calitas_variant_window;
+typedef struct calitas_variant_hit_info {
+  int32_t window_idx;                        /* -1: hit of a reference window (offsets below = the record's) */
+  int32_t start_offset, end_offset, guide_start_offset, guide_end_offset;      /* reference coordinates (SearchReference.scala:615-620) */
+  int32_t set_rank;                          /* 0: the hit overlaps no variant of its window */
+} calitas_variant_hit_info;
+int calitas_search_variants(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides, const int32_t* guide_class,
+                            const calitas_limits* limits, int32_t window_size, const char* chrom,
+                            int64_t n_windows, const calitas_variant_window* windows, int64_t n_alleles, const calitas_variant_allele* alleles,
+                            int64_t n_sets, const uint32_t* set_rank, calitas_hitset** out);
+const calitas_variant_hit_info* calitas_hitset_variant_info(const calitas_hitset* h);   /* NULL unless the set came from calitas_search_variants */
+
 /* ---- AlignToReference / variant windows -----------------------------------------------------------------------
  * One SequentialGuideAligner.align per task (SequentialGuideAligner.scala:228), batched.  best != 0 applies the
  * alignBest/alignToRefBest limits per guide (SequentialGuideAligner.scala:336-343, 407-417: d = protospacer length,
