@@ -620,26 +620,33 @@ struct CanonArgs {
   const uint64_t* cand; int64_t n_cand; const GuideSpec* specs; int32_t slots; int32_t explicit_mode; const ExplicitWindow* windows;
   const CKey* ckeys; int32_t* rank; uint32_t* gbase; uint32_t* flag; uint8_t* slot_owned; int32_t drop_halo; KeyLayout key;
 };
-// One thread per candidate: it finds its group's extent among its neighbours' keys and decides its own slots (canon_slot_rank); results per slot:
-// rank (position in the group's kept list or -1), gbase (first slot of the group), flag (kept and reported), slot_owned.  The r-th kept alignment of
-// a group later goes to output position pos[gbase] + r (pos = exclusive scan of flag), i.e. groups in candidate order, retval order inside a group.
-// Groups of more than 32 slots are decided by their first candidate's thread alone (canon_group).
+// k_canon, two passes, one thread per candidate in both.
+// Pass 1 (k_canon): which alignments are kept.  Only alignments that overlap by more than max_overlap interact, and two alignments whose end columns
+// differ by at least max_cols - max_overlap cannot (an alignment has at most max_cols columns), so a thread looks no further than its CLUSTER: the run of
+// neighbouring candidates of its group whose end columns follow each other closer than that -- one site, a few adjacent end columns -- and decides its
+// own slots there (canon_slot_rank; clusters of more than 32 slots, i.e. tandem repeats, are decided by their first candidate's thread with canon_group).
+// Pass 2 (k_canon_rank): the position of every kept alignment in its GROUP's kept list (retval order: score desc, gapBases asc, arrival), by counting
+// the kept alignments of the group that sort before it.  Results per slot: flag (kept and reported), rank, gbase (first slot of the group), slot_owned;
+// the r-th kept alignment of a group later goes to output position pos[gbase] + r (pos = exclusive scan of flag).
 CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_cand) return;
-  const uint64_t grp = key_group(a.key, a.cand[i]);
-  int64_t i0 = i; while (i0 > 0 && key_group(a.key, a.cand[i0 - 1]) == grp) --i0;
-  int64_t i1 = i + 1; while (i1 < a.n_cand && key_group(a.key, a.cand[i1]) == grp) ++i1;
-  const int64_t base = i0 * a.slots; const int64_t n = (i1 - i0) * a.slots;
-  const int32_t gidx = a.explicit_mode ? a.windows[key_window(a.key, a.cand[i])].guide_idx : key_guide(a.key, a.cand[i]);
+  const uint64_t ck = a.cand[i]; const uint64_t grp = key_group(a.key, ck);
+  const int32_t gidx = a.explicit_mode ? a.windows[key_window(a.key, ck)].guide_idx : key_guide(a.key, ck);
   const int32_t max_total = a.specs[gidx].max_total_diffs, max_overlap = a.specs[gidx].max_overlap;
+  const int32_t reach = max_overlap < 0 ? 0x7FFFFFFF : a.specs[gidx].max_cols - max_overlap;   // end columns this far apart (or further) never overlap by more than max_overlap (a negative limit: even disjoint ones "overlap" by 0 > limit)
+  int64_t i0 = i; int32_t col = key_col(a.key, ck);
+  while (i0 > 0) { const uint64_t p = a.cand[i0 - 1]; if (key_group(a.key, p) != grp || col - key_col(a.key, p) >= reach) break; col = key_col(a.key, p); --i0; }
+  int64_t i1 = i + 1; col = key_col(a.key, ck);
+  while (i1 < a.n_cand) { const uint64_t p = a.cand[i1]; if (key_group(a.key, p) != grp || key_col(a.key, p) - col >= reach) break; col = key_col(a.key, p); ++i1; }
+  const int64_t base = i0 * a.slots; const int64_t n = (i1 - i0) * a.slots;
   const CKey* keys = a.ckeys + base;
   if (n > 32) {
     if (i != i0) return;
     canon_group(keys, a.rank + base, (int)n, max_total, max_overlap);
     for (int64_t k = 0; k < n; ++k) {
-      const int st = ck_state(keys[k]); const bool halo = st == 2;
-      a.gbase[base + k] = (uint32_t)base; a.slot_owned[base + k] = halo ? 0 : 1; a.flag[base + k] = (a.rank[base + k] >= 0 && !(halo && a.drop_halo)) ? 1u : 0u;
+      const bool halo = ck_state(keys[k]) == 2;
+      a.slot_owned[base + k] = halo ? 0 : 1; a.flag[base + k] = (a.rank[base + k] >= 0 && !(halo && a.drop_halo)) ? 1u : 0u;
     }
     return;
   }
@@ -647,7 +654,24 @@ CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
     const int k = (int)(i - i0) * a.slots + q; const int64_t s = base + k;
     const int st = ck_state(keys[k]); const bool halo = st == 2;
     const int r = st == 0 ? -1 : canon_slot_rank(keys, (int)n, k, max_total, max_overlap);
-    a.rank[s] = r; a.gbase[s] = (uint32_t)base; a.slot_owned[s] = halo ? 0 : 1; a.flag[s] = (r >= 0 && !(halo && a.drop_halo)) ? 1u : 0u;
+    a.slot_owned[s] = halo ? 0 : 1; a.flag[s] = (r >= 0 && !(halo && a.drop_halo)) ? 1u : 0u;
+  }
+}
+CAL_KERNEL __launch_bounds__(128) k_canon_rank(CanonArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_cand) return;
+  const uint64_t grp = key_group(a.key, a.cand[i]);
+  int64_t i0 = i; while (i0 > 0 && key_group(a.key, a.cand[i0 - 1]) == grp) --i0;
+  int64_t i1 = i + 1; while (i1 < a.n_cand && key_group(a.key, a.cand[i1]) == grp) ++i1;
+  const int64_t base = i0 * a.slots; const int64_t n = (i1 - i0) * a.slots;
+  for (int q = 0; q < a.slots; ++q) {
+    const int64_t k = (i - i0) * a.slots + q, s = base + k;
+    a.gbase[s] = (uint32_t)base;
+    if (!a.flag[s]) { a.rank[s] = -1; continue; }
+    const CKey me = a.ckeys[s];
+    int r = 0;
+    for (int64_t y = 0; y < n; ++y) if (y != k && a.flag[base + y] && ck_before(a.ckeys[base + y], (int)y, me, (int)k)) ++r;
+    a.rank[s] = r;
   }
 }
 #ifndef CAL_HOSTSIM
@@ -1136,7 +1160,10 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
     CAL_LAUNCH(k_canon_warp, (unsigned)dev::sm_count(e->device) * 16, 128, 0, s, 1, ca, e->idx.as<uint32_t>(), e->keyA.as<uint32_t>(), e->key1.as<uint32_t>()); dev::launch_check("k_canon_warp"); ++e->launches;
   } else
 #endif
-  { CAL_LAUNCH(k_canon, blocks_for(n_cand, 128), 128, 0, s, 1, ca); dev::launch_check("k_canon"); ++e->launches; }
+  {
+    CAL_LAUNCH(k_canon, blocks_for(n_cand, 128), 128, 0, s, 1, ca); dev::launch_check("k_canon"); ++e->launches;
+    CAL_LAUNCH(k_canon_rank, blocks_for(n_cand, 128), 128, 0, s, 1, ca); dev::launch_check("k_canon_rank"); ++e->launches;
+  }
   tb = dev::exclusive_sum_u32_tmp((size_t)n_slots); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)n_slots, s); ++e->launches;
   CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, e->pos.as<uint32_t>() + (n_slots - 1), e->flag.as<uint32_t>() + (n_slots - 1), (const unsigned long long*)nullptr, e->h_count_dev + CNT_KEPT); dev::launch_check("k_publish_sum");
@@ -1828,6 +1855,10 @@ int calitas_microbench_int(calitas_engine* e, int32_t kind, double* tera_ops_per
 int64_t calitas_hitset_count(const calitas_hitset* h) { return h ? h->n : 0; }
 const calitas_hit* calitas_hitset_data(const calitas_hitset* h) { return h ? (const calitas_hit*)h->buf.p : nullptr; }
 int32_t calitas_hitset_stride(const calitas_hitset* h) { return h ? h->stride : CALITAS_HIT_WORDS * 4; }
+int calitas_reference_own_range(const calitas_reference* r, int32_t contig, int64_t* own_begin, int64_t* own_end) {
+  if (!r || contig < 0 || contig >= (int32_t)r->len.size() || !own_begin || !own_end) return set_error(CALITAS_EINVAL, "bad arguments");
+  *own_begin = r->own_b[(size_t)contig]; *own_end = r->own_e[(size_t)contig]; return CALITAS_OK;
+}
 void calitas_hitset_free(calitas_hitset* h) { if (!h) return; if (h->owner) { h->owner->pinned_pool.push_back(h->buf); if (h->info.p) h->owner->pinned_pool.push_back(h->info); } delete h; }
 const calitas_variant_hit_info* calitas_hitset_variant_info(const calitas_hitset* h) { return h ? (const calitas_variant_hit_info*)h->info.p : nullptr; }
 int calitas_hitset_stats(const calitas_hitset* h, double ms[8], int64_t counts[8]) {

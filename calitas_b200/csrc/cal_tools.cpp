@@ -77,7 +77,7 @@ void sort_alignments(std::vector<HitX>& v) {
 }
 
 // ---- ReferenceHit rows (ReferenceHit.scala:99-132, 210-254) ----------------------------------------------------------------------
-struct VariantAllele { Str id; int pos; Str ref, alt; float af; };
+struct VariantAllele { Str id; int pos; Str ref, alt; float af; const void* rec = nullptr; int alt_idx = 0; /* the VCF record and which of its ALTs */ };
 Str variant_display(const VariantAllele& v) {   // SearchReference.scala:106-109
   char buf[64]; std::snprintf(buf, sizeof buf, "%.3f", (double)v.af);
   return (v.id.empty() ? Str(".") : v.id) + ":" + std::to_string(v.pos - 1) + ":" + v.ref + ">" + v.alt + ":" + buf;
@@ -171,17 +171,22 @@ void write_row(Str& out, const RowContext& cx, const RowConst& rc, const GuideDe
 }
 
 // ReferenceHit.sort order (ReferenceHit.scala:276-287) on hit records: contig, coordinate_start, strand ("+" < "-"), score descending.
-bool hit_sorts_before(const calitas_hit* a, const calitas_hit* b) {
-  const int ca = calitas_hit_contig_idx(a), cb = calitas_hit_contig_idx(b); if (ca != cb) return ca < cb;
-  const int sa = calitas_hit_guide_start_offset(a), sb = calitas_hit_guide_start_offset(b); if (sa != sb) return sa < sb;
-  const char ta = calitas_hit_strand(a), tb = calitas_hit_strand(b); if (ta != tb) return ta < tb;
-  return a->score > b->score;
+// A hit of one engine's result set: the record, its annotation when the set came from calitas_search_variants (else NULL), the engine.
+struct HitRef {
+  const calitas_hit* h; const calitas_variant_hit_info* v; int engine;
+  int gstart() const { return v ? v->guide_start_offset : calitas_hit_guide_start_offset(h); }       // reference coordinate (variant-window hits keep window offsets in the record)
+};
+bool hit_sorts_before(const HitRef& a, const HitRef& b) {
+  const int ca = calitas_hit_contig_idx(a.h), cb = calitas_hit_contig_idx(b.h); if (ca != cb) return ca < cb;
+  const int sa = a.gstart(), sb = b.gstart(); if (sa != sb) return sa < sb;
+  const char ta = calitas_hit_strand(a.h), tb = calitas_hit_strand(b.h); if (ta != tb) return ta < tb;
+  return a.h->score > b.h->score;
 }
 // order[0, seg) and order[seg, end) are each sorted (one guide's hits of the shards so far, and of the next shard).  Shards are ascending base
 // ranges, but consecutive windows overlap by guide length + d + g - 1 bases, so the last window of one shard and the first of the next can
 // report hits whose starts interleave (whenever removeOverlaps does not collapse them, e.g. a large -O).  Only that stretch is merged: stable,
 // the earlier shard first on equal keys, which is the single engine's arrival order.
-void merge_at_cut(std::vector<const calitas_hit*>& order, size_t seg) {
+void merge_at_cut(std::vector<HitRef>& order, size_t seg) {
   if (seg == 0 || seg >= order.size() || !hit_sorts_before(order[seg], order[seg - 1])) return;
   auto first = std::upper_bound(order.begin(), order.begin() + (long)seg, order[seg], hit_sorts_before);                 // prefix elements <= the segment's first stay put
   auto last = std::lower_bound(order.begin() + (long)seg, order.end(), order[seg - 1], hit_sorts_before);                // segment elements >= the prefix's last stay put
@@ -339,7 +344,7 @@ VariantWindow build_variant_window(const std::vector<const VcfRecord*>& vars, co
   for (size_t i = 0; i < vars.size(); ++i) {
     const VcfRecord* v = vars[i]; const int a = alleles[i];
     const float af = (v->has_af && a - 1 < (int)v->afs.size()) ? v->afs[(size_t)a - 1] : 0.0f;     // SearchReference.scala:199
-    w.alleles.push_back(VariantAllele{ v->id, v->pos, v->ref, v->alts[(size_t)a - 1], af });
+    w.alleles.push_back(VariantAllele{ v->id, v->pos, v->ref, v->alts[(size_t)a - 1], af, v, a - 1 });
   }
   for (size_t k = w.alleles.size(); k-- > 0;) {   // right to left (:270-279)
     const VariantAllele& a = w.alleles[k]; const size_t at = (size_t)(a.pos - ws);
@@ -442,6 +447,94 @@ Str render_rows(const std::vector<HitX>& hits, const GuideDef& gd, const Str& ch
   return text;
 }
 
+// ---- SearchReference -v on the device: what calitas_search_variants needs, built from the host-side variant windows -------------------------
+// Variant sets are named by numbers that are equal iff the sets are equal (all the device needs to group hits): a single allele gets
+// 1 + its index among all (record, ALT) pairs of the VCF, larger sets are interned.  The reference orders rows that tie on
+// (contig, start, strand, score) across variant groups by a HashMap; the oracle orders them by the group key's text: fix_variant_ties does that on the
+// few rows concerned instead of ranking millions of descriptions up front.
+struct VcfDevicePlan {
+  std::vector<VcfRecord> recs;
+  std::vector<std::vector<VariantWindow>> by_class;            // host windows per padding class
+  std::vector<int32_t> guide_class;
+  std::vector<const VariantWindow*> flat;                       // class-major
+  std::vector<int32_t> flat_class;
+  std::vector<calitas_variant_allele> alleles; std::vector<uint32_t> set_id;
+  std::vector<int32_t> first_allele, first_set;
+  std::vector<std::vector<calitas_variant_window>> eng_windows; std::vector<std::vector<int32_t>> eng_flat;     // per engine: the windows it processes, and their index in `flat`
+};
+extern "C" int calitas_reference_own_range(const calitas_reference* r, int32_t contig, int64_t* own_begin, int64_t* own_end);
+
+void build_vcf_device_plan(VcfDevicePlan& P, const calitas_genome_view& genome, const calitas_search_options& opt, const std::vector<GuideDef>& defs, int chrom_idx,
+                           int n_engines, const calitas_reference* const* refs) {
+  P.recs = parse_vcf(opt.vcf_text);
+  std::map<int, int> class_of_padding;
+  for (size_t g = 0; g < defs.size(); ++g) {
+    const int padding = defs[g].length() - 1 + opt.limits.max_guide_diffs + opt.limits.max_gaps_between_guide_and_pam;      // SearchReference.scala:575
+    auto it = class_of_padding.find(padding);
+    if (it == class_of_padding.end()) { it = class_of_padding.emplace(padding, (int)P.by_class.size()).first; P.by_class.push_back(variant_windows(genome, P.recs, chrom_idx, padding, opt.max_variants)); }
+    P.guide_class.push_back(it->second);
+  }
+  // allele numbers: index of the (record, ALT) pair in the VCF; the same pair in different windows is the same variant
+  std::vector<uint32_t> alt_base(P.recs.size() + 1, 0);
+  for (size_t r = 0; r < P.recs.size(); ++r) alt_base[r + 1] = alt_base[r] + (uint32_t)P.recs[r].alts.size();
+  const uint32_t n_single = alt_base.back();
+  std::map<std::vector<uint32_t>, uint32_t> set_no;
+  auto number_of = [&](int, const VariantAllele& a) -> uint32_t { return alt_base[(size_t)((const VcfRecord*)a.rec - P.recs.data())] + (uint32_t)a.alt_idx; };
+  for (size_t c = 0; c < P.by_class.size(); ++c) for (auto& w : P.by_class[c]) { P.flat.push_back(&w); P.flat_class.push_back((int32_t)c); }
+  std::vector<std::vector<uint32_t>> wnum(P.flat.size());
+  for (size_t i = 0; i < P.flat.size(); ++i) for (auto& a : P.flat[i]->alleles) wnum[i].push_back(number_of(P.flat[i]->contig, a));
+  for (size_t i = 0; i < P.flat.size(); ++i) {
+    const VariantWindow& w = *P.flat[i]; const int m = (int)w.alleles.size();
+    P.first_allele.push_back((int32_t)P.alleles.size()); P.first_set.push_back((int32_t)P.set_id.size());
+    for (auto& a : w.alleles) P.alleles.push_back(calitas_variant_allele{ a.pos, (int32_t)a.ref.size(), (int32_t)a.alt.size() });
+    for (int a = 0; a < m; ++a) for (int b = a + 1; b <= m; ++b) {
+      if (b - a == 1) { P.set_id.push_back(1u + wnum[i][(size_t)a]); continue; }
+      std::vector<uint32_t> key(wnum[i].begin() + a, wnum[i].begin() + b);
+      auto it = set_no.find(key); if (it == set_no.end()) it = set_no.emplace(std::move(key), (uint32_t)set_no.size()).first;
+      P.set_id.push_back(1u + n_single + it->second);
+    }
+  }
+  // per engine: the windows whose first base it owns, plus those within two reference windows of its cuts (halo: they take part in removeOverlaps there, too)
+  P.eng_windows.resize((size_t)n_engines); P.eng_flat.resize((size_t)n_engines);
+  const int64_t halo = 2 * (int64_t)opt.window_size;
+  for (int s = 0; s < n_engines; ++s) {
+    std::vector<int64_t> ob((size_t)genome.n_contigs), oe((size_t)genome.n_contigs);
+    for (int c = 0; c < genome.n_contigs; ++c) ck(calitas_reference_own_range(refs[s], c, &ob[(size_t)c], &oe[(size_t)c]));
+    for (size_t i = 0; i < P.flat.size(); ++i) {
+      const VariantWindow& w = *P.flat[i]; const int64_t st = w.start - 1; const int c = w.contig;
+      const bool owned = st >= ob[(size_t)c] && st < oe[(size_t)c];
+      const bool near = oe[(size_t)c] > ob[(size_t)c] && st >= ob[(size_t)c] - halo && st < oe[(size_t)c] + halo;
+      if (!owned && !near) continue;
+      P.eng_windows[(size_t)s].push_back(calitas_variant_window{ (const uint8_t*)w.bases.data(), (int32_t)w.bases.size(), c, w.start, (int32_t)w.alleles.size(), P.first_allele[i], P.first_set[i],
+                                                                  P.flat_class[i], owned ? 1 : 0 });
+      P.eng_flat[(size_t)s].push_back((int32_t)i);
+    }
+  }
+}
+
+// Flanks of a variant-window hit, taken from the window where it reaches far enough (SearchReference.scala:599-612); `h` holds window offsets.
+Flanks window_flanks(const VariantWindow& w, const HitX& h) {
+  const int wl = (int)w.bases.size();
+  Flanks raw;   // window-orientation flanks (:599-602)
+  if (h.guide_start_offset >= 10) { raw.has[0] = true; raw.v[0] = w.bases.substr((size_t)h.guide_start_offset - 10, 10); }
+  if (wl - h.guide_end_offset >= 10) { raw.has[1] = true; raw.v[1] = w.bases.substr((size_t)h.guide_end_offset, 10); }
+  if (h.start_offset >= 8) { raw.has[2] = true; raw.v[2] = w.bases.substr((size_t)h.start_offset - 8, 8); }
+  if (wl - h.end_offset >= 8) { raw.has[3] = true; raw.v[3] = w.bases.substr((size_t)h.end_offset, 8); }
+  Flanks fl = raw;
+  if (h.strand == '-') {   // :604-612
+    fl.has[0] = raw.has[1]; fl.v[0] = revcomp(raw.v[1]); fl.has[1] = raw.has[0]; fl.v[1] = revcomp(raw.v[0]);
+    fl.has[2] = raw.has[3]; fl.v[2] = revcomp(raw.v[3]); fl.has[3] = raw.has[2]; fl.v[3] = revcomp(raw.v[2]);
+  }
+  return fl;
+}
+
+// variant_description of the variants of `w` a hit with reference span [so, eo] overlaps (ReferenceHit.scala:211, 231)
+Str variant_description_of(const VariantWindow& w, int so, int eo) {
+  Str d; bool first = true;
+  for (auto& v : w.alleles) if (v.pos - 1 >= so && v.pos - 1 <= eo) { if (!first) d += ';'; d += variant_display(v); first = false; }
+  return d;
+}
+
 }  // namespace
 
 extern "C" {
@@ -511,10 +604,12 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
     if (n_engines <= 0 || !engines || !refs || !genome || n_guides <= 0 || !guides || !opt || (out_fd < 0 && !out_tsv)) bad("bad arguments");
     for (int s = 0; s < n_engines; ++s) if (!engines[s] || !refs[s]) bad("engine or reference is NULL");
     if (out_tsv) *out_tsv = nullptr;
-    // removeOverlaps + sort run on the device per engine, except (i) with a VCF, where variant-window hits join the same groups, and (ii) with
-    // -O <= 0 on several engines: every later hit of a group then "overlaps" (>= 0), the reference's sweep (SearchReference.scala:662-672) has
-    // unbounded reach, and no halo can make a shard's sweep see what it would need; both cases gather raw hits and de-duplicate on the host.
-    const bool host_dedup = opt->vcf_text != nullptr || (n_engines > 1 && opt->limits.max_overlap <= 0);
+    // removeOverlaps + sort run on the device per engine -- with a VCF too: the variant windows' hits join the reference hits' groups there
+    // (calitas_search_variants) -- except with -O <= 0 on several engines: every later hit of a group then "overlaps" (>= 0), the reference's sweep
+    // (SearchReference.scala:662-672) has unbounded reach, and no halo can make a shard's sweep see what it would need; that case gathers raw hits
+    // and de-duplicates on the host.
+    const bool host_dedup = n_engines > 1 && opt->limits.max_overlap <= 0;
+    const bool device_vcf = opt->vcf_text != nullptr && !host_dedup;      // variant windows are aligned, merged and de-duplicated by calitas_search_variants
     const bool stream = out_fd >= 0 && !host_dedup;
     int64_t streamed_bytes = 0;
     std::vector<GuideDef> defs; for (int g = 0; g < n_guides; ++g) defs.push_back(parse_guide(guides[g]));
@@ -547,8 +642,14 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
       // the first call's buffer set-up (page-locking the result buffer costs ~0.5 s per GB) shrinks with the batch and hides behind rendering,
       // and the pinned result memory is two batches instead of the whole run.  Other paths search all guides in one call.
       const int GUIDE_BATCH = stream ? 32 : n_guides;
+      VcfDevicePlan vplan;
+      if (device_vcf) { build_vcf_device_plan(vplan, *genome, *opt, defs, chrom_idx, n_engines, refs); pt.lap("vcf: parse, windows, variant sets"); }
       auto search_batch = [&](int g0, int g1, std::vector<HitSet>& into) {
-        run_all([&](int s) { ck(calitas_search(engines[s], refs[s], g1 - g0, guides + g0, &opt->limits, opt->window_size, opt->chrom, host_dedup ? 0 : 1, &into[(size_t)s].h)); });
+        run_all([&](int s) {
+          if (device_vcf) ck(calitas_search_variants(engines[s], refs[s], g1 - g0, guides + g0, vplan.guide_class.data() + g0, &opt->limits, opt->window_size, opt->chrom,
+                                                     (int64_t)vplan.eng_windows[(size_t)s].size(), vplan.eng_windows[(size_t)s].data(), (int64_t)vplan.alleles.size(), vplan.alleles.data(),
+                                                     (int64_t)vplan.set_id.size(), vplan.set_id.data(), &into[(size_t)s].h));
+          else ck(calitas_search(engines[s], refs[s], g1 - g0, guides + g0, &opt->limits, opt->window_size, opt->chrom, host_dedup ? 0 : 1, &into[(size_t)s].h)); });
       };
       std::vector<HitSet> hs((size_t)n_engines);
       search_batch(0, std::min(GUIDE_BATCH, n_guides), hs);
@@ -564,11 +665,27 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
         std::vector<int64_t> cursor((size_t)n_engines, 0);          // every hit set is guide-major; guide_idx counts from the batch's first guide
         const int rec_words = calitas_hitset_stride(hs[0].h) / 4;     // one record size per call: the same guides and limits went to every engine
         for (int g = g0; g < g1; ++g) {
-          std::vector<const calitas_hit*> order;                    // this guide's hits: shard 0's, then shard 1's, ... = ReferenceHit.sort order
+          std::vector<HitRef> order;                                // this guide's hits: shard 0's, then shard 1's, ... = ReferenceHit.sort order
           for (int s = 0; s < n_engines; ++s) {
             int64_t& i = cursor[(size_t)s]; const HitSet& h_ = hs[(size_t)s]; const size_t seg = order.size();
-            for (; i < h_.n() && calitas_hit_guide_idx(h_.at(i)) == g - g0; ++i) order.push_back(h_.at(i));
+            const calitas_variant_hit_info* vi = calitas_hitset_variant_info(h_.h);
+            for (; i < h_.n() && calitas_hit_guide_idx(h_.at(i)) == g - g0; ++i) order.push_back(HitRef{ h_.at(i), vi ? vi + i : nullptr, s });
             if (!host_dedup) merge_at_cut(order, seg);
+          }
+          // the host window behind a variant-window hit
+          auto window_of = [&](const HitRef& r) -> const VariantWindow& { return *vplan.flat[(size_t)vplan.eng_flat[(size_t)r.engine][(size_t)r.v->window_idx]]; };
+          if (device_vcf) {   // rows tying on (contig, start, strand, score) across variant groups: the oracle's order is the group key's text (see VcfDevicePlan)
+            for (size_t a = 0; a < order.size();) {
+              size_t b = a + 1; while (b < order.size() && !hit_sorts_before(order[a], order[b]) && !hit_sorts_before(order[b], order[a])) ++b;
+              bool mixed = false; for (size_t k = a + 1; k < b; ++k) if (order[k].v->set_rank != order[a].v->set_rank) mixed = true;
+              if (mixed) {
+                std::vector<std::pair<Str, HitRef>> run;
+                for (size_t k = a; k < b; ++k) run.emplace_back(order[k].v->window_idx >= 0 && order[k].v->set_rank ? variant_description_of(window_of(order[k]), order[k].v->start_offset, order[k].v->end_offset) : Str(), order[k]);
+                std::stable_sort(run.begin(), run.end(), [](const std::pair<Str, HitRef>& x, const std::pair<Str, HitRef>& y) { return x.first < y.first; });
+                for (size_t k = a; k < b; ++k) order[k] = run[k - a].second;
+              }
+              a = b;
+            }
           }
           const GuideDef& gd = defs[(size_t)g]; const RowContext& cx = cxs[(size_t)g]; const RowConst& rc = rcs[(size_t)g];
           // without a VCF the device has already de-duplicated and sorted: rows are final, rendered straight into text blocks of ROW_BLOCK rows
@@ -579,8 +696,15 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
             if (blk) blk->reserve((size_t)(e_ - b) * 640);
             RenderedFix r;
             for (int64_t k = b; k < e_; ++k) {
-              HitX h; unpack_hit(reinterpret_cast<const uint32_t*>(order[(size_t)k]), rec_words, h);
+              HitX h; unpack_hit(reinterpret_cast<const uint32_t*>(order[(size_t)k].h), rec_words, h);
               const Str& gt = guide_text_of(rc, h.pam_idx);
+              if (order[(size_t)k].v && order[(size_t)k].v->window_idx >= 0) {        // hit of a variant window (SearchReference.scala:596-622): bases and flanks come from the window
+                const calitas_variant_hit_info& v = *order[(size_t)k].v; const VariantWindow& w = window_of(order[(size_t)k]);
+                render_hit_fix(h, gt.data(), (int)gt.size(), w.bases.data() + h.start_offset, h.end_offset - h.start_offset, false, r);
+                const Row row = make_row(cx, rc, h, r, gd, w.contig, v.start_offset, v.end_offset, v.guide_start_offset, v.guide_end_offset, w.alleles, window_flanks(w, h));
+                if (blk) *blk += row.line; else out[(size_t)k] = row;
+                continue;
+              }
               render_hit_fix(h, gt.data(), (int)gt.size(), (const char*)genome->bases[h.contig_idx] + h.start_offset, h.end_offset - h.start_offset, true, r);   // windows are upper-cased, SearchReference.scala:67
               if (blk) write_row(*blk, cx, rc, gd, h, r, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, nullptr, none);
               else out[(size_t)k] = make_row(cx, rc, h, r, gd, h.contig_idx, h.start_offset, h.end_offset, h.guide_start_offset, h.guide_end_offset, {}, none);
@@ -602,7 +726,7 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
       }
       pt.lap("reference rows");
     }
-    if (with_vcf) {  // SearchReference.scala:570-630
+    if (with_vcf && host_dedup) {  // SearchReference.scala:570-630 on the host (several engines with -O <= 0)
       std::vector<VcfRecord> recs = parse_vcf(opt->vcf_text);
       pt.lap("parse vcf");
       // variant windows depend on the guide only through the padding (Guide.length, :575): build once per distinct padding
@@ -635,17 +759,7 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
             const HitX h = h_.x(i);
             const Str& gt = guide_text_of(rcs[(size_t)g], h.pam_idx);
             RenderedFix r; render_hit_fix(h, gt.data(), (int)gt.size(), w.bases.data() + h.start_offset, h.end_offset - h.start_offset, false, r);
-            const int wl = (int)w.bases.size();
-            Flanks raw;   // window-orientation flanks (:599-602)
-            if (h.guide_start_offset >= 10) { raw.has[0] = true; raw.v[0] = w.bases.substr((size_t)h.guide_start_offset - 10, 10); }
-            if (wl - h.guide_end_offset >= 10) { raw.has[1] = true; raw.v[1] = w.bases.substr((size_t)h.guide_end_offset, 10); }
-            if (h.start_offset >= 8) { raw.has[2] = true; raw.v[2] = w.bases.substr((size_t)h.start_offset - 8, 8); }
-            if (wl - h.end_offset >= 8) { raw.has[3] = true; raw.v[3] = w.bases.substr((size_t)h.end_offset, 8); }
-            Flanks fl = raw;
-            if (h.strand == '-') {   // :604-612
-              fl.has[0] = raw.has[1]; fl.v[0] = revcomp(raw.v[1]); fl.has[1] = raw.has[0]; fl.v[1] = revcomp(raw.v[0]);
-              fl.has[2] = raw.has[3]; fl.v[2] = revcomp(raw.v[3]); fl.has[3] = raw.has[2]; fl.v[3] = revcomp(raw.v[2]);
-            }
+            const Flanks fl = window_flanks(w, h);
             const int so = w.ref_offset_at(h.start_offset, true), eo = w.ref_offset_at(h.end_offset, false);             // :615-620
             const int gso = w.ref_offset_at(h.guide_start_offset, true), geo = w.ref_offset_at(h.guide_end_offset, false);
             rows[(size_t)g].push_back(make_row(cxs[(size_t)g], rcs[(size_t)g], h, r, gd, w.contig, so, eo, gso, geo, w.alleles, fl));

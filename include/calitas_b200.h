@@ -118,6 +118,8 @@ int calitas_reference_load(calitas_engine* e, int32_t n_contigs, const char* con
                            const uint8_t* const* bases, const int64_t* have_begin, const int64_t* have_end,
                            const int64_t* own_begin, const int64_t* own_end, int32_t keep_raw, calitas_reference** out);
 void calitas_reference_free(calitas_engine* e, calitas_reference* r);
+/* The window starts of contig `contig` this reference owns (the own_begin / own_end it was loaded with; the whole contig for an unsharded load). */
+int calitas_reference_own_range(const calitas_reference* r, int32_t contig, int64_t* own_begin, int64_t* own_end);
 /* Contiguous split of the genome into n_shards base ranges for contig-range sharding: fills, for `shard`,
  * own_begin/own_end per contig (window starts owned) and have_begin/have_end (bases needed, incl. a halo of `halo` bases). */
 int calitas_shard_plan(int32_t n_contigs, const int64_t* lengths, int32_t shard, int32_t n_shards, int64_t halo,
