@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--aux-pams", default=None, help="comma-separated auxiliary PAMs (BASELINE configs[3]: --pam ngg --aux-pams nag)")
     ap.add_argument("--tasks", type=int, default=None, help="config2: (guide, locus) pairs per step")
     ap.add_argument("--records", type=int, default=None, help="config5: VCF records genome-wide")
+    ap.add_argument("--one-process", action="store_true", help="search workloads: ONE process drives --gpus engines on host threads and ends with one merged table in its "
+                    "address space (calitas_search_sharded); not for torchrun launches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--lib", default=None, help="alternative build of libcalitas_b200.so (kernel A/B experiments); default = the product library")
@@ -519,6 +521,67 @@ def run_search(args, job):
     engine.close()
 
 
+def run_search_one_process(args):
+    """N engines in one process (what a JVM host would do, bindings/scala B200Search): the step ends with ONE table in this address space."""
+    import ctypes as C
+    import torch
+    from calitas_b200._capi import Engine, Library, Limits
+    w = args.w
+    N = args.gpus
+    if torch.cuda.device_count() < N:
+        raise SystemExit("--one-process --gpus %d needs %d visible devices" % (N, N))
+    guides = guide_list(w)
+    genome = make_genome(w, args.scale, guides)
+    n = len(genome.lengths)
+    lib = Library(os.path.abspath(args.lib)) if args.lib else None
+    engines = [Engine(d, lib=lib) for d in range(N)]
+    L = (C.c_int64 * n)(*genome.lengths)
+    refs = []
+    t0 = time.perf_counter()
+    for sidx, e in enumerate(engines):
+        ob, oe, hb, he = [(C.c_int64 * n)() for _ in range(4)]
+        e.lib.check(e.lib.L.calitas_shard_plan(n, L, sidx, N, C.c_int64(4000), ob, oe, hb, he))
+        arrays = [genome.range(c, hb[c], he[c]) if he[c] > hb[c] else None for c in range(n)]
+        refs.append(e.load_reference_ranges(genome.names, genome.lengths, [(hb[c], he[c]) for c in range(n)], [(ob[c], oe[c]) for c in range(n)], arrays))
+        del arrays
+    t_setup = time.perf_counter() - t0
+    lim = Limits(w["d"], w["p"], w["g"], -1, 10)
+    sampler = ClockSampler(range(N))
+    sampler.start()
+    stats = []
+    for it in range(args.warmup + args.steps):
+        for d in range(N):
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        hs = Engine.search_sharded(engines, refs, guides, lim, window_size=1000)
+        wall = time.perf_counter() - t0
+        st = hs.stats(); st["hits"] = len(hs); st["wall_ms"] = wall * 1e3
+        ms = (C.c_double * 8)(); cnt = (C.c_int64 * 8)()
+        hs.lib.check(hs.lib.L.calitas_hitset_stats(hs.ptr, ms, cnt))
+        st["merge_ms"] = ms[6]
+        hs.free()
+        if it >= args.warmup:
+            stats.append(st)
+    clocks = sampler.stop()
+    dev_ms = sum(s["ms_total"] for s in stats) / len(stats)
+    wall_ms = sum(s["wall_ms"] for s in stats) / len(stats)
+    bpg = genome.total() * len(guides)
+    out = {"metric": METRIC, "value": bpg / (dev_ms * 1e-3) / 1e9, "unit": "Gbp*guides/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": workload_config(args, genome, guides),
+           "e2e": {"value": bpg / (wall_ms * 1e-3) / 1e9, "unit": "Gbp*guides/s", "ms_per_step": wall_ms, "h2d_bytes_per_step": stats[-1]["h2d_bytes"], "d2h_bytes_per_step": stats[-1]["d2h_bytes"],
+                   "api": "calitas_search_sharded (C ABI), ONE process, %d engines on host threads: guide strings in -> ONE merged, sorted table of hit records in this process's pinned memory" % N,
+                   "merge_ms": sum(s["merge_ms"] for s in stats) / len(stats)},
+           "gpu_launches": int(sum(s["launches"] for s in stats)), "clocks": clocks,
+           "breakdown_ms": {"device_max_over_engines": dev_ms, "host_merge": sum(s["merge_ms"] for s in stats) / len(stats), "wall": wall_ms},
+           "counts": {"hits": stats[-1]["hits"], "candidates": stats[-1]["candidates"]}, "setup_s": {"generate_and_load_all_shards": t_setup}}
+    out["config"]["parallelism"] = "one process, %d engines (one per GPU) on host threads, contig-range shards, host-side merge at the cuts" % N
+    print(json.dumps(out))
+    for r in refs:
+        r.free()
+    for e in engines:
+        e.close()
+
+
 # ------------------------------------------------------------------------------------------------------------------------------------------
 # config2: AlignToReference batch
 # ------------------------------------------------------------------------------------------------------------------------------------------
@@ -658,6 +721,11 @@ def main():
         return
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"          # the version banner would land on stdout next to the one JSON line
+    if args.one_process:
+        if world > 1 or args.w["kind"] != "search":
+            raise SystemExit("--one-process is a single-process mode of the search workloads")
+        run_search_one_process(args)
+        return
     job = Job(args)
     if os.environ.get("CALITAS_BENCH_VERBOSE"):
         print("[bench] rank %d cpus %s" % (rank, sorted(os.sched_getaffinity(0))), file=sys.stderr)

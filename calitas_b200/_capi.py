@@ -125,11 +125,12 @@ class A2ROptions(C.Structure):
 EXPORTS = [
     # include/calitas_b200.h
     "calitas_engine_create", "calitas_engine_destroy", "calitas_engine_get_costs", "calitas_last_error", "calitas_reference_load", "calitas_reference_free", "calitas_reference_own_range",
-    "calitas_shard_plan", "calitas_search", "calitas_search_variants", "calitas_hitset_variant_info", "calitas_align_regions", "calitas_align_targets", "calitas_hitset_count", "calitas_hitset_data", "calitas_hitset_stride",
+    "calitas_shard_plan", "calitas_search", "calitas_search_sharded", "calitas_search_variants", "calitas_hitset_variant_info", "calitas_align_regions", "calitas_align_targets", "calitas_hitset_count", "calitas_hitset_data", "calitas_hitset_stride",
     "calitas_hitset_free", "calitas_hitset_stats", "calitas_render_alignments", "calitas_free_text", "calitas_microbench_int",
     # include/calitas_b200_tools.h
     "calitas_tool_align", "calitas_tool_align_best", "calitas_tool_align_to_ref", "calitas_tool_search_reference", "calitas_tool_search_reference_batch", "calitas_tool_search_reference_batch_fd", "calitas_tool_align_to_reference",
-    "calitas_tool_variant_windows", "calitas_tool_pairwise_align",
+    "calitas_tool_variant_windows", "calitas_tool_pairwise_align", "calitas_tool_variant_plan_create", "calitas_tool_variant_plan_free", "calitas_tool_variant_plan_counts",
+    "calitas_tool_variant_plan_search",
 ]
 
 
@@ -155,6 +156,9 @@ class Library:
         L.calitas_hitset_data.restype = C.c_void_p
         L.calitas_hitset_data.argtypes = [C.c_void_p]
         L.calitas_hitset_stride.restype = C.c_int32
+        L.calitas_hitset_variant_info.restype = C.c_void_p
+        L.calitas_hitset_variant_info.argtypes = [C.c_void_p]
+        L.calitas_tool_variant_plan_free.argtypes = [C.c_void_p]
         L.calitas_hitset_stride.argtypes = [C.c_void_p]
         L.calitas_hitset_free.argtypes = [C.c_void_p]
         L.calitas_hitset_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -354,6 +358,19 @@ class Engine:
         p = C.c_void_p()
         self.lib.check(self.lib.L.calitas_search(self.ptr, ref.ptr, len(guides), arr, C.byref(lim), window_size, _b(chrom), 1 if dedup else 0, C.byref(p)))
         return HitSet(self.lib, p)
+
+    @staticmethod
+    def search_sharded(engines, refs, guides, limits, window_size=1000, chrom=None):
+        """calitas_search_sharded: engines[s] holds shard s in refs[s]; returns ONE merged hit set (owned by engines[0])."""
+        lib = engines[0].lib
+        arr, keep = make_guides(guides)
+        lim = limits if isinstance(limits, Limits) else Limits(*limits)
+        n = len(engines)
+        e_arr = (C.c_void_p * n)(*[e.ptr for e in engines])
+        r_arr = (C.c_void_p * n)(*[r.ptr for r in refs])
+        p = C.c_void_p()
+        lib.check(lib.L.calitas_search_sharded(n, e_arr, r_arr, len(guides), arr, C.byref(lim), window_size, _b(chrom), C.byref(p)))
+        return HitSet(lib, p)
 
     def align_targets(self, guides, tasks, limits, best=False):
         """tasks: [(guide_idx, bases, target_offset)]"""

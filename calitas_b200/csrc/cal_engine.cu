@@ -11,6 +11,9 @@
 //   dedup          removeOverlaps + ReferenceHit.sort: radix sorts + per-(guide, contig, strand) sweep
 // AlignToReference / variant windows use k_scan_explicit (one thread per window and strand) and the same tail.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -1779,6 +1782,99 @@ int calitas_search_variants(calitas_engine* e, const calitas_reference* ref, int
   if (n_windows < 0 || (n_windows && (!windows || !guide_class)) || n_alleles < 0 || (n_alleles && !alleles) || n_sets < 0 || (n_sets && !set_rank)) return set_error(CALITAS_EINVAL, "bad variant arguments");
   VariantPlan vp{ n_windows, windows, guide_class, alleles, n_alleles, set_rank, n_sets };
   return search_impl(e, ref, n_guides, guides, limits, window_size, chrom, 1, &vp, out);
+}
+
+// One table in one address space from N engines (one per GPU, each holding shard s of calitas_shard_plan): the engines search concurrently on host
+// threads; per guide the shards' lists (each in ReferenceHit.sort order, ascending base ranges) are concatenated and merged where they meet -- consecutive
+// windows overlap by guide length + d + g - 1 bases, so the last window of one shard and the first of the next can report hits whose starts interleave --
+// stably, the earlier shard first on equal keys (the single engine's arrival order).
+}  // extern "C"
+namespace {
+template <int RW> struct RecN { uint32_t w[RW]; };
+template <int RW> bool rec_sorts_before(const RecN<RW>& a, const RecN<RW>& b) {      // ReferenceHit.sort (ReferenceHit.scala:276-287): contig, coordinate_start, strand, -score
+  const int ca = rec_contig(a.w), cb = rec_contig(b.w); if (ca != cb) return ca < cb;
+  const int sa = rec_gstart(a.w), sb = rec_gstart(b.w); if (sa != sb) return sa < sb;
+  if (rec_neg(a.w) != rec_neg(b.w)) return rec_neg(a.w) < rec_neg(b.w);
+  return rec_score(a.w) > rec_score(b.w);
+}
+template <int RW> void merge_guide_segments(RecN<RW>* out, const std::vector<std::pair<const RecN<RW>*, int64_t>>& segs) {
+  int64_t n = 0;
+  for (auto& sg : segs) {
+    if (sg.second == 0) continue;
+    std::memcpy(out + n, sg.first, (size_t)sg.second * sizeof(RecN<RW>));
+    const int64_t seg = n; n += sg.second;
+    if (seg == 0 || !rec_sorts_before<RW>(out[seg], out[seg - 1])) continue;
+    RecN<RW>* first = std::upper_bound(out, out + seg, out[seg], rec_sorts_before<RW>);               // prefix elements <= the segment's first stay put
+    RecN<RW>* last = std::lower_bound(out + seg, out + n, out[seg - 1], rec_sorts_before<RW>);          // segment elements >= the prefix's last stay put
+    std::inplace_merge(first, out + seg, last, rec_sorts_before<RW>);
+  }
+}
+}  // namespace
+extern "C" {
+
+int calitas_search_sharded(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, int32_t n_guides, const calitas_guide* guides,
+                           const calitas_limits* limits, int32_t window_size, const char* chrom, calitas_hitset** out) {
+  if (n_engines <= 0 || !engines || !refs || !out) return set_error(CALITAS_EINVAL, "bad arguments");
+  if (n_engines == 1) return search_impl(engines[0], refs[0], n_guides, guides, limits, window_size, chrom, 1, nullptr, out);
+  *out = nullptr;
+  std::vector<calitas_hitset*> hs((size_t)n_engines, nullptr); std::vector<int> rc((size_t)n_engines, CALITAS_OK); std::vector<std::string> msg((size_t)n_engines);
+  {
+    std::vector<std::thread> th;
+    for (int s = 0; s < n_engines; ++s) th.emplace_back([&, s]() {
+      rc[(size_t)s] = search_impl(engines[s], refs[s], n_guides, guides, limits, window_size, chrom, 1, nullptr, &hs[(size_t)s]);
+      if (rc[(size_t)s] != CALITAS_OK) msg[(size_t)s] = g_last_error; });
+    for (auto& t : th) t.join();
+  }
+  auto free_all = [&] { for (auto* h : hs) calitas_hitset_free(h); };
+  for (int s = 0; s < n_engines; ++s) if (rc[(size_t)s] != CALITAS_OK) { free_all(); return set_error(rc[(size_t)s], msg[(size_t)s]); }
+  return guarded([&]() -> int {
+    const auto t0 = std::chrono::steady_clock::now();
+    const int stride = hs[0]->stride; const int rw = stride / 4;
+    for (auto* h : hs) if (h->stride != stride) { free_all(); throw std::runtime_error("engines returned different record sizes"); }
+    // per engine and guide: where the guide's records begin (every list is guide-major)
+    std::vector<std::vector<int64_t>> begin((size_t)n_engines, std::vector<int64_t>((size_t)n_guides + 1, 0));
+    int64_t total = 0;
+    for (int s = 0; s < n_engines; ++s) {
+      const char* base = (const char*)hs[(size_t)s]->buf.p; const int64_t n = hs[(size_t)s]->n; int64_t i = 0;
+      for (int g = 0; g < n_guides; ++g) {
+        begin[(size_t)s][(size_t)g] = i;
+        int64_t lo = i, hi = n;                         // first record with guide_idx > g
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rec_guide((const uint32_t*)(base + (size_t)mid * stride)) <= g) lo = mid + 1; else hi = mid; }
+        i = lo;
+      }
+      begin[(size_t)s][(size_t)n_guides] = i; total += n;
+      if (i != n) { free_all(); throw std::runtime_error("hit set is not guide-major"); }
+    }
+    std::vector<int64_t> at((size_t)n_guides + 1, 0);
+    for (int g = 0; g < n_guides; ++g) { int64_t c = 0; for (int s = 0; s < n_engines; ++s) c += begin[(size_t)s][(size_t)g + 1] - begin[(size_t)s][(size_t)g]; at[(size_t)g + 1] = at[(size_t)g] + c; }
+    calitas_engine* e0 = engines[0]; dev::set_device(e0->device);
+    PinnedBuf pin = take_pinned(e0, (size_t)std::max<int64_t>(1, total) * stride);
+    // guides are independent: merged on host threads
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_guides, std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()))));
+    std::atomic<int> next(0); std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back([&]() {
+      for (;;) {
+        const int g = next.fetch_add(1); if (g >= n_guides) return;
+        char* dst = (char*)pin.p + (size_t)at[(size_t)g] * stride;
+        if (rw == CALITAS_HIT_WORDS) {
+          std::vector<std::pair<const RecN<CALITAS_HIT_WORDS>*, int64_t>> segs;
+          for (int s = 0; s < n_engines; ++s) segs.emplace_back((const RecN<CALITAS_HIT_WORDS>*)((const char*)hs[(size_t)s]->buf.p + (size_t)begin[(size_t)s][(size_t)g] * stride), begin[(size_t)s][(size_t)g + 1] - begin[(size_t)s][(size_t)g]);
+          merge_guide_segments<CALITAS_HIT_WORDS>((RecN<CALITAS_HIT_WORDS>*)dst, segs);
+        } else {
+          std::vector<std::pair<const RecN<CALITAS_HIT_WIDE_WORDS>*, int64_t>> segs;
+          for (int s = 0; s < n_engines; ++s) segs.emplace_back((const RecN<CALITAS_HIT_WIDE_WORDS>*)((const char*)hs[(size_t)s]->buf.p + (size_t)begin[(size_t)s][(size_t)g] * stride), begin[(size_t)s][(size_t)g + 1] - begin[(size_t)s][(size_t)g]);
+          merge_guide_segments<CALITAS_HIT_WIDE_WORDS>((RecN<CALITAS_HIT_WIDE_WORDS>*)dst, segs);
+        }
+      } });
+    for (auto& t : th) t.join();
+    std::unique_ptr<calitas_hitset> m(new calitas_hitset());
+    m->owner = e0; m->n = total; m->buf = pin; m->stride = stride;
+    for (int s = 0; s < n_engines; ++s) { for (int k = 0; k < 8; ++k) { m->ms[k] = std::max(m->ms[k], hs[(size_t)s]->ms[k]); m->counts[k] += hs[(size_t)s]->counts[k]; } }
+    m->ms[6] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();      // host-side merge into one table
+    free_all();
+    *out = m.release();
+    return CALITAS_OK;
+  });
 }
 
 int calitas_align_regions(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides, int64_t n_tasks,

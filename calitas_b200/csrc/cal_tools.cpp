@@ -11,6 +11,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -917,6 +918,39 @@ int calitas_tool_pairwise_align(calitas_engine* e, int64_t n_pairs, const char* 
     *out_tsv = dup_text(text);
     return CALITAS_OK;
   });
+}
+
+// ---- the variant plan as an object: built once per (VCF, guide batch, engines), searched any number of times ---------------------------------------
+struct calitas_variant_plan { VcfDevicePlan plan; std::vector<GuideDef> defs; };
+
+int calitas_tool_variant_plan_create(const calitas_genome_view* genome, const calitas_search_options* opt, int32_t n_guides, const calitas_guide* guides,
+                                     int32_t n_engines, const calitas_reference* const* refs, calitas_variant_plan** out) {
+  return guarded([&]() -> int {
+    if (!genome || !opt || !opt->vcf_text || n_guides <= 0 || !guides || n_engines <= 0 || !refs || !out) bad("bad arguments");
+    *out = nullptr;
+    std::unique_ptr<calitas_variant_plan> p(new calitas_variant_plan());
+    for (int g = 0; g < n_guides; ++g) p->defs.push_back(parse_guide(guides[g]));
+    int chrom_idx = -1; if (opt->chrom && opt->chrom[0]) { chrom_idx = contig_index(*genome, opt->chrom); if (chrom_idx < 0) bad(Str("Unknown chromosome: ") + opt->chrom); }
+    build_vcf_device_plan(p->plan, *genome, *opt, p->defs, chrom_idx, n_engines, refs);
+    *out = p.release();
+    return CALITAS_OK;
+  });
+}
+void calitas_tool_variant_plan_free(calitas_variant_plan* p) { delete p; }
+int calitas_tool_variant_plan_counts(const calitas_variant_plan* p, int32_t engine, int64_t* n_records, int64_t* n_windows, int64_t* n_window_bases) {
+  if (!p || engine < 0 || engine >= (int32_t)p->plan.eng_windows.size()) return calitas_tools_set_error(CALITAS_EINVAL, "bad arguments");
+  if (n_records) *n_records = (int64_t)p->plan.recs.size();
+  if (n_windows) *n_windows = (int64_t)p->plan.eng_windows[(size_t)engine].size();
+  if (n_window_bases) { int64_t b = 0; for (auto& w : p->plan.eng_windows[(size_t)engine]) b += w.length; *n_window_bases = b; }
+  return CALITAS_OK;
+}
+// calitas_search_variants for engine `engine` of the plan (the guides must be the ones the plan was built for)
+int calitas_tool_variant_plan_search(const calitas_variant_plan* p, int32_t engine, calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
+                                     const calitas_limits* limits, int32_t window_size, const char* chrom, calitas_hitset** out) {
+  if (!p || engine < 0 || engine >= (int32_t)p->plan.eng_windows.size() || n_guides != (int32_t)p->plan.guide_class.size()) return calitas_tools_set_error(CALITAS_EINVAL, "bad arguments");
+  const VcfDevicePlan& P = p->plan;
+  return calitas_search_variants(e, ref, n_guides, guides, P.guide_class.data(), limits, window_size, chrom, (int64_t)P.eng_windows[(size_t)engine].size(), P.eng_windows[(size_t)engine].data(),
+                                 (int64_t)P.alleles.size(), P.alleles.data(), (int64_t)P.set_id.size(), P.set_id.data(), out);
 }
 
 int calitas_tool_variant_windows(const calitas_genome_view* genome, const char* vcf_text, const char* chrom, int32_t padding, int32_t max_variants, char** out_text) {

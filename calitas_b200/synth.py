@@ -226,3 +226,57 @@ def synthetic_vcf(genome, contig_bases, n_records, seed=20260104, cluster_fracti
             rid += 1
             lines.append("\t".join([genome.names[c], str(p), "rs%d" % rid, ref, ",".join(alt), ".", "PASS", "AF=" + afs]))
     return "\n".join(lines) + "\n"
+
+
+def synthetic_vcf_fast(genome, arrays, ranges, n_records, seed=20260104, cluster_fraction=0.05):
+    """The shape of synthetic_vcf (BASELINE configs[4]) for millions of records: positions and alleles are drawn with numpy, only the text is built in a
+    Python loop.  arrays[c] holds bases [ranges[c][0], ranges[c][1]) of contig c (None / empty range: no records there); n_records counts the WHOLE genome,
+    each contig range gets its share.  85 % SNPs, 7.5 % insertions, 7.5 % deletions (1-10 bp), ~2 % multi-allelic SNPs, ~5 % of records inside 30-bp clusters."""
+    total = float(genome.total())
+    lines = ["##fileformat=VCFv4.2", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO"]
+    rid = 0
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    code = np.full(256, 255, dtype=np.uint8)
+    for i, b in enumerate(b"ACGT"):
+        code[b] = i
+    for c, (lo, hi) in enumerate(ranges):
+        a = arrays[c]
+        if a is None or hi - lo < 200:
+            continue
+        rng = np.random.default_rng([seed, c, int(lo)])
+        n = max(1, int(round(n_records * (hi - lo) / total)))
+        pos = rng.integers(lo + 20, hi - 40, size=int(n * (1 - cluster_fraction)) + 1)           # 1-based POS = 0-based index + 1 below
+        k = int(n * cluster_fraction)
+        if k:
+            seeds = rng.choice(pos, size=max(1, k // 3))
+            pos = np.concatenate([pos, np.repeat(seeds, 3)[:k] + rng.integers(1, 30, size=min(k, 3 * len(seeds)))])
+        pos = np.unique(np.clip(pos, lo + 20, hi - 41))
+        ref_code = code[a[pos - lo]]                                                              # base at 0-based index pos (POS = pos + 1)
+        pos = pos[ref_code < 4]; ref_code = ref_code[ref_code < 4]
+        m = pos.size
+        kind = rng.random(m)
+        alt1 = (ref_code + rng.integers(1, 4, size=m)) % 4
+        alt2 = (ref_code + 1 + (alt1 - ref_code) % 4 % 3) % 4                                       # a second, different ALT for the multi-allelic SNPs
+        multi = rng.random(m) < 0.02
+        ins_len = rng.integers(1, 11, size=m)
+        ins_bases = acgt[rng.integers(0, 4, size=(m, 10))]
+        del_len = rng.integers(1, 11, size=m)
+        af = np.maximum(0.01, rng.random((m, 2)) ** 3)
+        name = genome.names[c]
+        for j in range(m):
+            p = int(pos[j]); r1 = "ACGT"[ref_code[j]]
+            if kind[j] < 0.85:
+                if multi[j] and alt2[j] != alt1[j] and alt2[j] != ref_code[j]:
+                    ref, alt, afs = r1, "ACGT"[alt1[j]] + "," + "ACGT"[alt2[j]], "%.4g,%.4g" % (af[j, 0], af[j, 1])
+                else:
+                    ref, alt, afs = r1, "ACGT"[alt1[j]], "%.4g" % af[j, 0]
+            elif kind[j] < 0.925:
+                ref, alt, afs = r1, r1 + ins_bases[j, :ins_len[j]].tobytes().decode(), "%.4g" % af[j, 0]
+            else:
+                seg = a[p - lo:p - lo + del_len[j] + 1].tobytes()
+                if b"N" in seg or len(seg) < del_len[j] + 1:
+                    continue
+                ref, alt, afs = seg.decode(), r1, "%.4g" % af[j, 0]
+            rid += 1
+            lines.append("%s\t%d\trs%d\t%s\t%s\t.\tPASS\tAF=%s" % (name, p + 1, rid, ref, alt, afs))
+    return "\n".join(lines) + "\n"

@@ -57,7 +57,7 @@ class Facade:
         return _table(self._text(out), _INT_GA)[0]
 
     def _ref(self, e, contigs):
-        key = (id(e), tuple((c[0], len(c[1]), hash(c[1])) for c in contigs))
+        key = (id(e), tuple((c[0], len(c[1]), c[1].ctypes.data if hasattr(c[1], "ctypes") else hash(c[1])) for c in contigs))
         cache = self.__dict__.setdefault("_refs", {})
         if key not in cache:
             if len(cache) > 8:

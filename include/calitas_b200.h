@@ -135,6 +135,14 @@ int calitas_shard_plan(int32_t n_contigs, const int64_t* lengths, int32_t shard,
 int calitas_search(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
                    const calitas_limits* limits, int32_t window_size, const char* chrom, int32_t dedup, calitas_hitset** out);
 
+/* The same over n_engines engines (one per GPU; engine s holds shard s of calitas_shard_plan(.., s, n_engines, ..) in refs[s]), ending with ONE table in
+ * one address space, as SearchReference.execute does (SearchReference.scala:641-648): the engines run concurrently on host threads, then each guide's
+ * per-shard lists are concatenated in shard order and merged by the ReferenceHit.sort key where they meet (consecutive windows overlap, so hits of
+ * neighbouring shards can interleave around a cut).  The result is owned by engines[0]; stats: ms[] = maximum over the engines, ms[6] = the host-side
+ * merge, counts[] = sums.  Needs max_overlap >= 1 (see calitas_search). */
+int calitas_search_sharded(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, int32_t n_guides,
+                           const calitas_guide* guides, const calitas_limits* limits, int32_t window_size, const char* chrom, calitas_hitset** out);
+
 /* ---- SearchReference -v: reference windows and variant windows, merged on the device -------------------------------------------------------
  * Replaces the variant loop of SearchReference.execute (SearchReference.scala:570-630) together with removeOverlaps + ReferenceHit.sort over the union
  * of both hit lists (:641-648, 653-675).  The host builds the variant windows (VariantWindow / VariantSet, :101-400); the engine aligns every guide g

@@ -77,25 +77,86 @@ def _oracle_rows(text, offset):
              r["padded_target"], r["total_mm_plus_gaps"], r["pam_used"]) for r in rows]
 
 
+def _engine_rows(world, m, guides):
+    from calitas_b200 import testing
+    g, arrays = world["genome"], world["arrays"]
+    text = world["engine"].render_alignments(m, guides, list(zip(g.names, arrays)), upper_case=True)
+    rows = testing._table(text, testing._INT_GA)
+    return [(x["guideStartOffset"], x["guideEndOffset"], x["strand"], x["score"], x["cigar"], x["paddedGuide"], x["paddedAlignment"], x["paddedTarget"],
+             x["edits"], "".join(ch for ch in x["guide"] if ch.islower())) for x in rows]
+
+
 @pytest.mark.parametrize("contig,k0", [(0, 30000), (7, 101), (23, 40011)])
 def test_slices_match_the_oracle(world, contig, k0):
     import pyoracle
-    from calitas_b200 import testing
     g, arrays, guides, r = world["genome"], world["arrays"], world["guides"], world["rec"]
     start, length = k0 * STEP, 2_000_000
     assert start + length < g.lengths[contig]
     sl = bytes(arrays[contig][start:start + length])
-    fac = testing.Facade()
-    for gi in (0, 3):
+    for gi in range(GUIDES_N):
         exp = [t for t in _oracle_rows(pyoracle.search_reference([(g.names[contig], sl)], guides[gi], raw=True, threads=8), start)
                if t[0] >= start + 1500 and t[1] <= start + length - 1500]
         m = r[(r["guide_idx"] == gi) & (r["contig_idx"] == contig) & (r["guide_start_offset"] >= start + 1500) & (r["guide_end_offset"] <= start + length - 1500)]
-        text = world["engine"].render_alignments(m, guides, list(zip(g.names, arrays)), upper_case=True)
-        rows = testing._table(text, testing._INT_GA)
-        got = [(x["guideStartOffset"], x["guideEndOffset"], x["strand"], x["score"], x["cigar"], x["paddedGuide"], x["paddedAlignment"], x["paddedTarget"],
-                x["edits"], "".join(ch for ch in x["guide"] if ch.islower())) for x in rows]
+        got = _engine_rows(world, m, guides)
         assert len(exp) > 50
         assert got == exp, (contig, gi)
+
+
+# BASELINE configs[3] shapes at full size: 6 guide diffs / 2 gaps with two PAMs, PAM-less, and a 5' PAM (DP runs on the reverse complement)
+CONFIG4_GUIDES = [("CTTGCCCCACAGGGCAGTAAngg", ["nag"]), "CTTGCCCCACAGGGCAGTAA", "tttvCTTGCCCCACAGGGCAGTAA", ("GGGGCCACTAGGGACAGGATngg", ["nag"])]
+
+
+@pytest.fixture(scope="module")
+def world6(world):
+    from calitas_b200._capi import Limits
+    lim = Limits(6, 1, 2, -1, 10)
+    hs = world["engine"].search(world["ref"], CONFIG4_GUIDES, lim, window_size=1000, dedup=True)
+    rec = hs.records()
+    hs.free()
+    return dict(rec=rec, lim=lim)
+
+
+@pytest.mark.parametrize("contig,k0", [(2, 52001), (21, 977)])
+def test_config4_shapes_match_the_oracle_on_slices(world, world6, contig, k0):
+    import pyoracle
+    g, arrays, r = world["genome"], world["arrays"], world6["rec"]
+    assert r.size > 4 * 1_000_000                          # ~1 100 hits/Mbp/guide at 6 diffs
+    start, length = k0 * (1000 - (23 + 6 + 2 - 1)), 1_000_000
+    assert start + length < g.lengths[contig]
+    sl = bytes(arrays[contig][start:start + length])
+    for gi, gd in enumerate(CONFIG4_GUIDES):
+        seq, aux = (gd, []) if isinstance(gd, str) else gd
+        step_g = 1000 - (len(seq) + 6 + 2 - 1)            # the window grid depends on the raw guide length (SearchReference.scala:528-530)
+        s0 = (start // step_g + 1) * step_g               # slice aligned to this guide's grid
+        sl = bytes(arrays[contig][s0:s0 + length])
+        exp = [t for t in _oracle_rows(pyoracle.search_reference([(g.names[contig], sl)], seq, aux_pams=aux, raw=True, threads=8, d=6, g=2), s0)
+               if t[0] >= s0 + 1500 and t[1] <= s0 + length - 1500]
+        m = r[(r["guide_idx"] == gi) & (r["contig_idx"] == contig) & (r["guide_start_offset"] >= s0 + 1500) & (r["guide_end_offset"] <= s0 + length - 1500)]
+        got = _engine_rows(world, m, [x if isinstance(x, str) else x for x in CONFIG4_GUIDES])
+        assert len(exp) > 100, (gi, len(exp))
+        assert got == exp, (contig, gi)
+
+
+def test_config5_vcf_slice_matches_the_oracle(world):
+    """BASELINE configs[4]: SearchReference -v.  A synthetic PrepareVcf-shaped VCF over the first 2 Mbp of chrY, searched with -c chrY on the full genome
+    (reference windows + variant windows merged and de-duplicated on the device); every row that ends inside the slice must equal the oracle's row
+    (all 34 columns; the oracle sees the slice as a contig of the same name, so coordinates, flanks and variant descriptions need no shifting)."""
+    import pyoracle
+    from calitas_b200 import synth, testing
+    g, arrays = world["genome"], world["arrays"]
+    c, length = 23, 2_000_000
+    sub = synth.Genome([g.names[c]], [length], g.seed)
+    vcf = synth.synthetic_vcf(sub, [arrays[c][:length]], 6000)
+    assert vcf.count("\n") > 5000
+    fac = testing.Facade()
+    contigs = list(zip(g.names, arrays))
+    for guide, aux, kw in ((synth.BASELINE_GUIDE, [], {}), ("CTTGCCCCACAGGGCAGTAAngg", ["nag"], dict(d=6, g=2))):
+        exp = [l for l in pyoracle.search_reference([(g.names[c], bytes(arrays[c][:length]))], guide, aux_pams=aux, vcf_text=vcf, raw=True, threads=8, **kw).split("\n") if l]
+        got = [l for l in fac.search_reference(contigs, guide, aux_pams=aux, vcf_text=vcf, chrom=g.names[c], raw=True, **kw).split("\n") if l]
+        inside = lambda l: int(l.split("\t")[5]) <= length - 1500            # coordinate_end
+        e_rows, g_rows = [l for l in exp[1:] if inside(l)], [l for l in got[1:] if inside(l)]
+        assert exp[0] == got[0] and len(e_rows) > 150 and any("+variants" in l for l in e_rows)
+        assert g_rows == e_rows, guide
 
 
 def test_dedup_output_is_a_subset_of_the_raw_output(world):

@@ -374,3 +374,30 @@ def test_align_best_mode_negative_overlap_cannot_happen_but_wide_costs_clamp(eng
         for O in (-1, 0, 3):
             kw = dict(max_guide_diffs=8, max_pam_diffs=1, max_gaps=3, max_total_diffs=12, max_overlap=O)     # d = 8 -> k_edits > 6: the wide kernels
             assert eng.align(guide, target, **kw) == pyoracle.align(guide, target, **kw), (k, O)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(d=6, g=2), dict(O=25), dict(O=1, max_variants=3)])
+def test_search_reference_with_dense_vcf(eng, small_genome, kw):
+    """SearchReference -v with clustered variants (allele combinations, suffix re-chunking), multi-allelic records and indels: the variant windows' hits
+    are merged with the reference hits, grouped per variant set and de-duplicated on the device; rows must equal the oracle's, ties across variant groups included."""
+    g, contigs = small_genome
+    arrays = [np.frombuffer(b, dtype=np.uint8) for _, b in contigs]
+    vcf = synth.synthetic_vcf_fast(g, arrays, [(0, l) for l in g.lengths], 2500, cluster_fraction=0.3)
+    # variants right on planted sites, so that hits really differ between haplotypes
+    extra = []
+    for c, lst in enumerate(g.planted):
+        for (pos, seq) in lst[:12]:
+            p = pos + 5
+            ref = chr(arrays[c][p])
+            if ref in "ACGT":
+                extra.append("%s\t%d\tsite%d_%d\t%s\t%s\t.\tPASS\tAF=0.25" % (g.names[c], p + 1, c, p, ref, "ACGT"[("ACGT".index(ref) + 1) % 4]))
+    body = [l for l in vcf.split("\n") if l and not l.startswith("#")] + extra
+    order = {n: i for i, n in enumerate(g.names)}
+    seen = set()
+    body = [l for l in sorted(body, key=lambda l: (order[l.split("\t")[0]], int(l.split("\t")[1]))) if not ((l.split("\t")[0], l.split("\t")[1]) in seen or seen.add((l.split("\t")[0], l.split("\t")[1])))]
+    vcf = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n" + "\n".join(body) + "\n"
+    for guide, aux in ((synth.BASELINE_GUIDE, []), ("CTTGCCCCACAGGGCAGTAAngg", ["nag"])):
+        exp = _lines(pyoracle.search_reference(contigs, guide, aux_pams=aux, vcf_text=vcf, raw=True, **kw))
+        got = _lines(eng.search_reference(contigs, guide, aux_pams=aux, vcf_text=vcf, raw=True, **kw))
+        assert sum("+variants" in l for l in exp) > 5
+        assert got == exp, (guide, kw)

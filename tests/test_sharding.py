@@ -92,3 +92,33 @@ def test_shard_plan_covers_genome(lib):
                 assert 0 <= hb[c] <= ob[c] <= oe[c] <= he[c] <= lengths[c]
                 owned[c] += oe[c] - ob[c]
         assert owned == lengths
+
+
+@pytest.mark.parametrize("max_overlap", [10, 25])
+def test_search_sharded_returns_one_merged_table(lib, max_overlap):
+    """calitas_search_sharded: N engines on host threads, one table in one address space == the single-engine table (dense repeats across the cuts,
+    where neighbouring shards' hits interleave by start)."""
+    import test_parity_random as T
+    contigs = [(n, np.frombuffer(b, dtype=np.uint8)) for n, b in T._tandem_repeat_contigs(511, 220)] + [(n, b) for n, b in synth.config1_genome(scale=0.01, n_sites=30).contigs()]
+    guides = [synth.BASELINE_GUIDE, ("CTTGCCCCACAGGGCAGTAAngg", ["nag"]), "GGGGCCACTAGGGACAGGAT"]
+    lim = Limits(5, 1, 3, -1, max_overlap)
+    e = Engine(0, lib=lib)
+    ref = e.load_reference(contigs)
+    whole = e.search(ref, guides, lim, dedup=True).records()
+    ref.free()
+    assert whole.size > 200
+    for n_shards in (2, 3, 5):
+        engines = [e] + [Engine(0, lib=lib) for _ in range(n_shards - 1)]
+        refs = [en.load_reference(contigs, shard=(s, n_shards, 4000)) for s, en in enumerate(engines)]
+        hs = Engine.search_sharded(engines, refs, guides, lim)
+        got = hs.records()
+        hs.free()
+        for r in refs:
+            r.free()
+        for en in engines[1:]:
+            en.close()
+        a, b = got.copy(), whole.copy()
+        a["task_idx"] = 0
+        b["task_idx"] = 0
+        assert a.size == b.size and a.tobytes() == b.tobytes(), n_shards
+    e.close()
