@@ -125,7 +125,7 @@ class A2ROptions(C.Structure):
 EXPORTS = [
     # include/calitas_b200.h
     "calitas_engine_create", "calitas_engine_destroy", "calitas_engine_get_costs", "calitas_last_error", "calitas_reference_load", "calitas_reference_free", "calitas_reference_own_range",
-    "calitas_shard_plan", "calitas_search", "calitas_search_sharded", "calitas_search_variants", "calitas_hitset_variant_info", "calitas_align_regions", "calitas_align_targets", "calitas_hitset_count", "calitas_hitset_data", "calitas_hitset_stride",
+    "calitas_shard_plan", "calitas_search", "calitas_search_sharded", "calitas_search_variants", "calitas_variant_set_load", "calitas_variant_set_free", "calitas_hitset_variant_info", "calitas_align_regions", "calitas_align_targets", "calitas_hitset_count", "calitas_hitset_data", "calitas_hitset_stride",
     "calitas_hitset_free", "calitas_hitset_stats", "calitas_render_alignments", "calitas_free_text", "calitas_microbench_int",
     # include/calitas_b200_tools.h
     "calitas_tool_align", "calitas_tool_align_best", "calitas_tool_align_to_ref", "calitas_tool_search_reference", "calitas_tool_search_reference_batch", "calitas_tool_search_reference_batch_fd", "calitas_tool_align_to_reference",

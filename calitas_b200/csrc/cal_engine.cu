@@ -434,6 +434,76 @@ CAL_D uint32_t spread_bits16(uint32_t v) {    // bit i of v -> bit 2 i
   v &= 0xFFFFu; v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu; v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
   return v;
 }
+// target codes right of an alignment's last guide column j, for the PAM extension: code(k) = base at column j + 1 + k
+struct RegCodes { uint64_t e0, e1; int first; CAL_D uint32_t operator()(int k) const { const int idx = first + k; return (uint32_t)((idx < 16 ? e0 >> (4 * idx) : e1 >> (4 * (idx - 16))) & 15u); } };
+// Everything after the traceback of one guide alignment, shared by the register-resident aligners: the diffs filter (SequentialGuideAligner.scala:447,450),
+// extend_pam for every PAM (:433-492), the ops of guide-PAM gap and PAM, Cigar.reverse for a 5' PAM, the coordinates of make_hit (:263-310, 505-524),
+// the record as 16-byte stores and the canon key.  `ops`: n_g two-bit ops, first alignment column in the low bits; term / term_op: the trailing gap run.
+template <class Codes>
+CAL_D void emit_hit_slots(const AlignArgs& a, const CandCtx& x, const GuideSpec& g, Ops128 ops, int n_g, int term, int term_op, int32_t best, int t_start, int32_t j,
+                          const Codes& after, int64_t slot0) {
+  const Scores& sc = a.sc;
+  const int diffs = popc32((uint32_t)((ops.lo | (ops.lo >> 1)) & 0x55555555u)) + popc32((uint32_t)(((ops.lo | (ops.lo >> 1)) >> 32) & 0x55555555u)) +
+                    popc32((uint32_t)((ops.hi | (ops.hi >> 1)) & 0x55555555u)) + popc32((uint32_t)(((ops.hi | (ops.hi >> 1)) >> 32) & 0x55555555u));
+  if (diffs > g.d) return;                               // SequentialGuideAligner.scala:447,450
+  const int terminal_d = term_op == OP_D ? term : 0;
+  const int n_pams = g.n_pams;
+  for (int pi = 0; pi < (n_pams > 0 ? n_pams : 1); ++pi) {
+    int32_t score = best, offset = 0; uint32_t xmask = 0; int pam_len = 0;
+    if (n_pams > 0) {                                    // extend_pam (SequentialGuideAligner.scala:433-492)
+      pam_len = g.pam_len[pi];
+      int max_extra = g.g - term; const int alt = g.max_tot_filter - diffs; if (alt < max_extra) max_extra = alt;
+      bool have = false;
+      for (int off = 0; off <= max_extra; ++off) {
+        int limit = g.p; const int l2 = g.max_tot_filter - diffs - off; if (l2 < limit) limit = l2;
+        if (j + off + pam_len > x.m || limit < 0) continue;
+        int32_t ps = 0; int nx = 0; uint32_t xm = 0;
+        for (int q = 0; q < pam_len; ++q) {
+          const bool pr = pairs(g.pam[pi][q], after(off + q));
+          ps += pr ? sc.pam_match : sc.pam_mismatch;
+          if (!((pr ? sc.pam_match : sc.pam_mismatch) > 0)) { ++nx; xm |= 1u << q; }                // op '=' iff addend > 0 (:468)
+        }
+        if (nx > limit) continue;
+        const int32_t total = best + ps + off * sc.query_gap;
+        if (!have || total > score) { have = true; score = total; offset = off; xmask = xm; }      // maxBy keeps the first maximum
+      }
+      if (!have) continue;
+    }
+    const int tail = n_pams > 0 ? offset + pam_len : 0;
+    const int n_ops = n_g + tail;
+    Ops128 all = ops;
+    if (tail) {
+      Ops128 ext = shl128(Ops128{ (uint64_t)spread_bits16(xmask), 0ull }, 2 * offset);       // the PAM columns (X = 1, '=' = 0) ...
+      ext.lo |= offset ? ((1ull << (2 * offset)) - 1) : 0ull;                                 // ... behind offset x D (3): the guide-PAM gap (offset <= 26)
+      ext = shl128(ext, 2 * n_g);
+      all.lo |= ext.lo; all.hi |= ext.hi;
+    }
+    if (g.five_prime) {                                  // Cigar.reverse (:267,284): reverse the n_ops fields
+      Ops128 r{ rev_fields2(all.hi), rev_fields2(all.lo) };
+      all = shr128(r, 2 * (64 - n_ops));
+    }
+    const int32_t s0 = t_start - 1, e0c = j + tail, trail_dp = terminal_d + tail;
+    int32_t start; int lead, trail;
+    if (x.dir == 0) { start = x.geom.w_begin + s0; lead = 0; trail = trail_dp; }
+    else { start = x.geom.w_end - e0c; lead = trail_dp; trail = 0; }                               // flip about the window (:271-274, 305-308)
+    uint32_t* rec = a.recs + (slot0 + pi) * a.rw;
+    const uint32_t where = rec_make_where(x.gidx, x.contig_idx, (x.dir ^ g.five_prime) != 0);
+    const uint32_t shape = rec_make_shape(n_ops, e0c - s0, lead, trail, n_pams > 0 ? pi : -1);
+#ifndef CAL_HOSTSIM
+    uint4* r4 = reinterpret_cast<uint4*>(rec);
+    r4[0] = make_uint4((uint32_t)start, (uint32_t)(x.task), (uint32_t)score, where);
+    r4[1] = make_uint4(shape, (uint32_t)all.lo, (uint32_t)(all.lo >> 32), (uint32_t)all.hi);
+    if (a.rw > CALITAS_HIT_WORDS) { r4[2] = make_uint4((uint32_t)(all.hi >> 32), 0u, 0u, 0u); r4[3] = make_uint4(0u, 0u, 0u, 0u); }
+#else
+    rec[0] = (uint32_t)start; rec[1] = (uint32_t)(x.task); rec[2] = (uint32_t)score; rec[3] = where; rec[4] = shape;
+    rec[5] = (uint32_t)all.lo; rec[6] = (uint32_t)(all.lo >> 32); rec[7] = (uint32_t)all.hi;
+    if (a.rw > CALITAS_HIT_WORDS) { rec[8] = (uint32_t)(all.hi >> 32); for (int k = 9; k < a.rw; ++k) rec[k] = 0u; }
+#endif
+    const int gaps = popc32((uint32_t)all.lo & 0xAAAAAAAAu) + popc32((uint32_t)(all.lo >> 32) & 0xAAAAAAAAu) + popc32((uint32_t)all.hi & 0xAAAAAAAAu) + popc32((uint32_t)(all.hi >> 32) & 0xAAAAAAAAu);
+    const int edits = diffs + offset + popc32(xmask);    // non-'=' columns: the guide part, the guide-PAM gap, the PAM mismatches
+    a.ckeys[slot0 + pi] = ckey_make(score, start, start + (e0c - s0), gaps, edits, x.owned);
+  }
+}
 template <int KB>
 CAL_D void align_fast(const AlignArgs& a) {
   constexpr int B = 2 * KB + 1;
@@ -506,72 +576,10 @@ CAL_D void align_fast(const AlignArgs& a) {
     ++n_g;
     cdir = next;
   }
-  const int diffs = popc32((uint32_t)((ops.lo | (ops.lo >> 1)) & 0x55555555u)) + popc32((uint32_t)(((ops.lo | (ops.lo >> 1)) >> 32) & 0x55555555u)) +
-                    popc32((uint32_t)((ops.hi | (ops.hi >> 1)) & 0x55555555u)) + popc32((uint32_t)(((ops.hi | (ops.hi >> 1)) >> 32) & 0x55555555u));
-  if (diffs > g.d) return;                               // SequentialGuideAligner.scala:447,450
-  const int t_start = base + ct + 1;                     // 1-based first target column
-  const int terminal_d = term_op == OP_D ? term : 0;
   // after n slides code k of the window is column j - KB + 1 + k: the base right of the alignment (column j + 1) is code KB
   const uint64_t e0 = (uint64_t)A[0] | ((uint64_t)A[1] << 32), e1 = (uint64_t)A[2] | ((uint64_t)A[3] << 32);
-  const int64_t slot0 = i * a.slots;
-  const int n_pams = g.n_pams;
-  for (int pi = 0; pi < (n_pams > 0 ? n_pams : 1); ++pi) {
-    int32_t score = best, offset = 0; uint32_t xmask = 0; int pam_len = 0;
-    if (n_pams > 0) {                                    // extend_pam (SequentialGuideAligner.scala:433-492)
-      pam_len = g.pam_len[pi];
-      int max_extra = g.g - term; const int alt = g.max_tot_filter - diffs; if (alt < max_extra) max_extra = alt;
-      bool have = false;
-      for (int off = 0; off <= max_extra; ++off) {
-        int limit = g.p; const int l2 = g.max_tot_filter - diffs - off; if (l2 < limit) limit = l2;
-        if (j + off + pam_len > x.m || limit < 0) continue;
-        int32_t ps = 0; int nx = 0; uint32_t xm = 0;
-        for (int q = 0; q < pam_len; ++q) {
-          const int idx = KB + off + q;
-          const uint32_t code = (uint32_t)((idx < 16 ? e0 >> (4 * idx) : e1 >> (4 * (idx - 16))) & 15u);
-          const bool pr = pairs(g.pam[pi][q], code);
-          ps += pr ? sc.pam_match : sc.pam_mismatch;
-          if (!((pr ? sc.pam_match : sc.pam_mismatch) > 0)) { ++nx; xm |= 1u << q; }                // op '=' iff addend > 0 (:468)
-        }
-        if (nx > limit) continue;
-        const int32_t total = best + ps + off * sc.query_gap;
-        if (!have || total > score) { have = true; score = total; offset = off; xmask = xm; }      // maxBy keeps the first maximum
-      }
-      if (!have) continue;
-    }
-    const int tail = n_pams > 0 ? offset + pam_len : 0;
-    const int n_ops = n_g + tail;
-    Ops128 all = ops;
-    if (tail) {
-      Ops128 ext = shl128(Ops128{ (uint64_t)spread_bits16(xmask), 0ull }, 2 * offset);       // the PAM columns (X = 1, '=' = 0) ...
-      ext.lo |= offset ? ((1ull << (2 * offset)) - 1) : 0ull;                                 // ... behind offset x D (3): the guide-PAM gap (offset <= 26)
-      ext = shl128(ext, 2 * n_g);
-      all.lo |= ext.lo; all.hi |= ext.hi;
-    }
-    if (g.five_prime) {                                  // Cigar.reverse (:267,284): reverse the n_ops fields
-      Ops128 r{ rev_fields2(all.hi), rev_fields2(all.lo) };
-      all = shr128(r, 2 * (64 - n_ops));
-    }
-    const int32_t s0 = t_start - 1, e0c = j + tail, trail_dp = terminal_d + tail;
-    int32_t start; int lead, trail;
-    if (x.dir == 0) { start = x.geom.w_begin + s0; lead = 0; trail = trail_dp; }
-    else { start = x.geom.w_end - e0c; lead = trail_dp; trail = 0; }                               // flip about the window (:271-274, 305-308)
-    uint32_t* rec = a.recs + (slot0 + pi) * a.rw;
-    const uint32_t where = rec_make_where(x.gidx, x.contig_idx, (x.dir ^ g.five_prime) != 0);
-    const uint32_t shape = rec_make_shape(n_ops, e0c - s0, lead, trail, n_pams > 0 ? pi : -1);
-#ifndef CAL_HOSTSIM
-    uint4* r4 = reinterpret_cast<uint4*>(rec);
-    r4[0] = make_uint4((uint32_t)start, (uint32_t)(x.task), (uint32_t)score, where);
-    r4[1] = make_uint4(shape, (uint32_t)all.lo, (uint32_t)(all.lo >> 32), (uint32_t)all.hi);
-    if (a.rw > CALITAS_HIT_WORDS) { r4[2] = make_uint4((uint32_t)(all.hi >> 32), 0u, 0u, 0u); r4[3] = make_uint4(0u, 0u, 0u, 0u); }
-#else
-    rec[0] = (uint32_t)start; rec[1] = (uint32_t)(x.task); rec[2] = (uint32_t)score; rec[3] = where; rec[4] = shape;
-    rec[5] = (uint32_t)all.lo; rec[6] = (uint32_t)(all.lo >> 32); rec[7] = (uint32_t)all.hi;
-    if (a.rw > CALITAS_HIT_WORDS) { rec[8] = (uint32_t)(all.hi >> 32); for (int k = 9; k < a.rw; ++k) rec[k] = 0u; }
-#endif
-    const int gaps = popc32((uint32_t)all.lo & 0xAAAAAAAAu) + popc32((uint32_t)(all.lo >> 32) & 0xAAAAAAAAu) + popc32((uint32_t)all.hi & 0xAAAAAAAAu) + popc32((uint32_t)(all.hi >> 32) & 0xAAAAAAAAu);
-    const int edits = diffs + offset + popc32(xmask);    // non-'=' columns: the guide part, the guide-PAM gap, the PAM mismatches
-    a.ckeys[slot0 + pi] = ckey_make(score, start, start + (e0c - s0), gaps, edits, x.owned);
-  }
+  const RegCodes after{ e0, e1, KB };
+  emit_hit_slots(a, x, g, ops, n_g, term, term_op, best, base + ct + 1, j, after, i * a.slots);
 }
 CAL_KERNEL __launch_bounds__(128) k_align_fast6(AlignArgs a) { align_fast<6>(a); }
 CAL_KERNEL __launch_bounds__(128) k_align_fast5(AlignArgs a) { align_fast<5>(a); }
@@ -591,9 +599,9 @@ CAL_KERNEL __launch_bounds__(128) k_group_starts(const uint32_t* flag, const uin
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && flag[i]) gstart[pos[i]] = (uint32_t)i;
 }
-CAL_KERNEL __launch_bounds__(128) k_align_group(AlignArgs a, const uint32_t* gstart, int64_t n_groups) {
+CAL_KERNEL __launch_bounds__(128) k_align_group(AlignArgs a, const uint32_t* gstart, int64_t n_groups, const uint32_t* only /* NULL: every group; else the groups flagged != 0 */) {
   const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= n_groups) return;
+  if (gi >= n_groups || (only && !only[gi])) return;
   const int64_t i0 = gstart[gi], i1 = gi + 1 < n_groups ? (int64_t)gstart[gi + 1] : a.n_cand;
   const CandCtx x = decode_candidate(a, a.cand[i0]);
   const GuideSpec& g = a.specs[x.gidx];
@@ -610,6 +618,94 @@ CAL_KERNEL __launch_bounds__(128) k_align_group(AlignArgs a, const uint32_t* gst
     for (int64_t i = i0; i < i1; ++i) { GuideAln aln; if (band_align(g, a.sc, fetch, col_at((int)(i - i0)), aln, trace)) post_alignment(a, x, g, fetch, aln, i); }
   }
 }
+
+#ifndef CAL_HOSTSIM
+// The same work with a WARP per (window, strand) group: lane r - 1 owns DP row r (a protospacer has at most 32 rows) and the matrices are filled along
+// anti-diagonals, cell (r, c) at step r + c - 1.  A cell needs max3(D, L, U) of (r-1, c-1) and max(D, U) of (r-1, c) from the lane above -- two
+// shuffles -- and max3 of its own previous cell; scores stay tagged as in band_align_k, so the predecessor choices fall out of the maxima.  One trace
+// byte per cell goes to shared memory (33 x 161 bytes per warp), the last row's end scores too; then the lanes trace 32 candidate columns at a time,
+// packing ops into registers and finishing with emit_hit_slots.  Nothing lives in local memory: against the thread-per-group kernel above (168
+// registers, 7.3 KB of stack, 18 % of the warps resident, latency-bound on its byte trace) this one is issue-bound.
+// Groups that do not fit (window wider than GROUP_W columns, alignments longer than 64 columns) are flagged for k_align_group.
+const int GROUP_WARPS = 4;
+struct SmemCodes { const uint8_t* codes; int first; CAL_D uint32_t operator()(int k) const { return codes[first + k]; } };
+CAL_KERNEL __launch_bounds__(32 * GROUP_WARPS) k_align_group_warp(AlignArgs a, const uint32_t* gstart, int64_t n_groups, uint32_t* slow) {
+  constexpr int TW = GROUP_W + 1, EXT = 64;
+  __shared__ uint8_t s_trace[GROUP_WARPS][(CALITAS_MAX_PROTOSPACER + 1) * TW + 15];
+  __shared__ uint8_t s_codes[GROUP_WARPS][TW + EXT + 3];
+  __shared__ int32_t s_end[GROUP_WARPS][TW + 3];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint8_t* trace = s_trace[wib]; uint8_t* codes = s_codes[wib]; int32_t* ends = s_end[wib];
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const Scores& sc = a.sc;
+  const int32_t gI4 = 4 * sc.target_gap, gD4 = 4 * sc.query_gap, mis4 = 4 * sc.mismatch, dmatch4 = 4 * (sc.match - sc.mismatch), NEG4 = 4 * NEG_SCORE;
+  for (int64_t gi = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); gi < n_groups; gi += n_warps) {
+    const int64_t i0 = gstart[gi], i1 = gi + 1 < n_groups ? (int64_t)gstart[gi + 1] : a.n_cand;
+    const int n_cols = (int)(i1 - i0);
+    const CandCtx x = decode_candidate(a, a.cand[i0]);
+    const GuideSpec& g = a.specs[x.gidx];
+    const int n = g.lp;
+    const int first = key_col(a.key, a.cand[i0]), last = key_col(a.key, a.cand[i1 - 1]);
+    const int jlo = first - g.span > 0 ? first - g.span : 0;
+    const int W = last - jlo;
+    int pam_max = 0; for (int k = 0; k < g.n_pams; ++k) pam_max = pam_max > g.pam_len[k] ? pam_max : g.pam_len[k];
+    const bool fits = W <= GROUP_W && g.max_cols <= 64 && g.g + pam_max <= EXT;
+    if (lane == 0) slow[gi] = fits ? 0u : 1u;
+    if (!fits) continue;
+    for (int64_t sl = i0 * a.slots + lane; sl < i1 * a.slots; sl += 32) a.ckeys[sl] = CKey{ 0, 0, 0, 0u };
+    const NibFetch fetch{ a.nib, x.first, x.m, x.dir };
+    for (int c = 1 + lane; c <= W + EXT; c += 32) codes[c] = (uint8_t)(jlo + c <= x.m ? fetch(jlo + c) : 0u);
+    if (lane < n) trace[(lane + 1) * TW] = (uint8_t)((lane == 0 ? TG_DIAG : TG_UP) << 2);     // local column 0: leading insertions only
+    __syncwarp();
+    // ---- fill along anti-diagonals ---------------------------------------------------------------------------------------------------------
+    const uint32_t qm = lane < n ? g.qmask[lane] : 0u;
+    int32_t m3_p1, m3_p2, mup_p1;                       // of this row's cell at the previous step (p1) and the one before (p2): max3(D, L, U) and max(D, U), tagged
+    { const int32_t d0 = NEG4 + TG_DIAG, l0 = NEG4 + TG_LEFT, u0 = (lane + 1) * gI4 + TG_UP; m3_p1 = max3_s32(d0, l0, u0); m3_p2 = m3_p1; mup_p1 = d0 > u0 ? d0 : u0; }
+    const int steps = W + n - 1;
+    for (int t = 1; t <= steps; ++t) {
+      int32_t diag_in = __shfl_up_sync(0xFFFFFFFFu, m3_p2, 1), up_in = __shfl_up_sync(0xFFFFFFFFu, mup_p1, 1);
+      if (lane == 0) { diag_in = TG_DIAG; up_in = TG_DIAG; }                                 // row 0 is all zero (free leading target): Diagonal wins its ties
+      const int c = t - lane;
+      int32_t n3 = m3_p1, nup = mup_p1;
+      if (lane < n && c >= 1 && c <= W) {
+        const uint32_t mt = (qm >> codes[c]) & 1u;
+        const int32_t add4 = mis4 + (int32_t)mt * dmatch4;
+        const int32_t md = diag_in, mu = up_in, ml = m3_p1;
+        const int32_t nd = (md | 3) + add4, nu = ((mu & ~3) | TG_UP) + gI4, nl = ((ml & ~3) | TG_LEFT) + gD4;
+        trace[(lane + 1) * TW + c] = (uint8_t)(((uint32_t)md & 3u) | (((uint32_t)mu & 3u) << 2) | (((uint32_t)ml & 3u) << 4) | (mt << 6));
+        n3 = max3_s32(nd, nl, nu); nup = nd > nu ? nd : nu;
+        if (lane == n - 1) ends[c] = n3;
+      }
+      m3_p2 = m3_p1; m3_p1 = n3; mup_p1 = nup;
+    }
+    __syncwarp();
+    // ---- every candidate column: traceback + extension + records, 32 at a time --------------------------------------------------------------------
+    for (int k = lane; k < n_cols; k += 32) {
+      const int32_t j = key_col(a.key, a.cand[i0 + k]);
+      const int c = j - jlo;
+      const int32_t mbest = ends[c], best = mbest >> 2;
+      if (best < g.min_score) continue;
+      Ops128 ops{ 0ull, 0ull };
+      int ci = n, cc = c, cdir = mbest & 3, n_g = 0, term = 0, term_op = 0;
+      while (ci > 0 && n_g < 64) {
+        const uint32_t cell = trace[ci * TW + cc];
+        const int next = (int)(cdir == TG_DIAG ? (cell & 3u) : (cdir == TG_UP ? ((cell >> 2) & 3u) : ((cell >> 4) & 3u)));
+        uint32_t op;
+        if (cdir == TG_DIAG) { op = (cell >> 6) ? OP_EQ : OP_X; --ci; --cc; }
+        else if (cdir == TG_LEFT) { op = OP_D; --cc; }
+        else { op = OP_I; --ci; }
+        if (n_g == term && op >= OP_I && (term == 0 || (int)op == term_op)) { ++term; term_op = (int)op; }
+        ops.hi = (ops.hi << 2) | (ops.lo >> 62); ops.lo = (ops.lo << 2) | op;
+        ++n_g;
+        cdir = next;
+      }
+      const SmemCodes after{ codes, c + 1 };
+      emit_hit_slots(a, x, g, ops, n_g, term, term_op, best, jlo + cc + 1, j, after, (i0 + k) * a.slots);
+    }
+    __syncwarp();
+  }
+}
+#endif
 
 CAL_KERNEL __launch_bounds__(128) k_align(AlignArgs a) { align_body<ALIGN_KB>(a); }
 CAL_KERNEL __launch_bounds__(128) k_align5(AlignArgs a) { align_body<5>(a); }
@@ -853,10 +949,20 @@ CAL_D int32_t var_ref_offset(const VarWindowDev& w, const calitas_variant_allele
 }
 struct VarKeyLayout { int32_t set_bits, contig_bits, score_hi, score_bits, start_bits; };
 // What calitas_search_variants adds to a search: the variant windows whose hits are merged with the reference windows' hits.
-struct VariantPlan {
-  int64_t n_windows; const calitas_variant_window* windows; const int32_t* guide_class; const calitas_variant_allele* alleles; int64_t n_alleles;
-  const uint32_t* set_rank; int64_t n_sets;
-};
+struct VariantPlan { const calitas_variant_set* vs; const int32_t* guide_class; };
+// tasks of a span of guides: guide g (class c) is aligned against the windows [class_begin[c], class_end[c]) of the set; task t of the span belongs to
+// the guide whose offset range holds t
+struct VarTaskGuide { int64_t first_task; int32_t guide, w_begin; };
+CAL_KERNEL __launch_bounds__(256) k_variant_tasks(const VarWindowDev* windows, const VarTaskGuide* guides, int32_t n_guides, int64_t n_tasks, ExplicitWindow* out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  int lo = 0, hi = n_guides - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (guides[mid].first_task <= t) lo = mid; else hi = mid - 1; }
+  const VarTaskGuide g = guides[lo];
+  const int32_t w = g.w_begin + (int32_t)(t - g.first_task);
+  const VarWindowDev v = windows[w];
+  out[t] = ExplicitWindow{ v.nib_start, v.length, 0, g.guide, v.contig_idx, w, v.owned };
+}
 // One thread per merged hit (reference hits first, then variant-window hits, each in arrival order): reference coordinates, the variant set the hit
 // overlaps (ReferenceHit.scala:211), and the two sort keys of the sweep order: major = guide | contig | set, minor = start | strand | score_hi - score.
 CAL_KERNEL __launch_bounds__(256) k_variant_keys(const uint32_t* recs, int32_t rw, int64_t n_ref, int64_t n, const VarWindowDev* windows, const calitas_variant_allele* alleles,
@@ -994,6 +1100,13 @@ struct calitas_hitset {
   calitas_engine* owner = nullptr; PinnedBuf buf; int64_t n = 0; int32_t stride = CALITAS_HIT_WORDS * 4; PinnedBuf info; /* calitas_variant_hit_info per hit, search_variants only */ double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 };
 
+// Variant windows of one VCF, resident on the device of `owner` (calitas_variant_set_load): packed bases, descriptors, alleles, variant-set names.
+struct calitas_variant_set {
+  calitas_engine* owner = nullptr; int64_t n_windows = 0, n_alleles = 0, n_sets = 0, nib_words = 0; uint32_t max_len = 1, max_rank = 0; int32_t n_contigs = 0;
+  DBuf nib, windows, alleles, sets;
+  std::vector<int64_t> class_begin, class_end;          // windows are sorted by guide_class
+};
+
 enum { CNT_GROUPS = 3, CNT_KEPT = 4, CNT_KEEPERS = 5 /* + 6: overflow flag as published */, CNT_DEDUP_OVERFLOW = 7 };
 enum { CE_SCAN_B = 0, CE_SCAN_E, CE_COUNT, CE_SORTED, CE_ALIGN_B, CE_ALIGN_E, CE_TAIL_B, CE_TAIL_E, CE_COPY_B, CE_COPY_E, CE_N };
 struct ChunkEvents { dev::Event ev[CE_N]; };
@@ -1007,7 +1120,7 @@ struct calitas_engine {
   std::vector<ChunkEvents> chunk_ev;
   size_t out_hits_hint = 1u << 16;
   DBuf cand_b, cand_c;
-  DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, sowned, out_owned, var_windows, var_alleles, var_sets, var_info, var_info2, var_nib, var_raw, out2, vk1, vk2, vk3, vi1, vi2, vi3;
+  DBuf specs, cand, cand_sorted, hits, valid, rank, perm, flag, pos, out, tmp, key1, keyA, idx, idx2, key_b, sstart, send, sscore, windows, nib_tmp, slot_owned, sowned, out_owned, var_info, var_info2, out2, vk1, vk2, vk3, vi1, vi2, vi3;
   // eight 64-bit device counters and their pinned host mirror: slots 0..2 = candidate counts of the three scan buffers (run_explicit uses 0),
   // slot CNT_DEDUP_OVERFLOW = k_dedup_keys' "a field does not fit its sort-key width" flag
   unsigned long long* h_count = nullptr;       // pinned + mapped: the device stores into it through h_count_dev (no copy engine involved)
@@ -1095,6 +1208,7 @@ struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> alig
   bool fast; int64_t nib_words;                                            // fast: every guide of the launch fits align_fast's 64-column window; nib_words: size of `nib`
   const DedupLayout* dedup; int32_t max_overlap;                           // dedup != nullptr: removeOverlaps + ReferenceHit.sort over the kept alignments
   DBuf* out_owned;                                                         // plain compaction only: when given, one byte per output record (1 = owned, 0 = halo) goes here
+  bool any_wide_group = true;                                              // best mode: some group may not fit k_align_group_warp's tile (window > GROUP_W columns or alignments > 64 columns)
 };
 
 // align_fast<KB> keeps 64 target codes per candidate in registers: band + guide-PAM gap + longest PAM must fit, and the extension indexes 32 of them
@@ -1148,7 +1262,15 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
     const int64_t n_groups = (int64_t)((volatile unsigned long long*)e->h_count)[CNT_GROUPS];
     CAL_LAUNCH(k_group_starts, blocks_for(n_cand, 128), 128, 0, s, 1, gflag, gpos, n_cand, e->idx.as<uint32_t>()); dev::launch_check("k_group_starts"); ++e->launches;
     dev::event_record(P.ev_align_b, s);
-    CAL_LAUNCH(k_align_group, blocks_for(n_groups, 128), 128, 0, s, 1, aa, e->idx.as<uint32_t>(), n_groups); dev::launch_check("k_align_group");
+#ifndef CAL_HOSTSIM
+    if (!std::getenv("CALITAS_NO_GROUP_WARP")) {          // warp per group; what does not fit its shared-memory tile is flagged and goes through the thread-per-group kernel
+      e->idx2.ensure((size_t)n_groups * 4);
+      CAL_LAUNCH(k_align_group_warp, (unsigned)dev::sm_count(e->device) * 8, 32 * GROUP_WARPS, 0, s, 1, aa, e->idx.as<uint32_t>(), n_groups, e->idx2.as<uint32_t>()); dev::launch_check("k_align_group_warp"); ++e->launches;
+      if (P.any_wide_group) { CAL_LAUNCH(k_align_group, blocks_for(n_groups, 128), 128, 0, s, 1, aa, e->idx.as<uint32_t>(), n_groups, (const uint32_t*)e->idx2.as<uint32_t>()); dev::launch_check("k_align_group"); }
+      else --e->launches;
+    } else
+#endif
+    { CAL_LAUNCH(k_align_group, blocks_for(n_groups, 128), 128, 0, s, 1, aa, e->idx.as<uint32_t>(), n_groups, (const uint32_t*)nullptr); dev::launch_check("k_align_group"); }
   }
   else { CAL_LAUNCH(k_align_wide, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_wide"); }
   ++e->launches;
@@ -1287,6 +1409,7 @@ void explicit_core(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, 
     counts[1] += (int64_t)n_cand;
     // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
     Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), L.slots, true, L.banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, drop_halo, key, L.rw, L.fast, nib_words, nullptr, 0, out_owned };
+    P.any_wide_group = max_len > (uint32_t)GROUP_W || L.rw > CALITAS_HIT_WORDS;          // record size > 32 bytes <=> some guide can produce more than 48 columns (the warp kernel takes 64)
     int64_t n_aln = 0;
     const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_out, 0, n_aln);
     if (n_cand) ms[2] += dev::event_ms(e->ev[2], e->ev[3]);
@@ -1336,61 +1459,43 @@ void score_bounds(const std::vector<GuideSpec>& specs, size_t g0, size_t g1, con
 int64_t merge_variant_hits(calitas_engine* e, const VariantPlan& vp, const std::vector<GuideSpec>& specs, const calitas_limits* limits, const calitas_reference* ref, int rw, int64_t n_ref,
                            double ms[8], int64_t counts[8]) {
   dev::Stream s = e->stream;
-  const int64_t n_w = vp.n_windows;
+  const calitas_variant_set& vs = *vp.vs;
+  if (vs.owner != e) throw InvalidArgument("the variant set belongs to another engine");
+  if (vs.n_contigs != (int32_t)ref->len.size()) throw InvalidArgument("the variant set was loaded for another reference");
   int64_t n = n_ref;
-  if (n_w > 0) {
-    // ---- window bases: concatenated at multiples of 8 with a gap, uploaded raw and packed on the device like the reference --------------------------
-    std::vector<VarWindowDev> wd((size_t)n_w); std::vector<int64_t> off((size_t)n_w);
-    int64_t total = 64; uint32_t max_len = 1;
-    for (int64_t w = 0; w < n_w; ++w) {
-      const calitas_variant_window& v = vp.windows[w];
-      if (v.length < 0 || (uint32_t)v.length > MAX_WINDOW_LEN || (v.length && !v.bases) || v.n_alleles < 0 || v.first_allele < 0 || v.first_allele + (int64_t)v.n_alleles > vp.n_alleles ||
-          v.first_set < 0 || v.first_set + (int64_t)v.n_alleles * (v.n_alleles + 1) / 2 > vp.n_sets || v.contig_idx < 0 || v.contig_idx >= (int)ref->len.size())
-        throw InvalidArgument("bad variant window");
-      off[(size_t)w] = total; max_len = std::max<uint32_t>(max_len, (uint32_t)v.length);
-      wd[(size_t)w] = VarWindowDev{ total, v.length, v.contig_idx, v.ref_start, v.n_alleles, v.first_allele, v.first_set, v.owned ? 1 : 0, 0 };
-      total += (v.length + 7) / 8 * 8 + 8;
-    }
-    total += 64;
-    {
-      std::vector<uint8_t> raw((size_t)total, 0);
-      for (int64_t w = 0; w < n_w; ++w) if (vp.windows[w].length) std::memcpy(raw.data() + off[(size_t)w], vp.windows[w].bases, (size_t)vp.windows[w].length);
-      e->var_raw.ensure((size_t)total); e->var_nib.ensure((size_t)total / 2 + 8);
-      dev::h2d(e->var_raw.p, raw.data(), (size_t)total, s);
-      const int64_t n_words = total / 8;
-      const unsigned grid = (unsigned)std::min<int64_t>((n_words + 255) / 256, (int64_t)dev::sm_count(e->device) * 16);
-      CAL_LAUNCH(k_pack, grid, 256, 256, s, 2, e->var_raw.as<uint8_t>(), e->var_nib.as<uint32_t>(), n_words); dev::launch_check("k_pack"); ++e->launches;
-      dev::stream_sync(s);                                 // `raw` goes out of scope
-      counts[4] += total;
-    }
-    e->var_windows.ensure(wd.size() * sizeof(VarWindowDev)); dev::h2d(e->var_windows.p, wd.data(), wd.size() * sizeof(VarWindowDev), s);
-    e->var_alleles.ensure(std::max<size_t>(1, (size_t)vp.n_alleles) * sizeof(calitas_variant_allele)); dev::h2d(e->var_alleles.p, vp.alleles, (size_t)vp.n_alleles * sizeof(calitas_variant_allele), s);
-    e->var_sets.ensure(std::max<size_t>(1, (size_t)vp.n_sets) * 4); dev::h2d(e->var_sets.p, vp.set_rank, (size_t)vp.n_sets * 4, s);
-    counts[4] += (int64_t)(wd.size() * sizeof(VarWindowDev) + (size_t)vp.n_alleles * sizeof(calitas_variant_allele) + (size_t)vp.n_sets * 4);
-    // ---- tasks: every guide against the windows of its class, guides in spans that keep a task list under 2^25 entries ---------------------------
+  if (vs.n_windows > 0) {
+    // ---- tasks: every guide against the windows of its class, built on the device for spans of guides that keep a task list under 2^25 entries ------
     const LaunchShape L = launch_shape(specs, 0, specs.size(), rw);
-    std::vector<ExplicitWindow> tasks;
-    const size_t TASK_SPAN = (size_t)1 << 25;
+    const int64_t TASK_SPAN = (int64_t)1 << 25;
+    std::vector<VarTaskGuide> span; int64_t span_tasks = 0;
+    auto flush = [&]() {
+      if (span_tasks == 0) { span.clear(); return; }
+      e->var_info2.ensure(span.size() * sizeof(VarTaskGuide)); dev::h2d(e->var_info2.p, span.data(), span.size() * sizeof(VarTaskGuide), s);
+      e->windows.ensure((size_t)span_tasks * sizeof(ExplicitWindow));
+      CAL_LAUNCH(k_variant_tasks, blocks_for(span_tasks, 256), 256, 0, s, 1, vs.windows.as<VarWindowDev>(), e->var_info2.as<VarTaskGuide>(), (int32_t)span.size(), span_tasks, e->windows.as<ExplicitWindow>());
+      dev::launch_check("k_variant_tasks"); ++e->launches;
+      dev::stream_sync(s);                                 // `span` is reused
+      counts[4] += (int64_t)(span.size() * sizeof(VarTaskGuide));
+      explicit_core(e, vs.nib.as<uint32_t>(), vs.nib_words, span_tasks, vs.max_len, L, false, &e->out_owned, n, ms, counts);
+      span.clear(); span_tasks = 0;
+    };
     for (size_t g = 0; g < specs.size(); ++g) {
-      for (int64_t w = 0; w < n_w; ++w) {
-        const calitas_variant_window& v = vp.windows[w];
-        if (v.guide_class != vp.guide_class[g]) continue;
-        tasks.push_back(ExplicitWindow{ off[(size_t)w], v.length, 0, (int32_t)g, v.contig_idx, (int32_t)w, v.owned ? 1 : 0 });
-      }
-      if (tasks.size() >= TASK_SPAN || (g + 1 == specs.size() && !tasks.empty())) {
-        e->windows.ensure(tasks.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, tasks.data(), tasks.size() * sizeof(ExplicitWindow), s); dev::stream_sync(s);
-        counts[4] += (int64_t)(tasks.size() * sizeof(ExplicitWindow));
-        explicit_core(e, e->var_nib.as<uint32_t>(), total / 8, (int64_t)tasks.size(), max_len, L, false, &e->out_owned, n, ms, counts);
-        tasks.clear();
-      }
+      const int32_t c = vp.guide_class[g];
+      if (c < 0 || c >= (int32_t)vs.class_begin.size()) continue;                    // no windows of that class
+      const int64_t nw = vs.class_end[(size_t)c] - vs.class_begin[(size_t)c];
+      if (nw == 0) continue;
+      if (span_tasks + nw > TASK_SPAN && span_tasks > 0) flush();
+      span.push_back(VarTaskGuide{ span_tasks, (int32_t)g, (int32_t)vs.class_begin[(size_t)c] });
+      span_tasks += nw;
     }
+    flush();
   }
   if (n == 0) return 0;
   if (n >= (1ll << 32)) throw LimitExceeded("too many hits in one batch");
   // ---- keys: sweep order = (guide, contig, variant set | start, strand, -score, arrival) via two stable sorts, minor key first ---------------------------
   VarKeyLayout V; DedupLayout F;
   {
-    uint32_t max_rank = 0; for (int64_t k = 0; k < vp.n_sets; ++k) max_rank = std::max(max_rank, vp.set_rank[k]);
+    const uint32_t max_rank = vs.max_rank;
     int64_t max_clen = 1; for (int64_t l : ref->len) max_clen = std::max(max_clen, l);
     V.set_bits = std::max(1, bit_length(max_rank)); V.contig_bits = std::max(1, bit_length((uint64_t)(ref->len.size() - 1))); V.start_bits = std::min(31, bit_length((uint64_t)max_clen));
     score_bounds(specs, 0, specs.size(), e->sc, V.score_hi, V.score_bits);
@@ -1407,7 +1512,7 @@ int64_t merge_variant_hits(calitas_engine* e, const VariantPlan& vp, const std::
   const uint32_t* recs = e->out.as<uint32_t>();
   uint64_t* major = e->vk1.as<uint64_t>(); uint64_t* minor = e->vk2.as<uint64_t>(); uint64_t* ktmp = e->vk3.as<uint64_t>();
   uint32_t* i1 = e->vi1.as<uint32_t>(); uint32_t* i2 = e->vi2.as<uint32_t>(); uint32_t* i3 = e->vi3.as<uint32_t>();
-  CAL_LAUNCH(k_variant_keys, blocks_for(n, 256), 256, 0, s, 1, recs, rw, n_ref, n, e->var_windows.as<VarWindowDev>(), e->var_alleles.as<calitas_variant_allele>(), e->var_sets.as<uint32_t>(), V,
+  CAL_LAUNCH(k_variant_keys, blocks_for(n, 256), 256, 0, s, 1, recs, rw, n_ref, n, vs.windows.as<VarWindowDev>(), vs.alleles.as<calitas_variant_allele>(), vs.sets.as<uint32_t>(), V,
              e->var_info.as<VarInfo>(), major, minor, i1, d_overflow); dev::launch_check("k_variant_keys"); ++e->launches;
   size_t tb = dev::sort_pairs_u64_tmp(nn, 0, 64); e->tmp.ensure(tb);
   dev::sort_pairs_u64(e->tmp.p, tb, minor, ktmp, i1, i2, nn, 0, V.start_bits + 1 + V.score_bits, s); ++e->launches;          // i2: merged-list index, in minor order
@@ -1480,7 +1585,7 @@ void calitas_engine_destroy(calitas_engine* e) {
     dev::set_device(e->device);
     dev::stream_sync(e->scan_stream); dev::stream_sync(e->scan_stream2); dev::stream_sync(e->pub_stream); dev::stream_sync(e->stream); dev::stream_sync(e->copy_stream);
     for (DBuf* b : { &e->cand_b, &e->cand_c, &e->specs, &e->cand, &e->cand_sorted, &e->hits, &e->valid, &e->rank, &e->perm, &e->flag, &e->pos, &e->out, &e->tmp, &e->key1, &e->keyA,
-                     &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp, &e->slot_owned, &e->sowned, &e->out_owned, &e->var_windows, &e->var_alleles, &e->var_sets, &e->var_info, &e->var_info2, &e->var_nib, &e->var_raw, &e->out2, &e->vk1, &e->vk2, &e->vk3, &e->vi1, &e->vi2, &e->vi3 }) b->release();
+                     &e->idx, &e->idx2, &e->key_b, &e->sstart, &e->send, &e->sscore, &e->windows, &e->nib_tmp, &e->slot_owned, &e->sowned, &e->out_owned, &e->var_info, &e->var_info2, &e->out2, &e->vk1, &e->vk2, &e->vk3, &e->vi1, &e->vi2, &e->vi3 }) b->release();
     for (auto& p : e->pinned_pool) dev::free_host(p.p);
     dev::free_host(e->h_count); dev::free_(e->d_count);
     for (auto& ev : e->ev) dev::event_destroy(ev);
@@ -1776,11 +1881,68 @@ int calitas_search(calitas_engine* e, const calitas_reference* ref, int32_t n_gu
   return search_impl(e, ref, n_guides, guides, limits, window_size, chrom, dedup, nullptr, out);
 }
 
+int calitas_variant_set_load(calitas_engine* e, const calitas_reference* ref, int64_t n_windows, const calitas_variant_window* windows, int64_t n_alleles, const calitas_variant_allele* alleles,
+                             int64_t n_sets, const uint32_t* set_rank, calitas_variant_set** out) {
+  return guarded([&]() -> int {
+    if (!e || !ref || !out || n_windows < 0 || (n_windows && !windows) || n_alleles < 0 || (n_alleles && !alleles) || n_sets < 0 || (n_sets && !set_rank)) throw InvalidArgument("bad variant arguments");
+    *out = nullptr;
+    if (n_windows >= (1ll << 31)) throw LimitExceeded("too many variant windows");
+    dev::set_device(e->device); dev::Stream s = e->stream;
+    std::unique_ptr<calitas_variant_set> vs(new calitas_variant_set());
+    vs->owner = e; vs->n_windows = n_windows; vs->n_alleles = n_alleles; vs->n_sets = n_sets; vs->n_contigs = (int32_t)ref->len.size();
+    // window bases: concatenated at multiples of 8 with a gap, uploaded raw and packed on the device like the reference
+    std::vector<VarWindowDev> wd((size_t)n_windows);
+    int64_t total = 64; int32_t prev_class = 0;
+    for (int64_t w = 0; w < n_windows; ++w) {
+      const calitas_variant_window& v = windows[w];
+      if (v.length < 0 || (uint32_t)v.length > MAX_WINDOW_LEN || (v.length && !v.bases) || v.n_alleles < 0 || v.first_allele < 0 || v.first_allele + (int64_t)v.n_alleles > n_alleles ||
+          v.first_set < 0 || v.first_set + (int64_t)v.n_alleles * (v.n_alleles + 1) / 2 > n_sets || v.contig_idx < 0 || v.contig_idx >= vs->n_contigs || v.guide_class < 0 || v.guide_class >= (1 << 20))
+        throw InvalidArgument("bad variant window");
+      if (v.guide_class < prev_class) throw InvalidArgument("variant windows must be sorted by guide_class");
+      prev_class = v.guide_class;
+      if ((size_t)v.guide_class >= vs->class_begin.size()) { vs->class_begin.resize((size_t)v.guide_class + 1, w); vs->class_end.resize((size_t)v.guide_class + 1, w); }
+      vs->class_end[(size_t)v.guide_class] = w + 1;
+      vs->max_len = std::max<uint32_t>(vs->max_len, (uint32_t)v.length);
+      wd[(size_t)w] = VarWindowDev{ total, v.length, v.contig_idx, v.ref_start, v.n_alleles, v.first_allele, v.first_set, v.owned ? 1 : 0, 0 };
+      total += (v.length + 7) / 8 * 8 + 8;
+    }
+    for (size_t c = 0; c < vs->class_begin.size(); ++c) if (vs->class_end[c] < vs->class_begin[c]) vs->class_end[c] = vs->class_begin[c];
+    total += 64;
+    for (int64_t k = 0; k < n_sets; ++k) vs->max_rank = std::max(vs->max_rank, set_rank[k]);
+    {
+      // the bases are copied into one staging buffer on all host threads (millions of small windows)
+      std::vector<uint8_t> raw((size_t)total, 0);
+      const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_windows / 65536 + 1, std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()))));
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) th.emplace_back([&, t]() { for (int64_t w = n_windows * t / nt; w < n_windows * (t + 1) / nt; ++w) if (windows[w].length) std::memcpy(raw.data() + wd[(size_t)w].nib_start, windows[w].bases, (size_t)windows[w].length); });
+      for (auto& t : th) t.join();
+      DBuf d_raw; d_raw.ensure((size_t)total); vs->nib.ensure((size_t)total / 2 + 8);
+      dev::h2d(d_raw.p, raw.data(), (size_t)total, s);
+      const int64_t n_words = total / 8;
+      const unsigned grid = (unsigned)std::min<int64_t>((n_words + 255) / 256, (int64_t)dev::sm_count(e->device) * 16);
+      CAL_LAUNCH(k_pack, grid, 256, 256, s, 2, d_raw.as<uint8_t>(), vs->nib.as<uint32_t>(), n_words); dev::launch_check("k_pack");
+      dev::stream_sync(s);
+      d_raw.release();
+      vs->nib_words = n_words;
+    }
+    vs->windows.ensure(std::max<size_t>(1, wd.size()) * sizeof(VarWindowDev)); dev::h2d(vs->windows.p, wd.data(), wd.size() * sizeof(VarWindowDev), s);
+    vs->alleles.ensure(std::max<size_t>(1, (size_t)n_alleles) * sizeof(calitas_variant_allele)); dev::h2d(vs->alleles.p, alleles, (size_t)n_alleles * sizeof(calitas_variant_allele), s);
+    vs->sets.ensure(std::max<size_t>(1, (size_t)n_sets) * 4); dev::h2d(vs->sets.p, set_rank, (size_t)n_sets * 4, s);
+    dev::stream_sync(s);
+    *out = vs.release();
+    return CALITAS_OK;
+  });
+}
+void calitas_variant_set_free(calitas_variant_set* vs) {
+  if (!vs) return;
+  try { if (vs->owner) dev::set_device(vs->owner->device); vs->nib.release(); vs->windows.release(); vs->alleles.release(); vs->sets.release(); } catch (...) {}
+  delete vs;
+}
+
 int calitas_search_variants(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides, const int32_t* guide_class, const calitas_limits* limits,
-                            int32_t window_size, const char* chrom, int64_t n_windows, const calitas_variant_window* windows, int64_t n_alleles, const calitas_variant_allele* alleles,
-                            int64_t n_sets, const uint32_t* set_rank, calitas_hitset** out) {
-  if (n_windows < 0 || (n_windows && (!windows || !guide_class)) || n_alleles < 0 || (n_alleles && !alleles) || n_sets < 0 || (n_sets && !set_rank)) return set_error(CALITAS_EINVAL, "bad variant arguments");
-  VariantPlan vp{ n_windows, windows, guide_class, alleles, n_alleles, set_rank, n_sets };
+                            int32_t window_size, const char* chrom, const calitas_variant_set* variants, calitas_hitset** out) {
+  if (!variants || !guide_class) return set_error(CALITAS_EINVAL, "bad variant arguments");
+  VariantPlan vp{ variants, guide_class };
   return search_impl(e, ref, n_guides, guides, limits, window_size, chrom, 1, &vp, out);
 }
 

@@ -462,6 +462,18 @@ struct VcfDevicePlan {
   std::vector<calitas_variant_allele> alleles; std::vector<uint32_t> set_id;
   std::vector<int32_t> first_allele, first_set;
   std::vector<std::vector<calitas_variant_window>> eng_windows; std::vector<std::vector<int32_t>> eng_flat;     // per engine: the windows it processes, and their index in `flat`
+  std::vector<calitas_variant_set*> eng_set;                    // per engine: the windows on its device (loaded by the first search)
+  std::mutex mu;
+  VcfDevicePlan() {}
+  VcfDevicePlan(const VcfDevicePlan&) = delete;
+  ~VcfDevicePlan() { for (auto* v : eng_set) calitas_variant_set_free(v); }
+  const calitas_variant_set* device_set(int s, calitas_engine* e, const calitas_reference* ref) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (eng_set.size() < eng_windows.size()) eng_set.resize(eng_windows.size(), nullptr);
+    if (!eng_set[(size_t)s]) ck(calitas_variant_set_load(e, ref, (int64_t)eng_windows[(size_t)s].size(), eng_windows[(size_t)s].data(), (int64_t)alleles.size(), alleles.data(),
+                                                         (int64_t)set_id.size(), set_id.data(), &eng_set[(size_t)s]));
+    return eng_set[(size_t)s];
+  }
 };
 extern "C" int calitas_reference_own_range(const calitas_reference* r, int32_t contig, int64_t* own_begin, int64_t* own_end);
 
@@ -648,8 +660,7 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
       auto search_batch = [&](int g0, int g1, std::vector<HitSet>& into) {
         run_all([&](int s) {
           if (device_vcf) ck(calitas_search_variants(engines[s], refs[s], g1 - g0, guides + g0, vplan.guide_class.data() + g0, &opt->limits, opt->window_size, opt->chrom,
-                                                     (int64_t)vplan.eng_windows[(size_t)s].size(), vplan.eng_windows[(size_t)s].data(), (int64_t)vplan.alleles.size(), vplan.alleles.data(),
-                                                     (int64_t)vplan.set_id.size(), vplan.set_id.data(), &into[(size_t)s].h));
+                                                     vplan.device_set(s, engines[s], refs[s]), &into[(size_t)s].h));
           else ck(calitas_search(engines[s], refs[s], g1 - g0, guides + g0, &opt->limits, opt->window_size, opt->chrom, host_dedup ? 0 : 1, &into[(size_t)s].h)); });
       };
       std::vector<HitSet> hs((size_t)n_engines);
@@ -945,12 +956,14 @@ int calitas_tool_variant_plan_counts(const calitas_variant_plan* p, int32_t engi
   return CALITAS_OK;
 }
 // calitas_search_variants for engine `engine` of the plan (the guides must be the ones the plan was built for)
-int calitas_tool_variant_plan_search(const calitas_variant_plan* p, int32_t engine, calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
+int calitas_tool_variant_plan_search(calitas_variant_plan* p, int32_t engine, calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
                                      const calitas_limits* limits, int32_t window_size, const char* chrom, calitas_hitset** out) {
   if (!p || engine < 0 || engine >= (int32_t)p->plan.eng_windows.size() || n_guides != (int32_t)p->plan.guide_class.size()) return calitas_tools_set_error(CALITAS_EINVAL, "bad arguments");
-  const VcfDevicePlan& P = p->plan;
-  return calitas_search_variants(e, ref, n_guides, guides, P.guide_class.data(), limits, window_size, chrom, (int64_t)P.eng_windows[(size_t)engine].size(), P.eng_windows[(size_t)engine].data(),
-                                 (int64_t)P.alleles.size(), P.alleles.data(), (int64_t)P.set_id.size(), P.set_id.data(), out);
+  return guarded([&]() -> int {
+    VcfDevicePlan& P = p->plan;
+    ck(calitas_search_variants(e, ref, n_guides, guides, P.guide_class.data(), limits, window_size, chrom, P.device_set(engine, e, ref), out));   // the first call uploads the windows
+    return CALITAS_OK;
+  });
 }
 
 int calitas_tool_variant_windows(const calitas_genome_view* genome, const char* vcf_text, const char* chrom, int32_t padding, int32_t max_variants, char** out_text) {

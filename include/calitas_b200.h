@@ -154,6 +154,7 @@ int calitas_search_sharded(int32_t n_engines, calitas_engine* const* engines, co
  *               sets carry equal values > 0, and the values order the groups the way the caller wants rows that tie on (contig, start, strand, score)
  *               ordered (the reference's own order among such rows is a HashMap's);
  *   owned = 0   marks a halo window of a sharded run: its hits take part in removeOverlaps and are never reported.
+ * The windows live on the device as a calitas_variant_set; calitas_search_variants builds the (guide, window) tasks there.
  * The result set holds records in ReferenceHit.sort order per guide, and one calitas_variant_hit_info per record (calitas_hitset_variant_info):
  * hits of variant windows keep window-relative offsets in the record (task_idx = window index) and carry the reference offsets here. */
 typedef struct calitas_variant_allele { int32_t pos /* 1-based POS */, ref_len, alt_len; } calitas_variant_allele;
@@ -167,10 +168,13 @@ typedef struct calitas_variant_hit_info {
   int32_t start_offset, end_offset, guide_start_offset, guide_end_offset;      /* reference coordinates (SearchReference.scala:615-620) */
   int32_t set_rank;                          /* 0: the hit overlaps no variant of its window */
 } calitas_variant_hit_info;
+/* The variant windows of one VCF on the engine's device (uploaded and packed once, like the reference; sorted by guide_class). */
+typedef struct calitas_variant_set calitas_variant_set;
+int calitas_variant_set_load(calitas_engine* e, const calitas_reference* ref, int64_t n_windows, const calitas_variant_window* windows,
+                             int64_t n_alleles, const calitas_variant_allele* alleles, int64_t n_sets, const uint32_t* set_rank, calitas_variant_set** out);
+void calitas_variant_set_free(calitas_variant_set* variants);
 int calitas_search_variants(calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides, const int32_t* guide_class,
-                            const calitas_limits* limits, int32_t window_size, const char* chrom,
-                            int64_t n_windows, const calitas_variant_window* windows, int64_t n_alleles, const calitas_variant_allele* alleles,
-                            int64_t n_sets, const uint32_t* set_rank, calitas_hitset** out);
+                            const calitas_limits* limits, int32_t window_size, const char* chrom, const calitas_variant_set* variants, calitas_hitset** out);
 const calitas_variant_hit_info* calitas_hitset_variant_info(const calitas_hitset* h);   /* NULL unless the set came from calitas_search_variants */
 
 /* ---- AlignToReference / variant windows -----------------------------------------------------------------------

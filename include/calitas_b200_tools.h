@@ -76,13 +76,14 @@ int calitas_tool_pairwise_align(calitas_engine* e, int64_t n_pairs, const char* 
 
 /* SearchReference -v in two steps, for callers that search the same VCF repeatedly: the plan holds the parsed VCF, the variant windows of every padding
  * class of the guides (SearchReference.scala:217-399, 575) and, per engine, the windows it processes (owned, or halo around its shard's cuts);
- * calitas_tool_variant_plan_search runs calitas_search_variants for one engine of it.  calitas_tool_search_reference* build such a plan internally. */
+ * calitas_tool_variant_plan_search runs calitas_search_variants for one engine of it (its first call uploads that
+ * engine's windows: calitas_variant_set_load).  calitas_tool_search_reference* build such a plan internally. */
 typedef struct calitas_variant_plan calitas_variant_plan;
 int calitas_tool_variant_plan_create(const calitas_genome_view* genome, const calitas_search_options* opt, int32_t n_guides, const calitas_guide* guides,
                                      int32_t n_engines, const calitas_reference* const* refs, calitas_variant_plan** out);
 void calitas_tool_variant_plan_free(calitas_variant_plan* p);
 int calitas_tool_variant_plan_counts(const calitas_variant_plan* p, int32_t engine, int64_t* n_records, int64_t* n_windows, int64_t* n_window_bases);
-int calitas_tool_variant_plan_search(const calitas_variant_plan* p, int32_t engine, calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
+int calitas_tool_variant_plan_search(calitas_variant_plan* p, int32_t engine, calitas_engine* e, const calitas_reference* ref, int32_t n_guides, const calitas_guide* guides,
                                      const calitas_limits* limits, int32_t window_size, const char* chrom, calitas_hitset** out);
 
 /* Inspection hook for the variant path (SearchReference.scala:217-399): one line per variant window
