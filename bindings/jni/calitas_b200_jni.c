@@ -11,7 +11,7 @@
  *
  * Conventions: handles travel as jlong; a failing call throws IllegalArgumentException (CALITAS_EINVAL = the reference's require())
  * or IllegalStateException with calitas_last_error() and returns 0 / NULL; hit records come back as a direct ByteBuffer over the
- * engine's pinned host memory (72-byte little-endian calitas_hit records), valid until hitsetFree(handle).
+ * engine's pinned host memory (little-endian calitas_hit records, hitsetStride(handle) = 32 or 64 bytes each), valid until hitsetFree(handle).
  */
 #include <jni.h>
 #include <stdint.h>
@@ -29,20 +29,32 @@ static void throw_for(JNIEnv* env, int rc, const char* fallback) {
   if (c) (*env)->ThrowNew(env, c, (msg && msg[0]) ? msg : fallback);
 }
 
-/* String[] guides + String[][] auxPams -> calitas_guide[]; everything is released by free_guides after the call (the engine copies what it keeps). */
-typedef struct guide_pack {
-  jsize n; calitas_guide* g; jstring* seq_ref; const char** seq; jsize* n_aux; jstring** aux_ref; const char*** aux;
-} guide_pack;
+/* A Java String copied into malloc'd memory; the local reference and the JVM's UTF buffer are released at once, so that loops over thousands of
+ * elements never fill the local-reference table (JNI guarantees 16 slots) nor hold JVM buffers. */
+static char* dup_jstring(JNIEnv* env, jstring s) {
+  if (!s) return NULL;
+  const char* u = (*env)->GetStringUTFChars(env, s, NULL);
+  char* c = NULL;
+  if (u) { size_t n = strlen(u); c = (char*)malloc(n + 1); if (c) memcpy(c, u, n + 1); (*env)->ReleaseStringUTFChars(env, s, u); }
+  return c;
+}
+static char* dup_array_string(JNIEnv* env, jobjectArray arr, jsize i) {
+  jstring s = (jstring)(*env)->GetObjectArrayElement(env, arr, i);
+  char* c = dup_jstring(env, s);
+  if (s) (*env)->DeleteLocalRef(env, s);
+  return c;
+}
 
-static void free_guides(JNIEnv* env, guide_pack* p) {
+/* String[] guides + String[][] auxPams -> calitas_guide[] over owned copies; free_guides releases them after the call (the engine copies what it keeps). */
+typedef struct guide_pack { jsize n; calitas_guide* g; char** seq; jsize* n_aux; char*** aux; } guide_pack;
+
+static void free_guides(guide_pack* p) {
   if (!p->g) return;
   for (jsize i = 0; i < p->n; ++i) {
-    if (p->seq && p->seq[i]) (*env)->ReleaseStringUTFChars(env, p->seq_ref[i], p->seq[i]);
-    if (p->aux && p->aux[i]) { for (jsize k = 0; k < p->n_aux[i]; ++k) if (p->aux[i][k]) (*env)->ReleaseStringUTFChars(env, p->aux_ref[i][k], p->aux[i][k]); }
-    if (p->aux) free((void*)p->aux[i]);
-    if (p->aux_ref) free(p->aux_ref[i]);
+    if (p->seq) free(p->seq[i]);
+    if (p->aux && p->aux[i]) { for (jsize k = 0; k < p->n_aux[i]; ++k) free(p->aux[i][k]); free(p->aux[i]); }
   }
-  free(p->g); free(p->seq_ref); free((void*)p->seq); free(p->n_aux); free(p->aux_ref); free((void*)p->aux);
+  free(p->g); free(p->seq); free(p->n_aux); free(p->aux);
   memset(p, 0, sizeof *p);
 }
 
@@ -51,27 +63,24 @@ static int pack_guides(JNIEnv* env, jobjectArray guides, jobjectArray auxPams, g
   if (!guides) return 0;
   p->n = (*env)->GetArrayLength(env, guides);
   const size_t n = (size_t)(p->n > 0 ? p->n : 1);
-  p->g = (calitas_guide*)calloc(n, sizeof *p->g); p->seq_ref = (jstring*)calloc(n, sizeof *p->seq_ref); p->seq = (const char**)calloc(n, sizeof *p->seq);
-  p->n_aux = (jsize*)calloc(n, sizeof *p->n_aux); p->aux_ref = (jstring**)calloc(n, sizeof *p->aux_ref); p->aux = (const char***)calloc(n, sizeof *p->aux);
-  if (!p->g || !p->seq_ref || !p->seq || !p->n_aux || !p->aux_ref || !p->aux) return 0;
+  p->g = (calitas_guide*)calloc(n, sizeof *p->g); p->seq = (char**)calloc(n, sizeof *p->seq);
+  p->n_aux = (jsize*)calloc(n, sizeof *p->n_aux); p->aux = (char***)calloc(n, sizeof *p->aux);
+  if (!p->g || !p->seq || !p->n_aux || !p->aux) return 0;
   for (jsize i = 0; i < p->n; ++i) {
-    p->seq_ref[i] = (jstring)(*env)->GetObjectArrayElement(env, guides, i);
-    if (!p->seq_ref[i]) return 0;
-    p->seq[i] = (*env)->GetStringUTFChars(env, p->seq_ref[i], NULL);
+    p->seq[i] = dup_array_string(env, guides, i);
     if (!p->seq[i]) return 0;
     jobjectArray aux = auxPams ? (jobjectArray)(*env)->GetObjectArrayElement(env, auxPams, i) : NULL;
     p->n_aux[i] = aux ? (*env)->GetArrayLength(env, aux) : 0;
     if (p->n_aux[i] > 0) {
-      p->aux_ref[i] = (jstring*)calloc((size_t)p->n_aux[i], sizeof(jstring)); p->aux[i] = (const char**)calloc((size_t)p->n_aux[i], sizeof(char*));
-      if (!p->aux_ref[i] || !p->aux[i]) return 0;
+      p->aux[i] = (char**)calloc((size_t)p->n_aux[i], sizeof(char*));
+      if (!p->aux[i]) { (*env)->DeleteLocalRef(env, aux); return 0; }
       for (jsize k = 0; k < p->n_aux[i]; ++k) {
-        p->aux_ref[i][k] = (jstring)(*env)->GetObjectArrayElement(env, aux, k);
-        if (!p->aux_ref[i][k]) return 0;
-        p->aux[i][k] = (*env)->GetStringUTFChars(env, p->aux_ref[i][k], NULL);
-        if (!p->aux[i][k]) return 0;
+        p->aux[i][k] = dup_array_string(env, aux, k);
+        if (!p->aux[i][k]) { (*env)->DeleteLocalRef(env, aux); return 0; }
       }
     }
-    p->g[i].sequence = p->seq[i]; p->g[i].aux_pams = p->aux[i]; p->g[i].n_aux_pams = (int32_t)p->n_aux[i];
+    if (aux) (*env)->DeleteLocalRef(env, aux);
+    p->g[i].sequence = p->seq[i]; p->g[i].aux_pams = (const char* const*)p->aux[i]; p->g[i].n_aux_pams = (int32_t)p->n_aux[i];
   }
   return 1;
 }
@@ -87,7 +96,7 @@ static int read_limits(JNIEnv* env, jintArray limits, calitas_limits* out) {    
 static jobject wrap_hits(JNIEnv* env, calitas_hitset* hs, jlongArray outHandle) {
   jlong h = (jlong)(intptr_t)hs;
   (*env)->SetLongArrayRegion(env, outHandle, 0, 1, &h);                                   /* the caller frees with hitsetFree(handle) */
-  return (*env)->NewDirectByteBuffer(env, (void*)calitas_hitset_data(hs), (jlong)calitas_hitset_count(hs) * (jlong)sizeof(calitas_hit));
+  return (*env)->NewDirectByteBuffer(env, (void*)calitas_hitset_data(hs), (jlong)calitas_hitset_count(hs) * (jlong)calitas_hitset_stride(hs));   /* 32- or 64-byte records: hitsetStride(handle) */
 }
 
 /* ---- engine: new SequentialGuideAligner(mismatchNetCost, genomeGapNetCost, guideGapNetCost, pamMismatchNetCost) ------------------------ */
@@ -129,9 +138,10 @@ JNIEXPORT jlong JNICALL JFN(referenceLoad)(JNIEnv* env, jclass cls, jlong engine
   (void)cls;
   const jsize n = (*env)->GetArrayLength(env, names);
   const size_t nn = (size_t)(n > 0 ? n : 1);
-  jstring* name_ref = (jstring*)calloc(nn, sizeof(jstring)); const char** name = (const char**)calloc(nn, sizeof(char*));
+  char** name = (char**)calloc(nn, sizeof(char*));
   const uint8_t** ptr = (const uint8_t**)calloc(nn, sizeof(uint8_t*)); int64_t* num = (int64_t*)calloc(nn * 5, sizeof(int64_t));
-  calitas_reference* ref = NULL; int rc = CALITAS_ESTATE; int ok = name_ref && name && ptr && num;
+  calitas_reference* ref = NULL; int rc = CALITAS_ESTATE; int ok = name && ptr && num;
+  const char* why = "bad reference arguments";
   if (ok) {
     (*env)->GetLongArrayRegion(env, lengths, 0, n, (jlong*)num);
     const int ranges = haveBegin && haveEnd && ownBegin && ownEnd;
@@ -140,18 +150,23 @@ JNIEXPORT jlong JNICALL JFN(referenceLoad)(JNIEnv* env, jclass cls, jlong engine
       (*env)->GetLongArrayRegion(env, ownBegin, 0, n, (jlong*)(num + 3 * n)); (*env)->GetLongArrayRegion(env, ownEnd, 0, n, (jlong*)(num + 4 * n));
     }
     for (jsize c = 0; c < n && ok; ++c) {
-      name_ref[c] = (jstring)(*env)->GetObjectArrayElement(env, names, c);
-      name[c] = name_ref[c] ? (*env)->GetStringUTFChars(env, name_ref[c], NULL) : NULL;
+      name[c] = dup_array_string(env, names, c);
+      if (!name[c]) { ok = 0; break; }
+      const int64_t need = ranges ? num[2 * n + c] - num[n + c] : num[c];                 /* bases the engine will read from this buffer */
       jobject b = (*env)->GetObjectArrayElement(env, bases, c);
-      ptr[c] = b ? (const uint8_t*)(*env)->GetDirectBufferAddress(env, b) : NULL;
-      if (!name[c]) ok = 0;
+      if (b) {
+        ptr[c] = (const uint8_t*)(*env)->GetDirectBufferAddress(env, b);
+        const jlong cap = (*env)->GetDirectBufferCapacity(env, b);
+        (*env)->DeleteLocalRef(env, b);
+        if (!ptr[c] || cap < need) { ok = 0; why = "a contig's direct buffer is shorter than its base range (or not a direct buffer)"; }
+      } else if (need > 0) { ok = 0; why = "a contig with bases to load has no buffer"; }
     }
-    if (ok) rc = calitas_reference_load(PTR(calitas_engine, engine), (int32_t)n, name, num, ptr, ranges ? num + n : NULL, ranges ? num + 2 * n : NULL,
+    if (ok) rc = calitas_reference_load(PTR(calitas_engine, engine), (int32_t)n, (const char* const*)name, num, ptr, ranges ? num + n : NULL, ranges ? num + 2 * n : NULL,
                                         ranges ? num + 3 * n : NULL, ranges ? num + 4 * n : NULL, 0, &ref);
-    for (jsize c = 0; c < n; ++c) if (name[c]) (*env)->ReleaseStringUTFChars(env, name_ref[c], name[c]);
+    for (jsize c = 0; c < n; ++c) free(name[c]);
   }
-  free(name_ref); free((void*)name); free((void*)ptr); free(num);
-  if (!ok) { throw_for(env, CALITAS_EINVAL, "bad reference arguments"); return 0; }
+  free(name); free((void*)ptr); free(num);
+  if (!ok) { jclass c = (*env)->FindClass(env, "java/lang/IllegalArgumentException"); if (c) (*env)->ThrowNew(env, c, why); return 0; }
   if (rc) { throw_for(env, rc, "calitas_reference_load failed"); return 0; }
   return (jlong)(intptr_t)ref;
 }
@@ -164,11 +179,11 @@ JNIEXPORT jobject JNICALL JFN(search)(JNIEnv* env, jclass cls, jlong engine, jlo
   (void)cls;
   calitas_limits lim; guide_pack gp; calitas_hitset* hs = NULL; jobject out = NULL;
   if (!read_limits(env, limits, &lim)) { throw_for(env, CALITAS_EINVAL, "limits must hold 5 values"); return NULL; }
-  if (!pack_guides(env, guides, auxPams, &gp)) { free_guides(env, &gp); throw_for(env, CALITAS_EINVAL, "bad guide arguments"); return NULL; }
-  const char* chrom_utf = chrom ? (*env)->GetStringUTFChars(env, chrom, NULL) : NULL;
-  const int rc = calitas_search(PTR(calitas_engine, engine), PTR(const calitas_reference, ref), (int32_t)gp.n, gp.g, &lim, windowSize, chrom_utf, dedup ? 1 : 0, &hs);
-  if (chrom_utf) (*env)->ReleaseStringUTFChars(env, chrom, chrom_utf);
-  free_guides(env, &gp);
+  if (!pack_guides(env, guides, auxPams, &gp)) { free_guides(&gp); throw_for(env, CALITAS_EINVAL, "bad guide arguments"); return NULL; }
+  char* chrom_c = dup_jstring(env, chrom);
+  const int rc = calitas_search(PTR(calitas_engine, engine), PTR(const calitas_reference, ref), (int32_t)gp.n, gp.g, &lim, windowSize, chrom_c, dedup ? 1 : 0, &hs);
+  free(chrom_c);
+  free_guides(&gp);
   if (rc) throw_for(env, rc, "calitas_search failed"); else out = wrap_hits(env, hs, outHandle);
   return out;
 }
@@ -179,25 +194,36 @@ JNIEXPORT jobject JNICALL JFN(alignTargets)(JNIEnv* env, jclass cls, jlong engin
   (void)cls;
   calitas_limits lim; guide_pack gp; calitas_hitset* hs = NULL; jobject out = NULL;
   if (!read_limits(env, limits, &lim)) { throw_for(env, CALITAS_EINVAL, "limits must hold 5 values"); return NULL; }
-  if (!pack_guides(env, guides, auxPams, &gp)) { free_guides(env, &gp); throw_for(env, CALITAS_EINVAL, "bad guide arguments"); return NULL; }
+  if (!pack_guides(env, guides, auxPams, &gp)) { free_guides(&gp); throw_for(env, CALITAS_EINVAL, "bad guide arguments"); return NULL; }
   const jsize n = (*env)->GetArrayLength(env, targets);
   const size_t nn = (size_t)(n > 0 ? n : 1);
-  calitas_target_task* tasks = (calitas_target_task*)calloc(nn, sizeof *tasks); jbyteArray* arr = (jbyteArray*)calloc(nn, sizeof *arr);
-  jint* gi = (jint*)calloc(nn, sizeof *gi); jint* off = (jint*)calloc(nn, sizeof *off);
+  calitas_target_task* tasks = (calitas_target_task*)calloc(nn, sizeof *tasks);
+  jint* gi = (jint*)calloc(nn, sizeof *gi); jint* off = (jint*)calloc(nn, sizeof *off); size_t* at = (size_t*)calloc(nn + 1, sizeof *at);
+  uint8_t* pool = NULL;
   int rc = CALITAS_ESTATE;
-  if (tasks && arr && gi && off) {
+  if (tasks && gi && off && at) {
     (*env)->GetIntArrayRegion(env, guideIdx, 0, n, gi); (*env)->GetIntArrayRegion(env, targetOffsets, 0, n, off);
-    for (jsize t = 0; t < n; ++t) {                                                     /* byte[] targets are copied by the JVM or pinned; released below */
-      arr[t] = (jbyteArray)(*env)->GetObjectArrayElement(env, targets, t);
-      tasks[t].guide_idx = gi[t]; tasks[t].target_offset = off[t];
-      tasks[t].length = arr[t] ? (int32_t)(*env)->GetArrayLength(env, arr[t]) : 0;
-      tasks[t].bases = arr[t] ? (const uint8_t*)(*env)->GetByteArrayElements(env, arr[t], NULL) : NULL;
+    /* two passes, one local reference alive at a time: sizes, then one copy of every target into a single pool (no per-array pinning) */
+    for (jsize t = 0; t < n; ++t) {
+      jbyteArray a = (jbyteArray)(*env)->GetObjectArrayElement(env, targets, t);
+      const jsize len = a ? (*env)->GetArrayLength(env, a) : 0;
+      if (a) (*env)->DeleteLocalRef(env, a);
+      at[t + 1] = at[t] + (size_t)len;
     }
-    rc = calitas_align_targets(PTR(calitas_engine, engine), (int32_t)gp.n, gp.g, (int64_t)n, tasks, &lim, best ? 1 : 0, &hs);
-    for (jsize t = 0; t < n; ++t) if (tasks[t].bases) (*env)->ReleaseByteArrayElements(env, arr[t], (jbyte*)tasks[t].bases, JNI_ABORT);
+    pool = (uint8_t*)malloc(at[n] ? at[n] : 1);
+    if (pool) {
+      for (jsize t = 0; t < n; ++t) {
+        const jsize len = (jsize)(at[t + 1] - at[t]);
+        jbyteArray a = (jbyteArray)(*env)->GetObjectArrayElement(env, targets, t);
+        if (a && len > 0) (*env)->GetByteArrayRegion(env, a, 0, len, (jbyte*)(pool + at[t]));
+        if (a) (*env)->DeleteLocalRef(env, a);
+        tasks[t].guide_idx = gi[t]; tasks[t].target_offset = off[t]; tasks[t].length = (int32_t)len; tasks[t].bases = pool + at[t];
+      }
+      rc = calitas_align_targets(PTR(calitas_engine, engine), (int32_t)gp.n, gp.g, (int64_t)n, tasks, &lim, best ? 1 : 0, &hs);
+    }
   }
-  free(tasks); free(arr); free(gi); free(off);
-  free_guides(env, &gp);
+  free(tasks); free(gi); free(off); free(at); free(pool);
+  free_guides(&gp);
   if (rc) throw_for(env, rc, "calitas_align_targets failed"); else out = wrap_hits(env, hs, outHandle);
   return out;
 }
@@ -208,7 +234,7 @@ JNIEXPORT jobject JNICALL JFN(alignRegions)(JNIEnv* env, jclass cls, jlong engin
   (void)cls;
   calitas_limits lim; guide_pack gp; calitas_hitset* hs = NULL; jobject out = NULL;
   if (!read_limits(env, limits, &lim)) { throw_for(env, CALITAS_EINVAL, "limits must hold 5 values"); return NULL; }
-  if (!pack_guides(env, guides, auxPams, &gp)) { free_guides(env, &gp); throw_for(env, CALITAS_EINVAL, "bad guide arguments"); return NULL; }
+  if (!pack_guides(env, guides, auxPams, &gp)) { free_guides(&gp); throw_for(env, CALITAS_EINVAL, "bad guide arguments"); return NULL; }
   const jsize n = (*env)->GetArrayLength(env, guideIdx);
   const size_t nn = (size_t)(n > 0 ? n : 1);
   calitas_region_task* tasks = (calitas_region_task*)calloc(nn, sizeof *tasks);
@@ -221,9 +247,35 @@ JNIEXPORT jobject JNICALL JFN(alignRegions)(JNIEnv* env, jclass cls, jlong engin
     rc = calitas_align_regions(PTR(calitas_engine, engine), PTR(const calitas_reference, ref), (int32_t)gp.n, gp.g, (int64_t)n, tasks, &lim, best ? 1 : 0, &hs);
   }
   free(tasks); free(gi); free(ci); free(len); free(st);
-  free_guides(env, &gp);
+  free_guides(&gp);
   if (rc) throw_for(env, rc, "calitas_align_regions failed"); else out = wrap_hits(env, hs, outHandle);
   return out;
 }
 
+/* ---- the same over several engines (one per GPU), ONE merged table back (calitas_search_sharded) --------------------------------------------------- */
+JNIEXPORT jobject JNICALL JFN(searchSharded)(JNIEnv* env, jclass cls, jlongArray engines, jlongArray refs, jobjectArray guides, jobjectArray auxPams, jintArray limits,
+                                             jint windowSize, jstring chrom, jlongArray outHandle) {
+  (void)cls;
+  calitas_limits lim; guide_pack gp; calitas_hitset* hs = NULL; jobject out = NULL;
+  if (!read_limits(env, limits, &lim)) { throw_for(env, CALITAS_EINVAL, "limits must hold 5 values"); return NULL; }
+  const jsize ne = engines ? (*env)->GetArrayLength(env, engines) : 0;
+  if (ne <= 0 || !refs || (*env)->GetArrayLength(env, refs) != ne) { throw_for(env, CALITAS_EINVAL, "engines and refs must have the same, positive length"); return NULL; }
+  if (!pack_guides(env, guides, auxPams, &gp)) { free_guides(&gp); throw_for(env, CALITAS_EINVAL, "bad guide arguments"); return NULL; }
+  jlong* eh = (jlong*)calloc((size_t)ne, sizeof *eh); jlong* rh = (jlong*)calloc((size_t)ne, sizeof *rh);
+  calitas_engine** ep = (calitas_engine**)calloc((size_t)ne, sizeof *ep); const calitas_reference** rp = (const calitas_reference**)calloc((size_t)ne, sizeof *rp);
+  int rc = CALITAS_ESTATE;
+  if (eh && rh && ep && rp) {
+    (*env)->GetLongArrayRegion(env, engines, 0, ne, eh); (*env)->GetLongArrayRegion(env, refs, 0, ne, rh);
+    for (jsize s = 0; s < ne; ++s) { ep[s] = PTR(calitas_engine, eh[s]); rp[s] = PTR(const calitas_reference, rh[s]); }
+    char* chrom_c = dup_jstring(env, chrom);
+    rc = calitas_search_sharded((int32_t)ne, ep, rp, (int32_t)gp.n, gp.g, &lim, windowSize, chrom_c, &hs);
+    free(chrom_c);
+  }
+  free(eh); free(rh); free(ep); free((void*)rp);
+  free_guides(&gp);
+  if (rc) throw_for(env, rc, "calitas_search_sharded failed"); else out = wrap_hits(env, hs, outHandle);
+  return out;
+}
+
+JNIEXPORT jint JNICALL JFN(hitsetStride)(JNIEnv* env, jclass cls, jlong handle) { (void)env; (void)cls; return (jint)calitas_hitset_stride(PTR(calitas_hitset, handle)); }
 JNIEXPORT void JNICALL JFN(hitsetFree)(JNIEnv* env, jclass cls, jlong handle) { (void)env; (void)cls; calitas_hitset_free(PTR(calitas_hitset, handle)); }

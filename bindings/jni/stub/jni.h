@@ -26,5 +26,8 @@ struct JNINativeInterface_ {
   void (*ReleaseByteArrayElements)(JNIEnv*, jbyteArray, jbyte*, jint);
   jobject (*NewDirectByteBuffer)(JNIEnv*, void*, jlong);
   void* (*GetDirectBufferAddress)(JNIEnv*, jobject);
+  jlong (*GetDirectBufferCapacity)(JNIEnv*, jobject);
+  void (*DeleteLocalRef)(JNIEnv*, jobject);
+  void (*GetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, jbyte*);
 };
 #endif

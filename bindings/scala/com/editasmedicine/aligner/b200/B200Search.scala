@@ -7,7 +7,8 @@ import com.editasmedicine.aligner.SequentialGuideAligner.Guide
 
 /** What SearchReference.execute calls instead of its window loop (SearchReference.scala:527-564) and of removeOverlaps + ReferenceHit.sort
   * (:641-648) when no VCF is given: one engine per GPU, the genome sharded by contig range, every guide of the run in one call.
-  * The alignments come back de-duplicated and in ReferenceHit.sort order per guide; the caller feeds them to `hitBuilder.build` as before.
+  * The alignments come back de-duplicated and in ReferenceHit.sort order per guide, in ONE table whatever the number of engines (the shard
+  * lists are merged at the cuts on the native side); the caller feeds them to `hitBuilder.build` as before.
   * Uncompiled here (no scalac in this image).
   *
   * @param devices     CUDA device ids, one engine each
@@ -35,22 +36,22 @@ final class B200Search(devices: Seq[Int], costs: Array[Int], contigNames: Array[
     val pams    = guides.map { case (g, aux) => (g.filter(_.isLower) +: aux).filter(_.nonEmpty).toIndexedSeq }
     val limits  = Array(maxGuideDiffs, maxPamMismatches, maxGapsBetweenGuideAndPam, maxTotalDiffs, maxOverlap)
     val out     = Array.fill(guides.length)(IndexedSeq.newBuilder[GuideAlignment])
-    // shards are independent: run the engines on their own threads, then concatenate per guide in shard order
-    val results = engines.indices.par.map { s =>
-      val handle = new Array[Long](1)
-      val buf = Native.search(engines(s), refs(s), guides.map(_._1).toArray, guides.map(_._2.toArray).toArray, limits, windowSize, chrom.orNull, true, handle)
-      (buf, handle(0))
-    }.seq
-    results.foreach { case (buf, handle) =>
-      var i = 0
-      while (i < HitDecoder.count(buf)) {
-        val r = HitDecoder.raw(buf, i)
-        val fetch = (start: Int, end: Int) => { val a = new Array[Byte](end - start); val b = contigBases(r.contigIdx).duplicate(); b.position(start); b.get(a); new String(a).toUpperCase.getBytes }
-        out(r.guideIdx) += HitDecoder.decode(r, parsed(r.guideIdx), pams(r.guideIdx), contigNames(r.contigIdx), fetch)
-        i += 1
-      }
-      Native.hitsetFree(handle)
+    require(maxOverlap >= 1 || engines.length == 1,
+      "with --max-overlap <= 0 removeOverlaps reaches across the whole contig and cannot run per shard: use one engine (or search with dedup = false and run removeOverlaps over the gathered hits)")
+    // The shards run concurrently inside the native call.  Their per-guide lists are NOT simply concatenated: consecutive windows overlap by
+    // guide length + d + g - 1 bases, so the last window of one shard and the first of the next can report hits whose starts interleave; the native
+    // side merges each guide's lists by the ReferenceHit.sort key where they meet (calitas_search_sharded, merge_guide_segments) and returns ONE table.
+    val handle = new Array[Long](1)
+    val buf    = Native.searchSharded(engines, refs, guides.map(_._1).toArray, guides.map(_._2.toArray).toArray, limits, windowSize, chrom.orNull, handle)
+    val stride = Native.hitsetStride(handle(0))
+    var i = 0
+    while (i < HitDecoder.count(buf, stride)) {
+      val r = HitDecoder.raw(buf, i, stride)
+      val fetch = (start: Int, end: Int) => { val a = new Array[Byte](end - start); val b = contigBases(r.contigIdx).duplicate(); b.position(start); b.get(a); new String(a).toUpperCase.getBytes }
+      out(r.guideIdx) += HitDecoder.decode(r, parsed(r.guideIdx), pams(r.guideIdx), contigNames(r.contigIdx), fetch)
+      i += 1
     }
+    Native.hitsetFree(handle(0))
     out.map(_.result()).toIndexedSeq
   }
 

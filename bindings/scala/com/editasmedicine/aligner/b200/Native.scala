@@ -9,7 +9,7 @@ import java.nio.ByteBuffer
   *
   * Handles are opaque pointers carried as Long.  A failing call throws IllegalArgumentException where the reference's `require`
   * would (CALITAS_EINVAL) and IllegalStateException otherwise.  Hit records come back as a direct ByteBuffer over the engine's
-  * pinned host memory: 72-byte little-endian records (HitDecoder), valid until hitsetFree(handle).
+  * pinned host memory: little-endian records of hitsetStride(handle) = 32 or 64 bytes (HitDecoder), valid until hitsetFree(handle).
   */
 object Native {
   System.loadLibrary("calitas_b200_jni")
@@ -41,5 +41,12 @@ object Native {
                            contigIdx: Array[Int], starts: Array[Long], lengths: Array[Int], limits: Array[Int], best: Boolean,
                            outHandle: Array[Long]): ByteBuffer
 
+  /** The same over several engines (engine s holds shard s of shardPlan(.., s, engines.length, ..) in refs(s)): the engines run concurrently on native
+    * threads and ONE table comes back, merged per guide at the shard cuts (calitas_search_sharded).  Needs maxOverlap >= 1. */
+  @native def searchSharded(engines: Array[Long], refs: Array[Long], guides: Array[String], auxPams: Array[Array[String]], limits: Array[Int],
+                            windowSize: Int, chrom: String, outHandle: Array[Long]): ByteBuffer
+
+  /** Bytes per record of a result set: 32 (calitas_hit) or 64 (calitas_hit_wide). */
+  @native def hitsetStride(handle: Long): Int
   @native def hitsetFree(handle: Long): Unit
 }
