@@ -894,18 +894,36 @@ CAL_HD int32_t soa_overlap(const int32_t* s_start, const int32_t* s_end, int64_t
 // With segmented != 0 (max_overlap >= 1) a segment also starts where a hit begins more than CALITAS_MAX_OPS bases after its predecessor in the
 // list: no earlier hit of either strand can then overlap it at all, so both chains restart there unconditionally and segments are
 // independent.  With max_overlap <= 0 every later hit "overlaps" (>= 0) and a (guide, contig) run is swept by one thread.
+// Halo sentinel (sharded references): a run that begins with halo hits begins at an interior shard cut, where this engine does not know the state of the
+// reference's loop (its current hit may be one this shard never saw).  A hit R is a RESTART -- it ends any skipping and becomes the current hit whatever came
+// before, in the reference's loop as in this one -- when it overlaps every earlier hit of its strand by less than max_overlap.  For the hits this shard sees
+// that is checked directly; the hits it does not see lie in windows more than HALO_WINDOWS before its first owned window, i.e. they end before
+// (first owned hit's start) - halo_bases, so they cannot touch a hit that starts at or after that.  The first owned hit of a run is therefore decided exactly
+// iff such a restart exists at or before it; if not, the halo was too short for this input and *unsafe is raised: the call fails with CALITAS_ELIMIT
+// instead of returning a guess ("Multi-GPU").
 CAL_KERNEL __launch_bounds__(128) k_sweep(const uint64_t* key, const int32_t* s_start, const int32_t* s_end, const int32_t* s_score, const uint8_t* s_owned, int64_t n, int32_t max_overlap,
                                           int32_t segmented, int32_t strand_shift /* bit of the strand; the (guide, contig) run is key >> (strand_shift + 1 + start_bits) */, int32_t start_bits,
-                                          uint32_t* keep) {
+                                          uint32_t* keep, uint32_t* unsafe, int32_t halo_bases) {
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i0 >= n) return;
   const int gshift = strand_shift + 1 + start_bits;
   const uint64_t grp = key[i0] >> gshift;
-  if (i0 > 0 && (key[i0 - 1] >> gshift) == grp && !(segmented && s_start[i0] - s_start[i0 - 1] > CALITAS_MAX_OPS)) return;
+  const bool run_start = i0 == 0 || (key[i0 - 1] >> gshift) != grp;
+  if (!run_start && !(segmented && s_start[i0] - s_start[i0 - 1] > CALITAS_MAX_OPS)) return;
   int64_t cur[2] = { -1, -1 };
+  const bool at_cut = run_start && !s_owned[i0];            // the list continues to the left, out of this shard's sight
+  bool unknown[2] = { at_cut, at_cut }; int32_t max_end[2] = { -0x7FFFFFFF, -0x7FFFFFFF }, last_restart[2] = { -0x7FFFFFFF, -0x7FFFFFFF };
   for (int64_t i = i0; i < n; ++i) {
     if (i > i0 && ((key[i] >> gshift) != grp || (segmented && s_start[i] - s_start[i - 1] > CALITAS_MAX_OPS))) break;
     const int st = (int)((key[i] >> strand_shift) & 1ull);
+    if (unknown[st]) {
+      if (max_end[st] == -0x7FFFFFFF || max_end[st] - s_start[i] < max_overlap) last_restart[st] = s_start[i];      // overlaps every earlier visible hit by < max_overlap
+      if (s_owned[i]) {                                      // the first owned hit of this strand: was there a restart out of the unseen hits' reach?
+        if (last_restart[st] == -0x7FFFFFFF || last_restart[st] < s_start[i] - halo_bases) *unsafe = 1u;
+        unknown[st] = false;
+      }
+      if (s_end[i] > max_end[st]) max_end[st] = s_end[i];
+    }
     const int64_t c = cur[st];
     if (c < 0) cur[st] = i;
     else if (soa_overlap(s_start, s_end, i, c) >= max_overlap && s_score[i] <= s_score[c]) keep[i] = 0;
@@ -1107,7 +1125,7 @@ struct calitas_variant_set {
   std::vector<int64_t> class_begin, class_end;          // windows are sorted by guide_class
 };
 
-enum { CNT_GROUPS = 3, CNT_KEPT = 4, CNT_KEEPERS = 5 /* + 6: overflow flag as published */, CNT_DEDUP_OVERFLOW = 7 };
+enum { CNT_GROUPS = 3, CNT_KEPT = 4, CNT_KEEPERS = 5 /* + 6: overflow flag as published */, CNT_DEDUP_OVERFLOW = 7 /* low word: key overflow; high word: halo sentinel */ };
 enum { CE_SCAN_B = 0, CE_SCAN_E, CE_COUNT, CE_SORTED, CE_ALIGN_B, CE_ALIGN_E, CE_TAIL_B, CE_TAIL_E, CE_COPY_B, CE_COPY_E, CE_N };
 struct ChunkEvents { dev::Event ev[CE_N]; };
 
@@ -1208,6 +1226,7 @@ struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> alig
   bool fast; int64_t nib_words;                                            // fast: every guide of the launch fits align_fast's 64-column window; nib_words: size of `nib`
   const DedupLayout* dedup; int32_t max_overlap;                           // dedup != nullptr: removeOverlaps + ReferenceHit.sort over the kept alignments
   DBuf* out_owned;                                                         // plain compaction only: when given, one byte per output record (1 = owned, 0 = halo) goes here
+  int32_t halo_bases = 0;                                                  // k_sweep's halo sentinel: HALO_WINDOWS * step - window overlap - CALITAS_MAX_OPS
   bool any_wide_group = true;                                              // best mode: some group may not fit k_align_group_warp's tile (window > GROUP_W columns or alignments > 64 columns)
 };
 
@@ -1332,12 +1351,14 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
   e->key_b.ensure((size_t)n * 4);
   uint32_t* keep = e->rank.as<uint32_t>(); uint32_t* kpos = e->key_b.as<uint32_t>();   // rank (one word per slot) is free again after k_canon
   CAL_LAUNCH(k_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, aa.recs, rw, e->slot_owned.as<uint8_t>(), sidx, n, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_sweep_prepare"); ++e->launches;
-  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, skey, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, P.max_overlap, P.max_overlap >= 1 ? 1 : 0, strand_shift, L.start_bits, keep); dev::launch_check("k_sweep"); ++e->launches;
+  CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, skey, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, P.max_overlap, P.max_overlap >= 1 ? 1 : 0, strand_shift, L.start_bits, keep, d_overflow + 1, P.halo_bases); dev::launch_check("k_sweep"); ++e->launches;
   tb = dev::exclusive_sum_u32_tmp((size_t)n); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, keep, kpos, (size_t)n, s); ++e->launches;
   CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, kpos + (n - 1), keep + (n - 1), (const unsigned long long*)(e->d_count + CNT_DEDUP_OVERFLOW), e->h_count_dev + CNT_KEEPERS); dev::launch_check("k_publish_sum");
   dev::stream_sync(s);
-  if (((volatile unsigned long long*)e->h_count)[CNT_KEEPERS + 1]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in removeOverlaps");
+  { const unsigned long long fl = ((volatile unsigned long long*)e->h_count)[CNT_KEEPERS + 1];
+    if (fl & 0xFFFFFFFFull) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in removeOverlaps");
+    if (fl >> 32) throw LimitExceeded("removeOverlaps: a chain of overlapping hits runs through the whole halo of a shard cut; this input cannot be de-duplicated per shard (search with dedup = 0 and run removeOverlaps over the gathered hits, or use fewer shards)"); }
   const int64_t nk = (int64_t)((volatile unsigned long long*)e->h_count)[CNT_KEEPERS];
   if (nk == 0) return 0;
   ensure_out(e, rw, out_n, nk, projected_total);
@@ -1457,7 +1478,7 @@ void score_bounds(const std::vector<GuideSpec>& specs, size_t g0, size_t g1, con
 // hits already in e->out (arrival order; e->out_owned says which are reported), de-duplicated per (guide, contig, strand, variant set) and put in
 // ReferenceHit.sort order (:641-648, 653-675).  Result: records in e->out2, annotations in e->var_info2; returns their number.
 int64_t merge_variant_hits(calitas_engine* e, const VariantPlan& vp, const std::vector<GuideSpec>& specs, const calitas_limits* limits, const calitas_reference* ref, int rw, int64_t n_ref,
-                           double ms[8], int64_t counts[8]) {
+                           int32_t halo_bases, double ms[8], int64_t counts[8]) {
   dev::Stream s = e->stream;
   const calitas_variant_set& vs = *vp.vs;
   if (vs.owner != e) throw InvalidArgument("the variant set belongs to another engine");
@@ -1524,7 +1545,7 @@ int64_t merge_variant_hits(calitas_engine* e, const VariantPlan& vp, const std::
   CAL_LAUNCH(k_variant_sweep_prepare, blocks_for(n, 256), 256, 0, s, 1, recs, rw, e->var_info.as<VarInfo>(), e->out_owned.as<uint8_t>(), ktmp, i3, n, major,
              e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>()); dev::launch_check("k_variant_sweep_prepare"); ++e->launches;
   CAL_LAUNCH(k_sweep, blocks_for(n, 128), 128, 0, s, 1, major, e->sstart.as<int32_t>(), e->send.as<int32_t>(), e->sscore.as<int32_t>(), e->sowned.as<uint8_t>(), n, limits->max_overlap,
-             limits->max_overlap >= 1 ? 1 : 0, 0, 0, e->flag.as<uint32_t>()); dev::launch_check("k_sweep"); ++e->launches;
+             limits->max_overlap >= 1 ? 1 : 0, 0, 0, e->flag.as<uint32_t>(), d_overflow + 1, halo_bases); dev::launch_check("k_sweep"); ++e->launches;
   tb = dev::exclusive_sum_u32_tmp(nn); e->tmp.ensure(tb);
   dev::exclusive_sum_u32(e->tmp.p, tb, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), nn, s); ++e->launches;
   CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, e->pos.as<uint32_t>() + (n - 1), e->flag.as<uint32_t>() + (n - 1), (const unsigned long long*)nullptr, e->h_count_dev + CNT_KEEPERS); dev::launch_check("k_publish_sum");
@@ -1539,7 +1560,9 @@ int64_t merge_variant_hits(calitas_engine* e, const VariantPlan& vp, const std::
   CAL_LAUNCH(k_variant_gather, blocks_for(nk, 256), 256, 0, s, 1, recs, rw, e->var_info.as<VarInfo>(), i2, nk, e->out2.as<uint32_t>(), e->var_info2.as<VarInfo>()); dev::launch_check("k_variant_gather"); ++e->launches;
   CAL_LAUNCH(k_publish_u64, 1, 1, 0, s, 1, e->d_count + CNT_DEDUP_OVERFLOW, e->h_count_dev + CNT_KEEPERS + 1); dev::launch_check("k_publish_u64");
   dev::stream_sync(s);
-  if (((volatile unsigned long long*)e->h_count)[CNT_KEEPERS + 1]) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in the variant merge");
+  { const unsigned long long fl = ((volatile unsigned long long*)e->h_count)[CNT_KEEPERS + 1];
+    if (fl & 0xFFFFFFFFull) throw std::runtime_error("internal error: a hit field exceeds its sort-key width in the variant merge");
+    if (fl >> 32) throw LimitExceeded("removeOverlaps: a chain of overlapping hits runs through the whole halo of a shard cut; this input cannot be de-duplicated per shard (use fewer shards)"); }
   return nk;
 }
 
@@ -1795,6 +1818,7 @@ static int search_impl(calitas_engine* e, const calitas_reference* ref_c, int32_
         dev::event_record(ce.ev[CE_TAIL_B], s);
         Pipeline P{ e, cand_slot[slot]->as<uint64_t>(), ce.ev[CE_SORTED], ce.ev[CE_ALIGN_B], ce.ev[CE_ALIGN_E], e->specs.as<GuideSpec>(), ch.slots, false, ch.banded,
                     ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, dedup == 0 && !vp, ch.key, rw, ch.fast, ref->total_padded / 8, (dedup && !vp) ? &ch.dedup : nullptr, limits->max_overlap, vp ? &e->out_owned : nullptr };
+        P.halo_bases = HALO_WINDOWS * ch.step - (window_size - ch.step) - CALITAS_MAX_OPS;
         int64_t n_aln = 0;
         // room in e->out: what this chunk adds, and (when it has to grow) the rest of the call projected from the hits per guide so far
         const size_t projected = ch.g0 > 0 ? (size_t)((double)n_out * (double)n_guides / (double)ch.g0 * 1.15) + 4096 : e->out_hits_hint;
@@ -1824,7 +1848,8 @@ static int search_impl(calitas_engine* e, const calitas_reference* ref_c, int32_
       PinnedBuf info_pin;
       if (vp) {        // variant windows: align, merge with the reference hits, removeOverlaps + sort, then one copy of records and annotations
         dev::stream_sync(cs); dev::stream_sync(s);
-        n_out = merge_variant_hits(e, *vp, specs, limits, ref, rw, n_out, ms, counts);
+        int32_t halo_bases = 0x7FFFFFFF; for (auto& ch : chunks) halo_bases = std::min(halo_bases, HALO_WINDOWS * ch.step - (window_size - ch.step) - CALITAS_MAX_OPS);
+        n_out = merge_variant_hits(e, *vp, specs, limits, ref, rw, n_out, halo_bases, ms, counts);
         if ((size_t)n_out * rec_bytes > pin.cap) { e->pinned_pool.push_back(pin); pin = take_pinned(e, (size_t)n_out * rec_bytes); }
         info_pin = take_pinned(e, std::max<size_t>(1, (size_t)n_out) * sizeof(calitas_variant_hit_info));
         dev::event_record(e->ev[6], s);

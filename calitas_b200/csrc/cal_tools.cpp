@@ -610,6 +610,7 @@ int calitas_tool_search_reference(calitas_engine* e, const calitas_reference* re
 // SearchReference.execute for a batch of guides over 1..N engines (one per GPU, each holding a contig-range shard of the same genome,
 // calitas_shard_plan): the engines run concurrently on host threads, shards are independent, the host concatenates per guide in shard order.
 // out_fd >= 0: the table is written to that descriptor (streamed block by block when there is no VCF) and *out_tsv stays NULL.
+static thread_local bool g_force_host_dedup = false;      // set for the retry after an engine's halo sentinel fired (see search_reference_batch_impl's callers)
 static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
                                        int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
                                        int out_fd, char** out_tsv, int64_t* n_hits, int64_t* n_bytes) {
@@ -621,7 +622,7 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
     // (calitas_search_variants) -- except with -O <= 0 on several engines: every later hit of a group then "overlaps" (>= 0), the reference's sweep
     // (SearchReference.scala:662-672) has unbounded reach, and no halo can make a shard's sweep see what it would need; that case gathers raw hits
     // and de-duplicates on the host.
-    const bool host_dedup = n_engines > 1 && opt->limits.max_overlap <= 0;
+    const bool host_dedup = n_engines > 1 && (opt->limits.max_overlap <= 0 || g_force_host_dedup);
     const bool device_vcf = opt->vcf_text != nullptr && !host_dedup;      // variant windows are aligned, merged and de-duplicated by calitas_search_variants
     const bool stream = out_fd >= 0 && !host_dedup;
     int64_t streamed_bytes = 0;
@@ -809,7 +810,14 @@ static int search_reference_batch_impl(int32_t n_engines, calitas_engine* const*
 int calitas_tool_search_reference_batch(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
                                         int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
                                         char** out_tsv, int64_t* n_hits) {
-  return search_reference_batch_impl(n_engines, engines, refs, genome, n_guides, guides, guide_ids, opt, -1, out_tsv, n_hits, nullptr);
+  int rc = search_reference_batch_impl(n_engines, engines, refs, genome, n_guides, guides, guide_ids, opt, -1, out_tsv, n_hits, nullptr);
+  if (rc == CALITAS_ELIMIT && n_engines > 1 && std::strstr(calitas_last_error(), "removeOverlaps: a chain")) {
+    // an engine's halo sentinel: this input chains overlapping hits through a whole shard halo; gather raw hits and run removeOverlaps + sort on the host instead
+    g_force_host_dedup = true;
+    rc = search_reference_batch_impl(n_engines, engines, refs, genome, n_guides, guides, guide_ids, opt, -1, out_tsv, n_hits, nullptr);
+    g_force_host_dedup = false;
+  }
+  return rc;
 }
 int calitas_tool_search_reference_batch_fd(int32_t n_engines, calitas_engine* const* engines, const calitas_reference* const* refs, const calitas_genome_view* genome,
                                            int32_t n_guides, const calitas_guide* guides, const char* const* guide_ids, const calitas_search_options* opt,
