@@ -507,7 +507,14 @@ def run_search(args, job):
         out["config"]["cpu_binding_rank0"] = ("cpus %d-%d (GPU-local NUMA node)" % (job.numa[0], job.numa[-1])) if job.numa else "none"
         if per_rank is not None:
             out["per_rank"] = {"ms_per_step": [round(r[0], 3) for r in per_rank], "scan_ms": [round(r[1], 3) for r in per_rank], "candidates": [int(r[2]) for r in per_rank]}
-        records = last["hs"].records() if keep_records and "hs" in last else None
+        records = None
+        if keep_records and "hs" in last:
+            # only the hits of the sample region are decoded (contig 0, first 100 Mbp): the step returns tens of millions of records
+            from calitas_b200._capi import decode_hits
+            raw = last["hs"].raw_words()
+            sel = (((raw[:, 3] >> 13) & 0x3FFFF) == 1) & (raw[:, 0].view(np.int32) < 100_000_000 + 4096)
+            records = decode_hits(raw[sel])
+            del raw
         threads = os.cpu_count() or 1
         if world == 1 and not args.no_cpu_baseline:
             # a 100-Mbp slice of the genome (and the whole 10-Mbp genome for config1), all host cores
@@ -652,7 +659,7 @@ def run_a2r(args, job):
         value, e2e = n / (dev_ms_max * 1e-3) / 1e6, n / (wall_ms_max * 1e-3) / 1e6
         peaks = peaks_file()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel: the grouped DP (k_align_group).  Algorithmic bytes per task: 2 strands x 61 columns x 1 slot x one hit record written + the 61 packed bases read
+        # dominant kernel: the grouped DP (k_align_group_warp).  Algorithmic bytes per task: 2 strands x 61 columns x 1 slot x one hit record written + the 61 packed bases read
         rec = 32
         alg_bytes = len(mine) * (2 * (w["window"] + 1) * rec + (w["window"] + 1) * 0.5)
         cells = len(mine) * 2.0 * (w["window"] + 1) * 20
@@ -662,10 +669,10 @@ def run_a2r(args, job):
                "e2e": {"value": e2e, "unit": "Mpairs/s", "ms_per_step": wall_ms_max, "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
                        "api": "calitas_align_regions(best=1) (C ABI): task array + guide strings in host memory -> per-task alignments in pinned host memory"},
                "gpu_launches": int(sum(s["launches"] for s in stats)), "clocks": clocks,
-               "roofline": {"kernel": "k_align_group", "bound": "hbm", "achieved": alg_bytes / (st["ms_align"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+               "roofline": {"kernel": "k_align_group_warp", "bound": "hbm", "achieved": alg_bytes / (st["ms_align"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (st["ms_align"] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "avg_launch_ms": st["ms_align"], "share_of_step": st["ms_align"] / st["ms_total"],
                             "note": "algorithmic bytes = one record per end column and strand written + the packed region read; the kernel is integer-ALU-bound (DP cells), see roofline_int"},
-               "roofline_int": {"kernel": "k_align_group", "bound": "int_alu_pipe", "unit": "G DP cells/s (3 matrices per cell)", "achieved": cells / (st["ms_align"] * 1e-3) / 1e9,
+               "roofline_int": {"kernel": "k_align_group_warp", "bound": "int_alu_pipe", "unit": "G DP cells/s (3 matrices per cell)", "achieved": cells / (st["ms_align"] * 1e-3) / 1e9,
                                 "cells_per_task": 2 * (w["window"] + 1) * 20},
                "breakdown_ms": {"scan": st["ms_scan"], "align": st["ms_align"], "sort_canon_dedup": st["ms_other"], "d2h": st["ms_d2h"], "wall": st["wall_ms"]},
                "counts": {"alignments": total_hits, "candidates": total_cand, "tasks": n}, "setup_s": {"generate": t_gen, "load_and_pack": t_load}}

@@ -740,8 +740,11 @@ CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
   while (i1 < a.n_cand) { const uint64_t p = a.cand[i1]; if (key_group(a.key, p) != grp || key_col(a.key, p) - col >= reach) break; col = key_col(a.key, p); ++i1; }
   const int64_t base = i0 * a.slots; const int64_t n = (i1 - i0) * a.slots;
   const CKey* keys = a.ckeys + base;
+  // the usual group is one cluster: then the cluster's kept list is the group's and pass 2 has nothing to do for these slots (gbase != ~0 tells it)
+  const bool whole_group = (i0 == 0 || key_group(a.key, a.cand[i0 - 1]) != grp) && (i1 == a.n_cand || key_group(a.key, a.cand[i1]) != grp);
   if (n > 32) {
     if (i != i0) return;
+    for (int64_t k = 0; k < n; ++k) a.gbase[base + k] = 0xFFFFFFFFu;
     canon_group(keys, a.rank + base, (int)n, max_total, max_overlap);
     for (int64_t k = 0; k < n; ++k) {
       const bool halo = ck_state(keys[k]) == 2;
@@ -754,11 +757,13 @@ CAL_KERNEL __launch_bounds__(128) k_canon(CanonArgs a) {
     const int st = ck_state(keys[k]); const bool halo = st == 2;
     const int r = st == 0 ? -1 : canon_slot_rank(keys, (int)n, k, max_total, max_overlap);
     a.slot_owned[s] = halo ? 0 : 1; a.flag[s] = (r >= 0 && !(halo && a.drop_halo)) ? 1u : 0u;
+    a.rank[s] = r; a.gbase[s] = whole_group ? (uint32_t)base : 0xFFFFFFFFu;
   }
 }
 CAL_KERNEL __launch_bounds__(128) k_canon_rank(CanonArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n_cand) return;
+  if (a.gbase[i * a.slots] != 0xFFFFFFFFu) return;            // pass 1 ranked this candidate's slots: its cluster was its whole group
   const uint64_t grp = key_group(a.key, a.cand[i]);
   int64_t i0 = i; while (i0 > 0 && key_group(a.key, a.cand[i0 - 1]) == grp) --i0;
   int64_t i1 = i + 1; while (i1 < a.n_cand && key_group(a.key, a.cand[i1]) == grp) ++i1;
