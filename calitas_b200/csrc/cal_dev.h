@@ -16,6 +16,7 @@
 #include <cub/device/device_scan.cuh>
 
 #define CAL_KERNEL __global__ void
+#define CAL_MAXNREG(n) __maxnreg__(n)
 #define CAL_PHASE(k)
 #define CAL_SHARED_DYN(type, name) extern __shared__ __align__(16) unsigned char cal_smem_raw_[]; type* name = reinterpret_cast<type*>(cal_smem_raw_)
 #define CAL_LAUNCH(kernel, grid, block, smem, stream, nphases, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
@@ -114,6 +115,7 @@ template <class F> void launch(unsigned grid, unsigned block, int nphases, F f) 
 #define blockDim cal::sim::blockDim_
 #define gridDim cal::sim::gridDim_
 #define CAL_KERNEL static void
+#define CAL_MAXNREG(n)
 #define CAL_PHASE(k) if (cal::sim::phase_ == (k))
 #define CAL_SHARED_DYN(type, name) type* name = reinterpret_cast<type*>(cal::sim::smem_)
 #define CAL_LAUNCH(kernel, grid, block, smem, stream, nphases, ...) cal::sim::launch((unsigned)(grid), (unsigned)(block), (nphases), [&] { kernel(__VA_ARGS__); })

@@ -168,7 +168,7 @@ CAL_D void scan_window(const uint8_t* tb, int32_t rs, int32_t re, int32_t c_lo, 
 
 // Block = TILE_WINDOWS windows x 2 directions x 4 (guide slot, window part) pairs = 512 threads; a thread owns one window part, one
 // direction and every scan_slots-th pair of guides of the chunk.
-CAL_KERNEL __launch_bounds__(4 * SCAN_THREADS) k_scan_tiled(ScanArgs a) {
+CAL_KERNEL CAL_MAXNREG(56) k_scan_tiled(ScanArgs a) {
   CAL_SHARED_DYN(uint32_t, smem);
   const int ng = a.g_end - a.g_begin;
   uint32_t* s_peq = smem;                       // ng * 32 words
