@@ -39,7 +39,6 @@ const int ALIGN_KB = 6;          // k_align keeps a 2*6+1-diagonal DP band in re
 const int SCAN_SMEM_LIMIT = 200 * 1024;   // dynamic shared memory a k_scan_tiled CTA may ask for
 const int TILE_WINDOWS = 64;      // windows per scan tile at the default window size; halved until the tile fits shared memory for larger -w
 const int HALO_WINDOWS = 2;      // windows processed beyond each interior shard cut so that removeOverlaps sees both sides of the cut
-const int SCAN_THREADS = 2 * TILE_WINDOWS;
 #ifndef CAL_SCAN_NG
 #define CAL_SCAN_NG 2
 #endif
@@ -1824,6 +1823,7 @@ static int search_impl(calitas_engine* e, const calitas_reference* ref_c, int32_
         Pipeline P{ e, cand_slot[slot]->as<uint64_t>(), ce.ev[CE_SORTED], ce.ev[CE_ALIGN_B], ce.ev[CE_ALIGN_E], e->specs.as<GuideSpec>(), ch.slots, false, ch.banded,
                     ref->d_nib, ch.ts->d_contigs, (int)ch.ts->contigs.size(), window_size, ch.step, nullptr, dedup == 0 && !vp, ch.key, rw, ch.fast, ref->total_padded / 8, (dedup && !vp) ? &ch.dedup : nullptr, limits->max_overlap, vp ? &e->out_owned : nullptr };
         P.halo_bases = HALO_WINDOWS * ch.step - (window_size - ch.step) - CALITAS_MAX_OPS;
+        if (const char* hb = std::getenv("CALITAS_TEST_HALO_BASES")) P.halo_bases = std::atoi(hb);      // tests: a reach so short that the sentinel fires on ordinary input
         int64_t n_aln = 0;
         // room in e->out: what this chunk adds, and (when it has to grow) the rest of the call projected from the hits per guide so far
         const size_t projected = ch.g0 > 0 ? (size_t)((double)n_out * (double)n_guides / (double)ch.g0 * 1.15) + 4096 : e->out_hits_hint;

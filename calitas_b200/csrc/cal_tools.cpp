@@ -294,18 +294,51 @@ struct VcfRecord { Str chrom; int pos; Str id, ref; std::vector<Str> alts; std::
 
 std::vector<Str> split(const Str& s, char sep) { std::vector<Str> out; size_t a = 0; for (;;) { size_t b = s.find(sep, a); if (b == Str::npos) { out.push_back(s.substr(a)); return out; } out.push_back(s.substr(a, b - a)); a = b + 1; } }
 
-std::vector<VcfRecord> parse_vcf(const char* text) {
-  std::vector<VcfRecord> out;
-  for (const Str& raw : split(text, '\n')) {
-    Str line = raw; if (!line.empty() && line.back() == '\r') line.pop_back();
-    if (line.empty() || line[0] == '#') continue;
-    std::vector<Str> f = split(line, '\t');
-    if (f.size() < 5) bad("malformed VCF record: " + line);
-    VcfRecord v; v.chrom = f[0]; v.pos = std::atoi(f[1].c_str()); v.id = f[2] == "." ? Str() : f[2]; v.ref = f[3];
-    for (const Str& a : split(f[4], ',')) if (a != ".") v.alts.push_back(a);
-    if (f.size() >= 8) for (const Str& kv : split(f[7], ';')) if (kv.compare(0, 3, "AF=") == 0) { v.has_af = true; for (const Str& x : split(kv.substr(3), ',')) v.afs.push_back(x == "." ? 0.0f : std::strtof(x.c_str(), nullptr)); }
-    out.push_back(std::move(v));
+// One VCF data line [b, e) (no newline) -> record; false for blank lines and header lines.  Fields are cut with pointer arithmetic: a 3-million-record file
+// is parsed in a fraction of a second per host thread.
+bool parse_vcf_line(const char* b, const char* e, VcfRecord& v) {
+  if (e > b && e[-1] == '\r') --e;
+  if (e == b || *b == '#') return false;
+  const char* f[9]; int nf = 0; f[nf++] = b;
+  for (const char* p = b; p < e && nf < 9; ++p) if (*p == '\t') f[nf++] = p + 1;
+  if (nf < 5) bad("malformed VCF record: " + Str(b, e));
+  auto end_of = [&](int k) { return k + 1 < nf ? f[k + 1] - 1 : e; };
+  v.chrom.assign(f[0], end_of(0)); v.pos = std::atoi(Str(f[1], end_of(1)).c_str());
+  v.id.assign(f[2], end_of(2)); if (v.id == ".") v.id.clear();
+  v.ref.assign(f[3], end_of(3));
+  for (const char* p = f[4], *q = end_of(4);;) { const char* c = std::find(p, q, ','); if (!(c - p == 1 && *p == '.')) v.alts.emplace_back(p, c); if (c == q) break; p = c + 1; }
+  if (nf >= 8) {
+    for (const char* p = f[7], *q = end_of(7);;) {
+      const char* c = std::find(p, q, ';');
+      if (c - p >= 3 && p[0] == 'A' && p[1] == 'F' && p[2] == '=') {
+        v.has_af = true;
+        for (const char* x = p + 3;;) { const char* y = std::find(x, c, ','); v.afs.push_back((y - x == 1 && *x == '.') ? 0.0f : std::strtof(Str(x, y).c_str(), nullptr)); if (y == c) break; x = y + 1; }
+      }
+      if (c == q) break; p = c + 1;
+    }
   }
+  return true;
+}
+
+std::vector<VcfRecord> parse_vcf(const char* text) {
+  const size_t n = std::strlen(text);
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>(n / (4u << 20) + 1, std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency()))));
+  std::vector<size_t> cut((size_t)nt + 1, n); cut[0] = 0;
+  for (int t = 1; t < nt; ++t) { size_t p = n * (size_t)t / (size_t)nt; while (p < n && text[p] != '\n') ++p; cut[(size_t)t] = p < n ? p + 1 : n; }
+  std::vector<std::vector<VcfRecord>> part((size_t)nt);
+  parallel_for(nt, 1, [&](int64_t tb, int64_t te) {
+    for (int64_t t = tb; t < te; ++t) {
+      std::vector<VcfRecord>& out = part[(size_t)t];
+      for (size_t p = cut[(size_t)t]; p < cut[(size_t)t + 1];) {
+        const char* b = text + p; const char* e = (const char*)std::memchr(b, '\n', cut[(size_t)t + 1] - p); if (!e) e = text + cut[(size_t)t + 1];
+        VcfRecord v; if (parse_vcf_line(b, e, v)) out.push_back(std::move(v));
+        p = (size_t)(e - text) + 1;
+      }
+    } });
+  if (nt == 1) return std::move(part[0]);
+  size_t total = 0; for (auto& v : part) total += v.size();
+  std::vector<VcfRecord> out; out.reserve(total);
+  for (auto& v : part) for (auto& r : v) out.push_back(std::move(r));
   return out;
 }
 
@@ -479,7 +512,9 @@ extern "C" int calitas_reference_own_range(const calitas_reference* r, int32_t c
 
 void build_vcf_device_plan(VcfDevicePlan& P, const calitas_genome_view& genome, const calitas_search_options& opt, const std::vector<GuideDef>& defs, int chrom_idx,
                            int n_engines, const calitas_reference* const* refs) {
+  PhaseTimer pt;
   P.recs = parse_vcf(opt.vcf_text);
+  pt.lap("  vcf: parse");
   std::map<int, int> class_of_padding;
   for (size_t g = 0; g < defs.size(); ++g) {
     const int padding = defs[g].length() - 1 + opt.limits.max_guide_diffs + opt.limits.max_gaps_between_guide_and_pam;      // SearchReference.scala:575
@@ -487,6 +522,7 @@ void build_vcf_device_plan(VcfDevicePlan& P, const calitas_genome_view& genome, 
     if (it == class_of_padding.end()) { it = class_of_padding.emplace(padding, (int)P.by_class.size()).first; P.by_class.push_back(variant_windows(genome, P.recs, chrom_idx, padding, opt.max_variants)); }
     P.guide_class.push_back(it->second);
   }
+  pt.lap("  vcf: variant windows");
   // allele numbers: index of the (record, ALT) pair in the VCF; the same pair in different windows is the same variant
   std::vector<uint32_t> alt_base(P.recs.size() + 1, 0);
   for (size_t r = 0; r < P.recs.size(); ++r) alt_base[r + 1] = alt_base[r] + (uint32_t)P.recs[r].alts.size();
@@ -494,19 +530,31 @@ void build_vcf_device_plan(VcfDevicePlan& P, const calitas_genome_view& genome, 
   std::map<std::vector<uint32_t>, uint32_t> set_no;
   auto number_of = [&](int, const VariantAllele& a) -> uint32_t { return alt_base[(size_t)((const VcfRecord*)a.rec - P.recs.data())] + (uint32_t)a.alt_idx; };
   for (size_t c = 0; c < P.by_class.size(); ++c) for (auto& w : P.by_class[c]) { P.flat.push_back(&w); P.flat_class.push_back((int32_t)c); }
-  std::vector<std::vector<uint32_t>> wnum(P.flat.size());
-  for (size_t i = 0; i < P.flat.size(); ++i) for (auto& a : P.flat[i]->alleles) wnum[i].push_back(number_of(P.flat[i]->contig, a));
-  for (size_t i = 0; i < P.flat.size(); ++i) {
-    const VariantWindow& w = *P.flat[i]; const int m = (int)w.alleles.size();
-    P.first_allele.push_back((int32_t)P.alleles.size()); P.first_set.push_back((int32_t)P.set_id.size());
-    for (auto& a : w.alleles) P.alleles.push_back(calitas_variant_allele{ a.pos, (int32_t)a.ref.size(), (int32_t)a.alt.size() });
-    for (int a = 0; a < m; ++a) for (int b = a + 1; b <= m; ++b) {
-      if (b - a == 1) { P.set_id.push_back(1u + wnum[i][(size_t)a]); continue; }
-      std::vector<uint32_t> key(wnum[i].begin() + a, wnum[i].begin() + b);
-      auto it = set_no.find(key); if (it == set_no.end()) it = set_no.emplace(std::move(key), (uint32_t)set_no.size()).first;
-      P.set_id.push_back(1u + n_single + it->second);
+  // offsets first (cheap), then the alleles and the single-allele sets on all host threads; only the sets of several alleles are interned one by one
+  const size_t nw = P.flat.size();
+  P.first_allele.resize(nw); P.first_set.resize(nw);
+  { size_t na = 0, ns = 0; for (size_t i = 0; i < nw; ++i) { const size_t m = P.flat[i]->alleles.size(); P.first_allele[i] = (int32_t)na; P.first_set[i] = (int32_t)ns; na += m; ns += m * (m + 1) / 2;
+      if (na >= (1ull << 31) || ns >= (1ull << 31)) bad("too many variant alleles / variant sets"); }
+    P.alleles.resize(na); P.set_id.assign(ns, 0u); }
+  std::mutex multi_mu; std::vector<std::pair<size_t, std::vector<uint32_t>>> multi;       // (position in set_id, allele numbers)
+  parallel_for((int64_t)nw, 4096, [&](int64_t wb, int64_t we) {
+    std::vector<std::pair<size_t, std::vector<uint32_t>>> mine; std::vector<uint32_t> num;
+    for (int64_t i = wb; i < we; ++i) {
+      const VariantWindow& w = *P.flat[(size_t)i]; const int m = (int)w.alleles.size();
+      num.clear();
+      for (int k = 0; k < m; ++k) { const VariantAllele& a = w.alleles[(size_t)k]; P.alleles[(size_t)P.first_allele[(size_t)i] + (size_t)k] = calitas_variant_allele{ a.pos, (int32_t)a.ref.size(), (int32_t)a.alt.size() }; num.push_back(number_of(w.contig, a)); }
+      size_t at = (size_t)P.first_set[(size_t)i];
+      for (int a = 0; a < m; ++a) for (int b = a + 1; b <= m; ++b, ++at) {
+        if (b - a == 1) P.set_id[at] = 1u + num[(size_t)a];
+        else mine.emplace_back(at, std::vector<uint32_t>(num.begin() + a, num.begin() + b));
+      }
     }
+    if (!mine.empty()) { std::lock_guard<std::mutex> lk(multi_mu); for (auto& x : mine) multi.push_back(std::move(x)); } });
+  for (auto& x : multi) {
+    auto it = set_no.find(x.second); if (it == set_no.end()) it = set_no.emplace(x.second, (uint32_t)set_no.size()).first;
+    P.set_id[x.first] = 1u + n_single + it->second;
   }
+  pt.lap("  vcf: alleles and variant sets");
   // per engine: the windows whose first base it owns, plus those within two reference windows of its cuts (halo: they take part in removeOverlaps there, too)
   P.eng_windows.resize((size_t)n_engines); P.eng_flat.resize((size_t)n_engines);
   const int64_t halo = 2 * (int64_t)opt.window_size;
@@ -523,6 +571,7 @@ void build_vcf_device_plan(VcfDevicePlan& P, const calitas_genome_view& genome, 
       P.eng_flat[(size_t)s].push_back((int32_t)i);
     }
   }
+  pt.lap("  vcf: per-engine window lists");
 }
 
 // Flanks of a variant-window hit, taken from the window where it reaches far enough (SearchReference.scala:599-612); `h` holds window offsets.

@@ -122,3 +122,29 @@ def test_search_sharded_returns_one_merged_table(lib, max_overlap):
         b["task_idx"] = 0
         assert a.size == b.size and a.tobytes() == b.tobytes(), n_shards
     e.close()
+
+
+def test_halo_sentinel_fails_the_call_and_the_tool_falls_back(lib, monkeypatch):
+    """k_sweep's halo sentinel: when no restart of the removeOverlaps loop lies within reach of a shard's first owned hit, calitas_search fails with
+    CALITAS_ELIMIT instead of guessing, and calitas_tool_search_reference_batch gathers raw hits and de-duplicates on the host.  No real input has
+    triggered it, so the test shortens the reach (CALITAS_TEST_HALO_BASES) until ordinary dense repeats do."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import pyoracle
+    import test_parity_random as T
+    from calitas_b200 import _capi
+    from calitas_b200.testing import Facade
+    contigs = T._tandem_repeat_contigs(503, 160)
+    lim = Limits(5, 1, 3, -1, 10)
+    e = Engine(0, lib=lib)
+    r = e.load_reference(contigs, shard=(1, 3, 4000))
+    assert len(e.search(r, [synth.BASELINE_GUIDE], lim, dedup=True)) > 10          # the real reach: fine
+    monkeypatch.setenv("CALITAS_TEST_HALO_BASES", "-100000")                          # nothing counts as within reach: every cut with halo hits is flagged
+    with pytest.raises(_capi.CalitasError) as ei:
+        e.search(r, [synth.BASELINE_GUIDE], lim, dedup=True)
+    assert ei.value.code == 3 and "halo" in ei.value.message                          # CALITAS_ELIMIT
+    r.free()
+    e.close()
+    exp = [l for l in pyoracle.search_reference(contigs, synth.BASELINE_GUIDE, guide_id="g0", raw=True).split("\n") if l]
+    got = [l for l in Facade(lib).search_reference_batch(contigs, [synth.BASELINE_GUIDE], ["g0"], n_shards=3).split("\n") if l]
+    assert got == exp and len(exp) > 100
