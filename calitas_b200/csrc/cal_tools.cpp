@@ -292,7 +292,6 @@ Str contig_slice(const calitas_genome_view& g, int contig, int start, int end) {
 // ---- variant windows (SearchReference.scala:101-400) -----------------------------------------------------------------------------------
 struct VcfRecord { Str chrom; int pos; Str id, ref; std::vector<Str> alts; std::vector<float> afs; bool has_af = false; int end() const { return pos + (int)ref.size() - 1; } };
 
-std::vector<Str> split(const Str& s, char sep) { std::vector<Str> out; size_t a = 0; for (;;) { size_t b = s.find(sep, a); if (b == Str::npos) { out.push_back(s.substr(a)); return out; } out.push_back(s.substr(a, b - a)); a = b + 1; } }
 
 // One VCF data line [b, e) (no newline) -> record; false for blank lines and header lines.  Fields are cut with pointer arithmetic: a 3-million-record file
 // is parsed in a fraction of a second per host thread.
@@ -314,7 +313,8 @@ bool parse_vcf_line(const char* b, const char* e, VcfRecord& v) {
         v.has_af = true;
         for (const char* x = p + 3;;) { const char* y = std::find(x, c, ','); v.afs.push_back((y - x == 1 && *x == '.') ? 0.0f : std::strtof(Str(x, y).c_str(), nullptr)); if (y == c) break; x = y + 1; }
       }
-      if (c == q) break; p = c + 1;
+      if (c == q) break;
+      p = c + 1;
     }
   }
   return true;
