@@ -94,7 +94,7 @@ CAL_KERNEL __launch_bounds__(256) k_pack(const uint8_t* __restrict__ raw, uint32
 // ------------------------------------------------------------------------------------------------------------------------------------
 struct ScanArgs {
   const uint32_t* nib; const ContigDev* contigs; const Tile* tiles; const GuideSpec* specs;
-  int32_t g_begin, g_end, window_size, step, min_len, scan_slots, tile_windows, inline_emit;
+  int32_t g_begin, g_end, window_size, step, min_len, scan_slots, tile_windows;
   uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap; KeyLayout key;
 };
 
@@ -119,7 +119,7 @@ inline int __vimin3_s32(int a, int b, int c) { int m = a < b ? a : b; return m <
 // DIR 1: right to left, the tables then hold the complemented masks.  Column p = 1.. in scan order.  Blocks of 8 columns run branch-free:
 // the running minimum of the distance decides, once per block, whether the (rare) per-column emission replay is needed.  Tables of a
 // thread's guides are adjacent (32 words apart).
-template <int DIR, int NG, bool INLINE>
+template <int DIR, int NG>
 CAL_D void scan_window(const uint8_t* tb, int32_t rs, int32_t re, int32_t c_lo, int32_t c_hi, const ScanGuide* sg, uint64_t* cand, unsigned long long* count, unsigned long long cap) {
   // Columns [c_lo, c_hi) (0-based, scan order) of the window are this thread's; when c_lo > 0 the chains are warmed up over the lp + k_edits
   // columns before c_lo from the fresh state: an alignment with <= k_edits edits that ends at or after c_lo starts inside that stretch, and a
@@ -141,19 +141,8 @@ CAL_D void scan_window(const uint8_t* tb, int32_t rs, int32_t re, int32_t c_lo, 
 #pragma unroll
       for (int j = 0; j < NG; ++j) myers_step(st[j], CAL_EQ(j, b)); }
   }
-  if (INLINE) {
-    // Thresholds of 6 edits and more: about one column in a thousand is a candidate, a third of the warp-blocks would replay.  Testing every column in
-    // the loop costs one compare per column and guide (the running minimum goes away) and no replay: ~5 % more ALU work instead of ~10 %.
-    for (; c + 8 <= n; c += 8) {
-      const uint8_t* q = DIR == 0 ? p + c : p - c;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t b = DIR == 0 ? q[k] : q[-k];
-#pragma unroll
-        for (int j = 0; j < NG; ++j) CAL_STEP1(j, st[j], b, c + k + 1)
-      }
-    }
-  }
+  // (An in-loop test of every column instead of the block minimum + replay was measured at thresholds of 6 edits, where a third of the warp-blocks
+  //  replay: 71.4 instead of 63.5 ms per 16-guide scan, and 449 instead of 395 ms per default step; the replay stays.)
   for (; c + 8 <= n; c += 8) {
     const uint8_t* q = DIR == 0 ? p + c : p - c;
     MyersState save[NG]; int32_t mn[NG], prev[NG];
@@ -276,8 +265,7 @@ CAL_KERNEL CAL_MAXNREG(56) k_scan_tiled(ScanArgs a) {
         sg[j].peq = s_peq + (g + j) * 32 + dir * 16; sg[j].lp = s_meta[4 * (g + j)]; sg[j].k_edits = s_meta[4 * (g + j) + 1];
         sg[j].key_base = make_key(a.key, (uint32_t)(a.g_begin + g + j), wid, (uint32_t)(dir ^ s_meta[4 * (g + j) + 2]), 0);
       }
-#define CAL_SCAN_CALL(N) { if (a.inline_emit) { if (dir == 0) scan_window<0, N, true>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); else scan_window<1, N, true>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); } \
-                           else { if (dir == 0) scan_window<0, N, false>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); else scan_window<1, N, false>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); } }
+#define CAL_SCAN_CALL(N) { if (dir == 0) scan_window<0, N>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); else scan_window<1, N>(s_bytes, rs, re, c_lo, c_hi, sg, a.cand, a.cand_count, a.cand_cap); }
       if (cnt == SCAN_NG) CAL_SCAN_CALL(SCAN_NG)
       else if (cnt >= 2) { CAL_SCAN_CALL(2) if (cnt == 3) { sg[0] = sg[2]; CAL_SCAN_CALL(1) } }
       else CAL_SCAN_CALL(1)
@@ -1715,7 +1703,7 @@ void calitas_reference_free(calitas_engine* e, calitas_reference* r) {
 }
 
 // One guide chunk of a search: consecutive guides sharing the raw guide length, hence the window tiling (SearchReference.scala:528-530).
-struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded, inline_emit; bool fast; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; KeyLayout key; DedupLayout dedup; };
+struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded; bool fast; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; KeyLayout key; DedupLayout dedup; };
 
 static int search_impl(calitas_engine* e, const calitas_reference* ref_c, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
                        int32_t window_size, const char* chrom, int32_t dedup, const VariantPlan* vp, calitas_hitset** out) {
@@ -1756,8 +1744,6 @@ static int search_impl(calitas_engine* e, const calitas_reference* ref_c, int32_
       ch.n_tiles = t_end - ch.t_begin;
       ch.slots = 1; ch.banded = 1; for (int g = g0; g < g1; ++g) { ch.slots = std::max(ch.slots, specs[(size_t)g].slots); ch.banded = std::max(ch.banded, std::max(specs[(size_t)g].k_edits, specs[(size_t)g].band_k)); }
       if (ch.banded > ALIGN_KB) ch.banded = 0;
-      { int kmax = 0; for (int g = g0; g < g1; ++g) kmax = std::max(kmax, specs[(size_t)g].k_edits);
-        const char* ie = std::getenv("CALITAS_SCAN_INLINE_EMIT"); ch.inline_emit = ie ? std::atoi(ie) : (kmax >= 6 ? 1 : 0); }      // the variable forces either form (A/B runs)
       ch.fast = ch.banded > 0; for (int g = g0; g < g1; ++g) ch.fast = ch.fast && fits_align_fast(specs[(size_t)g], ch.banded);
       const int ng = g1 - g0;
       ch.smem = scan_smem_bytes(ng, ch.ts->tile_windows, window_size, ch.step);
@@ -1800,7 +1786,7 @@ static int search_impl(calitas_engine* e, const calitas_reference* ref_c, int32_
       dev::zero(e->d_count + slot, 8, ss);
       dev::event_record(ce.ev[CE_SCAN_B], ss);
       if (ch.n_tiles) {
-        ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len, ch.scan_slots, ch.ts->tile_windows, ch.inline_emit,
+        ScanArgs sa{ ref->d_nib, ch.ts->d_contigs, ch.ts->d_tiles + ch.t_begin, e->specs.as<GuideSpec>(), ch.g0, ch.g1, window_size, ch.step, ch.raw_len, ch.scan_slots, ch.ts->tile_windows,
                      cand_slot[slot]->as<uint64_t>(), e->d_count + slot, (unsigned long long)e->cand_cap_hint, ch.key };
         // always 2 * tile_windows * 4 threads (512 at the default window size): 4 / scan_slots window parts per guide slot
         CAL_LAUNCH(k_scan_tiled, (unsigned)ch.n_tiles, 2 * ch.ts->tile_windows * 4, ch.smem, ss, 3, sa);
