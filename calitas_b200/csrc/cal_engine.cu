@@ -305,6 +305,21 @@ CAL_KERNEL __launch_bounds__(128) k_scan_explicit(ScanExplicitArgs a) {
   scan_range_generic(words, rs, re, dir, s.peq[dir], s.lp, s.k_edits, emit);
 }
 
+// Best mode (alignBest / alignToRefBest: d = protospacer length) makes EVERY column of both strands a candidate -- the semi-global edit distance of an
+// lp-row pattern never exceeds lp -- so the candidate list is written directly, already in (window, strand, column) order: no scan, no sort.
+CAL_KERNEL __launch_bounds__(256) k_window_columns(const ExplicitWindow* windows, int64_t n_windows, uint32_t* cnt) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 2 * n_windows) { const int32_t len = windows[t >> 1].len; cnt[t] = len > 0 ? (uint32_t)len : 0u; }
+}
+CAL_KERNEL __launch_bounds__(256) k_all_columns(const ExplicitWindow* windows, int64_t n_windows, const uint32_t* off, KeyLayout key, uint64_t* out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n_windows) return;
+  const int32_t len = windows[t >> 1].len;
+  const uint64_t base = make_key(key, 0, (uint32_t)(t >> 1), (uint32_t)(t & 1), 0);
+  uint64_t* o = out + off[t];
+  for (int32_t c = 1; c <= len; ++c) o[c - 1] = base | (uint32_t)c;
+}
+
 // ------------------------------------------------------------------------------------------------------------------------------------
 // k_align: candidate -> exact DP + traceback + PAM extension -> hit slots
 // ------------------------------------------------------------------------------------------------------------------------------------
@@ -1232,6 +1247,7 @@ struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> alig
   bool fast; int64_t nib_words;                                            // fast: every guide of the launch fits align_fast's 64-column window; nib_words: size of `nib`
   const DedupLayout* dedup; int32_t max_overlap;                           // dedup != nullptr: removeOverlaps + ReferenceHit.sort over the kept alignments
   DBuf* out_owned;                                                         // plain compaction only: when given, one byte per output record (1 = owned, 0 = halo) goes here
+  bool presorted = false;                                                  // the candidate keys are already in (guide, window, strand, column) order
   int32_t halo_bases = 0;                                                  // k_sweep's halo sentinel: HALO_WINDOWS * step - window overlap - CALITAS_MAX_OPS
   bool any_wide_group = true;                                              // best mode: some group may not fit k_align_group_warp's tile (window > GROUP_W columns or alignments > 64 columns)
 };
@@ -1257,15 +1273,18 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
   if (n_cand == 0) { dev::event_record(P.ev_sorted, s); dev::event_record(P.ev_align_b, s); dev::event_record(P.ev_align_e, s); return 0; }
   if (n_cand * (int64_t)P.slots >= (1ll << 32)) throw LimitExceeded("too many candidate alignments in one batch");
   // 1. sort candidate keys -> (guide, window, strand, end column)
-  e->cand_sorted.ensure((size_t)n_cand * 8);
-  size_t tb = dev::sort_keys_u64_tmp((size_t)n_cand, 0, P.key.bits); e->tmp.ensure(tb);
-  dev::sort_keys_u64(e->tmp.p, tb, P.cand, e->cand_sorted.as<uint64_t>(), (size_t)n_cand, 0, P.key.bits, s); ++e->launches;
+  size_t tb = 0;
+  if (!P.presorted) {
+    e->cand_sorted.ensure((size_t)n_cand * 8);
+    tb = dev::sort_keys_u64_tmp((size_t)n_cand, 0, P.key.bits); e->tmp.ensure(tb);
+    dev::sort_keys_u64(e->tmp.p, tb, P.cand, e->cand_sorted.as<uint64_t>(), (size_t)n_cand, 0, P.key.bits, s); ++e->launches;
+  }
   dev::event_record(P.ev_sorted, s);                      // the candidate buffer may be refilled by the next scan from here on
   // 2. align
   const int64_t n_slots = n_cand * P.slots;
   e->hits.ensure((size_t)n_slots * rw * 4); e->valid.ensure((size_t)n_slots * sizeof(CKey));
   AlignArgs aa; std::memset(&aa, 0, sizeof aa);
-  aa.cand = e->cand_sorted.as<uint64_t>(); aa.n_cand = n_cand; aa.specs = P.d_specs; aa.sc = e->sc; aa.slots = P.slots; aa.explicit_mode = P.explicit_mode ? 1 : 0;
+  aa.cand = P.presorted ? P.cand : e->cand_sorted.as<uint64_t>(); aa.n_cand = n_cand; aa.specs = P.d_specs; aa.sc = e->sc; aa.slots = P.slots; aa.explicit_mode = P.explicit_mode ? 1 : 0;
   aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows;
   aa.recs = e->hits.as<uint32_t>(); aa.rw = rw; aa.ckeys = e->valid.as<CKey>(); aa.key = P.key; aa.nib_last_word = P.nib_words - 1;
   dev::event_record(P.ev_align_b, s);
@@ -1399,12 +1418,14 @@ std::vector<GuideSpec> build_specs(calitas_engine* e, int32_t n_guides, const ca
 
 // explicit-window path shared by align_regions / align_targets
 // Shape of a launch over a set of guides: alignment slots per candidate, which align kernel, record size.
-struct LaunchShape { int slots, banded, rw; bool fast; };
+struct LaunchShape { int slots, banded, rw; bool fast; bool all_columns; /* every guide's threshold admits every column (best mode) */ };
 LaunchShape launch_shape(const std::vector<GuideSpec>& specs, size_t g0, size_t g1, int rw_all) {
-  LaunchShape L{ 1, 1, rw_all, true };
+  LaunchShape L{ 1, 1, rw_all, true, g1 > g0 };
   for (size_t g = g0; g < g1; ++g) { L.slots = std::max(L.slots, specs[g].slots); L.banded = std::max(L.banded, std::max(specs[g].k_edits, specs[g].band_k)); }
   if (L.banded > ALIGN_KB) L.banded = 0;
   L.fast = L.banded > 0; for (size_t g = g0; g < g1; ++g) L.fast = L.fast && fits_align_fast(specs[g], L.banded);
+  for (size_t g = g0; g < g1; ++g) L.all_columns = L.all_columns && specs[g].k_edits >= specs[g].lp;
+  if (L.banded > 0 || std::getenv("CALITAS_NO_ALL_COLUMNS")) L.all_columns = false;
   return L;
 }
 int rec_words_of(const std::vector<GuideSpec>& specs) { int m = 1; for (auto& sp : specs) m = std::max(m, sp.max_cols); return rec_words_for(m); }
@@ -1420,6 +1441,20 @@ void explicit_core(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, 
   for (int64_t w0 = 0; w0 < n_windows; w0 += batch) {
     const int64_t nw = std::min(batch, n_windows - w0);
     unsigned long long n_cand = 0;
+    if (L.all_columns) {
+      e->flag.ensure((size_t)(2 * nw) * 4); e->pos.ensure((size_t)(2 * nw) * 4);
+      dev::event_record(e->ev[4], s);
+      CAL_LAUNCH(k_window_columns, blocks_for(2 * nw, 256), 256, 0, s, 1, e->windows.as<ExplicitWindow>() + w0, nw, e->flag.as<uint32_t>()); dev::launch_check("k_window_columns"); ++e->launches;
+      size_t tb0 = dev::exclusive_sum_u32_tmp((size_t)(2 * nw)); e->tmp.ensure(tb0);
+      dev::exclusive_sum_u32(e->tmp.p, tb0, e->flag.as<uint32_t>(), e->pos.as<uint32_t>(), (size_t)(2 * nw), s); ++e->launches;
+      CAL_LAUNCH(k_publish_sum, 1, 1, 0, s, 1, e->pos.as<uint32_t>() + (2 * nw - 1), e->flag.as<uint32_t>() + (2 * nw - 1), (const unsigned long long*)nullptr, e->h_count_dev); dev::launch_check("k_publish_sum");
+      dev::stream_sync(s);
+      n_cand = *(volatile unsigned long long*)e->h_count;
+      if (n_cand >= (1ull << 32)) throw LimitExceeded("too many candidate columns in one batch");
+      e->cand.ensure((size_t)std::max<unsigned long long>(n_cand, 1) * 8);
+      CAL_LAUNCH(k_all_columns, blocks_for(2 * nw, 256), 256, 0, s, 1, e->windows.as<ExplicitWindow>() + w0, nw, e->pos.as<uint32_t>(), key, e->cand.as<uint64_t>()); dev::launch_check("k_all_columns"); ++e->launches;
+      dev::event_record(e->ev[5], s);
+    } else
     for (;;) {
       e->cand.ensure(e->cand_cap_hint * 8);
       dev::zero(e->d_count, 8, s);
@@ -1436,6 +1471,7 @@ void explicit_core(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, 
     counts[1] += (int64_t)n_cand;
     // window ids inside the batch are relative to w0: rebase through the pointer passed to the tail
     Pipeline P{ e, e->cand.as<uint64_t>(), e->ev[7], e->ev[2], e->ev[3], e->specs.as<GuideSpec>(), L.slots, true, L.banded, d_nib, nullptr, 0, 0, 0, e->windows.as<ExplicitWindow>() + w0, drop_halo, key, L.rw, L.fast, nib_words, nullptr, 0, out_owned };
+    P.presorted = L.all_columns;
     P.any_wide_group = max_len > (uint32_t)GROUP_W || L.rw > CALITAS_HIT_WORDS;          // record size > 32 bytes <=> some guide can produce more than 48 columns (the warp kernel takes 64)
     int64_t n_aln = 0;
     const int64_t n_kept = run_tail(P, (int64_t)n_cand, n_out, 0, n_aln);
