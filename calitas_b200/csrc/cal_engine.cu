@@ -1454,6 +1454,7 @@ void explicit_core(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, 
       e->cand.ensure((size_t)std::max<unsigned long long>(n_cand, 1) * 8);
       CAL_LAUNCH(k_all_columns, blocks_for(2 * nw, 256), 256, 0, s, 1, e->windows.as<ExplicitWindow>() + w0, nw, e->pos.as<uint32_t>(), key, e->cand.as<uint64_t>()); dev::launch_check("k_all_columns"); ++e->launches;
       dev::event_record(e->ev[5], s);
+      dev::event_sync(e->ev[5]);                            // its time is read right below
     } else
     for (;;) {
       e->cand.ensure(e->cand_cap_hint * 8);
