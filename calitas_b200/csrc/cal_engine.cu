@@ -415,7 +415,8 @@ CAL_D void align_body(const AlignArgs& a) {
 // but nothing goes through byte arrays in local memory:
 //   * the 64 target codes the candidate can touch (band + PAM extension) are loaded once as nine 32-bit words and kept in registers; the reverse
 //     strand costs one BREV per word (reversing the bits of a word reverses the order of its 4-bit codes AND complements each code: A=1 <-> T=8,
-//     C=2 <-> G=4) instead of a complement per fetched base; per DP row the 256-bit window slides by one code (eight funnel shifts);
+//     C=2 <-> G=4) instead of a complement per fetched base; from them four bit vectors say which window positions hold A, C, G, T, and a DP row
+//     reads the match flags of its whole band from them with one shift (no per-cell code extraction, no per-cell match-trace bit);
 //   * the traceback shifts each 2-bit op straight into a 128-bit register pair (first column ends up in the low bits = guide orientation for a
 //     3' PAM; a 5' PAM reverses the fields at the end), counts and the terminal gap run are taken on the way;
 //   * the extension appends the guide-PAM gap and the PAM ops with shifts, and the record leaves as two (four) 16-byte stores.
@@ -451,7 +452,8 @@ CAL_D uint32_t spread_bits16(uint32_t v) {    // bit i of v -> bit 2 i
   return v;
 }
 // target codes right of an alignment's last guide column j, for the PAM extension: code(k) = base at column j + 1 + k
-struct RegCodes { uint64_t e0, e1; int first; CAL_D uint32_t operator()(int k) const { const int idx = first + k; return (uint32_t)((idx < 16 ? e0 >> (4 * idx) : e1 >> (4 * (idx - 16))) & 15u); } };
+struct RegCodes { uint64_t e0, e1, e2, e3; int first;
+  CAL_D uint32_t operator()(int k) const { const int idx = first + k; const uint64_t e = idx < 32 ? (idx < 16 ? e0 : e1) : (idx < 48 ? e2 : e3); return (uint32_t)(e >> (4 * (idx & 15))) & 15u; } };
 // Everything after the traceback of one guide alignment, shared by the register-resident aligners: the diffs filter (SequentialGuideAligner.scala:447,450),
 // extend_pam for every PAM (:433-492), the ops of guide-PAM gap and PAM, Cigar.reverse for a 5' PAM, the coordinates of make_hit (:263-310, 505-524),
 // the record as 16-byte stores and the canon key.  `ops`: n_g two-bit ops, first alignment column in the low bits; term / term_op: the trailing gap run.
@@ -520,6 +522,16 @@ CAL_D void emit_hit_slots(const AlignArgs& a, const CandCtx& x, const GuideSpec&
     a.ckeys[slot0 + pi] = ckey_make(score, start, start + (e0c - s0), gaps, edits, x.owned);
   }
 }
+// The 64 target codes from DP column base + 1 on, in scan order, as eight words (reverse strand: reversed and complemented by BREV).
+CAL_D void load_code_window(const AlignArgs& a, const CandCtx& x, int base, uint32_t A[8]) {
+  const int64_t q_lo = x.dir == 0 ? x.first + base : x.first + x.m - (base + 1) - 63;       // lowest nibble index of the stretch
+  const int64_t w0 = q_lo >> 3; const int sh = (int)(q_lo & 7) * 4;
+  uint32_t W[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { int64_t w = w0 + k; w = w < 0 ? 0 : (w > a.nib_last_word ? a.nib_last_word : w); W[k] = __ldg(a.nib + w); }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const uint32_t v = shift_in_low_bits(W[k], W[k + 1], sh); if (x.dir == 0) A[k] = v; else A[7 - k] = brev32(v); }
+}
 template <int KB>
 CAL_D void align_fast(const AlignArgs& a) {
   constexpr int B = 2 * KB + 1;
@@ -534,44 +546,47 @@ CAL_D void align_fast(const AlignArgs& a) {
   const int base = j - n - KB;                       // cell (i, t) is target column c = i + base + t; the register window starts at column base + 1
   // ---- the 64 codes from column base + 1 on, in scan order -----------------------------------------------------------------------------
   uint32_t A[8];
-  {
-    const int64_t q_lo = x.dir == 0 ? x.first + base : x.first + x.m - (base + 1) - 63;       // lowest nibble index of the stretch
-    const int64_t w0 = q_lo >> 3; const int sh = (int)(q_lo & 7) * 4;
-    uint32_t W[9];
+  load_code_window(a, x, base, A);
+  // ---- which positions of the window pair with which base: four 64-bit vectors (bit k = the code at window position k holds base b), N excluded.
+  //      A DP row then gets the match flags of its whole band with one shift: position of diagonal t in row r is r - 1 + t.
+  uint64_t T[4] = { 0ull, 0ull, 0ull, 0ull };
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { int64_t w = w0 + k; w = w < 0 ? 0 : (w > a.nib_last_word ? a.nib_last_word : w); W[k] = __ldg(a.nib + w); }
+  for (int k = 0; k < 6; ++k) {                        // 48 positions cover lp + 2 KB + 1 <= 45
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { const uint32_t v = shift_in_low_bits(W[k], W[k + 1], sh); if (x.dir == 0) A[k] = v; else A[7 - k] = brev32(v); }
+    for (int b = 0; b < 4; ++b) {
+      uint32_t v = (A[k] >> b) & 0x11111111u;          // bit b of each of the word's eight codes, at stride 4 ...
+      v = (v | (v >> 3)) & 0x03030303u; v = (v | (v >> 6)) & 0x000F000Fu; v = (v | (v >> 12)) & 0xFFu;     // ... compressed to eight adjacent bits
+      T[b] |= (uint64_t)v << (8 * k);
+    }
   }
-  // ---- DP fill: band_align_k's recurrence with the codes taken from the sliding window --------------------------------------------------
+  { const uint64_t is_n = T[0] & T[1] & T[2] & T[3];   // code 15: upper-case N never matches (SequentialGuideAligner.scala:144)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) T[b] &= ~is_n; }
+  // ---- DP fill: band_align_k's recurrence -------------------------------------------------------------------------------------------------
   const Scores& sc = a.sc;
   const int32_t NEG4 = 4 * NEG_SCORE;
   int32_t d[B], l[B], u[B];
   uint32_t trd[CALITAS_MAX_PROTOSPACER + 1], tru[CALITAS_MAX_PROTOSPACER + 1], trl[CALITAS_MAX_PROTOSPACER + 1], trm[CALITAS_MAX_PROTOSPACER + 1];
 #pragma unroll
   for (int t = 0; t < B; ++t) { const int c = base + t; const int32_t v = (c >= 0 && c <= j) ? 0 : NEG4; d[t] = v + TG_DIAG; l[t] = v + TG_LEFT; u[t] = v + TG_UP; }
-  const int32_t gI4 = 4 * sc.target_gap, gD4 = 4 * sc.query_gap, mis4 = 4 * sc.mismatch, dmatch4 = 4 * (sc.match - sc.mismatch);
+  const int32_t gI4 = 4 * sc.target_gap, gD4 = 4 * sc.query_gap, mis4 = 4 * sc.mismatch, match4 = 4 * sc.match;
   for (int r = 1; r <= n; ++r) {
-    const uint32_t qm = g.qmask[r - 1];
-    const uint64_t win = (uint64_t)A[0] | ((uint64_t)A[1] << 32);        // codes of columns r + base .. : diagonal t of this row is code t
-    uint32_t wd = 0, wu = 0, wl = 0, wm = 0;
+    const uint32_t qs = g.q[r - 1];                     // the row's base set
+    const uint64_t tq = ((qs & 1u) ? T[0] : 0ull) | ((qs & 2u) ? T[1] : 0ull) | ((qs & 4u) ? T[2] : 0ull) | ((qs & 8u) ? T[3] : 0ull);
+    const uint32_t m = (uint32_t)(tq >> (r - 1)) & ((1u << B) - 1u);     // bit t: the row's base pairs with the target base of diagonal t
+    uint32_t wd = 0, wu = 0, wl = 0;
     int32_t left_d = NEG4 + TG_DIAG, left_l = NEG4 + TG_LEFT, left_u = NEG4 + TG_UP;
 #pragma unroll
     for (int t = 0; t < B; ++t) {
-      const uint32_t code = (uint32_t)(win >> (4 * t)) & 15u;
-      const uint32_t mt = (qm >> code) & 1u;
-      const int32_t add4 = mis4 + (int32_t)mt * dmatch4;
+      const int32_t add4 = (m & (1u << t)) ? match4 : mis4;
       const int32_t md = max3_s32(d[t], l[t], u[t]);
       const int32_t mu = t + 1 < B ? (d[t + 1] > u[t + 1] ? d[t + 1] : u[t + 1]) : NEG4 + TG_DIAG;
       const int32_t ml = max3_s32(left_d, left_l, left_u);
       const int32_t nd = (md | 3) + add4, nu = ((mu & ~3) | TG_UP) + gI4, nl = ((ml & ~3) | TG_LEFT) + gD4;
-      wd = shift_in_low_bits(wd, (uint32_t)md, 2); wu = shift_in_low_bits(wu, (uint32_t)mu, 2); wl = shift_in_low_bits(wl, (uint32_t)ml, 2); wm = shift_in_low_bits(wm, mt, 1);
+      wd = shift_in_low_bits(wd, (uint32_t)md, 2); wu = shift_in_low_bits(wu, (uint32_t)mu, 2); wl = shift_in_low_bits(wl, (uint32_t)ml, 2);
       d[t] = nd; u[t] = nu; l[t] = nl; left_d = nd; left_l = nl; left_u = nu;
     }
-    trd[r] = wd; tru[r] = wu; trl[r] = wl; trm[r] = wm;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) A[k] = shift_in_low_bits(A[k], A[k + 1], 4);   // slide the window one column to the right
-    A[7] >>= 4;
+    trd[r] = wd; tru[r] = wu; trl[r] = wl; trm[r] = m;
   }
   const int32_t mbest = max3_s32(d[KB], l[KB], u[KB]);
   const int32_t best = mbest >> 2;
@@ -583,7 +598,7 @@ CAL_D void align_fast(const AlignArgs& a) {
     const int shb = 32 - 2 * B + 2 * ct;
     const int next = (int)(((cdir == TG_DIAG ? trd[ci] : (cdir == TG_UP ? tru[ci] : trl[ci])) >> shb) & 3u);
     uint32_t op;
-    if (cdir == TG_DIAG) { op = ((trm[ci] >> (32 - B + ct)) & 1u) ? OP_EQ : OP_X; --ci; }
+    if (cdir == TG_DIAG) { op = ((trm[ci] >> ct) & 1u) ? OP_EQ : OP_X; --ci; }
     else if (cdir == TG_LEFT) { op = OP_D; --ct; }
     else { op = OP_I; --ci; ++ct; }
     if (ct < 0 || ct >= B) return;                       // cannot happen for an accepted end cell; keeps indexing safe
@@ -592,9 +607,10 @@ CAL_D void align_fast(const AlignArgs& a) {
     ++n_g;
     cdir = next;
   }
-  // after n slides code k of the window is column j - KB + 1 + k: the base right of the alignment (column j + 1) is code KB
-  const uint64_t e0 = (uint64_t)A[0] | ((uint64_t)A[1] << 32), e1 = (uint64_t)A[2] | ((uint64_t)A[3] << 32);
-  const RegCodes after{ e0, e1, KB };
+  // window position k is column base + 1 + k: the base right of the alignment (column j + 1) is position n + KB.  The window is loaded again (from
+  // L1/L2) rather than kept in eight registers across the DP loop.
+  load_code_window(a, x, base, A);
+  const RegCodes after{ (uint64_t)A[0] | ((uint64_t)A[1] << 32), (uint64_t)A[2] | ((uint64_t)A[3] << 32), (uint64_t)A[4] | ((uint64_t)A[5] << 32), (uint64_t)A[6] | ((uint64_t)A[7] << 32), n + KB };
   emit_hit_slots(a, x, g, ops, n_g, term, term_op, best, base + ct + 1, j, after, i * a.slots);
 }
 CAL_KERNEL __launch_bounds__(128) k_align_fast6(AlignArgs a) { align_fast<6>(a); }
@@ -1256,7 +1272,7 @@ struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> alig
 bool fits_align_fast(const GuideSpec& sp, int banded) {
   const int kb = banded > 5 ? 6 : (banded == 5 ? 5 : 4);
   int pam = 0; for (int k = 0; k < sp.n_pams; ++k) pam = std::max<int>(pam, sp.pam_len[k]);
-  return !std::getenv("CALITAS_NO_ALIGN_FAST") && sp.lp + kb + sp.g + pam <= 64 && kb + sp.g + pam <= 32;
+  return !std::getenv("CALITAS_NO_ALIGN_FAST") && sp.lp + kb + sp.g + pam <= 64;
 }
 
 // e->out must hold (out_n + more) records; the first out_n are kept
