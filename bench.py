@@ -225,7 +225,9 @@ def workload_config(args, genome, guides):
            "name": args.workload, "guides_per_step": w["guides"], "genome_bp": genome.total(), "window_size": 1000, "max_guide_diffs": w["d"],
            "max_pam_mismatches": w["p"], "max_gaps_between_guide_and_pam": w["g"], "pams": pams, "max_overlap": 10, "dedup": "removeOverlaps+sort on device",
            "l2": "inputs larger than L2 (packed reference shard per scan launch >> 126 MB)" if genome.total() > 5e8 else "L2 flushed between steps by a 256-MB device write",
-           "parallelism": "contig-range shards, 1 rank per GPU, no collective"}
+           "parallelism": "contig-range shards, 1 rank per GPU, no collective",
+           "n_fraction": round(sum(e - b for blocks in genome.n_blocks for (b, e) in blocks) / float(genome.total()), 4),
+           "n_fraction_note": "genome_bp (the metric's numerator) counts every base; windows inside N blocks (telomeres, centromere-like and scattered blocks) are trimmed away, not scanned"}
     if w["kind"] == "vcf":
         cfg["workload"] += "; -v synthetic PrepareVcf-shaped VCF, %d records genome-wide, max-variants 16" % w["records"]
         cfg["vcf_records"] = w["records"]

@@ -2001,13 +2001,13 @@ int calitas_variant_set_load(calitas_engine* e, const calitas_reference* ref, in
       std::vector<std::thread> th;
       for (int t = 0; t < nt; ++t) th.emplace_back([&, t]() { for (int64_t w = n_windows * t / nt; w < n_windows * (t + 1) / nt; ++w) if (windows[w].length) std::memcpy(raw.data() + wd[(size_t)w].nib_start, windows[w].bases, (size_t)windows[w].length); });
       for (auto& t : th) t.join();
-      DBuf d_raw; d_raw.ensure((size_t)total); vs->nib.ensure((size_t)total / 2 + 8);
+      DBuf d_raw; struct Guard { DBuf& b; ~Guard() { try { b.release(); } catch (...) {} } } guard{ d_raw };
+      d_raw.ensure((size_t)total); vs->nib.ensure((size_t)total / 2 + 8);
       dev::h2d(d_raw.p, raw.data(), (size_t)total, s);
       const int64_t n_words = total / 8;
       const unsigned grid = (unsigned)std::min<int64_t>((n_words + 255) / 256, (int64_t)dev::sm_count(e->device) * 16);
       CAL_LAUNCH(k_pack, grid, 256, 256, s, 2, d_raw.as<uint8_t>(), vs->nib.as<uint32_t>(), n_words); dev::launch_check("k_pack");
       dev::stream_sync(s);
-      d_raw.release();
       vs->nib_words = n_words;
     }
     vs->windows.ensure(std::max<size_t>(1, wd.size()) * sizeof(VarWindowDev)); dev::h2d(vs->windows.p, wd.data(), wd.size() * sizeof(VarWindowDev), s);
@@ -2163,14 +2163,23 @@ int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_gui
       windows[(size_t)i] = ExplicitWindow{ total, t.length, t.target_offset, t.guide_idx, -1, (int32_t)i, 1 };
       total += (t.length + 7) / 8 * 8 + 8;
     }
-    // targets are small: pack on the host into the same 4-bit code words the device packer produces
-    std::vector<uint32_t> words((size_t)total / 8 + 1, 0u);
-    for (int64_t i = 0; i < n_tasks; ++i) {
-      const calitas_target_task& t = tasks[i]; const int64_t b = windows[(size_t)i].nib_start;
-      for (int32_t k = 0; k < t.length; ++k) words[(size_t)((b + k) >> 3)] |= target_code(t.bases[k]) << (((b + k) & 7) * 4);
+    // the target bytes are gathered into one staging buffer on all host threads, uploaded and packed by k_pack, like the reference and the variant windows
+    total = (total + 7) / 8 * 8 + 64;
+    {
+      std::vector<uint8_t> raw((size_t)total, 0);
+      const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_tasks / 65536 + 1, std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()))));
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) th.emplace_back([&, t]() { for (int64_t i = n_tasks * t / nt; i < n_tasks * (t + 1) / nt; ++i) if (tasks[i].length) std::memcpy(raw.data() + windows[(size_t)i].nib_start, tasks[i].bases, (size_t)tasks[i].length); });
+      for (auto& t : th) t.join();
+      DBuf d_raw; struct Guard { DBuf& b; ~Guard() { try { b.release(); } catch (...) {} } } guard{ d_raw };
+      d_raw.ensure((size_t)total); e->nib_tmp.ensure((size_t)total / 2 + 8);
+      dev::h2d(d_raw.p, raw.data(), (size_t)total, e->stream);
+      const int64_t n_words = total / 8;
+      const unsigned grid = (unsigned)std::min<int64_t>((n_words + 255) / 256, (int64_t)dev::sm_count(e->device) * 16);
+      CAL_LAUNCH(k_pack, grid, 256, 256, e->stream, 2, d_raw.as<uint8_t>(), e->nib_tmp.as<uint32_t>(), n_words); dev::launch_check("k_pack");
+      dev::stream_sync(e->stream);
     }
-    e->nib_tmp.ensure(words.size() * 4); dev::h2d(e->nib_tmp.p, words.data(), words.size() * 4, e->stream); dev::stream_sync(e->stream);
-    *out = run_explicit(e, e->nib_tmp.as<uint32_t>(), (int64_t)words.size(), windows, specs);
+    *out = run_explicit(e, e->nib_tmp.as<uint32_t>(), total / 8, windows, specs);
     return CALITAS_OK;
   });
 }
