@@ -331,6 +331,7 @@ struct AlignArgs {
   const ExplicitWindow* windows;                                             // explicit (window ids index this array)
   uint32_t* recs; int32_t rw; CKey* ckeys; KeyLayout key;        // packed hit records, rw words each, and one canon key per alignment slot (cal_core.cuh)
   int64_t nib_last_word;                                        // last valid word of `nib` (align_fast clamps its nine loads to it)
+  int32_t match4, mis4, up4, left4;                             // align_pair: 4 * match, 4 * mismatch, 4 * target_gap + TG_UP, 4 * query_gap + TG_LEFT
 };
 struct NibFetch {
   const uint32_t* nib; int64_t first; int32_t m; int dir;
@@ -616,6 +617,168 @@ CAL_D void align_fast(const AlignArgs& a) {
 CAL_KERNEL __launch_bounds__(128) k_align_fast6(AlignArgs a) { align_fast<6>(a); }
 CAL_KERNEL __launch_bounds__(128) k_align_fast5(AlignArgs a) { align_fast<5>(a); }
 CAL_KERNEL __launch_bounds__(128) k_align_fast4(AlignArgs a) { align_fast<4>(a); }
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// align_pair: align_fast for TWO candidates per thread (candidates 2p and 2p + 1 of the sorted list), their DP cells side by side in the two 16-bit
+// halves of one register.  The packed forms of the cell's instructions (VIMNMX3.S16x2, VIMNMX.S16x2, VIADDMNMX.S16x2) issue at the rate of the 32-bit
+// ones (measured: 17.3 against 18.5 T thread-instructions/s), the tag and mask operations are plain 32-bit logic, so one instruction stream fills two
+// band matrices.  Same cells, tie order and traces as align_fast; what changes is how the numbers are held:
+//   * a value is 4 * score + tag in 16 bits.  Unreachable cells start at PAIR_FLOOR and every sum is clamped there by the VIADDMNMX that forms it, so
+//     nothing wraps.  A clamped value is too large by construction but never above PAIR_FLOOR + 3 + r * match4 in row r, and every cell on a path to an
+//     accepted end cell holds at least 4 * min_score - (n - r) * match4: the launch takes this kernel only when
+//     PAIR_FLOOR + 3 + n * match4 < 4 * min_score for every guide (pair_fits; defaults: -27 197 < 1 872), so on those cells every maximum is decided
+//     between exact values, exactly as in 32 bits;
+//   * the row's match flags come from bit-REVERSED position vectors, cell 0 in the top bit of each half: one PRMT turns the two top bits into two
+//     half-word masks that select 4 * match or 4 * mismatch per half, and the flags move up one bit per cell;
+//   * the 2-bit winners are not extracted cell by cell: acc = 4 * acc + value and ref = 4 * ref + (value with its tag forced) are two IMADs on the
+//     otherwise idle FMA pipe, whatever spills out of a half spills out of both alike, and ref - acc (Diagonal: tag forced to 3) or acc - ref (Up, Left:
+//     tag cleared) is the clean sum of 4^k * (3 - tag) or 4^k * tag per half; eight cells per half-word, so cells 8 .. B-1 use a second accumulator.
+// MEASURED, AND NOT THE DEFAULT (CALITAS_ALIGN_PAIR=1 selects it; parity green on hostsim and on the GPU): the fill drops from 2 x 207 to 310 instructions
+// per row of two candidates (ALU-pipe instructions 2 x 150 -> 175), but on 2.0 x 10^7 candidates (config 4, a quarter genome) the kernel takes 7.22 ms
+// against k_align_fast6's 6.56 ms (ncu, profiles/r02r_summary.txt): traceback, PAM extension and record emission are per candidate and already were
+// 32 % of align_fast's instructions, so the whole kernel executes only 15 % fewer (4.78 G against 5.65 G warp instructions), and at 96 registers it runs
+// 18 warps per SM instead of 24 with two dependent local-memory walks per thread (long-scoreboard stall 3.2 per issue against 1.6; issue slots 58 %
+// against 74 %).  With both walks interleaved it went from 8.5 to 7.2 ms; config 4 as a whole: 420 against 442 Gbp*guides/s.
+// ------------------------------------------------------------------------------------------------------------------------------------
+const int32_t PAIR_FLOOR = -32000;                      // a multiple of 4; leaves room for one addend below it (pair_fits bounds the addends)
+CAL_D uint32_t p2_pack(int32_t lo, int32_t hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+CAL_D int32_t p2_half(uint32_t v, int lane) { return (int32_t)(int16_t)(uint16_t)(lane ? (v >> 16) : (v & 0xFFFFu)); }
+#if defined(__CUDA_ARCH__)
+CAL_D uint32_t p2_max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+CAL_D uint32_t p2_max(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+CAL_D uint32_t p2_addmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }           // per half: max(a + b, c)
+CAL_D uint32_t p2_signmask(uint32_t v) { uint32_t r; asm("prmt.b32 %0, %1, 0, 0xbb99;" : "=r"(r) : "r"(v)); return r; }   // per half: 0xFFFF when its top bit is set (selector bit 3: replicate the byte's sign; __byte_perm drops that bit)
+CAL_D uint32_t p2_shift_in(uint32_t acc, uint32_t v) { uint32_t r; asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(r) : "r"(acc), "r"(v)); return r; }   // 4 * acc + v as ONE IMAD (FMA pipe)
+#else
+CAL_D uint32_t p2_max3(uint32_t a, uint32_t b, uint32_t c) {
+  auto m3 = [](int32_t x, int32_t y, int32_t z) { const int32_t m = x > y ? x : y; return m > z ? m : z; };
+  return p2_pack(m3(p2_half(a, 0), p2_half(b, 0), p2_half(c, 0)), m3(p2_half(a, 1), p2_half(b, 1), p2_half(c, 1)));
+}
+CAL_D uint32_t p2_max(uint32_t a, uint32_t b) { return p2_max3(a, b, b); }
+CAL_D uint32_t p2_addmax(uint32_t a, uint32_t b, uint32_t c) {
+  auto am = [](int32_t x, int32_t y, int32_t z) { const int32_t v = (int32_t)(int16_t)(uint16_t)(x + y); return v > z ? v : z; };
+  return p2_pack(am(p2_half(a, 0), p2_half(b, 0), p2_half(c, 0)), am(p2_half(a, 1), p2_half(b, 1), p2_half(c, 1)));
+}
+CAL_D uint32_t p2_signmask(uint32_t v) { return ((v & 0x8000u) ? 0xFFFFu : 0u) | ((v & 0x80000000u) ? 0xFFFF0000u : 0u); }
+CAL_D uint32_t p2_shift_in(uint32_t acc, uint32_t v) { return acc * 4u + v; }
+#endif
+// bit-reversed position vectors of one candidate's code window: bit 63 - k of R[b] = the code at window position k holds base b (N excluded)
+CAL_D void pair_vectors(const AlignArgs& a, const CandCtx& x, int base, uint64_t R[4]) {
+  uint32_t A[8];
+  load_code_window(a, x, base, A);
+  uint64_t T[4] = { 0ull, 0ull, 0ull, 0ull };
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      uint32_t v = (A[k] >> b) & 0x11111111u;
+      v = (v | (v >> 3)) & 0x03030303u; v = (v | (v >> 6)) & 0x000F000Fu; v = (v | (v >> 12)) & 0xFFu;
+      T[b] |= (uint64_t)v << (8 * k);
+    }
+  }
+  const uint64_t is_n = T[0] & T[1] & T[2] & T[3];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) { const uint64_t t = T[b] & ~is_n; R[b] = ((uint64_t)brev32((uint32_t)t) << 32) | (uint64_t)brev32((uint32_t)(t >> 32)); }
+}
+template <int KB>
+CAL_D void align_pair(const AlignArgs& a) {
+  constexpr int B = 2 * KB + 1;
+  constexpr int B1 = B < 8 ? B : 8;                    // cells in the first trace accumulator
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = 2 * p;
+  if (i0 >= a.n_cand) return;
+  const bool two = i0 + 1 < a.n_cand;                  // an odd list ends with a thread whose second half repeats the first and reports nothing
+  const uint64_t key0 = a.cand[i0], key1 = a.cand[two ? i0 + 1 : i0];
+  const int32_t j0 = key_col(a.key, key0), j1 = key_col(a.key, key1);
+  const CandCtx x0 = decode_candidate(a, key0), x1 = decode_candidate(a, key1);
+  const GuideSpec& g0 = a.specs[x0.gidx]; const GuideSpec& g1 = a.specs[x1.gidx];
+  for (int s = 0; s < (two ? 2 : 1) * a.slots; ++s) a.ckeys[i0 * a.slots + s] = CKey{ 0, 0, 0, 0u };
+  const int n = g0.lp;                                 // the same for every guide of the launch (pair_fits)
+  const int base0 = j0 - n - KB, base1 = j1 - n - KB;
+  uint64_t R0[4], R1[4];
+  pair_vectors(a, x0, base0, R0); pair_vectors(a, x1, base1, R1);
+  // ---- DP fill ------------------------------------------------------------------------------------------------------------------------------
+  const uint32_t FLOORP = p2_pack(PAIR_FLOOR, PAIR_FLOOR);
+  const uint32_t MISP = p2_pack(a.mis4, a.mis4), XP = p2_pack(a.match4 ^ a.mis4, a.match4 ^ a.mis4), UPP = p2_pack(a.up4, a.up4), LEFTP = p2_pack(a.left4, a.left4);
+  const uint32_t T3 = 0x00030003u, TC = 0xFFFCFFFCu;
+  uint32_t d[B], l[B], u[B];
+  uint32_t trd[CALITAS_MAX_PROTOSPACER + 1], tru[CALITAS_MAX_PROTOSPACER + 1], trl[CALITAS_MAX_PROTOSPACER + 1], trm[CALITAS_MAX_PROTOSPACER + 1];
+  uint32_t trd2[CALITAS_MAX_PROTOSPACER + 1], tru2[CALITAS_MAX_PROTOSPACER + 1], trl2[CALITAS_MAX_PROTOSPACER + 1];
+#pragma unroll
+  for (int t = 0; t < B; ++t) {
+    const int c0 = base0 + t, c1 = base1 + t;
+    const int32_t v0 = (c0 >= 0 && c0 <= j0) ? 0 : PAIR_FLOOR, v1 = (c1 >= 0 && c1 <= j1) ? 0 : PAIR_FLOOR;
+    d[t] = p2_pack(v0 + TG_DIAG, v1 + TG_DIAG); l[t] = p2_pack(v0 + TG_LEFT, v1 + TG_LEFT); u[t] = p2_pack(v0 + TG_UP, v1 + TG_UP);
+  }
+  for (int r = 1; r <= n; ++r) {
+    const uint32_t qs0 = g0.q[r - 1], qs1 = g1.q[r - 1];
+    const uint64_t tq0 = ((qs0 & 1u) ? R0[0] : 0ull) | ((qs0 & 2u) ? R0[1] : 0ull) | ((qs0 & 4u) ? R0[2] : 0ull) | ((qs0 & 8u) ? R0[3] : 0ull);
+    const uint64_t tq1 = ((qs1 & 1u) ? R1[0] : 0ull) | ((qs1 & 2u) ? R1[1] : 0ull) | ((qs1 & 4u) ? R1[2] : 0ull) | ((qs1 & 8u) ? R1[3] : 0ull);
+    // cell t of the row sits at window position r - 1 + t = bit 63 - (r - 1 + t) of the reversed vector: cell 0 goes to the top bit of its half
+    uint32_t mm = (uint32_t)(((tq0 << (r - 1)) >> 48) & 0xFFFFu) | ((uint32_t)((tq1 << (r - 1)) >> 48) << 16);
+    trm[r] = mm;
+    uint32_t ad = 0, rd = 0, au = 0, ru = 0, al = 0, rl = 0;
+    uint32_t left_d = p2_pack(PAIR_FLOOR + TG_DIAG, PAIR_FLOOR + TG_DIAG), left_l = p2_pack(PAIR_FLOOR + TG_LEFT, PAIR_FLOOR + TG_LEFT), left_u = p2_pack(PAIR_FLOOR + TG_UP, PAIR_FLOOR + TG_UP);
+#pragma unroll
+    for (int t = 0; t < B; ++t) {
+      const uint32_t add4 = (p2_signmask(mm) & XP) ^ MISP;              // 4 * match where the half's flag is set, else 4 * mismatch
+      mm += mm;                                                         // the next cell's flags move to the top (what crosses into the upper half stays below the bits still to be read: B <= 16)
+      const uint32_t md = p2_max3(d[t], l[t], u[t]);
+      const uint32_t mu = t + 1 < B ? p2_max(d[t + 1], u[t + 1]) : p2_pack(PAIR_FLOOR + TG_DIAG, PAIR_FLOOR + TG_DIAG);
+      const uint32_t ml = p2_max3(left_d, left_l, left_u);
+      const uint32_t fd = md | T3, fu = mu & TC, fl = ml & TC;          // the value with its tag forced to 3 / cleared
+      const uint32_t nd = p2_addmax(fd, add4, FLOORP), nu = p2_addmax(fu, UPP, FLOORP), nl = p2_addmax(fl, LEFTP, FLOORP);
+      if (t == B1) { trd[r] = rd - ad; tru[r] = au - ru; trl[r] = al - rl; ad = rd = au = ru = al = rl = 0; }
+      ad = p2_shift_in(ad, md); rd = p2_shift_in(rd, fd); au = p2_shift_in(au, mu); ru = p2_shift_in(ru, fu); al = p2_shift_in(al, ml); rl = p2_shift_in(rl, fl);
+      d[t] = nd; u[t] = nu; l[t] = nl; left_d = nd; left_l = nl; left_u = nu;
+    }
+    if (B > B1) { trd2[r] = rd - ad; tru2[r] = au - ru; trl2[r] = al - rl; }
+    else { trd[r] = rd - ad; tru[r] = au - ru; trl[r] = al - rl; }
+  }
+  const uint32_t mbest2 = p2_max3(d[KB], l[KB], u[KB]);
+  // ---- traceback: the two candidates' walks run side by side (two independent chains of dependent local-memory loads in flight) -----------------
+  struct Walk { Ops128 ops; int ci, ct, cdir, n_g, term, term_op; };
+  Walk w0{ Ops128{ 0ull, 0ull }, 0, KB, 0, 0, 0, 0 }, w1 = w0;
+  const int32_t mb0 = p2_half(mbest2, 0), mb1 = p2_half(mbest2, 1);
+  if ((mb0 >> 2) >= g0.min_score) { w0.ci = n; w0.cdir = mb0 & 3; }
+  if (two && (mb1 >> 2) >= g1.min_score) { w1.ci = n; w1.cdir = mb1 & 3; }
+  const bool live0 = w0.ci > 0, live1 = w1.ci > 0;
+  bool bad0 = false, bad1 = false;
+  auto walk_step = [&](Walk& w, const int lsh, bool& bad) {
+    const bool second = w.ct >= B1;
+    const int shb = lsh + 2 * (second ? B - 1 - w.ct : B1 - 1 - w.ct);
+    const uint32_t tw = w.cdir == TG_DIAG ? (second ? trd2[w.ci] : trd[w.ci]) : (w.cdir == TG_UP ? (second ? tru2[w.ci] : tru[w.ci]) : (second ? trl2[w.ci] : trl[w.ci]));
+    const int f = (int)((tw >> shb) & 3u);
+    const int next = w.cdir == TG_DIAG ? 3 - f : f;
+    uint32_t op;
+    if (w.cdir == TG_DIAG) { op = ((trm[w.ci] >> (lsh + 15 - w.ct)) & 1u) ? OP_EQ : OP_X; --w.ci; }
+    else if (w.cdir == TG_LEFT) { op = OP_D; --w.ct; }
+    else { op = OP_I; --w.ci; ++w.ct; }
+    if (w.ct < 0 || w.ct >= B) { bad = true; w.ci = 0; w.ct = 0; return; }          // cannot happen for an accepted end cell; keeps indexing safe
+    if (w.n_g == w.term && op >= OP_I && (w.term == 0 || (int)op == w.term_op)) { ++w.term; w.term_op = (int)op; }
+    w.ops.hi = (w.ops.hi << 2) | (w.ops.lo >> 62); w.ops.lo = (w.ops.lo << 2) | op;
+    ++w.n_g;
+    w.cdir = next;
+  };
+  while (w0.ci > 0 || w1.ci > 0) {
+    if (w0.ci > 0) walk_step(w0, 0, bad0);
+    if (w1.ci > 0) walk_step(w1, 16, bad1);
+  }
+  // ---- emission, as in align_fast ----------------------------------------------------------------------------------------------------------
+#pragma unroll 1
+  for (int lane = 0; lane < 2; ++lane) {
+    if (lane ? (!live1 || bad1) : (!live0 || bad0)) continue;
+    const CandCtx& x = lane ? x1 : x0; const GuideSpec& g = lane ? g1 : g0; const Walk& w = lane ? w1 : w0;
+    const int32_t j = lane ? j1 : j0; const int base = lane ? base1 : base0;
+    uint32_t A[8];
+    load_code_window(a, x, base, A);
+    const RegCodes after{ (uint64_t)A[0] | ((uint64_t)A[1] << 32), (uint64_t)A[2] | ((uint64_t)A[3] << 32), (uint64_t)A[4] | ((uint64_t)A[5] << 32), (uint64_t)A[6] | ((uint64_t)A[7] << 32), n + KB };
+    emit_hit_slots(a, x, g, w.ops, w.n_g, w.term, w.term_op, (lane ? mb1 : mb0) >> 2, base + w.ct + 1, j, after, (i0 + lane) * a.slots);
+  }
+}
+CAL_KERNEL __launch_bounds__(128, 5) k_align_pair6(AlignArgs a) { align_pair<6>(a); }
+CAL_KERNEL __launch_bounds__(128, 5) k_align_pair5(AlignArgs a) { align_pair<5>(a); }
+CAL_KERNEL __launch_bounds__(128, 5) k_align_pair4(AlignArgs a) { align_pair<4>(a); }
 
 // Wide thresholds on short explicit windows (alignBest / alignToRefBest: every end column is a candidate): one thread per (window, strand)
 // group of consecutive sorted candidates fills the DP once and traces every candidate column (band_align_group).
@@ -1093,17 +1256,30 @@ CAL_KERNEL k_publish_sum(const uint32_t* a, const uint32_t* b, const unsigned lo
 //   kind 1  IMAD only            -> FMA-pipe issue rate
 //   kind 2  LOP3 and IMAD, 1:1   -> both pipes together (scheduler issue limit)
 //   kind 3  IMAD.HI only, kind 4 LEA.HI only: rates of the two candidate instructions for the score update
+//   kind 5-11: the instructions of the DP cell (VIMNMX3, its packed 16-bit forms, SHF) and ALU + FMA mixes with two register operands per instruction
 // ------------------------------------------------------------------------------------------------------------------------------------
 #ifndef CAL_HOSTSIM
 CAL_D uint32_t pk_lop3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 CAL_D uint32_t pk_imad(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 CAL_D uint32_t pk_imadhi(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 CAL_D uint32_t pk_leahi(uint32_t a, uint32_t b, uint32_t c) { return b + (a >> 31) + (c & 0u); }
+CAL_D uint32_t pk_max3(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)__vimax3_s32((int)a, (int)b, (int)c); }
+CAL_D uint32_t pk_max3x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+CAL_D uint32_t pk_addmaxx2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+CAL_D uint32_t pk_shf(uint32_t a, uint32_t b, uint32_t c) { return __funnelshift_r(a, b, 2) + (c & 0u); }
+CAL_D uint32_t pk_lop2i(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("lop3.b32 %0, %1, %2, 0x00030003, 0xf8;" : "=r"(d) : "r"(a), "r"(b)); return d + (c & 0u); }     // two registers + an immediate
+CAL_D uint32_t pk_imad1(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm volatile("mad.lo.u32 %0, %1, 5, %2;" : "=r"(d) : "r"(a), "r"(b)); return d + (c & 0u); }                // register x immediate + register
 #else
 inline uint32_t pk_lop3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
 inline uint32_t pk_imad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
 inline uint32_t pk_imadhi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(((uint64_t)a * b) >> 32) + c; }
 inline uint32_t pk_leahi(uint32_t a, uint32_t b, uint32_t c) { return b + (a >> 31) + (c & 0u); }
+inline uint32_t pk_max3(uint32_t a, uint32_t b, uint32_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+inline uint32_t pk_max3x2(uint32_t a, uint32_t b, uint32_t c) { return pk_max3(a, b, c); }
+inline uint32_t pk_addmaxx2(uint32_t a, uint32_t b, uint32_t c) { return a + b > c ? a + b : c; }
+inline uint32_t pk_shf(uint32_t a, uint32_t b, uint32_t c) { return (a >> 2) | (b << 30) | (c & 0u); }
+inline uint32_t pk_lop2i(uint32_t a, uint32_t b, uint32_t c) { return (a | (b & 0x00030003u)) + (c & 0u); }
+inline uint32_t pk_imad1(uint32_t a, uint32_t b, uint32_t c) { return a * 5u + b + (c & 0u); }
 #endif
 #define CAL_PEAK_ROUND(OP_EVEN, OP_ODD) _Pragma("unroll") for (int k = 0; k < 8; ++k) a[k] = (k & 1) ? OP_ODD(a[k], a[(k + 3) & 7], a[(k + 5) & 7]) : OP_EVEN(a[k], a[(k + 3) & 7], a[(k + 5) & 7]);
 CAL_KERNEL __launch_bounds__(256) k_int_peak(uint32_t* out, int iters, int kind, uint32_t seed) {
@@ -1114,7 +1290,14 @@ CAL_KERNEL __launch_bounds__(256) k_int_peak(uint32_t* out, int iters, int kind,
   else if (kind == 1) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_imad, pk_imad) CAL_PEAK_ROUND(pk_imad, pk_imad) }
   else if (kind == 2) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_lop3, pk_imad) CAL_PEAK_ROUND(pk_imad, pk_lop3) }
   else if (kind == 3) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_imadhi, pk_imadhi) CAL_PEAK_ROUND(pk_imadhi, pk_imadhi) }
-  else                for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_leahi, pk_leahi) CAL_PEAK_ROUND(pk_leahi, pk_leahi) }
+  else if (kind == 4) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_leahi, pk_leahi) CAL_PEAK_ROUND(pk_leahi, pk_leahi) }
+  else if (kind == 5) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_max3, pk_max3) CAL_PEAK_ROUND(pk_max3, pk_max3) }                  // VIMNMX3
+  else if (kind == 6) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_max3x2, pk_max3x2) CAL_PEAK_ROUND(pk_max3x2, pk_max3x2) }          // VIMNMX3.S16x2
+  else if (kind == 7) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_addmaxx2, pk_addmaxx2) CAL_PEAK_ROUND(pk_addmaxx2, pk_addmaxx2) }  // VIADDMNMX.S16x2
+  else if (kind == 8) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_shf, pk_shf) CAL_PEAK_ROUND(pk_shf, pk_shf) }                      // SHF (funnel shift)
+  else if (kind == 9) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_lop2i, pk_imad1) CAL_PEAK_ROUND(pk_imad1, pk_lop2i) }              // LOP3 and IMAD with two register operands each, 1:1
+  else if (kind == 10) for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_max3x2, pk_imad1) CAL_PEAK_ROUND(pk_imad1, pk_max3x2) }           // VIMNMX3.S16x2 and IMAD, 1:1
+  else                for (int it = 0; it < iters; ++it) { CAL_PEAK_ROUND(pk_lop2i, pk_lop2i) CAL_PEAK_ROUND(pk_lop2i, pk_lop2i) }              // kind 11: LOP3 with an immediate
   uint32_t r = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) r ^= a[k];
@@ -1260,7 +1443,7 @@ struct Pipeline {   // tail shared by the tiled and explicit paths: sort -> alig
   const GuideSpec* d_specs; int slots; bool explicit_mode; int banded;   // banded: 0 = wide thresholds, else the largest k_edits of the launch (<= ALIGN_KB)
   const uint32_t* nib; const ContigDev* d_contigs; int n_contigs; int window_size; int step; const ExplicitWindow* d_windows; bool drop_halo;
   KeyLayout key; int rw;                                                   // rw: 32-bit words per hit record of this call
-  bool fast; int64_t nib_words;                                            // fast: every guide of the launch fits align_fast's 64-column window; nib_words: size of `nib`
+  int fast; int64_t nib_words;                                             // fast: 0 = no, 1 = every guide of the launch fits align_fast's 64-column window, 2 = and align_pair's 16-bit scores (align_level); nib_words: size of `nib`
   const DedupLayout* dedup; int32_t max_overlap;                           // dedup != nullptr: removeOverlaps + ReferenceHit.sort over the kept alignments
   DBuf* out_owned;                                                         // plain compaction only: when given, one byte per output record (1 = owned, 0 = halo) goes here
   bool presorted = false;                                                  // the candidate keys are already in (guide, window, strand, column) order
@@ -1273,6 +1456,25 @@ bool fits_align_fast(const GuideSpec& sp, int banded) {
   const int kb = banded > 5 ? 6 : (banded == 5 ? 5 : 4);
   int pam = 0; for (int k = 0; k < sp.n_pams; ++k) pam = std::max<int>(pam, sp.pam_len[k]);
   return !std::getenv("CALITAS_NO_ALIGN_FAST") && sp.lp + kb + sp.g + pam <= 64;
+}
+
+// align_pair<KB> holds 4 * score + tag in 16 bits: see its header for the argument behind the second condition
+bool pair_fits(const GuideSpec& sp, const Scores& sc) {
+  const int32_t match4 = 4 * sc.match, big = 700;
+  const int32_t adds[4] = { match4, 4 * sc.mismatch, 4 * sc.target_gap + TG_UP, 4 * sc.query_gap + TG_LEFT };
+  for (int k = 0; k < 4; ++k) if (adds[k] > big || adds[k] < -big) return false;                    // PAIR_FLOOR + an addend stays inside 16 bits
+  if (match4 <= 0 || (int64_t)match4 * sp.lp + 3 > 32767) return false;
+  return (int64_t)PAIR_FLOOR + 3 + (int64_t)sp.lp * match4 < 4 * (int64_t)sp.min_score;
+}
+// 0: the general kernels; 1: align_fast; 2: align_pair (all guides of the launch of one protospacer length)
+int align_level(const std::vector<GuideSpec>& specs, size_t g0, size_t g1, int banded, const Scores& sc) {
+  if (banded <= 0 || g1 <= g0) return 0;
+  int level = std::getenv("CALITAS_ALIGN_PAIR") ? 2 : 1;        // align_pair is exact but measured slower than align_fast (see its header): opt-in
+  for (size_t g = g0; g < g1; ++g) {
+    if (!fits_align_fast(specs[g], banded)) return 0;
+    if (specs[g].lp != specs[g0].lp || !pair_fits(specs[g], sc)) level = 1;
+  }
+  return level;
 }
 
 // e->out must hold (out_n + more) records; the first out_n are kept
@@ -1304,7 +1506,15 @@ int64_t run_tail(const Pipeline& P, int64_t n_cand, int64_t out_n, size_t projec
   aa.nib = P.nib; aa.contigs = P.d_contigs; aa.n_contigs = P.n_contigs; aa.window_size = P.window_size; aa.step = P.step; aa.windows = P.d_windows;
   aa.recs = e->hits.as<uint32_t>(); aa.rw = rw; aa.ckeys = e->valid.as<CKey>(); aa.key = P.key; aa.nib_last_word = P.nib_words - 1;
   dev::event_record(P.ev_align_b, s);
-  if (P.banded > 0 && P.fast) {
+  aa.match4 = 4 * e->sc.match; aa.mis4 = 4 * e->sc.mismatch; aa.up4 = 4 * e->sc.target_gap + TG_UP; aa.left4 = 4 * e->sc.query_gap + TG_LEFT;
+  if (std::getenv("CALITAS_TRACE")) std::fprintf(stderr, "[calitas trace] align: %lld candidates, banded %d, level %d (2 = align_pair, 1 = align_fast)\n", (long long)n_cand, P.banded, P.fast);
+  if (P.banded > 0 && P.fast == 2) {
+    const unsigned blocks = blocks_for((n_cand + 1) / 2, 128);
+    if (P.banded > 5) { CAL_LAUNCH(k_align_pair6, blocks, 128, 0, s, 1, aa); dev::launch_check("k_align_pair6"); }
+    else if (P.banded == 5) { CAL_LAUNCH(k_align_pair5, blocks, 128, 0, s, 1, aa); dev::launch_check("k_align_pair5"); }
+    else { CAL_LAUNCH(k_align_pair4, blocks, 128, 0, s, 1, aa); dev::launch_check("k_align_pair4"); }
+  }
+  else if (P.banded > 0 && P.fast) {
     if (P.banded > 5) { CAL_LAUNCH(k_align_fast6, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_fast6"); }
     else if (P.banded == 5) { CAL_LAUNCH(k_align_fast5, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_fast5"); }
     else { CAL_LAUNCH(k_align_fast4, blocks_for(n_cand, 128), 128, 0, s, 1, aa); dev::launch_check("k_align_fast4"); }
@@ -1434,12 +1644,12 @@ std::vector<GuideSpec> build_specs(calitas_engine* e, int32_t n_guides, const ca
 
 // explicit-window path shared by align_regions / align_targets
 // Shape of a launch over a set of guides: alignment slots per candidate, which align kernel, record size.
-struct LaunchShape { int slots, banded, rw; bool fast; bool all_columns; /* every guide's threshold admits every column (best mode) */ };
-LaunchShape launch_shape(const std::vector<GuideSpec>& specs, size_t g0, size_t g1, int rw_all) {
-  LaunchShape L{ 1, 1, rw_all, true, g1 > g0 };
+struct LaunchShape { int slots, banded, rw; int fast; bool all_columns; /* every guide's threshold admits every column (best mode) */ };
+LaunchShape launch_shape(const std::vector<GuideSpec>& specs, size_t g0, size_t g1, int rw_all, const Scores& sc) {
+  LaunchShape L{ 1, 1, rw_all, 0, g1 > g0 };
   for (size_t g = g0; g < g1; ++g) { L.slots = std::max(L.slots, specs[g].slots); L.banded = std::max(L.banded, std::max(specs[g].k_edits, specs[g].band_k)); }
   if (L.banded > ALIGN_KB) L.banded = 0;
-  L.fast = L.banded > 0; for (size_t g = g0; g < g1; ++g) L.fast = L.fast && fits_align_fast(specs[g], L.banded);
+  L.fast = align_level(specs, g0, g1, L.banded, sc);
   for (size_t g = g0; g < g1; ++g) L.all_columns = L.all_columns && specs[g].k_edits >= specs[g].lp;
   if (L.banded > 0 || std::getenv("CALITAS_NO_ALL_COLUMNS")) L.all_columns = false;
   return L;
@@ -1503,7 +1713,7 @@ calitas_hitset* run_explicit(calitas_engine* e, const uint32_t* d_nib, int64_t n
   dev::Stream s = e->stream; dev::set_device(e->device);
   e->launches = 0;
   dev::event_record(e->ev[0], s);
-  const LaunchShape L = launch_shape(specs, 0, specs.size(), rec_words_of(specs));
+  const LaunchShape L = launch_shape(specs, 0, specs.size(), rec_words_of(specs), e->sc);
   e->specs.ensure(specs.size() * sizeof(GuideSpec)); dev::h2d(e->specs.p, specs.data(), specs.size() * sizeof(GuideSpec), s);
   e->windows.ensure(windows.size() * sizeof(ExplicitWindow)); dev::h2d(e->windows.p, windows.data(), windows.size() * sizeof(ExplicitWindow), s);
   double ms[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; int64_t counts[8] = { (int64_t)windows.size(), 0, 0, 0, 0, 0, 0, 0 };
@@ -1545,7 +1755,7 @@ int64_t merge_variant_hits(calitas_engine* e, const VariantPlan& vp, const std::
   int64_t n = n_ref;
   if (vs.n_windows > 0) {
     // ---- tasks: every guide against the windows of its class, built on the device for spans of guides that keep a task list under 2^25 entries ------
-    const LaunchShape L = launch_shape(specs, 0, specs.size(), rw);
+    const LaunchShape L = launch_shape(specs, 0, specs.size(), rw, e->sc);
     const int64_t TASK_SPAN = (int64_t)1 << 25;
     std::vector<VarTaskGuide> span; int64_t span_tasks = 0;
     auto flush = [&]() {
@@ -1756,7 +1966,7 @@ void calitas_reference_free(calitas_engine* e, calitas_reference* r) {
 }
 
 // One guide chunk of a search: consecutive guides sharing the raw guide length, hence the window tiling (SearchReference.scala:528-530).
-struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded; bool fast; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; KeyLayout key; DedupLayout dedup; };
+struct SearchChunk { int g0, g1, raw_len, step, slots, scan_slots, banded; int fast; calitas_reference::TileSet* ts; size_t t_begin, n_tiles, smem; int64_t bases; KeyLayout key; DedupLayout dedup; };
 
 static int search_impl(calitas_engine* e, const calitas_reference* ref_c, int32_t n_guides, const calitas_guide* guides, const calitas_limits* limits,
                        int32_t window_size, const char* chrom, int32_t dedup, const VariantPlan* vp, calitas_hitset** out) {
@@ -1797,7 +2007,7 @@ static int search_impl(calitas_engine* e, const calitas_reference* ref_c, int32_
       ch.n_tiles = t_end - ch.t_begin;
       ch.slots = 1; ch.banded = 1; for (int g = g0; g < g1; ++g) { ch.slots = std::max(ch.slots, specs[(size_t)g].slots); ch.banded = std::max(ch.banded, std::max(specs[(size_t)g].k_edits, specs[(size_t)g].band_k)); }
       if (ch.banded > ALIGN_KB) ch.banded = 0;
-      ch.fast = ch.banded > 0; for (int g = g0; g < g1; ++g) ch.fast = ch.fast && fits_align_fast(specs[(size_t)g], ch.banded);
+      ch.fast = align_level(specs, (size_t)g0, (size_t)g1, ch.banded, e->sc);
       const int ng = g1 - g0;
       ch.smem = scan_smem_bytes(ng, ch.ts->tile_windows, window_size, ch.step);
       if (ch.smem > (size_t)SCAN_SMEM_LIMIT) throw LimitExceeded("window size too large for the shared-memory tile");
@@ -2186,7 +2396,7 @@ int calitas_align_targets(calitas_engine* e, int32_t n_guides, const calitas_gui
 
 int calitas_microbench_int(calitas_engine* e, int32_t kind, double* tera_ops_per_s) {
   return guarded([&]() -> int {
-    if (!e || !tera_ops_per_s || kind < 0 || kind > 4) throw InvalidArgument("bad microbench arguments");
+    if (!e || !tera_ops_per_s || kind < 0 || kind > 11) throw InvalidArgument("bad microbench arguments");
     dev::set_device(e->device); dev::Stream s = e->stream;
     const int iters = 4096; const unsigned grid = (unsigned)dev::sm_count(e->device) * 16, block = 256;
     e->tmp.ensure((size_t)grid * block * 4);

@@ -68,7 +68,10 @@ def random_case(rng):
                                     max_overlap=int(rng.choice([0, 5, 10, 100])), target_offset=int(rng.integers(0, 1000)))
 
 
-def test_align_random_cases(eng):
+@pytest.mark.parametrize("paired", [False, True])
+def test_align_random_cases(eng, monkeypatch, paired):
+    if paired:
+        monkeypatch.setenv("CALITAS_ALIGN_PAIR", "1")            # the opt-in two-candidates-per-thread aligner (align_pair) on the same cases
     rng = np.random.default_rng(7)
     n = 400 if eng.name == "hostsim" else 150
     for k in range(n):
@@ -138,6 +141,22 @@ def test_search_reference_variants_of_the_call(eng, small_genome, guide, aux, kw
     g, contigs = small_genome
     exp = _lines(pyoracle.search_reference(contigs, guide, aux_pams=aux, raw=True, **kw))
     got = _lines(eng.search_reference(contigs, guide, aux_pams=aux, raw=True, **kw))
+    assert got == exp
+
+
+@pytest.mark.parametrize("guide,aux,kw", [
+    ("CTTGCCCCACAGGGCAGTAAngg", ["nag"], dict(d=6, g=2, p=1)),
+    ("tttvCTTGCCCCACAGGGCAGTAA", [], dict(d=5, g=1, p=1)),
+    ("CTTGCCCCACAGGGCAGTAAnrg", [], dict(d=4)),
+])
+def test_search_reference_with_the_paired_16_bit_aligner(eng, small_genome, monkeypatch, guide, aux, kw):
+    """CALITAS_ALIGN_PAIR=1: align_pair (two candidates per thread, 16-bit packed scores) instead of align_fast.  Not the default (slower on the B200),
+    kept exact: same rows as the oracle, odd and even candidate counts, both strands, 5' and 3' PAMs, band widths 4 / 5 / 6."""
+    monkeypatch.setenv("CALITAS_ALIGN_PAIR", "1")
+    g, contigs = small_genome
+    exp = _lines(pyoracle.search_reference(contigs, guide, aux_pams=aux, raw=True, **kw))
+    got = _lines(eng.search_reference(contigs, guide, aux_pams=aux, raw=True, **kw))
+    assert len(exp) > 10
     assert got == exp
 
 
