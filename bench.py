@@ -28,8 +28,8 @@ sys.path.insert(0, ROOT)
 # shipped library, see DESIGN.md "k_scan_tiled"; per 8 columns x 2 guides: 112 LOP3 + 32 LEA.HI + 8 VIMNMX3 | 56 IMAD.IADD | 16 LDS + 8 LDS.U8):
 # ALU pipe 7 LOP3 + 2 LEA.HI + 0.5 VIMNMX3; FMA pipe 3.5 IMAD.IADD; LSU 1 LDS + 0.5 LDS.U8.
 ALU_OPS_PER_COLUMN = 9.5
-NCU_SCAN = {"dram_over_algorithmic": 406.4 / 386.2, "alu_pipe_pct": 88.6, "issue_active_pct": 71.9, "fma_pipe_pct": 17.9,
-            "source": "profiles/r01f_summary.txt (ncu --set full of k_scan_tiled, d=5); d=6: profiles/r02a_summary.txt (85.9 / 72.8 / 17.6)"}
+NCU_SCAN = {"dram_over_algorithmic": (387.4 + 17.4) / 386.2, "alu_pipe_pct": 89.0, "issue_active_pct": 71.9, "fma_pipe_pct": 17.7,
+            "source": "profiles/r02_1gpu_default16_summary.txt (ncu --set full of k_scan_tiled, d=5, 56 registers); d=6: profiles/r02_1gpu_config4_summary.txt (86.3 / 72.9 / 17.4)"}
 REF_OPS_PER_BP_GUIDE = 240   # 2 strands x 20 rows x 6 int32 ops of the reference's recurrence
 
 # BASELINE.json configs; "default" is the north_star target (100 guides, defaults) the headline metric is quoted on
@@ -492,7 +492,7 @@ def run_search(args, job):
             "clocks": clocks,
             "roofline": {"kernel": "k_scan_tiled", "bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                          "traffic": alg_bytes * NCU_SCAN["dram_over_algorithmic"], "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                         "(profiles/r01f_summary.txt: 388.2 + 18.1 = 406.4 MB for 386.2 MB algorithmic), scaled to this launch's algorithmic bytes", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                         "(profiles/r02_1gpu_default16_summary.txt: 387.4 + 17.4 = 404.8 MB for 386.2 MB algorithmic), scaled to this launch's algorithmic bytes", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                          "note": "streaming read of the 4-bit packed shard once per launch; the kernel is integer-ALU-bound (see roofline_int), so the HBM fraction is small by design",
                          "avg_launch_ms": scan_launch_ms, "launches_per_step": launches, "share_of_step": st["ms_scan"] / st["ms_total"]},
             "roofline_int": {"kernel": "k_scan_tiled", "bound": "int_alu_pipe", "achieved": int_achieved, "peak": int_peaks["alu_lop3"], "unit": "Tiop/s (ALU-pipe thread instructions)",
