@@ -11,7 +11,7 @@ import pytest
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import pyoracle
 from calitas_b200 import synth
-from calitas_b200._capi import CalitasError, Engine, Limits
+from calitas_b200._capi import DEFAULT_COSTS, CalitasError, Engine, Limits
 
 ENGINES = ["hostsim", pytest.param("gpu", marks=pytest.mark.gpu)]
 
@@ -110,3 +110,35 @@ def test_per_shard_dedup_with_nonpositive_max_overlap_is_refused(eng):
     assert len(e.search(whole, [synth.BASELINE_GUIDE], Limits(5, 1, 3, -1, 0), dedup=True)) >= 1
     whole.free()
     e.close()
+
+
+def test_align_targets_batch_equals_single_calls(eng):
+    """calitas_align_targets gathers the tasks' bases on several host threads into one staging buffer and packs them on the device: a batch of ragged
+    targets (1 base to a few hundred, two guides, non-zero offsets) must give, task by task, the records of the single-task calls."""
+    rng = np.random.default_rng(23)
+    e = eng.t.engine(DEFAULT_COSTS)
+    guides = ["CTTGCCCCACAGGGCAGTAAnrg", "tttvGACCCCCTCCACCCCGCCTC"]
+    lim = Limits(4, 1, 2, -1, 10)
+    site = "CTTGCCCCACAGGGCAGTAATGG"
+    tasks = []
+    for i in range(3000):
+        n = int(rng.integers(1, 300))
+        t = "".join(rng.choice(list("ACGT"), size=n))
+        if n > 40 and rng.random() < 0.5:
+            p = int(rng.integers(0, n - len(site)))
+            s = list(site); s[int(rng.integers(0, 20))] = "A"
+            t = t[:p] + "".join(s) + t[p + len(site):]
+        tasks.append((int(rng.integers(0, 2)), t, int(rng.integers(0, 5000))))
+    batch = e.align_targets(guides, tasks, lim).records()
+    assert batch.size > 500
+    by_task = {}
+    for r in batch:
+        by_task.setdefault(int(r["task_idx"]), []).append(r)
+    for i in list(rng.choice(len(tasks), size=60, replace=False)) + [0, len(tasks) - 1]:
+        single = e.align_targets(guides, [tasks[int(i)]], lim).records()
+        got = by_task.get(int(i), [])
+        assert len(got) == single.size, i
+        for a, b in zip(got, single):
+            for f in batch.dtype.names:
+                if f != "task_idx":
+                    assert np.array_equal(a[f], b[f]), (i, f)
