@@ -31,7 +31,7 @@ Q="--scale 0.25 $D16"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_scan_tiled -s 1 -c 1 -o gpurun_out/${R}_scan5 python bench.py $Q > gpurun_out/${R}_ncu1.log 2>&1; echo rc=$?
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_align_fast5 -s 1 -c 1 -o gpurun_out/${R}_align5 python bench.py $Q > gpurun_out/${R}_ncu2.log 2>&1; echo rc=$?
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_align_fast6 -s 1 -c 1 -o gpurun_out/${R}_align6 python bench.py --workload config4 $Q > gpurun_out/${R}_ncu3.log 2>&1; echo rc=$?
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_canonE -s 1 -c 1 -o gpurun_out/${R}_canon6 python bench.py --workload config4 $Q > gpurun_out/${R}_ncu4.log 2>&1; echo rc=$?
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:^k_canon$ -s 1 -c 1 -o gpurun_out/${R}_canon6 python bench.py --workload config4 $Q > gpurun_out/${R}_ncu4.log 2>&1; echo rc=$?
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_scan_tiled -s 1 -c 1 -o gpurun_out/${R}_scan6 python bench.py --workload config4 $Q > gpurun_out/${R}_ncu5.log 2>&1; echo rc=$?
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_align_group_warp -c 1 -o gpurun_out/${R}_groupwarp python bench.py --workload config2 --tasks 200000 --scale 0.1 --steps 1 --warmup 0 $NC > gpurun_out/${R}_ncu6.log 2>&1; echo rc=$?
 ls -la gpurun_out/${R}_* | wc -l
