@@ -281,28 +281,53 @@ struct ScanExplicitArgs {
   const uint32_t* nib; const ExplicitWindow* windows; int64_t n_windows; const GuideSpec* specs;
   uint64_t* cand; unsigned long long* cand_count; unsigned long long cand_cap; KeyLayout key;
 };
-struct GlobalWords {   // word accessor over global memory with nibble base offset
-  const uint32_t* nib; int64_t base;
-  CAL_D uint32_t operator[](int32_t w) const { return __ldg(nib + base + w); }
-};
-template <class Words, class Emit>
-CAL_D void scan_range_generic(const Words& words, int32_t rs, int32_t re, int dir, const uint32_t* peq, int lp, int k_edits, const Emit& emit) {
+// One window in one direction, word by word: a packed word is loaded once and its codes are taken from the low (left to right) or the high end (right to
+// left: DIR 1 scans the reverse complement with the complemented tables), so a column costs a mask/shift pair instead of an index computation and a load.
+CAL_D void scan_words(const uint32_t* nib, int64_t nib_start, int32_t len, int dir, const uint32_t* peq, int lp, int k_edits, const Emitter& emit) {
   MyersState st; myers_init(st, lp);
-  if (dir == 0) { for (int32_t r = rs; r < re; ++r) { uint32_t c = (words[r >> 3] >> ((r & 7) * 4)) & 15u; myers_step(st, peq[c]); if (st.score <= k_edits) emit(r - rs + 1); } }
-  else { for (int32_t r = re - 1; r >= rs; --r) { uint32_t c = (words[r >> 3] >> ((r & 7) * 4)) & 15u; myers_step(st, peq[c]); if (st.score <= k_edits) emit(re - r); } }
+  int32_t col = 1, left = len;
+  if (dir == 0) {
+    int64_t wi = nib_start >> 3; int k = (int)(nib_start & 7);
+    uint32_t word = __ldg(nib + wi) >> (4 * k);
+    while (left > 0) {
+      int n = 8 - k; if (n > left) n = left;
+      for (int q = 0; q < n; ++q) { const uint32_t c = word & 15u; word >>= 4; myers_step(st, peq[c]); if (st.score <= k_edits) emit(col); ++col; }
+      left -= n; k = 0; ++wi; if (left > 0) word = __ldg(nib + wi);
+    }
+  } else {
+    const int64_t last = nib_start + len - 1;
+    int64_t wi = last >> 3; int k = (int)(last & 7);
+    uint32_t word = __ldg(nib + wi) << (4 * (7 - k));
+    while (left > 0) {
+      int n = k + 1; if (n > left) n = left;
+      for (int q = 0; q < n; ++q) { const uint32_t c = word >> 28; word <<= 4; myers_step(st, peq[c]); if (st.score <= k_edits) emit(col); ++col; }
+      left -= n; k = 7; --wi; if (left > 0) word = __ldg(nib + wi);
+    }
+  }
 }
+// thread = (window, direction); a block is 128 consecutive windows of one direction.  Window lists are guide-major (variant tasks) or sorted by guide
+// in practice, so the mask tables of the block's first window's guide are staged in shared memory; a window of another guide reads its tables from global memory.
 CAL_KERNEL __launch_bounds__(128) k_scan_explicit(ScanExplicitArgs a) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= 2 * a.n_windows) return;
-  const int dir = t >= a.n_windows ? 1 : 0;
-  const int64_t w = dir ? t - a.n_windows : t;
-  const ExplicitWindow ew = a.windows[w];
-  if (ew.len <= 0) return;
-  const GuideSpec& s = a.specs[ew.guide_idx];
-  GlobalWords words{ a.nib, ew.nib_start >> 3 };
-  const int32_t rs = (int32_t)(ew.nib_start & 7), re = rs + ew.len;
-  Emitter emit{ a.cand, a.cand_count, a.cand_cap, make_key(a.key, 0, (uint32_t)w, (uint32_t)(dir ^ s.five_prime), 0) };
-  scan_range_generic(words, rs, re, dir, s.peq[dir], s.lp, s.k_edits, emit);
+  CAL_SHARED_DYN(uint32_t, smem);                      // 32 words of mask tables (direction, code) + the guide they belong to
+  const int64_t tb = (int64_t)blockIdx.x * blockDim.x, t = tb + threadIdx.x;
+  CAL_PHASE(0) {
+    const int64_t wb = tb >= a.n_windows ? tb - a.n_windows : tb;
+    const int32_t g0 = a.windows[wb].guide_idx;
+    if (threadIdx.x < 32) smem[threadIdx.x] = a.specs[g0].peq[threadIdx.x >> 4][threadIdx.x & 15];
+    if (threadIdx.x == 32) smem[32] = (uint32_t)g0;
+  }
+  __syncthreads();
+  CAL_PHASE(1) {
+    if (t >= 2 * a.n_windows) return;
+    const int dir = t >= a.n_windows ? 1 : 0;
+    const int64_t w = dir ? t - a.n_windows : t;
+    const ExplicitWindow ew = a.windows[w];
+    if (ew.len <= 0) return;
+    const GuideSpec& s = a.specs[ew.guide_idx];
+    Emitter emit{ a.cand, a.cand_count, a.cand_cap, make_key(a.key, 0, (uint32_t)w, (uint32_t)(dir ^ s.five_prime), 0) };
+    if (ew.guide_idx == (int32_t)smem[32]) scan_words(a.nib, ew.nib_start, ew.len, dir, smem + 16 * dir, s.lp, s.k_edits, emit);
+    else scan_words(a.nib, ew.nib_start, ew.len, dir, s.peq[dir], s.lp, s.k_edits, emit);
+  }
 }
 
 // Best mode (alignBest / alignToRefBest: d = protospacer length) makes EVERY column of both strands a candidate -- the semi-global edit distance of an
@@ -1687,7 +1712,7 @@ void explicit_core(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, 
       dev::zero(e->d_count, 8, s);
       ScanExplicitArgs sa{ d_nib, e->windows.as<ExplicitWindow>() + w0, nw, e->specs.as<GuideSpec>(), e->cand.as<uint64_t>(), e->d_count, (unsigned long long)e->cand_cap_hint, key };
       dev::event_record(e->ev[4], s);
-      CAL_LAUNCH(k_scan_explicit, blocks_for(2 * nw, 128), 128, 0, s, 1, sa); dev::launch_check("k_scan_explicit"); ++e->launches;
+      CAL_LAUNCH(k_scan_explicit, blocks_for(2 * nw, 128), 128, 256, s, 2, sa); dev::launch_check("k_scan_explicit"); ++e->launches;
       dev::event_record(e->ev[5], s);
       CAL_LAUNCH(k_publish_u64, 1, 1, 0, s, 1, e->d_count, e->h_count_dev); dev::launch_check("k_publish_u64"); dev::stream_sync(s);
       n_cand = *(volatile unsigned long long*)e->h_count;
