@@ -1687,7 +1687,7 @@ void explicit_core(calitas_engine* e, const uint32_t* d_nib, int64_t nib_words, 
                    int64_t& n_out, double ms[8], int64_t counts[8]) {
   dev::Stream s = e->stream;
   // batches bound the candidate buffer: in best mode every column of every window is a candidate
-  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_windows, L.banded ? (1 << 22) : (1 << 18)));
+  const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(n_windows, L.banded ? (1 << 25) : (1 << 18)));
   const KeyLayout key = make_key_layout(max_len, (uint64_t)batch, 1);       // window ids are relative to the batch; the guide comes from the window
   for (int64_t w0 = 0; w0 < n_windows; w0 += batch) {
     const int64_t nw = std::min(batch, n_windows - w0);
